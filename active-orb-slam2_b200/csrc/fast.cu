@@ -1,0 +1,202 @@
+// Per-cell FAST-9/16 with 3x3 non-max suppression: replaces the cv::FAST loop of
+// ORBextractor::ComputeKeyPointsOctTree (reference src/ORBextractor.cc:765-829; OpenCV fast.cpp/fast_score.cpp).
+//
+// One CTA = a run of up to ORBX_FAST_CELLS cells of one cell-row of one level of one frame.  The tile
+// (cells + 3-pixel ring) is staged in shared memory once; scores, suppression and the reference's
+// "no corner at iniThFAST -> retry the cell at minThFAST" rule (ORBextractor.cc:809-815) all run from there.
+//   score(p)  = max over the 16 arcs of 9 contiguous ring pixels of min|I(ring)-I(p)| (one sign) - 1
+//   corner    iff score >= threshold;  kept iff score is strictly greater than its 8 neighbours, where
+//               neighbours outside the cell's detection region [3,cw-3)x[3,ch-3) count as 0.
+// Survivors are appended to the (frame, level) candidate list as x | y<<12 | score<<24 in the coordinates of
+// ORBextractor.cc:822-823 (relative to minBorderX/Y).  Order inside the list is unspecified; the quadtree
+// kernel never depends on it.
+#include "orbx_internal.cuh"
+
+#define FAST_THREADS 256
+
+// The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
+// (0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
+
+// score of the pixel at p (row pitch tp) or 0 if it is not a corner at `th`
+__device__ __forceinline__ int fast_score(const uint8_t *p, int tp, int th) {
+    const int v = p[0];
+    // compass test: a 9-arc contains two adjacent compass pixels (0,4,8,12) of the same polarity
+    const int c0 = p[3 * tp], c4 = p[3], c8 = p[-3 * tp], c12 = p[-3];
+    const int hi = v + th, lo = v - th;
+    const unsigned br = (c0 > hi) | ((c4 > hi) << 1) | ((c8 > hi) << 2) | ((c12 > hi) << 3);
+    const unsigned dk = (c0 < lo) | ((c4 < lo) << 1) | ((c8 < lo) << 2) | ((c12 < lo) << 3);
+    const unsigned brr = ((br << 1) | (br >> 3)) & 0xf, dkr = ((dk << 1) | (dk >> 3)) & 0xf;
+    if (((br & brr) | (dk & dkr)) == 0) return 0;
+    int r[16];
+    r[0] = c0; r[4] = c4; r[8] = c8; r[12] = c12;
+    r[1] = p[3 * tp + 1]; r[2] = p[2 * tp + 2]; r[3] = p[tp + 3];
+    r[5] = p[-tp + 3]; r[6] = p[-2 * tp + 2]; r[7] = p[-3 * tp + 1];
+    r[9] = p[-3 * tp - 1]; r[10] = p[-2 * tp - 2]; r[11] = p[-tp - 3];
+    r[13] = p[tp - 3]; r[14] = p[2 * tp - 2]; r[15] = p[3 * tp - 1];
+    // sliding min / max over windows of 9 on the circular ring: 2, 4, 8 by doubling, then +1
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn2[k] = min(r[k], r[(k + 1) & 15]);
+        mx2[k] = max(r[k], r[(k + 1) & 15]);
+    }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    }
+    int lo_of_max = 255, hi_of_min = 0;  // min over arcs of the arc maximum, max over arcs of the arc minimum
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), r[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), r[(k + 8) & 15]);
+        hi_of_min = max(hi_of_min, mn9);
+        lo_of_max = min(lo_of_max, mx9);
+    }
+    // darker ring: min(v - ring) = v - arc max; brighter ring: min(ring - v) = arc min - v
+    const int best = max(v - lo_of_max, hi_of_min - v);
+    return best > th ? best - 1 : 0;
+}
+
+struct FastShared {
+    int cnt[ORBX_FAST_CELLS];     // survivors per cell in the current pass
+    int empty[ORBX_FAST_CELLS];
+    int n_out;                    // entries in the output list
+    int any_empty;
+    int base;                     // reserved start in the global candidate list
+};
+
+// dynamic smem layout: [tile bytes th x tp][score bytes th x tp][out words]
+__global__ void __launch_bounds__(FAST_THREADS)
+k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv,
+       const OrbxFastChunk *__restrict__ chunks, uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand,
+       int *__restrict__ status, int ini_th, int min_th, int tp_max, int th_max) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ FastShared sh;
+    const OrbxFastChunk ck = chunks[blockIdx.x];
+    const int frame = blockIdx.y;
+    const OrbxLevel &L = lv[ck.level];
+    const int tw = ck.tw, th = ck.th;
+    const int tid = threadIdx.x;
+
+    // ---- stage the tile: 32-bit loads from the padded level buffer --------------------------------
+    const int gx0 = ORBX_EDGE + ck.x0;                // padded-buffer column of the tile origin
+    const int shift = gx0 & 3;
+    const int words = (shift + tw + 3) >> 2;
+    const int tp = tp_max;                             // smem row pitch (bytes, multiple of 4)
+    uint8_t *tile = smem;
+    uint8_t *score = smem + (size_t)tp * th_max;
+    uint32_t *out = reinterpret_cast<uint32_t *>(score + (size_t)tp * th_max);
+    const uint8_t *src = pyr + (size_t)frame * pyr_frame + L.off + (size_t)(ORBX_EDGE + ck.y0) * L.pitch + (gx0 - shift);
+    for (int i = tid; i < words * th; i += FAST_THREADS) {
+        const int r = i / words, c = i - r * words;
+        reinterpret_cast<uint32_t *>(tile + (size_t)r * tp)[c] =
+            __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + c);
+    }
+    for (int i = tid; i < (tp * th) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
+    if (tid < ORBX_FAST_CELLS) { sh.cnt[tid] = 0; sh.empty[tid] = 1; }
+    if (tid == 0) { sh.n_out = 0; sh.any_empty = 0; }
+    __syncthreads();
+
+    const uint8_t *t0 = tile + shift;                  // tile pixel (x,y) = t0[y*tp + x]
+    uint8_t *s0 = score + shift;
+    const int vw = tw - 6, vh = th - 6;                // detection region
+    const int npx = vw * vh;
+    const int wcell = ck.wcell;
+
+    for (int pass = 0; pass < 2; pass++) {
+        const int thr = pass == 0 ? ini_th : min_th;
+        // scores
+        for (int i = tid; i < npx; i += FAST_THREADS) {
+            const int y = i / vw, x = i - y * vw;     // detection-region coordinates
+            if (pass == 1) {
+                if (!sh.empty[x / wcell]) continue;    // only the cells that found nothing at iniThFAST
+            }
+            s0[(y + 3) * tp + x + 3] = (uint8_t)fast_score(t0 + (y + 3) * tp + x + 3, tp, thr);
+        }
+        __syncthreads();
+        // 3x3 non-max suppression inside the cell's detection region
+        for (int i = tid; i < npx; i += FAST_THREADS) {
+            const int y = i / vw, x = i - y * vw;
+            const int cell = x / wcell;
+            if (pass == 1 && !sh.empty[cell]) continue;
+            const uint8_t *sp = s0 + (y + 3) * tp + x + 3;
+            const int s = sp[0];
+            if (s == 0) continue;
+            const int cx0 = cell * wcell;                                   // first detection column of the cell
+            const int cx1 = cell == ck.ncells - 1 ? vw : cx0 + wcell;      // one past the last
+            const bool l = x > cx0, r = x + 1 < cx1, u = y > 0, d = y + 1 < vh;
+            bool keep = true;
+            if (l) keep = keep && s > sp[-1];
+            if (r) keep = keep && s > sp[1];
+            if (u) {
+                keep = keep && s > sp[-tp];
+                if (l) keep = keep && s > sp[-tp - 1];
+                if (r) keep = keep && s > sp[-tp + 1];
+            }
+            if (d) {
+                keep = keep && s > sp[tp];
+                if (l) keep = keep && s > sp[tp - 1];
+                if (r) keep = keep && s > sp[tp + 1];
+            }
+            if (keep) {
+                atomicAdd(&sh.cnt[cell], 1);
+                const int o = atomicAdd(&sh.n_out, 1);
+                // coordinates relative to minBorder: tile origin x0-16 plus the pixel's tile position
+                out[o] = (uint32_t)(ck.x0 - ORBX_BORDER + x + 3) | ((uint32_t)(ck.y0 - ORBX_BORDER + y + 3) << 12) |
+                         ((uint32_t)s << 24);
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (tid < ck.ncells) {
+                const int em = sh.cnt[tid] == 0;
+                sh.empty[tid] = em;
+                if (em) sh.any_empty = 1;
+            }
+            __syncthreads();
+            if (!sh.any_empty) break;
+        }
+    }
+
+    // ---- append to the (frame, level) candidate list ------------------------------------------------
+    const int n_out = sh.n_out;
+    if (n_out == 0) return;
+    if (tid == 0) sh.base = atomicAdd(&ncand[frame * ORBX_MAX_LEVELS + ck.level], n_out);
+    __syncthreads();
+    const int base = sh.base;
+    uint32_t *dst = cand + (size_t)frame * cand_frame + L.cand_off;
+    for (int i = tid; i < n_out; i += FAST_THREADS) {
+        if (base + i < L.cand_cap) dst[base + i] = out[i];
+        else atomicOr(&status[frame], ORBX_ST_CAND_OVERFLOW);
+    }
+}
+
+// tile + score planes, then the survivor list: at most one survivor per 2x2 block of a cell's detection region
+size_t orbx_fast_smem_bytes(int tp_max, int th_max) {
+    const int out_words = (tp_max / 2 + ORBX_FAST_CELLS + 2) * (th_max / 2 + 2);
+    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * out_words;
+}
+
+orbx_status orbx_launch_fast(orbx_extractor *e, int batch, cudaStream_t s) {
+    ORBX_CUDA(cudaMemsetAsync(e->d_ncand, 0, sizeof(int) * ORBX_MAX_LEVELS * batch, s));
+    if (e->n_chunks == 0) return ORBX_OK;
+    const int tp_max = e->fast_tp, th_max = e->fast_th;
+    const size_t smem = orbx_fast_smem_bytes(tp_max, th_max);
+    dim3 grid(e->n_chunks, batch);
+    k_fast<<<grid, FAST_THREADS, smem, s>>>(e->d_pyr, e->pyr_frame_cap, e->d_lv, e->d_chunks, e->d_cand, e->cand_frame_cap,
+                                            e->d_ncand, e->d_status, e->ini_th, e->min_th, tp_max, th_max);
+    e->last_launches++;
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+orbx_status orbx_fast_init(size_t smem_bytes) {
+    if (smem_bytes > 227 * 1024) {
+        orbx_set_error("FAST tile needs %zu bytes of shared memory", smem_bytes);
+        return ORBX_ERR_UNSUPPORTED;
+    }
+    ORBX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    return ORBX_OK;
+}

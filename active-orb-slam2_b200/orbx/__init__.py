@@ -1,1 +1,1 @@
-"""orbx — host-side Python harness over the C-ABI library (include/orbx.h)."""
+"""orbx: B200-native ORB front-end of Active-ORB-SLAM2 (host-side mirror of the reference's class surface)."""

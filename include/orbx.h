@@ -1,0 +1,113 @@
+/* orbx — C ABI of the B200-native hot path of Active-ORB-SLAM2 (sm_100a CUDA behind plain C).
+ *
+ * The reference (XinkeAE/Active-ORB-SLAM2) has no FFI layer: its "operator API" for this path is three
+ * C++ class surfaces.  Each entry point below names the reference interface it replaces;
+ * active-orb-slam2_b200/adapter/ re-creates those C++ classes on top of this ABI, and INTEGRATION.md
+ * shows the binding a maintainer adds.
+ *
+ * Conventions: POD only; every function returns orbx_status (0 = OK, negative = error) and never throws;
+ * handles are opaque, independent, and NOT re-entrant (like ORB_SLAM2::ORBextractor, which mutates
+ * mvImagePyramid): use one handle per host thread / camera.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  "_host" entry points take host pointers and are synchronous;
+ * "_device" entry points take device pointers and only enqueue work on `stream`.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int orbx_status;
+enum {
+    ORBX_OK = 0,
+    ORBX_ERR_INVALID = -1,     /* bad argument */
+    ORBX_ERR_CUDA = -2,        /* CUDA runtime error; orbx_last_error() has the text */
+    ORBX_ERR_NO_DEVICE = -3,   /* no CUDA device / not an sm_100 part */
+    ORBX_ERR_CAPACITY = -4,    /* input larger than the handle was created for */
+    ORBX_ERR_UNSUPPORTED = -5, /* shape the reference itself cannot process (e.g. nIni == 0) */
+    ORBX_ERR_NOMEM = -6,
+    ORBX_ERR_ABORTED = -7      /* stop flag was raised (LocalBA) */
+};
+
+const char *orbx_last_error(void); /* thread-local text of the last failure */
+int orbx_version(void);
+
+/* ---- cv::KeyPoint, 28 bytes (what ORBextractor::operator() fills, ORBextractor.cc:1043) ------------- */
+typedef struct {
+    float x, y;     /* pt, level-0 pixel coordinates */
+    float size;     /* 31 * scale[octave], truncated to int (ORBextractor.cc:837) */
+    float angle;    /* degrees, cv::fastAtan2 of the intensity centroid */
+    float response; /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* -1 */
+} orbx_keypoint;
+
+/* =====================================================================================================
+ * ORBextractor  (reference include/ORBextractor.h:45-111, src/ORBextractor.cc)
+ * ===================================================================================================== */
+typedef struct orbx_extractor orbx_extractor;
+
+/* replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (ORBextractor.cc:410).  max_width/max_height/max_batch size the device buffers once. */
+orbx_status orbx_extractor_create(orbx_extractor **out, int nfeatures, float scale_factor, int nlevels,
+                                  int ini_th_fast, int min_th_fast, int max_width, int max_height,
+                                  int max_batch, int device);
+void orbx_extractor_destroy(orbx_extractor *e);
+
+/* keypoint capacity of ONE frame (sum over levels of quota + slack; DistributeOctTree may return a few
+ * more than the quota, ORBextractor.cc:663).  Output arrays are [batch][capacity]. */
+int orbx_extractor_capacity(const orbx_extractor *e);
+
+/* replaces GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (ORBextractor.h:62-82); any pointer may be NULL; arrays of nlevels. */
+orbx_status orbx_extractor_tables(const orbx_extractor *e, float *scale, float *inv_scale, float *sigma2,
+                                  float *inv_sigma2, int32_t *features_per_level);
+
+/* replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (ORBextractor.cc:1043) for
+ * `batch` independent 8-bit single-channel frames of identical size.
+ *   images[b]   host pointer to frame b, `stride` bytes between rows
+ *   kps         host, [batch][capacity]        desc  host, [batch][capacity][32]
+ *   counts      host, [batch]  number of keypoints of frame b (level-major order like the reference)
+ * An empty image (width or height 0) yields counts 0 and ORBX_OK, like the reference's silent return. */
+orbx_status orbx_extractor_run_host(orbx_extractor *e, const uint8_t *const *images, int batch, int width,
+                                    int height, int stride, orbx_keypoint *kps, uint8_t *desc,
+                                    int32_t *counts);
+
+/* same, device-resident: d_images holds `batch` frames `frame_pitch` bytes apart; outputs are device
+ * pointers with the layout above.  Only enqueues on `stream`. */
+orbx_status orbx_extractor_run_device(orbx_extractor *e, const uint8_t *d_images, size_t frame_pitch,
+                                      int batch, int width, int height, int stride, orbx_keypoint *d_kps,
+                                      uint8_t *d_desc, int32_t *d_counts, void *stream);
+
+/* replaces the public member mvImagePyramid (ORBextractor.h:85; read by Frame::ComputeStereoMatches,
+ * Frame.cc:502,592,609): geometry of level `level` of the last run, and a device pointer to the first
+ * INTERIOR pixel of frame `batch_idx` (19-pixel REFLECT_101 pad around it, like the reference). */
+orbx_status orbx_extractor_pyramid(const orbx_extractor *e, int batch_idx, int level, const uint8_t **d_ptr,
+                                   int *width, int *height, int *pitch);
+/* copies that level (interior only, or with the pad when with_border != 0) to host memory, rows `dst_stride` apart */
+orbx_status orbx_extractor_pyramid_host(const orbx_extractor *e, int batch_idx, int level, int with_border,
+                                        uint8_t *dst, int dst_stride);
+
+/* stage access for parity tests: FAST candidates of one level before DistributeOctTree, as packed words
+ * (x | y<<12 | score<<24, coordinates relative to the 16-pixel border like ORBextractor.cc:822-823);
+ * order is unspecified.  Returns the count through *n (may exceed cap; only cap are copied). */
+orbx_status orbx_extractor_candidates_host(const orbx_extractor *e, int batch_idx, int level, uint32_t *dst,
+                                           int cap, int *n);
+
+/* same kind of stage access: the keypoints DistributeOctTree kept for one level, in the reference's list
+ * order (ORBextractor.cc:749-768), packed as above; and the 7x7-blurred copy of a level (ORBextractor.cc:1086) */
+orbx_status orbx_extractor_level_keypoints_host(const orbx_extractor *e, int batch_idx, int level, uint32_t *dst,
+                                                int cap, int *n);
+orbx_status orbx_extractor_blurred_host(const orbx_extractor *e, int batch_idx, int level, uint8_t *dst,
+                                        int dst_stride);
+
+/* number of kernels launched by the last run (bench.py reports it as gpu_launches) */
+int orbx_extractor_last_launches(const orbx_extractor *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -346,10 +346,13 @@ void orbo_extractor_tables(const orbo_extractor *e, float *scale, float *inv_sca
     if (umax16) for (int v = 0; v <= HALF_PATCH; v++) umax16[v] = e->umax[v];
 }
 
-/* DistributeOctTree stops once the node list holds >= quota nodes; one DivideNode adds at most 3 */
+/* DistributeOctTree stops once the node list holds >= quota nodes; one DivideNode adds at most 3.  The
+ * first pass always runs, so a level can also return up to 4*nIni nodes even when its quota is smaller;
+ * nIni <= 16 is enforced in orbo_extract. */
+#define NINI_MAX 16
 int orbo_extractor_capacity(const orbo_extractor *e) {
     int c = 0;
-    for (int l = 0; l < e->nlevels; l++) c += e->quota[l] + 3;
+    for (int l = 0; l < e->nlevels; l++) c += e->quota[l] + 3 > 4 * NINI_MAX ? e->quota[l] + 3 : 4 * NINI_MAX;
     return c;
 }
 
@@ -649,6 +652,7 @@ int orbo_extract(orbo_extractor *e, const uint8_t *img, int w, int h, int stride
         const int minBX = EDGE_THRESHOLD - 3, minBY = minBX;
         const int maxBX = e->lw[l] - EDGE_THRESHOLD + 3, maxBY = e->lh[l] - EDGE_THRESHOLD + 3;
         level_off[l] = total;
+        if ((int)roundf((float)(maxBX - minBX) / (maxBY - minBY)) > NINI_MAX) { free(tmp); return -3; }
         int n = distribute_octree(e->cand[l], e->ncand[l], minBX, maxBX, minBY, maxBY, e->quota[l], tmp + total);
         if (n < 0) { free(tmp); return -3; }
         const int scaledPatch = (int)(PATCH_SIZE * e->scale[l]);
@@ -695,6 +699,12 @@ int orbo_extract(orbo_extractor *e, const uint8_t *img, int w, int h, int stride
     memcpy(kps, tmp, sizeof(orbo_keypoint) * total);
     free(tmp);
     return total;
+}
+
+/* test hook: DistributeOctTree on an arbitrary candidate list (coordinates relative to minX/minY) */
+int orbo_distribute(const orbo_keypoint *K, int nK, int minX, int maxX, int minY, int maxY, int N,
+                    orbo_keypoint *out) {
+    return distribute_octree(K, nK, minX, maxX, minY, maxY, N, out);
 }
 
 int orbo_level_info(const orbo_extractor *e, int level, int *w, int *h, int *stride) {

@@ -54,6 +54,7 @@ def _declare(L):
     L.orbo_level_ptr.restype = C.c_void_p
     L.orbo_level_ptr.argtypes = [C.c_void_p, C.c_int]
     L.orbo_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orbo_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.orbo_stage_seconds.argtypes = [C.c_void_p, C.c_void_p]
     L.orbo_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.orbo_gaussian7_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -181,3 +182,15 @@ def descriptor(blurred, x, y, angle_deg):
 def ic_angle(img, x, y):
     img = np.ascontiguousarray(img, np.uint8)
     return lib().orbo_ic_angle(img.ctypes.data + y * img.strides[0] + x, img.strides[0])
+
+
+def distribute(cands, min_x, max_x, min_y, max_y, n):
+    """DistributeOctTree on a KP_DTYPE candidate array (x, y relative to min_x/min_y)."""
+    cands = np.ascontiguousarray(cands, KP_DTYPE)
+    w, h = max_x - min_x, max_y - min_y
+    n_ini = max(int(round(w / max(h, 1))), 1)
+    out = np.zeros(max(n + 3, 4 * n_ini) + 8, KP_DTYPE)
+    r = lib().orbo_distribute(_p(cands), len(cands), min_x, max_x, min_y, max_y, n, _p(out))
+    if r < 0:
+        raise RuntimeError("distribute failed: %d" % r)
+    return out[:r].copy()

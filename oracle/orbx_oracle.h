@@ -40,6 +40,9 @@ int orbo_extract(orbo_extractor *e, const uint8_t *img, int w, int h, int stride
 int orbo_level_info(const orbo_extractor *e, int level, int *w, int *h, int *stride);
 const uint8_t *orbo_level_ptr(const orbo_extractor *e, int level); /* interior origin of the padded buffer */
 int orbo_level_candidates(const orbo_extractor *e, int level, orbo_keypoint *out, int cap);
+/* DistributeOctTree alone (ORBextractor.cc:539-763); out must hold max(N+3, 4*nIni) entries; <0 = nIni==0 */
+int orbo_distribute(const orbo_keypoint *K, int nK, int minX, int maxX, int minY, int maxY, int N,
+                    orbo_keypoint *out);
 /* seconds spent per stage in the last orbo_extract: pyramid, fast, octree, orient, blur, desc */
 void orbo_stage_seconds(const orbo_extractor *e, double out[6]);
 
