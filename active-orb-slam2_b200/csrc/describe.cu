@@ -12,7 +12,9 @@
 #define DESC_THREADS 256
 #define DESC_WARPS (DESC_THREADS / 32)
 
-__device__ __constant__ int8_t c_pattern[1024] = {
+// 256 test pairs x (x0,y0,x1,y1); lane j reads its own 32 bytes, so this lives in global memory (L1-cached,
+// two 128-bit loads per lane) rather than in the constant bank, whose divergent reads serialise 32-way
+__device__ __align__(16) int8_t g_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 __device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:454-469
@@ -120,7 +122,10 @@ k_describe(const uint8_t *__restrict__ pyr, size_t pyr_frame, const uint8_t *__r
     sincos_rn(__fmul_rn(angle, factorPI), sn, cs);
     const int bp = L.bpitch;
     const uint8_t *bc = blur + (size_t)frame * blur_frame + L.boff + (size_t)y * bp + x;
-    const int8_t *pat = c_pattern + lane * 32;
+    union { int4 v[2]; int8_t b[32]; } pu;
+    pu.v[0] = __ldg(reinterpret_cast<const int4 *>(g_pattern) + 2 * lane);
+    pu.v[1] = __ldg(reinterpret_cast<const int4 *>(g_pattern) + 2 * lane + 1);
+    const int8_t *pat = pu.b;
     unsigned val = 0;
 #pragma unroll
     for (int bit = 0; bit < 8; bit++) {

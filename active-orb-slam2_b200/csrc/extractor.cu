@@ -384,6 +384,8 @@ extern "C" void orbx_extractor_destroy(orbx_extractor *e) {
     cudaFree(e->d_chunks); cudaFree(e->d_btiles); cudaFree(e->d_cand); cudaFree(e->d_skey); cudaFree(e->d_scand);
     cudaFree(e->d_ncand); cudaFree(e->d_lvl_kp); cudaFree(e->d_lvl_cnt); cudaFree(e->d_status); cudaFree(e->d_img);
     cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
+    for (int i = 0; e->prof_ev && i < e->prof_slots * (ORBX_STAGES + 1); i++) cudaEventDestroy(e->prof_ev[i]);
+    free(e->prof_ev);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->stream) cudaStreamDestroy(e->stream);
     free(e);
@@ -426,11 +428,21 @@ extern "C" orbx_status orbx_extractor_run_device(orbx_extractor *e, const uint8_
     orbx_status st = configure(e, width, height);
     if (st) return st;
     ORBX_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int) * batch, s));
+    cudaEvent_t *ev = e->prof_ev ? e->prof_ev + (size_t)(e->prof_runs % e->prof_slots) * (ORBX_STAGES + 1) : nullptr;
+#define MARK(i) if (ev) ORBX_CUDA(cudaEventRecord(ev[i], s))
+    MARK(0);
     if ((st = orbx_launch_pyramid(e, d_images, frame_pitch, batch, stride, s))) return st;
+    MARK(1);
     if ((st = orbx_launch_fast(e, batch, s))) return st;
+    MARK(2);
     if ((st = orbx_launch_octree(e, batch, s))) return st;
+    MARK(3);
     if ((st = orbx_launch_blur(e, batch, s))) return st;
+    MARK(4);
     if ((st = orbx_launch_describe(e, batch, d_kps, d_desc, d_counts, s))) return st;
+    MARK(5);
+#undef MARK
+    if (ev) e->prof_runs++;
     return ORBX_OK;
 }
 
@@ -543,3 +555,38 @@ extern "C" orbx_status orbx_extractor_level_keypoints_host(const orbx_extractor 
 }
 
 extern "C" int orbx_extractor_last_launches(const orbx_extractor *e) { return e ? e->last_launches : 0; }
+
+extern "C" orbx_status orbx_extractor_profile(orbx_extractor *e, int slots) {
+    if (!e || slots < 0) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(e->device));
+    ORBX_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; e->prof_ev && i < e->prof_slots * (ORBX_STAGES + 1); i++) cudaEventDestroy(e->prof_ev[i]);
+    free(e->prof_ev);
+    e->prof_ev = nullptr;
+    e->prof_slots = e->prof_runs = 0;
+    if (slots == 0) return ORBX_OK;
+    e->prof_ev = (cudaEvent_t *)calloc((size_t)slots * (ORBX_STAGES + 1), sizeof(cudaEvent_t));
+    if (!e->prof_ev) return ORBX_ERR_NOMEM;
+    e->prof_slots = slots;
+    for (int i = 0; i < slots * (ORBX_STAGES + 1); i++) ORBX_CUDA(cudaEventCreate(&e->prof_ev[i]));
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_extractor_stage_ms(orbx_extractor *e, int *runs, float *ms) {
+    if (!e || !runs || !ms || !e->prof_ev) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(e->device));
+    const int n = e->prof_runs < e->prof_slots ? e->prof_runs : e->prof_slots;
+    for (int k = 0; k < ORBX_STAGES; k++) ms[k] = 0.f;
+    for (int r = 0; r < n; r++) {
+        cudaEvent_t *ev = e->prof_ev + (size_t)r * (ORBX_STAGES + 1);
+        ORBX_CUDA(cudaEventSynchronize(ev[ORBX_STAGES]));
+        for (int k = 0; k < ORBX_STAGES; k++) {
+            float t = 0.f;
+            ORBX_CUDA(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+            ms[k] += t;
+        }
+    }
+    *runs = n;
+    e->prof_runs = 0;
+    return ORBX_OK;
+}

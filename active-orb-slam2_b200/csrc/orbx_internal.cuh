@@ -116,7 +116,11 @@ struct orbx_extractor {
     cudaEvent_t ev_h2d[2];
     int last_launches;
     int last_batch;
+    // optional per-stage timing (orbx_extractor_profile): events [prof_slots][ORBX_STAGES + 1] on the launching stream
+    cudaEvent_t *prof_ev;
+    int prof_slots, prof_runs;
 };
+#define ORBX_STAGES 5   // pyramid, fast, quadtree, blur, describe
 
 // ---- kernel launchers (one per stage) ---------------------------------------------------------------
 orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size_t frame_pitch, int batch,

@@ -59,3 +59,5 @@ def _declare(L):
     L.orbx_extractor_level_keypoints_host.argtypes = [vp, i, i, vp, i, C.POINTER(i)]
     L.orbx_extractor_blurred_host.argtypes = [vp, i, i, vp, i]
     L.orbx_extractor_last_launches.argtypes = [vp]
+    L.orbx_extractor_profile.argtypes = [vp, i]
+    L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

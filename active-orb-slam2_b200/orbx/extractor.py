@@ -142,3 +142,15 @@ class ORBextractor:
 
     def last_launches(self):
         return self._L.orbx_extractor_last_launches(self._h)
+
+    STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
+
+    def profile(self, slots):
+        check(self._L.orbx_extractor_profile(self._h, slots))
+
+    def stage_ms(self):
+        """-> (runs, {stage: summed milliseconds over those runs}) since the last call"""
+        n = C.c_int()
+        ms = np.zeros(5, np.float32)
+        check(self._L.orbx_extractor_stage_ms(self._h, C.byref(n), ms.ctypes.data))
+        return n.value, dict(zip(self.STAGES, ms.tolist()))

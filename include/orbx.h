@@ -104,6 +104,13 @@ orbx_status orbx_extractor_level_keypoints_host(const orbx_extractor *e, int bat
 orbx_status orbx_extractor_blurred_host(const orbx_extractor *e, int batch_idx, int level, uint8_t *dst,
                                         int dst_stride);
 
+/* per-stage device timing for bench.py: after orbx_extractor_profile(e, slots) every run records CUDA events
+ * on its launching stream around the five stages (pyramid, FAST, quadtree, blur, describe) into a ring of
+ * `slots` runs; orbx_extractor_stage_ms sums the elapsed milliseconds of the recorded runs per stage into
+ * ms[5], returns how many runs that was, and restarts the ring.  slots = 0 switches it off. */
+orbx_status orbx_extractor_profile(orbx_extractor *e, int slots);
+orbx_status orbx_extractor_stage_ms(orbx_extractor *e, int *runs, float *ms);
+
 /* number of kernels launched by the last run (bench.py reports it as gpu_launches) */
 int orbx_extractor_last_launches(const orbx_extractor *e);
 
