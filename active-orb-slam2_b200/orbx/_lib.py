@@ -59,5 +59,13 @@ def _declare(L):
     L.orbx_extractor_level_keypoints_host.argtypes = [vp, i, i, vp, i, C.POINTER(i)]
     L.orbx_extractor_blurred_host.argtypes = [vp, i, i, vp, i]
     L.orbx_extractor_last_launches.argtypes = [vp]
+    L.orbx_hamming256.argtypes = [vp, vp]
+    L.orbx_matcher_create.argtypes = [C.POINTER(vp), i, i, i, i]
+    L.orbx_matcher_destroy.restype = None
+    L.orbx_matcher_destroy.argtypes = [vp]
+    L.orbx_match_projection_points_host.argtypes = [vp, vp, i, vp, vp, f, f, vp, vp]
+    L.orbx_match_projection_frame_host.argtypes = [vp, vp, i, vp, vp, vp, vp, i, i, f, i, vp, vp]
+    L.orbx_match_projection_frame_device.argtypes = [vp, vp, i, vp]
+    L.orbx_matcher_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -94,3 +94,98 @@ class PlaneWorld:
             tv = np.mod(np.rint(yw[m] * self.texscale + 1024).astype(np.int64), 2048)
             out[m] = self.tex[i][tv, tu]
         return out
+
+
+# ---- matcher scenes: a current frame, and points that project near its keypoints ----------------
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+TUM1_K = (517.306408, 516.469215, 318.643040, 255.313989, 40.0, 40.0 / 517.306408)   # fx fy cx cy bf b
+
+
+def scale_factors(nlevels=8, sf=1.2):
+    s = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        s[i] = np.float32(np.float64(s[i - 1]) * np.float64(np.float32(sf)))
+    return s
+
+
+def random_frame(rng, n, w=640, h=480, nlevels=8, stereo_frac=0.5, claimed_frac=0.05):
+    """a Frame view with n keypoints laid out like extractor output (integer level coordinates times the level scale)"""
+    sf = scale_factors(nlevels)
+    oct_ = rng.choice(nlevels, n, p=np.array([1.2 ** -l for l in range(nlevels)]) / sum(1.2 ** -l for l in range(nlevels))).astype(np.int32)
+    k = np.zeros(n, KP_DTYPE)
+    lx = rng.integers(19, (w / sf[oct_]).astype(np.int64) - 19)
+    ly = rng.integers(19, (h / sf[oct_]).astype(np.int64) - 19)
+    k["x"] = lx.astype(np.float32) * sf[oct_]
+    k["y"] = ly.astype(np.float32) * sf[oct_]
+    k["octave"] = oct_
+    k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k["size"] = (31 * sf[oct_]).astype(np.int32)
+    k["response"] = rng.integers(7, 200, n)
+    k["class_id"] = -1
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    ur = np.where(rng.random(n) < stereo_frac, k["x"] - rng.uniform(2, 40, n).astype(np.float32), np.float32(-1)).astype(np.float32)
+    claimed = (rng.random(n) < claimed_frac).astype(np.uint8)
+    return dict(keys_un=k, desc=desc, u_right=ur, claimed=claimed, bounds=(0.0, 0.0, float(w), float(h)), K=TUM1_K, scale_factors=sf)
+
+
+def flip_bits(rng, desc, nbits):
+    out = desc.copy()
+    for r in range(len(out)):
+        for b in rng.choice(256, int(nbits[r]), replace=False):
+            out[r, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def last_frame_points(rng, cur, n_pts, dup_frac=0.15, angle_jitter=8.0):
+    """points of a 'last frame' that project near keypoints of `cur` under pose (Rcw, tcw); some share a target"""
+    LP = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("valid", "u1"),
+                   ("blocks", "u1"), ("pad", "u1", (2,))])
+    fx, fy, cx, cy, bf, b = cur["K"]
+    n = len(cur["keys_un"])
+    yaw = rng.uniform(-0.05, 0.05)
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    t = rng.uniform(-0.1, 0.1, 3)
+    tgt = rng.integers(0, n, n_pts)
+    ndup = int(dup_frac * n_pts)
+    if ndup and n_pts > ndup:
+        tgt[-ndup:] = tgt[:ndup]                       # several points aim at the same keypoint -> claim conflicts
+    k = cur["keys_un"][tgt]
+    u = k["x"].astype(np.float64) + rng.normal(0, 2.0, n_pts)
+    v = k["y"].astype(np.float64) + rng.normal(0, 2.0, n_pts)
+    z = rng.uniform(1.0, 8.0, n_pts)
+    behind = rng.random(n_pts) < 0.03
+    z[behind] *= -1
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    pw = (pc - t) @ R                                   # R^T (pc - t)
+    pts = np.zeros(n_pts, LP)
+    pts["x"], pts["y"], pts["z"] = pw[:, 0], pw[:, 1], pw[:, 2]
+    pts["octave"] = np.clip(k["octave"] + rng.integers(-1, 2, n_pts), 0, len(cur["scale_factors"]) - 1)
+    pts["angle"] = np.mod(k["angle"] + rng.normal(0, angle_jitter, n_pts) + np.where(rng.random(n_pts) < 0.1, 90, 0), 360).astype(np.float32)
+    pts["valid"] = rng.random(n_pts) > 0.05
+    pts["blocks"] = rng.random(n_pts) > 0.2
+    desc = flip_bits(rng, cur["desc"][tgt], rng.integers(0, 90, n_pts))
+    return pts, desc, R.astype(np.float32), t.astype(np.float32)
+
+
+def track_points(rng, cur, n_pts, dup_frac=0.15):
+    """map points as Frame::isInFrustum leaves them (mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos)"""
+    TP = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                   ("in_view", "u1"), ("blocks", "u1"), ("pad", "u1", (2,))])
+    n = len(cur["keys_un"])
+    tgt = rng.integers(0, n, n_pts)
+    ndup = int(dup_frac * n_pts)
+    if ndup and n_pts > ndup:
+        tgt[-ndup:] = tgt[:ndup]
+    k = cur["keys_un"][tgt]
+    pts = np.zeros(n_pts, TP)
+    pts["proj_x"] = k["x"] + rng.normal(0, 1.5, n_pts)
+    pts["proj_y"] = k["y"] + rng.normal(0, 1.5, n_pts)
+    ur = cur["u_right"][tgt]
+    pts["proj_xr"] = np.where(ur > 0, ur + rng.normal(0, 2.0, n_pts), pts["proj_x"] - 10)
+    pts["view_cos"] = rng.uniform(0.99, 1.0, n_pts)
+    pts["level"] = np.clip(k["octave"] + rng.integers(0, 2, n_pts), 0, len(cur["scale_factors"]) - 1)
+    pts["in_view"] = rng.random(n_pts) > 0.1
+    pts["blocks"] = rng.random(n_pts) > 0.1
+    desc = flip_bits(rng, cur["desc"][tgt], rng.integers(0, 110, n_pts))
+    return pts, desc

@@ -114,6 +114,84 @@ orbx_status orbx_extractor_stage_ms(orbx_extractor *e, int *runs, float *ms);
 /* number of kernels launched by the last run (bench.py reports it as gpu_launches) */
 int orbx_extractor_last_launches(const orbx_extractor *e);
 
+/* =====================================================================================================
+ * ORBmatcher  (reference include/ORBmatcher.h:37-102, src/ORBmatcher.cc; Frame grid src/Frame.cc:259-274,
+ * :356-421).  The adapter gathers these POD views from Frame / MapPoint with the reference's own getters and
+ * writes `match` back into Frame::mvpMapPoints.
+ * ===================================================================================================== */
+
+/* replaces static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&) (ORBmatcher.cc:1647);
+ * plain host function (256-bit Hamming distance) */
+int orbx_hamming256(const uint8_t a[32], const uint8_t b[32]);
+
+typedef struct {                 /* a Frame as the matchers read it (include/Frame.h) */
+    int32_t n;                   /* N */
+    const int32_t *n_dev;        /* device entry points only: if non-NULL, N is read from here on the device */
+    const orbx_keypoint *keys_un; /* mvKeysUn */
+    const uint8_t *desc;         /* mDescriptors, n x 32, 16-byte aligned */
+    const float *u_right;        /* mvuRight (NULL = all negative) */
+    const uint8_t *claimed;      /* 1 where mvpMapPoints[i] && mvpMapPoints[i]->Observations()>0 (NULL = none) */
+    float min_x, min_y, max_x, max_y;      /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float grid_w_inv, grid_h_inv;          /* mfGridElementWidthInv, mfGridElementHeightInv (64 x 48 grid) */
+    float fx, fy, cx, cy, bf, b;
+    const float *scale_factors;  /* mvScaleFactors */
+    int32_t nlevels;
+} orbx_frame_view;
+
+typedef struct {                 /* a map point prepared by Frame::isInFrustum (MapPoint.h mTrack* members) */
+    float proj_x, proj_y, proj_xr, view_cos;   /* mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos */
+    int32_t level;               /* mnTrackScaleLevel */
+    uint8_t in_view;             /* mbTrackInView && !isBad() */
+    uint8_t blocks;              /* Observations() > 0 */
+    uint8_t pad[2];
+} orbx_track_point;
+
+typedef struct {                 /* keypoint i of the last frame together with its map point */
+    float x, y, z;               /* pMP->GetWorldPos() */
+    float angle;                 /* LastFrame.mvKeysUn[i].angle */
+    int32_t octave;              /* LastFrame.mvKeys[i].octave */
+    uint8_t valid;               /* pMP && !LastFrame.mvbOutlier[i] */
+    uint8_t blocks;              /* pMP->Observations() > 0 */
+    uint8_t pad[2];
+} orbx_last_point;
+
+typedef struct orbx_matcher orbx_matcher;   /* device scratch + stream; ORBmatcher itself is stateless */
+orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints, int max_points, int max_jobs, int device);
+void orbx_matcher_destroy(orbx_matcher *m);
+
+/* replaces int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)
+ * (ORBmatcher.cc:45-129), mfNNratio passed as nnratio.  match[F->n] is Frame::mvpMapPoints as indices into
+ * `pts` (in/out: entries that receive no match are left untouched); *nmatches is the return value. */
+orbx_status orbx_match_projection_points_host(orbx_matcher *m, const orbx_frame_view *F, int n_pts,
+                                              const orbx_track_point *pts, const uint8_t *pt_desc, float th,
+                                              float nnratio, int32_t *match, int32_t *nmatches);
+
+/* replaces int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th,
+ * const bool bMono) (ORBmatcher.cc:1328-1470).  Rcw/tcw = CurrentFrame.mTcw (row-major 3x3, 3); forward /
+ * backward = the reference's bForward / bBackward (:1350-1351); check_ori = mbCheckOrientation. */
+orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const orbx_frame_view *cur, int n_last,
+                                             const orbx_last_point *pts, const uint8_t *last_desc,
+                                             const float Rcw[9], const float tcw[3], int forward, int backward,
+                                             float th, int check_ori, int32_t *match, int32_t *nmatches);
+
+/* batched, device-resident form of the call above: every pointer inside a job is a device pointer; d_jobs is a
+ * device array of n_jobs (<= max_jobs) independent (current, last) pairs.  Only enqueues on `stream`. */
+typedef struct {
+    orbx_frame_view cur;
+    int32_t n_last;
+    const orbx_last_point *pts;
+    const uint8_t *last_desc;
+    float Rcw[9], tcw[3];
+    int32_t forward, backward;
+    float th;
+    int32_t check_ori;
+    int32_t *match;              /* cur.n entries, in/out */
+    int32_t *nmatches;           /* 1 entry */
+} orbx_frame_match_job;
+orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
+                                               void *stream);
+int orbx_matcher_last_launches(const orbx_matcher *m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,235 @@
+/* orbx CPU oracle, matcher part — TEST INFRASTRUCTURE ONLY (see orbx_oracle.h).
+ *
+ * Restates, in dependency-free C and in the reference's own sequential order:
+ *   ORBmatcher::DescriptorDistance                               src/ORBmatcher.cc:1647-1663
+ *   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea  src/Frame.cc:259-274, :411-421, :356-409
+ *   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)          src/ORBmatcher.cc:45-129
+ *   ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, mono)  src/ORBmatcher.cc:1328-1470
+ *   ORBmatcher::ComputeThreeMaxima                                          src/ORBmatcher.cc:1601-1642
+ * cv::Mat float products are plain sequential float arithmetic (verified against cv2.gemm):
+ * ((r0*x0 + r1*x1) + r2*x2) + t.  Compile with -ffp-contract=off.
+ * PARITY PINNING: the reference holds no tests or vectors for this path => unpinned by the reference; the
+ * restatement is line-by-line and tests/test_match_oracle.py cross-checks it against an independent numpy
+ * brute-force statement of the same rules.
+ */
+#include "orbx_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define TH_HIGH 100
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+
+int orbo_hamming256(const uint8_t *a, const uint8_t *b) {
+    const uint32_t *pa = (const uint32_t *)a, *pb = (const uint32_t *)b;
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+/* ---- Frame grid ---- */
+typedef struct {
+    int *start;   /* GRID_COLS*GRID_ROWS + 1, cell = ix*GRID_ROWS + iy */
+    int *idx;     /* keypoint indices, ascending inside a cell (push_back order) */
+} grid_t;
+
+static void grid_build(const orbo_frame *F, grid_t *g) {
+    const int nc = GRID_COLS * GRID_ROWS;
+    g->start = (int *)calloc(nc + 1, sizeof(int));
+    g->idx = (int *)malloc(sizeof(int) * (F->n > 0 ? F->n : 1));
+    int *cell = (int *)malloc(sizeof(int) * (F->n > 0 ? F->n : 1));
+    for (int i = 0; i < F->n; i++) {
+        /* PosInGrid, Frame.cc:411-421 */
+        const int px = (int)roundf((F->keys_un[i].x - F->min_x) * F->grid_w_inv);
+        const int py = (int)roundf((F->keys_un[i].y - F->min_y) * F->grid_h_inv);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) { cell[i] = -1; continue; }
+        cell[i] = px * GRID_ROWS + py;
+        g->start[cell[i] + 1]++;
+    }
+    for (int c = 0; c < nc; c++) g->start[c + 1] += g->start[c];
+    int *cur = (int *)malloc(sizeof(int) * nc);
+    memcpy(cur, g->start, sizeof(int) * nc);
+    for (int i = 0; i < F->n; i++) if (cell[i] >= 0) g->idx[cur[cell[i]]++] = i;
+    free(cur); free(cell);
+}
+static void grid_free(grid_t *g) { free(g->start); free(g->idx); }
+
+/* GetFeaturesInArea, Frame.cc:356-409; returns count, indices in out (cap F->n) */
+static int features_in_area(const orbo_frame *F, const grid_t *g, float x, float y, float r, int minLevel, int maxLevel,
+                            int *out) {
+    int n = 0;
+    int nMinCellX = (int)floorf((x - F->min_x - r) * F->grid_w_inv); if (nMinCellX < 0) nMinCellX = 0;
+    if (nMinCellX >= GRID_COLS) return 0;
+    int nMaxCellX = (int)ceilf((x - F->min_x + r) * F->grid_w_inv); if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floorf((y - F->min_y - r) * F->grid_h_inv); if (nMinCellY < 0) nMinCellY = 0;
+    if (nMinCellY >= GRID_ROWS) return 0;
+    int nMaxCellY = (int)ceilf((y - F->min_y + r) * F->grid_h_inv); if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
+    if (nMaxCellY < 0) return 0;
+    const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int j = g->start[c]; j < g->start[c + 1]; j++) {
+                const orbo_keypoint *kp = &F->keys_un[g->idx[j]];
+                if (bCheckLevels) {
+                    if (kp->octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                }
+                const float distx = kp->x - x, disty = kp->y - y;
+                if (fabsf(distx) < r && fabsf(disty) < r) out[n++] = g->idx[j];
+            }
+        }
+    return n;
+}
+
+int orbo_features_in_area(const orbo_frame *F, float x, float y, float r, int minLevel, int maxLevel, int *out) {
+    grid_t g;
+    grid_build(F, &g);
+    const int n = features_in_area(F, &g, x, y, r, minLevel, maxLevel, out);
+    grid_free(&g);
+    return n;
+}
+
+/* ORBmatcher.cc:1601-1642 on bin sizes */
+void orbo_three_maxima(const int *histo, int L, int *ind1, int *ind2, int *ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    *ind1 = *ind2 = *ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+/* SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:45-129.
+ * match[k] (F->n entries) is the caller's mvpMapPoints as point indices: -1 = none on entry unless F->claimed[k];
+ * on return match[k] = index of the map point written there, untouched otherwise. */
+int orbo_search_by_projection_points(const orbo_frame *F, int n_pts, const orbo_track_point *P, const uint8_t *pt_desc,
+                                     float th, float nnratio, int32_t *match) {
+    grid_t g;
+    grid_build(F, &g);
+    int *ind = (int *)malloc(sizeof(int) * (F->n > 0 ? F->n : 1));
+    uint8_t *blocked = (uint8_t *)calloc(F->n > 0 ? F->n : 1, 1);   /* mvpMapPoints[idx] && Observations()>0 */
+    for (int k = 0; k < F->n; k++) blocked[k] = F->claimed ? F->claimed[k] : 0;
+    int nmatches = 0;
+    const int bFactor = th != 1.0f;
+    for (int i = 0; i < n_pts; i++) {
+        const orbo_track_point *p = &P[i];
+        if (!p->in_view) continue;                 /* !mbTrackInView || isBad() */
+        const int lvl = p->level;
+        float r = p->view_cos > 0.998f ? 2.5f : 4.0f;   /* RadiusByViewingCos, :131-137 */
+        if (bFactor) r *= th;
+        const float rs = r * F->scale_factors[lvl];
+        const int n = features_in_area(F, &g, p->proj_x, p->proj_y, rs, lvl - 1, lvl, ind);
+        if (n == 0) continue;
+        const uint8_t *d = pt_desc + (size_t)32 * i;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < n; c++) {
+            const int idx = ind[c];
+            if (blocked[idx]) continue;
+            if (F->u_right && F->u_right[idx] > 0) {
+                const float er = fabsf(p->proj_xr - F->u_right[idx]);
+                if (er > rs) continue;
+            }
+            const int dist = orbo_hamming256(d, F->desc + (size_t)32 * idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F->keys_un[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys_un[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            match[bestIdx] = i;
+            blocked[bestIdx] = p->blocks;   /* later points skip it iff this map point has Observations()>0 */
+            nmatches++;
+        }
+    }
+    free(ind); free(blocked);
+    grid_free(&g);
+    return nmatches;
+}
+
+/* SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), ORBmatcher.cc:1328-1470.
+ * forward / backward are the reference's bForward / bBackward (:1350-1351), computed by the caller from the
+ * two poses.  match as above (indices into the last frame). */
+int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orbo_last_point *Lp, const uint8_t *last_desc,
+                                    const float Rcw[9], const float tcw[3], int forward, int backward, float th,
+                                    int check_ori, int32_t *match) {
+    grid_t g;
+    grid_build(Cur, &g);
+    int *ind = (int *)malloc(sizeof(int) * (Cur->n > 0 ? Cur->n : 1));
+    uint8_t *blocked = (uint8_t *)calloc(Cur->n > 0 ? Cur->n : 1, 1);
+    for (int k = 0; k < Cur->n; k++) blocked[k] = Cur->claimed ? Cur->claimed[k] : 0;
+    int *hist_kp = (int *)malloc(sizeof(int) * (n_last > 0 ? n_last : 1));   /* rotHist entries in push order */
+    int *hist_bin = (int *)malloc(sizeof(int) * (n_last > 0 ? n_last : 1));
+    int nh = 0, nmatches = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < n_last; i++) {
+        const orbo_last_point *p = &Lp[i];
+        if (!p->valid) continue;                   /* pMP && !mvbOutlier[i] */
+        const float xc = ((Rcw[0] * p->x + Rcw[1] * p->y) + Rcw[2] * p->z) + tcw[0];
+        const float yc = ((Rcw[3] * p->x + Rcw[4] * p->y) + Rcw[5] * p->z) + tcw[1];
+        const float zc = ((Rcw[6] * p->x + Rcw[7] * p->y) + Rcw[8] * p->z) + tcw[2];
+        const float invzc = (float)(1.0 / (double)zc);
+        if (invzc < 0) continue;
+        const float u = Cur->fx * xc * invzc + Cur->cx;
+        const float v = Cur->fy * yc * invzc + Cur->cy;
+        if (u < Cur->min_x || u > Cur->max_x) continue;
+        if (v < Cur->min_y || v > Cur->max_y) continue;
+        const int oct = p->octave;
+        const float radius = th * Cur->scale_factors[oct];
+        int n;
+        if (forward) n = features_in_area(Cur, &g, u, v, radius, oct, -1, ind);
+        else if (backward) n = features_in_area(Cur, &g, u, v, radius, 0, oct, ind);
+        else n = features_in_area(Cur, &g, u, v, radius, oct - 1, oct + 1, ind);
+        if (n == 0) continue;
+        const uint8_t *d = last_desc + (size_t)32 * i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < n; c++) {
+            const int i2 = ind[c];
+            if (blocked[i2]) continue;
+            if (Cur->u_right && Cur->u_right[i2] > 0) {
+                const float ur = u - Cur->bf * invzc;
+                const float er = fabsf(ur - Cur->u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orbo_hamming256(d, Cur->desc + (size_t)32 * i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            match[bestIdx2] = i;
+            blocked[bestIdx2] = p->blocks;
+            nmatches++;
+            if (check_ori) {
+                float rot = p->angle - Cur->keys_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                hist_kp[nh] = bestIdx2; hist_bin[nh] = bin; nh++;
+            }
+        }
+    }
+    if (check_ori) {
+        int cnt[HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (int j = 0; j < nh; j++) cnt[hist_bin[j]]++;
+        orbo_three_maxima(cnt, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int j = 0; j < nh; j++)
+            if (hist_bin[j] != i1 && hist_bin[j] != i2 && hist_bin[j] != i3) { match[hist_kp[j]] = -1; nmatches--; }
+    }
+    free(ind); free(blocked); free(hist_kp); free(hist_bin);
+    grid_free(&g);
+    return nmatches;
+}

@@ -194,3 +194,100 @@ def distribute(cands, min_x, max_x, min_y, max_y, n):
     if r < 0:
         raise RuntimeError("distribute failed: %d" % r)
     return out[:r].copy()
+
+
+# ---- matchers (oracle/match_oracle.c) --------------------------------------------------------------------------
+TRACK_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                              ("in_view", "u1"), ("blocks", "u1"), ("pad", "u1", (2,))])
+LAST_POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("valid", "u1"),
+                             ("blocks", "u1"), ("pad", "u1", (2,))])
+assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24
+
+
+class OFrame(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("claimed", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("b", C.c_float),
+                ("scale_factors", C.c_void_p), ("nlevels", C.c_int32)]
+
+
+def _oframe(fr):
+    """fr: dict with keys_un, desc, u_right (or None), claimed (or None), bounds=(minx,miny,maxx,maxy), K=(fx,fy,cx,cy,bf,b),
+    scale_factors.  Returns (OFrame, keepalive list)."""
+    keys = np.ascontiguousarray(fr["keys_un"], KP_DTYPE)
+    desc = np.ascontiguousarray(fr["desc"], np.uint8)
+    sf = np.ascontiguousarray(fr["scale_factors"], np.float32)
+    keep = [keys, desc, sf]
+    f = OFrame()
+    f.n = len(keys)
+    f.keys_un, f.desc, f.scale_factors, f.nlevels = keys.ctypes.data, desc.ctypes.data, sf.ctypes.data, len(sf)
+    if fr.get("u_right") is not None:
+        ur = np.ascontiguousarray(fr["u_right"], np.float32); keep.append(ur); f.u_right = ur.ctypes.data
+    if fr.get("claimed") is not None:
+        cl = np.ascontiguousarray(fr["claimed"], np.uint8); keep.append(cl); f.claimed = cl.ctypes.data
+    mnx, mny, mxx, mxy = (np.float32(v) for v in fr["bounds"])
+    f.min_x, f.min_y, f.max_x, f.max_y = mnx, mny, mxx, mxy
+    f.grid_w_inv = np.float32(64) / (mxx - mnx)      # Frame.cc:127-128
+    f.grid_h_inv = np.float32(48) / (mxy - mny)
+    f.fx, f.fy, f.cx, f.cy, f.bf, f.b = (np.float32(v) for v in fr["K"])
+    return f, keep
+
+
+def _declare_match(L):
+    if getattr(L, "_match_declared", False):
+        return
+    L.orbo_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+    L.orbo_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    L.orbo_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+    L.orbo_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    L.orbo_search_by_projection_frame.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    L._match_declared = True
+
+
+def hamming256(a, b):
+    L = lib(); _declare_match(L)
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return L.orbo_hamming256(_p(a), _p(b))
+
+
+def features_in_area(fr, x, y, r, min_level=-1, max_level=-1):
+    L = lib(); _declare_match(L)
+    f, keep = _oframe(fr)
+    out = np.zeros(max(f.n, 1), np.int32)
+    n = L.orbo_features_in_area(C.byref(f), x, y, r, min_level, max_level, _p(out))
+    return out[:n].copy()
+
+
+def three_maxima(hist):
+    L = lib(); _declare_match(L)
+    h = np.ascontiguousarray(hist, np.int32)
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    L.orbo_three_maxima(_p(h), len(h), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def search_by_projection_points(fr, pts, pt_desc, th, nnratio=0.8, match=None):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) -> (nmatches, match[F.n])"""
+    L = lib(); _declare_match(L)
+    f, keep = _oframe(fr)
+    pts = np.ascontiguousarray(pts, TRACK_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    m = np.full(f.n, -1, np.int32) if match is None else np.ascontiguousarray(match, np.int32).copy()
+    n = L.orbo_search_by_projection_points(C.byref(f), len(pts), _p(pts), _p(pd), th, nnratio, _p(m))
+    return n, m
+
+
+def search_by_projection_frame(cur, last_pts, last_desc, Rcw, tcw, forward, backward, th, check_ori=True, match=None):
+    """ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, mono) -> (nmatches, match[Cur.n])"""
+    L = lib(); _declare_match(L)
+    f, keep = _oframe(cur)
+    pts = np.ascontiguousarray(last_pts, LAST_POINT_DTYPE)
+    pd = np.ascontiguousarray(last_desc, np.uint8)
+    R = np.ascontiguousarray(Rcw, np.float32).reshape(9)
+    t = np.ascontiguousarray(tcw, np.float32).reshape(3)
+    m = np.full(f.n, -1, np.int32) if match is None else np.ascontiguousarray(match, np.int32).copy()
+    n = L.orbo_search_by_projection_frame(C.byref(f), len(pts), _p(pts), _p(pd), _p(R), _p(t), int(forward), int(backward), th,
+                                          int(check_ori), _p(m))
+    return n, m

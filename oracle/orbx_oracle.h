@@ -59,6 +59,43 @@ int orbo_cv_round_f(float v);
 void orbo_descriptor(const uint8_t *blurred_center, int stride, float angle_deg, uint8_t desc[32]);
 float orbo_ic_angle(const uint8_t *center, int stride);
 
+/* ---- matchers (src/ORBmatcher.cc, src/Frame.cc grid) ---- */
+typedef struct {                 /* a Frame as the matchers read it (include/Frame.h) */
+    int32_t n;                   /* N */
+    const orbo_keypoint *keys_un; /* mvKeysUn */
+    const uint8_t *desc;         /* mDescriptors, n x 32 */
+    const float *u_right;        /* mvuRight (NULL = all negative) */
+    const uint8_t *claimed;      /* 1 where mvpMapPoints[i] && mvpMapPoints[i]->Observations()>0 (NULL = none) */
+    float min_x, min_y, max_x, max_y;      /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float grid_w_inv, grid_h_inv;          /* mfGridElementWidthInv, mfGridElementHeightInv */
+    float fx, fy, cx, cy, bf, b;
+    const float *scale_factors;  /* mvScaleFactors */
+    int32_t nlevels;
+} orbo_frame;
+typedef struct {                 /* a map point prepared by Frame::isInFrustum (MapPoint.h mTrack* members) */
+    float proj_x, proj_y, proj_xr, view_cos;
+    int32_t level;               /* mnTrackScaleLevel */
+    uint8_t in_view;             /* mbTrackInView && !isBad() */
+    uint8_t blocks;              /* Observations() > 0 */
+    uint8_t pad[2];
+} orbo_track_point;
+typedef struct {                 /* keypoint i of the last frame with its map point */
+    float x, y, z;               /* pMP->GetWorldPos() */
+    float angle;                 /* LastFrame.mvKeysUn[i].angle */
+    int32_t octave;              /* LastFrame.mvKeys[i].octave */
+    uint8_t valid;               /* pMP && !mvbOutlier[i] */
+    uint8_t blocks;              /* pMP->Observations() > 0 */
+    uint8_t pad[2];
+} orbo_last_point;
+int orbo_hamming256(const uint8_t *a, const uint8_t *b);
+int orbo_features_in_area(const orbo_frame *F, float x, float y, float r, int minLevel, int maxLevel, int *out);
+void orbo_three_maxima(const int *histo, int L, int *ind1, int *ind2, int *ind3);
+int orbo_search_by_projection_points(const orbo_frame *F, int n_pts, const orbo_track_point *P, const uint8_t *pt_desc,
+                                     float th, float nnratio, int32_t *match);
+int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orbo_last_point *Lp, const uint8_t *last_desc,
+                                    const float Rcw[9], const float tcw[3], int forward, int backward, float th,
+                                    int check_ori, int32_t *match);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,171 @@
+"""Oracle matchers (oracle/match_oracle.c) against an independent brute-force statement of the reference rules
+(src/ORBmatcher.cc:45-129, :1328-1470; src/Frame.cc:356-421).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from orbx import synth
+
+f32 = np.float32
+
+
+def popcount_dist(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def test_hamming_matches_popcount():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+        assert O.hamming256(a, b) == popcount_dist(a, b)
+    z = np.zeros(32, np.uint8)
+    assert O.hamming256(z, z) == 0 and O.hamming256(z, ~z) == 256
+
+
+def brute_window(fr, x, y, r, min_level, max_level):
+    """GetFeaturesInArea without the grid: same members, same order (cell column, cell row, index)"""
+    k = fr["keys_un"]
+    mnx, mny, mxx, mxy = (f32(v) for v in fr["bounds"])
+    wi, hi = f32(64) / (mxx - mnx), f32(48) / (mxy - mny)
+    x, y, r = f32(x), f32(y), f32(r)
+    x0 = max(0, int(np.floor((x - mnx - r) * wi))); x1 = min(63, int(np.ceil((x - mnx + r) * wi)))
+    y0 = max(0, int(np.floor((y - mny - r) * hi))); y1 = min(47, int(np.ceil((y - mny + r) * hi)))
+    if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+        return []
+    out = []
+    for i in range(len(k)):
+        px = int(np.floor(abs((k["x"][i] - mnx) * wi) + f32(0.5)) * np.sign((k["x"][i] - mnx) * wi))
+        py = int(np.floor(abs((k["y"][i] - mny) * hi) + f32(0.5)) * np.sign((k["y"][i] - mny) * hi))
+        if not (0 <= px < 64 and 0 <= py < 48) or not (x0 <= px <= x1 and y0 <= py <= y1):
+            continue
+        if (min_level > 0 or max_level >= 0):
+            if k["octave"][i] < min_level or (max_level >= 0 and k["octave"][i] > max_level):
+                continue
+        if abs(k["x"][i] - x) < r and abs(k["y"][i] - y) < r:
+            out.append((px, py, i))
+    return [i for _, _, i in sorted(out)]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_features_in_area(seed):
+    rng = np.random.default_rng(seed)
+    fr = synth.random_frame(rng, 600)
+    for _ in range(60):
+        x, y, r = rng.uniform(-20, 660), rng.uniform(-20, 500), rng.uniform(1, 60)
+        lv = [(-1, -1), (0, 3), (2, -1), (1, 2), (0, -1)][rng.integers(0, 5)]
+        assert O.features_in_area(fr, x, y, r, *lv).tolist() == brute_window(fr, x, y, r, *lv)
+
+
+def test_three_maxima():
+    assert O.three_maxima([0] * 30) == (-1, -1, -1)
+    h = [0] * 30; h[3], h[7], h[9] = 50, 40, 30
+    assert O.three_maxima(h) == (3, 7, 9)
+    h[7], h[9] = 4, 3
+    assert O.three_maxima(h) == (3, -1, -1)
+    h[7] = 6
+    assert O.three_maxima(h) == (3, 7, -1)
+
+
+def brute_frame(cur, pts, desc, R, t, forward, backward, th, check_ori):
+    k = cur["keys_un"]
+    fx, fy, cx, cy, bf, b = (f32(v) for v in cur["K"])
+    mnx, mny, mxx, mxy = (f32(v) for v in cur["bounds"])
+    blocked = cur["claimed"].astype(bool).copy()
+    match = np.full(len(k), -1, np.int32)
+    hist, nm = [], 0
+    R = R.astype(f32)
+    for i in range(len(pts)):
+        p = pts[i]
+        if not p["valid"]:
+            continue
+        X = np.array([p["x"], p["y"], p["z"]], f32)
+        c = [f32(f32(f32(R[r, 0] * X[0]) + f32(R[r, 1] * X[1])) + f32(R[r, 2] * X[2])) + t[r] for r in range(3)]
+        invz = f32(1.0 / np.float64(c[2]))
+        if invz < 0:
+            continue
+        u = f32(f32(f32(fx * c[0]) * invz) + cx); v = f32(f32(f32(fy * c[1]) * invz) + cy)
+        if u < mnx or u > mxx or v < mny or v > mxy:
+            continue
+        o = int(p["octave"])
+        rad = f32(f32(th) * cur["scale_factors"][o])
+        lv = (o, -1) if forward else ((0, o) if backward else (o - 1, o + 1))
+        best, bi = 256, -1
+        for j in brute_window(cur, u, v, rad, *lv):
+            if blocked[j]:
+                continue
+            if cur["u_right"][j] > 0 and abs(f32(f32(u - f32(bf * invz)) - cur["u_right"][j])) > rad:
+                continue
+            d = popcount_dist(desc[i], cur["desc"][j])
+            if d < best:
+                best, bi = d, j
+        if best <= 100:
+            match[bi] = i; blocked[bi] = bool(p["blocks"]); nm += 1
+            if check_ori:
+                rot = f32(p["angle"] - k["angle"][bi])
+                if rot < 0:
+                    rot = f32(rot + f32(360))
+                bn = int(np.floor(f32(rot * f32(1.0 / 30)) + f32(0.5)))
+                hist.append((0 if bn == 30 else bn, bi))
+    if check_ori:
+        cnt = np.bincount([h[0] for h in hist], minlength=30)
+        keep = O.three_maxima(cnt)
+        for bn, bi in hist:
+            if bn not in keep:
+                match[bi] = -1; nm -= 1
+    return nm, match
+
+
+@pytest.mark.parametrize("seed,mode", [(0, "win"), (1, "fwd"), (2, "bwd"), (3, "win")])
+def test_search_by_projection_frame(seed, mode):
+    rng = np.random.default_rng(seed)
+    cur = synth.random_frame(rng, 500)
+    pts, desc, R, t = synth.last_frame_points(rng, cur, 400)
+    fw, bw = mode == "fwd", mode == "bwd"
+    for th in (7.0, 15.0):
+        n, m = O.search_by_projection_frame(cur, pts, desc, R, t, fw, bw, th, True)
+        n2, m2 = brute_frame(cur, pts, desc, R, t, fw, bw, th, True)
+        assert n == n2 and np.array_equal(m, m2)
+        assert n > 50
+
+
+def brute_points(F, pts, desc, th, nnratio):
+    k = F["keys_un"]
+    blocked = F["claimed"].astype(bool).copy()
+    match = np.full(len(k), -1, np.int32)
+    nm = 0
+    for i in range(len(pts)):
+        p = pts[i]
+        if not p["in_view"]:
+            continue
+        r = f32(2.5) if p["view_cos"] > f32(0.998) else f32(4.0)
+        if th != 1.0:
+            r = f32(r * f32(th))
+        rs = f32(r * F["scale_factors"][p["level"]])
+        bd, bl, bd2, bl2, bi = 256, -1, 256, -1, -1
+        for j in brute_window(F, p["proj_x"], p["proj_y"], rs, int(p["level"]) - 1, int(p["level"])):
+            if blocked[j]:
+                continue
+            if F["u_right"][j] > 0 and abs(f32(p["proj_xr"] - F["u_right"][j])) > rs:
+                continue
+            d = popcount_dist(desc[i], F["desc"][j])
+            if d < bd:
+                bd2, bd, bl2, bl, bi = bd, d, bl, int(k["octave"][j]), j
+            elif d < bd2:
+                bl2, bd2 = int(k["octave"][j]), d
+        if bd <= 100:
+            if bl == bl2 and f32(bd) > f32(f32(nnratio) * f32(bd2)):
+                continue
+            match[bi] = i; blocked[bi] = bool(p["blocks"]); nm += 1
+    return nm, match
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_search_by_projection_points(seed):
+    rng = np.random.default_rng(100 + seed)
+    F = synth.random_frame(rng, 700)
+    pts, desc = synth.track_points(rng, F, 500)
+    for th in (1.0, 3.0, 5.0):
+        n, m = O.search_by_projection_points(F, pts, desc, th, 0.8)
+        n2, m2 = brute_points(F, pts, desc, th, 0.8)
+        assert n == n2 and np.array_equal(m, m2)
+    assert n > 50
