@@ -3,10 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl orbx|reference]
 
-A "step" is one pass of the hot path over one batch of B synthetic 640x480 frames (1000 features, 8 levels).
+A "step" is one pass of the hot path over one batch of B synthetic 640x480 frames (1000 features, 8 levels):
+ORBextractor::operator() on every frame, then ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th=7) of every
+frame against its predecessor (the predecessor is the same scene shifted by (13, 7) px, its
+map points lie on a plane at z = 4 m and the current pose is the matching translation).
   value     frames/s with the batch already resident in HBM (CUDA events on the launching stream)
-  e2e       frames/s through the public host API (orbx_extractor_run_host): pinned host frames in, H2D copy,
-            kernels, D2H of keypoints + descriptors + counts, every step
+  e2e       frames/s with HOST buffers: pinned frames + last-frame points in, H2D copies, the C-ABI calls, D2H of
+            keypoints + descriptors + counts + matches, stream-synchronised every step
   roofline  dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration vs measured HBM peak
   cpu_baseline  the CPU oracle (a dependency-free port of the reference path) on this box's host cores
 N > 1 (torchrun, one rank per GPU): frames are independent, so every rank runs its own batch (weak scaling, no
@@ -29,11 +32,12 @@ for p in (ROOT, os.path.join(ROOT, "active-orb-slam2_b200")):
 import numpy as np  # noqa: E402
 
 W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
-METRIC = "frames/sec ORB extract (640x480, 1000 kpts)"
+METRIC = "frames/sec ORB extract+match (640x480, 1000 kpts)"
 # SURVEY.md §8(d) / DESIGN.md: compulsory bytes per VGA frame of each stage (level sizes of the 8-level pyramid)
 PYR_PADDED = 1158012
 PYR_INTERIOR = 950532
 ALGO_BYTES = {
+    "match": 2 * NFEAT * (32 + 24) + NFEAT * 8,    # both descriptor sets + points/keypoints in, match array out (~104 KB)
     "pyramid": W * H + PYR_PADDED,                 # read the frame, write the padded pyramid
     "fast": PYR_INTERIOR,                          # read every level once (+ a few KB of candidates)
     "quadtree": 0,
@@ -108,20 +112,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_path(frames, seconds_budget, threads):
-    """oracle extractor on `threads` host threads (ctypes releases the GIL); returns (fps, frames_done, seconds)"""
+def cpu_path(frames, seconds_budget, threads, nbase=16):
+    """the same extract+match workload on the CPU oracle, `threads` host threads (ctypes releases the GIL), one
+    extractor per thread; frames[k * nbase + b] is variant k of base image b.  Returns (fps, frames_done, seconds)."""
     from oracle import oracle_py as O
+    from orbx import synth
     O.lib()
     done = [0] * threads
     stop_at = [None]
+    nvar = max(len(frames) // nbase, 1)
+    fx, fy, cx, cy, bf, bb = synth.TUM1_K
+    Z = 4.0
+    sf = synth.scale_factors(NLEVELS, SCALE)
+    R = np.eye(3, dtype=np.float32)
+    tshift = np.array([13.0 * Z / fx, 7.0 * Z / fy, 0.0], np.float32)
 
     def work(t):
         ex = O.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
-        i = t
+        b, k, prev = t % nbase, 0, None
         while time.perf_counter() < stop_at[0]:
-            ex(frames[i % len(frames)])
+            kp, de = ex(frames[(k * nbase + b) % len(frames)])
+            last = (kp, de) if prev is None else prev
+            pts = np.zeros(len(last[0]), O.LAST_POINT_DTYPE)
+            pts["x"] = (last[0]["x"].astype(np.float64) - cx) / fx * Z
+            pts["y"] = (last[0]["y"].astype(np.float64) - cy) / fy * Z
+            pts["z"], pts["angle"], pts["octave"], pts["valid"], pts["blocks"] = Z, last[0]["angle"], last[0]["octave"], 1, 1
+            cur = dict(keys_un=kp, desc=de, u_right=None, claimed=None, bounds=(0.0, 0.0, float(W), float(H)), K=synth.TUM1_K,
+                       scale_factors=sf)
+            O.search_by_projection_frame(cur, pts, last[1], R, tshift if prev is not None else np.zeros(3, np.float32), False, False,
+                                         7.0, True)
+            prev = (kp, de)
+            k += 1
+            if k == nvar:
+                k, prev = 0, None
             done[t] += 1
-            i += threads
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
@@ -138,7 +162,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = make_frames(16)
+    frames = make_frames(64)
     budget = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     for _ in range(args.warmup):
         cpu_path(frames, min(budget, 1.0), cores)
@@ -149,12 +173,13 @@ def run_reference(args, rank):
         vals.append(fps); n_frames += n
     total = time.perf_counter() - t0
     v = n_frames / total
-    sample = "%d steps x %.1f s of G-rect VGA frames on %d host threads, one oracle extractor per thread" % (args.steps, budget, cores)
+    sample = "%d steps x %.1f s of G-rect VGA frames (extract + SearchByProjection vs predecessor) on %d host threads, one oracle extractor per thread" % (args.steps, budget, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C1 extractor: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7", "batch": args.batch},
+        "config": {"workload": "C2 extract+match: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7; each frame matched against its "
+                               "predecessor with SearchByProjection(Cur, Last, th=7)", "batch": args.batch},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference itself cannot be built here (needs OpenCV/Eigen/Pangolin); this is the dependency-free C oracle of its "
@@ -179,7 +204,10 @@ def main():
         return
 
     import torch
+    from orbx import synth
+    from orbx._lib import KP_DTYPE
     from orbx.extractor import ORBextractor
+    from orbx.matcher import LAST_POINT_DTYPE, FrameMatchJob, ORBmatcher, fill_view
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the orbx hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -189,18 +217,85 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     npool = 8                                           # 8 x 64 x 300 KB = 157 MB of inputs > 126 MB L2
-    host = torch.from_numpy(make_frames(npool * B, seed0=100 * rank)).pin_memory()
+    NBASE = 16
+    frames_np = make_frames(npool * B, seed0=100 * rank)
+    host = torch.from_numpy(frames_np).pin_memory()
     dev = host.cuda()
     ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local_rank)
+    mt = ORBmatcher(0.9, True, max_keypoints=ex.capacity, max_points=ex.capacity, max_jobs=B, device=local_rank)
     cap = ex.capacity
     d_kps = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
     d_desc = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
     d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_match = torch.empty(B * cap, dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_sf = torch.from_numpy(ex.GetScaleFactors()).cuda()
     stream = torch.cuda.current_stream()
 
-    def step_device(i):
-        src = dev[(i % npool) * B:(i % npool + 1) * B]
+    def extract_device(slot, src=None):
+        src = dev[slot * B:(slot + 1) * B] if src is None else src
         ex.run_device(src.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
+
+    # ---- setup (untimed): extract the whole pool once to build every frame's "last frame" (its predecessor) ----
+    fx, fy, cx, cy, bf, bb = synth.TUM1_K
+    Z = 4.0
+    last_pts = np.zeros((npool * B, cap), LAST_POINT_DTYPE)      # predecessor's keypoints as map points
+    last_desc = np.zeros((npool * B, cap, 32), np.uint8)
+    last_n = np.zeros(npool * B, np.int32)
+    pose_t = np.zeros((npool * B, 3), np.float32)
+    pool_kps, pool_desc, pool_cnt = [], [], []
+    for slot in range(npool):
+        extract_device(slot)
+        torch.cuda.synchronize()
+        pool_kps.append(d_kps.cpu().numpy().view(KP_DTYPE).reshape(B, cap).copy())
+        pool_desc.append(d_desc.cpu().numpy().reshape(B, cap, 32).copy())
+        pool_cnt.append(d_cnt.cpu().numpy().copy())
+    for g in range(npool * B):
+        p = g - NBASE if g >= NBASE else g               # same base image, previous shift (itself for the first variant)
+        ps, pj = divmod(p, B)
+        n = int(pool_cnt[ps][pj])
+        k = pool_kps[ps][pj][:n]
+        last_n[g] = n
+        last_pts[g, :n]["x"] = (k["x"].astype(np.float64) - cx) / fx * Z
+        last_pts[g, :n]["y"] = (k["y"].astype(np.float64) - cy) / fy * Z
+        last_pts[g, :n]["z"] = Z
+        last_pts[g, :n]["angle"] = k["angle"]
+        last_pts[g, :n]["octave"] = k["octave"]
+        last_pts[g, :n]["valid"] = 1
+        last_pts[g, :n]["blocks"] = 1
+        last_desc[g, :n] = pool_desc[ps][pj][:n]
+        if g >= NBASE:
+            pose_t[g] = (13.0 * Z / fx, 7.0 * Z / fy, 0.0)   # np.roll by (7, 13): the scene moves +13 px in x, +7 px in y
+    h_last_pts = torch.from_numpy(last_pts.view(np.uint8).reshape(npool * B, -1)).pin_memory()
+    h_last_desc = torch.from_numpy(last_desc.reshape(npool * B, -1)).pin_memory()
+    d_last_pts, d_last_desc = h_last_pts.cuda(), h_last_desc.cuda()
+
+    def build_jobs(pts_ptr, pts_stride, desc_ptr, desc_stride, slot):
+        jobs = (FrameMatchJob * B)()
+        for j in range(B):
+            g = slot * B + j
+            J = jobs[j]
+            J.cur.n, J.cur.n_dev = 0, d_cnt.data_ptr() + 4 * j
+            J.cur.keys_un, J.cur.desc = d_kps.data_ptr() + 28 * cap * j, d_desc.data_ptr() + 32 * cap * j
+            J.cur.u_right, J.cur.claimed, J.cur.scale_factors = None, None, d_sf.data_ptr()
+            fill_view(J.cur, (0.0, 0.0, float(W), float(H)), synth.TUM1_K, NLEVELS)
+            J.n_last = int(last_n[g])
+            J.pts, J.last_desc = pts_ptr + pts_stride * j, desc_ptr + desc_stride * j
+            J.Rcw[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1]
+            J.tcw[:] = pose_t[g].tolist()
+            J.forward = J.backward = 0
+            J.th, J.check_ori = 7.0, 1
+            J.match, J.nmatches = d_match.data_ptr() + 4 * cap * j, d_nm.data_ptr() + 4 * j
+        return torch.from_numpy(np.frombuffer(bytes(jobs), np.uint8).copy()).cuda()
+
+    ps_, ds_ = cap * LAST_POINT_DTYPE.itemsize, cap * 32
+    jobs_dev = [build_jobs(d_last_pts.data_ptr() + ps_ * B * s_, ps_, d_last_desc.data_ptr() + ds_ * B * s_, ds_, s_) for s_ in range(npool)]
+
+    def step_device(i):
+        slot = i % npool
+        extract_device(slot)
+        d_match.fill_(-1)
+        mt.search_frames_device(jobs_dev[slot].data_ptr(), B, stream.cuda_stream)
 
     def barrier():
         if dist is not None:
@@ -210,46 +305,72 @@ def main():
     for i in range(Wm):
         step_device(i)
     torch.cuda.synchronize()
-    launches_per_step = ex.last_launches()
+    launches_per_step = ex.last_launches() + 1 + 1      # + fill kernel + matcher kernel
     ex.profile(K)
+    ev_m = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(K):
-        step_device(Wm + i)
+        slot = (Wm + i) % npool
+        extract_device(slot)
+        ev_m[i][0].record(stream)
+        d_match.fill_(-1)
+        mt.search_frames_device(jobs_dev[slot].data_ptr(), B, stream.cuda_stream)
+        ev_m[i][1].record(stream)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop()
     runs, stage_ms = ex.stage_ms()
+    stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / K
     ex.profile(0)
     kp_per_frame = float(d_cnt.float().mean().item())
+    matches_per_frame = float(d_nm.float().mean().item())
 
-    # ---- end to end through the host API: pinned frames in, keypoints/descriptors/counts out, every step ----
-    h_kps = torch.empty(B * cap * 28, dtype=torch.uint8).pin_memory().numpy()
-    h_desc = torch.empty(B * cap * 32, dtype=torch.uint8).pin_memory().numpy()
-    h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory().numpy()
-    hnp = host.numpy()
-    import ctypes as C
-    from orbx._lib import check, lib
-    L = lib()
+    # ---- end to end with HOST buffers: every step copies its frames and last-frame points from pinned host memory,
+    # runs extract + match through the C ABI, and reads keypoints, descriptors, counts and matches back ----
+    e_img = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+    e_pts = torch.empty((B, ps_), dtype=torch.uint8, device="cuda")
+    e_desc = torch.empty((B, ds_), dtype=torch.uint8, device="cuda")
+    h_kps = torch.empty(B * cap * 28, dtype=torch.uint8).pin_memory()
+    h_desc = torch.empty(B * cap * 32, dtype=torch.uint8).pin_memory()
+    h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_match = torch.empty(B * cap, dtype=torch.int32).pin_memory()
+    h_nm = torch.zeros(B, dtype=torch.int32).pin_memory()
+    jobs_e2e = [build_jobs(e_pts.data_ptr(), ps_, e_desc.data_ptr(), ds_, s_) for s_ in range(npool)]
+    h2d = B * W * H + B * ps_ + B * ds_
+    d2h = B * cap * 28 + B * cap * 32 + 4 * B + 4 * B * cap + 4 * B
 
     def step_host(i):
-        base = (i % npool) * B
-        ptrs = (C.c_void_p * B)(*[hnp[base + j].ctypes.data for j in range(B)])
-        check(L.orbx_extractor_run_host(ex._h, ptrs, B, W, H, W, h_kps.ctypes.data, h_desc.ctypes.data, h_cnt.ctypes.data))
+        slot = i % npool
+        e_img.copy_(host[slot * B:(slot + 1) * B], non_blocking=True)
+        e_pts.copy_(h_last_pts[slot * B:(slot + 1) * B], non_blocking=True)
+        e_desc.copy_(h_last_desc[slot * B:(slot + 1) * B], non_blocking=True)
+        extract_device(slot, e_img)
+        d_match.fill_(-1)
+        mt.search_frames_device(jobs_e2e[slot].data_ptr(), B, stream.cuda_stream)
+        h_kps.copy_(d_kps, non_blocking=True)
+        h_desc.copy_(d_desc, non_blocking=True)
+        h_cnt.copy_(d_cnt, non_blocking=True)
+        h_match.copy_(d_match, non_blocking=True)
+        h_nm.copy_(d_nm, non_blocking=True)
+        stream.synchronize()
+        return int(h_nm.sum())
 
     for i in range(Wm):
         step_host(i)
     barrier()
     t0 = time.perf_counter()
+    nm_e2e = 0
     for i in range(K):
-        step_host(Wm + i)
+        nm_e2e += step_host(Wm + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    hnp = frames_np
 
     if dist is not None:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
@@ -269,13 +390,15 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "C1 extractor: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7 (C2 extract+match: matcher not built yet)",
+            "config": {"workload": "C2 extract+match: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7; each frame matched against its "
+                                   "predecessor with SearchByProjection(Cur, Last, th=7) (%.0f matches/frame)" % matches_per_frame,
                        "batch_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective on the data path" % world,
                        "l2": "inputs cycle through a %d-frame pool (%.0f MB > 126 MB L2); per-step working set %.0f MB" % (
                            npool * B, npool * B * W * H / 1e6, B * 3.3),
                        "keypoints_per_frame": kp_per_frame},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": B * cap * 60 + 4 * B,
-                    "api": "orbx_extractor_run_host (synchronous, pinned host buffers)"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "pinned host frames + last-frame points -> H2D -> orbx_extractor_run_device + orbx_match_projection_frame_device -> D2H of "
+                           "keypoints, descriptors, counts, matches; stream-synchronised every step", "matches_per_step": nm_e2e / K},
             "gpu_launches": launches_per_step * K,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -288,13 +411,14 @@ def main():
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            fps, n, dt = cpu_path(hnp[:16], 12.0, cores)
+            fps, n, dt = cpu_path(hnp[:64], 12.0, cores)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "sample": "%d G-rect VGA frames in %.1f s on %d host threads (C oracle, one extractor per thread)" % (n, dt, cores)}
+                                   "sample": "%d G-rect VGA frames (extract + SearchByProjection vs predecessor) in %.1f s on %d host threads (C oracle, one extractor per thread)" % (n, dt, cores)}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    mt.close()
     ex.close()
 
 
