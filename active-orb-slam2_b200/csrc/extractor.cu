@@ -18,6 +18,16 @@ void orbx_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+cudaError_t orbx_raise_smem(const void *kernel) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes);
+}
+
 extern "C" const char *orbx_last_error(void) { return g_err; }
 extern "C" int orbx_version(void) { return 100; }
 

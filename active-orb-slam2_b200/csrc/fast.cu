@@ -197,6 +197,6 @@ orbx_status orbx_fast_init(size_t smem_bytes) {
         orbx_set_error("FAST tile needs %zu bytes of shared memory", smem_bytes);
         return ORBX_ERR_UNSUPPORTED;
     }
-    ORBX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    ORBX_CUDA(ORBX_RAISE_SMEM(k_fast));
     return ORBX_OK;
 }

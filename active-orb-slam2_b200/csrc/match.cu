@@ -13,19 +13,24 @@
 #include "orbx_internal.cuh"
 #include "block_scan.cuh"
 
-#define M_THREADS 256
+#define M_THREADS 1024
+#define M_WARPS (M_THREADS / 32)
 #define GRID_COLS 64   // FRAME_GRID_COLS, Frame.h:38
 #define GRID_ROWS 48   // FRAME_GRID_ROWS, Frame.h:37
 #define NCELL (GRID_COLS * GRID_ROWS)
 #define TH_HIGH 100    // ORBmatcher.cc:36
 #define HISTO_LENGTH 30
+#define M_MAX_KP 8192  // keypoints per frame the shared-memory grid can hold
 
 struct orbx_matcher {
     int device, max_kp, max_pts, max_jobs;
-    int *d_gidx;      // [jobs][max_kp]  keypoint indices in grid-cell order
+    int smem;         // dynamic shared memory of the match kernels
     int *d_choice;    // [jobs][2][max_pts]
     int *d_minclaim;  // [jobs][2][max_kp]
     int *d_owner;     // [jobs][max_kp]
+    int *d_sweeps;    // [jobs] sweeps the claim resolution took (diagnostics)
+    int2 *d_cand;     // [jobs][M_CAND][max_pts] candidate (key, pack) per point, entry-major
+    int *d_lcount;    // [jobs][2][max_pts] candidates per point; overflow list
     // staging of the _host entry points (one job)
     orbx_keypoint *d_keys; uint8_t *d_desc; float *d_uright; uint8_t *d_claimed; float *d_scale;
     void *d_pts; uint8_t *d_ptdesc; int32_t *d_match; int32_t *d_nm; orbx_frame_match_job *d_job;
@@ -33,58 +38,92 @@ struct orbx_matcher {
     int last_launches;
 };
 
+// static part of the shared state; the dynamic part holds the grid (see MatchGrid)
 struct MatchShared {
-    int start[NCELL + 1];
-    int cur[NCELL];
     int warp_tmp[34];
     int hist[HISTO_LENGTH];
     int keep[3];
-    int nacc, nrej;
+    int nacc, nrej, changed, novf;
 };
 
+// The frame's keypoints re-ordered by grid cell (cell = ix*GRID_ROWS + iy, ascending index inside a cell, which
+// is the push_back order of Frame::AssignFeaturesToGrid), resident in shared memory.  Because cells of one grid
+// column are adjacent, the part of a search window that lies in column ix is ONE contiguous range.
+struct MatchGrid {
+    int *start;     // NCELL + 1
+    int *cur;       // NCELL (build only)
+    float *x, *y;   // mvKeysUn[idx].pt
+    int *oct;       // mvKeysUn[idx].octave
+    int *idx;       // original keypoint index
+    __device__ void carve(int *base, int max_kp) {
+        start = base; cur = base + NCELL + 1;
+        x = reinterpret_cast<float *>(cur + NCELL); y = x + max_kp;
+        oct = reinterpret_cast<int *>(y + max_kp); idx = oct + max_kp;
+    }
+};
+static size_t match_smem_bytes(int max_kp) { return sizeof(int) * (2 * NCELL + 1) + (size_t)16 * max_kp; }
+
 __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t *b) {
-    const uint4 b0 = *reinterpret_cast<const uint4 *>(b), b1 = *reinterpret_cast<const uint4 *>(b + 16);
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(b)), b1 = __ldg(reinterpret_cast<const uint4 *>(b + 16));
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-// Frame::AssignFeaturesToGrid: cell = ix*GRID_ROWS + iy, indices ascending inside a cell (push_back order)
-__device__ void grid_build(const orbx_frame_view &F, int n, MatchShared &sh, int *gidx) {
+__device__ __forceinline__ int grid_cell(const orbx_frame_view &F, float kx, float ky) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kx, F.min_x), F.grid_w_inv));   // Frame::PosInGrid
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(ky, F.min_y), F.grid_h_inv));
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return -1;
+    return px * GRID_ROWS + py;
+}
+
+// Frame::AssignFeaturesToGrid
+__device__ void grid_build(const orbx_frame_view &F, int n, MatchShared &sh, MatchGrid &g) {
     const int tid = threadIdx.x;
-    for (int c = tid; c <= NCELL; c += M_THREADS) sh.start[c] = 0;
+    for (int c = tid; c <= NCELL; c += M_THREADS) g.start[c] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += M_THREADS) {
-        const int px = (int)roundf(__fmul_rn(__fsub_rn(F.keys_un[i].x, F.min_x), F.grid_w_inv));   // PosInGrid
-        const int py = (int)roundf(__fmul_rn(__fsub_rn(F.keys_un[i].y, F.min_y), F.grid_h_inv));
-        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
-        atomicAdd(&sh.start[px * GRID_ROWS + py], 1);
+        const int c = grid_cell(F, F.keys_un[i].x, F.keys_un[i].y);
+        if (c >= 0) atomicAdd(&g.start[c], 1);
     }
-    block_excl_scan(sh.start, NCELL + 1, sh.warp_tmp);
-    for (int c = tid; c < NCELL; c += M_THREADS) sh.cur[c] = sh.start[c];
+    block_excl_scan(g.start, NCELL + 1, sh.warp_tmp);
+    for (int c = tid; c < NCELL; c += M_THREADS) g.cur[c] = g.start[c];
     __syncthreads();
     for (int i = tid; i < n; i += M_THREADS) {
-        const int px = (int)roundf(__fmul_rn(__fsub_rn(F.keys_un[i].x, F.min_x), F.grid_w_inv));
-        const int py = (int)roundf(__fmul_rn(__fsub_rn(F.keys_un[i].y, F.min_y), F.grid_h_inv));
-        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
-        gidx[atomicAdd(&sh.cur[px * GRID_ROWS + py], 1)] = i;
+        const int c = grid_cell(F, F.keys_un[i].x, F.keys_un[i].y);
+        if (c >= 0) g.idx[atomicAdd(&g.cur[c], 1)] = i;
     }
     __syncthreads();
     for (int c = tid; c < NCELL; c += M_THREADS) {
-        const int b = sh.start[c], e = sh.start[c + 1];
+        const int b = g.start[c], e = g.start[c + 1];
         for (int i = b + 1; i < e; i++) {
-            const int k = gidx[i];
+            const int k = g.idx[i];
             int j = i - 1;
-            while (j >= b && gidx[j] > k) { gidx[j + 1] = gidx[j]; j--; }
-            gidx[j + 1] = k;
+            while (j >= b && g.idx[j] > k) { g.idx[j + 1] = g.idx[j]; j--; }
+            g.idx[j + 1] = k;
         }
+    }
+    __syncthreads();
+    for (int j = tid; j < g.start[NCELL]; j += M_THREADS) {
+        const orbx_keypoint &kp = F.keys_un[g.idx[j]];
+        g.x[j] = kp.x; g.y[j] = kp.y; g.oct[j] = kp.octave;
     }
     __syncthreads();
 }
 
-// Frame::GetFeaturesInArea: calls fn(idx) for every keypoint of the window, in the reference's order
+// Frame::GetFeaturesInArea, warp-cooperative, in two phases so that the global loads of a window are issued
+// together instead of one grid column at a time:
+//   1. lanes scan the window column by column in shared memory and compact the keypoints that pass the level and
+//      |dx|,|dy| < r tests into a per-warp list of (grid position, seq);
+//   2. whenever 32 entries are waiting (and at the end) every lane takes one entry and ALL lanes call
+//      fn(valid, keypoint index, seq).
+// seq increases in the reference's visiting order (column by column, cell by cell, push order), so the reference's
+// "first strict minimum" is the minimum of (dist, seq).
+#define M_LIST 64
 template <class Fn>
-__device__ __forceinline__ void features_in_area(const orbx_frame_view &F, const MatchShared &sh, const int *gidx, float x,
-                                                 float y, float r, int minLevel, int maxLevel, Fn fn) {
+__device__ __forceinline__ void features_in_area(const orbx_frame_view &F, const MatchGrid &g, int2 *list, float x, float y,
+                                                 float r, int minLevel, int maxLevel, Fn fn) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const float dx0 = __fsub_rn(x, F.min_x), dy0 = __fsub_rn(y, F.min_y);
     int x0 = (int)floorf(__fmul_rn(__fsub_rn(dx0, r), F.grid_w_inv)); x0 = max(0, x0);
     if (x0 >= GRID_COLS) return;
@@ -95,73 +134,175 @@ __device__ __forceinline__ void features_in_area(const orbx_frame_view &F, const
     int y1 = (int)ceilf(__fmul_rn(__fadd_rn(dy0, r), F.grid_h_inv)); y1 = min(GRID_ROWS - 1, y1);
     if (y1 < 0) return;
     const bool check = (minLevel > 0) || (maxLevel >= 0);
-    for (int ix = x0; ix <= x1; ix++)
-        for (int iy = y0; iy <= y1; iy++) {
-            const int c = ix * GRID_ROWS + iy;
-            for (int j = sh.start[c]; j < sh.start[c + 1]; j++) {
-                const int idx = gidx[j];
-                const orbx_keypoint &kp = F.keys_un[idx];
-                if (check) {
-                    const int oct = kp.octave;
-                    if (oct < minLevel) continue;
-                    if (maxLevel >= 0 && oct > maxLevel) continue;
-                }
-                if (fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r) fn(idx);
+    int seq0 = 0, count = 0;
+    for (int ix = x0; ix <= x1; ix++) {
+        const int s = g.start[ix * GRID_ROWS + y0], e = g.start[ix * GRID_ROWS + y1 + 1];
+        for (int jb = s; jb < e; jb += 32) {
+            const int j = jb + lane;
+            bool pass = j < e;
+            if (pass && check) {
+                const int oct = g.oct[j];
+                pass = oct >= minLevel && !(maxLevel >= 0 && oct > maxLevel);
+            }
+            if (pass) pass = fabsf(__fsub_rn(g.x[j], x)) < r && fabsf(__fsub_rn(g.y[j], y)) < r;
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass) list[count + __popc(m & lt)] = make_int2(j, seq0 + (j - s));
+            count += __popc(m);
+            __syncwarp();
+            if (count >= 32) {
+                const int2 c = list[lane];
+                fn(true, g.idx[c.x], c.y);
+                __syncwarp();
+                if (lane < count - 32) list[lane] = list[lane + 32];   // count - 32 < 32: no overlap
+                count -= 32;
+                __syncwarp();
             }
         }
+        seq0 += e - s;
+    }
+    if (count > 0) {
+        const bool valid = lane < count;
+        const int2 c = valid ? list[lane] : make_int2(0, 0);
+        fn(valid, valid ? g.idx[c.x] : 0, c.y);
+    }
+    __syncwarp();
 }
 
-// sweeps of "choose among the keypoints not claimed by a smaller index" until nothing changes
+__device__ __forceinline__ unsigned warp_min(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// A candidate is (key, pack): key = dist << 22 | seq (unique per point, ordered like the reference's scan),
+// pack = keypoint index | octave << 16.  An Eval provides
+//   candidates(i, emit)  warp-cooperative enumeration of the candidates of point i that pass every test that does
+//                        not depend on claims; ALL lanes call emit(valid, key, pack) once per round of <= 32
+//   decide(k1,p1,k2,p2)  the reference's accept rule from the two smallest unclaimed candidates
+//   blocks(i)            Observations() > 0 of point i
+struct Best2 {
+    unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
+    int p1 = -1, p2 = -1;
+    __device__ __forceinline__ void add(unsigned key, int pack) {
+        if (key < k1) { k2 = k1; p2 = p1; k1 = key; p1 = pack; }
+        else if (key < k2) { k2 = key; p2 = pack; }
+    }
+};
+
+// claim-dependent choice of point i by a whole warp (used for points whose candidate list overflowed)
 template <class Eval>
-__device__ void resolve_claims(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int max_pts,
-                               int max_kp, Eval eval, int &final_buf) {
-    const int tid = threadIdx.x;
+__device__ int eval_warp(const Eval &ev, int i, const int *minclaim) {
+    Best2 b;
+    ev.candidates(i, [&](bool valid, unsigned key, int pack) {
+        if (valid && minclaim[pack & 0xffff] >= i) b.add(key, pack);
+    });
+    const unsigned w1 = warp_min(b.k1);
+    if (w1 == 0xffffffffu) return -1;
+    const int src = __ffs(__ballot_sync(0xffffffffu, b.k1 == w1)) - 1;
+    const int p1 = __shfl_sync(0xffffffffu, b.p1, src);
+    const bool me = (threadIdx.x & 31) == src;
+    const unsigned cand = me ? b.k2 : b.k1;
+    const int candp = me ? b.p2 : b.p1;
+    const unsigned w2 = warp_min(cand);
+    int p2 = -1;
+    if (w2 != 0xffffffffu) p2 = __shfl_sync(0xffffffffu, candp, __ffs(__ballot_sync(0xffffffffu, cand == w2)) - 1);
+    return ev.decide(w1, p1, w2, p2);
+}
+
+#define M_CAND 64   // candidates kept per point; points with more fall back to eval_warp in every sweep
+
+// The reference's sequential claim semantics as a fixed point.  Candidate lists are built once (they do not depend
+// on claims); every sweep then lets each point pick among the candidates not claimed by a smaller index in the
+// previous sweep, until no choice changes.
+template <class Eval>
+__device__ void resolve_claims(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int2 *cand,
+                               int *lcount, int *ovf, int max_pts, int max_kp, MatchShared &sh, const Eval &ev, int &final_buf) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     int *mc[2] = {minclaim2, minclaim2 + max_kp};
     int *ch[2] = {choice2, choice2 + max_pts};
     for (int k = tid; k < n_kp; k += M_THREADS) mc[0][k] = (claimed && claimed[k]) ? -1 : 0x7fffffff;
     for (int i = tid; i < n_pts; i += M_THREADS) ch[0][i] = -2;
+    if (tid == 0) sh.novf = 0;
     __syncthreads();
-    int cur = 0;
+    for (int i = warp; i < n_pts; i += M_WARPS) {
+        int cnt = 0;
+        ev.candidates(i, [&](bool valid, unsigned key, int pack) {
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            const int pos = cnt + __popc(m & lt);
+            if (valid && pos < M_CAND) cand[(size_t)pos * max_pts + i] = make_int2((int)key, pack);
+            cnt += __popc(m);
+        });
+        if (lane == 0) {
+            lcount[i] = cnt;
+            if (cnt > M_CAND) ovf[atomicAdd(&sh.novf, 1)] = i;
+        }
+    }
+    __syncthreads();
+    const int novf = sh.novf;
+    int cur = 0, sweeps = 0;
     for (int sweep = 0; sweep <= n_pts + 1; sweep++) {
         const int nxt = cur ^ 1;
         int changed = 0;
+        const int *mcc = mc[cur];
         for (int k = tid; k < n_kp; k += M_THREADS) mc[nxt][k] = (claimed && claimed[k]) ? -1 : 0x7fffffff;
         for (int i = tid; i < n_pts; i += M_THREADS) {
-            const int c = eval(i, mc[cur]);
-            ch[nxt][i] = c;
+            const int cnt = lcount[i];
+            if (cnt > M_CAND) continue;
+            Best2 b;
+            for (int e = 0; e < cnt; e++) {
+                const int2 c = cand[(size_t)e * max_pts + i];
+                if (mcc[c.y & 0xffff] >= i) b.add((unsigned)c.x, c.y);
+            }
+            const int c = b.k1 == 0xffffffffu ? -1 : ev.decide(b.k1, b.p1, b.k2, b.p2);
             changed |= c != ch[cur][i];
+            ch[nxt][i] = c;
+        }
+        for (int o = warp; o < novf; o += M_WARPS) {
+            const int i = ovf[o];
+            const int c = eval_warp(ev, i, mcc);
+            if (lane == 0) {
+                changed |= c != ch[cur][i];
+                ch[nxt][i] = c;
+            }
         }
         __syncthreads();
         for (int i = tid; i < n_pts; i += M_THREADS) {
             const int c = ch[nxt][i];
-            if (c >= 0) atomicMin(&mc[nxt][c], eval.blocks(i) ? i : 0x7fffffff);
+            if (c >= 0 && ev.blocks(i)) atomicMin(&mc[nxt][c], i);
         }
         cur = nxt;
+        sweeps++;
         if (!__syncthreads_or(changed)) break;
     }
     final_buf = cur;
+    if (tid == 0) sh.changed = sweeps;
 }
 
 // ---- SearchByProjection(CurrentFrame, LastFrame, th, bMono) ------------------------------------------------------
 struct FrameEval {
     const orbx_frame_match_job &J;
     const orbx_frame_view &F;
-    const MatchShared &sh;
-    const int *gidx;
+    const MatchGrid &g;
+    int2 *list;      // this warp's compaction list (M_LIST entries)
     __device__ bool blocks(int i) const { return J.pts[i].blocks != 0; }
-    __device__ int operator()(int i, const int *minclaim) const {
+    __device__ int decide(unsigned k1, int p1, unsigned, int) const {
+        return (k1 >> 22) <= TH_HIGH ? (p1 & 0xffff) : -1;        // ORBmatcher.cc:1421
+    }
+    template <class Emit>
+    __device__ void candidates(int i, Emit emit) const {
         const orbx_last_point p = J.pts[i];
-        if (!p.valid) return -1;
+        if (!p.valid) return;
         const float *R = J.Rcw, *t = J.tcw;
         const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], p.x), __fmul_rn(R[1], p.y)), __fmul_rn(R[2], p.z)), t[0]);
         const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], p.x), __fmul_rn(R[4], p.y)), __fmul_rn(R[5], p.z)), t[1]);
         const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], p.x), __fmul_rn(R[7], p.y)), __fmul_rn(R[8], p.z)), t[2]);
         const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)zc));     // const float invzc = 1.0/x3Dc.at<float>(2)
-        if (invzc < 0) return -1;
+        if (invzc < 0) return;
         const float u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, xc), invzc), F.cx);
         const float v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, yc), invzc), F.cy);
-        if (u < F.min_x || u > F.max_x) return -1;
-        if (v < F.min_y || v > F.max_y) return -1;
+        if (u < F.min_x || u > F.max_x) return;
+        if (v < F.min_y || v > F.max_y) return;
         const int oct = p.octave;
         const float radius = __fmul_rn(J.th, F.scale_factors[oct]);
         int minL, maxL;
@@ -169,38 +310,41 @@ struct FrameEval {
         else if (J.backward) { minL = 0; maxL = oct; }
         else { minL = oct - 1; maxL = oct + 1; }
         const uint8_t *d = J.last_desc + (size_t)32 * i;
-        const uint4 d0 = *reinterpret_cast<const uint4 *>(d), d1 = *reinterpret_cast<const uint4 *>(d + 16);
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
         const float ur = __fsub_rn(u, __fmul_rn(F.bf, invzc));
-        int bestDist = 256, bestIdx = -1;
-        features_in_area(F, sh, gidx, u, v, radius, minL, maxL, [&](int i2) {
-            if (minclaim[i2] < i) return;
-            if (F.u_right) {
-                const float urk = F.u_right[i2];
-                if (urk > 0 && fabsf(__fsub_rn(ur, urk)) > radius) return;
+        features_in_area(F, g, list, u, v, radius, minL, maxL, [&](bool valid, int i2, int seq) {
+            unsigned key = 0;
+            if (valid) {
+                const float urk = F.u_right ? F.u_right[i2] : -1.f;
+                key = ((unsigned)hamming256(d0, d1, F.desc + (size_t)32 * i2) << 22) | (unsigned)seq;
+                if (urk > 0 && fabsf(__fsub_rn(ur, urk)) > radius) valid = false;      // ORBmatcher.cc:1405-1411
             }
-            const int dist = hamming256(d0, d1, F.desc + (size_t)32 * i2);
-            if (dist < bestDist) { bestDist = dist; bestIdx = i2; }
+            emit(valid, key, i2);
         });
-        return bestDist <= TH_HIGH ? bestIdx : -1;
     }
 };
 
 __global__ void __launch_bounds__(M_THREADS)
-k_match_frame(const orbx_frame_match_job *__restrict__ jobs, int *__restrict__ gidx_all, int *__restrict__ choice_all,
-              int *__restrict__ minclaim_all, int *__restrict__ owner_all, int max_kp, int max_pts) {
+k_match_frame(const orbx_frame_match_job *__restrict__ jobs, int *__restrict__ choice_all, int *__restrict__ minclaim_all,
+              int *__restrict__ owner_all, int *__restrict__ sweeps_all, int2 *__restrict__ cand_all, int *__restrict__ lcount_all,
+              int max_kp, int max_pts) {
+    extern __shared__ __align__(16) int dyn[];
     __shared__ MatchShared sh;
     __shared__ orbx_frame_match_job J;
+    __shared__ MatchGrid g;
     const int tid = threadIdx.x, job = blockIdx.x;
-    if (tid == 0) J = jobs[job];
+    if (tid == 0) { J = jobs[job]; g.carve(dyn, max_kp); }
     __syncthreads();
     const orbx_frame_view &F = J.cur;
     const int n = min(F.n_dev ? *F.n_dev : F.n, max_kp), n_pts = min(J.n_last, max_pts);
-    int *gidx = gidx_all + (size_t)job * max_kp, *choice2 = choice_all + (size_t)job * 2 * max_pts;
+    int *choice2 = choice_all + (size_t)job * 2 * max_pts;
     int *minclaim2 = minclaim_all + (size_t)job * 2 * max_kp, *owner = owner_all + (size_t)job * max_kp;
-    grid_build(F, n, sh, gidx);
-    FrameEval ev{J, F, sh, gidx};
+    grid_build(F, n, sh, g);
+    __shared__ int2 lists[M_WARPS][M_LIST];
+    FrameEval ev{J, F, g, lists[tid >> 5]};
     int fb;
-    resolve_claims(n, n_pts, F.claimed, choice2, minclaim2, max_pts, max_kp, ev, fb);
+    resolve_claims(n, n_pts, F.claimed, choice2, minclaim2, cand_all + (size_t)job * M_CAND * max_pts,
+                   lcount_all + (size_t)job * 2 * max_pts, lcount_all + (size_t)job * 2 * max_pts + max_pts, max_pts, max_kp, sh, ev, fb);
     const int *choice = choice2 + (size_t)fb * max_pts;
     // owner = last point that wrote mvpMapPoints[k]; rotation histogram over every accepted point (:1431-1446)
     for (int k = tid; k < n; k += M_THREADS) owner[k] = -1;
@@ -253,7 +397,7 @@ k_match_frame(const orbx_frame_match_job *__restrict__ jobs, int *__restrict__ g
         if (nrej) atomicAdd(&sh.nrej, nrej);
     }
     __syncthreads();
-    if (tid == 0) *J.nmatches = sh.nacc - sh.nrej;
+    if (tid == 0) { *J.nmatches = sh.nacc - sh.nrej; sweeps_all[job] = sh.changed; }
 }
 
 // ---- SearchByProjection(Frame &F, vpMapPoints, th) ------------------------------------------------------------
@@ -269,53 +413,63 @@ struct PointsJob {
 struct PointsEval {
     const PointsJob &J;
     const orbx_frame_view &F;
-    const MatchShared &sh;
-    const int *gidx;
+    const MatchGrid &g;
+    int2 *list;
     __device__ bool blocks(int i) const { return J.pts[i].blocks != 0; }
-    __device__ int operator()(int i, const int *minclaim) const {
+    // The reference keeps (best, second) in visiting order (ORBmatcher.cc:101-114); that equals: best = first
+    // occurrence of the minimum, second = first occurrence of the minimum among the rest, i.e. the two smallest keys.
+    __device__ int decide(unsigned k1, int p1, unsigned k2, int p2) const {
+        const int bestDist = (int)(k1 >> 22);
+        if (bestDist > TH_HIGH) return -1;
+        const int bestLevel = p1 >> 16;
+        const int bestDist2 = k2 == 0xffffffffu ? 256 : (int)(k2 >> 22), bestLevel2 = k2 == 0xffffffffu ? -1 : (p2 >> 16);
+        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2)) return -1;   // :118-121
+        return p1 & 0xffff;
+    }
+    template <class Emit>
+    __device__ void candidates(int i, Emit emit) const {
         const orbx_track_point p = J.pts[i];
-        if (!p.in_view) return -1;
+        if (!p.in_view) return;
         float r = p.view_cos > 0.998f ? 2.5f : 4.0f;             // RadiusByViewingCos
         if (J.th != 1.0f) r = __fmul_rn(r, J.th);
         const float rs = __fmul_rn(r, F.scale_factors[p.level]);
         const uint8_t *d = J.pt_desc + (size_t)32 * i;
-        const uint4 d0 = *reinterpret_cast<const uint4 *>(d), d1 = *reinterpret_cast<const uint4 *>(d + 16);
-        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-        features_in_area(F, sh, gidx, p.proj_x, p.proj_y, rs, p.level - 1, p.level, [&](int idx) {
-            if (minclaim[idx] < i) return;
-            if (F.u_right) {
-                const float urk = F.u_right[idx];
-                if (urk > 0 && fabsf(__fsub_rn(p.proj_xr, urk)) > rs) return;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
+        features_in_area(F, g, list, p.proj_x, p.proj_y, rs, p.level - 1, p.level, [&](bool valid, int idx, int seq) {
+            unsigned key = 0;
+            int pack = 0;
+            if (valid) {
+                const float urk = F.u_right ? F.u_right[idx] : -1.f;
+                pack = idx | (F.keys_un[idx].octave << 16);
+                key = ((unsigned)hamming256(d0, d1, F.desc + (size_t)32 * idx) << 22) | (unsigned)seq;
+                if (urk > 0 && fabsf(__fsub_rn(p.proj_xr, urk)) > rs) valid = false;   // ORBmatcher.cc:91-96
             }
-            const int dist = hamming256(d0, d1, F.desc + (size_t)32 * idx);
-            if (dist < bestDist) {
-                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.keys_un[idx].octave; bestIdx = idx;
-            } else if (dist < bestDist2) {
-                bestLevel2 = F.keys_un[idx].octave; bestDist2 = dist;
-            }
+            emit(valid, key, pack);
         });
-        if (bestDist > TH_HIGH) return -1;
-        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2)) return -1;
-        return bestIdx;
     }
 };
 
 __global__ void __launch_bounds__(M_THREADS)
-k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ gidx_all, int *__restrict__ choice_all,
-               int *__restrict__ minclaim_all, int *__restrict__ owner_all, int max_kp, int max_pts) {
+k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ choice_all, int *__restrict__ minclaim_all,
+               int *__restrict__ owner_all, int *__restrict__ sweeps_all, int2 *__restrict__ cand_all, int *__restrict__ lcount_all,
+              int max_kp, int max_pts) {
+    extern __shared__ __align__(16) int dyn[];
     __shared__ MatchShared sh;
     __shared__ PointsJob J;
+    __shared__ MatchGrid g;
     const int tid = threadIdx.x, job = blockIdx.x;
-    if (tid == 0) J = jobs[job];
+    if (tid == 0) { J = jobs[job]; g.carve(dyn, max_kp); }
     __syncthreads();
     const orbx_frame_view &F = J.F;
     const int n = min(F.n_dev ? *F.n_dev : F.n, max_kp), n_pts = min(J.n_pts, max_pts);
-    int *gidx = gidx_all + (size_t)job * max_kp, *choice2 = choice_all + (size_t)job * 2 * max_pts;
+    int *choice2 = choice_all + (size_t)job * 2 * max_pts;
     int *minclaim2 = minclaim_all + (size_t)job * 2 * max_kp, *owner = owner_all + (size_t)job * max_kp;
-    grid_build(F, n, sh, gidx);
-    PointsEval ev{J, F, sh, gidx};
+    grid_build(F, n, sh, g);
+    __shared__ int2 lists[M_WARPS][M_LIST];
+    PointsEval ev{J, F, g, lists[tid >> 5]};
     int fb;
-    resolve_claims(n, n_pts, F.claimed, choice2, minclaim2, max_pts, max_kp, ev, fb);
+    resolve_claims(n, n_pts, F.claimed, choice2, minclaim2, cand_all + (size_t)job * M_CAND * max_pts,
+                   lcount_all + (size_t)job * 2 * max_pts, lcount_all + (size_t)job * 2 * max_pts + max_pts, max_pts, max_kp, sh, ev, fb);
     const int *choice = choice2 + (size_t)fb * max_pts;
     for (int k = tid; k < n; k += M_THREADS) owner[k] = -1;
     if (tid == 0) sh.nacc = 0;
@@ -330,7 +484,7 @@ k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ gidx_all, i
     if (nacc) atomicAdd(&sh.nacc, nacc);
     __syncthreads();
     for (int k = tid; k < n; k += M_THREADS) if (owner[k] >= 0) J.match[k] = owner[k];
-    if (tid == 0) *J.nmatches = sh.nacc;
+    if (tid == 0) { *J.nmatches = sh.nacc; sweeps_all[job] = sh.changed; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -349,7 +503,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
-    cudaFree(m->d_gidx); cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_keys);
+    cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_sweeps); cudaFree(m->d_cand); cudaFree(m->d_lcount); cudaFree(m->d_keys);
     cudaFree(m->d_desc); cudaFree(m->d_uright); cudaFree(m->d_claimed); cudaFree(m->d_scale); cudaFree(m->d_pts);
     cudaFree(m->d_ptdesc); cudaFree(m->d_match); cudaFree(m->d_nm); cudaFree(m->d_job);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -362,6 +516,10 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     if (max_keypoints < 1 || max_points < 1 || max_jobs < 1) {
         orbx_set_error("orbx_matcher_create: bad argument");
         return ORBX_ERR_INVALID;
+    }
+    if (max_keypoints > M_MAX_KP) {
+        orbx_set_error("orbx_matcher_create: at most %d keypoints per frame fit the shared-memory grid", M_MAX_KP);
+        return ORBX_ERR_UNSUPPORTED;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -382,10 +540,12 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     const size_t ptsz = sizeof(orbx_track_point) > sizeof(orbx_last_point) ? sizeof(orbx_track_point) : sizeof(orbx_last_point);
     cudaError_t ce = cudaSuccess;
 #define TRY(x) if (ce == cudaSuccess) ce = (x)
-    TRY(cudaMalloc((void **)&m->d_gidx, sizeof(int) * kp * jb));
     TRY(cudaMalloc((void **)&m->d_choice, sizeof(int) * 2 * pt * jb));
     TRY(cudaMalloc((void **)&m->d_minclaim, sizeof(int) * 2 * kp * jb));
     TRY(cudaMalloc((void **)&m->d_owner, sizeof(int) * kp * jb));
+    TRY(cudaMalloc((void **)&m->d_sweeps, sizeof(int) * jb));
+    TRY(cudaMalloc((void **)&m->d_cand, sizeof(int2) * M_CAND * pt * jb));
+    TRY(cudaMalloc((void **)&m->d_lcount, sizeof(int) * 2 * pt * jb));
     TRY(cudaMalloc((void **)&m->d_keys, sizeof(orbx_keypoint) * kp));
     TRY(cudaMalloc((void **)&m->d_desc, 32 * kp));
     TRY(cudaMalloc((void **)&m->d_uright, sizeof(float) * kp));
@@ -397,6 +557,9 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     TRY(cudaMalloc((void **)&m->d_nm, sizeof(int32_t)));
     TRY(cudaMalloc((void **)&m->d_job, sizeof(orbx_frame_match_job) > sizeof(PointsJob) ? sizeof(orbx_frame_match_job) : sizeof(PointsJob)));
     TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    m->smem = (int)match_smem_bytes(max_keypoints);
+    TRY(ORBX_RAISE_SMEM(k_match_frame));
+    TRY(ORBX_RAISE_SMEM(k_match_points));
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_matcher_create: %s", cudaGetErrorString(ce));
@@ -443,8 +606,8 @@ extern "C" orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const
     ORBX_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
     if (n_jobs == 0) return ORBX_OK;
-    k_match_frame<<<n_jobs, M_THREADS, 0, (cudaStream_t)stream>>>(d_jobs, m->d_gidx, m->d_choice, m->d_minclaim, m->d_owner,
-                                                                  m->max_kp, m->max_pts);
+    k_match_frame<<<n_jobs, M_THREADS, m->smem, (cudaStream_t)stream>>>(d_jobs, m->d_choice, m->d_minclaim, m->d_owner, m->d_sweeps, m->d_cand, m->d_lcount, m->max_kp,
+                                                                        m->max_pts);
     m->last_launches = 1;
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
@@ -515,8 +678,8 @@ extern "C" orbx_status orbx_match_projection_points_host(orbx_matcher *m, const 
     J.th = th; J.nnratio = nnratio;
     J.match = m->d_match; J.nmatches = m->d_nm;
     ORBX_CUDA(cudaMemcpyAsync(m->d_job, &J, sizeof(J), cudaMemcpyHostToDevice, s));
-    k_match_points<<<1, M_THREADS, 0, s>>>((const PointsJob *)m->d_job, m->d_gidx, m->d_choice, m->d_minclaim, m->d_owner,
-                                           m->max_kp, m->max_pts);
+    k_match_points<<<1, M_THREADS, m->smem, s>>>((const PointsJob *)m->d_job, m->d_choice, m->d_minclaim, m->d_owner, m->d_sweeps, m->d_cand, m->d_lcount, m->max_kp,
+                                                 m->max_pts);
     m->last_launches = 1;
     ORBX_CUDA(cudaGetLastError());
     if (F->n) ORBX_CUDA(cudaMemcpyAsync(match, m->d_match, sizeof(int32_t) * F->n, cudaMemcpyDeviceToHost, s));
@@ -526,3 +689,11 @@ extern "C" orbx_status orbx_match_projection_points_host(orbx_matcher *m, const 
 }
 
 extern "C" int orbx_matcher_last_launches(const orbx_matcher *m) { return m ? m->last_launches : 0; }
+
+extern "C" orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs) {
+    if (!m || !out || n_jobs < 0 || n_jobs > m->max_jobs) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(m->device));
+    ORBX_CUDA(cudaDeviceSynchronize());
+    ORBX_CUDA(cudaMemcpy(out, m->d_sweeps, sizeof(int32_t) * n_jobs, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}

@@ -253,6 +253,6 @@ orbx_status orbx_launch_octree(orbx_extractor *e, int batch, cudaStream_t s) {
 }
 
 orbx_status orbx_octree_init(int smem_bytes) {
-    ORBX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    ORBX_CUDA(ORBX_RAISE_SMEM(k_octree));
     return ORBX_OK;
 }

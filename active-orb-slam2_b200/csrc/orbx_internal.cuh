@@ -15,6 +15,12 @@
 #define ORBX_NINI_MAX 16      // initial quadtree nodes per level (image aspect up to 16:1)
 #define ORBX_OCT_CELLS 4096   // counting-sort cells of the quadtree kernel
 #define ORBX_FAST_CELLS 8     // max cells per FAST tile
+// opt-in dynamic shared memory ceiling of sm_100 (227 KB).  The attribute is per kernel, not per handle, so it is
+// always raised to the ceiling: a second handle with smaller needs must not lower it under a live one.
+#define ORBX_SMEM_OPTIN (227 * 1024)
+// raise the kernel's dynamic shared memory limit to everything the device allows next to its static part
+#define ORBX_RAISE_SMEM(kernel) orbx_raise_smem((const void *)(kernel))
+cudaError_t orbx_raise_smem(const void *kernel);
 
 void orbx_set_error(const char *fmt, ...);
 

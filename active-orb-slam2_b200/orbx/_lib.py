@@ -67,5 +67,6 @@ def _declare(L):
     L.orbx_match_projection_frame_host.argtypes = [vp, vp, i, vp, vp, vp, vp, i, i, f, i, vp, vp]
     L.orbx_match_projection_frame_device.argtypes = [vp, vp, i, vp]
     L.orbx_matcher_last_launches.argtypes = [vp]
+    L.orbx_matcher_last_sweeps.argtypes = [vp, vp, i]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -115,3 +115,8 @@ class ORBmatcher:
     def search_frames_device(self, d_jobs, n_jobs, stream=0):
         """batched device-resident SearchByProjection(Cur, Last): d_jobs = device pointer to orbx_frame_match_job[n_jobs]"""
         check(self._L.orbx_match_projection_frame_device(self._h, d_jobs, n_jobs, stream))
+
+    def last_sweeps(self, n_jobs=1):
+        out = np.zeros(n_jobs, np.int32)
+        check(self._L.orbx_matcher_last_sweeps(self._h, out.ctypes.data, n_jobs))
+        return out

@@ -329,6 +329,7 @@ def main():
     ex.profile(0)
     kp_per_frame = float(d_cnt.float().mean().item())
     matches_per_frame = float(d_nm.float().mean().item())
+    match_sweeps = mt.last_sweeps(B).tolist()
 
     # ---- end to end with HOST buffers: every step copies its frames and last-frame points from pinned host memory,
     # runs extract + match through the C ABI, and reads keypoints, descriptors, counts and matches back ----
@@ -395,7 +396,7 @@ def main():
                        "batch_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective on the data path" % world,
                        "l2": "inputs cycle through a %d-frame pool (%.0f MB > 126 MB L2); per-step working set %.0f MB" % (
                            npool * B, npool * B * W * H / 1e6, B * 3.3),
-                       "keypoints_per_frame": kp_per_frame},
+                       "keypoints_per_frame": kp_per_frame, "match_sweeps_max": max(match_sweeps), "match_sweeps_mean": sum(match_sweeps) / B},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pinned host frames + last-frame points -> H2D -> orbx_extractor_run_device + orbx_match_projection_frame_device -> D2H of "
                            "keypoints, descriptors, counts, matches; stream-synchronised every step", "matches_per_step": nm_e2e / K},

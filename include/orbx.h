@@ -191,6 +191,8 @@ typedef struct {
 orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
                                                void *stream);
 int orbx_matcher_last_launches(const orbx_matcher *m);
+/* diagnostics: how many sweeps the claim resolution of each job of the last call took (synchronises) */
+orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs);
 
 #ifdef __cplusplus
 }

@@ -119,3 +119,18 @@ def test_batched_device_jobs(matcher):
         n_ref, m_ref = refs[j]
         assert keep[10 * j + 9].item() == n_ref
         assert np.array_equal(keep[10 * j + 8].cpu().numpy(), m_ref)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_dense_windows_overflow_path(matcher, seed):
+    """small image, many keypoints, large radius: windows hold hundreds of candidates (> the per-point list) """
+    rng = np.random.default_rng(300 + seed)
+    cur = synth.random_frame(rng, 3000, w=320, h=240)
+    pts, desc, R, t = synth.last_frame_points(rng, cur, 1500, dup_frac=0.3)
+    n_ref, m_ref = O.search_by_projection_frame(cur, pts, desc, R, t, False, False, 15.0, True)
+    n, m = matcher.SearchByProjectionLast(cur, pts, desc, R, t, False, False, 15.0)
+    assert n == n_ref and np.array_equal(m, m_ref)
+    tp, tdesc = synth.track_points(rng, cur, 1500, dup_frac=0.3)
+    n_ref, m_ref = O.search_by_projection_points(cur, tp, tdesc, 5.0, 0.8)
+    n, m = matcher.SearchByProjection(cur, tp, tdesc, 5.0)
+    assert n == n_ref and np.array_equal(m, m_ref)
