@@ -189,3 +189,75 @@ def track_points(rng, cur, n_pts, dup_frac=0.15):
     pts["blocks"] = rng.random(n_pts) > 0.1
     desc = flip_bits(rng, cur["desc"][tgt], rng.integers(0, 110, n_pts))
     return pts, desc
+
+
+# ---- local bundle adjustment problems -----------------------------------------------------------
+def _quat_from_R(R):
+    """(x, y, z, w), w >= 0"""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s])
+    else:
+        i = int(np.argmax(np.diag(R))); j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[i] = 0.25 * s; q[3] = (R[k, j] - R[j, k]) / s; q[j] = (R[j, i] + R[i, j]) / s; q[k] = (R[k, i] + R[i, k]) / s
+    if q[3] < 0:
+        q = -q
+    return q / np.linalg.norm(q)
+
+
+def _rot(axis, a):
+    c, s = np.cos(a), np.sin(a)
+    return {0: np.array([[1, 0, 0], [0, c, -s], [0, s, c]]), 1: np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]),
+            2: np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])}[axis]
+
+
+def lba_problem(seed, n_kf=20, n_pts=3000, obs_per_pt=4, stereo=False, n_fixed=0, outlier_frac=0.05, w=640, h=480):
+    """P keyframes looking down +z at L points in a 6 x 4 x 6 m box 2-8 m ahead; every point is observed by
+    `obs_per_pt` keyframes; pixel noise N(0, sigma_octave^2), 5 % outliers (+20 px); poses perturbed by 1 cm / 0.5 deg,
+    points by 2 cm.  The first n_fixed keyframes are fixed.  Returns a dict of numpy arrays (orbx_lba_problem fields)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf, _ = TUM1_K
+    Rs, ts = [], []
+    for k in range(n_kf):
+        R = _rot(1, rng.uniform(-0.15, 0.15)) @ _rot(0, rng.uniform(-0.05, 0.05))
+        c = np.array([rng.uniform(-1.0, 1.0), rng.uniform(-0.3, 0.3), rng.uniform(-0.5, 0.5)])   # camera centre
+        Rs.append(R.T); ts.append(-R.T @ c)                                                     # Tcw
+    X = np.stack([rng.uniform(-3, 3, n_pts), rng.uniform(-2, 2, n_pts), rng.uniform(2, 8, n_pts)], 1)
+    e_kf, e_pt, e_obs, e_is2, e_st = [], [], [], [], []
+    sf = scale_factors(8)
+    for l in range(n_pts):
+        seen = 0
+        for k in rng.permutation(n_kf):
+            if seen == obs_per_pt:
+                break
+            Xc = Rs[k] @ X[l] + ts[k]
+            if Xc[2] < 0.5:
+                continue
+            u, v = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
+            if not (0 <= u < w and 0 <= v < h):
+                continue
+            octv = int(rng.integers(0, 8))
+            sig = float(sf[octv])
+            du, dv = rng.normal(0, sig, 2)
+            if rng.random() < outlier_frac:
+                du += 20.0
+            ur = u + du - bf / Xc[2] + rng.normal(0, sig)
+            e_kf.append(k); e_pt.append(l); e_obs.append((np.float32(u + du), np.float32(v + dv), np.float32(ur)))
+            e_is2.append(np.float32(1.0) / (sf[octv] * sf[octv])); e_st.append(1 if stereo else 0)
+            seen += 1
+    kf_pose = np.zeros((n_kf, 7))
+    for k in range(n_kf):
+        Rn = _rot(int(rng.integers(0, 3)), np.deg2rad(rng.normal(0, 0.5))) @ Rs[k] if k >= n_fixed else Rs[k]
+        tn = ts[k] + (rng.normal(0, 0.01, 3) if k >= n_fixed else 0)
+        Rf = Rn.astype(np.float32).astype(np.float64)          # poses enter as float cv::Mat (Converter::toSE3Quat)
+        kf_pose[k, :4] = _quat_from_R(Rf)
+        kf_pose[k, 4:] = tn.astype(np.float32)
+    pts = (X + rng.normal(0, 0.02, X.shape)).astype(np.float32).astype(np.float64)
+    fixed = np.zeros(n_kf, np.uint8); fixed[:n_fixed] = 1
+    return dict(kf_pose=kf_pose, kf_fixed=fixed, pts=pts, e_kf=np.array(e_kf, np.int32), e_pt=np.array(e_pt, np.int32),
+                e_obs=np.array(e_obs, np.float64).reshape(-1, 3), e_inv_sigma2=np.array(e_is2, np.float32),
+                e_stereo=np.array(e_st, np.uint8), K=(float(np.float32(fx)), float(np.float32(fy)), float(np.float32(cx)),
+                                                      float(np.float32(cy)), float(np.float32(bf))))

@@ -291,3 +291,56 @@ def search_by_projection_frame(cur, last_pts, last_desc, Rcw, tcw, forward, back
     n = L.orbo_search_by_projection_frame(C.byref(f), len(pts), _p(pts), _p(pd), _p(R), _p(t), int(forward), int(backward), th,
                                           int(check_ori), _p(m))
     return n, m
+
+
+# ---- local bundle adjustment (oracle/lba_oracle.c) ------------------------------------------------------------
+class OLbaProblem(C.Structure):
+    _fields_ = [("n_kf", C.c_int32), ("kf_pose", C.c_void_p), ("kf_fixed", C.c_void_p), ("n_pts", C.c_int32), ("pts", C.c_void_p),
+                ("n_edges", C.c_int32), ("e_kf", C.c_void_p), ("e_pt", C.c_void_p), ("e_obs", C.c_void_p),
+                ("e_inv_sigma2", C.c_void_p), ("e_stereo", C.c_void_p),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
+                ("stop_flag", C.c_void_p)]
+
+
+class OLbaTrace(C.Structure):
+    _fields_ = [("n_trials", C.c_int32), ("chi2", C.c_double * 256), ("lambda_", C.c_double * 256), ("dim", C.c_int32),
+                ("lambda0", C.c_double), ("Hschur", C.c_void_p), ("bschur", C.c_void_p), ("xp", C.c_void_p)]
+
+
+def lba_pack(prob, cls=OLbaProblem):
+    """prob: dict from synth.lba_problem -> (ctypes struct, keepalive)"""
+    keep = dict(kf_pose=np.ascontiguousarray(prob["kf_pose"], np.float64), kf_fixed=np.ascontiguousarray(prob["kf_fixed"], np.uint8),
+                pts=np.ascontiguousarray(prob["pts"], np.float64), e_kf=np.ascontiguousarray(prob["e_kf"], np.int32),
+                e_pt=np.ascontiguousarray(prob["e_pt"], np.int32), e_obs=np.ascontiguousarray(prob["e_obs"], np.float64),
+                e_inv_sigma2=np.ascontiguousarray(prob["e_inv_sigma2"], np.float32), e_stereo=np.ascontiguousarray(prob["e_stereo"], np.uint8))
+    P = cls()
+    P.n_kf, P.n_pts, P.n_edges = len(keep["kf_pose"]), len(keep["pts"]), len(keep["e_kf"])
+    for k, v in keep.items():
+        setattr(P, k, v.ctypes.data)
+    P.fx, P.fy, P.cx, P.cy, P.bf = prob["K"]
+    if prob.get("stop_flag") is not None:
+        keep["stop_flag"] = prob["stop_flag"]
+        P.stop_flag = prob["stop_flag"].ctypes.data
+    return P, keep
+
+
+def lba_solve(prob, its1=5, its2=10, want_system=False):
+    """Optimizer::LocalBundleAdjustment on a synthetic problem -> dict(kf, pts, chi2, erase, trials, chi2_trace, lambda_trace[, Hschur, bschur, xp])"""
+    L = lib()
+    L.orbo_lba_solve.argtypes = [C.POINTER(OLbaProblem), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OLbaTrace)]
+    P, keep = lba_pack(prob)
+    kf, pt = np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3))
+    chi2, erase = np.zeros(P.n_edges), np.zeros(P.n_edges, np.uint8)
+    tr = OLbaTrace()
+    dim = 6 * int((np.asarray(prob["kf_fixed"]) == 0).sum())
+    if want_system:
+        Hs, bs, xp = np.zeros((dim, dim)), np.zeros(dim), np.zeros(dim)
+        tr.Hschur, tr.bschur, tr.xp = Hs.ctypes.data, bs.ctypes.data, xp.ctypes.data
+    rc = L.orbo_lba_solve(C.byref(P), its1, its2, _p(kf), _p(pt), _p(chi2), _p(erase), C.byref(tr))
+    n = min(tr.n_trials, 256)
+    out = dict(kf=kf, pts=pt, chi2=chi2, erase=erase, trials=tr.n_trials, chi2_trace=np.array(tr.chi2[:n]), lambda_trace=np.array(tr.lambda_[:n]),
+               stopped=rc)
+    if want_system:
+        d = tr.dim
+        out.update(Hschur=Hs.reshape(-1)[:d * d].reshape(d, d).copy(), bschur=bs[:d].copy(), xp=xp[:d].copy(), lambda0=tr.lambda0)
+    return out

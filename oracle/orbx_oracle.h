@@ -96,6 +96,33 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
                                     const float Rcw[9], const float tcw[3], int forward, int backward, float th,
                                     int check_ori, int32_t *match);
 
+/* ---- local bundle adjustment (src/Optimizer.cc:454-779 + g2o) ---- */
+typedef struct {
+    int32_t n_kf;                /* keyframe vertices: local (free) and fixed */
+    const double *kf_pose;       /* n_kf x 7: quaternion (x,y,z,w) then translation, = SE3Quat of Converter::toSE3Quat(Tcw) */
+    const uint8_t *kf_fixed;     /* vSE3->setFixed(...) */
+    int32_t n_pts;
+    const double *pts;           /* n_pts x 3, Converter::toVector3d(GetWorldPos()) */
+    int32_t n_edges;
+    const int32_t *e_kf, *e_pt;  /* vertex indices of every observation */
+    const double *e_obs;         /* n_edges x 3: kpUn.pt.x, kpUn.pt.y, mvuRight (third unused for monocular edges) */
+    const float *e_inv_sigma2;   /* mvInvLevelSigma2[kpUn.octave] */
+    const uint8_t *e_stereo;     /* 1 = EdgeStereoSE3ProjectXYZ, 0 = EdgeSE3ProjectXYZ */
+    double fx, fy, cx, cy, bf;
+    const volatile uint8_t *stop_flag;   /* pbStopFlag (may be NULL) */
+} orbo_lba_problem;
+#define ORBO_LBA_MAX_TRACE 256
+typedef struct {
+    int32_t n_trials;            /* LM trials over both rounds */
+    double chi2[ORBO_LBA_MAX_TRACE], lambda[ORBO_LBA_MAX_TRACE];
+    int32_t dim;                 /* 6 x free poses */
+    double lambda0;
+    double *Hschur, *bschur, *xp;   /* optional: reduced system and pose update of the very first trial (dim x dim, dim, dim) */
+} orbo_lba_trace;
+/* kf_out n_kf x 7, pt_out n_pts x 3, chi2_out / erase_out per edge (Optimizer.cc:709-735); returns 1 if stopped before starting */
+int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out, double *pt_out, double *chi2_out,
+                   uint8_t *erase_out, orbo_lba_trace *tr);
+
 #ifdef __cplusplus
 }
 #endif
