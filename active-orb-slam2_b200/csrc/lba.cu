@@ -1,0 +1,806 @@
+// Local bundle adjustment: replaces the g2o work behind Optimizer::LocalBundleAdjustment (reference
+// src/Optimizer.cc:454-779): EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ computeError + linearizeOplus
+// (Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:103-157, :188-234), BaseBinaryEdge::constructQuadraticForm
+// with the Huber kernel (core/base_binary_edge.hpp:55-120, core/robust_kernel_impl.cpp:78-91),
+// BlockSolver::buildSystem / setLambda / solve incl. the Schur complement (core/block_solver.hpp:354-486),
+// the reduced solve (solvers/linear_solver_eigen.h:94-124, here a dense Cholesky), VertexSE3Expmap::oplusImpl /
+// SE3Quat::exp (types/se3quat.h:223-257) and the Levenberg schedule
+// (core/optimization_algorithm_levenberg.cpp:61-189) with the two-round outlier policy of Optimizer.cc:659-735.
+//
+// Everything is double precision like g2o (tolerance vs the oracle: 1e-4 relative on poses / points, identical
+// outlier sets); none of it is shaped as a dense GEMM: the Schur product is block-sparse (about 30x fewer flops
+// than the dense 6P x 3L x 6P contraction) and needs f64, so the tensor pipes are not used.
+//   k_lba_err      one thread per edge: residual, chi2, robustified chi2 (block-reduced)
+//   k_lba_build    one thread per edge: Jacobians, weighted blocks; H_ll / b_l by global atomics (one landmark sees
+//                  ~4 edges), H_pp / b_p pre-reduced per CTA in shared memory, H_pl stored per edge
+//   k_lba_schur    one warp per landmark (edges are sorted by landmark): D^-1, b_schur, and every pose pair's 6x6
+//                  block accumulated in a CTA-private shared-memory copy of the upper block triangle of H_schur,
+//                  flushed once per CTA
+//   k_lba_solve    one CTA: Cholesky + two triangular solves of the reduced system in shared memory
+//   k_lba_update   landmark back-substitution, point and pose updates, Levenberg's scale term
+// The Levenberg control flow runs on the host and reads four doubles back per trial.
+#include <math.h>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "orbx_internal.cuh"
+
+#define LBA_THREADS 256
+#define LBA_SMEM_KF 64          // H_pp pre-reduction in shared memory up to this many free keyframes
+#define LBA_SCHUR_CTAS 32
+#define LBA_SCHUR_THREADS 512
+#define LBA_SOLVE_THREADS 1024
+
+struct LbaDev {
+    int n_kf, n_pts, n_edges, np, n;         // np free keyframes, n = 6 np
+    double *kf;          // [n_kf][7] quaternion (x,y,z,w), translation
+    const int *kfidx;    // [n_kf] index in the reduced system or -1 (fixed)
+    double *pt;          // [n_pts][3]
+    const int *ptstart;  // [n_pts + 1] edges are sorted by landmark
+    const int *ekf, *ept;
+    const double *obs;   // [E][3]
+    const double *info;  // [E]
+    const uint8_t *stereo;
+    uint8_t *level1;     // [E] excluded from the second round
+    double *err, *chi2;  // [E][3], [E]  (the edge's stored _error / chi2())
+    double *Hpl;         // [E][18]  6x3 row-major
+    double *Hpp;         // [np][27]  21 upper-triangular entries of the 6x6 block, then b_p
+    double *Hll;         // [n_pts][9]  6 upper-triangular entries of the 3x3 block, then b_l
+    double *Hs, *bs, *xp, *xl;   // [n][n] (upper block triangle filled), [n], [n], [n_pts][3]
+    double *scal;        // 0 chi2, 1 scale, 2 max diagonal, 3 solve ok
+    double fx, fy, cx, cy, bf;
+    float bf_f;
+    double d_mono, d_stereo;     // Huber deltas (float sqrt(5.991), sqrt(7.815), Optimizer.cc:569-570)
+};
+
+__device__ __forceinline__ void quat_to_R(const double *q, double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) tmp[w] = v;
+    __syncthreads();
+    double s = 0;
+    if (w == 0) {
+        s = lane < (int)(blockDim.x >> 5) ? tmp[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    __syncthreads();
+    return s;   // valid in thread 0
+}
+
+// residual of edge e at the current estimates; returns the depth
+__device__ __forceinline__ double edge_residual(const LbaDev &D, int e, const double R[9], const double *t, double Xc[3], double er[3]) {
+    const double *X = D.pt + 3 * D.ept[e];
+    for (int r = 0; r < 3; r++) Xc[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + t[r];
+    const double *o = D.obs + 3 * e;
+    if (!D.stereo[e]) {
+        er[0] = o[0] - (Xc[0] / Xc[2] * D.fx + D.cx);
+        er[1] = o[1] - (Xc[1] / Xc[2] * D.fy + D.cy);
+        er[2] = 0;
+    } else {   // cam_project keeps 1/z and bf in float (types_six_dof_expmap.cpp:150-157)
+        const float invz = __fdiv_rn(1.0f, (float)Xc[2]);
+        const double u = Xc[0] * (double)invz * D.fx + D.cx;
+        er[0] = o[0] - u;
+        er[1] = o[1] - (Xc[1] * (double)invz * D.fy + D.cy);
+        er[2] = o[2] - (u - (double)__fmul_rn(D.bf_f, invz));
+    }
+    return Xc[2];
+}
+
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_err(LbaDev D, int robust) {
+    __shared__ double tmp[32];
+    const int e = blockIdx.x * LBA_THREADS + threadIdx.x;
+    double c = 0;
+    if (e < D.n_edges && !D.level1[e]) {
+        double R[9], Xc[3], er[3];
+        const double *T = D.kf + 7 * D.ekf[e];
+        quat_to_R(T, R);
+        edge_residual(D, e, R, T + 4, Xc, er);
+        D.err[3 * e] = er[0]; D.err[3 * e + 1] = er[1]; D.err[3 * e + 2] = er[2];
+        c = D.info[e] * (er[0] * er[0] + er[1] * er[1] + er[2] * er[2]);
+        D.chi2[e] = c;
+        if (robust) {
+            const double d = D.stereo[e] ? D.d_stereo : D.d_mono, dsqr = d * d;
+            if (c > dsqr) c = 2 * sqrt(c) * d - dsqr;
+        }
+    }
+    const double s = block_sum(c, tmp);
+    if (threadIdx.x == 0 && s != 0) atomicAdd(&D.scal[0], s);
+}
+
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_build(LbaDev D, int robust) {
+    __shared__ double hpp[LBA_SMEM_KF * 27];
+    const bool use_smem = D.np <= LBA_SMEM_KF;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < D.np * 27; i += LBA_THREADS) hpp[i] = 0;
+        __syncthreads();
+    }
+    const int e = blockIdx.x * LBA_THREADS + threadIdx.x;
+    if (e < D.n_edges && !D.level1[e]) {
+        const int dim = D.stereo[e] ? 3 : 2;
+        double R[9], Xc[3], er[3];
+        const double *T = D.kf + 7 * D.ekf[e];
+        quat_to_R(T, R);
+        edge_residual(D, e, R, T + 4, Xc, er);
+        er[0] = D.err[3 * e]; er[1] = D.err[3 * e + 1]; er[2] = D.err[3 * e + 2];   // the stored _error
+        const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = D.fx, fy = D.fy, bf = D.bf;
+        double A[9], B[18];
+        for (int c = 0; c < 3; c++) {
+            A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+            A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+            A[6 + c] = dim == 3 ? A[c] - bf * R[6 + c] / z2 : 0.0;
+        }
+        B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
+        B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
+        if (dim == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
+        else { for (int i = 12; i < 18; i++) B[i] = 0; }
+        const double info = D.info[e];
+        double rho1 = 1.0;
+        if (robust) {
+            const double d = D.stereo[e] ? D.d_stereo : D.d_mono;
+            if (D.chi2[e] > d * d) rho1 = d / sqrt(D.chi2[e]);
+        }
+        const double w = rho1 * info;
+        double wr[3];   // omega_r * rho1 = -info * e * rho1
+        for (int d = 0; d < 3; d++) wr[d] = -info * er[d] * rho1;
+        double *hl = D.Hll + 9 * D.ept[e];
+        int k = 0;
+        for (int a = 0; a < 3; a++)
+            for (int b = a; b < 3; b++) atomicAdd(&hl[k++], w * (A[a] * A[b] + A[3 + a] * A[3 + b] + A[6 + a] * A[6 + b]));
+        for (int a = 0; a < 3; a++) atomicAdd(&hl[6 + a], A[a] * wr[0] + A[3 + a] * wr[1] + A[6 + a] * wr[2]);
+        const int ip = D.kfidx[D.ekf[e]];
+        if (ip >= 0) {
+            double *hp = use_smem ? hpp + 27 * ip : D.Hpp + 27 * ip;
+            k = 0;
+            for (int a = 0; a < 6; a++)
+                for (int b = a; b < 6; b++) atomicAdd(&hp[k++], w * (B[a] * B[b] + B[6 + a] * B[6 + b] + B[12 + a] * B[12 + b]));
+            for (int a = 0; a < 6; a++) atomicAdd(&hp[21 + a], B[a] * wr[0] + B[6 + a] * wr[1] + B[12 + a] * wr[2]);
+            double *hpl = D.Hpl + 18 * (size_t)e;
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 3; b++) hpl[3 * a + b] = w * (B[a] * A[b] + B[6 + a] * A[3 + b] + B[12 + a] * A[6 + b]);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < D.np * 27; i += LBA_THREADS)
+            if (hpp[i] != 0) atomicAdd(&D.Hpp[i], hpp[i]);
+    }
+}
+
+// computeLambdaInit: max |diagonal| over every active vertex (optimization_algorithm_levenberg.cpp:166-180)
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_maxdiag(LbaDev D) {
+    __shared__ double tmp[32];
+    double m = 0;
+    const int diag6[6] = {0, 6, 11, 15, 18, 20}, diag3[3] = {0, 3, 5};
+    for (int i = threadIdx.x; i < D.np * 6; i += LBA_THREADS) m = fmax(m, fabs(D.Hpp[27 * (i / 6) + diag6[i % 6]]));
+    for (int i = threadIdx.x; i < D.n_pts * 3; i += LBA_THREADS) m = fmax(m, fabs(D.Hll[9 * (i / 3) + diag3[i % 3]]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) tmp[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < LBA_THREADS / 32; w++) m = fmax(m, tmp[w]);
+        D.scal[2] = m;
+    }
+}
+
+// symmetric 3x3 inverse of (H_ll + lambda I); h = (xx, xy, xz, yy, yz, zz)
+__device__ __forceinline__ void dinv3(const double *h, double lambda, double I[6]) {
+    const double a = h[0] + lambda, b = h[1], c = h[2], e = h[3] + lambda, f = h[4], i = h[5] + lambda;
+    const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
+    const double id = 1.0 / (a * c00 + b * c01 + c * c02);
+    I[0] = c00 * id; I[1] = c01 * id; I[2] = c02 * id;
+    I[3] = (a * i - c * c) * id; I[4] = (b * c - a * f) * id; I[5] = (a * e - b * b) * id;
+}
+
+__device__ __forceinline__ int upper_block(int p1, int p2, int np) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); }
+
+// H_schur = H_pp + lambda I, b_schur = b_p  (block_solver.hpp:371-373, :436)
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_schur_init(LbaDev D, double lambda) {
+    const int n = D.n;
+    for (int i = blockIdx.x * LBA_THREADS + threadIdx.x; i < n * n; i += gridDim.x * LBA_THREADS) {
+        const int r = i / n, c = i - r * n, p = r / 6;
+        double v = 0;
+        if (c / 6 == p) {
+            int a = r - 6 * p, b = c - 6 * p;
+            if (a > b) { const int t = a; a = b; b = t; }
+            v = D.Hpp[27 * p + a * 6 - a * (a - 1) / 2 + (b - a)] + (a == b ? lambda : 0.0);
+        }
+        D.Hs[i] = v;
+    }
+    for (int i = blockIdx.x * LBA_THREADS + threadIdx.x; i < n; i += gridDim.x * LBA_THREADS) D.bs[i] = D.Hpp[27 * (i / 6) + 21 + i % 6];
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(LBA_SCHUR_THREADS) k_lba_schur(LbaDev D, double lambda) {
+    extern __shared__ __align__(16) double sacc[];     // [nblocks][36] then [n]
+    const int np = D.np, n = D.n, nblk = np * (np + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (SMEM) {
+        for (int i = tid; i < nblk * 36 + n; i += LBA_SCHUR_THREADS) sacc[i] = 0;
+        __syncthreads();
+    }
+    const int warps = gridDim.x * (LBA_SCHUR_THREADS / 32);
+    for (int l = blockIdx.x * (LBA_SCHUR_THREADS / 32) + (tid >> 5); l < D.n_pts; l += warps) {
+        const int s = D.ptstart[l], ne = D.ptstart[l + 1] - s;
+        if (ne == 0) continue;
+        const double *hl = D.Hll + 9 * l;
+        double Di[6];
+        dinv3(hl, lambda, Di);
+        const double db0 = Di[0] * hl[6] + Di[1] * hl[7] + Di[2] * hl[8], db1 = Di[1] * hl[6] + Di[3] * hl[7] + Di[4] * hl[8],
+                     db2 = Di[2] * hl[6] + Di[4] * hl[7] + Di[5] * hl[8];
+        for (int i = lane; i < ne; i += 32) {       // coefficients: b_schur -= B_i D^-1 b_l (block_solver.hpp:413)
+            const int e = s + i, p = D.kfidx[D.ekf[e]];
+            if (p < 0 || D.level1[e]) continue;
+            const double *B = D.Hpl + 18 * (size_t)e;
+            for (int a = 0; a < 6; a++) {
+                const double v = -(B[3 * a] * db0 + B[3 * a + 1] * db1 + B[3 * a + 2] * db2);
+                if (SMEM) atomicAdd(&sacc[nblk * 36 + 6 * p + a], v); else atomicAdd(&D.bs[6 * p + a], v);
+            }
+        }
+        for (int pr = lane; pr < ne * ne; pr += 32) {   // H_schur(i1,i2) -= B_i1 D^-1 B_i2^T for i1 <= i2 (:416-430)
+            const int i = pr / ne, j = pr - i * ne, e1 = s + i, e2 = s + j;
+            const int p1 = D.kfidx[D.ekf[e1]], p2 = D.kfidx[D.ekf[e2]];
+            if (p1 < 0 || p2 < 0 || p1 > p2 || D.level1[e1] || D.level1[e2] || (p1 == p2 && i != j)) continue;
+            const double *B1 = D.Hpl + 18 * (size_t)e1, *B2 = D.Hpl + 18 * (size_t)e2;
+            double b2[18];
+#pragma unroll
+            for (int k = 0; k < 18; k++) b2[k] = B2[k];
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const double u0 = B1[3 * a], u1 = B1[3 * a + 1], u2 = B1[3 * a + 2];
+                const double bd0 = u0 * Di[0] + u1 * Di[1] + u2 * Di[2], bd1 = u0 * Di[1] + u1 * Di[3] + u2 * Di[4],
+                             bd2 = u0 * Di[2] + u1 * Di[4] + u2 * Di[5];
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    const double v = -(bd0 * b2[3 * b] + bd1 * b2[3 * b + 1] + bd2 * b2[3 * b + 2]);
+                    if (SMEM) atomicAdd(&sacc[upper_block(p1, p2, np) * 36 + 6 * a + b], v);
+                    else atomicAdd(&D.Hs[(size_t)(6 * p1 + a) * n + 6 * p2 + b], v);
+                }
+            }
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int i = tid; i < nblk * 36; i += LBA_SCHUR_THREADS) {
+            const double v = sacc[i];
+            if (v == 0) continue;
+            const int blk = i / 36, ab = i - blk * 36;
+            int p1 = 0, rem = blk;                      // invert upper_block()
+            while (rem >= np - p1) { rem -= np - p1; p1++; }
+            const int p2 = p1 + rem;
+            atomicAdd(&D.Hs[(size_t)(6 * p1 + ab / 6) * n + 6 * p2 + ab % 6], v);
+        }
+        for (int i = tid; i < n; i += LBA_SCHUR_THREADS) if (sacc[nblk * 36 + i] != 0) atomicAdd(&D.bs[i], sacc[nblk * 36 + i]);
+    }
+}
+
+// dense Cholesky solve of the reduced camera system; A = upper block triangle of H_schur (row-major n x n).
+// W is the n x n workspace (shared memory when it fits, else the lower triangle of A itself).
+__global__ void __launch_bounds__(LBA_SOLVE_THREADS) k_lba_solve(LbaDev D, int use_smem) {
+    extern __shared__ __align__(16) double sw[];
+    __shared__ int ok;
+    const int n = D.n, tid = threadIdx.x;
+    double *W = use_smem ? sw : D.Hs;
+    const int ld = n;
+    // symmetric fill: element (r,c) with r >= c comes from the stored upper entry (c,r)
+    for (int i = tid; i < n * n; i += LBA_SOLVE_THREADS) {
+        const int r = i / n, c = i - r * n;
+        if (r >= c) {
+            const int pr = r / 6, pc = c / 6;
+            const double v = pr == pc ? D.Hs[(size_t)r * n + c] : D.Hs[(size_t)c * n + r];   // diagonal blocks are stored in full
+            if (use_smem) W[r * ld + c] = v;
+            else if (pr != pc) W[r * ld + c] = v;                 // in place: write the mirror of an off-diagonal block
+        }
+    }
+    if (tid == 0) ok = 1;
+    __syncthreads();
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) {
+            const double d = W[j * ld + j];
+            if (!(d > 0)) ok = 0; else W[j * ld + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (!ok) break;
+        const double dj = W[j * ld + j];
+        for (int i = j + 1 + tid; i < n; i += LBA_SOLVE_THREADS) W[i * ld + j] /= dj;
+        __syncthreads();
+        const int m = n - j - 1;                         // trailing update of the lower triangle
+        for (int t = tid; t < m * m; t += LBA_SOLVE_THREADS) {
+            const int r = j + 1 + t / m, c = j + 1 + t % m;
+            if (c <= r) W[r * ld + c] -= W[r * ld + j] * W[c * ld + j];
+        }
+        __syncthreads();
+    }
+    if (ok) {
+        // L y = b, then L^T x = y; one warp, lanes split the dot products
+        if (tid < 32) {
+            for (int i = 0; i < n; i++) {
+                double s = 0;
+                for (int k = tid; k < i; k += 32) s += W[i * ld + k] * D.xp[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (tid == 0) D.xp[i] = (D.bs[i] - s) / W[i * ld + i];
+                __syncwarp();
+            }
+            for (int i = n - 1; i >= 0; i--) {
+                double s = 0;
+                for (int k = i + 1 + tid; k < n; k += 32) s += W[k * ld + i] * D.xp[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (tid == 0) D.xp[i] = (D.xp[i] - s) / W[i * ld + i];
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int i = tid; i < n; i += LBA_SOLVE_THREADS) D.xp[i] = 0;   // failed factorisation: no step (the trial is rejected)
+    }
+    if (tid == 0) D.scal[3] = ok ? 1.0 : 0.0;
+}
+
+// Eigen::Quaterniond(Matrix3d)
+__device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t; t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        double qq[4];
+        qq[i] = 0.5 * t; t = 0.5 / t;
+        qq[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+        qq[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        qq[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    }
+}
+__device__ __forceinline__ void quat_normalize(double q[4]) {
+    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
+}
+
+// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*)
+__device__ void se3_oplus(double *T, const double *u) {
+    const double wx = u[0], wy = u[1], wz = u[2];
+    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double O2[9], R[9], V[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
+    if (theta < 0.00001) {
+        for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+    } else {
+        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
+        for (int i = 0; i < 9; i++) {
+            const double id = i % 4 == 0 ? 1.0 : 0.0;
+            R[i] = id + a * O[i] + b * O2[i];
+            V[i] = id + b * O[i] + c * O2[i];
+        }
+    }
+    double eq[4], et[3];
+    R_to_quat(R, eq);
+    quat_normalize(eq);
+    for (int r = 0; r < 3; r++) et[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
+    const double *b = T;   // q2
+    double nq[4];
+    nq[3] = eq[3] * b[3] - eq[0] * b[0] - eq[1] * b[1] - eq[2] * b[2];
+    nq[0] = eq[3] * b[0] + eq[0] * b[3] + eq[1] * b[2] - eq[2] * b[1];
+    nq[1] = eq[3] * b[1] + eq[1] * b[3] + eq[2] * b[0] - eq[0] * b[2];
+    nq[2] = eq[3] * b[2] + eq[2] * b[3] + eq[0] * b[1] - eq[1] * b[0];
+    double Rq[9], nt[3];
+    quat_to_R(eq, Rq);
+    for (int r = 0; r < 3; r++) nt[r] = et[r] + Rq[3 * r] * T[4] + Rq[3 * r + 1] * T[5] + Rq[3 * r + 2] * T[6];
+    quat_normalize(nq);
+    T[0] = nq[0]; T[1] = nq[1]; T[2] = nq[2]; T[3] = nq[3]; T[4] = nt[0]; T[5] = nt[1]; T[6] = nt[2];
+}
+
+// x_l = D^-1 (b_l - B^T x_p) (block_solver.hpp:461-481), SparseOptimizer::update, computeScale
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_update(LbaDev D, double lambda) {
+    __shared__ double tmp[32];
+    const int i = blockIdx.x * LBA_THREADS + threadIdx.x;
+    double sc = 0;
+    if (i < D.n_pts) {
+        const double *hl = D.Hll + 9 * i;
+        double c0 = hl[6], c1 = hl[7], c2 = hl[8];
+        for (int e = D.ptstart[i]; e < D.ptstart[i + 1]; e++) {
+            const int p = D.kfidx[D.ekf[e]];
+            if (p < 0 || D.level1[e]) continue;
+            const double *B = D.Hpl + 18 * (size_t)e, *x = D.xp + 6 * p;
+            for (int a = 0; a < 6; a++) { c0 -= B[3 * a] * x[a]; c1 -= B[3 * a + 1] * x[a]; c2 -= B[3 * a + 2] * x[a]; }
+        }
+        double Di[6];
+        dinv3(hl, lambda, Di);
+        const double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2, x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2, x2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
+        D.xl[3 * i] = x0; D.xl[3 * i + 1] = x1; D.xl[3 * i + 2] = x2;
+        sc = x0 * (lambda * x0 + hl[6]) + x1 * (lambda * x1 + hl[7]) + x2 * (lambda * x2 + hl[8]);
+        D.pt[3 * i] += x0; D.pt[3 * i + 1] += x1; D.pt[3 * i + 2] += x2;
+    } else if (i - D.n_pts < D.n_kf) {
+        const int k = i - D.n_pts, p = D.kfidx[k];
+        if (p >= 0) {
+            const double *x = D.xp + 6 * p, *b = D.Hpp + 27 * p + 21;
+            for (int a = 0; a < 6; a++) sc += x[a] * (lambda * x[a] + b[a]);
+            se3_oplus(D.kf + 7 * k, x);
+        }
+    }
+    const double s = block_sum(sc, tmp);
+    if (threadIdx.x == 0 && s != 0) atomicAdd(&D.scal[1], s);
+}
+
+// Optimizer.cc:671-703 / :709-735: stored chi2 over the threshold or depth not positive
+__global__ void __launch_bounds__(LBA_THREADS) k_lba_classify(LbaDev D, uint8_t *flag) {
+    const int e = blockIdx.x * LBA_THREADS + threadIdx.x;
+    if (e >= D.n_edges) return;
+    double R[9];
+    const double *T = D.kf + 7 * D.ekf[e], *X = D.pt + 3 * D.ept[e];
+    quat_to_R(T, R);
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + T[6];
+    flag[e] = (D.chi2[e] > (D.stereo[e] ? 7.815 : 5.991) || !(z > 0)) ? 1 : 0;
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------
+struct orbx_lba {
+    int device, max_kf, max_pts, max_edges;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    LbaDev D;
+    double *d_kf_bak, *d_pt_bak;
+    int *d_kfidx, *d_ptstart, *d_ekf, *d_ept;
+    double *d_obs, *d_info;
+    uint8_t *d_stereo, *d_flag;
+    double *h_scal;
+    std::vector<int> perm;      // sorted position -> caller's edge index
+    const volatile uint8_t *stop;
+    int launches;
+    int loaded;
+};
+
+extern "C" void orbx_lba_destroy(orbx_lba *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->D.kf); cudaFree(h->D.pt); cudaFree(h->D.level1); cudaFree(h->D.err); cudaFree(h->D.chi2); cudaFree(h->D.Hpl);
+    cudaFree(h->D.Hpp); cudaFree(h->D.Hll); cudaFree(h->D.Hs); cudaFree(h->D.bs); cudaFree(h->D.xp); cudaFree(h->D.xl);
+    cudaFree(h->D.scal); cudaFree(h->d_kf_bak); cudaFree(h->d_pt_bak); cudaFree(h->d_kfidx); cudaFree(h->d_ptstart);
+    cudaFree(h->d_ekf); cudaFree(h->d_ept); cudaFree(h->d_obs); cudaFree(h->d_info); cudaFree(h->d_stereo); cudaFree(h->d_flag);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int max_points, int max_edges, int device) {
+    if (!out) return ORBX_ERR_INVALID;
+    *out = nullptr;
+    if (max_keyframes < 1 || max_points < 1 || max_edges < 1) {
+        orbx_set_error("orbx_lba_create: bad argument");
+        return ORBX_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        orbx_set_error("no CUDA device %d (%d visible)", device, ndev);
+        return ORBX_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    ORBX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        orbx_set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return ORBX_ERR_NO_DEVICE;
+    }
+    ORBX_CUDA(cudaSetDevice(device));
+    orbx_lba *h = new orbx_lba();
+    memset(&h->D, 0, sizeof(h->D));
+    h->device = device; h->max_kf = max_keyframes; h->max_pts = max_points; h->max_edges = max_edges;
+    h->d_kf_bak = h->d_pt_bak = nullptr; h->d_kfidx = h->d_ptstart = h->d_ekf = h->d_ept = nullptr;
+    h->d_obs = h->d_info = nullptr; h->d_stereo = h->d_flag = nullptr; h->h_scal = nullptr;
+    h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->stop = nullptr; h->launches = 0; h->loaded = 0;
+    const size_t K = max_keyframes, L = max_points, E = max_edges, N = 6 * K;
+    cudaError_t ce = cudaSuccess;
+#define TRY(x) if (ce == cudaSuccess) ce = (x)
+    TRY(cudaMalloc((void **)&h->D.kf, sizeof(double) * 7 * K));
+    TRY(cudaMalloc((void **)&h->d_kf_bak, sizeof(double) * 7 * K));
+    TRY(cudaMalloc((void **)&h->d_kfidx, sizeof(int) * K));
+    TRY(cudaMalloc((void **)&h->D.pt, sizeof(double) * 3 * L));
+    TRY(cudaMalloc((void **)&h->d_pt_bak, sizeof(double) * 3 * L));
+    TRY(cudaMalloc((void **)&h->d_ptstart, sizeof(int) * (L + 1)));
+    TRY(cudaMalloc((void **)&h->d_ekf, sizeof(int) * E));
+    TRY(cudaMalloc((void **)&h->d_ept, sizeof(int) * E));
+    TRY(cudaMalloc((void **)&h->d_obs, sizeof(double) * 3 * E));
+    TRY(cudaMalloc((void **)&h->d_info, sizeof(double) * E));
+    TRY(cudaMalloc((void **)&h->d_stereo, E));
+    TRY(cudaMalloc((void **)&h->D.level1, E));
+    TRY(cudaMalloc((void **)&h->d_flag, E));
+    TRY(cudaMalloc((void **)&h->D.err, sizeof(double) * 3 * E));
+    TRY(cudaMalloc((void **)&h->D.chi2, sizeof(double) * E));
+    TRY(cudaMalloc((void **)&h->D.Hpl, sizeof(double) * 18 * E));
+    TRY(cudaMalloc((void **)&h->D.Hpp, sizeof(double) * 27 * K));
+    TRY(cudaMalloc((void **)&h->D.Hll, sizeof(double) * 9 * L));
+    TRY(cudaMalloc((void **)&h->D.Hs, sizeof(double) * N * N));
+    TRY(cudaMalloc((void **)&h->D.bs, sizeof(double) * N));
+    TRY(cudaMalloc((void **)&h->D.xp, sizeof(double) * N));
+    TRY(cudaMalloc((void **)&h->D.xl, sizeof(double) * 3 * L));
+    TRY(cudaMalloc((void **)&h->D.scal, sizeof(double) * 8));
+    TRY(cudaMallocHost((void **)&h->h_scal, sizeof(double) * 8));
+    TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TRY(cudaEventCreate(&h->ev0));
+    TRY(cudaEventCreate(&h->ev1));
+    TRY(ORBX_RAISE_SMEM(k_lba_schur<true>));
+    TRY(ORBX_RAISE_SMEM(k_lba_solve));
+#undef TRY
+    if (ce != cudaSuccess) {
+        orbx_set_error("orbx_lba_create: %s", cudaGetErrorString(ce));
+        orbx_lba_destroy(h);
+        return ORBX_ERR_CUDA;
+    }
+    *out = h;
+    return ORBX_OK;
+}
+
+// upload a problem: edges sorted by landmark, estimates, reduced indices
+static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
+    if (!P || P->n_kf < 0 || P->n_pts < 0 || P->n_edges < 0) return ORBX_ERR_INVALID;
+    if (P->n_kf > h->max_kf || P->n_pts > h->max_pts || P->n_edges > h->max_edges) {
+        orbx_set_error("problem (%d keyframes, %d points, %d edges) exceeds the handle (%d, %d, %d)", P->n_kf, P->n_pts, P->n_edges,
+                       h->max_kf, h->max_pts, h->max_edges);
+        return ORBX_ERR_CAPACITY;
+    }
+    if ((P->n_kf && (!P->kf_pose || !P->kf_fixed)) || (P->n_pts && !P->pts) ||
+        (P->n_edges && (!P->e_kf || !P->e_pt || !P->e_obs || !P->e_inv_sigma2 || !P->e_stereo)))
+        return ORBX_ERR_INVALID;
+    const int E = P->n_edges, L = P->n_pts, K = P->n_kf;
+    for (int e = 0; e < E; e++)
+        if (P->e_kf[e] < 0 || P->e_kf[e] >= K || P->e_pt[e] < 0 || P->e_pt[e] >= L) {
+            orbx_set_error("edge %d refers to vertex (%d, %d) outside the problem", e, P->e_kf[e], P->e_pt[e]);
+            return ORBX_ERR_INVALID;
+        }
+    std::vector<int> start(L + 1, 0), ekf(E), ept(E), kfidx(K);
+    std::vector<double> obs(3 * (size_t)E), info(E);
+    std::vector<uint8_t> st(E);
+    h->perm.assign(E, 0);
+    for (int e = 0; e < E; e++) start[P->e_pt[e] + 1]++;
+    for (int l = 0; l < L; l++) start[l + 1] += start[l];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int e = 0; e < E; e++) h->perm[cur[P->e_pt[e]]++] = e;       // stable: caller's order inside a landmark
+    for (int s = 0; s < E; s++) {
+        const int e = h->perm[s];
+        ekf[s] = P->e_kf[e]; ept[s] = P->e_pt[e]; st[s] = P->e_stereo[e] ? 1 : 0;
+        obs[3 * s] = P->e_obs[3 * e]; obs[3 * s + 1] = P->e_obs[3 * e + 1]; obs[3 * s + 2] = P->e_obs[3 * e + 2];
+        info[s] = (double)P->e_inv_sigma2[e];
+    }
+    int np = 0;
+    for (int k = 0; k < K; k++) kfidx[k] = P->kf_fixed[k] ? -1 : np++;
+    cudaStream_t s = h->stream;
+    LbaDev &D = h->D;
+    ORBX_CUDA(cudaMemcpyAsync(D.kf, P->kf_pose, sizeof(double) * 7 * K, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(D.pt, P->pts, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_kfidx, kfidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_ptstart, start.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice, s));
+    if (E) {
+        ORBX_CUDA(cudaMemcpyAsync(h->d_ekf, ekf.data(), sizeof(int) * E, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(cudaMemcpyAsync(h->d_ept, ept.data(), sizeof(int) * E, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(cudaMemcpyAsync(h->d_obs, obs.data(), sizeof(double) * 3 * E, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(cudaMemcpyAsync(h->d_info, info.data(), sizeof(double) * E, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(cudaMemcpyAsync(h->d_stereo, st.data(), E, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(cudaMemsetAsync(D.level1, 0, E, s));
+        ORBX_CUDA(cudaMemsetAsync(D.chi2, 0, sizeof(double) * E, s));
+        ORBX_CUDA(cudaMemsetAsync(D.err, 0, sizeof(double) * 3 * E, s));
+    }
+    ORBX_CUDA(cudaStreamSynchronize(s));      // the host vectors go out of scope
+    D.n_kf = K; D.n_pts = L; D.n_edges = E; D.np = np; D.n = 6 * np;
+    D.kfidx = h->d_kfidx; D.ptstart = h->d_ptstart; D.ekf = h->d_ekf; D.ept = h->d_ept; D.obs = h->d_obs; D.info = h->d_info;
+    D.stereo = h->d_stereo;
+    D.fx = P->fx; D.fy = P->fy; D.cx = P->cx; D.cy = P->cy; D.bf = P->bf; D.bf_f = (float)P->bf;
+    D.d_mono = (double)(float)sqrt(5.991); D.d_stereo = (double)(float)sqrt(7.815);
+    h->stop = P->stop_flag;
+    h->loaded = 1;
+    return ORBX_OK;
+}
+
+static inline int blocks_for(int n) { return n > 0 ? (n + LBA_THREADS - 1) / LBA_THREADS : 1; }
+
+static orbx_status lba_errors(orbx_lba *h, int robust) {      // computeActiveErrors + activeRobustChi2 -> scal[0]
+    ORBX_CUDA(cudaMemsetAsync(h->D.scal, 0, sizeof(double), h->stream));
+    k_lba_err<<<blocks_for(h->D.n_edges), LBA_THREADS, 0, h->stream>>>(h->D, robust);
+    h->launches++;
+    return ORBX_OK;
+}
+
+static orbx_status lba_build(orbx_lba *h, int robust) {       // BlockSolver::buildSystem
+    ORBX_CUDA(cudaMemsetAsync(h->D.Hpp, 0, sizeof(double) * 27 * (h->D.np ? h->D.np : 1), h->stream));
+    ORBX_CUDA(cudaMemsetAsync(h->D.Hll, 0, sizeof(double) * 9 * (h->D.n_pts ? h->D.n_pts : 1), h->stream));
+    k_lba_build<<<blocks_for(h->D.n_edges), LBA_THREADS, 0, h->stream>>>(h->D, robust);
+    h->launches++;
+    return ORBX_OK;
+}
+
+static size_t schur_smem(const LbaDev &D) { return sizeof(double) * ((size_t)D.np * (D.np + 1) / 2 * 36 + D.n); }
+
+static orbx_status lba_schur(orbx_lba *h, double lambda) {    // BlockSolver::solve up to the linear solve
+    const LbaDev &D = h->D;
+    k_lba_schur_init<<<blocks_for(D.n * D.n > 0 ? D.n * D.n : 1), LBA_THREADS, 0, h->stream>>>(D, lambda);
+    const size_t sm = schur_smem(D);
+    if (sm <= 200 * 1024) k_lba_schur<true><<<LBA_SCHUR_CTAS, LBA_SCHUR_THREADS, sm, h->stream>>>(D, lambda);
+    else k_lba_schur<false><<<4 * LBA_SCHUR_CTAS, LBA_SCHUR_THREADS, 0, h->stream>>>(D, lambda);
+    h->launches += 2;
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static orbx_status lba_solve_update(orbx_lba *h, double lambda) {
+    const LbaDev &D = h->D;
+    const size_t sm = sizeof(double) * (size_t)D.n * D.n;
+    const int use_smem = sm <= 200 * 1024;
+    k_lba_solve<<<1, LBA_SOLVE_THREADS, use_smem ? sm : 0, h->stream>>>(D, use_smem);
+    ORBX_CUDA(cudaMemsetAsync(D.scal + 1, 0, sizeof(double), h->stream));
+    k_lba_update<<<blocks_for(D.n_pts + D.n_kf), LBA_THREADS, 0, h->stream>>>(D, lambda);
+    h->launches += 2;
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static orbx_status read_scal(orbx_lba *h) {
+    ORBX_CUDA(cudaMemcpyAsync(h->h_scal, h->D.scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+static inline bool stop_requested(const orbx_lba *h) { return h->stop && *h->stop; }
+
+// optimizer.initializeOptimization(0) + optimizer.optimize(iterations)
+static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lba_result *res, bool *first) {
+    LbaDev &D = h->D;
+    orbx_status st;
+    double lambda = 0, ni = 2;
+    int nBad = 0;
+    for (int it = 0; it < iterations && !stop_requested(h); it++) {
+        if ((st = lba_errors(h, robust))) return st;
+        if ((st = lba_build(h, robust))) return st;
+        if (it == 0) { k_lba_maxdiag<<<1, LBA_THREADS, 0, h->stream>>>(D); h->launches++; }
+        if ((st = read_scal(h))) return st;
+        double currentChi = h->h_scal[0];
+        const double iniChi = currentChi;
+        if (it == 0) { lambda = 1e-5 * h->h_scal[2]; ni = 2; nBad = 0; }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            ORBX_CUDA(cudaMemcpyAsync(h->d_kf_bak, D.kf, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToDevice, h->stream));   // push
+            ORBX_CUDA(cudaMemcpyAsync(h->d_pt_bak, D.pt, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToDevice, h->stream));
+            if ((st = lba_schur(h, lambda))) return st;
+            const bool capture = *first;
+            if (capture) {
+                *first = false;
+                res->first_lambda = lambda;
+                if (res->first_Hschur) {
+                    std::vector<double> Hs((size_t)D.n * D.n);
+                    ORBX_CUDA(cudaMemcpyAsync(Hs.data(), D.Hs, sizeof(double) * Hs.size(), cudaMemcpyDeviceToHost, h->stream));
+                    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+                    for (int r = 0; r < D.n; r++)
+                        for (int c = 0; c < D.n; c++) {
+                            const bool up = r / 6 <= c / 6;
+                            res->first_Hschur[(size_t)r * D.n + c] = up ? Hs[(size_t)r * D.n + c] : Hs[(size_t)c * D.n + r];
+                        }
+                }
+                if (res->first_bschur) ORBX_CUDA(cudaMemcpyAsync(res->first_bschur, D.bs, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
+            }
+            if ((st = lba_solve_update(h, lambda))) return st;
+            if (capture && res->first_xp) ORBX_CUDA(cudaMemcpyAsync(res->first_xp, D.xp, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
+            if ((st = lba_errors(h, robust))) return st;
+            if ((st = read_scal(h))) return st;
+            double tempChi = h->h_scal[0];
+            const bool ok2 = h->h_scal[3] != 0.0;
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = currentChi - tempChi;
+            const double scale = h->h_scal[1] + 1e-3;
+            rho /= scale;
+            res->lm_trials++;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2;
+                ORBX_CUDA(cudaMemcpyAsync(D.kf, h->d_kf_bak, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToDevice, h->stream));   // pop
+                ORBX_CUDA(cudaMemcpyAsync(D.pt, h->d_pt_bak, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            qmax++;
+        } while (rho < 0 && qmax < 10 && !stop_requested(h));
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2, orbx_lba_result *res) {
+    if (!h || !prob || !res || !res->kf_pose || !res->pts || its1 < 0 || its2 < 0) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    h->launches = 0;
+    res->lm_trials = 0; res->stopped = 0; res->first_lambda = 0;
+    orbx_status st = lba_load(h, prob);
+    if (st) return st;
+    LbaDev &D = h->D;
+    const int E = D.n_edges;
+    if (stop_requested(h)) {       // Optimizer.cc:656-658
+        res->stopped = 1;
+        memcpy(res->kf_pose, prob->kf_pose, sizeof(double) * 7 * D.n_kf);
+        memcpy(res->pts, prob->pts, sizeof(double) * 3 * D.n_pts);
+        if (res->chi2) memset(res->chi2, 0, sizeof(double) * E);
+        if (res->erase) memset(res->erase, 0, E);
+        return ORBX_OK;
+    }
+    bool first = true;
+    if ((st = lba_optimize(h, its1, 1, res, &first))) return st;
+    if (!stop_requested(h) && its2 > 0) {
+        k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, h->stream>>>(D, D.level1);    // e->setLevel(1), Optimizer.cc:680-683
+        h->launches++;
+        if ((st = lba_optimize(h, its2, 0, res, &first))) return st;
+    }
+    k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, h->stream>>>(D, h->d_flag);        // vToErase, Optimizer.cc:709-735
+    h->launches++;
+    ORBX_CUDA(cudaGetLastError());
+    std::vector<double> chi(E);
+    std::vector<uint8_t> fl(E);
+    ORBX_CUDA(cudaMemcpyAsync(res->kf_pose, D.kf, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(res->pts, D.pt, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToHost, h->stream));
+    if (E) {
+        ORBX_CUDA(cudaMemcpyAsync(chi.data(), D.chi2, sizeof(double) * E, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(fl.data(), h->d_flag, E, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < E; s++) {
+        if (res->chi2) res->chi2[h->perm[s]] = chi[s];
+        if (res->erase) res->erase[h->perm[s]] = fl[s];
+    }
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_problem *prob, double lambda, int reps, float *ms,
+                                                  double *Hschur, double *bschur) {
+    if (!h || reps < 1) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    orbx_status st;
+    if (prob && (st = lba_load(h, prob))) return st;
+    if (!h->loaded) {
+        orbx_set_error("orbx_lba_build_schur_timed: no problem loaded");
+        return ORBX_ERR_INVALID;
+    }
+    h->launches = 0;
+    LbaDev &D = h->D;
+    ORBX_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < reps; r++) {
+        if ((st = lba_errors(h, 1))) return st;
+        if ((st = lba_build(h, 1))) return st;
+        if ((st = lba_schur(h, lambda))) return st;
+    }
+    ORBX_CUDA(cudaEventRecord(h->ev1, h->stream));
+    ORBX_CUDA(cudaEventSynchronize(h->ev1));
+    if (ms) ORBX_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    if (Hschur) {
+        std::vector<double> Hs((size_t)D.n * D.n);
+        ORBX_CUDA(cudaMemcpy(Hs.data(), D.Hs, sizeof(double) * Hs.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < D.n; r++)
+            for (int c = 0; c < D.n; c++) Hschur[(size_t)r * D.n + c] = r / 6 <= c / 6 ? Hs[(size_t)r * D.n + c] : Hs[(size_t)c * D.n + r];
+    }
+    if (bschur) ORBX_CUDA(cudaMemcpy(bschur, D.bs, sizeof(double) * D.n, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_lba_last_launches(const orbx_lba *h) { return h ? h->launches : 0; }

@@ -68,5 +68,11 @@ def _declare(L):
     L.orbx_match_projection_frame_device.argtypes = [vp, vp, i, vp]
     L.orbx_matcher_last_launches.argtypes = [vp]
     L.orbx_matcher_last_sweeps.argtypes = [vp, vp, i]
+    L.orbx_lba_create.argtypes = [C.POINTER(vp), i, i, i, i]
+    L.orbx_lba_destroy.restype = None
+    L.orbx_lba_destroy.argtypes = [vp]
+    L.orbx_lba_solve_host.argtypes = [vp, vp, i, i, vp]
+    L.orbx_lba_build_schur_timed.argtypes = [vp, vp, C.c_double, i, vp, vp, vp]
+    L.orbx_lba_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -1,0 +1,90 @@
+"""Host-side mirror of Optimizer::LocalBundleAdjustment (reference include/Optimizer.h:45, src/Optimizer.cc:454-779)
+over the orbx C ABI.  The problem is the POD form of the g2o graph the reference builds (Optimizer.cc:486-655):
+a dict with kf_pose (n x 7: quaternion x,y,z,w + translation), kf_fixed, pts (n x 3), e_kf, e_pt, e_obs (n x 3),
+e_inv_sigma2, e_stereo, K = (fx, fy, cx, cy, bf) and optionally stop_flag (uint8[1], the reference's pbStopFlag)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+
+class LbaProblem(C.Structure):
+    """orbx_lba_problem (include/orbx.h)"""
+    _fields_ = [("n_kf", C.c_int32), ("kf_pose", C.c_void_p), ("kf_fixed", C.c_void_p), ("n_pts", C.c_int32), ("pts", C.c_void_p),
+                ("n_edges", C.c_int32), ("e_kf", C.c_void_p), ("e_pt", C.c_void_p), ("e_obs", C.c_void_p),
+                ("e_inv_sigma2", C.c_void_p), ("e_stereo", C.c_void_p),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
+                ("stop_flag", C.c_void_p)]
+
+
+class LbaResult(C.Structure):
+    """orbx_lba_result (include/orbx.h)"""
+    _fields_ = [("kf_pose", C.c_void_p), ("pts", C.c_void_p), ("chi2", C.c_void_p), ("erase", C.c_void_p), ("lm_trials", C.c_int32),
+                ("stopped", C.c_int32), ("first_Hschur", C.c_void_p), ("first_bschur", C.c_void_p), ("first_xp", C.c_void_p),
+                ("first_lambda", C.c_double)]
+
+
+def pack_problem(prob):
+    keep = dict(kf_pose=np.ascontiguousarray(prob["kf_pose"], np.float64), kf_fixed=np.ascontiguousarray(prob["kf_fixed"], np.uint8),
+                pts=np.ascontiguousarray(prob["pts"], np.float64), e_kf=np.ascontiguousarray(prob["e_kf"], np.int32),
+                e_pt=np.ascontiguousarray(prob["e_pt"], np.int32), e_obs=np.ascontiguousarray(prob["e_obs"], np.float64),
+                e_inv_sigma2=np.ascontiguousarray(prob["e_inv_sigma2"], np.float32), e_stereo=np.ascontiguousarray(prob["e_stereo"], np.uint8))
+    P = LbaProblem()
+    P.n_kf, P.n_pts, P.n_edges = len(keep["kf_pose"]), len(keep["pts"]), len(keep["e_kf"])
+    for k, v in keep.items():
+        setattr(P, k, v.ctypes.data)
+    P.fx, P.fy, P.cx, P.cy, P.bf = prob["K"]
+    if prob.get("stop_flag") is not None:
+        keep["stop_flag"] = prob["stop_flag"]
+        P.stop_flag = prob["stop_flag"].ctypes.data
+    return P, keep
+
+
+class Optimizer:
+    """holds the device buffers; LocalBundleAdjustment() is the reference's static method"""
+
+    def __init__(self, max_keyframes=64, max_points=8192, max_edges=65536, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        check(self._L.orbx_lba_create(C.byref(self._h), max_keyframes, max_points, max_edges, device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.orbx_lba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def LocalBundleAdjustment(self, prob, its1=5, its2=10, want_system=False):
+        """-> dict(kf, pts, chi2, erase, trials, stopped[, Hschur, bschur, xp, lambda0])"""
+        P, keep = pack_problem(prob)
+        kf, pt = np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3))
+        chi2, erase = np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8)
+        R = LbaResult()
+        R.kf_pose, R.pts, R.chi2, R.erase = kf.ctypes.data, pt.ctypes.data, chi2.ctypes.data, erase.ctypes.data
+        dim = 6 * int((keep["kf_fixed"] == 0).sum())
+        if want_system:
+            Hs, bs, xp = np.zeros((dim, dim)), np.zeros(dim), np.zeros(dim)
+            R.first_Hschur, R.first_bschur, R.first_xp = Hs.ctypes.data, bs.ctypes.data, xp.ctypes.data
+        check(self._L.orbx_lba_solve_host(self._h, C.byref(P), its1, its2, C.byref(R)))
+        out = dict(kf=kf, pts=pt, chi2=chi2[:P.n_edges], erase=erase[:P.n_edges], trials=R.lm_trials, stopped=R.stopped)
+        if want_system:
+            out.update(Hschur=Hs, bschur=bs, xp=xp, lambda0=R.first_lambda)
+        return out
+
+    def build_schur_timed(self, prob, lam, reps=1, want_system=False):
+        """one Levenberg trial's system build (residuals + Jacobians + quadratic form + Schur complement), `reps` times;
+        -> (milliseconds for all reps, Hschur, bschur)"""
+        P, keep = (pack_problem(prob) if prob is not None else (None, None))
+        ms = C.c_float()
+        Hs = bs = None
+        dim = 6 * int((keep["kf_fixed"] == 0).sum()) if keep else 0
+        if want_system:
+            Hs, bs = np.zeros((dim, dim)), np.zeros(dim)
+        check(self._L.orbx_lba_build_schur_timed(self._h, C.byref(P) if P is not None else None, lam, reps, C.byref(ms),
+                                                 Hs.ctypes.data if want_system else None, bs.ctypes.data if want_system else None))
+        return ms.value, Hs, bs
+
+    def last_launches(self):
+        return self._L.orbx_lba_last_launches(self._h)

@@ -194,6 +194,59 @@ int orbx_matcher_last_launches(const orbx_matcher *m);
 /* diagnostics: how many sweeps the claim resolution of each job of the last call took (synchronises) */
 orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs);
 
+/* =====================================================================================================
+ * Optimizer::LocalBundleAdjustment  (reference include/Optimizer.h:45, src/Optimizer.cc:454-779, and the g2o
+ * pieces it drives: types_six_dof_expmap.{h,cpp}, base_binary_edge.hpp:55-120, robust_kernel_impl.cpp:78-91,
+ * block_solver.hpp:354-486, optimization_algorithm_levenberg.cpp:61-189).
+ * The adapter builds this POD problem exactly where the reference builds the g2o graph (Optimizer.cc:486-655)
+ * and writes the result back where it reads the graph (Optimizer.cc:709-778).
+ * ===================================================================================================== */
+typedef struct {
+    int32_t n_kf;                /* keyframe vertices: local (free) and fixed */
+    const double *kf_pose;       /* n_kf x 7: quaternion (x,y,z,w) then translation = Converter::toSE3Quat(pKF->GetPose()) */
+    const uint8_t *kf_fixed;     /* vSE3->setFixed(...) (Optimizer.cc:529, :541) */
+    int32_t n_pts;
+    const double *pts;           /* n_pts x 3, Converter::toVector3d(pMP->GetWorldPos()) */
+    int32_t n_edges;
+    const int32_t *e_kf, *e_pt;  /* vertex indices of every observation */
+    const double *e_obs;         /* n_edges x 3: kpUn.pt.x, kpUn.pt.y, mvuRight (third unused for monocular edges) */
+    const float *e_inv_sigma2;   /* mvInvLevelSigma2[kpUn.octave] */
+    const uint8_t *e_stereo;     /* 1 = EdgeStereoSE3ProjectXYZ, 0 = EdgeSE3ProjectXYZ */
+    double fx, fy, cx, cy, bf;
+    const volatile uint8_t *stop_flag;   /* pbStopFlag (may be NULL); polled between LM trials */
+} orbx_lba_problem;
+
+typedef struct {
+    double *kf_pose;             /* n_kf x 7, optimised SE3Quat of every keyframe vertex */
+    double *pts;                 /* n_pts x 3 */
+    double *chi2;                /* per edge: e->chi2() as the reference reads it at Optimizer.cc:718/:732 (may be NULL) */
+    uint8_t *erase;              /* per edge: 1 = goes to vToErase (chi2 over 5.991 / 7.815 or depth not positive) (may be NULL) */
+    int32_t lm_trials;           /* Levenberg trials over both rounds */
+    int32_t stopped;             /* 1 = the stop flag was already set, nothing was optimised (Optimizer.cc:656-658) */
+    /* optional inspection of the very first trial (parity tests; NULL to skip): reduced camera system
+     * Hschur (dim x dim, row-major, symmetric), bschur, pose update x_p, with dim = 6 x free keyframes */
+    double *first_Hschur, *first_bschur, *first_xp;
+    double first_lambda;
+} orbx_lba_result;
+
+typedef struct orbx_lba orbx_lba;
+orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int max_points, int max_edges, int device);
+void orbx_lba_destroy(orbx_lba *h);
+
+/* replaces Optimizer::LocalBundleAdjustment from optimizer.initializeOptimization() (Optimizer.cc:659) to the
+ * erase list (:735): optimize(its1) with Huber kernels, outlier classification, optimize(its2) without them.
+ * The reference calls it with its1 = 5, its2 = 10.  Host pointers; synchronous. */
+orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2, orbx_lba_result *res);
+
+/* one Levenberg trial's linear-system work on the current estimates, for bench.py ("LocalBA Schur build"):
+ * residuals + Jacobians + quadratic form (BlockSolver::buildSystem) + Schur complement (BlockSolver::solve up to
+ * the linear solve) with the given lambda, `reps` times back to back on the handle's stream; the elapsed device
+ * time of the repetitions comes back in *ms (CUDA events).  The problem of the last orbx_lba_solve_host call, or
+ * `prob` if non-NULL, is used. */
+orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_problem *prob, double lambda, int reps, float *ms,
+                                       double *Hschur, double *bschur);
+int orbx_lba_last_launches(const orbx_lba *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,6 +290,10 @@ static int schur_solve(lba *S, double lambda, double *xp, double *xl, double *Hs
     double *Hc = (double *)malloc(sizeof(double) * (n ? n * n : 1));
     memcpy(Hc, Hs, sizeof(double) * n * n);
     const int ok = n == 0 ? 1 : chol_solve(Hc, bs, xp, n);
+    if (!ok) {   /* failed factorisation: the trial is rejected whatever x holds; define x = 0 (the CUDA path does the same) */
+        memset(xp, 0, sizeof(double) * n);
+        memset(xl, 0, sizeof(double) * 3 * nl);
+    }
     if (ok) {
         for (int l = 0; l < nl; l++) {
             double c[3] = {S->bl[3 * l], S->bl[3 * l + 1], S->bl[3 * l + 2]};

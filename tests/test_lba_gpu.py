@@ -1,0 +1,90 @@
+"""GPU parity of LocalBundleAdjustment (liborbx.so through the C ABI) against the CPU oracle.
+Tolerance (north_star): 1e-4 relative on pose / point updates, identical outlier sets; the first trial's reduced camera
+system is held to 1e-9 relative (same arithmetic, different summation order)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from orbx import synth
+from orbx.optimizer import Optimizer
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def opt():
+    o = Optimizer(max_keyframes=40, max_points=4000, max_edges=20000)
+    yield o
+    o.close()
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def check_against_oracle(opt, p, its1=5, its2=10):
+    ref = O.lba_solve(p, its1, its2, want_system=True)
+    got = opt.LocalBundleAdjustment(p, its1, its2, want_system=True)
+    # first Levenberg trial: lambda, reduced system, pose update
+    assert abs(got["lambda0"] - ref["lambda0"]) <= 1e-12 * abs(ref["lambda0"])
+    assert rel(got["Hschur"], ref["Hschur"]) < 1e-9 and rel(got["bschur"], ref["bschur"]) < 1e-9
+    assert rel(got["xp"], ref["xp"]) < 1e-6
+    # result of the whole 5 + 10 schedule: updates within 1e-4 relative
+    assert got["trials"] == ref["trials"]
+    d_ref_kf, d_got_kf = ref["kf"] - p["kf_pose"], got["kf"] - p["kf_pose"]
+    d_ref_pt, d_got_pt = ref["pts"] - p["pts"], got["pts"] - p["pts"]
+    assert rel(d_got_kf, d_ref_kf) < TOL, rel(d_got_kf, d_ref_kf)
+    assert rel(d_got_pt, d_ref_pt) < TOL, rel(d_got_pt, d_ref_pt)
+    assert np.array_equal(got["erase"], ref["erase"])
+    assert np.allclose(got["chi2"], ref["chi2"], rtol=1e-4, atol=1e-6)
+    return ref, got
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+@pytest.mark.parametrize("n_fixed", [0, 1, 5])
+def test_c3_config(opt, stereo, n_fixed):
+    """20 keyframes x 3000 points x ~12k edges, 5 + 10 iterations"""
+    p = synth.lba_problem(1 + n_fixed, n_kf=20 + n_fixed if n_fixed == 5 else 20, n_pts=3000, stereo=stereo, n_fixed=n_fixed)
+    ref, got = check_against_oracle(opt, p)
+    assert ref["erase"].sum() > 100 and got["trials"] >= 10
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_small_and_mixed(opt, seed):
+    p = synth.lba_problem(10 + seed, n_kf=4 + seed, n_pts=80 + 40 * seed, obs_per_pt=2 + seed % 3, n_fixed=1)
+    rng = np.random.default_rng(seed)
+    p["e_stereo"] = (rng.random(len(p["e_kf"])) < 0.5).astype(np.uint8)      # mono and stereo edges in one window
+    check_against_oracle(opt, p, 3, 4)
+
+
+def test_fixed_keyframes_do_not_move(opt):
+    p = synth.lba_problem(3, n_kf=8, n_pts=300, n_fixed=3)
+    got = opt.LocalBundleAdjustment(p)
+    assert np.array_equal(got["kf"][:3], p["kf_pose"][:3])
+
+
+def test_stop_flag(opt):
+    p = synth.lba_problem(4, n_kf=4, n_pts=50, n_fixed=1)
+    p["stop_flag"] = np.ones(1, np.uint8)
+    got = opt.LocalBundleAdjustment(p)
+    assert got["stopped"] == 1 and np.array_equal(got["kf"], p["kf_pose"]) and np.array_equal(got["pts"], p["pts"])
+    assert got["trials"] == 0
+
+
+def test_capacity_and_bad_edges(opt):
+    from orbx._lib import OrbxError
+    p = synth.lba_problem(5, n_kf=50, n_pts=100)
+    with pytest.raises(OrbxError):
+        opt.LocalBundleAdjustment(p)          # 50 keyframes > handle's 40
+    p = synth.lba_problem(5, n_kf=4, n_pts=50)
+    p["e_pt"][0] = 999
+    with pytest.raises(OrbxError):
+        opt.LocalBundleAdjustment(p)
+
+
+def test_build_schur_timed_matches_first_system(opt):
+    p = synth.lba_problem(7, n_kf=12, n_pts=1500, n_fixed=2)
+    ref = O.lba_solve(p, 1, 0, want_system=True)
+    ms, Hs, bs = opt.build_schur_timed(p, ref["lambda0"], reps=3, want_system=True)
+    assert ms > 0 and rel(Hs, ref["Hschur"]) < 1e-9 and rel(bs, ref["bschur"]) < 1e-9
