@@ -373,6 +373,38 @@ def main():
     barrier()
     hnp = frames_np
 
+    # ---- LocalBA (20 keyframes x 3000 points x ~12k edges, 5 + 10 iterations), rank 0 only ----
+    lba = None
+    if rank == 0:
+        from orbx.optimizer import Optimizer
+        prob = synth.lba_problem(0, n_kf=20, n_pts=3000, stereo=False, n_fixed=1)
+        op = Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank)
+        op.LocalBundleAdjustment(prob)                    # warm-up
+        reps, trials = 5, 0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r_ = op.LocalBundleAdjustment(prob)
+            trials += r_["trials"]
+        lba_s = time.perf_counter() - t0
+        launches_lba = op.last_launches()
+        ms_build, _, _ = op.build_schur_timed(prob, 100.0, reps=50)
+        lba = {"config": "C3: 20 keyframes (1 fixed), 3000 points, %d mono edges, optimize(5) + optimize(10)" % len(prob["e_kf"]),
+               "lm_trials_per_s": trials / lba_s, "ms_per_window": 1e3 * lba_s / reps, "lm_trials_per_window": trials / reps,
+               "schur_build_us": 1e3 * ms_build / 50, "kernel_launches_per_window": launches_lba,
+               "api": "orbx_lba_solve_host (host buffers in and out, synchronous)",
+               "schur_build": "residuals + Jacobians + quadratic form + Schur complement of one Levenberg trial, device time (CUDA events)"}
+        if not args.no_cpu:
+            from oracle import oracle_py as O
+            t0 = time.perf_counter()
+            trials_c = 0
+            for _ in range(3):
+                trials_c += O.lba_solve(prob)["trials"]
+            cpu_s = time.perf_counter() - t0
+            lba["cpu_lm_trials_per_s"] = trials_c / cpu_s
+            lba["cpu_ms_per_window"] = 1e3 * cpu_s / 3
+            lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
+        op.close()
+
     if dist is not None:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -409,6 +441,7 @@ def main():
                                         "achieved": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9,
                                         "frac": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9 / peak}},
             "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
+            "lba": lba,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
