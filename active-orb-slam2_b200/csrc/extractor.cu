@@ -225,6 +225,10 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
                 c.last_cw = (int16_t)(j1 == nvalid ? last_cw : L.wcell + 6);
                 c.tw = (int16_t)((j1 - 1 - j0) * L.wcell + c.last_cw);
                 c.th = (int16_t)ch;
+                if (c.tw - 6 > 256 || c.th - 6 > 255) {      // the FAST kernel packs tile coordinates in 8 + 8 bits
+                    orbx_set_error("level %d: FAST tile %dx%d too large", l, c.tw, c.th);
+                    return ORBX_ERR_UNSUPPORTED;
+                }
                 g.chunks.push_back(c);
                 const int tp = (int)align_up(c.tw + 3, 4) + 4;
                 if (tp > g.fast_tp) g.fast_tp = tp;

@@ -14,21 +14,30 @@
 
 #define FAST_THREADS 256
 
+__host__ __device__ inline int orbx_fast_out_words(int tp_max, int th_max) {
+    return (tp_max / 2 + ORBX_FAST_CELLS + 2) * (th_max / 2 + 2);
+}
+
 // The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
 // (0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
 
-// score of the pixel at p (row pitch tp) or 0 if it is not a corner at `th`
-__device__ __forceinline__ int fast_score(const uint8_t *p, int tp, int th) {
+// compass test: a 9-arc contains two adjacent compass pixels (ring 0,4,8,12) of the same polarity, so a pixel that
+// fails this cannot be a corner at threshold th
+__device__ __forceinline__ bool fast_compass(const uint8_t *p, int tp, int th) {
     const int v = p[0];
-    // compass test: a 9-arc contains two adjacent compass pixels (0,4,8,12) of the same polarity
     const int c0 = p[3 * tp], c4 = p[3], c8 = p[-3 * tp], c12 = p[-3];
     const int hi = v + th, lo = v - th;
     const unsigned br = (c0 > hi) | ((c4 > hi) << 1) | ((c8 > hi) << 2) | ((c12 > hi) << 3);
     const unsigned dk = (c0 < lo) | ((c4 < lo) << 1) | ((c8 < lo) << 2) | ((c12 < lo) << 3);
-    const unsigned brr = ((br << 1) | (br >> 3)) & 0xf, dkr = ((dk << 1) | (dk >> 3)) & 0xf;
-    if (((br & brr) | (dk & dkr)) == 0) return 0;
+    // adjacent pairs (0,4) (4,8) (8,12) (12,0): x & rotl4(x)
+    return (((br & ((br << 1) | (br >> 3))) | (dk & ((dk << 1) | (dk >> 3)))) & 0xf) != 0;
+}
+
+// score of the pixel at p (row pitch tp) or 0 if it is not a corner at `th`
+__device__ __forceinline__ int fast_score(const uint8_t *p, int tp, int th) {
+    const int v = p[0];
     int r[16];
-    r[0] = c0; r[4] = c4; r[8] = c8; r[12] = c12;
+    r[0] = p[3 * tp]; r[4] = p[3]; r[8] = p[-3 * tp]; r[12] = p[-3];
     r[1] = p[3 * tp + 1]; r[2] = p[2 * tp + 2]; r[3] = p[tp + 3];
     r[5] = p[-tp + 3]; r[6] = p[-2 * tp + 2]; r[7] = p[-3 * tp + 1];
     r[9] = p[-3 * tp - 1]; r[10] = p[-2 * tp - 2]; r[11] = p[-tp - 3];
@@ -63,11 +72,16 @@ struct FastShared {
     int cnt[ORBX_FAST_CELLS];     // survivors per cell in the current pass
     int empty[ORBX_FAST_CELLS];
     int n_out;                    // entries in the output list
+    int n_list;                   // pixels that passed the compass test in the current pass
     int any_empty;
     int base;                     // reserved start in the global candidate list
+    uint8_t cellof[256];          // detection column -> cell of the chunk
 };
 
-// dynamic smem layout: [tile bytes th x tp][score bytes th x tp][out words]
+// dynamic smem layout: [tile bytes th x tp][score bytes th x tp][out words][list u16 th x tp]
+// Three phases per pass, so that only the few pixels that can be corners pay for the 16-arc score and the 3x3
+// suppression: (1) compass test on every pixel, survivors compacted into a list; (2) score of the listed pixels;
+// (3) suppression of the listed pixels with a non-zero score.
 __global__ void __launch_bounds__(FAST_THREADS)
 k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv,
        const OrbxFastChunk *__restrict__ chunks, uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand,
@@ -78,7 +92,8 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     const int frame = blockIdx.y;
     const OrbxLevel &L = lv[ck.level];
     const int tw = ck.tw, th = ck.th;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
 
     // ---- stage the tile: 32-bit loads from the padded level buffer --------------------------------
     const int gx0 = ORBX_EDGE + ck.x0;                // padded-buffer column of the tile origin
@@ -88,42 +103,57 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     uint8_t *tile = smem;
     uint8_t *score = smem + (size_t)tp * th_max;
     uint32_t *out = reinterpret_cast<uint32_t *>(score + (size_t)tp * th_max);
+    uint16_t *list = reinterpret_cast<uint16_t *>(out + orbx_fast_out_words(tp_max, th_max));
     const uint8_t *src = pyr + (size_t)frame * pyr_frame + L.off + (size_t)(ORBX_EDGE + ck.y0) * L.pitch + (gx0 - shift);
-    for (int i = tid; i < words * th; i += FAST_THREADS) {
-        const int r = i / words, c = i - r * words;
-        reinterpret_cast<uint32_t *>(tile + (size_t)r * tp)[c] =
-            __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + c);
+    for (int r = warp; r < th; r += FAST_THREADS / 32) {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch);
+        uint32_t *d = reinterpret_cast<uint32_t *>(tile + (size_t)r * tp);
+        for (int c = lane; c < words; c += 32) d[c] = __ldg(g + c);
     }
     for (int i = tid; i < (tp * th) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
+    const int vw = tw - 6, vh = th - 6;                // detection region
+    const int wcell = ck.wcell;
+    for (int x = tid; x < vw; x += FAST_THREADS) sh.cellof[x] = (uint8_t)(x / wcell);
     if (tid < ORBX_FAST_CELLS) { sh.cnt[tid] = 0; sh.empty[tid] = 1; }
-    if (tid == 0) { sh.n_out = 0; sh.any_empty = 0; }
+    if (tid == 0) { sh.n_out = 0; sh.any_empty = 0; sh.n_list = 0; }
     __syncthreads();
 
-    const uint8_t *t0 = tile + shift;                  // tile pixel (x,y) = t0[y*tp + x]
-    uint8_t *s0 = score + shift;
-    const int vw = tw - 6, vh = th - 6;                // detection region
-    const int npx = vw * vh;
-    const int wcell = ck.wcell;
+    const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
+    uint8_t *s0 = score + shift + 3 * tp + 3;
 
     for (int pass = 0; pass < 2; pass++) {
         const int thr = pass == 0 ? ini_th : min_th;
-        // scores
-        for (int i = tid; i < npx; i += FAST_THREADS) {
-            const int y = i / vw, x = i - y * vw;     // detection-region coordinates
-            if (pass == 1) {
-                if (!sh.empty[x / wcell]) continue;    // only the cells that found nothing at iniThFAST
+        // (1) compass test, survivors -> list (x | y << 8)
+        for (int y = warp; y < vh; y += FAST_THREADS / 32) {
+            const uint8_t *row = t0 + y * tp;
+            for (int xb = 0; xb < vw; xb += 32) {
+                const int x = xb + lane;
+                bool ok = x < vw;
+                if (ok && pass == 1) ok = sh.empty[sh.cellof[x]] != 0;   // only the cells that found nothing at iniThFAST
+                if (ok) ok = fast_compass(row + x, tp, thr);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (m == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh.n_list, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (ok) list[base + __popc(m & lt)] = (uint16_t)(x | (y << 8));
             }
-            s0[(y + 3) * tp + x + 3] = (uint8_t)fast_score(t0 + (y + 3) * tp + x + 3, tp, thr);
         }
         __syncthreads();
-        // 3x3 non-max suppression inside the cell's detection region
-        for (int i = tid; i < npx; i += FAST_THREADS) {
-            const int y = i / vw, x = i - y * vw;
-            const int cell = x / wcell;
-            if (pass == 1 && !sh.empty[cell]) continue;
-            const uint8_t *sp = s0 + (y + 3) * tp + x + 3;
+        const int n_list = sh.n_list;
+        // (2) scores of the listed pixels
+        for (int i = tid; i < n_list; i += FAST_THREADS) {
+            const int pos = list[i], x = pos & 0xff, y = pos >> 8;
+            s0[y * tp + x] = (uint8_t)fast_score(t0 + y * tp + x, tp, thr);
+        }
+        __syncthreads();
+        // (3) 3x3 non-max suppression inside the cell's detection region
+        for (int i = tid; i < n_list; i += FAST_THREADS) {
+            const int pos = list[i], x = pos & 0xff, y = pos >> 8;
+            const uint8_t *sp = s0 + y * tp + x;
             const int s = sp[0];
             if (s == 0) continue;
+            const int cell = sh.cellof[x];
             const int cx0 = cell * wcell;                                   // first detection column of the cell
             const int cx1 = cell == ck.ncells - 1 ? vw : cx0 + wcell;      // one past the last
             const bool l = x > cx0, r = x + 1 < cx1, u = y > 0, d = y + 1 < vh;
@@ -155,6 +185,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
                 sh.empty[tid] = em;
                 if (em) sh.any_empty = 1;
             }
+            if (tid == 0) sh.n_list = 0;
             __syncthreads();
             if (!sh.any_empty) break;
         }
@@ -175,8 +206,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
 
 // tile + score planes, then the survivor list: at most one survivor per 2x2 block of a cell's detection region
 size_t orbx_fast_smem_bytes(int tp_max, int th_max) {
-    const int out_words = (tp_max / 2 + ORBX_FAST_CELLS + 2) * (th_max / 2 + 2);
-    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * out_words;
+    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * orbx_fast_out_words(tp_max, th_max) + sizeof(uint16_t) * tp_max * th_max;
 }
 
 orbx_status orbx_launch_fast(orbx_extractor *e, int batch, cudaStream_t s) {
