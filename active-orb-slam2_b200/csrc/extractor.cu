@@ -51,7 +51,8 @@ static orbx_status grow(T **p, size_t *cap, size_t need) {
 struct Geometry {
     OrbxLevel lv[ORBX_MAX_LEVELS];
     size_t pyr_bytes, blur_bytes, cand_words;
-    std::vector<int2> rtab;
+    std::vector<uint32_t> rxt;
+    std::vector<int2> ryt;
     std::vector<uint32_t> lut;
     std::vector<OrbxFastChunk> chunks;
     std::vector<OrbxBlurTile> btiles;
@@ -169,11 +170,14 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
             g.lut.push_back(((uint32_t)bx[x] << (2 * D)) | spread_bits((uint32_t)(px[x] >> (15 - D))));
         L.luty_off = (int)g.lut.size();
         for (int y = 0; y <= L.bh; y++) g.lut.push_back(spread_bits((uint32_t)(py[y] >> (15 - D))) << 1);
-        // cv::resize tables (OpenCV resize.cpp, INTER_LINEAR 8U: 11-bit coefficients)
+        // cv::resize tables (OpenCV resize.cpp, INTER_LINEAR 8U: 11-bit coefficients), indexed by PADDED output
+        // coordinates so that the REFLECT_101 border of ORBextractor.cc:1122 costs the kernel nothing:
+        //   x entry (u32, one per padded column, 16-byte aligned groups of 4): sx | a1 << 16 | group_flag << 31, a0 = 2048 - a1
+        //   y entry (int2, one per padded row): sy0 | sy1 << 16,  b0 | b1 << 16
         if (l > 0) {
             const OrbxLevel &S = g.lv[l - 1];
             const double sx_ = 1. / ((double)L.w / S.w), sy_ = 1. / ((double)L.h / S.h);
-            L.rx_off = (int)g.rtab.size();
+            std::vector<uint32_t> xe(L.w);
             for (int dx = 0; dx < L.w; dx++) {
                 float fx = (float)((dx + 0.5) * sx_ - 0.5);
                 int sx = (int)floorf(fx);
@@ -181,17 +185,41 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
                 if (sx < 0) { fx = 0; sx = 0; }
                 if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
                 const int a0 = cv_round_f((1.f - fx) * 2048), a1 = cv_round_f(fx * 2048);
-                g.rtab.push_back(make_int2(sx, (a0 & 0xffff) | (a1 << 16)));
+                if (a0 + a1 != 2048 || a1 < 0 || a1 > 2048) {     // cannot happen: (1 - fx) and fx * 2048 are exact in float
+                    orbx_set_error("level %d: resize coefficients of column %d do not sum to 2048", l, dx);
+                    return ORBX_ERR_UNSUPPORTED;
+                }
+                xe[dx] = (uint32_t)sx | ((uint32_t)a1 << 16);
             }
-            L.ry_off = (int)g.rtab.size();
-            for (int dy = 0; dy < L.h; dy++) {
+            while (g.rxt.size() % 4) g.rxt.push_back(0);
+            L.rx_off = (int)g.rxt.size();
+            for (int px = 0; px < L.pitch; px++) {
+                int ix = px - ORBX_EDGE;
+                if (ix < 0) ix = -ix;
+                if (ix >= L.w) ix = 2 * L.w - 2 - ix;
+                g.rxt.push_back(px < L.w + 2 * ORBX_EDGE ? xe[ix] : 0u);
+            }
+            for (int px = 0; px < L.pitch; px += 4) {   // group flag: 4 columns whose sources lie in one 12-byte window
+                uint32_t *q = &g.rxt[L.rx_off + px];
+                bool ok = px + 3 < L.w + 2 * ORBX_EDGE;
+                for (int b = 1; b < 4 && ok; b++) {
+                    const int d = (int)(q[b] & 0xffff) - (int)(q[0] & 0xffff);
+                    ok = d >= 0 && d <= 7;
+                }
+                if (ok) q[0] |= 0x80000000u;
+            }
+            L.ry_off = (int)g.ryt.size();
+            for (int py = 0; py < L.ph; py++) {
+                int dy = py - ORBX_EDGE;
+                if (dy < 0) dy = -dy;
+                if (dy >= L.h) dy = 2 * L.h - 2 - dy;
                 float fy = (float)((dy + 0.5) * sy_ - 0.5);
                 const int sy = (int)floorf(fy);
                 fy -= sy;
                 const int b0 = cv_round_f((1.f - fy) * 2048), b1 = cv_round_f(fy * 2048);
                 const int sy0 = sy < 0 ? 0 : (sy >= S.h ? S.h - 1 : sy);
                 const int sy1 = sy + 1 < 0 ? 0 : (sy + 1 >= S.h ? S.h - 1 : sy + 1);
-                g.rtab.push_back(make_int2(sy0 | (sy1 << 16), (b0 & 0xffff) | (b1 << 16)));
+                g.ryt.push_back(make_int2(sy0 | (sy1 << 16), (b0 & 0xffff) | (b1 << 16)));
             }
         }
         // FAST tiles: runs of cells of one cell row (ORBextractor.cc:785-806 decides which cells exist)
@@ -276,7 +304,8 @@ static orbx_status configure(orbx_extractor *e, int w, int h) {
         if ((st = grow(&e->d_scand, &cap, g.cand_words * mb))) return st;
         e->cand_frame_cap = g.cand_words;
     }
-    if ((st = grow(&e->d_rtab, &e->rtab_cap, g.rtab.size() + 1))) return st;
+    if ((st = grow(&e->d_rxt, &e->rxt_cap, g.rxt.size() + 4))) return st;
+    if ((st = grow(&e->d_ryt, &e->ryt_cap, g.ryt.size() + 1))) return st;
     if ((st = grow(&e->d_lut, &e->lut_cap, g.lut.size() + 1))) return st;
     size_t cap = (size_t)e->chunks_cap;
     if ((st = grow(&e->d_chunks, &cap, g.chunks.size() + 1))) return st;
@@ -284,7 +313,8 @@ static orbx_status configure(orbx_extractor *e, int w, int h) {
     cap = (size_t)e->btiles_cap;
     if ((st = grow(&e->d_btiles, &cap, g.btiles.size() + 1))) return st;
     e->btiles_cap = (int)cap;
-    if (!g.rtab.empty()) ORBX_CUDA(cudaMemcpy(e->d_rtab, g.rtab.data(), sizeof(int2) * g.rtab.size(), cudaMemcpyHostToDevice));
+    if (!g.rxt.empty()) ORBX_CUDA(cudaMemcpy(e->d_rxt, g.rxt.data(), sizeof(uint32_t) * g.rxt.size(), cudaMemcpyHostToDevice));
+    if (!g.ryt.empty()) ORBX_CUDA(cudaMemcpy(e->d_ryt, g.ryt.data(), sizeof(int2) * g.ryt.size(), cudaMemcpyHostToDevice));
     ORBX_CUDA(cudaMemcpy(e->d_lut, g.lut.data(), sizeof(uint32_t) * g.lut.size(), cudaMemcpyHostToDevice));
     if (!g.chunks.empty())
         ORBX_CUDA(cudaMemcpy(e->d_chunks, g.chunks.data(), sizeof(OrbxFastChunk) * g.chunks.size(), cudaMemcpyHostToDevice));
@@ -394,7 +424,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->d_lv); cudaFree(e->d_pyr); cudaFree(e->d_blur); cudaFree(e->d_rtab); cudaFree(e->d_lut);
+    cudaFree(e->d_lv); cudaFree(e->d_pyr); cudaFree(e->d_blur); cudaFree(e->d_rxt); cudaFree(e->d_ryt); cudaFree(e->d_lut);
     cudaFree(e->d_chunks); cudaFree(e->d_btiles); cudaFree(e->d_cand); cudaFree(e->d_skey); cudaFree(e->d_scand);
     cudaFree(e->d_ncand); cudaFree(e->d_lvl_kp); cudaFree(e->d_lvl_cnt); cudaFree(e->d_status); cudaFree(e->d_img);
     cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);

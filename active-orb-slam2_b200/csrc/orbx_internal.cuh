@@ -62,7 +62,7 @@ struct OrbxLevel {
     int cshift;          // key >> cshift == counting-sort cell
     int ncells;          // n_ini << 2*d0, <= ORBX_OCT_CELLS
     int lutx_off, luty_off;  // offsets into the u32 path LUT
-    // resize tables (offsets into the int2 tables)
+    // resize tables (offsets into the u32 column table and the int2 row table)
     int rx_off, ry_off;
 };
 
@@ -99,7 +99,8 @@ struct orbx_extractor {
     uint8_t *d_pyr;           // [max_batch][pyr_frame_cap]
     size_t blur_frame_cap;
     uint8_t *d_blur;          // [max_batch][blur_frame_cap]
-    int2 *d_rtab;  size_t rtab_cap;      // resize offset / coefficient tables
+    uint32_t *d_rxt;  size_t rxt_cap;   // resize tables per padded output column / row (see extractor.cu)
+    int2 *d_ryt;  size_t ryt_cap;
     uint32_t *d_lut;  size_t lut_cap;    // quadtree path LUTs
     OrbxFastChunk *d_chunks;  int n_chunks, chunks_cap;
     int fast_tp, fast_th;     // smem tile pitch / rows of the FAST kernel (max over chunks)

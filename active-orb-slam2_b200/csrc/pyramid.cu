@@ -40,56 +40,76 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t *__restrict__ 
     *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// level l >= 1 from the interior of level l-1
+// bytes b, b+1 (in the low 16 bits) of the 12-byte window (w0, w1, w2), b in [0, 10]
+__device__ __forceinline__ uint32_t window2(uint32_t w0, uint32_t w1, uint32_t w2, int b) {
+    if (b < 4) return __funnelshift_rc(w0, w1, 8 * b);
+    if (b < 8) return __funnelshift_rc(w1, w2, 8 * (b - 4));
+    return w2 >> (8 * (b - 8));
+}
+
+__device__ __forceinline__ uint32_t resize_px(int a1, int b0, int b1, uint32_t t0, uint32_t t1) {
+    const int a0 = 2048 - a1;
+    const int s0 = a0 * (int)(t0 & 0xff) + a1 * (int)((t0 >> 8) & 0xff);
+    const int s1 = a0 * (int)(t1 & 0xff) + a1 * (int)((t1 >> 8) & 0xff);
+    return (uint32_t)((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// level l >= 1 from the interior of level l-1.  One thread = 4 consecutive bytes of one padded output row, so a warp
+// reads 128 consecutive table bytes and writes 128 consecutive output bytes.  Tables are indexed by padded output
+// coordinates (the reflected border is resolved on the host).  When the four source positions fall into one aligned
+// 12-byte window (flag bit of the group; always true in the interior at ORB-SLAM's scale factors) each source row
+// costs three 32-bit loads; otherwise (the few reflected groups at the row ends) bytes are loaded one by one.
 __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel S, OrbxLevel L,
-                                                    const int2 *__restrict__ rx, const int2 *__restrict__ ry) {
-    const int gx = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int py = blockIdx.y;
-    if (gx >= L.pitch) return;
+                                                    const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols4) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = id / cols4, g4 = id - py * cols4;
+    if (py >= L.ph) return;
     uint8_t *frame = pyr + (size_t)blockIdx.z * pyr_frame;
     const uint8_t *sint = frame + S.off + (size_t)ORBX_EDGE * S.pitch + ORBX_EDGE;  // interior origin of the source
-    uint8_t *dst = frame + L.off + (size_t)py * L.pitch + gx;
-    const int iy = reflect101(py - ORBX_EDGE, L.h);
-    const int2 yy = __ldg(ry + iy);
+    const int2 yy = __ldg(ry + py);
     const int sy0 = yy.x & 0xffff, sy1 = yy.x >> 16;
     const int b0 = (int)(short)(yy.y & 0xffff), b1 = yy.y >> 16;
     const uint8_t *r0 = sint + (size_t)sy0 * S.pitch;
     const uint8_t *r1 = sint + (size_t)sy1 * S.pitch;
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t v = 0;
+    const uint4 e4 = __ldg(rx + g4);
+    const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+    const int sx0 = (int)(e[0] & 0xffff);
+    uint32_t v = 0;
+    if (e[0] >> 31) {
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(r0 + sx0), a1 = reinterpret_cast<uintptr_t>(r1 + sx0);
+        const int mis = (int)(a0 & 3);                  // r0 and r1 differ by a multiple of the 16-byte pitch
+        const uint32_t *p0 = reinterpret_cast<const uint32_t *>(a0 - mis), *p1 = reinterpret_cast<const uint32_t *>(a1 - mis);
+        const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int px = gx + q * 4 + b;
-            uint32_t p = 0;
-            if (px < L.w + 2 * ORBX_EDGE) {
-                const int ix = reflect101(px - ORBX_EDGE, L.w);
-                const int2 xx = __ldg(rx + ix);
-                const int sx = xx.x;
-                const int a0 = (int)(short)(xx.y & 0xffff), a1 = xx.y >> 16;
-                const int s0 = a0 * (int)r0[sx] + a1 * (int)r0[sx + 1];   // sx+1 may touch the pad: a1 == 0 there
-                const int s1 = a0 * (int)r1[sx] + a1 * (int)r1[sx + 1];
-                p = (uint32_t)((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2);
-            }
-            v |= p << (8 * b);
+            const int off = mis + ((int)(e[b] & 0xffff) - sx0);
+            v |= resize_px((int)((e[b] >> 16) & 0x7fff), b0, b1, window2(u0, u1, u2, off), window2(v0, v1, v2, off)) << (8 * b);
         }
-        w[q] = v;
+    } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int sx = (int)(e[b] & 0xffff);          // sx+1 may touch the pad: a1 == 0 there
+            const uint32_t t0 = (uint32_t)r0[sx] | ((uint32_t)r0[sx + 1] << 8), t1 = (uint32_t)r1[sx] | ((uint32_t)r1[sx + 1] << 8);
+            v |= resize_px((int)((e[b] >> 16) & 0x7fff), b0, b1, t0, t1) << (8 * b);
+        }
     }
-    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint32_t *>(frame + L.off + (size_t)py * L.pitch + 4 * g4) = v;
 }
 
 orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size_t frame_pitch, int batch, int stride,
                                 cudaStream_t s) {
     for (int l = 0; l < e->nlevels; l++) {
         const OrbxLevel &L = e->lv[l];
-        dim3 block(64);
-        dim3 grid((L.pitch / 16 + block.x - 1) / block.x, L.ph, batch);
-        if (l == 0)
+        if (l == 0) {
+            dim3 block(64);
+            dim3 grid((L.pitch / 16 + block.x - 1) / block.x, L.ph, batch);
             k_pyr_level0<<<grid, block, 0, s>>>(d_images, frame_pitch, stride, e->d_pyr, e->pyr_frame_cap, L);
-        else
-            k_pyr_resize<<<grid, block, 0, s>>>(e->d_pyr, e->pyr_frame_cap, e->lv[l - 1], L,
-                                                e->d_rtab + L.rx_off, e->d_rtab + L.ry_off);
+        } else {
+            const int cols4 = L.pitch / 4, total = cols4 * L.ph;
+            dim3 grid((total + 255) / 256, 1, batch);
+            k_pyr_resize<<<grid, 256, 0, s>>>(e->d_pyr, e->pyr_frame_cap, e->lv[l - 1], L,
+                                              reinterpret_cast<const uint4 *>(e->d_rxt + L.rx_off), e->d_ryt + L.ry_off, cols4);
+        }
         e->last_launches++;
     }
     ORBX_CUDA(cudaGetLastError());
