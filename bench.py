@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -163,16 +163,12 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count() or 1
     frames = make_frames(64)
-    budget = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
-    for _ in range(args.warmup):
-        cpu_path(frames, min(budget, 1.0), cores)
-    vals, n_frames = [], 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fps, n, dt = cpu_path(frames, budget, cores)
-        vals.append(fps); n_frames += n
-    total = time.perf_counter() - t0
-    v = n_frames / total
+    # K "steps" are K equal slices of ONE timed run with persistent worker threads (a step is a bounded sample of the
+    # workload; starting threads and extractors per slice would only measure that overhead)
+    cpu_path(frames, 3.0 if args.warmup else 0.5, cores)
+    total_budget = max(10.0, min(60.0, 0.2 * args.steps))
+    v, n_frames, total = cpu_path(frames, total_budget, cores)
+    budget = total / max(args.steps, 1)
     sample = "%d steps x %.1f s of G-rect VGA frames (extract + SearchByProjection vs predecessor) on %d host threads, one oracle extractor per thread" % (args.steps, budget, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -190,7 +186,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
@@ -302,14 +298,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()                                      # sampled from the warm-up to the end of the end-to-end loop
     for i in range(Wm):
         step_device(i)
     torch.cuda.synchronize()
     launches_per_step = ex.last_launches() + 1 + 1      # + fill kernel + matcher kernel
     ex.profile(K)
     ev_m = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -323,7 +319,6 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop()
     runs, stage_ms = ex.stage_ms()
     stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / K
     ex.profile(0)
@@ -370,6 +365,7 @@ def main():
         nm_e2e += step_host(Wm + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
     barrier()
     hnp = frames_np
 
