@@ -34,6 +34,8 @@ struct orbx_matcher {
     // staging of the _host entry points (one job)
     orbx_keypoint *d_keys; uint8_t *d_desc; float *d_uright; uint8_t *d_claimed; float *d_scale;
     void *d_pts; uint8_t *d_ptdesc; int32_t *d_match; int32_t *d_nm; orbx_frame_match_job *d_job;
+    int *d_items;     // [jobs][2][max_pts] bucket matchers: work item -> (feature of a, node of b)
+    uint8_t *d_arena; size_t arena_cap, arena_used;   // staging of the bucket matchers' host inputs
     cudaStream_t stream;
     int last_launches;
 };
@@ -487,6 +489,183 @@ k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ choice_all,
     if (tid == 0) { *J.nmatches = sh.nacc; sweeps_all[job] = sh.changed; }
 }
 
+// ---- SearchByBoW (KF, F) / (KF, KF) and SearchForTriangulation --------------------------------------------------
+struct BucketDev {
+    orbx_bucket_job J;          // all pointers are device pointers
+    int32_t *match_a, *nmatches;
+};
+
+// work item = one feature of set a that lives in a node shared with set b, in the reference's processing order
+struct BucketEval {
+    const BucketDev &Jd;
+    const int *item_a, *item_bnode;    // per item: feature index in a, node index in b
+    __device__ bool blocks(int) const { return Jd.J.mode != 2; }        // SearchForTriangulation never sets vbMatched2
+    __device__ int decide(unsigned k1, int p1, unsigned k2, int) const {
+        const orbx_bucket_job &J = Jd.J;
+        const int d1 = (int)(k1 >> 22);
+        if (J.mode == 2) return p1 & 0xffff;                              // candidates are already <= TH_LOW and gated
+        const int d2 = k2 == 0xffffffffu ? 256 : (int)(k2 >> 22);
+        const bool pass = J.mode == 0 ? d1 <= 50 : d1 < 50;               // TH_LOW; ORBmatcher.cc:233 vs :598
+        if (!pass || !((float)d1 < __fmul_rn(J.nnratio, (float)d2))) return -1;
+        return p1 & 0xffff;
+    }
+    template <class Emit>
+    __device__ void candidates(int i, Emit emit) const {
+        const orbx_bucket_job &J = Jd.J;
+        const int lane = threadIdx.x & 31;
+        const int idx1 = item_a[i], nb = item_bnode[i];
+        if (!J.a.valid[idx1]) return;
+        const bool st1 = J.a.u_right && J.a.u_right[idx1] >= 0;
+        if (J.mode == 2 && J.only_stereo && !st1) return;
+        const uint8_t *d = J.a.desc + (size_t)32 * idx1;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
+        const int s = J.b.node_start[nb], e = J.b.node_start[nb + 1];
+        float la = 0, lb = 0, lc = 0, den = 0;
+        if (J.mode == 2) {     // epipolar line of kp1 in image 2, CheckDistEpipolarLine (ORBmatcher.cc:140-157)
+            const float x = J.a.keys_un[idx1].x, y = J.a.keys_un[idx1].y;
+            la = __fadd_rn(__fadd_rn(__fmul_rn(x, J.F12[0]), __fmul_rn(y, J.F12[3])), J.F12[6]);
+            lb = __fadd_rn(__fadd_rn(__fmul_rn(x, J.F12[1]), __fmul_rn(y, J.F12[4])), J.F12[7]);
+            lc = __fadd_rn(__fadd_rn(__fmul_rn(x, J.F12[2]), __fmul_rn(y, J.F12[5])), J.F12[8]);
+            den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        }
+        for (int kb = s; kb < e; kb += 32) {
+            const int k = kb + lane;
+            bool valid = k < e;
+            unsigned key = 0;
+            int idx2 = 0;
+            if (valid) {
+                idx2 = J.b.node_feat[k];
+                if (J.mode != 0 && !J.b.valid[idx2]) valid = false;
+            }
+            if (valid) {
+                const int dist = hamming256(d0, d1, J.b.desc + (size_t)32 * idx2);
+                const int seq = k - s;
+                if (J.mode == 2) {
+                    // the reference keeps a candidate when dist <= running best: the LAST of equal distances wins
+                    key = ((unsigned)dist << 22) | (unsigned)(0x3fffff - seq);
+                    const bool st2 = J.b.u_right && J.b.u_right[idx2] >= 0;
+                    if (J.only_stereo && !st2) valid = false;
+                    if (dist > 50) valid = false;
+                    const orbx_keypoint kp2 = J.b.keys_un[idx2];
+                    if (valid && !st1 && !st2) {
+                        const float dx = __fsub_rn(J.ex, kp2.x), dy = __fsub_rn(J.ey, kp2.y);
+                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, J.scale_b[kp2.octave])) valid = false;
+                    }
+                    if (valid) {
+                        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+                        if (den == 0) valid = false;
+                        else {
+                            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                            valid = (double)dsqr < __dmul_rn(3.84, (double)J.sigma2_b[kp2.octave]);
+                        }
+                    }
+                } else {
+                    key = ((unsigned)dist << 22) | (unsigned)seq;
+                }
+            }
+            emit(valid, key, idx2);
+        }
+    }
+};
+
+__global__ void __launch_bounds__(M_THREADS)
+k_match_buckets(const BucketDev *__restrict__ jobs, int *__restrict__ choice_all, int *__restrict__ minclaim_all,
+                int *__restrict__ items_all, int *__restrict__ sweeps_all, int2 *__restrict__ cand_all, int *__restrict__ lcount_all,
+                int max_kp, int max_pts) {
+    extern __shared__ __align__(16) int dyn[];      // node scan: [n_nodes_a + 1]
+    __shared__ MatchShared sh;
+    __shared__ BucketDev Jd;
+    const int tid = threadIdx.x, job = blockIdx.x;
+    if (tid == 0) Jd = jobs[job];
+    __syncthreads();
+    const orbx_bucket_job &J = Jd.J;
+    const int nA = min(J.a.n, max_pts), nB = min(J.b.n, max_kp);
+    int *choice2 = choice_all + (size_t)job * 2 * max_pts, *minclaim2 = minclaim_all + (size_t)job * 2 * max_kp;
+    int *item_a = items_all + (size_t)job * 2 * max_pts, *item_bnode = item_a + max_pts;
+    // merge-join of the two FeatureVectors (ORBmatcher.cc:176-258): every node of a looks its id up in b
+    int *off = dyn;
+    const int nna = J.a.n_nodes;
+    for (int ia = tid; ia <= nna; ia += M_THREADS) {
+        int cnt = 0;
+        if (ia < nna) {
+            const uint32_t id = J.a.node_id[ia];
+            int lo = 0, hi = J.b.n_nodes;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (J.b.node_id[mid] < id) lo = mid + 1; else hi = mid; }
+            if (lo < J.b.n_nodes && J.b.node_id[lo] == id) cnt = J.a.node_start[ia + 1] - J.a.node_start[ia];
+        }
+        off[ia] = cnt;
+    }
+    const int n_items = min(block_excl_scan(off, nna + 1, sh.warp_tmp), max_pts);
+    for (int ia = tid; ia < nna; ia += M_THREADS) {
+        const int cnt = (ia + 1 <= nna ? off[ia + 1] : n_items) - off[ia];
+        if (cnt <= 0) continue;
+        const uint32_t id = J.a.node_id[ia];
+        int lo = 0, hi = J.b.n_nodes;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (J.b.node_id[mid] < id) lo = mid + 1; else hi = mid; }
+        for (int k = 0; k < cnt && off[ia] + k < max_pts; k++) {
+            item_a[off[ia] + k] = J.a.node_feat[J.a.node_start[ia] + k];
+            item_bnode[off[ia] + k] = lo;
+        }
+    }
+    __syncthreads();
+    BucketEval ev{Jd, item_a, item_bnode};
+    int fb;
+    resolve_claims(nB, n_items, nullptr, choice2, minclaim2, cand_all + (size_t)job * M_CAND * max_pts,
+                   lcount_all + (size_t)job * 2 * max_pts, lcount_all + (size_t)job * 2 * max_pts + max_pts, max_pts, max_kp, sh, ev, fb);
+    const int *choice = choice2 + (size_t)fb * max_pts;
+    for (int i = tid; i < nA; i += M_THREADS) Jd.match_a[i] = -1;
+    if (tid < HISTO_LENGTH) sh.hist[tid] = 0;
+    if (tid == 0) { sh.nacc = 0; sh.nrej = 0; }
+    __syncthreads();
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nacc = 0;
+    for (int i = tid; i < n_items; i += M_THREADS) {
+        const int c = choice[i];
+        if (c < 0) continue;
+        nacc++;
+        const int idx1 = item_a[i];
+        Jd.match_a[idx1] = c;                 // a feature appears in exactly one node: no write conflict
+        if (J.check_ori) {
+            float rot = __fsub_rn(J.a.keys_un[idx1].angle, J.b.keys_un[c].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == HISTO_LENGTH) bin = 0;
+            if (bin >= 0 && bin < HISTO_LENGTH) atomicAdd(&sh.hist[bin], 1);
+        }
+    }
+    if (nacc) atomicAdd(&sh.nacc, nacc);
+    __syncthreads();
+    if (tid == 0) {   // ComputeThreeMaxima
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = sh.hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+            else if (s > max3) { max3 = s; i3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+        sh.keep[0] = i1; sh.keep[1] = i2; sh.keep[2] = i3;
+    }
+    __syncthreads();
+    if (J.check_ori) {
+        int nrej = 0;
+        for (int i = tid; i < n_items; i += M_THREADS) {
+            const int c = choice[i];
+            if (c < 0) continue;
+            const int idx1 = item_a[i];
+            float rot = __fsub_rn(J.a.keys_un[idx1].angle, J.b.keys_un[c].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == HISTO_LENGTH) bin = 0;
+            if (bin != sh.keep[0] && bin != sh.keep[1] && bin != sh.keep[2]) { Jd.match_a[idx1] = -1; nrej++; }
+        }
+        if (nrej) atomicAdd(&sh.nrej, nrej);
+    }
+    __syncthreads();
+    if (tid == 0) { *Jd.nmatches = sh.nacc - sh.nrej; sweeps_all[job] = sh.changed; }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 extern "C" int orbx_hamming256(const uint8_t a[32], const uint8_t b[32]) {
     int d = 0;
@@ -503,7 +682,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
-    cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_sweeps); cudaFree(m->d_cand); cudaFree(m->d_lcount); cudaFree(m->d_keys);
+    cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_sweeps); cudaFree(m->d_items); cudaFree(m->d_arena); cudaFree(m->d_cand); cudaFree(m->d_lcount); cudaFree(m->d_keys);
     cudaFree(m->d_desc); cudaFree(m->d_uright); cudaFree(m->d_claimed); cudaFree(m->d_scale); cudaFree(m->d_pts);
     cudaFree(m->d_ptdesc); cudaFree(m->d_match); cudaFree(m->d_nm); cudaFree(m->d_job);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -544,6 +723,9 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     TRY(cudaMalloc((void **)&m->d_minclaim, sizeof(int) * 2 * kp * jb));
     TRY(cudaMalloc((void **)&m->d_owner, sizeof(int) * kp * jb));
     TRY(cudaMalloc((void **)&m->d_sweeps, sizeof(int) * jb));
+    TRY(cudaMalloc((void **)&m->d_items, sizeof(int) * 2 * pt * jb));
+    m->arena_cap = 2 * (kp + pt) * (28 + 32 + 4 + 1 + 4 + 8) + 4096;
+    TRY(cudaMalloc((void **)&m->d_arena, m->arena_cap));
     TRY(cudaMalloc((void **)&m->d_cand, sizeof(int2) * M_CAND * pt * jb));
     TRY(cudaMalloc((void **)&m->d_lcount, sizeof(int) * 2 * pt * jb));
     TRY(cudaMalloc((void **)&m->d_keys, sizeof(orbx_keypoint) * kp));
@@ -560,6 +742,7 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     m->smem = (int)match_smem_bytes(max_keypoints);
     TRY(ORBX_RAISE_SMEM(k_match_frame));
     TRY(ORBX_RAISE_SMEM(k_match_points));
+    TRY(ORBX_RAISE_SMEM(k_match_buckets));
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_matcher_create: %s", cudaGetErrorString(ce));
@@ -695,5 +878,85 @@ extern "C" orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, i
     ORBX_CUDA(cudaSetDevice(m->device));
     ORBX_CUDA(cudaDeviceSynchronize());
     ORBX_CUDA(cudaMemcpy(out, m->d_sweeps, sizeof(int32_t) * n_jobs, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+// bump allocator over the staging arena: copies `bytes` from the host and returns the device address
+static orbx_status arena_put(orbx_matcher *m, const void *src, size_t bytes, const void **dev, cudaStream_t s) {
+    *dev = nullptr;
+    if (!src || bytes == 0) return ORBX_OK;
+    const size_t off = (m->arena_used + 15) & ~(size_t)15;
+    if (off + bytes > m->arena_cap) {
+        orbx_set_error("bucket matcher inputs exceed the staging arena (%zu bytes)", m->arena_cap);
+        return ORBX_ERR_CAPACITY;
+    }
+    ORBX_CUDA(cudaMemcpyAsync(m->d_arena + off, src, bytes, cudaMemcpyHostToDevice, s));
+    *dev = m->d_arena + off;
+    m->arena_used = off + bytes;
+    return ORBX_OK;
+}
+
+static orbx_status stage_bow_set(orbx_matcher *m, const orbx_bow_set *H, orbx_bow_set *D, int cap, cudaStream_t s) {
+    if (H->n < 0 || H->n_nodes < 0 || (H->n && (!H->keys_un || !H->desc || !H->valid)) ||
+        (H->n_nodes && (!H->node_id || !H->node_start || !H->node_feat)))
+        return ORBX_ERR_INVALID;
+    if (H->n > cap) {
+        orbx_set_error("%d features, matcher was created for %d", H->n, cap);
+        return ORBX_ERR_CAPACITY;
+    }
+    const int nf = H->n_nodes ? H->node_start[H->n_nodes] : 0;
+    if (nf < 0 || nf > H->n) return ORBX_ERR_INVALID;
+    for (int i = 0; i < H->n_nodes; i++) {
+        if (H->node_start[i] > H->node_start[i + 1] || (i && H->node_id[i - 1] >= H->node_id[i])) return ORBX_ERR_INVALID;
+    }
+    for (int k = 0; k < nf; k++) if (H->node_feat[k] < 0 || H->node_feat[k] >= H->n) return ORBX_ERR_INVALID;
+    *D = *H;
+    orbx_status st;
+    const void *p;
+    if ((st = arena_put(m, H->keys_un, sizeof(orbx_keypoint) * H->n, &p, s))) return st; D->keys_un = (const orbx_keypoint *)p;
+    if ((st = arena_put(m, H->desc, (size_t)32 * H->n, &p, s))) return st; D->desc = (const uint8_t *)p;
+    if ((st = arena_put(m, H->u_right, H->u_right ? sizeof(float) * H->n : 0, &p, s))) return st; D->u_right = (const float *)p;
+    if ((st = arena_put(m, H->valid, H->n, &p, s))) return st; D->valid = (const uint8_t *)p;
+    if ((st = arena_put(m, H->node_id, sizeof(uint32_t) * H->n_nodes, &p, s))) return st; D->node_id = (const uint32_t *)p;
+    if ((st = arena_put(m, H->node_start, sizeof(int32_t) * (H->n_nodes + 1), &p, s))) return st; D->node_start = (const int32_t *)p;
+    if ((st = arena_put(m, H->node_feat, sizeof(int32_t) * nf, &p, s))) return st; D->node_feat = (const int32_t *)p;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match_buckets_host(orbx_matcher *m, const orbx_bucket_job *job, int32_t *match_a, int32_t *nmatches) {
+    if (!m || !job || !match_a || !nmatches || job->mode < 0 || job->mode > 2) return ORBX_ERR_INVALID;
+    if (job->mode == 2 && (!job->sigma2_b || !job->scale_b || job->nlevels < 1 || job->nlevels > 64)) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    m->arena_used = 0;
+    BucketDev D;
+    memset(&D, 0, sizeof(D));
+    D.J = *job;
+    orbx_status st;
+    if ((st = stage_bow_set(m, &job->a, &D.J.a, m->max_pts, s))) return st;
+    if ((st = stage_bow_set(m, &job->b, &D.J.b, m->max_kp, s))) return st;
+    if (job->mode == 2) {
+        for (int i = 0; i < job->b.n; i++)
+            if (job->b.keys_un[i].octave < 0 || job->b.keys_un[i].octave >= job->nlevels) return ORBX_ERR_INVALID;
+        const void *p;
+        if ((st = arena_put(m, job->sigma2_b, sizeof(float) * job->nlevels, &p, s))) return st; D.J.sigma2_b = (const float *)p;
+        if ((st = arena_put(m, job->scale_b, sizeof(float) * job->nlevels, &p, s))) return st; D.J.scale_b = (const float *)p;
+    }
+    D.match_a = m->d_match;       // max_kp entries; set a is bounded by max_pts: use the larger of the two buffers
+    if (job->a.n > m->max_kp) {
+        orbx_set_error("%d features in set a, matcher was created for %d keypoints", job->a.n, m->max_kp);
+        return ORBX_ERR_CAPACITY;
+    }
+    D.nmatches = m->d_nm;
+    const void *djob;
+    if ((st = arena_put(m, &D, sizeof(D), &djob, s))) return st;
+    const size_t smem = sizeof(int) * ((size_t)job->a.n_nodes + 2);
+    k_match_buckets<<<1, M_THREADS, smem, s>>>((const BucketDev *)djob, m->d_choice, m->d_minclaim, m->d_items, m->d_sweeps, m->d_cand,
+                                               m->d_lcount, m->max_kp, m->max_pts);
+    m->last_launches = 1;
+    ORBX_CUDA(cudaGetLastError());
+    if (job->a.n) ORBX_CUDA(cudaMemcpyAsync(match_a, m->d_match, sizeof(int32_t) * job->a.n, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
     return ORBX_OK;
 }

@@ -120,3 +120,70 @@ class ORBmatcher:
         out = np.zeros(n_jobs, np.int32)
         check(self._L.orbx_matcher_last_sweeps(self._h, out.ctypes.data, n_jobs))
         return out
+
+
+class BowSet(C.Structure):
+    """orbx_bow_set (include/orbx.h)"""
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("valid", C.c_void_p),
+                ("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("node_start", C.c_void_p), ("node_feat", C.c_void_p)]
+
+
+class BucketJob(C.Structure):
+    """orbx_bucket_job (include/orbx.h)"""
+    _fields_ = [("a", BowSet), ("b", BowSet), ("mode", C.c_int32), ("nnratio", C.c_float), ("check_ori", C.c_int32),
+                ("only_stereo", C.c_int32), ("F12", C.c_float * 9), ("ex", C.c_float), ("ey", C.c_float),
+                ("sigma2_b", C.c_void_p), ("scale_b", C.c_void_p), ("nlevels", C.c_int32)]
+
+
+def _bow_set(S, d, valid, keep):
+    arrs = dict(keys_un=np.ascontiguousarray(d["keys_un"], KP_DTYPE), desc=np.ascontiguousarray(d["desc"], np.uint8),
+                u_right=np.ascontiguousarray(d["u_right"], np.float32), valid=np.ascontiguousarray(valid, np.uint8),
+                node_id=np.ascontiguousarray(d["node_id"], np.uint32), node_start=np.ascontiguousarray(d["node_start"], np.int32),
+                node_feat=np.ascontiguousarray(d["node_feat"], np.int32))
+    keep.append(arrs)
+    S.n, S.n_nodes = len(arrs["keys_un"]), len(arrs["node_id"])
+    for k, v in arrs.items():
+        setattr(S, k, v.ctypes.data)
+
+
+def _buckets(self, mode, A, B, va, vb, only_stereo=False, F12=None, epipole=(0, 0), sigma2=None, scale=None):
+    J, keep = BucketJob(), []
+    _bow_set(J.a, A, va, keep); _bow_set(J.b, B, vb, keep)
+    J.mode, J.nnratio, J.check_ori, J.only_stereo = mode, self.mfNNratio, int(self.mbCheckOrientation), int(only_stereo)
+    if F12 is not None:
+        J.F12[:] = np.asarray(F12, np.float32).reshape(9).tolist()
+    J.ex, J.ey = float(epipole[0]), float(epipole[1])
+    s2 = np.ascontiguousarray(sigma2 if sigma2 is not None else np.ones(8), np.float32)
+    sc = np.ascontiguousarray(scale if scale is not None else np.ones(8), np.float32)
+    J.sigma2_b, J.scale_b, J.nlevels = s2.ctypes.data, sc.ctypes.data, len(s2)
+    m = np.zeros(max(J.a.n, 1), np.int32)
+    n = C.c_int32()
+    check(self._L.orbx_match_buckets_host(self._h, C.byref(J), m.ctypes.data, C.byref(n)))
+    return n.value, m[:J.a.n]
+
+
+def _search_by_bow_frame(self, KF, F):
+    """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), ORBmatcher.cc:159 -> (nmatches, matches indexed by the frame's
+    features = keyframe feature index or -1)"""
+    n, ma = _buckets(self, 0, KF, F, KF["has_mp"], F["has_mp"])
+    out = np.full(len(F["keys_un"]), -1, np.int32)
+    sel = ma >= 0
+    out[ma[sel]] = np.nonzero(sel)[0]
+    return n, out
+
+
+def _search_by_bow_kf(self, KF1, KF2):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), ORBmatcher.cc:522 -> (nmatches, match12)"""
+    return _buckets(self, 1, KF1, KF2, KF1["has_mp"], KF2["has_mp"])
+
+
+def _search_for_triangulation(self, KF1, KF2, F12, epipole, sigma2_2, scale_2, bOnlyStereo=False):
+    """SearchForTriangulation, ORBmatcher.cc:657 -> (nmatches, vMatchedPairs as an (n, 2) array sorted by idx1)"""
+    n, ma = _buckets(self, 2, KF1, KF2, 1 - KF1["has_mp"], 1 - KF2["has_mp"], bOnlyStereo, F12, epipole, sigma2_2, scale_2)
+    idx1 = np.nonzero(ma >= 0)[0]
+    return n, np.stack([idx1, ma[idx1]], 1)
+
+
+ORBmatcher.SearchByBoW = _search_by_bow_frame
+ORBmatcher.SearchByBoWKF = _search_by_bow_kf
+ORBmatcher.SearchForTriangulation = _search_for_triangulation

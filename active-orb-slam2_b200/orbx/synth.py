@@ -261,3 +261,60 @@ def lba_problem(seed, n_kf=20, n_pts=3000, obs_per_pt=4, stereo=False, n_fixed=0
                 e_obs=np.array(e_obs, np.float64).reshape(-1, 3), e_inv_sigma2=np.array(e_is2, np.float32),
                 e_stereo=np.array(e_st, np.uint8), K=(float(np.float32(fx)), float(np.float32(fy)), float(np.float32(cx)),
                                                       float(np.float32(cy)), float(np.float32(bf))))
+
+
+# ---- vocabulary-node matcher scenes: two keyframes seeing the same 3-D points ---------------------------------------
+def bow_pair(seed, n_a=1000, n_b=1000, n_common=600, n_nodes=90, nlevels=8):
+    """Two feature sets with `n_common` true correspondences (similar descriptors, same vocabulary node, consistent
+    epipolar geometry), the rest unrelated.  Returns (A, B, F12, (ex, ey), sigma2, scale) with A/B dicts holding
+    keys_un, desc, u_right, has_mp (the feature already has a map point), node_id, node_start, node_feat."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf, _ = TUM1_K
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    sf = scale_factors(nlevels)
+    # camera 1 at the origin, camera 2 displaced and slightly rotated
+    R21 = _rot(1, rng.uniform(-0.1, 0.1)) @ _rot(0, rng.uniform(-0.03, 0.03))
+    t21 = np.array([rng.uniform(0.2, 0.5), rng.uniform(-0.05, 0.05), rng.uniform(-0.1, 0.1)])
+    X = np.stack([rng.uniform(-2, 2, n_common), rng.uniform(-1.5, 1.5, n_common), rng.uniform(2, 8, n_common)], 1)
+    x1 = (K @ X.T).T; x1 = x1[:, :2] / x1[:, 2:]
+    X2 = (R21 @ X.T).T + t21
+    x2 = (K @ X2.T).T; x2 = x2[:, :2] / x2[:, 2:]
+
+    def make_set(n, xy_common, desc_common, node_common, oct_common):
+        k = np.zeros(n, KP_DTYPE)
+        k["x"] = rng.uniform(20, 620, n); k["y"] = rng.uniform(20, 460, n)
+        k["octave"] = rng.integers(0, nlevels, n)
+        k["angle"] = rng.uniform(0, 360, n)
+        desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        node = rng.integers(0, n_nodes, n)
+        slots = rng.permutation(n)[:len(xy_common)]
+        k["x"][slots] = xy_common[:, 0] + rng.normal(0, 0.4, len(slots))
+        k["y"][slots] = xy_common[:, 1] + rng.normal(0, 0.4, len(slots))
+        k["octave"][slots] = oct_common
+        desc[slots] = desc_common
+        node[slots] = node_common
+        ur = np.where(rng.random(n) < 0.4, k["x"] - rng.uniform(2, 30, n), -1).astype(np.float32)
+        has_mp = (rng.random(n) < 0.5).astype(np.uint8)
+        # FeatureVector: ascending node ids (sparse ids like DBoW2 node numbers), lists in ascending feature order
+        ids = np.unique(node)
+        start = np.zeros(len(ids) + 1, np.int32)
+        feat = []
+        for j, nid in enumerate(ids):
+            f = np.nonzero(node == nid)[0]
+            feat.append(f); start[j + 1] = start[j] + len(f)
+        return dict(keys_un=k, desc=desc, u_right=ur, has_mp=has_mp, node_id=(ids * 7 + 3).astype(np.uint32), node_start=start,
+                    node_feat=np.concatenate(feat).astype(np.int32) if feat else np.zeros(0, np.int32)), slots
+
+    dcom = rng.integers(0, 256, (n_common, 32), dtype=np.uint8)
+    ncom = rng.integers(0, n_nodes, n_common)
+    ocom = rng.integers(0, nlevels, n_common)
+    A, sa = make_set(n_a, x1, dcom, ncom, ocom)
+    B, sb = make_set(n_b, x2, flip_bits(rng, dcom, rng.integers(0, 70, n_common)), ncom, np.clip(ocom + rng.integers(-1, 2, n_common), 0, nlevels - 1))
+    A["angle_ref"] = None
+    B["keys_un"]["angle"][sb] = np.mod(A["keys_un"]["angle"][sa] + rng.normal(0, 6, n_common) + np.where(rng.random(n_common) < 0.08, 120, 0), 360)
+    tx = np.array([[0, -t21[2], t21[1]], [t21[2], 0, -t21[0]], [-t21[1], t21[0], 0]])
+    F12 = (np.linalg.inv(K).T @ (tx @ R21) @ np.linalg.inv(K)).T          # x1^T F12 x2 = 0  (ORB-SLAM2's convention)
+    F12 = (F12 / np.abs(F12).max()).astype(np.float32)
+    C2 = t21                                                              # camera-1 centre in camera-2 coordinates
+    ex, ey = np.float32(fx * C2[0] / C2[2] + cx), np.float32(fy * C2[1] / C2[2] + cy)
+    return A, B, F12, (ex, ey), (sf * sf).astype(np.float32), sf

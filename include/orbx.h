@@ -190,6 +190,38 @@ typedef struct {
 } orbx_frame_match_job;
 orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
                                                void *stream);
+/* ---- vocabulary-node ("bucket") matchers ---------------------------------------------------------------------
+ * replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)        (ORBmatcher.cc:159-288)  mode 0
+ *          ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)      (ORBmatcher.cc:522-655)  mode 1
+ *          ORBmatcher::SearchForTriangulation(KF1, KF2, F12, pairs, onlyStereo)   (ORBmatcher.cc:657-823)  mode 2
+ * A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) is passed as ascending node ids + CSR lists.
+ * `valid` carries the per-feature map-point tests of the reference: modes 0/1: pMP && !pMP->isBad() (set b: mode 1
+ * only); mode 2: the feature has NO map point yet (both sets).
+ * match_a[i] = index in set b matched to feature i of set a, or -1.  Mode 0: the reference's output
+ * vpMapPointMatches is indexed by the frame's features; it is the inverse of match_a (a frame feature is claimed at
+ * most once).  Mode 2: vMatchedPairs = every (i, match_a[i]) with match_a[i] >= 0, in ascending i. */
+typedef struct {
+    int32_t n;
+    const orbx_keypoint *keys_un; /* mvKeysUn */
+    const uint8_t *desc;         /* n x 32 */
+    const float *u_right;        /* mvuRight (may be NULL) */
+    const uint8_t *valid;
+    int32_t n_nodes;
+    const uint32_t *node_id;     /* ascending */
+    const int32_t *node_start;   /* n_nodes + 1 */
+    const int32_t *node_feat;    /* feature indices, node by node */
+} orbx_bow_set;
+typedef struct {
+    orbx_bow_set a, b;
+    int32_t mode;
+    float nnratio;               /* mfNNratio */
+    int32_t check_ori, only_stereo;
+    float F12[9], ex, ey;        /* mode 2: F12 row-major; epipole of camera 1 in image 2 (ORBmatcher.cc:663-670) */
+    const float *sigma2_b, *scale_b;   /* mode 2: pKF2->mvLevelSigma2, pKF2->mvScaleFactors */
+    int32_t nlevels;
+} orbx_bucket_job;
+orbx_status orbx_match_buckets_host(orbx_matcher *m, const orbx_bucket_job *job, int32_t *match_a, int32_t *nmatches);
+
 int orbx_matcher_last_launches(const orbx_matcher *m);
 /* diagnostics: how many sweeps the claim resolution of each job of the last call took (synchronises) */
 orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs);

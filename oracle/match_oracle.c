@@ -233,3 +233,108 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
     grid_free(&g);
     return nmatches;
 }
+
+/* ---- bucket (vocabulary-node) matchers -------------------------------------------------------------------------
+ * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)        src/ORBmatcher.cc:159-288   mode 0
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)     src/ORBmatcher.cc:522-655   mode 1
+ * ORBmatcher::SearchForTriangulation(...)                src/ORBmatcher.cc:657-823   mode 2  (+ CheckDistEpipolarLine :140-157)
+ * A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) is given as sorted node ids + CSR lists.
+ * match_a[i] = index in set B matched to feature i of set A, or -1.  For mode 0 the reference's output is indexed by
+ * the frame's features (vpMapPointMatches[idxF] = pMP of idxKF); that array is the inverse of match_a (every B index
+ * is claimed at most once) and the caller inverts it. */
+static int check_epipolar(const orbo_keypoint *kp1, const orbo_keypoint *kp2, const float *F12, const float *sigma2_b) {
+    const float a = kp1->x * F12[0] + kp1->y * F12[3] + F12[6];
+    const float b = kp1->x * F12[1] + kp1->y * F12[4] + F12[7];
+    const float c = kp1->x * F12[2] + kp1->y * F12[5] + F12[8];
+    const float num = a * kp2->x + b * kp2->y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return 0;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2_b[kp2->octave];
+}
+
+int orbo_match_buckets(const orbo_bucket_job *J, int32_t *match_a) {
+    const orbo_bow_set *A = &J->a, *B = &J->b;
+    uint8_t *matched_b = (uint8_t *)calloc(B->n > 0 ? B->n : 1, 1);
+    int *hist_a = (int *)malloc(sizeof(int) * (A->n > 0 ? A->n : 1)), *hist_bin = (int *)malloc(sizeof(int) * (A->n > 0 ? A->n : 1));
+    int nh = 0, nmatches = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < A->n; i++) match_a[i] = -1;
+    int ia = 0, ib = 0;
+    while (ia < A->n_nodes && ib < B->n_nodes) {
+        if (A->node_id[ia] == B->node_id[ib]) {
+            for (int k1 = A->node_start[ia]; k1 < A->node_start[ia + 1]; k1++) {
+                const int idx1 = A->node_feat[k1];
+                if (!A->valid[idx1]) continue;               /* mode 0/1: !pMP || isBad; mode 2: already has a MapPoint */
+                const uint8_t *d1 = A->desc + (size_t)32 * idx1;
+                if (J->mode == 2) {
+                    const int bStereo1 = A->u_right && A->u_right[idx1] >= 0;
+                    if (J->only_stereo && !bStereo1) continue;
+                    int bestDist = TH_LOW, bestIdx2 = -1;
+                    for (int k2 = B->node_start[ib]; k2 < B->node_start[ib + 1]; k2++) {
+                        const int idx2 = B->node_feat[k2];
+                        if (matched_b[idx2] || !B->valid[idx2]) continue;     /* vbMatched2 is never set by the reference */
+                        const int bStereo2 = B->u_right && B->u_right[idx2] >= 0;
+                        if (J->only_stereo && !bStereo2) continue;
+                        const int dist = orbo_hamming256(d1, B->desc + (size_t)32 * idx2);
+                        if (dist > TH_LOW || dist > bestDist) continue;
+                        const orbo_keypoint *kp2 = &B->keys_un[idx2];
+                        if (!bStereo1 && !bStereo2) {
+                            const float distex = J->ex - kp2->x, distey = J->ey - kp2->y;
+                            if (distex * distex + distey * distey < 100 * J->scale_b[kp2->octave]) continue;
+                        }
+                        if (check_epipolar(&A->keys_un[idx1], kp2, J->F12, J->sigma2_b)) { bestIdx2 = idx2; bestDist = dist; }
+                    }
+                    if (bestIdx2 >= 0) {
+                        match_a[idx1] = bestIdx2;
+                        nmatches++;
+                        if (J->check_ori) {
+                            float rot = A->keys_un[idx1].angle - B->keys_un[bestIdx2].angle;
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            hist_a[nh] = idx1; hist_bin[nh] = bin; nh++;
+                        }
+                    }
+                } else {
+                    int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                    for (int k2 = B->node_start[ib]; k2 < B->node_start[ib + 1]; k2++) {
+                        const int idx2 = B->node_feat[k2];
+                        if (matched_b[idx2]) continue;                          /* vpMapPointMatches[realIdxF] / vbMatched2[idx2] */
+                        if (J->mode == 1 && !B->valid[idx2]) continue;           /* !pMP2 || pMP2->isBad() */
+                        const int dist = orbo_hamming256(d1, B->desc + (size_t)32 * idx2);
+                        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                        else if (dist < bestDist2) bestDist2 = dist;
+                    }
+                    const int pass = J->mode == 0 ? bestDist1 <= TH_LOW : bestDist1 < TH_LOW;
+                    if (pass && (float)bestDist1 < J->nnratio * (float)bestDist2) {
+                        match_a[idx1] = bestIdx2;
+                        matched_b[bestIdx2] = 1;
+                        if (J->check_ori) {
+                            float rot = A->keys_un[idx1].angle - B->keys_un[bestIdx2].angle;
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)roundf(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            hist_a[nh] = idx1; hist_bin[nh] = bin; nh++;
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            ia++; ib++;
+        } else if (A->node_id[ia] < B->node_id[ib]) {
+            while (ia < A->n_nodes && A->node_id[ia] < B->node_id[ib]) ia++;     /* lower_bound */
+        } else {
+            while (ib < B->n_nodes && B->node_id[ib] < A->node_id[ia]) ib++;
+        }
+    }
+    if (J->check_ori) {
+        int cnt[HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (int j = 0; j < nh; j++) cnt[hist_bin[j]]++;
+        orbo_three_maxima(cnt, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int j = 0; j < nh; j++)
+            if (hist_bin[j] != i1 && hist_bin[j] != i2 && hist_bin[j] != i3) { match_a[hist_a[j]] = -1; nmatches--; }
+    }
+    free(matched_b); free(hist_a); free(hist_bin);
+    return nmatches;
+}

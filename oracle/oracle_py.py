@@ -344,3 +344,52 @@ def lba_solve(prob, its1=5, its2=10, want_system=False):
         d = tr.dim
         out.update(Hschur=Hs.reshape(-1)[:d * d].reshape(d, d).copy(), bschur=bs[:d].copy(), xp=xp[:d].copy(), lambda0=tr.lambda0)
     return out
+
+
+# ---- vocabulary-node matchers --------------------------------------------------------------------------------
+class OBowSet(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("valid", C.c_void_p),
+                ("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("node_start", C.c_void_p), ("node_feat", C.c_void_p)]
+
+
+class OBucketJob(C.Structure):
+    _fields_ = [("a", OBowSet), ("b", OBowSet), ("mode", C.c_int32), ("nnratio", C.c_float), ("check_ori", C.c_int32),
+                ("only_stereo", C.c_int32), ("F12", C.c_float * 9), ("ex", C.c_float), ("ey", C.c_float),
+                ("sigma2_b", C.c_void_p), ("scale_b", C.c_void_p)]
+
+
+def fill_bow_set(S, d, valid, keep):
+    arrs = dict(keys_un=np.ascontiguousarray(d["keys_un"], KP_DTYPE), desc=np.ascontiguousarray(d["desc"], np.uint8),
+                u_right=np.ascontiguousarray(d["u_right"], np.float32), valid=np.ascontiguousarray(valid, np.uint8),
+                node_id=np.ascontiguousarray(d["node_id"], np.uint32), node_start=np.ascontiguousarray(d["node_start"], np.int32),
+                node_feat=np.ascontiguousarray(d["node_feat"], np.int32))
+    keep.append(arrs)
+    S.n, S.n_nodes = len(arrs["keys_un"]), len(arrs["node_id"])
+    for k, v in arrs.items():
+        setattr(S, k, v.ctypes.data)
+
+
+def bucket_valid(mode, A, B):
+    """per-feature map-point tests of the three reference functions"""
+    if mode == 2:
+        return 1 - A["has_mp"], 1 - B["has_mp"]
+    return A["has_mp"], B["has_mp"]
+
+
+def match_buckets(mode, A, B, nnratio=0.75, check_ori=True, only_stereo=False, F12=None, epipole=(0, 0), sigma2=None, scale=None):
+    """mode 0 SearchByBoW(KF,F), 1 SearchByBoW(KF,KF), 2 SearchForTriangulation -> (nmatches, match_a)"""
+    L = lib()
+    L.orbo_match_buckets.argtypes = [C.POINTER(OBucketJob), C.c_void_p]
+    J, keep = OBucketJob(), []
+    va, vb = bucket_valid(mode, A, B)
+    fill_bow_set(J.a, A, va, keep); fill_bow_set(J.b, B, vb, keep)
+    J.mode, J.nnratio, J.check_ori, J.only_stereo = mode, nnratio, int(check_ori), int(only_stereo)
+    if F12 is not None:
+        J.F12[:] = np.asarray(F12, np.float32).reshape(9).tolist()
+    J.ex, J.ey = float(epipole[0]), float(epipole[1])
+    s2 = np.ascontiguousarray(sigma2 if sigma2 is not None else np.ones(8), np.float32)
+    sc = np.ascontiguousarray(scale if scale is not None else np.ones(8), np.float32)
+    J.sigma2_b, J.scale_b = s2.ctypes.data, sc.ctypes.data
+    m = np.zeros(max(J.a.n, 1), np.int32)
+    n = L.orbo_match_buckets(C.byref(J), _p(m))
+    return n, m[:J.a.n]

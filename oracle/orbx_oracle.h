@@ -96,6 +96,26 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
                                     const float Rcw[9], const float tcw[3], int forward, int backward, float th,
                                     int check_ori, int32_t *match);
 
+typedef struct {                 /* one KeyFrame / Frame as the vocabulary-node matchers read it */
+    int32_t n;
+    const orbo_keypoint *keys_un; /* mvKeysUn (angle, pt, octave) */
+    const uint8_t *desc;         /* n x 32 */
+    const float *u_right;        /* mvuRight (may be NULL) */
+    const uint8_t *valid;        /* see orbo_match_buckets */
+    int32_t n_nodes;             /* DBoW2::FeatureVector: node ids ascending, CSR lists of feature indices */
+    const uint32_t *node_id;
+    const int32_t *node_start, *node_feat;
+} orbo_bow_set;
+typedef struct {
+    orbo_bow_set a, b;
+    int32_t mode;                /* 0 SearchByBoW(KF, F), 1 SearchByBoW(KF, KF), 2 SearchForTriangulation */
+    float nnratio;
+    int32_t check_ori, only_stereo;
+    float F12[9], ex, ey;        /* mode 2: fundamental matrix (row-major) and epipole of camera 1 in image 2 */
+    const float *sigma2_b, *scale_b;   /* pKF2->mvLevelSigma2, mvScaleFactors */
+} orbo_bucket_job;
+int orbo_match_buckets(const orbo_bucket_job *J, int32_t *match_a);
+
 /* ---- local bundle adjustment (src/Optimizer.cc:454-779 + g2o) ---- */
 typedef struct {
     int32_t n_kf;                /* keyframe vertices: local (free) and fixed */

@@ -169,3 +169,85 @@ def test_search_by_projection_points(seed):
         n2, m2 = brute_points(F, pts, desc, th, 0.8)
         assert n == n2 and np.array_equal(m, m2)
     assert n > 50
+
+
+# ---- vocabulary-node matchers (ORBmatcher.cc:159-288, :522-655, :657-823) ---------------------------------------
+def brute_buckets(mode, A, B, nnratio, check_ori, only_stereo, F12, epi, sigma2, scale):
+    va, vb = O.bucket_valid(mode, A, B)
+    nodes_a = {int(n): A["node_feat"][A["node_start"][j]:A["node_start"][j + 1]] for j, n in enumerate(A["node_id"])}
+    nodes_b = {int(n): B["node_feat"][B["node_start"][j]:B["node_start"][j + 1]] for j, n in enumerate(B["node_id"])}
+    match = np.full(len(va), -1, np.int32)
+    taken = np.zeros(len(vb), bool)
+    hist, nm = [], 0
+    ka, kb = A["keys_un"], B["keys_un"]
+    F = np.asarray(F12, f32).reshape(3, 3) if F12 is not None else None
+    for nid in sorted(set(nodes_a) & set(nodes_b)):
+        for i1 in nodes_a[nid]:
+            if not va[i1]:
+                continue
+            if mode == 2:
+                st1 = A["u_right"][i1] >= 0
+                if only_stereo and not st1:
+                    continue
+                best, bi = 50, -1
+                a = f32(f32(f32(ka["x"][i1] * F[0, 0]) + f32(ka["y"][i1] * F[1, 0])) + F[2, 0])
+                b = f32(f32(f32(ka["x"][i1] * F[0, 1]) + f32(ka["y"][i1] * F[1, 1])) + F[2, 1])
+                c = f32(f32(f32(ka["x"][i1] * F[0, 2]) + f32(ka["y"][i1] * F[1, 2])) + F[2, 2])
+                for i2 in nodes_b[nid]:
+                    if not vb[i2]:
+                        continue
+                    st2 = B["u_right"][i2] >= 0
+                    if only_stereo and not st2:
+                        continue
+                    d = popcount_dist(A["desc"][i1], B["desc"][i2])
+                    if d > 50 or d > best:
+                        continue
+                    if not st1 and not st2:
+                        dx, dy = f32(epi[0] - kb["x"][i2]), f32(epi[1] - kb["y"][i2])
+                        if f32(f32(dx * dx) + f32(dy * dy)) < f32(f32(100) * scale[kb["octave"][i2]]):
+                            continue
+                    num = f32(f32(f32(a * kb["x"][i2]) + f32(b * kb["y"][i2])) + c)
+                    den = f32(f32(a * a) + f32(b * b))
+                    if den == 0 or not (np.float64(f32(f32(num * num) / den)) < 3.84 * np.float64(sigma2[kb["octave"][i2]])):
+                        continue
+                    best, bi = d, i2
+                if bi >= 0:
+                    match[i1] = bi; nm += 1
+                    hist.append(i1)
+            else:
+                b1, b2, bi = 256, 256, -1
+                for i2 in nodes_b[nid]:
+                    if taken[i2] or (mode == 1 and not vb[i2]):
+                        continue
+                    d = popcount_dist(A["desc"][i1], B["desc"][i2])
+                    if d < b1:
+                        b2, b1, bi = b1, d, i2
+                    elif d < b2:
+                        b2 = d
+                if (b1 <= 50 if mode == 0 else b1 < 50) and f32(b1) < f32(f32(nnratio) * f32(b2)):
+                    match[i1] = bi; taken[bi] = True; nm += 1
+                    hist.append(i1)
+    if check_ori:
+        bins = []
+        for i1 in hist:
+            rot = f32(ka["angle"][i1] - kb["angle"][match[i1]])
+            if rot < 0:
+                rot = f32(rot + f32(360))
+            bn = int(np.floor(f32(rot * f32(1.0 / 30)) + f32(0.5)))
+            bins.append(0 if bn == 30 else bn)
+        keep = O.three_maxima(np.bincount(bins, minlength=30)) if bins else (-1, -1, -1)
+        for i1, bn in zip(hist, bins):
+            if bn not in keep:
+                match[i1] = -1; nm -= 1
+    return nm, match
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_bucket_matchers(mode, seed):
+    A, B, F12, epi, s2, sc = synth.bow_pair(seed, 400, 450, 250, n_nodes=25)
+    for only_stereo in ([False, True] if mode == 2 else [False]):
+        n, m = O.match_buckets(mode, A, B, 0.75, True, only_stereo, F12, epi, s2, sc)
+        n2, m2 = brute_buckets(mode, A, B, 0.75, True, only_stereo, F12, epi, s2, sc)
+        assert n == n2 and np.array_equal(m, m2)
+        assert n > (0 if only_stereo else 30)

@@ -134,3 +134,36 @@ def test_dense_windows_overflow_path(matcher, seed):
     n_ref, m_ref = O.search_by_projection_points(cur, tp, tdesc, 5.0, 0.8)
     n, m = matcher.SearchByProjection(cur, tp, tdesc, 5.0)
     assert n == n_ref and np.array_equal(m, m_ref)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("seed", range(4))
+def test_bucket_matchers(matcher, mode, seed):
+    """SearchByBoW(KF, F), SearchByBoW(KF, KF), SearchForTriangulation vs the oracle"""
+    A, B, F12, epi, s2, sc = synth.bow_pair(40 + seed, 1000 + 100 * seed, 1100, 600, n_nodes=90 if seed % 2 else 12)
+    matcher.mfNNratio = 0.75
+    try:
+        for only_stereo in ([False, True] if mode == 2 else [False]):
+            n_ref, m_ref = O.match_buckets(mode, A, B, 0.75, True, only_stereo, F12, epi, s2, sc)
+            if mode == 0:
+                n, mf = matcher.SearchByBoW(A, B)
+                inv = np.full(len(B["keys_un"]), -1, np.int32)
+                inv[m_ref[m_ref >= 0]] = np.nonzero(m_ref >= 0)[0]
+                assert n == n_ref and np.array_equal(mf, inv)
+            elif mode == 1:
+                n, m = matcher.SearchByBoWKF(A, B)
+                assert n == n_ref and np.array_equal(m, m_ref)
+            else:
+                n, pairs = matcher.SearchForTriangulation(A, B, F12, epi, s2, sc, only_stereo)
+                idx1 = np.nonzero(m_ref >= 0)[0]
+                assert n == n_ref and np.array_equal(pairs, np.stack([idx1, m_ref[idx1]], 1))
+            assert n_ref > 0
+    finally:
+        matcher.mfNNratio = 0.8
+
+
+def test_bucket_matchers_disjoint_vocabularies(matcher):
+    A, B, F12, epi, s2, sc = synth.bow_pair(9, 300, 300, 100, n_nodes=10)
+    B = dict(B, node_id=B["node_id"] + 1000)          # no shared node at all
+    n, m = matcher.SearchByBoWKF(A, B)
+    assert n == 0 and (m == -1).all()
