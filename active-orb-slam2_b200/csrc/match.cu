@@ -287,9 +287,10 @@ struct FrameEval {
     const orbx_frame_view &F;
     const MatchGrid &g;
     int2 *list;      // this warp's compaction list (M_LIST entries)
-    __device__ bool blocks(int i) const { return J.pts[i].blocks != 0; }
+    __device__ bool blocks(int i) const { return J.variant == 1 || J.pts[i].blocks != 0; }
     __device__ int decide(unsigned k1, int p1, unsigned, int) const {
-        return (k1 >> 22) <= TH_HIGH ? (p1 & 0xffff) : -1;        // ORBmatcher.cc:1421
+        const int lim = J.max_dist > 0 ? J.max_dist : TH_HIGH;     // ORBmatcher.cc:1421 (TH_HIGH) / :1553 (ORBdist)
+        return (int)(k1 >> 22) <= lim ? (p1 & 0xffff) : -1;
     }
     template <class Emit>
     __device__ void candidates(int i, Emit emit) const {
@@ -300,7 +301,7 @@ struct FrameEval {
         const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], p.x), __fmul_rn(R[4], p.y)), __fmul_rn(R[5], p.z)), t[1]);
         const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], p.x), __fmul_rn(R[7], p.y)), __fmul_rn(R[8], p.z)), t[2]);
         const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)zc));     // const float invzc = 1.0/x3Dc.at<float>(2)
-        if (invzc < 0) return;
+        if (J.variant == 0 && invzc < 0) return;                 // the KeyFrame overload has no depth-sign test
         const float u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, xc), invzc), F.cx);
         const float v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, yc), invzc), F.cy);
         if (u < F.min_x || u > F.max_x) return;
@@ -308,8 +309,8 @@ struct FrameEval {
         const int oct = p.octave;
         const float radius = __fmul_rn(J.th, F.scale_factors[oct]);
         int minL, maxL;
-        if (J.forward) { minL = oct; maxL = -1; }
-        else if (J.backward) { minL = 0; maxL = oct; }
+        if (J.variant == 0 && J.forward) { minL = oct; maxL = -1; }
+        else if (J.variant == 0 && J.backward) { minL = 0; maxL = oct; }
         else { minL = oct - 1; maxL = oct + 1; }
         const uint8_t *d = J.last_desc + (size_t)32 * i;
         const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
@@ -317,7 +318,7 @@ struct FrameEval {
         features_in_area(F, g, list, u, v, radius, minL, maxL, [&](bool valid, int i2, int seq) {
             unsigned key = 0;
             if (valid) {
-                const float urk = F.u_right ? F.u_right[i2] : -1.f;
+                const float urk = (F.u_right && J.variant == 0) ? F.u_right[i2] : -1.f;
                 key = ((unsigned)hamming256(d0, d1, F.desc + (size_t)32 * i2) << 22) | (unsigned)seq;
                 if (urk > 0 && fabsf(__fsub_rn(ur, urk)) > radius) valid = false;      // ORBmatcher.cc:1405-1411
             }
@@ -796,10 +797,9 @@ extern "C" orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const
     return ORBX_OK;
 }
 
-extern "C" orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const orbx_frame_view *cur, int n_last,
-                                                        const orbx_last_point *pts, const uint8_t *last_desc, const float Rcw[9],
-                                                        const float tcw[3], int forward, int backward, float th, int check_ori,
-                                                        int32_t *match, int32_t *nmatches) {
+static orbx_status match_frame_host(orbx_matcher *m, const orbx_frame_view *cur, int n_last, const orbx_last_point *pts,
+                                    const uint8_t *last_desc, const float Rcw[9], const float tcw[3], int forward, int backward,
+                                    float th, int check_ori, int max_dist, int variant, int32_t *match, int32_t *nmatches) {
     if (!m || !cur || n_last < 0 || !match || !nmatches || !Rcw || !tcw || (n_last && (!pts || !last_desc))) return ORBX_ERR_INVALID;
     if (n_last > m->max_pts) {
         orbx_set_error("%d points, matcher was created for %d", n_last, m->max_pts);
@@ -824,6 +824,7 @@ extern "C" orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const o
     memcpy(J.Rcw, Rcw, sizeof(J.Rcw));
     memcpy(J.tcw, tcw, sizeof(J.tcw));
     J.forward = forward; J.backward = backward; J.th = th; J.check_ori = check_ori;
+    J.max_dist = max_dist; J.variant = variant;
     J.match = m->d_match; J.nmatches = m->d_nm;
     ORBX_CUDA(cudaMemcpyAsync(m->d_job, &J, sizeof(J), cudaMemcpyHostToDevice, s));
     st = orbx_match_projection_frame_device(m, m->d_job, 1, s);
@@ -832,6 +833,21 @@ extern "C" orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const o
     ORBX_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaStreamSynchronize(s));
     return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const orbx_frame_view *cur, int n_last,
+                                                        const orbx_last_point *pts, const uint8_t *last_desc, const float Rcw[9],
+                                                        const float tcw[3], int forward, int backward, float th, int check_ori,
+                                                        int32_t *match, int32_t *nmatches) {
+    return match_frame_host(m, cur, n_last, pts, last_desc, Rcw, tcw, forward, backward, th, check_ori, TH_HIGH, 0, match, nmatches);
+}
+
+extern "C" orbx_status orbx_match_projection_keyframe_host(orbx_matcher *m, const orbx_frame_view *cur, int n_pts,
+                                                           const orbx_last_point *pts, const uint8_t *pt_desc, const float Rcw[9],
+                                                           const float tcw[3], float th, int orb_dist, int check_ori, int32_t *match,
+                                                           int32_t *nmatches) {
+    if (orb_dist < 1 || orb_dist > 256) return ORBX_ERR_INVALID;
+    return match_frame_host(m, cur, n_pts, pts, pt_desc, Rcw, tcw, 0, 0, th, check_ori, orb_dist, 1, match, nmatches);
 }
 
 extern "C" orbx_status orbx_match_projection_points_host(orbx_matcher *m, const orbx_frame_view *F, int n_pts,

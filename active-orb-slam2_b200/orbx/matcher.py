@@ -30,7 +30,8 @@ class FrameMatchJob(C.Structure):
     """orbx_frame_match_job (include/orbx.h)"""
     _fields_ = [("cur", FrameView), ("n_last", C.c_int32), ("pts", C.c_void_p), ("last_desc", C.c_void_p),
                 ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("forward", C.c_int32), ("backward", C.c_int32),
-                ("th", C.c_float), ("check_ori", C.c_int32), ("match", C.c_void_p), ("nmatches", C.c_void_p)]
+                ("th", C.c_float), ("check_ori", C.c_int32), ("match", C.c_void_p), ("nmatches", C.c_void_p),
+                ("max_dist", C.c_int32), ("variant", C.c_int32)]
 
 
 def fill_view(f, bounds, K, nlevels):
@@ -110,6 +111,20 @@ class ORBmatcher:
         check(self._L.orbx_match_projection_frame_host(self._h, C.byref(f), len(pts), pts.ctypes.data, pd.ctypes.data, R, t,
                                                        int(forward), int(backward), th, int(self.mbCheckOrientation),
                                                        m.ctypes.data, C.byref(n)))
+        return n.value, m
+
+    def SearchByProjectionKF(self, Cur, pts, pt_desc, Rcw, tcw, th, ORBdist, match=None):
+        """SearchByProjection(Frame &Cur, KeyFrame*, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1472 -> (nmatches, match);
+        pts[i].valid / .octave carry the adapter's host-side gates and PredictScale (see include/orbx.h)"""
+        f, keep = _view(Cur)
+        pts = np.ascontiguousarray(pts, LAST_POINT_DTYPE)
+        pd = np.ascontiguousarray(pt_desc, np.uint8)
+        R = (C.c_float * 9)(*np.asarray(Rcw, np.float32).reshape(9).tolist())
+        t = (C.c_float * 3)(*np.asarray(tcw, np.float32).reshape(3).tolist())
+        m = np.full(f.n, -1, np.int32) if match is None else np.ascontiguousarray(match, np.int32).copy()
+        n = C.c_int32()
+        check(self._L.orbx_match_projection_keyframe_host(self._h, C.byref(f), len(pts), pts.ctypes.data, pd.ctypes.data, R, t, th,
+                                                          int(ORBdist), int(self.mbCheckOrientation), m.ctypes.data, C.byref(n)))
         return n.value, m
 
     def search_frames_device(self, d_jobs, n_jobs, stream=0):

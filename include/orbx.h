@@ -174,6 +174,17 @@ orbx_status orbx_match_projection_frame_host(orbx_matcher *m, const orbx_frame_v
                                              const float Rcw[9], const float tcw[3], int forward, int backward,
                                              float th, int check_ori, int32_t *match, int32_t *nmatches);
 
+/* replaces int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound,
+ * const float th, const int ORBdist) (ORBmatcher.cc:1472-1599, relocalisation).  pts[i] describes pKF's map point i:
+ * valid = pMP && !isBad() && !sAlreadyFound.count(pMP) && the distance-invariance gate of :1516-1521; octave =
+ * pMP->PredictScale(dist3D, &CurrentFrame) (:1523) -- both evaluated by the adapter in the reference's own
+ * arithmetic; angle = pKF->mvKeysUn[i].angle.  cur->claimed marks every non-NULL mvpMapPoints entry (this overload
+ * does not look at Observations()); there is no depth-sign and no uRight test in this overload. */
+orbx_status orbx_match_projection_keyframe_host(orbx_matcher *m, const orbx_frame_view *cur, int n_pts,
+                                                const orbx_last_point *pts, const uint8_t *pt_desc, const float Rcw[9],
+                                                const float tcw[3], float th, int orb_dist, int check_ori,
+                                                int32_t *match, int32_t *nmatches);
+
 /* batched, device-resident form of the call above: every pointer inside a job is a device pointer; d_jobs is a
  * device array of n_jobs (<= max_jobs) independent (current, last) pairs.  Only enqueues on `stream`. */
 typedef struct {
@@ -187,6 +198,8 @@ typedef struct {
     int32_t check_ori;
     int32_t *match;              /* cur.n entries, in/out */
     int32_t *nmatches;           /* 1 entry */
+    int32_t max_dist;            /* accept threshold: TH_HIGH = 100 for the LastFrame overload; 0 means 100 */
+    int32_t variant;             /* 0 = LastFrame overload; 1 = KeyFrame (relocalisation) overload, see below */
 } orbx_frame_match_job;
 orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
                                                void *stream);

@@ -234,6 +234,68 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
     return nmatches;
 }
 
+/* SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist),
+ * ORBmatcher.cc:1472-1599 (relocalisation).  The caller evaluates the per-point host geometry exactly as the reference
+ * does (isBad / sAlreadyFound / distance-invariance gate :1516-1521 -> valid; MapPoint::PredictScale :1523 -> octave);
+ * every non-NULL mvpMapPoints entry blocks (claimed), and so does every match made here. */
+int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_last_point *Lp, const uint8_t *pt_desc,
+                                 const float Rcw[9], const float tcw[3], float th, int orb_dist, int check_ori, int32_t *match) {
+    grid_t g;
+    grid_build(Cur, &g);
+    int *ind = (int *)malloc(sizeof(int) * (Cur->n > 0 ? Cur->n : 1));
+    uint8_t *blocked = (uint8_t *)calloc(Cur->n > 0 ? Cur->n : 1, 1);
+    for (int k = 0; k < Cur->n; k++) blocked[k] = Cur->claimed ? Cur->claimed[k] : 0;
+    int *hist_kp = (int *)malloc(sizeof(int) * (n_pts > 0 ? n_pts : 1)), *hist_bin = (int *)malloc(sizeof(int) * (n_pts > 0 ? n_pts : 1));
+    int nh = 0, nmatches = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i = 0; i < n_pts; i++) {
+        const orbo_last_point *p = &Lp[i];
+        if (!p->valid) continue;
+        const float xc = ((Rcw[0] * p->x + Rcw[1] * p->y) + Rcw[2] * p->z) + tcw[0];
+        const float yc = ((Rcw[3] * p->x + Rcw[4] * p->y) + Rcw[5] * p->z) + tcw[1];
+        const float zc = ((Rcw[6] * p->x + Rcw[7] * p->y) + Rcw[8] * p->z) + tcw[2];
+        const float invzc = (float)(1.0 / (double)zc);          /* no depth-sign test in this overload */
+        const float u = Cur->fx * xc * invzc + Cur->cx;
+        const float v = Cur->fy * yc * invzc + Cur->cy;
+        if (u < Cur->min_x || u > Cur->max_x) continue;
+        if (v < Cur->min_y || v > Cur->max_y) continue;
+        const int lvl = p->octave;                                /* nPredictedLevel */
+        const float radius = th * Cur->scale_factors[lvl];
+        const int n = features_in_area(Cur, &g, u, v, radius, lvl - 1, lvl + 1, ind);
+        if (n == 0) continue;
+        const uint8_t *d = pt_desc + (size_t)32 * i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < n; c++) {
+            const int i2 = ind[c];
+            if (blocked[i2]) continue;
+            const int dist = orbo_hamming256(d, Cur->desc + (size_t)32 * i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            match[bestIdx2] = i;
+            blocked[bestIdx2] = 1;
+            nmatches++;
+            if (check_ori) {
+                float rot = p->angle - Cur->keys_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                hist_kp[nh] = bestIdx2; hist_bin[nh] = bin; nh++;
+            }
+        }
+    }
+    if (check_ori) {
+        int cnt[HISTO_LENGTH] = {0}, i1, i2, i3;
+        for (int j = 0; j < nh; j++) cnt[hist_bin[j]]++;
+        orbo_three_maxima(cnt, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int j = 0; j < nh; j++)
+            if (hist_bin[j] != i1 && hist_bin[j] != i2 && hist_bin[j] != i3) { match[hist_kp[j]] = -1; nmatches--; }
+    }
+    free(ind); free(blocked); free(hist_kp); free(hist_bin);
+    grid_free(&g);
+    return nmatches;
+}
+
 /* ---- bucket (vocabulary-node) matchers -------------------------------------------------------------------------
  * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)        src/ORBmatcher.cc:159-288   mode 0
  * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)     src/ORBmatcher.cc:522-655   mode 1

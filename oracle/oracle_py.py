@@ -393,3 +393,18 @@ def match_buckets(mode, A, B, nnratio=0.75, check_ori=True, only_stereo=False, F
     m = np.zeros(max(J.a.n, 1), np.int32)
     n = L.orbo_match_buckets(C.byref(J), _p(m))
     return n, m[:J.a.n]
+
+
+def search_by_projection_kf(cur, pts, pt_desc, Rcw, tcw, th, orb_dist, check_ori=True, match=None):
+    """ORBmatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) -> (nmatches, match[Cur.n])"""
+    L = lib(); _declare_match(L)
+    L.orbo_search_by_projection_kf.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                               C.c_int, C.c_int, C.c_void_p]
+    f, keep = _oframe(cur)
+    pts = np.ascontiguousarray(pts, LAST_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    R = np.ascontiguousarray(Rcw, np.float32).reshape(9)
+    t = np.ascontiguousarray(tcw, np.float32).reshape(3)
+    m = np.full(f.n, -1, np.int32) if match is None else np.ascontiguousarray(match, np.int32).copy()
+    n = L.orbo_search_by_projection_kf(C.byref(f), len(pts), _p(pts), _p(pd), _p(R), _p(t), th, orb_dist, int(check_ori), _p(m))
+    return n, m

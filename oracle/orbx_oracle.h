@@ -96,6 +96,8 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
                                     const float Rcw[9], const float tcw[3], int forward, int backward, float th,
                                     int check_ori, int32_t *match);
 
+int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_last_point *Lp, const uint8_t *pt_desc,
+                                 const float Rcw[9], const float tcw[3], float th, int orb_dist, int check_ori, int32_t *match);
 typedef struct {                 /* one KeyFrame / Frame as the vocabulary-node matchers read it */
     int32_t n;
     const orbo_keypoint *keys_un; /* mvKeysUn (angle, pt, octave) */

@@ -66,7 +66,7 @@ def test_three_maxima():
     assert O.three_maxima(h) == (3, 7, -1)
 
 
-def brute_frame(cur, pts, desc, R, t, forward, backward, th, check_ori):
+def brute_frame(cur, pts, desc, R, t, forward, backward, th, check_ori, kf=False, orb_dist=100):
     k = cur["keys_un"]
     fx, fy, cx, cy, bf, b = (f32(v) for v in cur["K"])
     mnx, mny, mxx, mxy = (f32(v) for v in cur["bounds"])
@@ -81,25 +81,25 @@ def brute_frame(cur, pts, desc, R, t, forward, backward, th, check_ori):
         X = np.array([p["x"], p["y"], p["z"]], f32)
         c = [f32(f32(f32(R[r, 0] * X[0]) + f32(R[r, 1] * X[1])) + f32(R[r, 2] * X[2])) + t[r] for r in range(3)]
         invz = f32(1.0 / np.float64(c[2]))
-        if invz < 0:
+        if invz < 0 and not kf:
             continue
         u = f32(f32(f32(fx * c[0]) * invz) + cx); v = f32(f32(f32(fy * c[1]) * invz) + cy)
         if u < mnx or u > mxx or v < mny or v > mxy:
             continue
         o = int(p["octave"])
         rad = f32(f32(th) * cur["scale_factors"][o])
-        lv = (o, -1) if forward else ((0, o) if backward else (o - 1, o + 1))
+        lv = (o, -1) if forward and not kf else ((0, o) if backward and not kf else (o - 1, o + 1))
         best, bi = 256, -1
         for j in brute_window(cur, u, v, rad, *lv):
             if blocked[j]:
                 continue
-            if cur["u_right"][j] > 0 and abs(f32(f32(u - f32(bf * invz)) - cur["u_right"][j])) > rad:
+            if not kf and cur["u_right"][j] > 0 and abs(f32(f32(u - f32(bf * invz)) - cur["u_right"][j])) > rad:
                 continue
             d = popcount_dist(desc[i], cur["desc"][j])
             if d < best:
                 best, bi = d, j
-        if best <= 100:
-            match[bi] = i; blocked[bi] = bool(p["blocks"]); nm += 1
+        if best <= orb_dist:
+            match[bi] = i; blocked[bi] = True if kf else bool(p["blocks"]); nm += 1
             if check_ori:
                 rot = f32(p["angle"] - k["angle"][bi])
                 if rot < 0:
@@ -251,3 +251,16 @@ def test_bucket_matchers(mode, seed):
         n2, m2 = brute_buckets(mode, A, B, 0.75, True, only_stereo, F12, epi, s2, sc)
         assert n == n2 and np.array_equal(m, m2)
         assert n > (0 if only_stereo else 30)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_projection_keyframe(seed):
+    """relocalisation overload, ORBmatcher.cc:1472-1599"""
+    rng = np.random.default_rng(50 + seed)
+    cur = synth.random_frame(rng, 500, claimed_frac=0.1)
+    pts, desc, R, t = synth.last_frame_points(rng, cur, 400)
+    for th, od in ((10.0, 100), (3.0, 64)):
+        n, m = O.search_by_projection_kf(cur, pts, desc, R, t, th, od, True)
+        n2, m2 = brute_frame(cur, pts, desc, R, t, False, False, th, True, kf=True, orb_dist=od)
+        assert n == n2 and np.array_equal(m, m2)
+    assert n > 20

@@ -167,3 +167,16 @@ def test_bucket_matchers_disjoint_vocabularies(matcher):
     B = dict(B, node_id=B["node_id"] + 1000)          # no shared node at all
     n, m = matcher.SearchByBoWKF(A, B)
     assert n == 0 and (m == -1).all()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_search_by_projection_keyframe(matcher, seed):
+    """relocalisation overload SearchByProjection(Cur, KF, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1472-1599"""
+    rng = np.random.default_rng(400 + seed)
+    cur = synth.random_frame(rng, 1200, claimed_frac=0.15)
+    pts, desc, R, t = synth.last_frame_points(rng, cur, 1000, dup_frac=0.3)
+    for th, od in ((10.0, 100), (3.0, 64)):
+        n_ref, m_ref = O.search_by_projection_kf(cur, pts, desc, R, t, th, od, True)
+        n, m = matcher.SearchByProjectionKF(cur, pts, desc, R, t, th, od)
+        assert n == n_ref and np.array_equal(m, m_ref)
+    assert n_ref > 0
