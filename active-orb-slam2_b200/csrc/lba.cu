@@ -25,77 +25,14 @@
 #include <vector>
 #include "orbx_internal.cuh"
 
-#define LBA_THREADS 256
-#define LBA_SMEM_KF 64          // H_pp pre-reduction in shared memory up to this many free keyframes
-#define LBA_SCHUR_CTAS 32
-#define LBA_SCHUR_THREADS 512
-#define LBA_SOLVE_THREADS 1024
+#include "lba_common.cuh"
 
-struct LbaDev {
-    int n_kf, n_pts, n_edges, np, n;         // np free keyframes, n = 6 np
-    double *kf;          // [n_kf][7] quaternion (x,y,z,w), translation
-    const int *kfidx;    // [n_kf] index in the reduced system or -1 (fixed)
-    double *pt;          // [n_pts][3]
-    const int *ptstart;  // [n_pts + 1] edges are sorted by landmark
-    const int *ekf, *ept;
-    const double *obs;   // [E][3]
-    const double *info;  // [E]
-    const uint8_t *stereo;
-    uint8_t *level1;     // [E] excluded from the second round
-    double *err, *chi2;  // [E][3], [E]  (the edge's stored _error / chi2())
-    double *Hpl;         // [E][18]  6x3 row-major
-    double *Hpp;         // [np][27]  21 upper-triangular entries of the 6x6 block, then b_p
-    double *Hll;         // [n_pts][9]  6 upper-triangular entries of the 3x3 block, then b_l
-    double *Hs, *bs, *xp, *xl;   // [n][n] (upper block triangle filled), [n], [n], [n_pts][3]
-    double *scal;        // 0 chi2, 1 scale, 2 max diagonal, 3 solve ok
-    double fx, fy, cx, cy, bf;
-    float bf_f;
-    double d_mono, d_stereo;     // Huber deltas (float sqrt(5.991), sqrt(7.815), Optimizer.cc:569-570)
-};
-
-__device__ __forceinline__ void quat_to_R(const double *q, double R[9]) {
-    const double x = q[0], y = q[1], z = q[2], w = q[3];
-    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
-}
-
-__device__ __forceinline__ double block_sum(double v, double *tmp) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) tmp[w] = v;
-    __syncthreads();
-    double s = 0;
-    if (w == 0) {
-        s = lane < (int)(blockDim.x >> 5) ? tmp[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    }
-    __syncthreads();
-    return s;   // valid in thread 0
-}
-
-// residual of edge e at the current estimates; returns the depth
-__device__ __forceinline__ double edge_residual(const LbaDev &D, int e, const double R[9], const double *t, double Xc[3], double er[3]) {
-    const double *X = D.pt + 3 * D.ept[e];
-    for (int r = 0; r < 3; r++) Xc[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + t[r];
-    const double *o = D.obs + 3 * e;
-    if (!D.stereo[e]) {
-        er[0] = o[0] - (Xc[0] / Xc[2] * D.fx + D.cx);
-        er[1] = o[1] - (Xc[1] / Xc[2] * D.fy + D.cy);
-        er[2] = 0;
-    } else {   // cam_project keeps 1/z and bf in float (types_six_dof_expmap.cpp:150-157)
-        const float invz = __fdiv_rn(1.0f, (float)Xc[2]);
-        const double u = Xc[0] * (double)invz * D.fx + D.cx;
-        er[0] = o[0] - u;
-        er[1] = o[1] - (Xc[1] * (double)invz * D.fy + D.cy);
-        er[2] = o[2] - (u - (double)__fmul_rn(D.bf_f, invz));
-    }
-    return Xc[2];
-}
+// lba_fused.cu
+size_t orbx_lba_fused_smem(int np);
+bool orbx_lba_fused_fits(int n_kf, int np);
+orbx_status orbx_lba_fused_init();
+orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
+                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s);
 
 __global__ void __launch_bounds__(LBA_THREADS) k_lba_err(LbaDev D, int robust) {
     __shared__ double tmp[32];
@@ -193,17 +130,6 @@ __global__ void __launch_bounds__(LBA_THREADS) k_lba_maxdiag(LbaDev D) {
         D.scal[2] = m;
     }
 }
-
-// symmetric 3x3 inverse of (H_ll + lambda I); h = (xx, xy, xz, yy, yz, zz)
-__device__ __forceinline__ void dinv3(const double *h, double lambda, double I[6]) {
-    const double a = h[0] + lambda, b = h[1], c = h[2], e = h[3] + lambda, f = h[4], i = h[5] + lambda;
-    const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
-    const double id = 1.0 / (a * c00 + b * c01 + c * c02);
-    I[0] = c00 * id; I[1] = c01 * id; I[2] = c02 * id;
-    I[3] = (a * i - c * c) * id; I[4] = (b * c - a * f) * id; I[5] = (a * e - b * b) * id;
-}
-
-__device__ __forceinline__ int upper_block(int p1, int p2, int np) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); }
 
 // H_schur = H_pp + lambda I, b_schur = b_p  (block_solver.hpp:371-373, :436)
 __global__ void __launch_bounds__(LBA_THREADS) k_lba_schur_init(LbaDev D, double lambda) {
@@ -348,68 +274,6 @@ __global__ void __launch_bounds__(LBA_SOLVE_THREADS) k_lba_solve(LbaDev D, int u
     if (tid == 0) D.scal[3] = ok ? 1.0 : 0.0;
 }
 
-// Eigen::Quaterniond(Matrix3d)
-__device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
-    double t = R[0] + R[4] + R[8];
-    if (t > 0) {
-        t = sqrt(t + 1.0);
-        q[3] = 0.5 * t; t = 0.5 / t;
-        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
-    } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[4 * i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-        double qq[4];
-        qq[i] = 0.5 * t; t = 0.5 / t;
-        qq[3] = (R[3 * k + j] - R[3 * j + k]) * t;
-        qq[j] = (R[3 * j + i] + R[3 * i + j]) * t;
-        qq[k] = (R[3 * k + i] + R[3 * i + k]) * t;
-        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
-    }
-}
-__device__ __forceinline__ void quat_normalize(double q[4]) {
-    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
-    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
-}
-
-// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*)
-__device__ void se3_oplus(double *T, const double *u) {
-    const double wx = u[0], wy = u[1], wz = u[2];
-    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
-    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-    double O2[9], R[9], V[9];
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
-    if (theta < 0.00001) {
-        for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
-    } else {
-        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
-        for (int i = 0; i < 9; i++) {
-            const double id = i % 4 == 0 ? 1.0 : 0.0;
-            R[i] = id + a * O[i] + b * O2[i];
-            V[i] = id + b * O[i] + c * O2[i];
-        }
-    }
-    double eq[4], et[3];
-    R_to_quat(R, eq);
-    quat_normalize(eq);
-    for (int r = 0; r < 3; r++) et[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
-    const double *b = T;   // q2
-    double nq[4];
-    nq[3] = eq[3] * b[3] - eq[0] * b[0] - eq[1] * b[1] - eq[2] * b[2];
-    nq[0] = eq[3] * b[0] + eq[0] * b[3] + eq[1] * b[2] - eq[2] * b[1];
-    nq[1] = eq[3] * b[1] + eq[1] * b[3] + eq[2] * b[0] - eq[0] * b[2];
-    nq[2] = eq[3] * b[2] + eq[2] * b[3] + eq[0] * b[1] - eq[1] * b[0];
-    double Rq[9], nt[3];
-    quat_to_R(eq, Rq);
-    for (int r = 0; r < 3; r++) nt[r] = et[r] + Rq[3 * r] * T[4] + Rq[3 * r + 1] * T[5] + Rq[3 * r + 2] * T[6];
-    quat_normalize(nq);
-    T[0] = nq[0]; T[1] = nq[1]; T[2] = nq[2]; T[3] = nq[3]; T[4] = nt[0]; T[5] = nt[1]; T[6] = nt[2];
-}
-
 // x_l = D^-1 (b_l - B^T x_p) (block_solver.hpp:461-481), SparseOptimizer::update, computeScale
 __global__ void __launch_bounds__(LBA_THREADS) k_lba_update(LbaDev D, double lambda) {
     __shared__ double tmp[32];
@@ -468,6 +332,7 @@ struct orbx_lba {
     const volatile uint8_t *stop;
     int launches;
     int loaded;
+    int use_fused;      // 0 = always the multi-kernel path (ORBX_LBA_MULTIKERNEL=1, for tests and large windows)
 };
 
 extern "C" void orbx_lba_destroy(orbx_lba *h) {
@@ -510,6 +375,7 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     h->d_kf_bak = h->d_pt_bak = nullptr; h->d_kfidx = h->d_ptstart = h->d_ekf = h->d_ept = nullptr;
     h->d_obs = h->d_info = nullptr; h->d_stereo = h->d_flag = nullptr; h->h_scal = nullptr;
     h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->stop = nullptr; h->launches = 0; h->loaded = 0;
+    { const char *mk = getenv("ORBX_LBA_MULTIKERNEL"); h->use_fused = !(mk && mk[0] == '1'); }
     const size_t K = max_keyframes, L = max_points, E = max_edges, N = 6 * K;
     cudaError_t ce = cudaSuccess;
 #define TRY(x) if (ce == cudaSuccess) ce = (x)
@@ -542,6 +408,7 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     TRY(cudaEventCreate(&h->ev1));
     TRY(ORBX_RAISE_SMEM(k_lba_schur<true>));
     TRY(ORBX_RAISE_SMEM(k_lba_solve));
+    if (ce == cudaSuccess && orbx_lba_fused_init() != ORBX_OK) ce = cudaErrorUnknown;
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_lba_create: %s", cudaGetErrorString(ce));
@@ -666,6 +533,27 @@ static inline bool stop_requested(const orbx_lba *h) { return h->stop && *h->sto
 static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lba_result *res, bool *first) {
     LbaDev &D = h->D;
     orbx_status st;
+    if (h->use_fused && iterations > 0 && orbx_lba_fused_fits(D.n_kf, D.np)) {
+        // whole optimize() call in one cluster kernel; the stop flag is honoured between the two rounds only (a round
+        // is a few hundred microseconds here, less than one iteration of the reference)
+        const int capture = *first ? 1 : 0;
+        const bool want = capture && (res->first_Hschur || res->first_bschur || res->first_xp);
+        ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 2, h->stream));
+        if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
+                                        D.scal + 4, h->stream)))
+            return st;
+        h->launches++;
+        ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+        if (want) {
+            if (res->first_Hschur) ORBX_CUDA(cudaMemcpyAsync(res->first_Hschur, D.Hs, sizeof(double) * D.n * D.n, cudaMemcpyDeviceToHost, h->stream));
+            if (res->first_bschur) ORBX_CUDA(cudaMemcpyAsync(res->first_bschur, D.bs, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
+            if (res->first_xp) ORBX_CUDA(cudaMemcpyAsync(res->first_xp, D.xp, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
+        }
+        ORBX_CUDA(cudaStreamSynchronize(h->stream));
+        res->lm_trials += (int)h->h_scal[4];
+        if (capture) { res->first_lambda = h->h_scal[5]; *first = false; }
+        return ORBX_OK;
+    }
     double lambda = 0, ni = 2;
     int nBad = 0;
     for (int it = 0; it < iterations && !stop_requested(h); it++) {

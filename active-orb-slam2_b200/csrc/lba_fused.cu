@@ -1,0 +1,452 @@
+// One optimizer.optimize(iterations) call of Optimizer::LocalBundleAdjustment (reference src/Optimizer.cc:659-706)
+// in ONE kernel: a thread-block cluster of 8 CTAs owns the window, the Levenberg loop of
+// g2o core/optimization_algorithm_levenberg.cpp:61-189 runs on the device, and the CTAs meet at cluster barriers
+// instead of going back to the host between stages (the multi-kernel path of lba.cu pays ~7 launches and one host
+// round trip per Levenberg trial).  Same arithmetic, same f64, same edge order per landmark as lba.cu.
+//
+//   landmarks (and with them the edges, which are sorted by landmark) are split into 8 contiguous ranges, one per CTA;
+//   H_ll / b_l of a landmark are accumulated in registers by the thread that owns it (no atomics);
+//   H_pp / b_p and the Schur complement are accumulated per CTA in shared memory and summed across the cluster through
+//   distributed shared memory in a fixed order, so every CTA sees bit-identical sums and takes the same Levenberg
+//   decision without any broadcast;
+//   the reduced camera system lives in CTA 0's shared memory in the upper block-triangular layout it was accumulated
+//   in, and is factorised there (blocked 6x6 Cholesky, A = U^T U) without ever touching global memory.
+// Used when the upper block triangle of H_schur fits shared memory (<= 36 free keyframes); larger windows take lba.cu.
+#include <cooperative_groups.h>
+#include "lba_common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define LF_THREADS 512
+#define LF_WARPS (LF_THREADS / 32)
+#define LF_CTAS 8
+#define LF_MAX_KF 64
+#define LF_SLOTS 4
+
+struct LfParams {
+    LbaDev D;
+    double *kf_bak, *pt_bak;
+    int iterations, robust;
+    int capture;                      // 1: store the first trial's reduced system
+    double *cap_Hs, *cap_bs, *cap_xp; // n x n (full symmetric), n, n
+    double *out;                      // [0] trials, [1] lambda of the first trial
+};
+
+struct LfShared {
+    double red[LF_SLOTS][LF_CTAS][4];   // cluster reductions land in CTA 0's copy
+    double tmp[32];
+    double bc[4];                        // values gathered by thread 0 for the whole CTA
+    int ok;
+};
+
+__device__ __forceinline__ double block_max(double v, double *tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) tmp[w] = v;
+    __syncthreads();
+    double s = 0;
+    if (w == 0) {
+        s = lane < (int)(blockDim.x >> 5) ? tmp[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    }
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
+    extern __shared__ __align__(16) double dyn[];
+    __shared__ LfShared sh;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank(), C = (int)cl.num_blocks();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const LbaDev &D = P.D;
+    const int np = D.np, n = D.n, nblk = np * (np + 1) / 2, n_kf = D.n_kf;
+
+    // shared-memory carve-up (identical in every CTA so that map_shared_rank addresses line up)
+    double *kfRt = dyn;                               // [n_kf][12]  R (row-major) and t of every keyframe
+    double *hpp = kfRt + 12 * LF_MAX_KF;              // [np][27]    this CTA's share of H_pp / b_p; CTA 0: the total
+    double *hs = hpp + 27 * np;                       // [nblk][36] + [n]  Schur accumulators; CTA 0: the reduced system
+    double *xp = hs + nblk * 36 + n;                  // [n]
+    LfShared *sh0 = cl.map_shared_rank(&sh, 0);
+    double *hpp0 = cl.map_shared_rank(hpp, 0), *hs0 = cl.map_shared_rank(hs, 0), *xp0 = cl.map_shared_rank(xp, 0);
+
+    const int l0 = (int)((long long)D.n_pts * rank / C), l1 = (int)((long long)D.n_pts * (rank + 1) / C);
+    int slot = 0;
+
+    // residuals (+ optionally the quadratic form) of this CTA's landmarks; returns nothing, partial sums go to CTA 0
+    auto linearize = [&](bool build) {
+        for (int k = tid; k < n_kf; k += LF_THREADS) {
+            double R[9];
+            double T[7];      // poses are written by CTA 0 on another SM: read them past the (incoherent) L1
+            for (int i = 0; i < 7; i++) T[i] = __ldcg(D.kf + 7 * k + i);
+            quat_to_R(T, R);
+            for (int i = 0; i < 9; i++) kfRt[12 * k + i] = R[i];
+            kfRt[12 * k + 9] = T[4]; kfRt[12 * k + 10] = T[5]; kfRt[12 * k + 11] = T[6];
+        }
+        if (build) for (int i = tid; i < 27 * np; i += LF_THREADS) hpp[i] = 0;
+        __syncthreads();
+        double chi = 0, mx = 0;
+        for (int l = l0 + tid; l < l1; l += LF_THREADS) {
+            double hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int e = D.ptstart[l]; e < D.ptstart[l + 1]; e++) {
+                if (D.level1[e]) continue;
+                const int kf = D.ekf[e];
+                const double *R = kfRt + 12 * kf;
+                double Xc[3], er[3];
+                edge_residual(D, e, R, R + 9, Xc, er);
+                D.err[3 * e] = er[0]; D.err[3 * e + 1] = er[1]; D.err[3 * e + 2] = er[2];
+                const double info = D.info[e];
+                const double c = info * (er[0] * er[0] + er[1] * er[1] + er[2] * er[2]);
+                D.chi2[e] = c;
+                double rho1 = 1.0, cr = c;
+                if (P.robust) {
+                    const double d = D.stereo[e] ? D.d_stereo : D.d_mono, dsqr = d * d;
+                    if (c > dsqr) { const double sq = sqrt(c); cr = 2 * sq * d - dsqr; rho1 = d / sq; }
+                }
+                chi += cr;
+                if (!build) continue;
+                const int dim = D.stereo[e] ? 3 : 2;
+                const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = D.fx, fy = D.fy, bf = D.bf;
+                double A[9], B[18];
+                for (int q = 0; q < 3; q++) {
+                    A[q] = -fx * R[q] / z + fx * x * R[6 + q] / z2;
+                    A[3 + q] = -fy * R[3 + q] / z + fy * y * R[6 + q] / z2;
+                    A[6 + q] = dim == 3 ? A[q] - bf * R[6 + q] / z2 : 0.0;
+                }
+                B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
+                B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
+                if (dim == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
+                else { for (int i = 12; i < 18; i++) B[i] = 0; }
+                const double w = rho1 * info;
+                double wr[3];
+                for (int d = 0; d < 3; d++) wr[d] = -info * er[d] * rho1;
+                int k = 0;
+                for (int a = 0; a < 3; a++)
+                    for (int b = a; b < 3; b++) hl[k++] += w * (A[a] * A[b] + A[3 + a] * A[3 + b] + A[6 + a] * A[6 + b]);
+                for (int a = 0; a < 3; a++) hl[6 + a] += A[a] * wr[0] + A[3 + a] * wr[1] + A[6 + a] * wr[2];
+                const int ip = D.kfidx[kf];
+                if (ip >= 0) {
+                    double *hp = hpp + 27 * ip;
+                    k = 0;
+                    for (int a = 0; a < 6; a++)
+                        for (int b = a; b < 6; b++) atomicAdd(&hp[k++], w * (B[a] * B[b] + B[6 + a] * B[6 + b] + B[12 + a] * B[12 + b]));
+                    for (int a = 0; a < 6; a++) atomicAdd(&hp[21 + a], B[a] * wr[0] + B[6 + a] * wr[1] + B[12 + a] * wr[2]);
+                    double *hpl = D.Hpl + 18 * (size_t)e;
+                    for (int a = 0; a < 6; a++)
+                        for (int b = 0; b < 3; b++) hpl[3 * a + b] = w * (B[a] * A[b] + B[6 + a] * A[3 + b] + B[12 + a] * A[6 + b]);
+                }
+            }
+            if (build) {
+                for (int i = 0; i < 9; i++) D.Hll[9 * l + i] = hl[i];
+                mx = fmax(mx, fmax(fabs(hl[0]), fmax(fabs(hl[3]), fabs(hl[5]))));
+            }
+        }
+        const double s = block_sum(chi, sh.tmp);
+        const double m = build ? block_max(mx, sh.tmp) : 0.0;
+        if (tid == 0) { sh0->red[slot][rank][0] = s; sh0->red[slot][rank][1] = m; }
+    };
+
+    double lambda = 0, ni = 2;
+    int nBad = 0, trials = 0;
+    bool first = P.capture != 0;
+
+    for (int it = 0; it < P.iterations; it++) {
+        // ---- computeActiveErrors + buildSystem ------------------------------------------------------------------
+        linearize(true);
+        __threadfence();
+        cl.sync();
+        for (int i = rank * LF_THREADS + tid; i < 27 * np; i += C * LF_THREADS) {     // H_pp / b_p: sum the 8 shares in rank order
+            double v = 0;
+            for (int r = 0; r < C; r++) v += cl.map_shared_rank(hpp, r)[i];
+            hpp0[i] = v;                                                               // only this thread touches entry i of CTA 0
+        }
+        cl.sync();
+        if (tid == 0) {      // every CTA sums the same numbers in the same order: identical decisions without a broadcast
+            double chi = 0, mx = 0;
+            for (int r = 0; r < C; r++) { chi += sh0->red[slot][r][0]; mx = fmax(mx, sh0->red[slot][r][1]); }
+            if (it == 0) {   // computeLambdaInit also looks at the pose diagonals
+                const int diag6[6] = {0, 6, 11, 15, 18, 20};
+                for (int i = 0; i < 6 * np; i++) mx = fmax(mx, fabs(hpp0[27 * (i / 6) + diag6[i % 6]]));
+            }
+            sh.bc[0] = chi; sh.bc[1] = mx;
+        }
+        __syncthreads();
+        double currentChi = sh.bc[0];
+        const double maxdiag = sh.bc[1];
+        slot = (slot + 1) % LF_SLOTS;
+        if (it == 0) { lambda = 1e-5 * maxdiag; ni = 2; nBad = 0; }
+        const double iniChi = currentChi;
+        double rho = 0;
+        int qmax = 0;
+        do {
+            // ---- push -----------------------------------------------------------------------------------------
+            for (int i = 3 * l0 + tid; i < 3 * l1; i += LF_THREADS) P.pt_bak[i] = D.pt[i];
+            if (rank == 0) for (int i = tid; i < 7 * n_kf; i += LF_THREADS) P.kf_bak[i] = D.kf[i];
+            // ---- Schur complement of this CTA's landmarks (block_solver.hpp:371-439) ----------------------------
+            for (int i = tid; i < nblk * 36 + n; i += LF_THREADS) hs[i] = 0;
+            __syncthreads();
+            for (int l = l0 + warp; l < l1; l += LF_WARPS) {
+                const int s = D.ptstart[l], ne = D.ptstart[l + 1] - s;
+                if (ne == 0) continue;
+                const double *hl = D.Hll + 9 * l;
+                double Di[6];
+                dinv3(hl, lambda, Di);
+                const double db0 = Di[0] * hl[6] + Di[1] * hl[7] + Di[2] * hl[8], db1 = Di[1] * hl[6] + Di[3] * hl[7] + Di[4] * hl[8],
+                             db2 = Di[2] * hl[6] + Di[4] * hl[7] + Di[5] * hl[8];
+                for (int i = lane; i < ne; i += 32) {
+                    const int e = s + i, p = D.kfidx[D.ekf[e]];
+                    if (p < 0 || D.level1[e]) continue;
+                    const double *B = D.Hpl + 18 * (size_t)e;
+                    for (int a = 0; a < 6; a++) atomicAdd(&hs[nblk * 36 + 6 * p + a], -(B[3 * a] * db0 + B[3 * a + 1] * db1 + B[3 * a + 2] * db2));
+                }
+                // one lane per (pair, row): 6 outputs each
+                for (int w6 = lane; w6 < ne * ne * 6; w6 += 32) {
+                    const int pr = w6 / 6, a = w6 - 6 * pr, i = pr / ne, j = pr - i * ne, e1 = s + i, e2 = s + j;
+                    const int p1 = D.kfidx[D.ekf[e1]], p2 = D.kfidx[D.ekf[e2]];
+                    if (p1 < 0 || p2 < 0 || p1 > p2 || D.level1[e1] || D.level1[e2] || (p1 == p2 && i != j)) continue;
+                    const double *B1 = D.Hpl + 18 * (size_t)e1 + 3 * a, *B2 = D.Hpl + 18 * (size_t)e2;
+                    const double u0 = B1[0], u1 = B1[1], u2 = B1[2];
+                    const double bd0 = u0 * Di[0] + u1 * Di[1] + u2 * Di[2], bd1 = u0 * Di[1] + u1 * Di[3] + u2 * Di[4],
+                                 bd2 = u0 * Di[2] + u1 * Di[4] + u2 * Di[5];
+                    double *dst = hs + upper_block(p1, p2, np) * 36 + 6 * a;
+#pragma unroll
+                    for (int b = 0; b < 6; b++) atomicAdd(&dst[b], -(bd0 * B2[3 * b] + bd1 * B2[3 * b + 1] + bd2 * B2[3 * b + 2]));
+                }
+            }
+            cl.sync();
+            // ---- sum the 8 shares in rank order into CTA 0, add H_pp + lambda I and b_p -------------------------------
+            for (int i = rank * LF_THREADS + tid; i < nblk * 36 + n; i += C * LF_THREADS) {
+                double v = 0;
+                for (int r = 0; r < C; r++) v += cl.map_shared_rank(hs, r)[i];
+                if (i < nblk * 36) {
+                    const int blk = i / 36, ab = i - 36 * blk;
+                    int p1 = 0, rem = blk;
+                    while (rem >= np - p1) { rem -= np - p1; p1++; }
+                    if (rem == 0) {        // diagonal block
+                        int a = ab / 6, b = ab - 6 * a;
+                        const bool dg = a == b;
+                        if (a > b) { const int t = a; a = b; b = t; }
+                        v += hpp0[27 * p1 + a * 6 - a * (a - 1) / 2 + (b - a)] + (dg ? lambda : 0.0);
+                    }
+                } else {
+                    const int k = i - nblk * 36;
+                    v += hpp0[27 * (k / 6) + 21 + k % 6];
+                }
+                hs0[i] = v;
+            }
+            cl.sync();
+            if (first && P.cap_Hs) {     // parity tests: the very first reduced system, expanded to a full symmetric matrix
+                for (int i = rank * LF_THREADS + tid; i < n * n; i += C * LF_THREADS) {
+                    int r = i / n, c = i - r * n;
+                    if (r / 6 > c / 6) { const int t = r; r = c; c = t; }
+                    P.cap_Hs[i] = hs0[upper_block(r / 6, c / 6, np) * 36 + 6 * (r % 6) + c % 6];
+                }
+                for (int i = rank * LF_THREADS + tid; i < n; i += C * LF_THREADS) P.cap_bs[i] = hs0[nblk * 36 + i];
+                cl.sync();
+            }
+            // ---- reduced solve in CTA 0: A = U^T U on the upper block triangle, then U^T y = b, U x = y -----------------
+            if (rank == 0) {
+                if (tid == 0) sh.ok = 1;
+                __syncthreads();
+                for (int k = 0; k < np; k++) {
+                    double *Ukk = hs + upper_block(k, k, np) * 36;
+                    if (tid == 0) {
+                        for (int a = 0; a < 6; a++) {
+                            double d = Ukk[7 * a];
+                            for (int m = 0; m < a; m++) d -= Ukk[6 * m + a] * Ukk[6 * m + a];
+                            if (!(d > 0)) { sh.ok = 0; break; }
+                            d = sqrt(d);
+                            Ukk[7 * a] = d;
+                            for (int b = a + 1; b < 6; b++) {
+                                double v = Ukk[6 * a + b];
+                                for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * Ukk[6 * m + b];
+                                Ukk[6 * a + b] = v / d;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (!sh.ok) break;
+                    const int T = np - k - 1;
+                    for (int t = tid; t < T * 6; t += LF_THREADS) {        // U_kj = U_kk^-T A_kj, one thread per column
+                        const int j = k + 1 + t / 6, b = t % 6;
+                        double *Akj = hs + upper_block(k, j, np) * 36;
+                        double y[6];
+                        for (int a = 0; a < 6; a++) {
+                            double v = Akj[6 * a + b];
+                            for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * y[m];
+                            y[a] = v / Ukk[7 * a];
+                        }
+                        for (int a = 0; a < 6; a++) Akj[6 * a + b] = y[a];
+                    }
+                    __syncthreads();
+                    const int npair = T * (T + 1) / 2;                       // A_ij -= U_ki^T U_kj for k < i <= j
+                    for (int t = tid; t < npair * 36; t += LF_THREADS) {
+                        const int pr = t / 36, ab = t - 36 * pr, a = ab / 6, b = ab - 6 * a;
+                        int i = 0, rem = pr;
+                        while (rem >= T - i) { rem -= T - i; i++; }
+                        const int bi = k + 1 + i, bj = bi + rem;
+                        const double *Uki = hs + upper_block(k, bi, np) * 36, *Ukj = hs + upper_block(k, bj, np) * 36;
+                        double v = 0;
+#pragma unroll
+                        for (int m = 0; m < 6; m++) v += Uki[6 * m + a] * Ukj[6 * m + b];
+                        hs[upper_block(bi, bj, np) * 36 + ab] -= v;
+                    }
+                    __syncthreads();
+                }
+                if (sh.ok) {
+                    if (warp == 0) {
+                        double *b = hs + nblk * 36;
+                        for (int k = 0; k < np; k++) {                      // forward: U^T y = b
+                            const double *Ukk = hs + upper_block(k, k, np) * 36;
+                            if (lane == 0) {
+                                for (int a = 0; a < 6; a++) {
+                                    double v = b[6 * k + a];
+                                    for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * b[6 * k + m];
+                                    b[6 * k + a] = v / Ukk[7 * a];
+                                }
+                            }
+                            __syncwarp();
+                            for (int t = lane; t < (np - k - 1) * 6; t += 32) {
+                                const int j = k + 1 + t / 6, c = t % 6;
+                                const double *Ukj = hs + upper_block(k, j, np) * 36;
+                                double v = 0;
+                                for (int a = 0; a < 6; a++) v += Ukj[6 * a + c] * b[6 * k + a];
+                                b[6 * j + c] -= v;
+                            }
+                            __syncwarp();
+                        }
+                        for (int k = np - 1; k >= 0; k--) {                 // backward: U x = y
+                            const double *Ukk = hs + upper_block(k, k, np) * 36;
+                            if (lane == 0) {
+                                for (int a = 5; a >= 0; a--) {
+                                    double v = b[6 * k + a];
+                                    for (int m = a + 1; m < 6; m++) v -= Ukk[6 * a + m] * b[6 * k + m];
+                                    b[6 * k + a] = v / Ukk[7 * a];
+                                }
+                            }
+                            __syncwarp();
+                            for (int t = lane; t < k * 6; t += 32) {
+                                const int i = t / 6, a = t % 6;
+                                const double *Uik = hs + upper_block(i, k, np) * 36;
+                                double v = 0;
+                                for (int c = 0; c < 6; c++) v += Uik[6 * a + c] * b[6 * k + c];
+                                b[6 * i + a] -= v;
+                            }
+                            __syncwarp();
+                        }
+                        for (int i = lane; i < n; i += 32) xp[i] = b[i];
+                    }
+                } else {
+                    for (int i = tid; i < n; i += LF_THREADS) xp[i] = 0;     // failed factorisation: no step, the trial is rejected
+                }
+                __syncthreads();
+                if (tid == 0) sh.red[slot][0][2] = sh.ok ? 1.0 : 0.0;
+            }
+            cl.sync();
+            if (rank != 0) for (int i = tid; i < n; i += LF_THREADS) xp[i] = xp0[i];
+            __syncthreads();
+            if (first && P.cap_xp) for (int i = rank * LF_THREADS + tid; i < n; i += C * LF_THREADS) P.cap_xp[i] = xp[i];
+            if (first && tid == 0 && rank == 0) P.out[1] = lambda;
+            first = false;
+            // ---- landmark back-substitution, update, computeScale ------------------------------------------------------
+            double sc = 0;
+            for (int l = l0 + tid; l < l1; l += LF_THREADS) {
+                const double *hl = D.Hll + 9 * l;
+                double c0 = hl[6], c1 = hl[7], c2 = hl[8];
+                for (int e = D.ptstart[l]; e < D.ptstart[l + 1]; e++) {
+                    const int p = D.kfidx[D.ekf[e]];
+                    if (p < 0 || D.level1[e]) continue;
+                    const double *B = D.Hpl + 18 * (size_t)e, *x = xp + 6 * p;
+                    for (int a = 0; a < 6; a++) { c0 -= B[3 * a] * x[a]; c1 -= B[3 * a + 1] * x[a]; c2 -= B[3 * a + 2] * x[a]; }
+                }
+                double Di[6];
+                dinv3(hl, lambda, Di);
+                const double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2, x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2,
+                             x2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
+                sc += x0 * (lambda * x0 + hl[6]) + x1 * (lambda * x1 + hl[7]) + x2 * (lambda * x2 + hl[8]);
+                D.pt[3 * l] += x0; D.pt[3 * l + 1] += x1; D.pt[3 * l + 2] += x2;
+            }
+            if (rank == 0 && tid < n_kf) {
+                const int p = D.kfidx[tid];
+                if (p >= 0) {
+                    const double *x = xp + 6 * p, *b = hpp + 27 * p + 21;
+                    for (int a = 0; a < 6; a++) sc += x[a] * (lambda * x[a] + b[a]);
+                    se3_oplus(D.kf + 7 * tid, x);
+                }
+            }
+            const double scs = block_sum(sc, sh.tmp);
+            if (tid == 0) sh0->red[slot][rank][3] = scs;
+            __threadfence();
+            cl.sync();
+            // ---- computeActiveErrors at the trial state ---------------------------------------------------------------------
+            linearize(false);
+            cl.sync();
+            if (tid == 0) {
+                double chi = 0, scl = 0;
+                for (int r = 0; r < C; r++) { chi += sh0->red[slot][r][0]; scl += sh0->red[slot][r][3]; }
+                sh.bc[0] = chi; sh.bc[2] = scl; sh.bc[3] = sh0->red[slot][0][2];
+            }
+            __syncthreads();
+            double tempChi = sh.bc[0];
+            const double scale = sh.bc[2];
+            const bool ok2 = sh.bc[3] != 0.0;
+            slot = (slot + 1) % LF_SLOTS;
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = (currentChi - tempChi) / (scale + 1e-3);
+            trials++;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2;
+                for (int i = 3 * l0 + tid; i < 3 * l1; i += LF_THREADS) D.pt[i] = P.pt_bak[i];            // pop
+                if (rank == 0) for (int i = tid; i < 7 * n_kf; i += LF_THREADS) D.kf[i] = P.kf_bak[i];
+            }
+            qmax++;
+            __threadfence();
+            cl.sync();
+        } while (rho < 0 && qmax < 10);
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    if (rank == 0 && tid == 0) P.out[0] = (double)trials;
+    cl.sync();     // no CTA may exit while others still read its shared memory
+}
+
+// ---- host glue (called from lba.cu) ---------------------------------------------------------------------------------
+size_t orbx_lba_fused_smem(int np) {
+    const size_t nblk = (size_t)np * (np + 1) / 2, n = 6 * (size_t)np;
+    return sizeof(double) * (12 * LF_MAX_KF + 27 * (size_t)np + nblk * 36 + n + n);
+}
+
+bool orbx_lba_fused_fits(int n_kf, int np) { return n_kf <= LF_MAX_KF && np >= 1 && orbx_lba_fused_smem(np) <= 200 * 1024; }
+
+orbx_status orbx_lba_fused_init() {
+    ORBX_CUDA(ORBX_RAISE_SMEM(k_lba_fused));
+    return ORBX_OK;
+}
+
+orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
+                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s) {
+    LfParams P;
+    P.D = D; P.kf_bak = kf_bak; P.pt_bak = pt_bak; P.iterations = iterations; P.robust = robust; P.capture = capture;
+    P.cap_Hs = cap_Hs; P.cap_bs = cap_bs; P.cap_xp = cap_xp; P.out = out;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(LF_CTAS);
+    cfg.blockDim = dim3(LF_THREADS);
+    cfg.dynamicSmemBytes = orbx_lba_fused_smem(D.np);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = LF_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_lba_fused, P));
+    return ORBX_OK;
+}

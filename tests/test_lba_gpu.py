@@ -88,3 +88,24 @@ def test_build_schur_timed_matches_first_system(opt):
     ref = O.lba_solve(p, 1, 0, want_system=True)
     ms, Hs, bs = opt.build_schur_timed(p, ref["lambda0"], reps=3, want_system=True)
     assert ms > 0 and rel(Hs, ref["Hschur"]) < 1e-9 and rel(bs, ref["bschur"]) < 1e-9
+
+
+def test_multikernel_path_matches_too(monkeypatch):
+    """windows too large for the cluster kernel take the host-driven multi-kernel path; force it on a small problem"""
+    monkeypatch.setenv("ORBX_LBA_MULTIKERNEL", "1")
+    o = Optimizer(max_keyframes=40, max_points=4000, max_edges=20000)
+    try:
+        p = synth.lba_problem(21, n_kf=10, n_pts=800, n_fixed=2, stereo=True)
+        check_against_oracle(o, p)
+    finally:
+        o.close()
+
+
+def test_large_window_uses_multikernel_path():
+    """45 free keyframes: the upper block triangle of H_schur no longer fits shared memory"""
+    o = Optimizer(max_keyframes=48, max_points=3000, max_edges=20000)
+    try:
+        p = synth.lba_problem(22, n_kf=46, n_pts=1500, n_fixed=1)
+        check_against_oracle(o, p, 3, 3)
+    finally:
+        o.close()
