@@ -333,6 +333,11 @@ struct orbx_lba {
     int launches;
     int loaded;
     int use_fused;      // 0 = always the multi-kernel path (ORBX_LBA_MULTIKERNEL=1, for tests and large windows)
+    // work lists of the cluster kernel
+    int pending;        // orbx_lba_solve_begin issued, orbx_lba_solve_end not yet
+    double *h_kf, *h_pt, *h_chi; uint8_t *h_flag;   // pinned result staging of the asynchronous form
+    int *d_kfc, *d_blkc; int4 *d_kfe, *d_kchunk, *d_pchunk, *d_pairs; double *d_hppart, *d_part, *d_dinv;
+    size_t cap_kfe, cap_kfc, cap_blkc, cap_kchunk, cap_pchunk, cap_pairs, cap_hppart, cap_part, cap_dinv;
 };
 
 extern "C" void orbx_lba_destroy(orbx_lba *h) {
@@ -343,7 +348,13 @@ extern "C" void orbx_lba_destroy(orbx_lba *h) {
     cudaFree(h->D.Hpp); cudaFree(h->D.Hll); cudaFree(h->D.Hs); cudaFree(h->D.bs); cudaFree(h->D.xp); cudaFree(h->D.xl);
     cudaFree(h->D.scal); cudaFree(h->d_kf_bak); cudaFree(h->d_pt_bak); cudaFree(h->d_kfidx); cudaFree(h->d_ptstart);
     cudaFree(h->d_ekf); cudaFree(h->d_ept); cudaFree(h->d_obs); cudaFree(h->d_info); cudaFree(h->d_stereo); cudaFree(h->d_flag);
+    cudaFree(h->d_kfe); cudaFree(h->d_kfc); cudaFree(h->d_blkc); cudaFree(h->d_kchunk); cudaFree(h->d_pchunk); cudaFree(h->d_pairs);
+    cudaFree(h->d_hppart); cudaFree(h->d_part); cudaFree(h->d_dinv);
     if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->h_kf) cudaFreeHost(h->h_kf);
+    if (h->h_pt) cudaFreeHost(h->h_pt);
+    if (h->h_chi) cudaFreeHost(h->h_chi);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -376,6 +387,10 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     h->d_obs = h->d_info = nullptr; h->d_stereo = h->d_flag = nullptr; h->h_scal = nullptr;
     h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->stop = nullptr; h->launches = 0; h->loaded = 0;
     { const char *mk = getenv("ORBX_LBA_MULTIKERNEL"); h->use_fused = !(mk && mk[0] == '1'); }
+    h->d_kfc = h->d_blkc = nullptr; h->d_kfe = h->d_kchunk = h->d_pchunk = h->d_pairs = nullptr;
+    h->d_hppart = h->d_part = h->d_dinv = nullptr;
+    h->pending = 0; h->h_kf = h->h_pt = h->h_chi = nullptr; h->h_flag = nullptr;
+    h->cap_kfe = h->cap_kfc = h->cap_blkc = h->cap_kchunk = h->cap_pchunk = h->cap_pairs = h->cap_hppart = h->cap_part = h->cap_dinv = 0;
     const size_t K = max_keyframes, L = max_points, E = max_edges, N = 6 * K;
     cudaError_t ce = cudaSuccess;
 #define TRY(x) if (ce == cudaSuccess) ce = (x)
@@ -401,8 +416,12 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     TRY(cudaMalloc((void **)&h->D.bs, sizeof(double) * N));
     TRY(cudaMalloc((void **)&h->D.xp, sizeof(double) * N));
     TRY(cudaMalloc((void **)&h->D.xl, sizeof(double) * 3 * L));
-    TRY(cudaMalloc((void **)&h->D.scal, sizeof(double) * 8));
-    TRY(cudaMallocHost((void **)&h->h_scal, sizeof(double) * 8));
+    TRY(cudaMalloc((void **)&h->D.scal, sizeof(double) * 16));
+    TRY(cudaMallocHost((void **)&h->h_scal, sizeof(double) * 16));
+    TRY(cudaMallocHost((void **)&h->h_kf, sizeof(double) * 7 * K));
+    TRY(cudaMallocHost((void **)&h->h_pt, sizeof(double) * 3 * L));
+    TRY(cudaMallocHost((void **)&h->h_chi, sizeof(double) * E));
+    TRY(cudaMallocHost((void **)&h->h_flag, E));
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRY(cudaEventCreate(&h->ev0));
     TRY(cudaEventCreate(&h->ev1));
@@ -416,6 +435,89 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
         return ORBX_ERR_CUDA;
     }
     *out = h;
+    return ORBX_OK;
+}
+
+template <typename T>
+static orbx_status lba_grow(T **p, size_t *cap, size_t need) {
+    if (need <= *cap && *p) return ORBX_OK;
+    if (*p) ORBX_CUDA(cudaFree(*p));
+    *p = nullptr;
+    need += need / 4 + 64;
+    ORBX_CUDA(cudaMalloc((void **)p, sizeof(T) * need));
+    *cap = need;
+    return ORBX_OK;
+}
+
+#define LBA_CHUNK 128
+// work lists of the cluster kernel: edges by keyframe, (edge, edge) pairs of a landmark by pose-pair block, both cut into chunks
+static orbx_status lba_build_lists(orbx_lba *h, const std::vector<int> &ekf, const std::vector<int> &ept, const std::vector<uint8_t> &st8,
+                                   const std::vector<int> &kfidx, const std::vector<int> &start) {
+    LbaDev &D = h->D;
+    const int E = D.n_edges, L = D.n_pts, np = D.np, nblk = np * (np + 1) / 2;
+    std::vector<int> kcount(np + 1, 0);
+    std::vector<int4> kfe(E > 0 ? E : 1);
+    for (int s = 0; s < E; s++) { const int p = kfidx[ekf[s]]; if (p >= 0) kcount[p + 1]++; }
+    for (int p = 0; p < np; p++) kcount[p + 1] += kcount[p];
+    { std::vector<int> cur(kcount.begin(), kcount.end() - 1);
+      for (int s = 0; s < E; s++) { const int p = kfidx[ekf[s]]; if (p >= 0) kfe[cur[p]++] = make_int4(s, ekf[s], ept[s], st8[s]); } }
+    std::vector<int4> kchunk;
+    std::vector<int> kfc(np + 1, 0);
+    for (int p = 0; p < np; p++) {
+        kfc[p] = (int)kchunk.size();
+        for (int b = kcount[p]; b < kcount[p + 1]; b += LBA_CHUNK) kchunk.push_back(make_int4(p, b, std::min(LBA_CHUNK, kcount[p + 1] - b), 0));
+    }
+    kfc[np] = (int)kchunk.size();
+    auto ub = [np](int p1, int p2) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); };
+    std::vector<int> bcount(nblk + 1, 0);
+    for (int l = 0; l < L; l++)
+        for (int i = start[l]; i < start[l + 1]; i++)
+            for (int j = start[l]; j < start[l + 1]; j++) {
+                const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
+                if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
+                bcount[ub(p1, p2) + 1]++;
+            }
+    for (int b = 0; b < nblk; b++) bcount[b + 1] += bcount[b];
+    std::vector<int4> pairs(bcount[nblk] > 0 ? bcount[nblk] : 1);
+    { std::vector<int> cur(bcount.begin(), bcount.end() - 1);
+      for (int l = 0; l < L; l++)
+          for (int i = start[l]; i < start[l + 1]; i++)
+              for (int j = start[l]; j < start[l + 1]; j++) {
+                  const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
+                  if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
+                  pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
+              } }
+    std::vector<int4> pchunk;
+    std::vector<int> blkc(nblk + 1, 0);
+    { int blk = 0;
+      for (int p1 = 0; p1 < np; p1++)
+          for (int p2 = p1; p2 < np; p2++, blk++) {
+              blkc[blk] = (int)pchunk.size();
+              for (int b = bcount[blk]; b < bcount[blk + 1]; b += LBA_CHUNK)
+                  pchunk.push_back(make_int4(blk, b, std::min(LBA_CHUNK, bcount[blk + 1] - b), p1 == p2));
+          }
+      blkc[nblk] = (int)pchunk.size(); }
+    orbx_status st;
+    if ((st = lba_grow(&h->d_kfe, &h->cap_kfe, kfe.size()))) return st;
+    if ((st = lba_grow(&h->d_kchunk, &h->cap_kchunk, kchunk.size() + 1))) return st;
+    if ((st = lba_grow(&h->d_kfc, &h->cap_kfc, kfc.size()))) return st;
+    if ((st = lba_grow(&h->d_pairs, &h->cap_pairs, pairs.size()))) return st;
+    if ((st = lba_grow(&h->d_pchunk, &h->cap_pchunk, pchunk.size() + 1))) return st;
+    if ((st = lba_grow(&h->d_blkc, &h->cap_blkc, blkc.size()))) return st;
+    if ((st = lba_grow(&h->d_hppart, &h->cap_hppart, 27 * (kchunk.size() + 1)))) return st;
+    if ((st = lba_grow(&h->d_part, &h->cap_part, 42 * (pchunk.size() + 1)))) return st;
+    if ((st = lba_grow(&h->d_dinv, &h->cap_dinv, 10 * (size_t)(L + 1)))) return st;
+    cudaStream_t s = h->stream;
+    ORBX_CUDA(cudaMemcpyAsync(h->d_kfe, kfe.data(), sizeof(int4) * kfe.size(), cudaMemcpyHostToDevice, s));
+    if (!kchunk.empty()) ORBX_CUDA(cudaMemcpyAsync(h->d_kchunk, kchunk.data(), sizeof(int4) * kchunk.size(), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_kfc, kfc.data(), sizeof(int) * kfc.size(), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_pairs, pairs.data(), sizeof(int4) * pairs.size(), cudaMemcpyHostToDevice, s));
+    if (!pchunk.empty()) ORBX_CUDA(cudaMemcpyAsync(h->d_pchunk, pchunk.data(), sizeof(int4) * pchunk.size(), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->d_blkc, blkc.data(), sizeof(int) * blkc.size(), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    D.kfe = h->d_kfe; D.kchunk = h->d_kchunk; D.kf_cstart = h->d_kfc; D.n_kchunks = (int)kchunk.size();
+    D.pairs = h->d_pairs; D.pchunk = h->d_pchunk; D.blk_cstart = h->d_blkc; D.n_pchunks = (int)pchunk.size();
+    D.hppart = h->d_hppart; D.part = h->d_part; D.dinv = h->d_dinv;
     return ORBX_OK;
 }
 
@@ -476,6 +578,10 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
     D.d_mono = (double)(float)sqrt(5.991); D.d_stereo = (double)(float)sqrt(7.815);
     h->stop = P->stop_flag;
     h->loaded = 1;
+    if (h->use_fused && orbx_lba_fused_fits(K, np)) {
+        const orbx_status lst = lba_build_lists(h, ekf, ept, st, kfidx, start);
+        if (lst) return lst;
+    }
     return ORBX_OK;
 }
 
@@ -538,19 +644,19 @@ static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lb
         // is a few hundred microseconds here, less than one iteration of the reference)
         const int capture = *first ? 1 : 0;
         const bool want = capture && (res->first_Hschur || res->first_bschur || res->first_xp);
-        ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 2, h->stream));
+        ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 2, h->stream));   // scal[6..11]: phase timers, cleared per solve
         if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
                                         D.scal + 4, h->stream)))
             return st;
         h->launches++;
-        ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
         if (want) {
             if (res->first_Hschur) ORBX_CUDA(cudaMemcpyAsync(res->first_Hschur, D.Hs, sizeof(double) * D.n * D.n, cudaMemcpyDeviceToHost, h->stream));
             if (res->first_bschur) ORBX_CUDA(cudaMemcpyAsync(res->first_bschur, D.bs, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
             if (res->first_xp) ORBX_CUDA(cudaMemcpyAsync(res->first_xp, D.xp, sizeof(double) * D.n, cudaMemcpyDeviceToHost, h->stream));
         }
         ORBX_CUDA(cudaStreamSynchronize(h->stream));
-        res->lm_trials += (int)h->h_scal[4];
+        res->lm_trials += (int)h->h_scal[4];     // scal[4] was cleared before this launch
         if (capture) { res->first_lambda = h->h_scal[5]; *first = false; }
         return ORBX_OK;
     }
@@ -626,6 +732,7 @@ extern "C" orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *
     if (st) return st;
     LbaDev &D = h->D;
     const int E = D.n_edges;
+    ORBX_CUDA(cudaMemsetAsync(D.scal + 6, 0, sizeof(double) * 6, h->stream));
     if (stop_requested(h)) {       // Optimizer.cc:656-658
         res->stopped = 1;
         memcpy(res->kf_pose, prob->kf_pose, sizeof(double) * 7 * D.n_kf);
@@ -657,6 +764,69 @@ extern "C" orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *
         if (res->chi2) res->chi2[h->perm[s]] = chi[s];
         if (res->erase) res->erase[h->perm[s]] = fl[s];
     }
+    return ORBX_OK;
+}
+
+// ---- asynchronous form: many windows in flight, one handle (and stream) per window -----------------------------------
+extern "C" orbx_status orbx_lba_solve_begin(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2) {
+    if (!h || !prob || its1 < 1 || its2 < 0) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    h->launches = 0;
+    h->pending = 0;
+    orbx_status st = lba_load(h, prob);
+    if (st) return st;
+    LbaDev &D = h->D;
+    if (!h->use_fused || !orbx_lba_fused_fits(D.n_kf, D.np)) {
+        orbx_set_error("orbx_lba_solve_begin: %d free keyframes do not fit the single-kernel path; use orbx_lba_solve_host", D.np);
+        return ORBX_ERR_UNSUPPORTED;
+    }
+    const int E = D.n_edges;
+    h->pending = stop_requested(h) ? 2 : 1;          // 2 = stopped before the start (Optimizer.cc:656-658)
+    if (h->pending == 2) return ORBX_OK;
+    cudaStream_t s = h->stream;
+    ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 8, s));
+    if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its1, 1, 0, nullptr, nullptr, nullptr, D.scal + 4, s))) return st;
+    if (its2 > 0) {
+        k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, s>>>(D, D.level1);
+        if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its2, 0, 0, nullptr, nullptr, nullptr, D.scal + 4, s))) return st;
+    }
+    k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, s>>>(D, h->d_flag);
+    h->launches = its2 > 0 ? 4 : 2;
+    ORBX_CUDA(cudaGetLastError());
+    ORBX_CUDA(cudaMemcpyAsync(h->h_kf, D.kf, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_pt, D.pt, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToHost, s));
+    if (E) {
+        ORBX_CUDA(cudaMemcpyAsync(h->h_chi, D.chi2, sizeof(double) * E, cudaMemcpyDeviceToHost, s));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, E, cudaMemcpyDeviceToHost, s));
+    }
+    ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_lba_solve_end(orbx_lba *h, const orbx_lba_problem *prob, orbx_lba_result *res) {
+    if (!h || !prob || !res || !res->kf_pose || !res->pts || !h->pending) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->device));
+    const LbaDev &D = h->D;
+    const int E = D.n_edges;
+    res->lm_trials = 0; res->stopped = 0; res->first_lambda = 0;
+    if (h->pending == 2) {
+        res->stopped = 1;
+        memcpy(res->kf_pose, prob->kf_pose, sizeof(double) * 7 * D.n_kf);
+        memcpy(res->pts, prob->pts, sizeof(double) * 3 * D.n_pts);
+        if (res->chi2) memset(res->chi2, 0, sizeof(double) * E);
+        if (res->erase) memset(res->erase, 0, E);
+        h->pending = 0;
+        return ORBX_OK;
+    }
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(res->kf_pose, h->h_kf, sizeof(double) * 7 * D.n_kf);
+    memcpy(res->pts, h->h_pt, sizeof(double) * 3 * D.n_pts);
+    for (int s = 0; s < E; s++) {
+        if (res->chi2) res->chi2[h->perm[s]] = h->h_chi[s];
+        if (res->erase) res->erase[h->perm[s]] = h->h_flag[s];
+    }
+    res->lm_trials = (int)h->h_scal[4];
+    h->pending = 0;
     return ORBX_OK;
 }
 
@@ -692,3 +862,10 @@ extern "C" orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_pr
 }
 
 extern "C" int orbx_lba_last_launches(const orbx_lba *h) { return h ? h->launches : 0; }
+
+/* diagnostics: nanoseconds the cluster kernel spent per phase in the last solve (build, schur, reduce, solve, update, err) */
+extern "C" orbx_status orbx_lba_phase_ns(const orbx_lba *h, double out[6]) {
+    if (!h || !out) return ORBX_ERR_INVALID;
+    for (int i = 0; i < 6; i++) out[i] = h->h_scal[6 + i];
+    return ORBX_OK;
+}

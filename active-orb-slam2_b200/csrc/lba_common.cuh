@@ -30,6 +30,17 @@ struct LbaDev {
     double fx, fy, cx, cy, bf;
     float bf_f;
     double d_mono, d_stereo;     // Huber deltas (float sqrt(5.991), sqrt(7.815), Optimizer.cc:569-570)
+    // work lists of the cluster kernel (lba_fused.cu), built on the host per window
+    const int4 *kfe;             // edges ordered by (free) keyframe: edge, keyframe, landmark, stereo
+    const int4 *kchunk;          // chunks of kfe: keyframe, first entry, entries
+    const int *kf_cstart;        // [np + 1] chunks of a keyframe
+    int n_kchunks;
+    const int4 *pairs;           // (edge, edge, landmark) with pose_i <= pose_j, ordered by upper block
+    const int4 *pchunk;          // chunks of pairs: block, first entry, entries, diagonal flag
+    const int *blk_cstart;       // [nblk + 1] chunks of a block
+    int n_pchunks;
+    double *hppart, *part;       // [n_kchunks][27], [n_pchunks][42] partial sums
+    double *dinv;                // [n_pts][10]  D^-1 (6) and D^-1 b_l (3) of the current trial, 16-byte aligned rows
 };
 
 __device__ __forceinline__ void quat_to_R(const double *q, double R[9]) {

@@ -5,19 +5,20 @@
 // round trip per Levenberg trial).  Same arithmetic, same f64, same edge order per landmark as lba.cu.
 //
 //   landmarks (and with them the edges, which are sorted by landmark) are split into 8 contiguous ranges, one per CTA;
-//   H_ll / b_l of a landmark are accumulated in registers by the thread that owns it (no atomics);
-//   H_pp / b_p and the Schur complement are accumulated per CTA in shared memory and summed across the cluster through
-//   distributed shared memory in a fixed order, so every CTA sees bit-identical sums and takes the same Levenberg
-//   decision without any broadcast;
-//   the reduced camera system lives in CTA 0's shared memory in the upper block-triangular layout it was accumulated
-//   in, and is factorised there (blocked 6x6 Cholesky, A = U^T U) without ever touching global memory.
+//   H_ll / b_l of a landmark are accumulated in registers by the thread that owns it;
+//   H_pp / b_p and the Schur complement are sums over lists the host builds once per window (edges by keyframe; pairs of
+//   edges of one landmark by pose-pair block), cut into chunks of 128: a warp reduces a chunk in registers and writes one
+//   partial block, CTA 0 adds the partials of a block in chunk order.  No atomics anywhere, so the sums are
+//   deterministic and every CTA takes the same Levenberg decision from the same numbers without a broadcast;
+//   the reduced camera system lives in CTA 0's shared memory in upper block-triangular layout and is factorised there
+//   (blocked 6x6 Cholesky, A = U^T U) without ever touching global memory.
 // Used when the upper block triangle of H_schur fits shared memory (<= 36 free keyframes); larger windows take lba.cu.
 #include <cooperative_groups.h>
 #include "lba_common.cuh"
 
 namespace cg = cooperative_groups;
 
-#define LF_THREADS 512
+#define LF_THREADS 256
 #define LF_WARPS (LF_THREADS / 32)
 #define LF_CTAS 8
 #define LF_MAX_KF 64
@@ -29,13 +30,14 @@ struct LfParams {
     int iterations, robust;
     int capture;                      // 1: store the first trial's reduced system
     double *cap_Hs, *cap_bs, *cap_xp; // n x n (full symmetric), n, n
-    double *out;                      // [0] trials, [1] lambda of the first trial
+    double *out;                      // [0] trials, [1] lambda of the first trial, [2..7] += nanoseconds per phase
 };
 
 struct LfShared {
     double red[LF_SLOTS][LF_CTAS][4];   // cluster reductions land in CTA 0's copy
     double tmp[32];
     double bc[4];                        // values gathered by thread 0 for the whole CTA
+    double invd[6];                      // 1 / diag(U_kk) of the current pivot block
     int ok;
 };
 
@@ -66,11 +68,12 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
 
     // shared-memory carve-up (identical in every CTA so that map_shared_rank addresses line up)
     double *kfRt = dyn;                               // [n_kf][12]  R (row-major) and t of every keyframe
-    double *hpp = kfRt + 12 * LF_MAX_KF;              // [np][27]    this CTA's share of H_pp / b_p; CTA 0: the total
-    double *hs = hpp + 27 * np;                       // [nblk][36] + [n]  Schur accumulators; CTA 0: the reduced system
-    double *xp = hs + nblk * 36 + n;                  // [n]
+    double *hpp = kfRt + 12 * LF_MAX_KF;              // [np][27]    H_pp / b_p (used in CTA 0)
+    double *hs = hpp + 27 * np;                       // [nblk][36] + [n]  the reduced system (used in CTA 0)
+    double *xp = hs + nblk * 36 + 2 * n;              // [n]   (hs is followed by b_schur [n] and 1/diag(U) [n])
     LfShared *sh0 = cl.map_shared_rank(&sh, 0);
-    double *hpp0 = cl.map_shared_rank(hpp, 0), *hs0 = cl.map_shared_rank(hs, 0), *xp0 = cl.map_shared_rank(xp, 0);
+    double *hs0 = cl.map_shared_rank(hs, 0), *xp0 = cl.map_shared_rank(xp, 0);
+    const int total_warps = C * LF_WARPS, gwarp = rank * LF_WARPS + warp;
 
     const int l0 = (int)((long long)D.n_pts * rank / C), l1 = (int)((long long)D.n_pts * (rank + 1) / C);
     int slot = 0;
@@ -85,7 +88,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             for (int i = 0; i < 9; i++) kfRt[12 * k + i] = R[i];
             kfRt[12 * k + 9] = T[4]; kfRt[12 * k + 10] = T[5]; kfRt[12 * k + 11] = T[6];
         }
-        if (build) for (int i = tid; i < 27 * np; i += LF_THREADS) hpp[i] = 0;
         __syncthreads();
         double chi = 0, mx = 0;
         for (int l = l0 + tid; l < l1; l += LF_THREADS) {
@@ -108,16 +110,18 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 chi += cr;
                 if (!build) continue;
                 const int dim = D.stereo[e] ? 3 : 2;
-                const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = D.fx, fy = D.fy, bf = D.bf;
+                // one reciprocal per edge instead of ~20 f64 divisions (results move by an ulp or two; tolerance 1e-4)
+                const double x = Xc[0], y = Xc[1], iz = 1.0 / Xc[2], iz2 = iz * iz, fx = D.fx, fy = D.fy, bf = D.bf;
+                const double xz = x * iz, yz = y * iz;
                 double A[9], B[18];
                 for (int q = 0; q < 3; q++) {
-                    A[q] = -fx * R[q] / z + fx * x * R[6 + q] / z2;
-                    A[3 + q] = -fy * R[3 + q] / z + fy * y * R[6 + q] / z2;
-                    A[6 + q] = dim == 3 ? A[q] - bf * R[6 + q] / z2 : 0.0;
+                    A[q] = -fx * R[q] * iz + fx * xz * R[6 + q] * iz;
+                    A[3 + q] = -fy * R[3 + q] * iz + fy * yz * R[6 + q] * iz;
+                    A[6 + q] = dim == 3 ? A[q] - bf * R[6 + q] * iz2 : 0.0;
                 }
-                B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
-                B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
-                if (dim == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
+                B[0] = xz * yz * fx; B[1] = -(1 + xz * xz) * fx; B[2] = yz * fx; B[3] = -iz * fx; B[4] = 0; B[5] = xz * iz * fx;
+                B[6] = (1 + yz * yz) * fy; B[7] = -xz * yz * fy; B[8] = -xz * fy; B[9] = 0; B[10] = -iz * fy; B[11] = yz * iz * fy;
+                if (dim == 3) { B[12] = B[0] - bf * y * iz2; B[13] = B[1] + bf * x * iz2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf * iz2; }
                 else { for (int i = 12; i < 18; i++) B[i] = 0; }
                 const double w = rho1 * info;
                 double wr[3];
@@ -128,11 +132,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 for (int a = 0; a < 3; a++) hl[6 + a] += A[a] * wr[0] + A[3 + a] * wr[1] + A[6 + a] * wr[2];
                 const int ip = D.kfidx[kf];
                 if (ip >= 0) {
-                    double *hp = hpp + 27 * ip;
-                    k = 0;
-                    for (int a = 0; a < 6; a++)
-                        for (int b = a; b < 6; b++) atomicAdd(&hp[k++], w * (B[a] * B[b] + B[6 + a] * B[6 + b] + B[12 + a] * B[12 + b]));
-                    for (int a = 0; a < 6; a++) atomicAdd(&hp[21 + a], B[a] * wr[0] + B[6 + a] * wr[1] + B[12 + a] * wr[2]);
                     double *hpl = D.Hpl + 18 * (size_t)e;
                     for (int a = 0; a < 6; a++)
                         for (int b = 0; b < 3; b++) hpl[3 * a + b] = w * (B[a] * A[b] + B[6 + a] * A[3 + b] + B[12 + a] * A[6 + b]);
@@ -151,25 +150,97 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
     double lambda = 0, ni = 2;
     int nBad = 0, trials = 0;
     bool first = P.capture != 0;
+    // phase timers (ns, CTA 0 thread 0): build, schur, reduce, solve, update, err  -> out[2..7]
+    unsigned long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
+    auto tick = [&](int ph) {
+        if (rank == 0 && tid == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (ph >= 0) tph[ph] += now - tlast;
+            tlast = now;
+        }
+    };
 
     for (int it = 0; it < P.iterations; it++) {
         // ---- computeActiveErrors + buildSystem ------------------------------------------------------------------
+        tick(-1);
         linearize(true);
         __threadfence();
         cl.sync();
-        for (int i = rank * LF_THREADS + tid; i < 27 * np; i += C * LF_THREADS) {     // H_pp / b_p: sum the 8 shares in rank order
-            double v = 0;
-            for (int r = 0; r < C; r++) v += cl.map_shared_rank(hpp, r)[i];
-            hpp0[i] = v;                                                               // only this thread touches entry i of CTA 0
+        // H_pp / b_p = sum over the edges of a keyframe of B^T W B / B^T W r: chunks of the keyframe-ordered edge list, one
+        // warp per chunk; B is recomputed from the stored error (cheaper than keeping 27 doubles per edge)
+        for (int ch = gwarp; ch < D.n_kchunks; ch += total_warps) {
+            const int4 cd = D.kchunk[ch];                   // x = keyframe (reduced index), y = first entry, z = entries
+            double acc[27];
+#pragma unroll
+            for (int i = 0; i < 27; i++) acc[i] = 0;
+            for (int q = lane; q < cd.z; q += 32) {
+                const int4 ke = D.kfe[cd.y + q];              // edge, keyframe, landmark, stereo: one round trip for the rest
+                const int e = ke.x;
+                const uint8_t off = D.level1[e];
+                const double *R = kfRt + 12 * ke.y;
+                const double *X = D.pt + 3 * ke.z;
+                const double X0 = __ldcg(X), X1 = __ldcg(X + 1), X2 = __ldcg(X + 2);
+                const double info = D.info[e], c = __ldcg(D.chi2 + e);
+                const double e0 = __ldcg(D.err + 3 * e), e1 = __ldcg(D.err + 3 * e + 1), e2 = __ldcg(D.err + 3 * e + 2);
+                if (off) continue;
+                const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + R[9], y = R[3] * X0 + R[4] * X1 + R[5] * X2 + R[10];
+                const double iz = 1.0 / (R[6] * X0 + R[7] * X1 + R[8] * X2 + R[11]), iz2 = iz * iz, xz = x * iz, yz = y * iz;
+                const double fx = D.fx, fy = D.fy, bf = D.bf;
+                const bool st = ke.w != 0;
+                double B[18];
+                B[0] = xz * yz * fx; B[1] = -(1 + xz * xz) * fx; B[2] = yz * fx; B[3] = -iz * fx; B[4] = 0; B[5] = xz * iz * fx;
+                B[6] = (1 + yz * yz) * fy; B[7] = -xz * yz * fy; B[8] = -xz * fy; B[9] = 0; B[10] = -iz * fy; B[11] = yz * iz * fy;
+                if (st) { B[12] = B[0] - bf * y * iz2; B[13] = B[1] + bf * x * iz2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf * iz2; }
+                else { for (int i = 12; i < 18; i++) B[i] = 0; }
+                double rho1 = 1.0;
+                if (P.robust) {
+                    const double d = st ? D.d_stereo : D.d_mono;
+                    if (c > d * d) rho1 = d / sqrt(c);
+                }
+                const double w = rho1 * info;
+                const double w0 = -info * e0 * rho1, w1 = -info * e1 * rho1, w2 = -info * e2 * rho1;
+                int k = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++)
+#pragma unroll
+                    for (int b = a; b < 6; b++) acc[k++] += w * (B[a] * B[b] + B[6 + a] * B[6 + b] + B[12 + a] * B[12 + b]);
+#pragma unroll
+                for (int a = 0; a < 6; a++) acc[21 + a] += B[a] * w0 + B[6 + a] * w1 + B[12 + a] * w2;
+            }
+            double mine = 0;
+#pragma unroll
+            for (int i = 0; i < 27; i++) {
+                double v = acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == i) mine = v;
+            }
+            if (lane < 27) D.hppart[(size_t)ch * 27 + lane] = mine;
+        }
+        __threadfence();
+        cl.sync();
+        if (rank == 0) {     // partials of a keyframe in chunk order
+            for (int i = tid; i < 27 * np; i += LF_THREADS) {
+                const int p = i / 27, c = i - 27 * p;
+                double v = 0;
+                for (int ch = D.kf_cstart[p]; ch < D.kf_cstart[p + 1]; ch++) v += __ldcg(D.hppart + (size_t)ch * 27 + c);
+                hpp[i] = v;
+            }
+            __syncthreads();
+            if (it == 0) {   // computeLambdaInit also looks at the pose diagonals
+                const int diag6[6] = {0, 6, 11, 15, 18, 20};
+                double mx = 0;
+                for (int i = tid; i < 6 * np; i += LF_THREADS) mx = fmax(mx, fabs(hpp[27 * (i / 6) + diag6[i % 6]]));
+                mx = block_max(mx, sh.tmp);
+                if (tid == 0) sh.red[slot][0][2] = mx;
+            }
         }
         cl.sync();
         if (tid == 0) {      // every CTA sums the same numbers in the same order: identical decisions without a broadcast
             double chi = 0, mx = 0;
             for (int r = 0; r < C; r++) { chi += sh0->red[slot][r][0]; mx = fmax(mx, sh0->red[slot][r][1]); }
-            if (it == 0) {   // computeLambdaInit also looks at the pose diagonals
-                const int diag6[6] = {0, 6, 11, 15, 18, 20};
-                for (int i = 0; i < 6 * np; i++) mx = fmax(mx, fabs(hpp0[27 * (i / 6) + diag6[i % 6]]));
-            }
+            if (it == 0) mx = fmax(mx, sh0->red[slot][0][2]);
             sh.bc[0] = chi; sh.bc[1] = mx;
         }
         __syncthreads();
@@ -177,6 +248,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
         const double maxdiag = sh.bc[1];
         slot = (slot + 1) % LF_SLOTS;
         if (it == 0) { lambda = 1e-5 * maxdiag; ni = 2; nBad = 0; }
+        tick(0);
         const double iniChi = currentChi;
         double rho = 0;
         int qmax = 0;
@@ -184,57 +256,86 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             // ---- push -----------------------------------------------------------------------------------------
             for (int i = 3 * l0 + tid; i < 3 * l1; i += LF_THREADS) P.pt_bak[i] = D.pt[i];
             if (rank == 0) for (int i = tid; i < 7 * n_kf; i += LF_THREADS) P.kf_bak[i] = D.kf[i];
-            // ---- Schur complement of this CTA's landmarks (block_solver.hpp:371-439) ----------------------------
-            for (int i = tid; i < nblk * 36 + n; i += LF_THREADS) hs[i] = 0;
-            __syncthreads();
-            for (int l = l0 + warp; l < l1; l += LF_WARPS) {
-                const int s = D.ptstart[l], ne = D.ptstart[l + 1] - s;
-                if (ne == 0) continue;
+            // ---- Schur complement (block_solver.hpp:371-439) -------------------------------------------------------------
+            // (1) D^-1 = (H_ll + lambda I)^-1 and D^-1 b_l of this CTA's landmarks
+            for (int l = l0 + tid; l < l1; l += LF_THREADS) {
                 const double *hl = D.Hll + 9 * l;
                 double Di[6];
                 dinv3(hl, lambda, Di);
-                const double db0 = Di[0] * hl[6] + Di[1] * hl[7] + Di[2] * hl[8], db1 = Di[1] * hl[6] + Di[3] * hl[7] + Di[4] * hl[8],
-                             db2 = Di[2] * hl[6] + Di[4] * hl[7] + Di[5] * hl[8];
-                for (int i = lane; i < ne; i += 32) {
-                    const int e = s + i, p = D.kfidx[D.ekf[e]];
-                    if (p < 0 || D.level1[e]) continue;
-                    const double *B = D.Hpl + 18 * (size_t)e;
-                    for (int a = 0; a < 6; a++) atomicAdd(&hs[nblk * 36 + 6 * p + a], -(B[3 * a] * db0 + B[3 * a + 1] * db1 + B[3 * a + 2] * db2));
-                }
-                // one lane per (pair, row): 6 outputs each
-                for (int w6 = lane; w6 < ne * ne * 6; w6 += 32) {
-                    const int pr = w6 / 6, a = w6 - 6 * pr, i = pr / ne, j = pr - i * ne, e1 = s + i, e2 = s + j;
-                    const int p1 = D.kfidx[D.ekf[e1]], p2 = D.kfidx[D.ekf[e2]];
-                    if (p1 < 0 || p2 < 0 || p1 > p2 || D.level1[e1] || D.level1[e2] || (p1 == p2 && i != j)) continue;
-                    const double *B1 = D.Hpl + 18 * (size_t)e1 + 3 * a, *B2 = D.Hpl + 18 * (size_t)e2;
-                    const double u0 = B1[0], u1 = B1[1], u2 = B1[2];
-                    const double bd0 = u0 * Di[0] + u1 * Di[1] + u2 * Di[2], bd1 = u0 * Di[1] + u1 * Di[3] + u2 * Di[4],
-                                 bd2 = u0 * Di[2] + u1 * Di[4] + u2 * Di[5];
-                    double *dst = hs + upper_block(p1, p2, np) * 36 + 6 * a;
-#pragma unroll
-                    for (int b = 0; b < 6; b++) atomicAdd(&dst[b], -(bd0 * B2[3 * b] + bd1 * B2[3 * b + 1] + bd2 * B2[3 * b + 2]));
-                }
+                double *o = D.dinv + 10 * (size_t)l;
+                for (int i = 0; i < 6; i++) o[i] = Di[i];
+                o[6] = Di[0] * hl[6] + Di[1] * hl[7] + Di[2] * hl[8];
+                o[7] = Di[1] * hl[6] + Di[3] * hl[7] + Di[4] * hl[8];
+                o[8] = Di[2] * hl[6] + Di[4] * hl[7] + Di[5] * hl[8];
             }
+            __threadfence();
             cl.sync();
-            // ---- sum the 8 shares in rank order into CTA 0, add H_pp + lambda I and b_p -------------------------------
-            for (int i = rank * LF_THREADS + tid; i < nblk * 36 + n; i += C * LF_THREADS) {
-                double v = 0;
-                for (int r = 0; r < C; r++) v += cl.map_shared_rank(hs, r)[i];
-                if (i < nblk * 36) {
+            // (2) every (edge, edge) pair of a landmark contributes B_i D^-1 B_j^T to block (pose_i, pose_j): chunks of the
+            //     block-ordered pair list, one warp per chunk, partial block per chunk
+            for (int ch = gwarp; ch < D.n_pchunks; ch += total_warps) {
+                const int4 cd = D.pchunk[ch];               // x = block, y = first entry, z = entries, w = 1 for a diagonal block
+                double acc[42];
+#pragma unroll
+                for (int i = 0; i < 42; i++) acc[i] = 0;
+                for (int q = lane; q < cd.z; q += 32) {
+                    const int4 pe = D.pairs[cd.y + q];          // edge i, edge j, landmark: everything below is one round trip
+                    const uint8_t off1 = D.level1[pe.x], off2 = D.level1[pe.y];
+                    const double2 *dv = reinterpret_cast<const double2 *>(D.dinv + 10 * (size_t)pe.z);
+                    const double2 *B1 = reinterpret_cast<const double2 *>(D.Hpl + 18 * (size_t)pe.x);
+                    const double2 *B2 = reinterpret_cast<const double2 *>(D.Hpl + 18 * (size_t)pe.y);
+                    double Di[10], b1[18], b2[18];
+#pragma unroll
+                    for (int i = 0; i < 5; i++) { const double2 t = __ldcg(dv + i); Di[2 * i] = t.x; Di[2 * i + 1] = t.y; }
+#pragma unroll
+                    for (int i = 0; i < 9; i++) { const double2 t = __ldcg(B1 + i); b1[2 * i] = t.x; b1[2 * i + 1] = t.y; }
+#pragma unroll
+                    for (int i = 0; i < 9; i++) { const double2 t = __ldcg(B2 + i); b2[2 * i] = t.x; b2[2 * i + 1] = t.y; }
+                    if (off1 || off2) continue;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        const double u0 = b1[3 * a], u1 = b1[3 * a + 1], u2 = b1[3 * a + 2];
+                        const double bd0 = u0 * Di[0] + u1 * Di[1] + u2 * Di[2], bd1 = u0 * Di[1] + u1 * Di[3] + u2 * Di[4],
+                                     bd2 = u0 * Di[2] + u1 * Di[4] + u2 * Di[5];
+#pragma unroll
+                        for (int b = 0; b < 6; b++) acc[6 * a + b] += bd0 * b2[3 * b] + bd1 * b2[3 * b + 1] + bd2 * b2[3 * b + 2];
+                        if (cd.w) acc[36 + a] += u0 * Di[6] + u1 * Di[7] + u2 * Di[8];     // coefficients: B_i D^-1 b_l (:413)
+                    }
+                }
+                double mine = 0;
+#pragma unroll
+                for (int i = 0; i < 42; i++) {
+                    double v = acc[i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == (i & 31)) { if (i < 32) mine = v; else D.part[(size_t)ch * 42 + i] = v; }
+                }
+                D.part[(size_t)ch * 42 + lane] = mine;
+            }
+            __threadfence();
+            cl.sync();
+            tick(1);
+            // (3) CTA 0: H_schur = H_pp + lambda I - sum, b_schur = b_p - sum, partials of a block in chunk order
+            if (rank == 0) {
+                for (int i = tid; i < nblk * 36; i += LF_THREADS) {
                     const int blk = i / 36, ab = i - 36 * blk;
+                    double v = 0;
+                    for (int ch = D.blk_cstart[blk]; ch < D.blk_cstart[blk + 1]; ch++) v -= __ldcg(D.part + (size_t)ch * 42 + ab);
                     int p1 = 0, rem = blk;
                     while (rem >= np - p1) { rem -= np - p1; p1++; }
                     if (rem == 0) {        // diagonal block
                         int a = ab / 6, b = ab - 6 * a;
                         const bool dg = a == b;
                         if (a > b) { const int t = a; a = b; b = t; }
-                        v += hpp0[27 * p1 + a * 6 - a * (a - 1) / 2 + (b - a)] + (dg ? lambda : 0.0);
+                        v += hpp[27 * p1 + a * 6 - a * (a - 1) / 2 + (b - a)] + (dg ? lambda : 0.0);
                     }
-                } else {
-                    const int k = i - nblk * 36;
-                    v += hpp0[27 * (k / 6) + 21 + k % 6];
+                    hs[i] = v;
                 }
-                hs0[i] = v;
+                for (int k = tid; k < n; k += LF_THREADS) {
+                    const int p = k / 6, a = k - 6 * p, blk = upper_block(p, p, np);
+                    double v = hpp[27 * p + 21 + a];
+                    for (int ch = D.blk_cstart[blk]; ch < D.blk_cstart[blk + 1]; ch++) v -= __ldcg(D.part + (size_t)ch * 42 + 36 + a);
+                    hs[nblk * 36 + k] = v;
+                }
             }
             cl.sync();
             if (first && P.cap_Hs) {     // parity tests: the very first reduced system, expanded to a full symmetric matrix
@@ -246,25 +347,36 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 for (int i = rank * LF_THREADS + tid; i < n; i += C * LF_THREADS) P.cap_bs[i] = hs0[nblk * 36 + i];
                 cl.sync();
             }
+            tick(2);
             // ---- reduced solve in CTA 0: A = U^T U on the upper block triangle, then U^T y = b, U x = y -----------------
             if (rank == 0) {
                 if (tid == 0) sh.ok = 1;
                 __syncthreads();
                 for (int k = 0; k < np; k++) {
                     double *Ukk = hs + upper_block(k, k, np) * 36;
-                    if (tid == 0) {
+                    if (warp == 0) {
+                        // 6x6 pivot block: lane b owns column b; 1/U_aa is kept so that every later solve multiplies
+                        double c[6];
+                        const int b = lane < 6 ? lane : 0;
+#pragma unroll
+                        for (int a = 0; a < 6; a++) c[a] = Ukk[6 * a + b];
+                        bool good = true;
+#pragma unroll
                         for (int a = 0; a < 6; a++) {
-                            double d = Ukk[7 * a];
-                            for (int m = 0; m < a; m++) d -= Ukk[6 * m + a] * Ukk[6 * m + a];
-                            if (!(d > 0)) { sh.ok = 0; break; }
-                            d = sqrt(d);
-                            Ukk[7 * a] = d;
-                            for (int b = a + 1; b < 6; b++) {
-                                double v = Ukk[6 * a + b];
-                                for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * Ukk[6 * m + b];
-                                Ukk[6 * a + b] = v / d;
-                            }
+                            double v = c[a];
+#pragma unroll
+                            for (int m = 0; m < a; m++) v -= __shfl_sync(0xffffffffu, c[m], a) * c[m];
+                            const double d = __shfl_sync(0xffffffffu, v, a);
+                            if (!(d > 0)) good = false;
+                            const double is = rsqrt(d);
+                            c[a] = b == a ? d * is : v * is;           // U_aa = sqrt(d); U_ab = v / U_aa
+                            if (lane == a) sh.invd[a] = is;
                         }
+                        if (lane < 6) {
+#pragma unroll
+                            for (int a = 0; a < 6; a++) if (a <= b) Ukk[6 * a + b] = c[a];
+                        }
+                        if (lane == 0 && !good) sh.ok = 0;
                     }
                     __syncthreads();
                     if (!sh.ok) break;
@@ -273,13 +385,17 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                         const int j = k + 1 + t / 6, b = t % 6;
                         double *Akj = hs + upper_block(k, j, np) * 36;
                         double y[6];
+#pragma unroll
                         for (int a = 0; a < 6; a++) {
                             double v = Akj[6 * a + b];
+#pragma unroll
                             for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * y[m];
-                            y[a] = v / Ukk[7 * a];
+                            y[a] = v * sh.invd[a];
                         }
+#pragma unroll
                         for (int a = 0; a < 6; a++) Akj[6 * a + b] = y[a];
                     }
+                    if (tid < 6) hs[nblk * 36 + n + 6 * k + tid] = sh.invd[tid];   // 1/diag(U) for the triangular solves
                     __syncthreads();
                     const int npair = T * (T + 1) / 2;                       // A_ij -= U_ki^T U_kj for k < i <= j
                     for (int t = tid; t < npair * 36; t += LF_THREADS) {
@@ -298,13 +414,15 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 if (sh.ok) {
                     if (warp == 0) {
                         double *b = hs + nblk * 36;
+                        const double *invd = hs + nblk * 36 + n;
                         for (int k = 0; k < np; k++) {                      // forward: U^T y = b
                             const double *Ukk = hs + upper_block(k, k, np) * 36;
                             if (lane == 0) {
+#pragma unroll
                                 for (int a = 0; a < 6; a++) {
                                     double v = b[6 * k + a];
                                     for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * b[6 * k + m];
-                                    b[6 * k + a] = v / Ukk[7 * a];
+                                    b[6 * k + a] = v * invd[6 * k + a];
                                 }
                             }
                             __syncwarp();
@@ -312,6 +430,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                                 const int j = k + 1 + t / 6, c = t % 6;
                                 const double *Ukj = hs + upper_block(k, j, np) * 36;
                                 double v = 0;
+#pragma unroll
                                 for (int a = 0; a < 6; a++) v += Ukj[6 * a + c] * b[6 * k + a];
                                 b[6 * j + c] -= v;
                             }
@@ -320,10 +439,11 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                         for (int k = np - 1; k >= 0; k--) {                 // backward: U x = y
                             const double *Ukk = hs + upper_block(k, k, np) * 36;
                             if (lane == 0) {
+#pragma unroll
                                 for (int a = 5; a >= 0; a--) {
                                     double v = b[6 * k + a];
                                     for (int m = a + 1; m < 6; m++) v -= Ukk[6 * a + m] * b[6 * k + m];
-                                    b[6 * k + a] = v / Ukk[7 * a];
+                                    b[6 * k + a] = v * invd[6 * k + a];
                                 }
                             }
                             __syncwarp();
@@ -331,6 +451,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                                 const int i = t / 6, a = t % 6;
                                 const double *Uik = hs + upper_block(i, k, np) * 36;
                                 double v = 0;
+#pragma unroll
                                 for (int c = 0; c < 6; c++) v += Uik[6 * a + c] * b[6 * k + c];
                                 b[6 * i + a] -= v;
                             }
@@ -345,6 +466,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 if (tid == 0) sh.red[slot][0][2] = sh.ok ? 1.0 : 0.0;
             }
             cl.sync();
+            tick(3);
             if (rank != 0) for (int i = tid; i < n; i += LF_THREADS) xp[i] = xp0[i];
             __syncthreads();
             if (first && P.cap_xp) for (int i = rank * LF_THREADS + tid; i < n; i += C * LF_THREADS) P.cap_xp[i] = xp[i];
@@ -381,8 +503,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             __threadfence();
             cl.sync();
             // ---- computeActiveErrors at the trial state ---------------------------------------------------------------------
+            tick(4);
             linearize(false);
             cl.sync();
+            tick(5);
             if (tid == 0) {
                 double chi = 0, scl = 0;
                 for (int r = 0; r < C; r++) { chi += sh0->red[slot][r][0]; scl += sh0->red[slot][r][3]; }
@@ -410,19 +534,23 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             qmax++;
             __threadfence();
             cl.sync();
+            tick(-1);
         } while (rho < 0 && qmax < 10);
         if (qmax == 10 || rho == 0) break;
         if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
         if (nBad >= 3) break;
     }
-    if (rank == 0 && tid == 0) P.out[0] = (double)trials;
+    if (rank == 0 && tid == 0) {
+        P.out[0] += (double)trials;
+        for (int i = 0; i < 6; i++) P.out[2 + i] += (double)tph[i];
+    }
     cl.sync();     // no CTA may exit while others still read its shared memory
 }
 
 // ---- host glue (called from lba.cu) ---------------------------------------------------------------------------------
 size_t orbx_lba_fused_smem(int np) {
     const size_t nblk = (size_t)np * (np + 1) / 2, n = 6 * (size_t)np;
-    return sizeof(double) * (12 * LF_MAX_KF + 27 * (size_t)np + nblk * 36 + n + n);
+    return sizeof(double) * (12 * LF_MAX_KF + 27 * (size_t)np + nblk * 36 + 3 * n);
 }
 
 bool orbx_lba_fused_fits(int n_kf, int np) { return n_kf <= LF_MAX_KF && np >= 1 && orbx_lba_fused_smem(np) <= 200 * 1024; }

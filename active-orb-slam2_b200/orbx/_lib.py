@@ -74,7 +74,10 @@ def _declare(L):
     L.orbx_lba_destroy.restype = None
     L.orbx_lba_destroy.argtypes = [vp]
     L.orbx_lba_solve_host.argtypes = [vp, vp, i, i, vp]
+    L.orbx_lba_solve_begin.argtypes = [vp, vp, i, i]
+    L.orbx_lba_solve_end.argtypes = [vp, vp, vp]
     L.orbx_lba_build_schur_timed.argtypes = [vp, vp, C.c_double, i, vp, vp, vp]
     L.orbx_lba_last_launches.argtypes = [vp]
+    L.orbx_lba_phase_ns.argtypes = [vp, vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

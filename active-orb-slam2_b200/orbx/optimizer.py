@@ -73,6 +73,22 @@ class Optimizer:
             out.update(Hschur=Hs, bschur=bs, xp=xp, lambda0=R.first_lambda)
         return out
 
+    def begin(self, prob, its1=5, its2=10):
+        """asynchronous LocalBundleAdjustment: enqueue the whole window on this handle's stream and return"""
+        self._pending = pack_problem(prob)
+        check(self._L.orbx_lba_solve_begin(self._h, C.byref(self._pending[0]), its1, its2))
+
+    def end(self):
+        """wait for begin() and return the same dict as LocalBundleAdjustment()"""
+        P, keep = self._pending
+        kf, pt = np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3))
+        chi2, erase = np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8)
+        R = LbaResult()
+        R.kf_pose, R.pts, R.chi2, R.erase = kf.ctypes.data, pt.ctypes.data, chi2.ctypes.data, erase.ctypes.data
+        check(self._L.orbx_lba_solve_end(self._h, C.byref(P), C.byref(R)))
+        self._pending = None
+        return dict(kf=kf, pts=pt, chi2=chi2[:P.n_edges], erase=erase[:P.n_edges], trials=R.lm_trials, stopped=R.stopped)
+
     def build_schur_timed(self, prob, lam, reps=1, want_system=False):
         """one Levenberg trial's system build (residuals + Jacobians + quadratic form + Schur complement), `reps` times;
         -> (milliseconds for all reps, Hschur, bschur)"""
@@ -88,3 +104,9 @@ class Optimizer:
 
     def last_launches(self):
         return self._L.orbx_lba_last_launches(self._h)
+
+    def phase_us(self):
+        """microseconds per phase of the cluster kernel in the last LocalBundleAdjustment call"""
+        ns = np.zeros(6)
+        check(self._L.orbx_lba_phase_ns(self._h, ns.ctypes.data))
+        return dict(zip(("build", "schur", "reduce", "solve", "update", "err"), (ns / 1e3).tolist()))

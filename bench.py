@@ -389,6 +389,26 @@ def main():
                "schur_build_us": 1e3 * ms_build / 50, "kernel_launches_per_window": launches_lba,
                "api": "orbx_lba_solve_host (host buffers in and out, synchronous)",
                "schur_build": "residuals + Jacobians + quadratic form + Schur complement of one Levenberg trial, device time (CUDA events)"}
+        # batched many-window mode: independent windows in flight, one handle + stream each
+        NW = 16
+        ops = [Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank) for _ in range(NW)]
+        probs = [synth.lba_problem(100 + i, n_kf=20, n_pts=3000, stereo=False, n_fixed=1) for i in range(NW)]
+        for o_, p_ in zip(ops, probs):
+            o_.begin(p_)
+        for o_ in ops:
+            o_.end()
+        t0 = time.perf_counter()
+        tr_b = 0
+        for _ in range(3):
+            for o_, p_ in zip(ops, probs):
+                o_.begin(p_)
+            for o_ in ops:
+                tr_b += o_.end()["trials"]
+        bat_s = time.perf_counter() - t0
+        lba["batched"] = {"windows_in_flight": NW, "windows_per_s": 3 * NW / bat_s, "lm_trials_per_s": tr_b / bat_s,
+                          "api": "orbx_lba_solve_begin / orbx_lba_solve_end, one handle per window"}
+        for o_ in ops:
+            o_.close()
         if not args.no_cpu:
             from oracle import oracle_py as O
             t0 = time.perf_counter()

@@ -283,6 +283,14 @@ void orbx_lba_destroy(orbx_lba *h);
  * The reference calls it with its1 = 5, its2 = 10.  Host pointers; synchronous. */
 orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2, orbx_lba_result *res);
 
+/* asynchronous form of orbx_lba_solve_host for many independent windows in flight (batched many-sequence mode, SURVEY
+ * §8e): one handle per window, each with its own stream.  _begin uploads the window and enqueues everything (both
+ * rounds, the outlier passes, the read-back into pinned staging) without waiting; _end waits for that handle and fills
+ * `res` (first_* inspection fields are not filled).  The stop flag is looked at once, in _begin.  Only windows that fit
+ * the single-kernel path (<= 36 free keyframes, <= 64 keyframes) are accepted; others return ORBX_ERR_UNSUPPORTED. */
+orbx_status orbx_lba_solve_begin(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2);
+orbx_status orbx_lba_solve_end(orbx_lba *h, const orbx_lba_problem *prob, orbx_lba_result *res);
+
 /* one Levenberg trial's linear-system work on the current estimates, for bench.py ("LocalBA Schur build"):
  * residuals + Jacobians + quadratic form (BlockSolver::buildSystem) + Schur complement (BlockSolver::solve up to
  * the linear solve) with the given lambda, `reps` times back to back on the handle's stream; the elapsed device
@@ -291,6 +299,9 @@ orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *prob, int i
 orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_problem *prob, double lambda, int reps, float *ms,
                                        double *Hschur, double *bschur);
 int orbx_lba_last_launches(const orbx_lba *h);
+/* diagnostics: nanoseconds the cluster kernel of the last orbx_lba_solve_host spent per phase
+ * (quadratic form, Schur accumulation, cluster reduction, reduced solve, update, residuals) */
+orbx_status orbx_lba_phase_ns(const orbx_lba *h, double out[6]);
 
 #ifdef __cplusplus
 }

@@ -109,3 +109,23 @@ def test_large_window_uses_multikernel_path():
         check_against_oracle(o, p, 3, 3)
     finally:
         o.close()
+
+
+def test_many_windows_in_flight():
+    """orbx_lba_solve_begin / _end: 6 independent windows on 6 handles, results identical to the synchronous call"""
+    probs = [synth.lba_problem(30 + i, n_kf=8 + i, n_pts=400 + 100 * i, n_fixed=1, stereo=bool(i % 2)) for i in range(6)]
+    hs = [Optimizer(max_keyframes=16, max_points=1000, max_edges=5000) for _ in probs]
+    try:
+        for h, p in zip(hs, probs):
+            h.begin(p)
+        outs = [h.end() for h in hs]
+        for h, p, o in zip(hs, probs, outs):
+            ref = h.LocalBundleAdjustment(p)
+            assert o["trials"] == ref["trials"]
+            assert rel(o["kf"], ref["kf"]) < 1e-9 and rel(o["pts"], ref["pts"]) < 1e-9
+            assert np.array_equal(o["erase"], ref["erase"])
+            orc = O.lba_solve(p)
+            assert np.array_equal(o["erase"], orc["erase"]) and rel(o["pts"] - p["pts"], orc["pts"] - p["pts"]) < TOL
+    finally:
+        for h in hs:
+            h.close()
