@@ -421,11 +421,11 @@ def main():
             lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
         op.close()
 
-    if dist is not None:
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = t.tolist()
-    frames_total = B * K * world
+    # the only collectives of the run: max of the timers, all-gather of per-rank counters
+    from orbx import shard
+    ms_total, e2e_s = shard.max_over_ranks([ms_total, e2e_s], device="cuda")
+    counters = shard.gather_counters([B * K, int(round(kp_per_frame * B)), int(round(matches_per_frame * B))], device="cuda")
+    frames_total = sum(c[0] for c in counters)
     value = frames_total / (ms_total * 1e-3)
     e2e = frames_total / e2e_s
 
@@ -444,7 +444,7 @@ def main():
                        "batch_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective on the data path" % world,
                        "l2": "inputs cycle through a %d-frame pool (%.0f MB > 126 MB L2); per-step working set %.0f MB" % (
                            npool * B, npool * B * W * H / 1e6, B * 3.3),
-                       "keypoints_per_frame": kp_per_frame, "match_sweeps_max": max(match_sweeps), "match_sweeps_mean": sum(match_sweeps) / B},
+                       "keypoints_per_frame": kp_per_frame, "frames_per_rank": [c[0] for c in counters], "match_sweeps_max": max(match_sweeps), "match_sweeps_mean": sum(match_sweeps) / B},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pinned host frames + last-frame points -> H2D -> orbx_extractor_run_device + orbx_match_projection_frame_device -> D2H of "
                            "keypoints, descriptors, counts, matches; stream-synchronised every step", "matches_per_step": nm_e2e / K},
