@@ -324,9 +324,9 @@ struct orbx_lba {
     cudaEvent_t ev0, ev1;
     LbaDev D;
     double *d_kf_bak, *d_pt_bak;
-    int *d_kfidx, *d_ptstart, *d_ekf, *d_ept;
-    double *d_obs, *d_info;
-    uint8_t *d_stereo, *d_flag;
+    uint8_t *d_flag;
+    uint8_t *arena_h, *arena_d; size_t arena_cap, arena_used;   // the window as uploaded (see lba_load)
+    std::vector<int> v_start, v_kfidx, v_kcount, v_bcount, v_cur;
     double *h_scal;
     std::vector<int> perm;      // sorted position -> caller's edge index
     const volatile uint8_t *stop;
@@ -336,19 +336,18 @@ struct orbx_lba {
     // work lists of the cluster kernel
     int pending;        // orbx_lba_solve_begin issued, orbx_lba_solve_end not yet
     double *h_kf, *h_pt, *h_chi; uint8_t *h_flag;   // pinned result staging of the asynchronous form
-    int *d_kfc, *d_blkc; int4 *d_kfe, *d_kchunk, *d_pchunk, *d_pairs; double *d_hppart, *d_part, *d_dinv;
-    size_t cap_kfe, cap_kfc, cap_blkc, cap_kchunk, cap_pchunk, cap_pairs, cap_hppart, cap_part, cap_dinv;
+    double *d_hppart, *d_part, *d_dinv;
+    size_t cap_hppart, cap_part;
 };
 
 extern "C" void orbx_lba_destroy(orbx_lba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->D.kf); cudaFree(h->D.pt); cudaFree(h->D.level1); cudaFree(h->D.err); cudaFree(h->D.chi2); cudaFree(h->D.Hpl);
+    cudaFree(h->D.level1); cudaFree(h->D.err); cudaFree(h->D.chi2); cudaFree(h->D.Hpl);
     cudaFree(h->D.Hpp); cudaFree(h->D.Hll); cudaFree(h->D.Hs); cudaFree(h->D.bs); cudaFree(h->D.xp); cudaFree(h->D.xl);
-    cudaFree(h->D.scal); cudaFree(h->d_kf_bak); cudaFree(h->d_pt_bak); cudaFree(h->d_kfidx); cudaFree(h->d_ptstart);
-    cudaFree(h->d_ekf); cudaFree(h->d_ept); cudaFree(h->d_obs); cudaFree(h->d_info); cudaFree(h->d_stereo); cudaFree(h->d_flag);
-    cudaFree(h->d_kfe); cudaFree(h->d_kfc); cudaFree(h->d_blkc); cudaFree(h->d_kchunk); cudaFree(h->d_pchunk); cudaFree(h->d_pairs);
+    cudaFree(h->D.scal); cudaFree(h->d_kf_bak); cudaFree(h->d_pt_bak); cudaFree(h->d_flag); cudaFree(h->arena_d);
+    if (h->arena_h) cudaFreeHost(h->arena_h);
     cudaFree(h->d_hppart); cudaFree(h->d_part); cudaFree(h->d_dinv);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->h_kf) cudaFreeHost(h->h_kf);
@@ -383,28 +382,19 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     orbx_lba *h = new orbx_lba();
     memset(&h->D, 0, sizeof(h->D));
     h->device = device; h->max_kf = max_keyframes; h->max_pts = max_points; h->max_edges = max_edges;
-    h->d_kf_bak = h->d_pt_bak = nullptr; h->d_kfidx = h->d_ptstart = h->d_ekf = h->d_ept = nullptr;
-    h->d_obs = h->d_info = nullptr; h->d_stereo = h->d_flag = nullptr; h->h_scal = nullptr;
+    h->d_kf_bak = h->d_pt_bak = nullptr; h->d_flag = nullptr; h->h_scal = nullptr;
+    h->arena_h = h->arena_d = nullptr; h->arena_cap = h->arena_used = 0;
     h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->stop = nullptr; h->launches = 0; h->loaded = 0;
     { const char *mk = getenv("ORBX_LBA_MULTIKERNEL"); h->use_fused = !(mk && mk[0] == '1'); }
-    h->d_kfc = h->d_blkc = nullptr; h->d_kfe = h->d_kchunk = h->d_pchunk = h->d_pairs = nullptr;
     h->d_hppart = h->d_part = h->d_dinv = nullptr;
     h->pending = 0; h->h_kf = h->h_pt = h->h_chi = nullptr; h->h_flag = nullptr;
-    h->cap_kfe = h->cap_kfc = h->cap_blkc = h->cap_kchunk = h->cap_pchunk = h->cap_pairs = h->cap_hppart = h->cap_part = h->cap_dinv = 0;
+    h->cap_hppart = h->cap_part = 0;
     const size_t K = max_keyframes, L = max_points, E = max_edges, N = 6 * K;
     cudaError_t ce = cudaSuccess;
 #define TRY(x) if (ce == cudaSuccess) ce = (x)
-    TRY(cudaMalloc((void **)&h->D.kf, sizeof(double) * 7 * K));
     TRY(cudaMalloc((void **)&h->d_kf_bak, sizeof(double) * 7 * K));
-    TRY(cudaMalloc((void **)&h->d_kfidx, sizeof(int) * K));
-    TRY(cudaMalloc((void **)&h->D.pt, sizeof(double) * 3 * L));
+    TRY(cudaMalloc((void **)&h->d_dinv, sizeof(double) * 10 * (L + 1)));
     TRY(cudaMalloc((void **)&h->d_pt_bak, sizeof(double) * 3 * L));
-    TRY(cudaMalloc((void **)&h->d_ptstart, sizeof(int) * (L + 1)));
-    TRY(cudaMalloc((void **)&h->d_ekf, sizeof(int) * E));
-    TRY(cudaMalloc((void **)&h->d_ept, sizeof(int) * E));
-    TRY(cudaMalloc((void **)&h->d_obs, sizeof(double) * 3 * E));
-    TRY(cudaMalloc((void **)&h->d_info, sizeof(double) * E));
-    TRY(cudaMalloc((void **)&h->d_stereo, E));
     TRY(cudaMalloc((void **)&h->D.level1, E));
     TRY(cudaMalloc((void **)&h->d_flag, E));
     TRY(cudaMalloc((void **)&h->D.err, sizeof(double) * 3 * E));
@@ -449,79 +439,32 @@ static orbx_status lba_grow(T **p, size_t *cap, size_t need) {
     return ORBX_OK;
 }
 
-#define LBA_CHUNK 128
-// work lists of the cluster kernel: edges by keyframe, (edge, edge) pairs of a landmark by pose-pair block, both cut into chunks
-static orbx_status lba_build_lists(orbx_lba *h, const std::vector<int> &ekf, const std::vector<int> &ept, const std::vector<uint8_t> &st8,
-                                   const std::vector<int> &kfidx, const std::vector<int> &start) {
-    LbaDev &D = h->D;
-    const int E = D.n_edges, L = D.n_pts, np = D.np, nblk = np * (np + 1) / 2;
-    std::vector<int> kcount(np + 1, 0);
-    std::vector<int4> kfe(E > 0 ? E : 1);
-    for (int s = 0; s < E; s++) { const int p = kfidx[ekf[s]]; if (p >= 0) kcount[p + 1]++; }
-    for (int p = 0; p < np; p++) kcount[p + 1] += kcount[p];
-    { std::vector<int> cur(kcount.begin(), kcount.end() - 1);
-      for (int s = 0; s < E; s++) { const int p = kfidx[ekf[s]]; if (p >= 0) kfe[cur[p]++] = make_int4(s, ekf[s], ept[s], st8[s]); } }
-    std::vector<int4> kchunk;
-    std::vector<int> kfc(np + 1, 0);
-    for (int p = 0; p < np; p++) {
-        kfc[p] = (int)kchunk.size();
-        for (int b = kcount[p]; b < kcount[p + 1]; b += LBA_CHUNK) kchunk.push_back(make_int4(p, b, std::min(LBA_CHUNK, kcount[p + 1] - b), 0));
-    }
-    kfc[np] = (int)kchunk.size();
-    auto ub = [np](int p1, int p2) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); };
-    std::vector<int> bcount(nblk + 1, 0);
-    for (int l = 0; l < L; l++)
-        for (int i = start[l]; i < start[l + 1]; i++)
-            for (int j = start[l]; j < start[l + 1]; j++) {
-                const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
-                if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
-                bcount[ub(p1, p2) + 1]++;
-            }
-    for (int b = 0; b < nblk; b++) bcount[b + 1] += bcount[b];
-    std::vector<int4> pairs(bcount[nblk] > 0 ? bcount[nblk] : 1);
-    { std::vector<int> cur(bcount.begin(), bcount.end() - 1);
-      for (int l = 0; l < L; l++)
-          for (int i = start[l]; i < start[l + 1]; i++)
-              for (int j = start[l]; j < start[l + 1]; j++) {
-                  const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
-                  if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
-                  pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
-              } }
-    std::vector<int4> pchunk;
-    std::vector<int> blkc(nblk + 1, 0);
-    { int blk = 0;
-      for (int p1 = 0; p1 < np; p1++)
-          for (int p2 = p1; p2 < np; p2++, blk++) {
-              blkc[blk] = (int)pchunk.size();
-              for (int b = bcount[blk]; b < bcount[blk + 1]; b += LBA_CHUNK)
-                  pchunk.push_back(make_int4(blk, b, std::min(LBA_CHUNK, bcount[blk + 1] - b), p1 == p2));
-          }
-      blkc[nblk] = (int)pchunk.size(); }
-    orbx_status st;
-    if ((st = lba_grow(&h->d_kfe, &h->cap_kfe, kfe.size()))) return st;
-    if ((st = lba_grow(&h->d_kchunk, &h->cap_kchunk, kchunk.size() + 1))) return st;
-    if ((st = lba_grow(&h->d_kfc, &h->cap_kfc, kfc.size()))) return st;
-    if ((st = lba_grow(&h->d_pairs, &h->cap_pairs, pairs.size()))) return st;
-    if ((st = lba_grow(&h->d_pchunk, &h->cap_pchunk, pchunk.size() + 1))) return st;
-    if ((st = lba_grow(&h->d_blkc, &h->cap_blkc, blkc.size()))) return st;
-    if ((st = lba_grow(&h->d_hppart, &h->cap_hppart, 27 * (kchunk.size() + 1)))) return st;
-    if ((st = lba_grow(&h->d_part, &h->cap_part, 42 * (pchunk.size() + 1)))) return st;
-    if ((st = lba_grow(&h->d_dinv, &h->cap_dinv, 10 * (size_t)(L + 1)))) return st;
-    cudaStream_t s = h->stream;
-    ORBX_CUDA(cudaMemcpyAsync(h->d_kfe, kfe.data(), sizeof(int4) * kfe.size(), cudaMemcpyHostToDevice, s));
-    if (!kchunk.empty()) ORBX_CUDA(cudaMemcpyAsync(h->d_kchunk, kchunk.data(), sizeof(int4) * kchunk.size(), cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_kfc, kfc.data(), sizeof(int) * kfc.size(), cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_pairs, pairs.data(), sizeof(int4) * pairs.size(), cudaMemcpyHostToDevice, s));
-    if (!pchunk.empty()) ORBX_CUDA(cudaMemcpyAsync(h->d_pchunk, pchunk.data(), sizeof(int4) * pchunk.size(), cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_blkc, blkc.data(), sizeof(int) * blkc.size(), cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaStreamSynchronize(s));
-    D.kfe = h->d_kfe; D.kchunk = h->d_kchunk; D.kf_cstart = h->d_kfc; D.n_kchunks = (int)kchunk.size();
-    D.pairs = h->d_pairs; D.pchunk = h->d_pchunk; D.blk_cstart = h->d_blkc; D.n_pchunks = (int)pchunk.size();
-    D.hppart = h->d_hppart; D.part = h->d_part; D.dinv = h->d_dinv;
+// One pinned host arena mirrored by one device arena: a window (estimates, sorted edges, work lists) is assembled in
+// place on the host and goes to the device in a single asynchronous copy.
+static orbx_status arena_reserve(orbx_lba *h, size_t bytes) {
+    if (bytes <= h->arena_cap && h->arena_h) return ORBX_OK;
+    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->arena_h) ORBX_CUDA(cudaFreeHost(h->arena_h));
+    if (h->arena_d) ORBX_CUDA(cudaFree(h->arena_d));
+    h->arena_h = h->arena_d = nullptr;
+    bytes += bytes / 4 + 4096;
+    ORBX_CUDA(cudaMallocHost((void **)&h->arena_h, bytes));
+    ORBX_CUDA(cudaMalloc((void **)&h->arena_d, bytes));
+    h->arena_cap = bytes;
     return ORBX_OK;
 }
+template <typename T>
+static T *arena_take(orbx_lba *h, size_t n, T **dev) {
+    h->arena_used = (h->arena_used + 15) & ~(size_t)15;
+    T *p = reinterpret_cast<T *>(h->arena_h + h->arena_used);
+    *dev = reinterpret_cast<T *>(h->arena_d + h->arena_used);
+    h->arena_used += sizeof(T) * n;
+    return p;
+}
 
-// upload a problem: edges sorted by landmark, estimates, reduced indices
+#define LBA_CHUNK 128
+// upload a problem: estimates, edges sorted by landmark, reduced indices, and (for the cluster kernel) the work lists:
+// edges by keyframe and (edge, edge) pairs of a landmark by pose-pair block, both cut into chunks
 static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
     if (!P || P->n_kf < 0 || P->n_pts < 0 || P->n_edges < 0) return ORBX_ERR_INVALID;
     if (P->n_kf > h->max_kf || P->n_pts > h->max_pts || P->n_edges > h->max_edges) {
@@ -538,50 +481,116 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
             orbx_set_error("edge %d refers to vertex (%d, %d) outside the problem", e, P->e_kf[e], P->e_pt[e]);
             return ORBX_ERR_INVALID;
         }
-    std::vector<int> start(L + 1, 0), ekf(E), ept(E), kfidx(K);
-    std::vector<double> obs(3 * (size_t)E), info(E);
-    std::vector<uint8_t> st(E);
-    h->perm.assign(E, 0);
+    // ---- counts first, so that the arena can be sized -----------------------------------------------------------------
+    std::vector<int> &start = h->v_start, &kfidx = h->v_kfidx, &kcount = h->v_kcount, &bcount = h->v_bcount, &cur = h->v_cur;
+    start.assign(L + 1, 0);
     for (int e = 0; e < E; e++) start[P->e_pt[e] + 1]++;
     for (int l = 0; l < L; l++) start[l + 1] += start[l];
-    std::vector<int> cur(start.begin(), start.end() - 1);
+    h->perm.assign(E, 0);
+    cur.assign(start.begin(), start.end() - 1);
     for (int e = 0; e < E; e++) h->perm[cur[P->e_pt[e]]++] = e;       // stable: caller's order inside a landmark
+    kfidx.assign(K, -1);
+    int np = 0;
+    for (int k = 0; k < K; k++) kfidx[k] = P->kf_fixed[k] ? -1 : np++;
+    const bool fused = h->use_fused && orbx_lba_fused_fits(K, np);
+    const int nblk = np * (np + 1) / 2;
+    auto ub = [np](int p1, int p2) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); };
+    size_t npairs = 0, n_kchunks = 0, n_pchunks = 0;
+    if (fused) {
+        kcount.assign(np + 1, 0);
+        bcount.assign(nblk + 1, 0);
+        for (int e = 0; e < E; e++) { const int p = kfidx[P->e_kf[e]]; if (p >= 0) kcount[p + 1]++; }
+        for (int l = 0; l < L; l++)
+            for (int i = start[l]; i < start[l + 1]; i++)
+                for (int j = start[l]; j < start[l + 1]; j++) {
+                    const int p1 = kfidx[P->e_kf[h->perm[i]]], p2 = kfidx[P->e_kf[h->perm[j]]];
+                    if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
+                    bcount[ub(p1, p2) + 1]++;
+                }
+        for (int p = 0; p < np; p++) { n_kchunks += (kcount[p + 1] + LBA_CHUNK - 1) / LBA_CHUNK; kcount[p + 1] += kcount[p]; }
+        for (int b = 0; b < nblk; b++) { n_pchunks += (bcount[b + 1] + LBA_CHUNK - 1) / LBA_CHUNK; bcount[b + 1] += bcount[b]; }
+        npairs = (size_t)bcount[nblk];
+    }
+    const size_t bytes = 8 * (size_t)(7 * K + 3 * L + 3 * E + E) + 4 * (size_t)(K + L + 1 + 2 * E) + E +
+                         16 * ((size_t)E + npairs + n_kchunks + n_pchunks) + 4 * (size_t)(np + 1 + nblk + 1) + 16 * 20;
+    orbx_status st = arena_reserve(h, bytes);
+    if (st) return st;
+    h->arena_used = 0;
+    LbaDev &D = h->D;
+    double *kf = arena_take(h, 7 * (size_t)K, &D.kf), *pt = arena_take(h, 3 * (size_t)L, &D.pt);
+    int *d_i; double *d_d; uint8_t *d_u; int4 *d_4;
+    int *a_kfidx = arena_take(h, K, &d_i); D.kfidx = d_i;
+    int *a_start = arena_take(h, (size_t)L + 1, &d_i); D.ptstart = d_i;
+    int *ekf = arena_take(h, E, &d_i); D.ekf = d_i;
+    int *ept = arena_take(h, E, &d_i); D.ept = d_i;
+    double *obs = arena_take(h, 3 * (size_t)E, &d_d); D.obs = d_d;
+    double *info = arena_take(h, E, &d_d); D.info = d_d;
+    uint8_t *st8 = arena_take(h, E, &d_u); D.stereo = d_u;
+    memcpy(kf, P->kf_pose, sizeof(double) * 7 * K);
+    memcpy(pt, P->pts, sizeof(double) * 3 * L);
+    memcpy(a_kfidx, kfidx.data(), sizeof(int) * K);
+    memcpy(a_start, start.data(), sizeof(int) * (L + 1));
     for (int s = 0; s < E; s++) {
         const int e = h->perm[s];
-        ekf[s] = P->e_kf[e]; ept[s] = P->e_pt[e]; st[s] = P->e_stereo[e] ? 1 : 0;
+        ekf[s] = P->e_kf[e]; ept[s] = P->e_pt[e]; st8[s] = P->e_stereo[e] ? 1 : 0;
         obs[3 * s] = P->e_obs[3 * e]; obs[3 * s + 1] = P->e_obs[3 * e + 1]; obs[3 * s + 2] = P->e_obs[3 * e + 2];
         info[s] = (double)P->e_inv_sigma2[e];
     }
-    int np = 0;
-    for (int k = 0; k < K; k++) kfidx[k] = P->kf_fixed[k] ? -1 : np++;
+    D.n_kchunks = D.n_pchunks = 0;
+    if (fused) {
+        int4 *kfe = arena_take(h, E > 0 ? E : 1, &d_4); D.kfe = d_4;
+        int4 *kchunk = arena_take(h, n_kchunks + 1, &d_4); D.kchunk = d_4;
+        int *kfc = arena_take(h, (size_t)np + 1, &d_i); D.kf_cstart = d_i;
+        int4 *pairs = arena_take(h, npairs + 1, &d_4); D.pairs = d_4;
+        int4 *pchunk = arena_take(h, n_pchunks + 1, &d_4); D.pchunk = d_4;
+        int *blkc = arena_take(h, (size_t)nblk + 1, &d_i); D.blk_cstart = d_i;
+        cur.assign(kcount.begin(), kcount.end() - 1);
+        for (int s = 0; s < E; s++) { const int p = kfidx[ekf[s]]; if (p >= 0) kfe[cur[p]++] = make_int4(s, ekf[s], ept[s], st8[s]); }
+        int nc = 0;
+        for (int p = 0; p < np; p++) {
+            kfc[p] = nc;
+            for (int b = kcount[p]; b < kcount[p + 1]; b += LBA_CHUNK) kchunk[nc++] = make_int4(p, b, std::min(LBA_CHUNK, kcount[p + 1] - b), 0);
+        }
+        kfc[np] = nc;
+        D.n_kchunks = nc;
+        cur.assign(bcount.begin(), bcount.end() - 1);
+        for (int l = 0; l < L; l++)
+            for (int i = start[l]; i < start[l + 1]; i++)
+                for (int j = start[l]; j < start[l + 1]; j++) {
+                    const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
+                    if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
+                    pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
+                }
+        nc = 0;
+        int blk = 0;
+        for (int p1 = 0; p1 < np; p1++)
+            for (int p2 = p1; p2 < np; p2++, blk++) {
+                blkc[blk] = nc;
+                for (int b = bcount[blk]; b < bcount[blk + 1]; b += LBA_CHUNK)
+                    pchunk[nc++] = make_int4(blk, b, std::min(LBA_CHUNK, bcount[blk + 1] - b), p1 == p2);
+            }
+        blkc[nblk] = nc;
+        D.n_pchunks = nc;
+        if ((st = lba_grow(&h->d_hppart, &h->cap_hppart, 27 * ((size_t)D.n_kchunks + 1)))) return st;
+        if ((st = lba_grow(&h->d_part, &h->cap_part, 42 * ((size_t)D.n_pchunks + 1)))) return st;
+        D.hppart = h->d_hppart; D.part = h->d_part; D.dinv = h->d_dinv;
+    }
+    if (h->arena_used > h->arena_cap) {
+        orbx_set_error("internal: arena sized %zu, used %zu", h->arena_cap, h->arena_used);
+        return ORBX_ERR_NOMEM;
+    }
     cudaStream_t s = h->stream;
-    LbaDev &D = h->D;
-    ORBX_CUDA(cudaMemcpyAsync(D.kf, P->kf_pose, sizeof(double) * 7 * K, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(D.pt, P->pts, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_kfidx, kfidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_ptstart, start.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(h->arena_d, h->arena_h, h->arena_used, cudaMemcpyHostToDevice, s));
     if (E) {
-        ORBX_CUDA(cudaMemcpyAsync(h->d_ekf, ekf.data(), sizeof(int) * E, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(cudaMemcpyAsync(h->d_ept, ept.data(), sizeof(int) * E, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(cudaMemcpyAsync(h->d_obs, obs.data(), sizeof(double) * 3 * E, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(cudaMemcpyAsync(h->d_info, info.data(), sizeof(double) * E, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(cudaMemcpyAsync(h->d_stereo, st.data(), E, cudaMemcpyHostToDevice, s));
         ORBX_CUDA(cudaMemsetAsync(D.level1, 0, E, s));
         ORBX_CUDA(cudaMemsetAsync(D.chi2, 0, sizeof(double) * E, s));
         ORBX_CUDA(cudaMemsetAsync(D.err, 0, sizeof(double) * 3 * E, s));
     }
-    ORBX_CUDA(cudaStreamSynchronize(s));      // the host vectors go out of scope
     D.n_kf = K; D.n_pts = L; D.n_edges = E; D.np = np; D.n = 6 * np;
-    D.kfidx = h->d_kfidx; D.ptstart = h->d_ptstart; D.ekf = h->d_ekf; D.ept = h->d_ept; D.obs = h->d_obs; D.info = h->d_info;
-    D.stereo = h->d_stereo;
     D.fx = P->fx; D.fy = P->fy; D.cx = P->cx; D.cy = P->cy; D.bf = P->bf; D.bf_f = (float)P->bf;
     D.d_mono = (double)(float)sqrt(5.991); D.d_stereo = (double)(float)sqrt(7.815);
     h->stop = P->stop_flag;
     h->loaded = 1;
-    if (h->use_fused && orbx_lba_fused_fits(K, np)) {
-        const orbx_status lst = lba_build_lists(h, ekf, ept, st, kfidx, start);
-        if (lst) return lst;
-    }
     return ORBX_OK;
 }
 
