@@ -258,7 +258,7 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
                     return ORBX_ERR_UNSUPPORTED;
                 }
                 g.chunks.push_back(c);
-                const int tp = (int)align_up(c.tw + 3, 4) + 4;
+                const int tp = (int)align_up(c.tw + 15, 16);     // TMA box: starts at a 16-byte aligned column, width multiple of 16
                 if (tp > g.fast_tp) g.fast_tp = tp;
                 if (ch > g.fast_th) g.fast_th = ch;
             }
@@ -272,6 +272,45 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
     g.pyr_bytes = pyr;
     g.blur_bytes = blur;
     g.cand_words = cand;
+    return ORBX_OK;
+}
+
+// TMA descriptors: level l of every frame as a (pitch, padded rows, frames) u8 tensor; one box = one FAST tile.  The
+// driver entry point is fetched through the runtime so that the library does not link libcuda.
+static orbx_status build_tensor_maps(orbx_extractor *e) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ORBX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) {
+            orbx_set_error("cuTensorMapEncodeTiled is not available in this driver");
+            return ORBX_ERR_UNSUPPORTED;
+        }
+        encode = (encode_fn)fn;
+    }
+    if (e->n_chunks == 0) return ORBX_OK;
+    if (e->fast_tp > 256 || e->fast_th > 256 || e->fast_tp % 16) {
+        orbx_set_error("FAST tile %dx%d does not fit a TMA box", e->fast_tp, e->fast_th);
+        return ORBX_ERR_UNSUPPORTED;
+    }
+    for (int l = 0; l < e->nlevels; l++) {
+        const OrbxLevel &L = e->lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.ph, (cuuint64_t)e->max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)e->pyr_frame_cap};
+        const cuuint32_t box[3] = {(cuuint32_t)e->fast_tp, (cuuint32_t)e->fast_th, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&e->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, e->d_pyr + L.off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            orbx_set_error("cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            return ORBX_ERR_CUDA;
+        }
+    }
     return ORBX_OK;
 }
 
@@ -326,6 +365,7 @@ static orbx_status configure(orbx_extractor *e, int w, int h) {
     e->fast_tp = g.fast_tp;
     e->fast_th = g.fast_th;
     if ((st = orbx_fast_init(orbx_fast_smem_bytes(e->fast_tp, e->fast_th)))) return st;
+    if ((st = build_tensor_maps(e))) return st;
     e->cur_w = w;
     e->cur_h = h;
     return ORBX_OK;

@@ -78,16 +78,22 @@ struct FastShared {
     uint8_t cellof[256];          // detection column -> cell of the chunk
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // dynamic smem layout: [tile bytes th x tp][score bytes th x tp][out words][list u16 th x tp]
+// The tile arrives by TMA: one cp.async.bulk.tensor of the (tp x th_max) box of the level's tensor map whose first column
+// is (19 + x0) rounded down to 16 (TMA wants 16-byte aligned row starts) and first row 19 + y0, completion on an mbarrier;
+// rows / columns past the level read as zero and are never looked at.
 // Three phases per pass, so that only the few pixels that can be corners pay for the 16-arc score and the 3x3
 // suppression: (1) compass test on every pixel, survivors compacted into a list; (2) score of the listed pixels;
 // (3) suppression of the listed pixels with a non-zero score.
 __global__ void __launch_bounds__(FAST_THREADS)
 k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv,
        const OrbxFastChunk *__restrict__ chunks, uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand,
-       int *__restrict__ status, int ini_th, int min_th, int tp_max, int th_max) {
-    extern __shared__ __align__(16) uint8_t smem[];
+       int *__restrict__ status, int ini_th, int min_th, int tp_max, int th_max, const __grid_constant__ OrbxTmaps maps) {
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ FastShared sh;
+    __shared__ __align__(8) uint64_t mbar;
     const OrbxFastChunk ck = chunks[blockIdx.x];
     const int frame = blockIdx.y;
     const OrbxLevel &L = lv[ck.level];
@@ -95,20 +101,27 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
 
-    // ---- stage the tile: 32-bit loads from the padded level buffer --------------------------------
-    const int gx0 = ORBX_EDGE + ck.x0;                // padded-buffer column of the tile origin
-    const int shift = gx0 & 3;
-    const int words = (shift + tw + 3) >> 2;
-    const int tp = tp_max;                             // smem row pitch (bytes, multiple of 4)
+    // ---- stage the tile by TMA ---------------------------------------------------------------------------
+    const int tp = tp_max;                             // smem row pitch = box width (multiple of 16)
+    const int gx0 = ORBX_EDGE + ck.x0;                 // padded-buffer column of the tile origin
+    const int shift = gx0 & 15;                        // the box starts at the aligned column gx0 - shift
     uint8_t *tile = smem;
     uint8_t *score = smem + (size_t)tp * th_max;
     uint32_t *out = reinterpret_cast<uint32_t *>(score + (size_t)tp * th_max);
     uint16_t *list = reinterpret_cast<uint16_t *>(out + orbx_fast_out_words(tp_max, th_max));
-    const uint8_t *src = pyr + (size_t)frame * pyr_frame + L.off + (size_t)(ORBX_EDGE + ck.y0) * L.pitch + (gx0 - shift);
-    for (int r = warp; r < th; r += FAST_THREADS / 32) {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch);
-        uint32_t *d = reinterpret_cast<uint32_t *>(tile + (size_t)r * tp);
-        for (int c = lane; c < words; c += 32) d[c] = __ldg(g + c);
+    const uint32_t mbar_a = smem_u32(&mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(tp * th_max);
+        const uint64_t tmap = reinterpret_cast<uint64_t>(&maps.m[ck.level]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(tile)), "l"(tmap), "r"(gx0 - shift), "r"(ORBX_EDGE + (int)ck.y0), "r"(frame), "r"(mbar_a)
+                     : "memory");
     }
     for (int i = tid; i < (tp * th) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
     const int vw = tw - 6, vh = th - 6;                // detection region
@@ -118,6 +131,9 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     if (tid == 0) { sh.n_out = 0; sh.any_empty = 0; sh.n_list = 0; }
     __syncthreads();
 
+    // everything above overlapped the copy; now wait for the tile (phase 0 of the barrier)
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(mbar_a) : "memory");
     const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
     uint8_t *s0 = score + shift + 3 * tp + 3;
 
@@ -216,7 +232,7 @@ orbx_status orbx_launch_fast(orbx_extractor *e, int batch, cudaStream_t s) {
     const size_t smem = orbx_fast_smem_bytes(tp_max, th_max);
     dim3 grid(e->n_chunks, batch);
     k_fast<<<grid, FAST_THREADS, smem, s>>>(e->d_pyr, e->pyr_frame_cap, e->d_lv, e->d_chunks, e->d_cand, e->cand_frame_cap,
-                                            e->d_ncand, e->d_status, e->ini_th, e->min_th, tp_max, th_max);
+                                            e->d_ncand, e->d_status, e->ini_th, e->min_th, tp_max, th_max, e->tmaps);
     e->last_launches++;
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;

@@ -1,5 +1,6 @@
 // Internal declarations shared by the CUDA translation units of liborbx.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -83,6 +84,11 @@ struct OrbxBlurTile {
 #define ORBX_BLUR_TW 64
 #define ORBX_BLUR_TH 32
 
+// TMA descriptors of the pyramid levels: 3-D u8 tensors (padded column, padded row, frame), one box = one FAST tile
+struct OrbxTmaps {
+    CUtensorMap m[ORBX_MAX_LEVELS];
+};
+
 struct orbx_extractor {
     int device;
     int nfeatures, nlevels, ini_th, min_th;
@@ -103,7 +109,8 @@ struct orbx_extractor {
     int2 *d_ryt;  size_t ryt_cap;
     uint32_t *d_lut;  size_t lut_cap;    // quadtree path LUTs
     OrbxFastChunk *d_chunks;  int n_chunks, chunks_cap;
-    int fast_tp, fast_th;     // smem tile pitch / rows of the FAST kernel (max over chunks)
+    int fast_tp, fast_th;     // smem tile pitch / rows of the FAST kernel (max over chunks) = TMA box
+    OrbxTmaps tmaps;          // rebuilt by configure()
     OrbxBlurTile *d_btiles;   int n_btiles, btiles_cap;
     uint32_t *d_cand;         // [max_batch][cand_frame_cap]  unsorted candidates (x | y<<12 | score<<24)
     uint32_t *d_skey;         // quadtree keys, sorted
