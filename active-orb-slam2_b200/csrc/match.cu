@@ -490,6 +490,95 @@ k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ choice_all,
     if (tid == 0) { *J.nmatches = sh.nacc; sweeps_all[job] = sh.changed; }
 }
 
+// ---- window + Hamming core of SearchByProjection(KF, Scw, ...), Fuse x2, SearchBySim3 ---------------------------------------
+struct WindowJob {
+    orbx_frame_view F;
+    int n_pts;
+    const orbx_window_point *pts;
+    const uint8_t *pt_desc;
+    int flags, max_dist;
+    const float *inv_sigma2;
+    int32_t *best_idx, *best_dist, *nacc;
+};
+
+struct WindowEval {
+    const WindowJob &J;
+    const orbx_frame_view &F;
+    const MatchGrid &g;
+    int2 *list;
+    __device__ bool blocks(int) const { return (J.flags & 2) != 0; }
+    __device__ int decide(unsigned k1, int p1, unsigned, int) const {
+        return (int)(k1 >> 22) <= J.max_dist ? (p1 & 0xffff) : -1;
+    }
+    template <class Emit>
+    __device__ void candidates(int i, Emit emit) const {
+        const orbx_window_point p = J.pts[i];
+        if (!p.valid) return;
+        const uint8_t *d = J.pt_desc + (size_t)32 * i;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
+        // level window applied like the reference does after KeyFrame::GetFeaturesInArea: oct < min || oct > max -> skip
+        features_in_area(F, g, list, p.u, p.v, p.radius, -1, -1, [&](bool valid, int idx, int seq) {
+            unsigned key = 0;
+            if (valid) {
+                const orbx_keypoint kp = F.keys_un[idx];
+                if (kp.octave < p.min_level || kp.octave > p.max_level) valid = false;
+                if (valid && (J.flags & 1)) {       // Fuse: reprojection error gate, ORBmatcher.cc:903-927
+                    const float ex = __fsub_rn(p.u, kp.x), ey = __fsub_rn(p.v, kp.y);
+                    const float urk = F.u_right ? F.u_right[idx] : -1.f;
+                    float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    double lim = 5.99;
+                    if (urk >= 0) { const float er = __fsub_rn(p.ur, urk); e2 = __fadd_rn(e2, __fmul_rn(er, er)); lim = 7.8; }
+                    if ((double)__fmul_rn(e2, J.inv_sigma2[kp.octave]) > lim) valid = false;
+                }
+                if (valid) key = ((unsigned)hamming256(d0, d1, F.desc + (size_t)32 * idx) << 22) | (unsigned)seq;
+            }
+            emit(valid, key, idx);
+        });
+    }
+};
+
+__global__ void __launch_bounds__(M_THREADS)
+k_match_window(const WindowJob *__restrict__ jobs, int *__restrict__ choice_all, int *__restrict__ minclaim_all,
+               int *__restrict__ sweeps_all, int2 *__restrict__ cand_all, int *__restrict__ lcount_all, int max_kp, int max_pts) {
+    extern __shared__ __align__(16) int dyn[];
+    __shared__ MatchShared sh;
+    __shared__ WindowJob J;
+    __shared__ MatchGrid g;
+    __shared__ int2 lists[M_WARPS][M_LIST];
+    const int tid = threadIdx.x, job = blockIdx.x;
+    if (tid == 0) { J = jobs[job]; g.carve(dyn, max_kp); }
+    __syncthreads();
+    const orbx_frame_view &F = J.F;
+    const int n = min(F.n_dev ? *F.n_dev : F.n, max_kp), n_pts = min(J.n_pts, max_pts);
+    int *choice2 = choice_all + (size_t)job * 2 * max_pts, *minclaim2 = minclaim_all + (size_t)job * 2 * max_kp;
+    int2 *cand = cand_all + (size_t)job * M_CAND * max_pts;
+    int *lcount = lcount_all + (size_t)job * 2 * max_pts;
+    grid_build(F, n, sh, g);
+    WindowEval ev{J, F, g, lists[tid >> 5]};
+    int fb;
+    resolve_claims(n, n_pts, (J.flags & 2) ? F.claimed : nullptr, choice2, minclaim2, cand, lcount, lcount + max_pts, max_pts, max_kp, sh, ev, fb);
+    const int *choice = choice2 + (size_t)fb * max_pts;
+    if (tid == 0) sh.nacc = 0;
+    __syncthreads();
+    // the distance of the chosen candidate: look it up in the point's list (overflowed lists recompute it)
+    int nacc = 0;
+    for (int i = tid; i < n_pts; i += M_THREADS) {
+        const int c = choice[i];
+        int dist = 256;
+        if (c >= 0) {
+            nacc++;
+            const uint8_t *d = J.pt_desc + (size_t)32 * i;
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
+            dist = hamming256(d0, d1, F.desc + (size_t)32 * c);
+        }
+        J.best_idx[i] = c;
+        J.best_dist[i] = dist;
+    }
+    if (nacc) atomicAdd(&sh.nacc, nacc);
+    __syncthreads();
+    if (tid == 0) { *J.nacc = sh.nacc; sweeps_all[job] = sh.changed; }
+}
+
 // ---- SearchByBoW (KF, F) / (KF, KF) and SearchForTriangulation --------------------------------------------------
 struct BucketDev {
     orbx_bucket_job J;          // all pointers are device pointers
@@ -744,6 +833,7 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     TRY(ORBX_RAISE_SMEM(k_match_frame));
     TRY(ORBX_RAISE_SMEM(k_match_points));
     TRY(ORBX_RAISE_SMEM(k_match_buckets));
+    TRY(ORBX_RAISE_SMEM(k_match_window));
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_matcher_create: %s", cudaGetErrorString(ce));
@@ -974,5 +1064,48 @@ extern "C" orbx_status orbx_match_buckets_host(orbx_matcher *m, const orbx_bucke
     if (job->a.n) ORBX_CUDA(cudaMemcpyAsync(match_a, m->d_match, sizeof(int32_t) * job->a.n, cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match_window_host(orbx_matcher *m, const orbx_frame_view *F, int n_pts, const orbx_window_point *pts,
+                                              const uint8_t *pt_desc, int flags, const float *inv_sigma2, int max_dist,
+                                              int32_t *best_idx, int32_t *best_dist, int32_t *n_accepted) {
+    if (!m || !F || n_pts < 0 || !best_idx || !best_dist || (n_pts && (!pts || !pt_desc)) || max_dist < 0 || max_dist > 256 ||
+        ((flags & 1) && !inv_sigma2))
+        return ORBX_ERR_INVALID;
+    if (n_pts > m->max_pts) {
+        orbx_set_error("%d points, matcher was created for %d", n_pts, m->max_pts);
+        return ORBX_ERR_CAPACITY;
+    }
+    ORBX_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    WindowJob J;
+    memset(&J, 0, sizeof(J));
+    orbx_status st = stage_frame(m, F, &J.F, s);
+    if (st) return st;
+    m->arena_used = 0;
+    const void *p;
+    if ((st = arena_put(m, pts, sizeof(orbx_window_point) * n_pts, &p, s))) return st; J.pts = (const orbx_window_point *)p;
+    if ((st = arena_put(m, pt_desc, (size_t)32 * n_pts, &p, s))) return st; J.pt_desc = (const uint8_t *)p;
+    if (flags & 1) { if ((st = arena_put(m, inv_sigma2, sizeof(float) * F->nlevels, &p, s))) return st; J.inv_sigma2 = (const float *)p; }
+    J.n_pts = n_pts; J.flags = flags; J.max_dist = max_dist;
+    // outputs live in the scratch that the other matchers use for `owner` (max_kp ints) -- sized for points here
+    if ((st = arena_put(m, best_idx, sizeof(int32_t) * (n_pts ? n_pts : 1), &p, s))) return st; J.best_idx = (int32_t *)p;
+    if ((st = arena_put(m, best_dist, sizeof(int32_t) * (n_pts ? n_pts : 1), &p, s))) return st; J.best_dist = (int32_t *)p;
+    J.nacc = m->d_nm;
+    const void *djob;
+    if ((st = arena_put(m, &J, sizeof(J), &djob, s))) return st;
+    k_match_window<<<1, M_THREADS, m->smem, s>>>((const WindowJob *)djob, m->d_choice, m->d_minclaim, m->d_sweeps, m->d_cand, m->d_lcount,
+                                                 m->max_kp, m->max_pts);
+    m->last_launches = 1;
+    ORBX_CUDA(cudaGetLastError());
+    if (n_pts) {
+        ORBX_CUDA(cudaMemcpyAsync(best_idx, J.best_idx, sizeof(int32_t) * n_pts, cudaMemcpyDeviceToHost, s));
+        ORBX_CUDA(cudaMemcpyAsync(best_dist, J.best_dist, sizeof(int32_t) * n_pts, cudaMemcpyDeviceToHost, s));
+    }
+    int32_t nacc = 0;
+    ORBX_CUDA(cudaMemcpyAsync(&nacc, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    if (n_accepted) *n_accepted = nacc;
     return ORBX_OK;
 }

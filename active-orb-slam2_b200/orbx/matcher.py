@@ -202,3 +202,24 @@ def _search_for_triangulation(self, KF1, KF2, F12, epipole, sigma2_2, scale_2, b
 ORBmatcher.SearchByBoW = _search_by_bow_frame
 ORBmatcher.SearchByBoWKF = _search_by_bow_kf
 ORBmatcher.SearchForTriangulation = _search_for_triangulation
+
+
+WINDOW_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                               ("valid", "u1"), ("pad", "u1", (3,))])
+
+
+def _match_window(self, KF, pts, pt_desc, flags, inv_sigma2, max_dist):
+    """window + Hamming core of SearchByProjection(KF, Scw, ...) [flags=2], Fuse(KF, pts, th) [1], Fuse(KF, Scw, ...) [0] and
+    SearchBySim3 [0]: -> (accepted, best_idx[n], best_dist[n]); see include/orbx.h for what the adapter does on the host"""
+    f, keep = _view(KF)
+    pts = np.ascontiguousarray(pts, WINDOW_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    s2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    bi, bd = np.full(max(len(pts), 1), -1, np.int32), np.full(max(len(pts), 1), 256, np.int32)
+    n = C.c_int32()
+    check(self._L.orbx_match_window_host(self._h, C.byref(f), len(pts), pts.ctypes.data, pd.ctypes.data, flags, s2.ctypes.data, max_dist,
+                                         bi.ctypes.data, bd.ctypes.data, C.byref(n)))
+    return n.value, bi[:len(pts)], bd[:len(pts)]
+
+
+ORBmatcher.MatchWindow = _match_window

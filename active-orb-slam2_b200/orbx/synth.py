@@ -318,3 +318,27 @@ def bow_pair(seed, n_a=1000, n_b=1000, n_common=600, n_nodes=90, nlevels=8):
     C2 = t21                                                              # camera-1 centre in camera-2 coordinates
     ex, ey = np.float32(fx * C2[0] / C2[2] + cx), np.float32(fy * C2[1] / C2[2] + cy)
     return A, B, F12, (ex, ey), (sf * sf).astype(np.float32), sf
+
+
+def window_points(rng, cur, n_pts, th=3.0, dup_frac=0.2):
+    """points already projected into a keyframe (u, v, ur, radius, level window) near its keypoints, plus descriptors"""
+    WP = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                   ("valid", "u1"), ("pad", "u1", (3,))])
+    n = len(cur["keys_un"])
+    tgt = rng.integers(0, n, n_pts)
+    ndup = int(dup_frac * n_pts)
+    if ndup and n_pts > ndup:
+        tgt[-ndup:] = tgt[:ndup]
+    k = cur["keys_un"][tgt]
+    sf = cur["scale_factors"]
+    lvl = np.clip(k["octave"] + rng.integers(0, 2, n_pts), 0, len(sf) - 1)
+    pts = np.zeros(n_pts, WP)
+    pts["u"] = k["x"] + rng.normal(0, 1.2, n_pts)
+    pts["v"] = k["y"] + rng.normal(0, 1.2, n_pts)
+    ur = cur["u_right"][tgt]
+    pts["ur"] = np.where(ur >= 0, ur + rng.normal(0, 1.5, n_pts), pts["u"] - 8)
+    pts["radius"] = np.float32(th) * sf[lvl]
+    pts["min_level"], pts["max_level"] = lvl - 1, lvl
+    pts["valid"] = rng.random(n_pts) > 0.1
+    desc = flip_bits(rng, cur["desc"][tgt], rng.integers(0, 80, n_pts))
+    return pts, desc

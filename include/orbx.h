@@ -203,6 +203,28 @@ typedef struct {
 } orbx_frame_match_job;
 orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
                                                void *stream);
+/* ---- window + Hamming core of the keyframe projection searches -------------------------------------------------------------
+ * serves ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)  (ORBmatcher.cc:290-403; flags = 2)
+ *        ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th)                                      (:825-975;  flags = 1)
+ *        ORBmatcher::Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)                    (:977-1100; flags = 0)
+ *        both passes of ORBmatcher::SearchBySim3                                           (:1102-1326; flags = 0)
+ * The adapter evaluates the per-point host geometry in the reference's own arithmetic (projection, IsInImage, the
+ * distance-invariance and viewing-angle gates -> valid; MapPoint::PredictScale -> level window; th * scale -> radius)
+ * and applies the outcome on the host in reference order (vpMatched, Replace / AddObservation, the mutual check).
+ * F is the KeyFrame seen through orbx_frame_view (KeyFrame::GetFeaturesInArea, KeyFrame.cc:630-669, is the Frame
+ * version without the level filter).  flags & 1: reprojection chi2 gate of Fuse (5.99 / 7.8 with inv_sigma2 =
+ * mvInvLevelSigma2); flags & 2: claims -- keypoints marked in F->claimed (vpMatched[idx] != NULL) or chosen by an
+ * earlier point are skipped.  best_idx[i] = keypoint or -1 (no candidate, or best distance > max_dist);
+ * best_dist[i] = its distance (256 if none). */
+typedef struct {
+    float u, v, ur, radius;
+    int32_t min_level, max_level;   /* nPredictedLevel - 1, nPredictedLevel */
+    uint8_t valid, pad[3];
+} orbx_window_point;
+orbx_status orbx_match_window_host(orbx_matcher *m, const orbx_frame_view *F, int n_pts, const orbx_window_point *pts,
+                                   const uint8_t *pt_desc, int flags, const float *inv_sigma2, int max_dist,
+                                   int32_t *best_idx, int32_t *best_dist, int32_t *n_accepted);
+
 /* ---- vocabulary-node ("bucket") matchers ---------------------------------------------------------------------
  * replaces ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)        (ORBmatcher.cc:159-288)  mode 0
  *          ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)      (ORBmatcher.cc:522-655)  mode 1

@@ -296,6 +296,58 @@ int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_la
     return nmatches;
 }
 
+/* Window + Hamming core shared by ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:290-403),
+ * Fuse(KeyFrame*, vpMapPoints, th) (:825-975), Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:977-1100) and the two
+ * passes of SearchBySim3 (:1102-1326).  The caller evaluates each point's host geometry in the reference's own arithmetic
+ * (projection, IsInImage, distance-invariance and viewing-angle gates -> valid; PredictScale -> the level window;
+ * th * scale[level] -> radius) and applies the outcome (vpMatched / map mutations / mutual check) on the host.
+ *   flags & 1  reprojection chi2 gate of Fuse (:903-927): 5.99 (monocular keypoint) / 7.8 (stereo keypoint, with ur)
+ *   flags & 2  claims: keypoints with F->claimed, or chosen by an earlier point, are skipped (vpMatched[idx], :375-376)
+ * best_idx[i] = chosen keypoint or -1 (none, or best distance > max_dist); best_dist[i] = its distance (256 if none). */
+int orbo_match_window(const orbo_frame *F, int n_pts, const orbo_window_point *P, const uint8_t *pt_desc, int flags,
+                      const float *inv_sigma2, int max_dist, int32_t *best_idx, int32_t *best_dist) {
+    grid_t g;
+    grid_build(F, &g);
+    int *ind = (int *)malloc(sizeof(int) * (F->n > 0 ? F->n : 1));
+    uint8_t *blocked = (uint8_t *)calloc(F->n > 0 ? F->n : 1, 1);
+    if (flags & 2) for (int k = 0; k < F->n; k++) blocked[k] = F->claimed ? F->claimed[k] : 0;
+    int nacc = 0;
+    for (int i = 0; i < n_pts; i++) {
+        const orbo_window_point *p = &P[i];
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (!p->valid) continue;
+        const int n = features_in_area(F, &g, p->u, p->v, p->radius, -1, -1, ind);     /* KeyFrame::GetFeaturesInArea has no level filter */
+        int bestDist = 256, bestIdx = -1;
+        for (int c = 0; c < n; c++) {
+            const int idx = ind[c];
+            if ((flags & 2) && blocked[idx]) continue;
+            const orbo_keypoint *kp = &F->keys_un[idx];
+            if (kp->octave < p->min_level || kp->octave > p->max_level) continue;
+            if (flags & 1) {
+                const float ex = p->u - kp->x, ey = p->v - kp->y;
+                if (F->u_right && F->u_right[idx] >= 0) {
+                    const float er = p->ur - F->u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_sigma2[kp->octave] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_sigma2[kp->octave] > 5.99) continue;
+                }
+            }
+            const int dist = orbo_hamming256(pt_desc + (size_t)32 * i, F->desc + (size_t)32 * idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestIdx >= 0 && bestDist <= max_dist) {
+            best_idx[i] = bestIdx; best_dist[i] = bestDist;
+            if (flags & 2) blocked[bestIdx] = 1;
+            nacc++;
+        }
+    }
+    free(ind); free(blocked);
+    grid_free(&g);
+    return nacc;
+}
+
 /* ---- bucket (vocabulary-node) matchers -------------------------------------------------------------------------
  * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)        src/ORBmatcher.cc:159-288   mode 0
  * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)     src/ORBmatcher.cc:522-655   mode 1

@@ -408,3 +408,20 @@ def search_by_projection_kf(cur, pts, pt_desc, Rcw, tcw, th, orb_dist, check_ori
     m = np.full(f.n, -1, np.int32) if match is None else np.ascontiguousarray(match, np.int32).copy()
     n = L.orbo_search_by_projection_kf(C.byref(f), len(pts), _p(pts), _p(pd), _p(R), _p(t), th, orb_dist, int(check_ori), _p(m))
     return n, m
+
+
+WINDOW_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                               ("valid", "u1"), ("pad", "u1", (3,))])
+
+
+def match_window(F, pts, pt_desc, flags, inv_sigma2, max_dist):
+    """window + Hamming core of SearchByProjection(KF, Scw, ...), Fuse x2, SearchBySim3 -> (accepted, best_idx, best_dist)"""
+    L = lib(); _declare_match(L)
+    L.orbo_match_window.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f, keep = _oframe(F)
+    pts = np.ascontiguousarray(pts, WINDOW_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    s2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    bi, bd = np.zeros(max(len(pts), 1), np.int32), np.zeros(max(len(pts), 1), np.int32)
+    n = L.orbo_match_window(C.byref(f), len(pts), _p(pts), _p(pd), flags, _p(s2), max_dist, _p(bi), _p(bd))
+    return n, bi[:len(pts)], bd[:len(pts)]

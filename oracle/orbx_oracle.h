@@ -98,6 +98,13 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
 
 int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_last_point *Lp, const uint8_t *pt_desc,
                                  const float Rcw[9], const float tcw[3], float th, int orb_dist, int check_ori, int32_t *match);
+typedef struct {                 /* a point already projected into the keyframe by the caller */
+    float u, v, ur, radius;      /* projection, u - bf/z, th * mvScaleFactors[nPredictedLevel] */
+    int32_t min_level, max_level; /* nPredictedLevel - 1, nPredictedLevel */
+    uint8_t valid, pad[3];
+} orbo_window_point;
+int orbo_match_window(const orbo_frame *F, int n_pts, const orbo_window_point *P, const uint8_t *pt_desc, int flags,
+                      const float *inv_sigma2, int max_dist, int32_t *best_idx, int32_t *best_dist);
 typedef struct {                 /* one KeyFrame / Frame as the vocabulary-node matchers read it */
     int32_t n;
     const orbo_keypoint *keys_un; /* mvKeysUn (angle, pt, octave) */

@@ -264,3 +264,43 @@ def test_search_by_projection_keyframe(seed):
         n2, m2 = brute_frame(cur, pts, desc, R, t, False, False, th, True, kf=True, orb_dist=od)
         assert n == n2 and np.array_equal(m, m2)
     assert n > 20
+
+
+def brute_window_match(F, pts, desc, flags, inv_s2, max_dist):
+    k = F["keys_un"]
+    blocked = F["claimed"].astype(bool).copy() if flags & 2 else np.zeros(len(k), bool)
+    bi, bd = np.full(len(pts), -1, np.int32), np.full(len(pts), 256, np.int32)
+    for i, p in enumerate(pts):
+        if not p["valid"]:
+            continue
+        best, b = 256, -1
+        for j in brute_window(F, p["u"], p["v"], p["radius"], -1, -1):
+            if blocked[j] or k["octave"][j] < p["min_level"] or k["octave"][j] > p["max_level"]:
+                continue
+            if flags & 1:
+                ex, ey = f32(p["u"] - k["x"][j]), f32(p["v"] - k["y"][j])
+                e2, lim = f32(f32(ex * ex) + f32(ey * ey)), 5.99
+                if F["u_right"][j] >= 0:
+                    er = f32(p["ur"] - F["u_right"][j]); e2, lim = f32(e2 + f32(er * er)), 7.8
+                if np.float64(f32(e2 * inv_s2[k["octave"][j]])) > lim:
+                    continue
+            d = popcount_dist(desc[i], F["desc"][j])
+            if d < best:
+                best, b = d, j
+        if b >= 0 and best <= max_dist:
+            bi[i], bd[i] = b, best
+            if flags & 2:
+                blocked[b] = True
+    return int((bi >= 0).sum()), bi, bd
+
+
+@pytest.mark.parametrize("flags,max_dist", [(0, 100), (1, 50), (2, 50), (3, 50)])
+def test_match_window(flags, max_dist):
+    rng = np.random.default_rng(70 + flags)
+    F = synth.random_frame(rng, 500, claimed_frac=0.1)
+    pts, desc = synth.window_points(rng, F, 400)
+    inv_s2 = (1.0 / (F["scale_factors"] ** 2)).astype(f32)
+    n, bi, bd = O.match_window(F, pts, desc, flags, inv_s2, max_dist)
+    n2, bi2, bd2 = brute_window_match(F, pts, desc, flags, inv_s2, max_dist)
+    assert n == n2 and np.array_equal(bi, bi2) and np.array_equal(bd, bd2)
+    assert n > 30

@@ -180,3 +180,17 @@ def test_search_by_projection_keyframe(matcher, seed):
         n, m = matcher.SearchByProjectionKF(cur, pts, desc, R, t, th, od)
         assert n == n_ref and np.array_equal(m, m_ref)
     assert n_ref > 0
+
+
+@pytest.mark.parametrize("flags,max_dist", [(0, 100), (1, 50), (2, 50), (3, 50)])
+@pytest.mark.parametrize("seed", range(3))
+def test_match_window(matcher, flags, max_dist, seed):
+    """window + Hamming core of SearchByProjection(KF, Scw, ...), Fuse x2, SearchBySim3 (ORBmatcher.cc:290-403, :825-1326)"""
+    rng = np.random.default_rng(500 + 10 * flags + seed)
+    F = synth.random_frame(rng, 1500, claimed_frac=0.1)
+    pts, desc = synth.window_points(rng, F, 1200, th=3.0 if seed else 8.0, dup_frac=0.3)
+    inv_s2 = (1.0 / (F["scale_factors"] ** 2)).astype(np.float32)
+    n_ref, bi_ref, bd_ref = O.match_window(F, pts, desc, flags, inv_s2, max_dist)
+    n, bi, bd = matcher.MatchWindow(F, pts, desc, flags, inv_s2, max_dist)
+    assert n == n_ref and np.array_equal(bi, bi_ref) and np.array_equal(bd, bd_ref)
+    assert n_ref > 100
