@@ -29,6 +29,10 @@ for p in (ROOT, os.path.join(ROOT, "active-orb-slam2_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np  # noqa: E402
 
 W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
