@@ -490,6 +490,121 @@ k_match_points(const PointsJob *__restrict__ jobs, int *__restrict__ choice_all,
     if (tid == 0) { *J.nmatches = sh.nacc; sweeps_all[job] = sh.changed; }
 }
 
+// ---- SearchForInitialization (ORBmatcher.cc:405-520) ----------------------------------------------------------------------
+struct InitJob {
+    orbx_frame_view F2;
+    int n1;
+    const orbx_keypoint *keys1;
+    const uint8_t *desc1;
+    const float *prev_xy;
+    int window, check_ori;
+    float nnratio;
+    int32_t *match12, *nmatches;
+    int *matched_dist, *match21;     // [F2.n] scratch
+};
+
+__global__ void __launch_bounds__(M_THREADS) k_match_init(const InitJob *__restrict__ jobs, int max_kp) {
+    extern __shared__ __align__(16) int dyn[];
+    __shared__ MatchShared sh;
+    __shared__ InitJob J;
+    __shared__ MatchGrid g;
+    __shared__ int2 lists[M_WARPS][M_LIST];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { J = jobs[blockIdx.x]; g.carve(dyn, max_kp); }
+    __syncthreads();
+    const orbx_frame_view &F2 = J.F2;
+    const int n2 = min(F2.n, max_kp), n1 = J.n1;
+    grid_build(F2, n2, sh, g);
+    for (int k = tid; k < n2; k += M_THREADS) { J.matched_dist[k] = 0x7fffffff; J.match21[k] = -1; }
+    for (int i = tid; i < n1; i += M_THREADS) J.match12[i] = -1;
+    if (tid < HISTO_LENGTH) sh.hist[tid] = 0;
+    if (tid == 0) sh.nacc = 0;
+    __syncthreads();
+    const float factor = 1.0f / HISTO_LENGTH;
+    if (tid < 32) {
+        // strictly sequential over F1's keypoints: a closer match may steal a keypoint from an earlier one (:470-474)
+        int nmatches = 0;
+        for (int i1 = 0; i1 < n1; i1++) {
+            const orbx_keypoint kp1 = J.keys1[i1];
+            if (kp1.octave > 0) continue;
+            const uint8_t *d = J.desc1 + (size_t)32 * i1;
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(d)), d1 = __ldg(reinterpret_cast<const uint4 *>(d + 16));
+            Best2 b;
+            features_in_area(F2, g, lists[0], J.prev_xy[2 * i1], J.prev_xy[2 * i1 + 1], (float)J.window, kp1.octave, kp1.octave,
+                             [&](bool valid, int i2, int seq) {
+                                 if (!valid) return;
+                                 const int dist = hamming256(d0, d1, F2.desc + (size_t)32 * i2);
+                                 if (J.matched_dist[i2] <= dist) return;
+                                 b.add(((unsigned)dist << 22) | (unsigned)seq, i2);
+                             });
+            const unsigned w1 = warp_min(b.k1);
+            if (w1 == 0xffffffffu) continue;
+            const int src = __ffs(__ballot_sync(0xffffffffu, b.k1 == w1)) - 1;
+            const int bestIdx2 = __shfl_sync(0xffffffffu, b.p1, src);
+            const unsigned w2 = warp_min(lane == src ? b.k2 : b.k1);
+            const int bestDist = (int)(w1 >> 22);
+            const float bestDist2 = w2 == 0xffffffffu ? 2147483647.0f : (float)(int)(w2 >> 22);      // (float)INT_MAX
+            if (bestDist <= 50 && (float)bestDist < __fmul_rn(bestDist2, J.nnratio)) {
+                if (lane == 0) {
+                    const int old = J.match21[bestIdx2];
+                    if (old >= 0) { J.match12[old] = -1; nmatches--; }
+                    J.match12[i1] = bestIdx2;
+                    J.match21[bestIdx2] = i1;
+                    J.matched_dist[bestIdx2] = bestDist;
+                    nmatches++;
+                    if (J.check_ori) {
+                        float rot = __fsub_rn(kp1.angle, F2.keys_un[bestIdx2].angle);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, factor));
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        sh.hist[bin]++;
+                        J.match21[bestIdx2] = i1;
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+            }
+        }
+        if (lane == 0) sh.nacc = nmatches;
+    }
+    __syncthreads();
+    // rotation histogram entries are the accepted i1 in order, including ones whose match was stolen later: the reference
+    // only removes an entry's match if it still has one (:503-507).  An accepted i1 is recognised by its histogram bin being
+    // recomputable only while it still holds a match; stolen ones have match12 == -1 and are skipped there as well.  The bin
+    // COUNTS however include stolen entries, which is why they were accumulated above at acceptance time.
+    if (J.check_ori) {
+        if (tid == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, a = -1, b = -1, c = -1;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int s = sh.hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; c = b; b = a; a = i; }
+                else if (s > max2) { max3 = max2; max2 = s; c = b; b = i; }
+                else if (s > max3) { max3 = s; c = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { b = -1; c = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { c = -1; }
+            sh.keep[0] = a; sh.keep[1] = b; sh.keep[2] = c;
+            sh.nrej = 0;
+        }
+        __syncthreads();
+        int nrej = 0;
+        for (int i1 = tid; i1 < n1; i1 += M_THREADS) {
+            const int i2 = J.match12[i1];
+            if (i2 < 0) continue;
+            float rot = __fsub_rn(J.keys1[i1].angle, F2.keys_un[i2].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == HISTO_LENGTH) bin = 0;
+            if (bin != sh.keep[0] && bin != sh.keep[1] && bin != sh.keep[2]) { J.match12[i1] = -1; nrej++; }
+        }
+        if (nrej) atomicAdd(&sh.nrej, nrej);
+        __syncthreads();
+        if (tid == 0) sh.nacc -= sh.nrej;
+    }
+    __syncthreads();
+    if (tid == 0) *J.nmatches = sh.nacc;
+}
+
 // ---- window + Hamming core of SearchByProjection(KF, Scw, ...), Fuse x2, SearchBySim3 ---------------------------------------
 struct WindowJob {
     orbx_frame_view F;
@@ -834,6 +949,7 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     TRY(ORBX_RAISE_SMEM(k_match_points));
     TRY(ORBX_RAISE_SMEM(k_match_buckets));
     TRY(ORBX_RAISE_SMEM(k_match_window));
+    TRY(ORBX_RAISE_SMEM(k_match_init));
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_matcher_create: %s", cudaGetErrorString(ce));
@@ -1107,5 +1223,42 @@ extern "C" orbx_status orbx_match_window_host(orbx_matcher *m, const orbx_frame_
     ORBX_CUDA(cudaMemcpyAsync(&nacc, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaStreamSynchronize(s));
     if (n_accepted) *n_accepted = nacc;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match_initialization_host(orbx_matcher *m, const orbx_frame_view *F1, const orbx_frame_view *F2,
+                                                      const float *prev_xy, int window_size, float nnratio, int check_ori,
+                                                      int32_t *match12, int32_t *nmatches) {
+    if (!m || !F1 || !F2 || !match12 || !nmatches || F1->n < 0 || (F1->n && (!F1->keys_un || !F1->desc || !prev_xy)) || window_size < 0)
+        return ORBX_ERR_INVALID;
+    if (F1->n > m->max_pts) {
+        orbx_set_error("%d keypoints in F1, matcher was created for %d points", F1->n, m->max_pts);
+        return ORBX_ERR_CAPACITY;
+    }
+    ORBX_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    InitJob J;
+    memset(&J, 0, sizeof(J));
+    orbx_status st = stage_frame(m, F2, &J.F2, s);
+    if (st) return st;
+    m->arena_used = 0;
+    const void *p;
+    const size_t n1 = (size_t)F1->n;
+    if ((st = arena_put(m, F1->keys_un, sizeof(orbx_keypoint) * n1, &p, s))) return st; J.keys1 = (const orbx_keypoint *)p;
+    if ((st = arena_put(m, F1->desc, 32 * n1, &p, s))) return st; J.desc1 = (const uint8_t *)p;
+    if ((st = arena_put(m, prev_xy, sizeof(float) * 2 * n1, &p, s))) return st; J.prev_xy = (const float *)p;
+    J.n1 = F1->n; J.window = window_size; J.check_ori = check_ori; J.nnratio = nnratio;
+    J.match12 = m->d_choice;                 // scratch of the claim resolution, unused by this kernel: >= max_pts ints
+    J.matched_dist = m->d_minclaim;          // >= 2 * max_kp ints
+    J.match21 = m->d_minclaim + m->max_kp;
+    J.nmatches = m->d_nm;
+    const void *djob;
+    if ((st = arena_put(m, &J, sizeof(J), &djob, s))) return st;
+    k_match_init<<<1, M_THREADS, m->smem, s>>>((const InitJob *)djob, m->max_kp);
+    m->last_launches = 1;
+    ORBX_CUDA(cudaGetLastError());
+    if (n1) ORBX_CUDA(cudaMemcpyAsync(match12, m->d_choice, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
     return ORBX_OK;
 }

@@ -68,6 +68,7 @@ def _declare(L):
     L.orbx_match_projection_frame_device.argtypes = [vp, vp, i, vp]
     L.orbx_match_projection_keyframe_host.argtypes = [vp, vp, i, vp, vp, vp, vp, f, i, i, vp, vp]
     L.orbx_match_buckets_host.argtypes = [vp, vp, vp, vp]
+    L.orbx_match_initialization_host.argtypes = [vp, vp, vp, vp, i, f, i, vp, vp]
     L.orbx_match_window_host.argtypes = [vp, vp, i, vp, vp, i, vp, i, vp, vp, vp]
     L.orbx_matcher_last_launches.argtypes = [vp]
     L.orbx_matcher_last_sweeps.argtypes = [vp, vp, i]

@@ -223,3 +223,23 @@ def _match_window(self, KF, pts, pt_desc, flags, inv_sigma2, max_dist):
 
 
 ORBmatcher.MatchWindow = _match_window
+
+
+def _search_for_initialization(self, F1, F2, vbPrevMatched, windowSize=100):
+    """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:405 -> (nmatches, vnMatches12,
+    updated vbPrevMatched)"""
+    f1, k1 = _view(F1)
+    f2, k2 = _view(F2)
+    prev = np.ascontiguousarray(vbPrevMatched, np.float32).reshape(-1, 2).copy()
+    m = np.full(max(f1.n, 1), -1, np.int32)
+    n = C.c_int32()
+    check(self._L.orbx_match_initialization_host(self._h, C.byref(f1), C.byref(f2), prev.ctypes.data, int(windowSize), self.mfNNratio,
+                                                 int(self.mbCheckOrientation), m.ctypes.data, C.byref(n)))
+    m = m[:f1.n]
+    sel = m >= 0                                   # ORBmatcher.cc:513-516
+    prev[sel, 0] = F2["keys_un"]["x"][m[sel]]
+    prev[sel, 1] = F2["keys_un"]["y"][m[sel]]
+    return n.value, m, prev
+
+
+ORBmatcher.SearchForInitialization = _search_for_initialization

@@ -203,6 +203,15 @@ typedef struct {
 } orbx_frame_match_job;
 orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const orbx_frame_match_job *d_jobs, int n_jobs,
                                                void *stream);
+/* replaces int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched,
+ * vector<int> &vnMatches12, int windowSize) (ORBmatcher.cc:405-520; monocular initialisation).  prev_xy = vbPrevMatched as
+ * (x, y) pairs, F1->n of them; match12 = vnMatches12.  The reference's last step (vbPrevMatched[i1] = F2 keypoint of the
+ * match, :513-516) is a copy the adapter does from match12.  A later, closer match may take a keypoint away from an
+ * earlier one (:470-474), so the points are processed strictly in order (one warp, lanes over a window's keypoints). */
+orbx_status orbx_match_initialization_host(orbx_matcher *m, const orbx_frame_view *F1, const orbx_frame_view *F2,
+                                           const float *prev_xy, int window_size, float nnratio, int check_ori,
+                                           int32_t *match12, int32_t *nmatches);
+
 /* ---- window + Hamming core of the keyframe projection searches -------------------------------------------------------------
  * serves ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)  (ORBmatcher.cc:290-403; flags = 2)
  *        ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th)                                      (:825-975;  flags = 1)

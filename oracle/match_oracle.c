@@ -296,6 +296,63 @@ int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_la
     return nmatches;
 }
 
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:405-520.
+ * prev[i] = vbPrevMatched[i1] (x, y); match12 out (F1 keypoints -> F2 index or -1); returns nmatches.  The final
+ * "update prev matched" step (:513-516) is a copy the caller does from match12. */
+int orbo_search_for_initialization(const orbo_frame *F1, const orbo_frame *F2, const float *prev_xy, int window_size, float nnratio,
+                                   int check_ori, int32_t *match12) {
+    grid_t g;
+    grid_build(F2, &g);
+    int *ind = (int *)malloc(sizeof(int) * (F2->n > 0 ? F2->n : 1));
+    int *matched_dist = (int *)malloc(sizeof(int) * (F2->n > 0 ? F2->n : 1)), *match21 = (int *)malloc(sizeof(int) * (F2->n > 0 ? F2->n : 1));
+    int *hist_i1 = (int *)malloc(sizeof(int) * (F1->n > 0 ? F1->n : 1)), *hist_bin = (int *)malloc(sizeof(int) * (F1->n > 0 ? F1->n : 1));
+    for (int k = 0; k < F2->n; k++) { matched_dist[k] = 2147483647; match21[k] = -1; }
+    for (int i = 0; i < F1->n; i++) match12[i] = -1;
+    int nh = 0, nmatches = 0;
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int i1 = 0; i1 < F1->n; i1++) {
+        const int level1 = F1->keys_un[i1].octave;
+        if (level1 > 0) continue;
+        const int n = features_in_area(F2, &g, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window_size, level1, level1, ind);
+        if (n == 0) continue;
+        const uint8_t *d1 = F1->desc + (size_t)32 * i1;
+        int bestDist = 2147483647, bestDist2 = 2147483647, bestIdx2 = -1;
+        for (int c = 0; c < n; c++) {
+            const int i2 = ind[c];
+            const int dist = orbo_hamming256(d1, F2->desc + (size_t)32 * i2);
+            if (matched_dist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if ((float)bestDist < (float)bestDist2 * nnratio) {
+                if (match21[bestIdx2] >= 0) { match12[match21[bestIdx2]] = -1; nmatches--; }
+                match12[i1] = bestIdx2;
+                match21[bestIdx2] = i1;
+                matched_dist[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) {
+                    float rot = F1->keys_un[i1].angle - F2->keys_un[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    hist_i1[nh] = i1; hist_bin[nh] = bin; nh++;
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int cnt[HISTO_LENGTH] = {0}, a, b, c;
+        for (int j = 0; j < nh; j++) cnt[hist_bin[j]]++;
+        orbo_three_maxima(cnt, HISTO_LENGTH, &a, &b, &c);
+        for (int j = 0; j < nh; j++)
+            if (hist_bin[j] != a && hist_bin[j] != b && hist_bin[j] != c && match12[hist_i1[j]] >= 0) { match12[hist_i1[j]] = -1; nmatches--; }
+    }
+    free(ind); free(matched_dist); free(match21); free(hist_i1); free(hist_bin);
+    grid_free(&g);
+    return nmatches;
+}
+
 /* Window + Hamming core shared by ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:290-403),
  * Fuse(KeyFrame*, vpMapPoints, th) (:825-975), Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:977-1100) and the two
  * passes of SearchBySim3 (:1102-1326).  The caller evaluates each point's host geometry in the reference's own arithmetic

@@ -425,3 +425,15 @@ def match_window(F, pts, pt_desc, flags, inv_sigma2, max_dist):
     bi, bd = np.zeros(max(len(pts), 1), np.int32), np.zeros(max(len(pts), 1), np.int32)
     n = L.orbo_match_window(C.byref(f), len(pts), _p(pts), _p(pd), flags, _p(s2), max_dist, _p(bi), _p(bd))
     return n, bi[:len(pts)], bd[:len(pts)]
+
+
+def search_for_initialization(F1, F2, prev_xy, window_size=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization -> (nmatches, match12)"""
+    L = lib(); _declare_match(L)
+    L.orbo_search_for_initialization.argtypes = [C.POINTER(OFrame), C.POINTER(OFrame), C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    f1, k1 = _oframe(F1)
+    f2, k2 = _oframe(F2)
+    pv = np.ascontiguousarray(prev_xy, np.float32)
+    m = np.zeros(max(f1.n, 1), np.int32)
+    n = L.orbo_search_for_initialization(C.byref(f1), C.byref(f2), _p(pv), window_size, nnratio, int(check_ori), _p(m))
+    return n, m[:f1.n]

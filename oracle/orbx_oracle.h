@@ -98,6 +98,8 @@ int orbo_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orb
 
 int orbo_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_last_point *Lp, const uint8_t *pt_desc,
                                  const float Rcw[9], const float tcw[3], float th, int orb_dist, int check_ori, int32_t *match);
+int orbo_search_for_initialization(const orbo_frame *F1, const orbo_frame *F2, const float *prev_xy, int window_size, float nnratio,
+                                   int check_ori, int32_t *match12);
 typedef struct {                 /* a point already projected into the keyframe by the caller */
     float u, v, ur, radius;      /* projection, u - bf/z, th * mvScaleFactors[nPredictedLevel] */
     int32_t min_level, max_level; /* nPredictedLevel - 1, nPredictedLevel */

@@ -304,3 +304,67 @@ def test_match_window(flags, max_dist):
     n2, bi2, bd2 = brute_window_match(F, pts, desc, flags, inv_s2, max_dist)
     assert n == n2 and np.array_equal(bi, bi2) and np.array_equal(bd, bd2)
     assert n > 30
+
+
+def brute_init(F1, F2, prev, win, nnratio, check_ori):
+    k1, k2 = F1["keys_un"], F2["keys_un"]
+    md = np.full(len(k2), 2 ** 31 - 1, np.int64)
+    m21 = np.full(len(k2), -1, np.int64)
+    m12 = np.full(len(k1), -1, np.int32)
+    hist, nm = [], 0
+    for i1 in range(len(k1)):
+        if k1["octave"][i1] > 0:
+            continue
+        b1, b2, bi = 2 ** 31 - 1, 2 ** 31 - 1, -1
+        for i2 in brute_window(F2, prev[i1, 0], prev[i1, 1], f32(win), 0, 0):
+            d = popcount_dist(F1["desc"][i1], F2["desc"][i2])
+            if md[i2] <= d:
+                continue
+            if d < b1:
+                b2, b1, bi = b1, d, i2
+            elif d < b2:
+                b2 = d
+        if b1 <= 50 and f32(b1) < f32(f32(b2) * f32(nnratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1; nm -= 1
+            m12[i1] = bi; m21[bi] = i1; md[bi] = b1; nm += 1
+            rot = f32(k1["angle"][i1] - k2["angle"][bi])
+            if rot < 0:
+                rot = f32(rot + f32(360))
+            bn = int(np.floor(f32(rot * f32(1.0 / 30)) + f32(0.5)))
+            hist.append((0 if bn == 30 else bn, i1))
+    if check_ori:
+        keep = O.three_maxima(np.bincount([h[0] for h in hist], minlength=30)) if hist else (-1, -1, -1)
+        for bn, i1 in hist:
+            if bn not in keep and m12[i1] >= 0:
+                m12[i1] = -1; nm -= 1
+    return nm, m12
+
+
+def init_pair(seed, n=900):
+    rng = np.random.default_rng(seed)
+    F1 = synth.random_frame(rng, n)
+    F2 = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in F1.items()}
+    F2["keys_un"]["x"] = F1["keys_un"]["x"] + rng.normal(0, 6, n).astype(f32)
+    F2["keys_un"]["y"] = F1["keys_un"]["y"] + rng.normal(0, 6, n).astype(f32)
+    F2["keys_un"]["angle"] = np.mod(F1["keys_un"]["angle"] + rng.normal(0, 5, n), 360).astype(f32)
+    F2["desc"] = synth.flip_bits(rng, F1["desc"], rng.integers(0, 60, n))
+    dup = rng.integers(0, n, n // 5)                 # several F1 keypoints look alike: later ones steal matches
+    F1["desc"][dup[: len(dup) // 2]] = synth.flip_bits(rng, F1["desc"][dup[len(dup) // 2: 2 * (len(dup) // 2)]], rng.integers(0, 10, len(dup) // 2))
+    F1["keys_un"]["x"][dup[: len(dup) // 2]] = F1["keys_un"]["x"][dup[len(dup) // 2: 2 * (len(dup) // 2)]] + 3
+    F1["keys_un"]["y"][dup[: len(dup) // 2]] = F1["keys_un"]["y"][dup[len(dup) // 2: 2 * (len(dup) // 2)]] + 3
+    F1["keys_un"]["octave"][dup[: len(dup) // 2]] = 0
+    F1["keys_un"]["octave"][dup[len(dup) // 2: 2 * (len(dup) // 2)]] = 0
+    F2["keys_un"]["octave"] = F1["keys_un"]["octave"].copy()
+    prev = np.stack([F1["keys_un"]["x"], F1["keys_un"]["y"]], 1).astype(f32)
+    return F1, F2, prev
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_for_initialization(seed):
+    F1, F2, prev = init_pair(80 + seed, 500)
+    for win in (30, 100):
+        n, m = O.search_for_initialization(F1, F2, prev, win, 0.9, True)
+        n2, m2 = brute_init(F1, F2, prev, win, 0.9, True)
+        assert n == n2 and np.array_equal(m, m2)
+    assert n > 20

@@ -194,3 +194,21 @@ def test_match_window(matcher, flags, max_dist, seed):
     n, bi, bd = matcher.MatchWindow(F, pts, desc, flags, inv_s2, max_dist)
     assert n == n_ref and np.array_equal(bi, bi_ref) and np.array_equal(bd, bd_ref)
     assert n_ref > 100
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_search_for_initialization(seed):
+    """monocular initialisation matcher, ORBmatcher.cc:405-520 (sequential stealing semantics)"""
+    from test_match_oracle import init_pair
+    F1, F2, prev = init_pair(600 + seed, 1500)
+    m = ORBmatcher(0.9, True, max_keypoints=2048, max_points=2048)
+    try:
+        for win in (30, 100):
+            n_ref, m_ref = O.search_for_initialization(F1, F2, prev, win, 0.9, True)
+            n, mm, newprev = m.SearchForInitialization(F1, F2, prev, win)
+            assert n == n_ref and np.array_equal(mm, m_ref)
+            sel = m_ref >= 0
+            assert np.array_equal(newprev[sel, 0], F2["keys_un"]["x"][m_ref[sel]]) and np.array_equal(newprev[~sel], prev[~sel])
+        assert n_ref > 50
+    finally:
+        m.close()
