@@ -10,12 +10,9 @@
 // Everything is double precision like g2o (tolerance vs the oracle: 1e-4 relative on poses / points, identical
 // outlier sets); none of it is shaped as a dense GEMM: the Schur product is block-sparse (about 30x fewer flops
 // than the dense 6P x 3L x 6P contraction) and needs f64, so the tensor pipes are not used.
-//   k_lba_err      one thread per edge: residual, chi2, robustified chi2 (block-reduced)
-//   k_lba_build    one thread per edge: Jacobians, weighted blocks; H_ll / b_l by global atomics (one landmark sees
-//                  ~4 edges), H_pp / b_p pre-reduced per CTA in shared memory, H_pl stored per edge
-//   k_lba_schur    one warp per landmark (edges are sorted by landmark): D^-1, b_schur, and every pose pair's 6x6
-//                  block accumulated in a CTA-private shared-memory copy of the upper block triangle of H_schur,
-//                  flushed once per CTA
+// This file is the host side (window upload, Levenberg control flow of the host-driven path, C ABI) plus
+//   k2_* (lba_chunk.cu)  residuals / Jacobians / quadratic form / Schur complement as atomic-free chunked sums
+//   k_lba_fused (lba_fused.cu)  a whole optimize() call in one thread-block cluster (windows up to 36 free keyframes)
 //   k_lba_solve    one CTA: Cholesky + two triangular solves of the reduced system in shared memory
 //   k_lba_update   landmark back-substitution, point and pose updates, Levenberg's scale term
 // The Levenberg control flow runs on the host and reads four doubles back per trial.
@@ -27,92 +24,16 @@
 
 #include "lba_common.cuh"
 
+// lba_chunk.cu
+orbx_status orbx_lba_chunk_linearize(const LbaDev &D, int robust, int build, int want_hpp, cudaStream_t s, int *launches);
+orbx_status orbx_lba_chunk_schur(const LbaDev &D, double lambda, cudaStream_t s, int *launches);
+orbx_status orbx_lba_chunk_init();
 // lba_fused.cu
 size_t orbx_lba_fused_smem(int np);
 bool orbx_lba_fused_fits(int n_kf, int np);
 orbx_status orbx_lba_fused_init();
 orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
                                   double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s);
-
-__global__ void __launch_bounds__(LBA_THREADS) k_lba_err(LbaDev D, int robust) {
-    __shared__ double tmp[32];
-    const int e = blockIdx.x * LBA_THREADS + threadIdx.x;
-    double c = 0;
-    if (e < D.n_edges && !D.level1[e]) {
-        double R[9], Xc[3], er[3];
-        const double *T = D.kf + 7 * D.ekf[e];
-        quat_to_R(T, R);
-        edge_residual(D, e, R, T + 4, Xc, er);
-        D.err[3 * e] = er[0]; D.err[3 * e + 1] = er[1]; D.err[3 * e + 2] = er[2];
-        c = D.info[e] * (er[0] * er[0] + er[1] * er[1] + er[2] * er[2]);
-        D.chi2[e] = c;
-        if (robust) {
-            const double d = D.stereo[e] ? D.d_stereo : D.d_mono, dsqr = d * d;
-            if (c > dsqr) c = 2 * sqrt(c) * d - dsqr;
-        }
-    }
-    const double s = block_sum(c, tmp);
-    if (threadIdx.x == 0 && s != 0) atomicAdd(&D.scal[0], s);
-}
-
-__global__ void __launch_bounds__(LBA_THREADS) k_lba_build(LbaDev D, int robust) {
-    __shared__ double hpp[LBA_SMEM_KF * 27];
-    const bool use_smem = D.np <= LBA_SMEM_KF;
-    if (use_smem) {
-        for (int i = threadIdx.x; i < D.np * 27; i += LBA_THREADS) hpp[i] = 0;
-        __syncthreads();
-    }
-    const int e = blockIdx.x * LBA_THREADS + threadIdx.x;
-    if (e < D.n_edges && !D.level1[e]) {
-        const int dim = D.stereo[e] ? 3 : 2;
-        double R[9], Xc[3], er[3];
-        const double *T = D.kf + 7 * D.ekf[e];
-        quat_to_R(T, R);
-        edge_residual(D, e, R, T + 4, Xc, er);
-        er[0] = D.err[3 * e]; er[1] = D.err[3 * e + 1]; er[2] = D.err[3 * e + 2];   // the stored _error
-        const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = D.fx, fy = D.fy, bf = D.bf;
-        double A[9], B[18];
-        for (int c = 0; c < 3; c++) {
-            A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
-            A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
-            A[6 + c] = dim == 3 ? A[c] - bf * R[6 + c] / z2 : 0.0;
-        }
-        B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
-        B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
-        if (dim == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
-        else { for (int i = 12; i < 18; i++) B[i] = 0; }
-        const double info = D.info[e];
-        double rho1 = 1.0;
-        if (robust) {
-            const double d = D.stereo[e] ? D.d_stereo : D.d_mono;
-            if (D.chi2[e] > d * d) rho1 = d / sqrt(D.chi2[e]);
-        }
-        const double w = rho1 * info;
-        double wr[3];   // omega_r * rho1 = -info * e * rho1
-        for (int d = 0; d < 3; d++) wr[d] = -info * er[d] * rho1;
-        double *hl = D.Hll + 9 * D.ept[e];
-        int k = 0;
-        for (int a = 0; a < 3; a++)
-            for (int b = a; b < 3; b++) atomicAdd(&hl[k++], w * (A[a] * A[b] + A[3 + a] * A[3 + b] + A[6 + a] * A[6 + b]));
-        for (int a = 0; a < 3; a++) atomicAdd(&hl[6 + a], A[a] * wr[0] + A[3 + a] * wr[1] + A[6 + a] * wr[2]);
-        const int ip = D.kfidx[D.ekf[e]];
-        if (ip >= 0) {
-            double *hp = use_smem ? hpp + 27 * ip : D.Hpp + 27 * ip;
-            k = 0;
-            for (int a = 0; a < 6; a++)
-                for (int b = a; b < 6; b++) atomicAdd(&hp[k++], w * (B[a] * B[b] + B[6 + a] * B[6 + b] + B[12 + a] * B[12 + b]));
-            for (int a = 0; a < 6; a++) atomicAdd(&hp[21 + a], B[a] * wr[0] + B[6 + a] * wr[1] + B[12 + a] * wr[2]);
-            double *hpl = D.Hpl + 18 * (size_t)e;
-            for (int a = 0; a < 6; a++)
-                for (int b = 0; b < 3; b++) hpl[3 * a + b] = w * (B[a] * A[b] + B[6 + a] * A[3 + b] + B[12 + a] * A[6 + b]);
-        }
-    }
-    if (use_smem) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < D.np * 27; i += LBA_THREADS)
-            if (hpp[i] != 0) atomicAdd(&D.Hpp[i], hpp[i]);
-    }
-}
 
 // computeLambdaInit: max |diagonal| over every active vertex (optimization_algorithm_levenberg.cpp:166-180)
 __global__ void __launch_bounds__(LBA_THREADS) k_lba_maxdiag(LbaDev D) {
@@ -128,86 +49,6 @@ __global__ void __launch_bounds__(LBA_THREADS) k_lba_maxdiag(LbaDev D) {
     if (threadIdx.x == 0) {
         for (int w = 0; w < LBA_THREADS / 32; w++) m = fmax(m, tmp[w]);
         D.scal[2] = m;
-    }
-}
-
-// H_schur = H_pp + lambda I, b_schur = b_p  (block_solver.hpp:371-373, :436)
-__global__ void __launch_bounds__(LBA_THREADS) k_lba_schur_init(LbaDev D, double lambda) {
-    const int n = D.n;
-    for (int i = blockIdx.x * LBA_THREADS + threadIdx.x; i < n * n; i += gridDim.x * LBA_THREADS) {
-        const int r = i / n, c = i - r * n, p = r / 6;
-        double v = 0;
-        if (c / 6 == p) {
-            int a = r - 6 * p, b = c - 6 * p;
-            if (a > b) { const int t = a; a = b; b = t; }
-            v = D.Hpp[27 * p + a * 6 - a * (a - 1) / 2 + (b - a)] + (a == b ? lambda : 0.0);
-        }
-        D.Hs[i] = v;
-    }
-    for (int i = blockIdx.x * LBA_THREADS + threadIdx.x; i < n; i += gridDim.x * LBA_THREADS) D.bs[i] = D.Hpp[27 * (i / 6) + 21 + i % 6];
-}
-
-template <bool SMEM>
-__global__ void __launch_bounds__(LBA_SCHUR_THREADS) k_lba_schur(LbaDev D, double lambda) {
-    extern __shared__ __align__(16) double sacc[];     // [nblocks][36] then [n]
-    const int np = D.np, n = D.n, nblk = np * (np + 1) / 2;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (SMEM) {
-        for (int i = tid; i < nblk * 36 + n; i += LBA_SCHUR_THREADS) sacc[i] = 0;
-        __syncthreads();
-    }
-    const int warps = gridDim.x * (LBA_SCHUR_THREADS / 32);
-    for (int l = blockIdx.x * (LBA_SCHUR_THREADS / 32) + (tid >> 5); l < D.n_pts; l += warps) {
-        const int s = D.ptstart[l], ne = D.ptstart[l + 1] - s;
-        if (ne == 0) continue;
-        const double *hl = D.Hll + 9 * l;
-        double Di[6];
-        dinv3(hl, lambda, Di);
-        const double db0 = Di[0] * hl[6] + Di[1] * hl[7] + Di[2] * hl[8], db1 = Di[1] * hl[6] + Di[3] * hl[7] + Di[4] * hl[8],
-                     db2 = Di[2] * hl[6] + Di[4] * hl[7] + Di[5] * hl[8];
-        for (int i = lane; i < ne; i += 32) {       // coefficients: b_schur -= B_i D^-1 b_l (block_solver.hpp:413)
-            const int e = s + i, p = D.kfidx[D.ekf[e]];
-            if (p < 0 || D.level1[e]) continue;
-            const double *B = D.Hpl + 18 * (size_t)e;
-            for (int a = 0; a < 6; a++) {
-                const double v = -(B[3 * a] * db0 + B[3 * a + 1] * db1 + B[3 * a + 2] * db2);
-                if (SMEM) atomicAdd(&sacc[nblk * 36 + 6 * p + a], v); else atomicAdd(&D.bs[6 * p + a], v);
-            }
-        }
-        for (int pr = lane; pr < ne * ne; pr += 32) {   // H_schur(i1,i2) -= B_i1 D^-1 B_i2^T for i1 <= i2 (:416-430)
-            const int i = pr / ne, j = pr - i * ne, e1 = s + i, e2 = s + j;
-            const int p1 = D.kfidx[D.ekf[e1]], p2 = D.kfidx[D.ekf[e2]];
-            if (p1 < 0 || p2 < 0 || p1 > p2 || D.level1[e1] || D.level1[e2] || (p1 == p2 && i != j)) continue;
-            const double *B1 = D.Hpl + 18 * (size_t)e1, *B2 = D.Hpl + 18 * (size_t)e2;
-            double b2[18];
-#pragma unroll
-            for (int k = 0; k < 18; k++) b2[k] = B2[k];
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-                const double u0 = B1[3 * a], u1 = B1[3 * a + 1], u2 = B1[3 * a + 2];
-                const double bd0 = u0 * Di[0] + u1 * Di[1] + u2 * Di[2], bd1 = u0 * Di[1] + u1 * Di[3] + u2 * Di[4],
-                             bd2 = u0 * Di[2] + u1 * Di[4] + u2 * Di[5];
-#pragma unroll
-                for (int b = 0; b < 6; b++) {
-                    const double v = -(bd0 * b2[3 * b] + bd1 * b2[3 * b + 1] + bd2 * b2[3 * b + 2]);
-                    if (SMEM) atomicAdd(&sacc[upper_block(p1, p2, np) * 36 + 6 * a + b], v);
-                    else atomicAdd(&D.Hs[(size_t)(6 * p1 + a) * n + 6 * p2 + b], v);
-                }
-            }
-        }
-    }
-    if (SMEM) {
-        __syncthreads();
-        for (int i = tid; i < nblk * 36; i += LBA_SCHUR_THREADS) {
-            const double v = sacc[i];
-            if (v == 0) continue;
-            const int blk = i / 36, ab = i - blk * 36;
-            int p1 = 0, rem = blk;                      // invert upper_block()
-            while (rem >= np - p1) { rem -= np - p1; p1++; }
-            const int p2 = p1 + rem;
-            atomicAdd(&D.Hs[(size_t)(6 * p1 + ab / 6) * n + 6 * p2 + ab % 6], v);
-        }
-        for (int i = tid; i < n; i += LBA_SCHUR_THREADS) if (sacc[nblk * 36 + i] != 0) atomicAdd(&D.bs[i], sacc[nblk * 36 + i]);
     }
 }
 
@@ -415,9 +256,9 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRY(cudaEventCreate(&h->ev0));
     TRY(cudaEventCreate(&h->ev1));
-    TRY(ORBX_RAISE_SMEM(k_lba_schur<true>));
     TRY(ORBX_RAISE_SMEM(k_lba_solve));
     if (ce == cudaSuccess && orbx_lba_fused_init() != ORBX_OK) ce = cudaErrorUnknown;
+    if (ce == cudaSuccess && orbx_lba_chunk_init() != ORBX_OK) ce = cudaErrorUnknown;
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_lba_create: %s", cudaGetErrorString(ce));
@@ -462,10 +303,13 @@ static T *arena_take(orbx_lba *h, size_t n, T **dev) {
     return p;
 }
 
-#define LBA_CHUNK 128
+// list chunk: the cluster kernel has 64 warps for the whole window and one CTA finishing the blocks, so it wants few, long
+// chunks; the multi-kernel path spreads chunks over the whole GPU and wants them short
+#define LBA_CHUNK_FUSED 128
+#define LBA_CHUNK_WIDE 64
 // upload a problem: estimates, edges sorted by landmark, reduced indices, and (for the cluster kernel) the work lists:
 // edges by keyframe and (edge, edge) pairs of a landmark by pose-pair block, both cut into chunks
-static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
+static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = false) {
     if (!P || P->n_kf < 0 || P->n_pts < 0 || P->n_edges < 0) return ORBX_ERR_INVALID;
     if (P->n_kf > h->max_kf || P->n_pts > h->max_pts || P->n_edges > h->max_edges) {
         orbx_set_error("problem (%d keyframes, %d points, %d edges) exceeds the handle (%d, %d, %d)", P->n_kf, P->n_pts, P->n_edges,
@@ -492,11 +336,11 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
     kfidx.assign(K, -1);
     int np = 0;
     for (int k = 0; k < K; k++) kfidx[k] = P->kf_fixed[k] ? -1 : np++;
-    const bool fused = h->use_fused && orbx_lba_fused_fits(K, np);
     const int nblk = np * (np + 1) / 2;
     auto ub = [np](int p1, int p2) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); };
     size_t npairs = 0, n_kchunks = 0, n_pchunks = 0;
-    if (fused) {
+    const int LBA_CHUNK = (!wide && h->use_fused && orbx_lba_fused_fits(K, np)) ? LBA_CHUNK_FUSED : LBA_CHUNK_WIDE;
+    if (true) {
         kcount.assign(np + 1, 0);
         bcount.assign(nblk + 1, 0);
         for (int e = 0; e < E; e++) { const int p = kfidx[P->e_kf[e]]; if (p >= 0) kcount[p + 1]++; }
@@ -537,7 +381,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
         info[s] = (double)P->e_inv_sigma2[e];
     }
     D.n_kchunks = D.n_pchunks = 0;
-    if (fused) {
+    if (true) {
         int4 *kfe = arena_take(h, E > 0 ? E : 1, &d_4); D.kfe = d_4;
         int4 *kchunk = arena_take(h, n_kchunks + 1, &d_4); D.kchunk = d_4;
         int *kfc = arena_take(h, (size_t)np + 1, &d_i); D.kf_cstart = d_i;
@@ -597,31 +441,15 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P) {
 static inline int blocks_for(int n) { return n > 0 ? (n + LBA_THREADS - 1) / LBA_THREADS : 1; }
 
 static orbx_status lba_errors(orbx_lba *h, int robust) {      // computeActiveErrors + activeRobustChi2 -> scal[0]
-    ORBX_CUDA(cudaMemsetAsync(h->D.scal, 0, sizeof(double), h->stream));
-    k_lba_err<<<blocks_for(h->D.n_edges), LBA_THREADS, 0, h->stream>>>(h->D, robust);
-    h->launches++;
-    return ORBX_OK;
+    return orbx_lba_chunk_linearize(h->D, robust, 0, 0, h->stream, &h->launches);
 }
 
-static orbx_status lba_build(orbx_lba *h, int robust) {       // BlockSolver::buildSystem
-    ORBX_CUDA(cudaMemsetAsync(h->D.Hpp, 0, sizeof(double) * 27 * (h->D.np ? h->D.np : 1), h->stream));
-    ORBX_CUDA(cudaMemsetAsync(h->D.Hll, 0, sizeof(double) * 9 * (h->D.n_pts ? h->D.n_pts : 1), h->stream));
-    k_lba_build<<<blocks_for(h->D.n_edges), LBA_THREADS, 0, h->stream>>>(h->D, robust);
-    h->launches++;
-    return ORBX_OK;
+static orbx_status lba_build(orbx_lba *h, int robust, int want_hpp) {       // computeActiveErrors + BlockSolver::buildSystem
+    return orbx_lba_chunk_linearize(h->D, robust, 1, want_hpp, h->stream, &h->launches);
 }
-
-static size_t schur_smem(const LbaDev &D) { return sizeof(double) * ((size_t)D.np * (D.np + 1) / 2 * 36 + D.n); }
 
 static orbx_status lba_schur(orbx_lba *h, double lambda) {    // BlockSolver::solve up to the linear solve
-    const LbaDev &D = h->D;
-    k_lba_schur_init<<<blocks_for(D.n * D.n > 0 ? D.n * D.n : 1), LBA_THREADS, 0, h->stream>>>(D, lambda);
-    const size_t sm = schur_smem(D);
-    if (sm <= 200 * 1024) k_lba_schur<true><<<LBA_SCHUR_CTAS, LBA_SCHUR_THREADS, sm, h->stream>>>(D, lambda);
-    else k_lba_schur<false><<<4 * LBA_SCHUR_CTAS, LBA_SCHUR_THREADS, 0, h->stream>>>(D, lambda);
-    h->launches += 2;
-    ORBX_CUDA(cudaGetLastError());
-    return ORBX_OK;
+    return orbx_lba_chunk_schur(h->D, lambda, h->stream, &h->launches);
 }
 
 static orbx_status lba_solve_update(orbx_lba *h, double lambda) {
@@ -672,8 +500,7 @@ static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lb
     double lambda = 0, ni = 2;
     int nBad = 0;
     for (int it = 0; it < iterations && !stop_requested(h); it++) {
-        if ((st = lba_errors(h, robust))) return st;
-        if ((st = lba_build(h, robust))) return st;
+        if ((st = lba_build(h, robust, it == 0))) return st;      // computeLambdaInit reads the H_pp diagonals
         if (it == 0) { k_lba_maxdiag<<<1, LBA_THREADS, 0, h->stream>>>(D); h->launches++; }
         if ((st = read_scal(h))) return st;
         double currentChi = h->h_scal[0];
@@ -844,7 +671,7 @@ extern "C" orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_pr
     if (!h || reps < 1) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->device));
     orbx_status st;
-    if (prob && (st = lba_load(h, prob))) return st;
+    if (prob && (st = lba_load(h, prob, true))) return st;
     if (!h->loaded) {
         orbx_set_error("orbx_lba_build_schur_timed: no problem loaded");
         return ORBX_ERR_INVALID;
@@ -853,8 +680,7 @@ extern "C" orbx_status orbx_lba_build_schur_timed(orbx_lba *h, const orbx_lba_pr
     LbaDev &D = h->D;
     ORBX_CUDA(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < reps; r++) {
-        if ((st = lba_errors(h, 1))) return st;
-        if ((st = lba_build(h, 1))) return st;
+        if ((st = lba_build(h, 1, 0))) return st;
         if ((st = lba_schur(h, lambda))) return st;
     }
     ORBX_CUDA(cudaEventRecord(h->ev1, h->stream));

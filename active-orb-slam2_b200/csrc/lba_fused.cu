@@ -7,7 +7,7 @@
 //   landmarks (and with them the edges, which are sorted by landmark) are split into 8 contiguous ranges, one per CTA;
 //   H_ll / b_l of a landmark are accumulated in registers by the thread that owns it;
 //   H_pp / b_p and the Schur complement are sums over lists the host builds once per window (edges by keyframe; pairs of
-//   edges of one landmark by pose-pair block), cut into chunks of 128: a warp reduces a chunk in registers and writes one
+//   edges of one landmark by pose-pair block), cut into chunks of 64: a warp reduces a chunk in registers and writes one
 //   partial block, CTA 0 adds the partials of a block in chunk order.  No atomics anywhere, so the sums are
 //   deterministic and every CTA takes the same Levenberg decision from the same numbers without a broadcast;
 //   the reduced camera system lives in CTA 0's shared memory in upper block-triangular layout and is factorised there

@@ -19,6 +19,10 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+static double g_t_schur = 0, g_t_chol = 0;   /* split of schur_solve: Schur complement build / dense solve + back-substitution */
 
 typedef struct { double q[4]; double t[3]; } se3;   /* q = (x,y,z,w) like Eigen::Quaterniond::coeffs() */
 
@@ -248,6 +252,7 @@ static void inv3(const double *M, double *I) {
 static int schur_solve(lba *S, double lambda, double *xp, double *xl, double *Hs, double *bs) {
     const orbo_lba_problem *P = S->P;
     const int np = S->np, nl = S->nl, n = 6 * np;
+    const double t_begin = now_s();
     memset(Hs, 0, sizeof(double) * n * n);
     for (int p = 0; p < np; p++)
         for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++)
@@ -287,6 +292,7 @@ static int schur_solve(lba *S, double lambda, double *xp, double *xl, double *Hs
             }
         }
     }
+    const double t_mid = now_s();
     double *Hc = (double *)malloc(sizeof(double) * (n ? n * n : 1));
     memcpy(Hc, Hs, sizeof(double) * n * n);
     const int ok = n == 0 ? 1 : chol_solve(Hc, bs, xp, n);
@@ -307,6 +313,7 @@ static int schur_solve(lba *S, double lambda, double *xp, double *xl, double *Hs
         }
     }
     free(Hc); free(Dinv); free(head); free(list); free(cur);
+    g_t_schur += t_mid - t_begin; g_t_chol += now_s() - t_mid;
     return ok;
 }
 
@@ -330,10 +337,12 @@ static int optimize(lba *S, int iterations, orbo_lba_trace *tr) {
     double lambda = 0, ni = 2;
     int nBad = 0, done = 0;
     for (int it = 0; it < iterations && !stop_requested(P); it++) {
+        double tb = now_s();
         double currentChi = compute_errors(S);
         const double iniChi = currentChi;
         double tempChi = currentChi;
         build_system(S);
+        if (tr) { tr->t_build += now_s() - tb; tr->n_builds++; }
         if (it == 0) {   /* computeLambdaInit: tau * max diagonal over every active vertex */
             double mx = 0;
             for (int p = 0; p < np; p++) for (int a = 0; a < 6; a++) mx = fmax(mx, fabs(S->Hpp[36 * p + 7 * a]));
@@ -344,7 +353,9 @@ static int optimize(lba *S, int iterations, orbo_lba_trace *tr) {
         int qmax = 0;
         do {
             memcpy(kf_bak, S->kf, sizeof(se3) * P->n_kf); memcpy(pt_bak, S->pt, sizeof(double) * 3 * P->n_pts);   /* push */
+            g_t_schur = g_t_chol = 0;
             const int ok2 = schur_solve(S, lambda, xp, xl, Hs, bs);
+            if (tr) { tr->t_schur += g_t_schur; tr->t_solve += g_t_chol; }
             if (tr && tr->n_trials == 0 && tr->Hschur) {   /* first trial of the call: keep the reduced system */
                 memcpy(tr->Hschur, Hs, sizeof(double) * n * n); memcpy(tr->bschur, bs, sizeof(double) * n);
                 tr->dim = n; tr->lambda0 = lambda;
@@ -400,7 +411,7 @@ int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out
     S.Hll = (double *)malloc(sizeof(double) * 9 * (P->n_pts ? P->n_pts : 1)); S.bl = (double *)malloc(sizeof(double) * 3 * (P->n_pts ? P->n_pts : 1));
     S.Hpl = (double *)calloc(18 * (size_t)(P->n_edges ? P->n_edges : 1), sizeof(double));
     S.err = (double *)calloc(3 * (size_t)(P->n_edges ? P->n_edges : 1), sizeof(double)); S.chi2 = (double *)calloc(P->n_edges ? P->n_edges : 1, sizeof(double));
-    if (tr) tr->n_trials = 0;
+    if (tr) { tr->n_trials = 0; tr->t_build = tr->t_schur = tr->t_solve = 0; tr->n_builds = 0; }
     int rc = 0;
     if (!stop_requested(P)) {
         S.robust = 1;

@@ -304,7 +304,8 @@ class OLbaProblem(C.Structure):
 
 class OLbaTrace(C.Structure):
     _fields_ = [("n_trials", C.c_int32), ("chi2", C.c_double * 256), ("lambda_", C.c_double * 256), ("dim", C.c_int32),
-                ("lambda0", C.c_double), ("Hschur", C.c_void_p), ("bschur", C.c_void_p), ("xp", C.c_void_p)]
+                ("lambda0", C.c_double), ("Hschur", C.c_void_p), ("bschur", C.c_void_p), ("xp", C.c_void_p),
+                ("t_build", C.c_double), ("t_schur", C.c_double), ("t_solve", C.c_double), ("n_builds", C.c_int32)]
 
 
 def lba_pack(prob, cls=OLbaProblem):
@@ -339,7 +340,7 @@ def lba_solve(prob, its1=5, its2=10, want_system=False):
     rc = L.orbo_lba_solve(C.byref(P), its1, its2, _p(kf), _p(pt), _p(chi2), _p(erase), C.byref(tr))
     n = min(tr.n_trials, 256)
     out = dict(kf=kf, pts=pt, chi2=chi2, erase=erase, trials=tr.n_trials, chi2_trace=np.array(tr.chi2[:n]), lambda_trace=np.array(tr.lambda_[:n]),
-               stopped=rc)
+               stopped=rc, t_build=tr.t_build, t_schur=tr.t_schur, t_solve=tr.t_solve, n_builds=tr.n_builds)
     if want_system:
         d = tr.dim
         out.update(Hschur=Hs.reshape(-1)[:d * d].reshape(d, d).copy(), bschur=bs[:d].copy(), xp=xp[:d].copy(), lambda0=tr.lambda0)

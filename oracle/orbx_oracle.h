@@ -149,6 +149,8 @@ typedef struct {
     int32_t dim;                 /* 6 x free poses */
     double lambda0;
     double *Hschur, *bschur, *xp;   /* optional: reduced system and pose update of the very first trial (dim x dim, dim, dim) */
+    double t_build, t_schur, t_solve; /* seconds: errors + quadratic form (per iteration); Schur complement; dense solve + back-substitution (per trial) */
+    int32_t n_builds;
 } orbo_lba_trace;
 /* kf_out n_kf x 7, pt_out n_pts x 3, chi2_out / erase_out per edge (Optimizer.cc:709-735); returns 1 if stopped before starting */
 int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out, double *pt_out, double *chi2_out,
