@@ -96,6 +96,17 @@ class PlaneWorld:
         return out
 
 
+_WORLDS = {}
+
+
+def stereo_world(seed, w=640, h=480, **kw):
+    """cached PlaneWorld (building the three textures takes half a second)"""
+    key = (seed, w, h, tuple(sorted(kw.items())))
+    if key not in _WORLDS:
+        _WORLDS[key] = PlaneWorld(seed, w, h, **kw)
+    return _WORLDS[key]
+
+
 # ---- matcher scenes (SURVEY §8d C2): a current frame, and points that project near its keypoints ----------------
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])

@@ -438,3 +438,39 @@ def search_for_initialization(F1, F2, prev_xy, window_size=100, nnratio=0.9, che
     m = np.zeros(max(f1.n, 1), np.int32)
     n = L.orbo_search_for_initialization(C.byref(f1), C.byref(f2), _p(pv), window_size, nnratio, int(check_ori), _p(m))
     return n, m[:f1.n]
+
+
+# ---- stereo association (oracle/stereo_oracle.c) ---------------------------------------------------------------
+class OStereoJob(C.Structure):
+    _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("keys_l", C.c_void_p), ("keys_r", C.c_void_p),
+                ("desc_l", C.c_void_p), ("desc_r", C.c_void_p), ("nlevels", C.c_int32), ("scale", C.c_void_p), ("inv_scale", C.c_void_p),
+                ("lvl_l", C.c_void_p), ("lvl_r", C.c_void_p), ("lvl_w", C.c_void_p), ("lvl_h", C.c_void_p),
+                ("pitch_l", C.c_void_p), ("pitch_r", C.c_void_p), ("bf", C.c_float), ("b", C.c_float)]
+
+
+def stereo_matches(keys_l, desc_l, keys_r, desc_r, pyr_l, pyr_r, scale, inv_scale, bf, b):
+    """Frame::ComputeStereoMatches.  pyr_l / pyr_r: lists of 2-D uint8 arrays (interior of every pyramid level).
+    Returns dict(u_right, depth, best_right, sad, kept)."""
+    L = lib()
+    L.orbo_stereo_matches.argtypes = [C.POINTER(OStereoJob)] + [C.c_void_p] * 4
+    kl, kr = np.ascontiguousarray(keys_l, KP_DTYPE), np.ascontiguousarray(keys_r, KP_DTYPE)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    pl = [np.ascontiguousarray(a, np.uint8) for a in pyr_l]
+    pr = [np.ascontiguousarray(a, np.uint8) for a in pyr_r]
+    n = len(pl)
+    sc, isc = np.ascontiguousarray(scale, np.float32), np.ascontiguousarray(inv_scale, np.float32)
+    ptr_l = np.array([a.ctypes.data for a in pl], np.uint64)
+    ptr_r = np.array([a.ctypes.data for a in pr], np.uint64)
+    lw = np.array([a.shape[1] for a in pl], np.int32)
+    lh = np.array([a.shape[0] for a in pl], np.int32)
+    sl = np.array([a.strides[0] for a in pl], np.int32)
+    sr = np.array([a.strides[0] for a in pr], np.int32)
+    J = OStereoJob(len(kl), len(kr), kl.ctypes.data, kr.ctypes.data, dl.ctypes.data, dr.ctypes.data, n, sc.ctypes.data,
+                   isc.ctypes.data, ptr_l.ctypes.data, ptr_r.ctypes.data, lw.ctypes.data, lh.ctypes.data, sl.ctypes.data,
+                   sr.ctypes.data, np.float32(bf), np.float32(b))
+    m = max(len(kl), 1)
+    ur, dp = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    br, sad = np.zeros(m, np.int32), np.zeros(m, np.int32)
+    kept = L.orbo_stereo_matches(C.byref(J), _p(ur), _p(dp), _p(br), _p(sad))
+    k = len(kl)
+    return dict(u_right=ur[:k], depth=dp[:k], best_right=br[:k], sad=sad[:k], kept=kept)

@@ -127,6 +127,22 @@ typedef struct {
 } orbo_bucket_job;
 int orbo_match_buckets(const orbo_bucket_job *J, int32_t *match_a);
 
+/* ---- stereo association (src/Frame.cc:495-669, Frame::ComputeStereoMatches) ---- */
+typedef struct {
+    int32_t n_left, n_right;             /* N, mvKeysRight.size() */
+    const orbo_keypoint *keys_l, *keys_r; /* mvKeys, mvKeysRight (raw keypoints; stereo input is pre-rectified) */
+    const uint8_t *desc_l, *desc_r;      /* mDescriptors, mDescriptorsRight */
+    int32_t nlevels;
+    const float *scale, *inv_scale;      /* mvScaleFactors, mvInvScaleFactors */
+    const uint8_t *const *lvl_l;         /* mpORBextractorLeft->mvImagePyramid[l]: first interior pixel of level l */
+    const uint8_t *const *lvl_r;         /* mpORBextractorRight->mvImagePyramid[l] */
+    const int32_t *lvl_w, *lvl_h, *pitch_l, *pitch_r;
+    float bf, b;                         /* mbf, mb */
+} orbo_stereo_job;
+/* fills mvuRight / mvDepth (n_left each); optional best_right[i] = right keypoint the Hamming search chose (-1 none) and
+ * sad[i] = the SAD pushed into vDistIdx (-1 if none).  Returns the number of associations kept after the median cut. */
+int orbo_stereo_matches(const orbo_stereo_job *J, float *u_right, float *depth, int32_t *best_right, int32_t *sad);
+
 /* ---- local bundle adjustment (src/Optimizer.cc:454-779 + g2o) ---- */
 typedef struct {
     int32_t n_kf;                /* keyframe vertices: local (free) and fixed */
