@@ -81,5 +81,11 @@ def _declare(L):
     L.orbx_lba_build_schur_timed.argtypes = [vp, vp, C.c_double, i, vp, vp, vp]
     L.orbx_lba_last_launches.argtypes = [vp]
     L.orbx_lba_phase_ns.argtypes = [vp, vp]
+    L.orbx_stereo_create.argtypes = [C.POINTER(vp), i, i, i]
+    L.orbx_stereo_destroy.restype = None
+    L.orbx_stereo_destroy.argtypes = [vp]
+    L.orbx_stereo_matches_device.argtypes = [vp, vp, vp, i, f, f, vp, vp, i, vp, vp]
+    L.orbx_stereo_matches_host.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, f, f, vp, vp, vp]
+    L.orbx_stereo_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -271,6 +271,45 @@ int orbx_matcher_last_launches(const orbx_matcher *m);
 orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs);
 
 /* =====================================================================================================
+ * Frame::ComputeStereoMatches  (reference include/Frame.h:96, src/Frame.cc:495-669).
+ * Consumes both keypoint / descriptor sets and both extractors' pyramids (mvImagePyramid) where they already
+ * are in device memory: row-band Hamming search, 11x11 SAD refinement over +-5 px on the keypoint's pyramid
+ * level, parabola fit, disparity gates, median-distance cut.  Fills mvuRight / mvDepth (-1 = no association).
+ * ===================================================================================================== */
+typedef struct orbx_stereo orbx_stereo;
+orbx_status orbx_stereo_create(orbx_stereo **out, int max_keypoints, int max_pairs, int device);
+void orbx_stereo_destroy(orbx_stereo *h);
+
+/* one camera of a batch of rectified pairs, as the extractor left it on the device: pair p has its keypoints at
+ * keys + p*pitch, descriptors at desc + p*pitch*32, keypoint count at counts[p*count_step], and its pyramid in slot
+ * first_slot + p*slot_step of `extractor`'s last run.  (One extractor run over frames L0 R0 L1 R1 ...: left =
+ * {kps, desc, counts, 2*capacity, 2, e, 0, 2}, right = {kps + capacity, desc + 32*capacity, counts + 1, 2*capacity, 2,
+ * e, 1, 2}; two extractors as in the reference: pitch = capacity, count_step = 1, first_slot 0, slot_step 1.) */
+typedef struct {
+    const orbx_keypoint *keys;       /* mvKeys / mvKeysRight (raw keypoints; stereo input is rectified) */
+    const uint8_t *desc;             /* mDescriptors / mDescriptorsRight */
+    const int32_t *counts;           /* device */
+    int32_t pitch, count_step;
+    const orbx_extractor *extractor; /* mpORBextractorLeft / mpORBextractorRight */
+    int32_t first_slot, slot_step;
+    int32_t max_count;               /* upper bound of the counts, sizes the launch (0 = pitch) */
+} orbx_stereo_side;
+
+/* replaces void Frame::ComputeStereoMatches() for n_pairs independent pairs; bf = mbf, b = mb.  Outputs (device):
+ * d_u_right / d_depth, pair p at + p*out_pitch (out_pitch >= left->pitch); d_kept[p] = associations that survive the
+ * median cut (may be NULL).  Only enqueues on `stream` (which must be ordered after the extractor runs). */
+orbx_status orbx_stereo_matches_device(orbx_stereo *h, const orbx_stereo_side *left, const orbx_stereo_side *right,
+                                       int n_pairs, float bf, float b, float *d_u_right, float *d_depth, int out_pitch,
+                                       int32_t *d_kept, void *stream);
+/* one pair, host keypoints / descriptors in, host mvuRight / mvDepth out (n_left each); the pyramids are those of slot
+ * left_slot / right_slot of the two extractors' last runs.  Synchronous. */
+orbx_status orbx_stereo_matches_host(orbx_stereo *h, const orbx_extractor *left, int left_slot, const orbx_extractor *right,
+                                     int right_slot, const orbx_keypoint *keys_l, const uint8_t *desc_l, int n_left,
+                                     const orbx_keypoint *keys_r, const uint8_t *desc_r, int n_right, float bf, float b,
+                                     float *u_right, float *depth, int32_t *n_kept);
+int orbx_stereo_last_launches(const orbx_stereo *h);
+
+/* =====================================================================================================
  * Optimizer::LocalBundleAdjustment  (reference include/Optimizer.h:45, src/Optimizer.cc:454-779, and the g2o
  * pieces it drives: types_six_dof_expmap.{h,cpp}, base_binary_edge.hpp:55-120, robust_kernel_impl.cpp:78-91,
  * block_solver.hpp:354-486, optimization_algorithm_levenberg.cpp:61-189).
