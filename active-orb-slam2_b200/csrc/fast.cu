@@ -21,18 +21,6 @@ __host__ __device__ inline int orbx_fast_out_words(int tp_max, int th_max) {
 // The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
 // (0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
 
-// compass test: a 9-arc contains two adjacent compass pixels (ring 0,4,8,12) of the same polarity, so a pixel that
-// fails this cannot be a corner at threshold th
-__device__ __forceinline__ bool fast_compass(const uint8_t *p, int tp, int th) {
-    const int v = p[0];
-    const int c0 = p[3 * tp], c4 = p[3], c8 = p[-3 * tp], c12 = p[-3];
-    const int hi = v + th, lo = v - th;
-    const unsigned br = (c0 > hi) | ((c4 > hi) << 1) | ((c8 > hi) << 2) | ((c12 > hi) << 3);
-    const unsigned dk = (c0 < lo) | ((c4 < lo) << 1) | ((c8 < lo) << 2) | ((c12 < lo) << 3);
-    // adjacent pairs (0,4) (4,8) (8,12) (12,0): x & rotl4(x)
-    return (((br & ((br << 1) | (br >> 3))) | (dk & ((dk << 1) | (dk >> 3)))) & 0xf) != 0;
-}
-
 // score of the pixel at p (row pitch tp) or 0 if it is not a corner at `th`
 __device__ __forceinline__ int fast_score(const uint8_t *p, int tp, int th) {
     const int v = p[0];
@@ -85,8 +73,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // is (19 + x0) rounded down to 16 (TMA wants 16-byte aligned row starts) and first row 19 + y0, completion on an mbarrier;
 // rows / columns past the level read as zero and are never looked at.
 // Three phases per pass, so that only the few pixels that can be corners pay for the 16-arc score and the 3x3
-// suppression: (1) compass test on every pixel, survivors compacted into a list; (2) score of the listed pixels;
-// (3) suppression of the listed pixels with a non-zero score.
+// suppression: (1) packed pre-test on every pixel (four per thread), survivors compacted into a list; (2) score of the
+// listed pixels; (3) suppression of the listed pixels with a non-zero score.
 __global__ void __launch_bounds__(FAST_THREADS)
 k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv,
        const OrbxFastChunk *__restrict__ chunks, uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand,
@@ -99,7 +87,6 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     const OrbxLevel &L = lv[ck.level];
     const int tw = ck.tw, th = ck.th;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
 
     // ---- stage the tile by TMA ---------------------------------------------------------------------------
     const int tp = tp_max;                             // smem row pitch = box width (multiple of 16)
@@ -137,22 +124,75 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
     uint8_t *s0 = score + shift + 3 * tp + 3;
 
+    // words of a tile row that hold detection pixels, and the magic number that divides an item index by their count
+    const int w_first = (shift + 3) >> 2, n_words = ((shift + 3 + vw - 1) >> 2) - w_first + 1;
+    const int n_items = vw > 0 && vh > 0 ? n_words * vh : 0;
+    const uint32_t w_magic = (uint32_t)((0x100000000ull + n_words - 1) / n_words);
+
     for (int pass = 0; pass < 2; pass++) {
         const int thr = pass == 0 ? ini_th : min_th;
-        // (1) compass test, survivors -> list (x | y << 8)
-        for (int y = warp; y < vh; y += FAST_THREADS / 32) {
-            const uint8_t *row = t0 + y * tp;
-            for (int xb = 0; xb < vw; xb += 32) {
-                const int x = xb + lane;
-                bool ok = x < vw;
-                if (ok && pass == 1) ok = sh.empty[sh.cellof[x]] != 0;   // only the cells that found nothing at iniThFAST
-                if (ok) ok = fast_compass(row + x, tp, thr);
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (m == 0) continue;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh.n_list, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (ok) list[base + __popc(m & lt)] = (uint16_t)(x | (y << 8));
+        // (1) compass pre-test on four pixels per thread (one aligned word of the tile row), survivors -> list (x | y << 8).
+        //     |ring - centre| > thr, polarity ignored, as packed bytes: d = VABSDIFF4, then bit 7 of ((d & 0x7f) + 127 - thr) | d.
+        //     A 9-arc holds two neighbouring pixels of {0,4,8,12} and two of {2,6,10,14}; opposite pixels OR-ed, the two
+        //     axes AND-ed.  It only has to be necessary: fast_score() decides.
+        const uint32_t kadd = thr <= 126 ? (uint32_t)(127 - thr) * 0x01010101u : 0u;
+        for (int it = warp * 32; it < n_items; it += FAST_THREADS) {
+            const int t = it + lane;
+            uint32_t m = 0;
+            int y = 0, x0 = 0;
+            if (t < n_items) {
+                y = n_words == 1 ? t : (int)__umulhi((uint32_t)t, w_magic);
+                const int wi = w_first + (t - y * n_words);
+                x0 = 4 * wi - (shift + 3);                      // detection column of byte 0 of the word
+                bool go = true;
+                if (pass == 1) go = (sh.empty[sh.cellof[max(x0, 0)]] | sh.empty[sh.cellof[min(x0 + 3, vw - 1)]]) != 0;
+                if (go) {
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(tile + (y + 3) * tp) + wi;
+                    const int tpw = tp >> 2;
+                    const uint32_t v = rw[0], wl = rw[-1], wr = rw[1];
+                    const uint32_t d0 = __vabsdiffu4(rw[3 * tpw], v), d8 = __vabsdiffu4(rw[-3 * tpw], v);
+                    const uint32_t d4 = __vabsdiffu4(__byte_perm(v, wr, 0x6543), v), d12 = __vabsdiffu4(__byte_perm(wl, v, 0x4321), v);
+                    const uint32_t a = ((d0 & 0x7f7f7f7fu) + kadd) | d0 | ((d8 & 0x7f7f7f7fu) + kadd) | d8;
+                    const uint32_t c = ((d4 & 0x7f7f7f7fu) + kadd) | d4 | ((d12 & 0x7f7f7f7fu) + kadd) | d12;
+                    m = a & c & 0x80808080u;
+                    if (m) {
+                        const uint32_t *up = rw + 2 * tpw, *dn = rw - 2 * tpw;
+                        const uint32_t e2 = __vabsdiffu4(__byte_perm(up[0], up[1], 0x5432), v);     // ring 2  (+2, +2)
+                        const uint32_t e14 = __vabsdiffu4(__byte_perm(up[-1], up[0], 0x5432), v);   // ring 14 (-2, +2)
+                        const uint32_t e6 = __vabsdiffu4(__byte_perm(dn[0], dn[1], 0x5432), v);     // ring 6  (+2, -2)
+                        const uint32_t e10 = __vabsdiffu4(__byte_perm(dn[-1], dn[0], 0x5432), v);   // ring 10 (-2, -2)
+                        const uint32_t f = ((e2 & 0x7f7f7f7fu) + kadd) | e2 | ((e10 & 0x7f7f7f7fu) + kadd) | e10;
+                        const uint32_t g = ((e6 & 0x7f7f7f7fu) + kadd) | e6 | ((e14 & 0x7f7f7f7fu) + kadd) | e14;
+                        m &= f & g;
+                    }
+                }
+            }
+            // keep the bytes that are detection pixels (and, in the second pass, lie in a cell that found nothing)
+            if (m) {
+                const int lo = max(-x0, 0), hi = min(vw - x0, 4);           // valid bytes of the word: [lo, hi)
+                m &= (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (4 - hi)));
+                if (pass == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (((m >> (8 * k + 7)) & 1u) && !sh.empty[sh.cellof[x0 + k]]) m &= ~(0x80u << (8 * k));
+                }
+            }
+            if (__ballot_sync(0xffffffffu, m != 0) == 0) continue;
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&sh.n_list, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+            const int yy = y << 8;
+            while (m) {
+                const int k = (__ffs(m) - 1) >> 3;
+                list[base++] = (uint16_t)((x0 + k) | yy);
+                m &= m - 1;
             }
         }
         __syncthreads();
