@@ -77,8 +77,9 @@ __device__ __forceinline__ double edge_residual(const LbaDev &D, int e, const do
         er[0] = o[0] - (Xc[0] / Xc[2] * D.fx + D.cx);
         er[1] = o[1] - (Xc[1] / Xc[2] * D.fy + D.cy);
         er[2] = 0;
-    } else {   // cam_project keeps 1/z and bf in float (types_six_dof_expmap.cpp:150-157)
-        const float invz = __fdiv_rn(1.0f, (float)Xc[2]);
+    } else {   // cam_project keeps 1/z and bf in float (types_six_dof_expmap.cpp:150-157); `1.0f/trans_xyz[2]` divides in
+               // double (the divisor is a double) and narrows once
+        const float invz = __double2float_rn(1.0 / Xc[2]);
         const double u = Xc[0] * (double)invz * D.fx + D.cx;
         er[0] = o[0] - u;
         er[1] = o[1] - (Xc[1] * (double)invz * D.fy + D.cy);

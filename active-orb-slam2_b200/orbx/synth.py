@@ -353,3 +353,38 @@ def window_points(rng, cur, n_pts, th=3.0, dup_frac=0.2):
     pts["valid"] = rng.random(n_pts) > 0.1
     desc = flip_bits(rng, cur["desc"][tgt], rng.integers(0, 80, n_pts))
     return pts, desc
+
+
+def pose_problem(seed, n=400, stereo_frac=0.6, outlier_frac=0.15, w=640, h=480, rot_deg=1.0, trans=0.03):
+    """One frame's PoseOptimization input: n map points 1-9 m ahead seen by a camera whose initial pose is
+    off by ~rot_deg / trans metres; pixel noise N(0, sigma_octave^2); outlier_frac of the observations are off by 15-40 px.
+    Map points and the pose enter as float (cv::Mat CV_32F), observations as float keypoints, like the reference."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf, _ = TUM1_K
+    R = _rot(1, rng.uniform(-0.3, 0.3)) @ _rot(0, rng.uniform(-0.1, 0.1))
+    t = rng.uniform(-0.5, 0.5, 3)
+    sf = scale_factors(8)
+    Xw, obs, is2 = [], [], []
+    while len(Xw) < n:
+        Xc = np.array([rng.uniform(-4, 4), rng.uniform(-3, 3), rng.uniform(1, 9)])
+        u, v = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
+        if not (0 <= u < w and 0 <= v < h):
+            continue
+        octv = int(rng.integers(0, 8))
+        sig = float(sf[octv])
+        du, dv, dr = rng.normal(0, sig, 3)
+        if rng.random() < outlier_frac:
+            a = rng.uniform(0, 2 * np.pi)
+            m = rng.uniform(15, 40)
+            du += m * np.cos(a); dv += m * np.sin(a)
+        ur = u + dr - bf / Xc[2] if rng.random() < stereo_frac else -1.0
+        Xw.append((R.T @ (Xc - t)).astype(np.float32))
+        obs.append((np.float32(u + du), np.float32(v + dv), np.float32(ur)))
+        is2.append(np.float32(1.0) / (sf[octv] * sf[octv]))
+    Rn = _rot(int(rng.integers(0, 3)), np.deg2rad(rng.normal(0, rot_deg))) @ R
+    tn = t + rng.normal(0, trans, 3)
+    pose = np.zeros(7)
+    pose[:4] = _quat_from_R(Rn.astype(np.float32).astype(np.float64))
+    pose[4:] = tn.astype(np.float32)
+    return dict(Xw=np.asarray(Xw, np.float64), obs=np.asarray(obs, np.float64), inv_sigma2=np.asarray(is2, np.float32), pose=pose,
+                K=(np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), np.float32(bf)))

@@ -54,7 +54,9 @@ static double edge_error(const lba *S, int e, double err[3], double *chi2) {
         const double u = Xc[0] / Xc[2] * P->fx + P->cx, v = Xc[1] / Xc[2] * P->fy + P->cy;
         err[0] = P->e_obs[3 * e] - u; err[1] = P->e_obs[3 * e + 1] - v; err[2] = 0;
     } else {
-        const float invz = 1.0f / (float)Xc[2];          /* cam_project keeps invz (and bf) in float, types_six_dof_expmap.cpp:150-157 */
+        /* cam_project keeps invz (and bf) in float, types_six_dof_expmap.cpp:150-157; `1.0f/trans_xyz[2]` has a double
+         * divisor, so the division is done in double and narrowed once */
+        const float invz = (float)(1.0 / Xc[2]);
         const double u = Xc[0] * invz * P->fx + P->cx, v = Xc[1] * invz * P->fy + P->cy;
         const double ur = u - (double)((float)P->bf * invz);
         err[0] = P->e_obs[3 * e] - u; err[1] = P->e_obs[3 * e + 1] - v; err[2] = P->e_obs[3 * e + 2] - ur;

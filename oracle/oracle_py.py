@@ -474,3 +474,34 @@ def stereo_matches(keys_l, desc_l, keys_r, desc_r, pyr_l, pyr_r, scale, inv_scal
     kept = L.orbo_stereo_matches(C.byref(J), _p(ur), _p(dp), _p(br), _p(sad))
     k = len(kl)
     return dict(u_right=ur[:k], depth=dp[:k], best_right=br[:k], sad=sad[:k], kept=kept)
+
+
+# ---- pose-only optimisation (oracle/pose_oracle.c) -------------------------------------------------------------
+class OPoseProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("Xw", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("pose", C.c_double * 7),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double)]
+
+
+def pose_pack(prob, cls=OPoseProblem):
+    """prob: dict(Xw[n,3], obs[n,3], inv_sigma2[n], pose[7], K=(fx,fy,cx,cy,bf)) -> (struct, keepalive)"""
+    Xw = np.ascontiguousarray(prob["Xw"], np.float64)
+    obs = np.ascontiguousarray(prob["obs"], np.float64)
+    s2 = np.ascontiguousarray(prob["inv_sigma2"], np.float32)
+    P = cls()
+    P.n, P.Xw, P.obs, P.inv_sigma2 = len(Xw), Xw.ctypes.data, obs.ctypes.data, s2.ctypes.data
+    for i, v in enumerate(np.asarray(prob["pose"], np.float64)):
+        P.pose[i] = v
+    P.fx, P.fy, P.cx, P.cy, P.bf = (float(v) for v in prob["K"][:5])
+    return P, [Xw, obs, s2]
+
+
+def pose_optimize(prob):
+    """Optimizer::PoseOptimization -> dict(pose[7], outlier[n], n_inliers, n_bad, trials)"""
+    L = lib()
+    L.orbo_pose_optimize.argtypes = [C.POINTER(OPoseProblem), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    P, keep = pose_pack(prob)
+    pose = np.zeros(7, np.float64)
+    out = np.zeros(max(P.n, 1), np.uint8)
+    nb, tr = C.c_int32(), C.c_int32()
+    r = L.orbo_pose_optimize(C.byref(P), _p(pose), _p(out), C.byref(nb), C.byref(tr))
+    return dict(pose=pose, outlier=out[:P.n].copy(), n_inliers=r, n_bad=nb.value, trials=tr.value)

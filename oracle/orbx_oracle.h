@@ -172,6 +172,18 @@ typedef struct {
 int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out, double *pt_out, double *chi2_out,
                    uint8_t *erase_out, orbo_lba_trace *tr);
 
+/* ---- pose-only optimisation (src/Optimizer.cc:239-452 + g2o unary edges) ---- */
+typedef struct {
+    int32_t n;                   /* keypoints with a map point (nInitialCorrespondences) */
+    const double *Xw;            /* n x 3: pMP->GetWorldPos() (float values widened, :305-308) */
+    const double *obs;           /* n x 3: kpUn.pt.x, kpUn.pt.y, mvuRight (negative = monocular edge) */
+    const float *inv_sigma2;     /* mvInvLevelSigma2[kpUn.octave] */
+    double pose[7];              /* Converter::toSE3Quat(pFrame->mTcw): quaternion (x,y,z,w), translation */
+    double fx, fy, cx, cy, bf;
+} orbo_pose_problem;
+/* returns nInitialCorrespondences - nBad; outlier[n] = mvbOutlier of the observations; pose_out = the recovered SE3Quat */
+int orbo_pose_optimize(const orbo_pose_problem *P, double pose_out[7], uint8_t *outlier, int32_t *n_bad, int32_t *lm_trials);
+
 #ifdef __cplusplus
 }
 #endif

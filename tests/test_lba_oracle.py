@@ -34,7 +34,7 @@ def project(R, t, X, K, stereo, smooth=False):
     if smooth:
         u = Xc[0] / Xc[2] * fx + cx
         return np.array([u, Xc[1] / Xc[2] * fy + cy, u - bf / Xc[2]]), Xc[2]
-    iz = np.float32(1.0) / np.float32(Xc[2])
+    iz = np.float32(1.0 / Xc[2])      # `1.0f/trans_xyz[2]`: double division narrowed once
     u = Xc[0] * iz * fx + cx
     return np.array([u, Xc[1] * iz * fy + cy, u - float(np.float32(bf) * iz)]), Xc[2]
 
