@@ -87,5 +87,10 @@ def _declare(L):
     L.orbx_stereo_matches_device.argtypes = [vp, vp, vp, i, f, f, vp, vp, i, vp, vp]
     L.orbx_stereo_matches_host.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, f, f, vp, vp, vp]
     L.orbx_stereo_last_launches.argtypes = [vp]
+    L.orbx_pose_create.argtypes = [C.POINTER(vp), i, i, i]
+    L.orbx_pose_destroy.restype = None
+    L.orbx_pose_destroy.argtypes = [vp]
+    L.orbx_pose_optimize_host.argtypes = [vp, vp, i, vp]
+    L.orbx_pose_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -110,3 +110,60 @@ class Optimizer:
         ns = np.zeros(6)
         check(self._L.orbx_lba_phase_ns(self._h, ns.ctypes.data))
         return dict(zip(("build", "schur", "reduce", "solve", "update", "err"), (ns / 1e3).tolist()))
+
+
+# ---- Optimizer::PoseOptimization (reference include/Optimizer.h:49, src/Optimizer.cc:239-452) ----------------------
+class PoseProblem(C.Structure):
+    """orbx_pose_problem (include/orbx.h)"""
+    _fields_ = [("n", C.c_int32), ("Xw", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("pose", C.c_double * 7),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double)]
+
+
+class PoseResult(C.Structure):
+    """orbx_pose_result (include/orbx.h)"""
+    _fields_ = [("pose", C.c_double * 7), ("outlier", C.c_void_p), ("n_inliers", C.c_int32), ("n_bad", C.c_int32),
+                ("lm_trials", C.c_int32)]
+
+
+class PoseOptimizer:
+    """holds the device buffers; PoseOptimization() is the reference's static method, batched over frames"""
+
+    def __init__(self, max_observations=65536, max_frames=64, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        check(self._L.orbx_pose_create(C.byref(self._h), max_observations, max_frames, device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.orbx_pose_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def PoseOptimization(self, probs):
+        """probs: one dict or a list of dicts(Xw[n,3], obs[n,3] (third < 0 = monocular), inv_sigma2[n], pose[7], K=(fx,fy,cx,cy,bf))
+        -> dict(pose, outlier, n_inliers, n_bad, trials) per problem"""
+        single = isinstance(probs, dict)
+        plist = [probs] if single else list(probs)
+        nf = len(plist)
+        P, R = (PoseProblem * max(nf, 1))(), (PoseResult * max(nf, 1))()
+        keep, outs = [], []
+        for f, p in enumerate(plist):
+            Xw = np.ascontiguousarray(p["Xw"], np.float64).reshape(-1, 3)
+            obs = np.ascontiguousarray(p["obs"], np.float64).reshape(-1, 3)
+            s2 = np.ascontiguousarray(p["inv_sigma2"], np.float32)
+            out = np.zeros(max(len(Xw), 1), np.uint8)
+            keep += [Xw, obs, s2]
+            outs.append(out)
+            P[f].n, P[f].Xw, P[f].obs, P[f].inv_sigma2 = len(Xw), Xw.ctypes.data, obs.ctypes.data, s2.ctypes.data
+            for i, v in enumerate(np.asarray(p["pose"], np.float64)):
+                P[f].pose[i] = v
+            P[f].fx, P[f].fy, P[f].cx, P[f].cy, P[f].bf = (float(v) for v in p["K"][:5])
+            R[f].outlier = out.ctypes.data
+        check(self._L.orbx_pose_optimize_host(self._h, P, nf, R))
+        res = [dict(pose=np.array(list(R[f].pose)), outlier=outs[f][:P[f].n].copy(), n_inliers=R[f].n_inliers, n_bad=R[f].n_bad,
+                    trials=R[f].lm_trials) for f in range(nf)]
+        return res[0] if single else res
+
+    def last_launches(self):
+        return self._L.orbx_pose_last_launches(self._h)

@@ -373,6 +373,38 @@ int orbx_lba_last_launches(const orbx_lba *h);
  * (quadratic form, Schur accumulation, cluster reduction, reduced solve, update, residuals) */
 orbx_status orbx_lba_phase_ns(const orbx_lba *h, double out[6]);
 
+/* =====================================================================================================
+ * Optimizer::PoseOptimization  (reference include/Optimizer.h:49, src/Optimizer.cc:239-452): the
+ * motion-only bundle adjustment Tracking runs right after every matcher call (Tracking.cc:870, :994, :1039).
+ * The adapter lists the keypoints that have a map point in index order, exactly where the reference builds the g2o
+ * graph (:275-350), and writes pose / mvbOutlier back where it reads them (:371-417, :424-430).
+ * ===================================================================================================== */
+typedef struct {
+    int32_t n;                   /* nInitialCorrespondences */
+    const double *Xw;            /* n x 3: pMP->GetWorldPos() widened to double (:305-308) */
+    const double *obs;           /* n x 3: kpUn.pt.x, kpUn.pt.y, mvuRight[i]; a negative third value = monocular edge (:281) */
+    const float *inv_sigma2;     /* mvInvLevelSigma2[kpUn.octave] */
+    double pose[7];              /* Converter::toSE3Quat(pFrame->mTcw): quaternion (x,y,z,w), translation */
+    double fx, fy, cx, cy, bf;   /* the frame's float intrinsics widened to double (e->fx = pFrame->fx ...) */
+} orbx_pose_problem;
+typedef struct {
+    double pose[7];              /* SE3quat_recov (:424-427); Converter::toCvMat + SetPose stay in the adapter */
+    uint8_t *outlier;            /* caller-allocated, n entries: mvbOutlier of the listed keypoints */
+    int32_t n_inliers;           /* the return value: nInitialCorrespondences - nBad (0 if n < 3, :355) */
+    int32_t n_bad;               /* pFrame->nBadPoseOpt */
+    int32_t lm_trials;           /* Levenberg trials over the four rounds (diagnostics) */
+} orbx_pose_result;
+
+typedef struct orbx_pose orbx_pose;
+/* max_observations: over the whole batch of one call */
+orbx_status orbx_pose_create(orbx_pose **out, int max_observations, int max_frames, int device);
+void orbx_pose_destroy(orbx_pose *h);
+/* replaces int Optimizer::PoseOptimization(Frame *pFrame) for n_frames independent frames in one launch (one thread
+ * block per frame; the four rounds, their Levenberg loops and the classifications run on the device).  Host pointers;
+ * synchronous. */
+orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_problem *probs, int n_frames, orbx_pose_result *res);
+int orbx_pose_last_launches(const orbx_pose *h);
+
 #ifdef __cplusplus
 }
 #endif
