@@ -187,6 +187,97 @@ def run_reference(args, rank):
     }))
 
 
+def bench_stereo(local_rank, with_cpu, n_pairs=32, reps=20):
+    """Frame::ComputeStereoMatches (SURVEY §8f-2) on n_pairs rectified VGA pairs, device-resident: one extractor run over
+    L0 R0 L1 R1 ..., then the two stereo kernels read keypoints, descriptors and both pyramids in place."""
+    import torch
+    from orbx import synth
+    from orbx.extractor import ORBextractor
+    from orbx.stereo import StereoMatcher, StereoSide
+    world = synth.stereo_world(0, W, H)
+    frames = []
+    for p in range(n_pairs):
+        frames += [world.render(0.02 * p, 0.01, 0.001 * p), world.render(0.02 * p, 0.01, 0.001 * p, right=True)]
+    bf, b = world.bf, world.bf / world.fx
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=2 * n_pairs, device=local_rank)
+    cap = ex.capacity
+    d_img = torch.from_numpy(np.stack(frames)).cuda()
+    d_kps = torch.zeros((2 * n_pairs, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((2 * n_pairs, cap, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2 * n_pairs, dtype=torch.int32, device="cuda")
+    d_ur = torch.zeros((n_pairs, cap), dtype=torch.float32, device="cuda")
+    d_dp = torch.zeros((n_pairs, cap), dtype=torch.float32, device="cuda")
+    d_kept = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream()
+    ex.run_device(d_img.data_ptr(), W * H, 2 * n_pairs, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), st.cuda_stream)
+    left = StereoSide(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), 2 * cap, 2, ex._h, 0, 2, cap)
+    right = StereoSide(d_kps.data_ptr() + 28 * cap, d_desc.data_ptr() + 32 * cap, d_cnt.data_ptr() + 4, 2 * cap, 2, ex._h, 1, 2, cap)
+    sm = StereoMatcher(max_keypoints=cap, max_pairs=n_pairs, device=local_rank)
+    run = lambda: sm.matches_device(left, right, n_pairs, bf, b, d_ur.data_ptr(), d_dp.data_ptr(), cap, d_kept.data_ptr(), st.cuda_stream)
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(reps):
+        run()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    kept = d_kept.cpu().numpy()
+    out = {"config": "%d rectified 640x480 pairs of the 3-plane world (z = 2, 4, 8 m), 1000 features per image, device-resident" % n_pairs,
+           "pairs_per_s": n_pairs / (ms * 1e-3), "ms_per_batch": ms, "kernel_launches_per_batch": sm.last_launches(),
+           "associations_per_pair": float(kept.mean()), "api": "orbx_stereo_matches_device after orbx_extractor_run_device (CUDA events)"}
+    if with_cpu:
+        from oracle import oracle_py as O
+        cnt = d_cnt.cpu().numpy()
+        kps = d_kps.cpu().numpy().view(O.KP_DTYPE).reshape(2 * n_pairs, cap)
+        desc = d_desc.cpu().numpy()
+        sc, isc = ex.GetScaleFactors(), ex.GetInverseScaleFactors()
+        t_cpu, n_cpu = 0.0, 0
+        for p in range(min(n_pairs, 8)):
+            pl = [ex.pyramid_level(l, 2 * p) for l in range(NLEVELS)]
+            pr = [ex.pyramid_level(l, 2 * p + 1) for l in range(NLEVELS)]
+            a = (kps[2 * p, :cnt[2 * p]], desc[2 * p, :cnt[2 * p]], kps[2 * p + 1, :cnt[2 * p + 1]], desc[2 * p + 1, :cnt[2 * p + 1]])
+            t0 = time.perf_counter()
+            r = O.stereo_matches(a[0], a[1], a[2], a[3], pl, pr, sc, isc, bf, b)
+            t_cpu += time.perf_counter() - t0
+            n_cpu += 1
+            assert r["kept"] == int(kept[p]), "stereo: GPU and oracle disagree on pair %d" % p
+        out["cpu_pairs_per_s"] = n_cpu / t_cpu
+        out["cpu"] = "C oracle, 1 thread, %d pairs (pyramids already built); same association counts as the GPU" % n_cpu
+    sm.close()
+    ex.close()
+    return out
+
+
+def bench_pose(local_rank, with_cpu, n_frames=64, n_obs=500, reps=10):
+    """Optimizer::PoseOptimization (SURVEY §8f-1) on n_frames frames of n_obs observations, host buffers in and out."""
+    from orbx import synth
+    from orbx.optimizer import PoseOptimizer
+    probs = [synth.pose_problem(1000 + f, n=n_obs) for f in range(n_frames)]
+    po = PoseOptimizer(max_observations=n_frames * n_obs, max_frames=n_frames, device=local_rank)
+    rs = po.PoseOptimization(probs)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rs = po.PoseOptimization(probs)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"config": "%d frames x %d observations (60 %% stereo, 15 %% outliers), 4 rounds x optimize(10)" % (n_frames, n_obs),
+           "frames_per_s": n_frames / dt, "ms_per_batch": 1e3 * dt, "kernel_launches_per_batch": po.last_launches(),
+           "lm_trials_per_frame": float(np.mean([r["trials"] for r in rs])),
+           "api": "orbx_pose_optimize_host (host buffers in and out, synchronous; includes packing in Python)"}
+    if with_cpu:
+        from oracle import oracle_py as O
+        t0 = time.perf_counter()
+        for f in range(8):
+            ref = O.pose_optimize(probs[f])
+            assert np.array_equal(ref["outlier"], rs[f]["outlier"]), "pose: GPU and oracle disagree on frame %d" % f
+        out["cpu_frames_per_s"] = 8 / (time.perf_counter() - t0)
+        out["cpu"] = "C oracle (g2o restated), 1 thread, 8 frames; identical outlier sets"
+    po.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -496,6 +587,11 @@ def main():
             lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
         op.close()
 
+    stereo = pose = None
+    if rank == 0:
+        stereo = bench_stereo(local_rank, not args.no_cpu)
+        pose = bench_pose(local_rank, not args.no_cpu)
+
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
     ms_total, e2e_s, ms_two_lanes = shard.max_over_ranks([ms_total, e2e_s, ms_two_lanes], device="cuda")
@@ -537,6 +633,8 @@ def main():
                                         "frac": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9 / peak}},
             "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
             "lba": lba,
+            "stereo": stereo,
+            "pose": pose,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1

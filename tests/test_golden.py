@@ -41,6 +41,56 @@ def test_oracle_reproduces_golden():
     r = O.lba_solve(p, 5, 10)
     g = np.load(os.path.join(GOLD, "lba_seed5.npz"))
     assert r["trials"] == int(g["trials"]) and np.array_equal(r["erase"], g["erase"]) and lba_rel(r["pts"], g["pts"]) < 1e-12
+    p = synth.lba_problem(6, n_kf=6, n_pts=300, stereo=True, n_fixed=1)
+    r = O.lba_solve(p, 5, 10)
+    g = np.load(os.path.join(GOLD, "lba_stereo_seed6.npz"))
+    assert np.array_equal(r["erase"], g["erase"]) and lba_rel(r["pts"], g["pts"]) < 1e-12 and lba_rel(r["kf"], g["kf"]) < 1e-12
+    st = oracle_stereo_seed0(O)
+    g = np.load(os.path.join(GOLD, "stereo_seed0.npz"))
+    assert st["u_right"].tobytes() == g["u_right"].tobytes() and st["depth"].tobytes() == g["depth"].tobytes() and st["kept"] == int(g["kept"])
+    r = O.pose_optimize(synth.pose_problem(3, n=300))
+    g = np.load(os.path.join(GOLD, "pose_seed3.npz"))
+    assert np.array_equal(r["outlier"], g["outlier"]) and r["n_inliers"] == int(g["n_inliers"]) and lba_rel(r["pose"], g["pose"]) < 1e-12
+
+
+def oracle_stereo_seed0(O):
+    world = synth.stereo_world(0)
+    exl, exr = O.Extractor(1000, 1.2, 8, 20, 7), O.Extractor(1000, 1.2, 8, 20, 7)
+    kl, dl = exl(world.render(0.0, 0.01, 0.0))
+    kr, dr = exr(world.render(0.0, 0.01, 0.0, right=True))
+    t = exl.tables()
+    return O.stereo_matches(kl, dl, kr, dr, [exl.level(l) for l in range(8)], [exr.level(l) for l in range(8)], t["scale"], t["inv_scale"],
+                            world.bf, world.bf / world.fx)
+
+
+@pytest.mark.gpu
+def test_cuda_stereo_and_pose_reproduce_golden():
+    """no oracle at run time: the CUDA path against the committed vectors"""
+    from orbx.extractor import ORBextractor
+    from orbx.optimizer import Optimizer, PoseOptimizer
+    from orbx.stereo import StereoMatcher
+    world = synth.stereo_world(0)
+    el, er, sm = ORBextractor(1000, 1.2, 8, 20, 7), ORBextractor(1000, 1.2, 8, 20, 7), StereoMatcher(max_keypoints=2048)
+    po, o = PoseOptimizer(max_observations=1000, max_frames=1), Optimizer(max_keyframes=16, max_points=1000, max_edges=5000)
+    try:
+        kl, dl = el(world.render(0.0, 0.01, 0.0))
+        kr, dr = er(world.render(0.0, 0.01, 0.0, right=True))
+        ur, dp, kept = sm.ComputeStereoMatches(el, er, kl, dl, kr, dr, world.bf, world.bf / world.fx)
+        g = np.load(os.path.join(GOLD, "stereo_seed0.npz"))
+        assert ur.tobytes() == g["u_right"].tobytes() and dp.tobytes() == g["depth"].tobytes() and kept == int(g["kept"])
+        p = synth.pose_problem(3, n=300)
+        r = po.PoseOptimization(p)
+        g = np.load(os.path.join(GOLD, "pose_seed3.npz"))
+        assert np.array_equal(r["outlier"], g["outlier"]) and r["n_inliers"] == int(g["n_inliers"])
+        assert lba_rel(r["pose"] - p["pose"], g["pose"] - p["pose"]) < 1e-4
+        p = synth.lba_problem(6, n_kf=6, n_pts=300, stereo=True, n_fixed=1)
+        g = np.load(os.path.join(GOLD, "lba_stereo_seed6.npz"))
+        r = o.LocalBundleAdjustment(p, 5, 10)
+        assert np.array_equal(r["erase"], g["erase"])
+        assert lba_rel(r["kf"] - p["kf_pose"], g["kf"] - p["kf_pose"]) < 1e-4 and lba_rel(r["pts"] - p["pts"], g["pts"] - p["pts"]) < 1e-4
+    finally:
+        for h in (el, er, sm, po, o):
+            h.close()
 
 
 @pytest.mark.gpu

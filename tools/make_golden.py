@@ -51,6 +51,22 @@ def main():
     r = O.lba_solve(p, 5, 10, want_system=True)
     np.savez_compressed(os.path.join(OUT, "lba_seed5.npz"), kf=r["kf"], pts=r["pts"], erase=r["erase"], chi2=r["chi2"], trials=r["trials"],
                         Hschur=r["Hschur"], bschur=r["bschur"], lambda0=r["lambda0"])
+    p = synth.lba_problem(6, n_kf=6, n_pts=300, stereo=True, n_fixed=1)
+    r = O.lba_solve(p, 5, 10)
+    np.savez_compressed(os.path.join(OUT, "lba_stereo_seed6.npz"), kf=r["kf"], pts=r["pts"], erase=r["erase"], trials=r["trials"])
+    # Frame::ComputeStereoMatches on one rendered pair of the 3-plane world
+    world = synth.stereo_world(0)
+    exl, exr = O.Extractor(1000, 1.2, 8, 20, 7), O.Extractor(1000, 1.2, 8, 20, 7)
+    kl, dl = exl(world.render(0.0, 0.01, 0.0))
+    kr, dr = exr(world.render(0.0, 0.01, 0.0, right=True))
+    t = exl.tables()
+    st = O.stereo_matches(kl, dl, kr, dr, [exl.level(l) for l in range(8)], [exr.level(l) for l in range(8)], t["scale"], t["inv_scale"],
+                          world.bf, world.bf / world.fx)
+    np.savez_compressed(os.path.join(OUT, "stereo_seed0.npz"), u_right=st["u_right"], depth=st["depth"], kept=st["kept"])
+    # Optimizer::PoseOptimization
+    pp = synth.pose_problem(3, n=300)
+    pr_ = O.pose_optimize(pp)
+    np.savez_compressed(os.path.join(OUT, "pose_seed3.npz"), pose=pr_["pose"], outlier=pr_["outlier"], n_inliers=pr_["n_inliers"])
     with open(os.path.join(OUT, "digests.txt"), "w") as f:
         for k in sorted(digests):
             f.write("%s %s\n" % (k, digests[k]))
