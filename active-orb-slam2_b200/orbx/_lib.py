@@ -92,5 +92,11 @@ def _declare(L):
     L.orbx_pose_destroy.argtypes = [vp]
     L.orbx_pose_optimize_host.argtypes = [vp, vp, i, vp]
     L.orbx_pose_last_launches.argtypes = [vp]
+    L.orbx_vocabulary_create.argtypes = [C.POINTER(vp), i, vp, vp, vp, vp, vp, i, i, i]
+    L.orbx_vocabulary_destroy.restype = None
+    L.orbx_vocabulary_destroy.argtypes = [vp]
+    L.orbx_vocabulary_transform_host.argtypes = [vp, vp, i, i, vp, vp, vp]
+    L.orbx_vocabulary_transform_device.argtypes = [vp, i, vp, vp, i, i, i, i, vp, vp, vp, vp]
+    L.orbx_vocabulary_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -388,3 +388,48 @@ def pose_problem(seed, n=400, stereo_frac=0.6, outlier_frac=0.15, w=640, h=480, 
     pose[4:] = tn.astype(np.float32)
     return dict(Xw=np.asarray(Xw, np.float64), obs=np.asarray(obs, np.float64), inv_sigma2=np.asarray(is2, np.float32), pose=pose,
                 K=(np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), np.float32(bf)))
+
+
+def random_vocabulary(seed, k=10, L=4, prune=0.1, dup=0.1, stop=0.02, shuffle=True):
+    """A vocabulary tree as a DBoW2 file would describe it (parent, descriptor, weight, is_leaf per node 1..n in file order):
+    up to k children per node, some branches end early (prune), some siblings share a descriptor (dup: exercises `d < best_d`
+    keeping the first child), some words are stopped (weight 0).  shuffle permutes the node ids so that siblings are not
+    consecutive.  Returns the arguments of orbx.vocabulary.tree_from_parents."""
+    rng = np.random.default_rng(seed)
+    parent, depth = [], []
+    frontier = [0]
+    for lvl in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            if p != 0 and rng.random() < prune:
+                continue                                           # p stays a leaf above the last level
+            for _ in range(int(rng.integers(2, k + 1))):
+                parent.append(p); depth.append(lvl)
+                nxt.append(len(parent))
+        frontier = nxt
+    n = len(parent)
+    parent = np.array(parent, np.int64)
+    desc = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    for i in range(1, n):
+        if parent[i] == parent[i - 1] and rng.random() < dup:
+            desc[i] = desc[i - 1]
+    has_child = np.zeros(n + 1, bool)
+    has_child[parent] = True
+    is_leaf = ~has_child[1:]
+    weight = np.where(is_leaf, rng.uniform(0.1, 9.0, n), 0.0).astype(np.float32)
+    weight[is_leaf & (rng.random(n) < stop)] = 0.0
+    if shuffle:
+        perm = rng.permutation(n)                                  # new id of old node i+1 is perm[i]+1
+        new_parent = np.zeros(n, np.int64)
+        new_parent[perm] = np.where(parent == 0, 0, perm[np.maximum(parent - 1, 0)] + 1)
+        nd, nw, nl = np.zeros_like(desc), np.zeros_like(weight), np.zeros_like(is_leaf)
+        nd[perm], nw[perm], nl[perm] = desc, weight, is_leaf
+        parent, desc, weight, is_leaf = new_parent, nd, nw, nl
+    return parent.astype(np.int32), desc, weight, is_leaf.astype(np.uint8), k, L
+
+
+def descriptors_near_words(rng, tree, n, flip=20):
+    """n descriptors: leaf descriptors of the tree with `flip` random bits flipped (so descents are not uniform noise)"""
+    leaves = np.nonzero(tree["word_id"] >= 0)[0]
+    pick = rng.choice(leaves, n)
+    return flip_bits(rng, tree["desc"][pick].copy(), np.full(n, flip))

@@ -405,6 +405,32 @@ void orbx_pose_destroy(orbx_pose *h);
 orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_problem *probs, int n_frames, orbx_pose_result *res);
 int orbx_pose_last_launches(const orbx_pose *h);
 
+/* =====================================================================================================
+ * DBoW2 TemplatedVocabulary::transform  (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1138-1262, called by
+ * Frame::ComputeBoW Frame.cc:286-293 and KeyFrame::ComputeBoW KeyFrame.cc:76-85 with levelsup = 4).
+ * The device does the per-feature descent of the vocabulary tree (FORB::distance = 256-bit Hamming, the FIRST child
+ * among equal distances wins) and returns, per feature, the word id, the word's weight and the node passed at level
+ * L - levelsup.  The adapter then runs the reference's own bookkeeping loop over these (BowVector::addWeight /
+ * FeatureVector::addFeature in feature order, skipping weight 0, then the L1 normalisation), which produces the
+ * std::map objects SearchByBoW / SearchForTriangulation consume.
+ * ===================================================================================================== */
+typedef struct orbx_vocabulary orbx_vocabulary;
+/* the tree as TemplatedVocabulary holds it in m_nodes (node 0 = root): CSR of every node's children in the reference's
+ * order, descriptors (32 bytes per node), weights, word ids (leaves).  Copied to the device once. */
+orbx_status orbx_vocabulary_create(orbx_vocabulary **out, int n_nodes, const int32_t *child_start, const int32_t *children,
+                                   const uint8_t *node_desc, const double *node_weight, const int32_t *node_word_id, int L,
+                                   int max_features, int device);
+void orbx_vocabulary_destroy(orbx_vocabulary *h);
+/* one feature set, host pointers; word / node / weight have n entries.  Synchronous. */
+orbx_status orbx_vocabulary_transform_host(orbx_vocabulary *h, const uint8_t *desc, int n, int levelsup, int32_t *word,
+                                           int32_t *node, double *weight);
+/* batched, device-resident (descriptors where the extractor left them): frame f has its descriptors at d_desc + f*pitch*32
+ * and counts[f*count_step] of them (<= max_count); outputs at + f*pitch.  Only enqueues on `stream`. */
+orbx_status orbx_vocabulary_transform_device(orbx_vocabulary *h, int levelsup, const uint8_t *d_desc, const int32_t *d_counts,
+                                             int count_step, int pitch, int max_count, int batch, int32_t *d_word, int32_t *d_node,
+                                             double *d_weight, void *stream);
+int orbx_vocabulary_last_launches(const orbx_vocabulary *h);
+
 #ifdef __cplusplus
 }
 #endif

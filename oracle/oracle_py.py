@@ -505,3 +505,25 @@ def pose_optimize(prob):
     nb, tr = C.c_int32(), C.c_int32()
     r = L.orbo_pose_optimize(C.byref(P), _p(pose), _p(out), C.byref(nb), C.byref(tr))
     return dict(pose=pose, outlier=out[:P.n].copy(), n_inliers=r, n_bad=nb.value, trials=tr.value)
+
+
+# ---- bag-of-words transform (oracle/bow_oracle.c) ---------------------------------------------------------------
+class OVocabulary(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("child_start", C.c_void_p), ("children", C.c_void_p), ("desc", C.c_void_p),
+                ("weight", C.c_void_p), ("word_id", C.c_void_p), ("L", C.c_int32)]
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """voc: dict(child_start, children, desc, weight, word_id, L) -> (word[n], node[n], weight[n]) per feature"""
+    L = lib()
+    L.orbo_bow_transform.restype = None
+    L.orbo_bow_transform.argtypes = [C.POINTER(OVocabulary), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    cs, ch = np.ascontiguousarray(voc["child_start"], np.int32), np.ascontiguousarray(voc["children"], np.int32)
+    nd, w = np.ascontiguousarray(voc["desc"], np.uint8), np.ascontiguousarray(voc["weight"], np.float64)
+    wid = np.ascontiguousarray(voc["word_id"], np.int32)
+    V = OVocabulary(len(cs) - 1, cs.ctypes.data, ch.ctypes.data, nd.ctypes.data, w.ctypes.data, wid.ctypes.data, int(voc["L"]))
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(d)
+    word, node, wt = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    L.orbo_bow_transform(C.byref(V), _p(d), n, levelsup, _p(word), _p(node), _p(wt))
+    return word[:n], node[:n], wt[:n]

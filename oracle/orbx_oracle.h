@@ -172,6 +172,20 @@ typedef struct {
 int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out, double *pt_out, double *chi2_out,
                    uint8_t *erase_out, orbo_lba_trace *tr);
 
+/* ---- bag-of-words transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1216-1262) ---- */
+typedef struct {
+    int32_t n_nodes;             /* m_nodes.size(); node 0 is the root */
+    const int32_t *child_start;  /* n_nodes + 1: CSR of m_nodes[id].children, in the reference's child order */
+    const int32_t *children;
+    const uint8_t *desc;         /* n_nodes x 32: m_nodes[id].descriptor (root unused) */
+    const double *weight;        /* m_nodes[id].weight */
+    const int32_t *word_id;      /* m_nodes[id].word_id (leaves) */
+    int32_t L;                   /* m_L */
+} orbo_vocabulary;
+/* per feature: word id, weight of the leaf reached and the node passed at level L - levelsup (0 if that level is <= 0) */
+void orbo_bow_transform(const orbo_vocabulary *V, const uint8_t *desc, int n, int levelsup, int32_t *word, int32_t *node,
+                        double *weight);
+
 /* ---- pose-only optimisation (src/Optimizer.cc:239-452 + g2o unary edges) ---- */
 typedef struct {
     int32_t n;                   /* keypoints with a map point (nInitialCorrespondences) */
