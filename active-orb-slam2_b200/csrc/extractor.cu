@@ -448,6 +448,9 @@ extern "C" orbx_status orbx_extractor_create(orbx_extractor **out, int nfeatures
         TRY(cudaMalloc((void **)&e->d_counts, sizeof(int32_t) * mb));
         TRY(cudaMallocHost((void **)&e->h_status, sizeof(int) * mb));
         TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        TRY(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
 #undef TRY
         e->img_cap = (size_t)max_width * max_height;
         st = configure(e, max_width, max_height);
@@ -472,6 +475,9 @@ extern "C" void orbx_extractor_destroy(orbx_extractor *e) {
     free(e->prof_ev);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->aux) cudaStreamDestroy(e->aux);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     free(e);
 }
 
@@ -519,9 +525,20 @@ extern "C" orbx_status orbx_extractor_run_device(orbx_extractor *e, const uint8_
     MARK(1);
     if ((st = orbx_launch_fast(e, batch, s))) return st;
     MARK(2);
-    if ((st = orbx_launch_octree(e, batch, s))) return st;
-    MARK(3);
-    if ((st = orbx_launch_blur(e, batch, s))) return st;
+    if (ev) {                       // per-stage timing asked for: one stream, stages back to back
+        if ((st = orbx_launch_octree(e, batch, s))) return st;
+        MARK(3);
+        if ((st = orbx_launch_blur(e, batch, s))) return st;
+    } else {
+        // The quadtree kernel has one CTA per (frame, level) and leaves most SMs idle; the blur only needs the pyramid.
+        // Fork after FAST: quadtree on the caller's stream, blur on the side stream, join before the descriptors.
+        ORBX_CUDA(cudaEventRecord(e->ev_fork, s));
+        ORBX_CUDA(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+        if ((st = orbx_launch_octree(e, batch, s))) return st;
+        if ((st = orbx_launch_blur(e, batch, e->aux))) return st;
+        ORBX_CUDA(cudaEventRecord(e->ev_join, e->aux));
+        ORBX_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
+    }
     MARK(4);
     if ((st = orbx_launch_describe(e, batch, d_kps, d_desc, d_counts, s))) return st;
     MARK(5);

@@ -129,6 +129,8 @@ struct orbx_extractor {
     int32_t *h_counts, *d_counts;
     int *h_status;
     cudaStream_t stream;      // private stream of the _host entry point
+    cudaStream_t aux;         // side stream: the blur runs next to the (under-filled) quadtree kernel
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2];
     int last_launches;
     int last_batch;
