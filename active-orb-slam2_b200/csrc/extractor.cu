@@ -204,7 +204,7 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
                 bool ok = px + 3 < L.w + 2 * ORBX_EDGE;
                 for (int b = 1; b < 4 && ok; b++) {
                     const int d = (int)(q[b] & 0xffff) - (int)(q[0] & 0xffff);
-                    ok = d >= 0 && d <= 7;
+                    ok = d >= 0 && d <= 6;        // bytes d, d+1 of an 8-byte window (pyramid.cu)
                 }
                 if (ok) q[0] |= 0x80000000u;
             }
@@ -224,7 +224,8 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
         }
         // FAST tiles: runs of cells of one cell row (ORBextractor.cc:785-806 decides which cells exist)
         const int maxBX = L.w - ORBX_BORDER, maxBY = L.h - ORBX_BORDER;
-        const int per_chunk = L.wcell >= 128 ? 1 : (128 / L.wcell > ORBX_FAST_CELLS ? ORBX_FAST_CELLS : 128 / L.wcell);
+        // up to ~200 detection columns per tile (the kernel packs tile x in 8 bits), cells spread evenly over the tiles of a row
+        const int max_per_chunk = L.wcell >= 200 ? 1 : (200 / L.wcell > ORBX_FAST_CELLS ? ORBX_FAST_CELLS : 200 / L.wcell);
         for (int i = 0; i < L.nrows; i++) {
             const int iniY = ORBX_BORDER + i * L.hcell;
             if (iniY >= maxBY - 3) continue;
@@ -242,6 +243,8 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
                 nvalid = j + 1;
                 last_cw = maxX - iniX;
             }
+            const int row_chunks = (nvalid + max_per_chunk - 1) / max_per_chunk;
+            const int per_chunk = row_chunks ? (nvalid + row_chunks - 1) / row_chunks : 1;
             for (int j0 = 0; j0 < nvalid; j0 += per_chunk) {
                 const int j1 = j0 + per_chunk < nvalid ? j0 + per_chunk : nvalid;
                 OrbxFastChunk c;

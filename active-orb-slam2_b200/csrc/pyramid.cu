@@ -25,6 +25,18 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t *__restrict__ 
     const int iy = reflect101(py - ORBX_EDGE, L.h);
     const uint8_t *row = img + (size_t)iy * stride;
     uint32_t w[4];
+    const int sx = gx - ORBX_EDGE;                     // source column of the first of the 16 bytes
+    const int mis = sx & 3;
+    if (sx >= 4 && sx - mis + 20 <= L.w && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
+        // interior: five aligned words cover the 16 source bytes (no reflection inside), one funnel shift per output word
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + sx - mis);
+        const uint32_t u0 = __ldg(p), u1 = __ldg(p + 1), u2 = __ldg(p + 2), u3 = __ldg(p + 3), u4 = __ldg(p + 4);
+        const int sh = 8 * mis;
+        w[0] = __funnelshift_r(u0, u1, sh); w[1] = __funnelshift_r(u1, u2, sh);
+        w[2] = __funnelshift_r(u2, u3, sh); w[3] = __funnelshift_r(u3, u4, sh);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         uint32_t v = 0;
@@ -40,25 +52,20 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t *__restrict__ 
     *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// bytes b, b+1 (in the low 16 bits) of the 12-byte window (w0, w1, w2), b in [0, 10]
-__device__ __forceinline__ uint32_t window2(uint32_t w0, uint32_t w1, uint32_t w2, int b) {
-    if (b < 4) return __funnelshift_rc(w0, w1, 8 * b);
-    if (b < 8) return __funnelshift_rc(w1, w2, 8 * (b - 4));
-    return w2 >> (8 * (b - 8));
-}
-
-__device__ __forceinline__ uint32_t resize_px(int a1, int b0, int b1, uint32_t t0, uint32_t t1) {
-    const int a0 = 2048 - a1;
-    const int s0 = a0 * (int)(t0 & 0xff) + a1 * (int)((t0 >> 8) & 0xff);
-    const int s1 = a0 * (int)(t1 & 0xff) + a1 * (int)((t1 >> 8) & 0xff);
+// OpenCV's fixed-point bilinear for one pixel: t0 / t1 hold the two horizontal neighbours of the upper / lower source row
+// in their low 16 bits, coef = a0 | a1 << 16 (a0 + a1 = 2048).  The horizontal step a0*p[sx] + a1*p[sx+1] is one DP2A.
+__device__ __forceinline__ uint32_t resize_px(uint32_t coef, int b0, int b1, uint32_t t0, uint32_t t1) {
+    const int s0 = (int)__dp2a_lo(coef, t0, 0u);
+    const int s1 = (int)__dp2a_lo(coef, t1, 0u);
     return (uint32_t)((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2);
 }
 
 // level l >= 1 from the interior of level l-1.  One thread = 4 consecutive bytes of one padded output row, so a warp
 // reads 128 consecutive table bytes and writes 128 consecutive output bytes.  Tables are indexed by padded output
-// coordinates (the reflected border is resolved on the host).  When the four source positions fall into one aligned
-// 12-byte window (flag bit of the group; always true in the interior at ORB-SLAM's scale factors) each source row
-// costs three 32-bit loads; otherwise (the few reflected groups at the row ends) bytes are loaded one by one.
+// coordinates (the reflected border is resolved on the host).  When the four source positions ascend and span at most 6
+// bytes (flag bit of the group; always true in the interior at ORB-SLAM's scale factors) each source row costs three
+// aligned 32-bit loads, two funnel shifts that bring bytes sx0 .. sx0+7 into a register pair, and one byte permute per
+// pixel; otherwise (the few reflected groups at the row ends) bytes are loaded one by one.
 __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel S, OrbxLevel L,
                                                     const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols4) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,17 +87,24 @@ __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, s
         const int mis = (int)(a0 & 3);                  // r0 and r1 differ by a multiple of the 16-byte pitch
         const uint32_t *p0 = reinterpret_cast<const uint32_t *>(a0 - mis), *p1 = reinterpret_cast<const uint32_t *>(a1 - mis);
         const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+        const int sh = 8 * mis;
+        const uint32_t qa0 = __funnelshift_r(u0, u1, sh), qa1 = __funnelshift_r(u1, u2, sh);   // bytes sx0 .. sx0+7 of the upper row
+        const uint32_t qb0 = __funnelshift_r(v0, v1, sh), qb1 = __funnelshift_r(v1, v2, sh);   // ... of the lower row
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int off = mis + ((int)(e[b] & 0xffff) - sx0);
-            v |= resize_px((int)((e[b] >> 16) & 0x7fff), b0, b1, window2(u0, u1, u2, off), window2(v0, v1, v2, off)) << (8 * b);
+            const uint32_t d = (e[b] & 0xffff) - (uint32_t)sx0;         // 0 .. 6
+            const uint32_t sel = d * 0x11u + 0x10u;                     // PRMT selector: bytes d, d+1 of the 8-byte window
+            const uint32_t a1 = (e[b] >> 16) & 0x7fff;
+            const uint32_t coef = (2048u - a1) | (a1 << 16);
+            v |= resize_px(coef, b0, b1, __byte_perm(qa0, qa1, sel), __byte_perm(qb0, qb1, sel)) << (8 * b);
         }
     } else {
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int sx = (int)(e[b] & 0xffff);          // sx+1 may touch the pad: a1 == 0 there
             const uint32_t t0 = (uint32_t)r0[sx] | ((uint32_t)r0[sx + 1] << 8), t1 = (uint32_t)r1[sx] | ((uint32_t)r1[sx + 1] << 8);
-            v |= resize_px((int)((e[b] >> 16) & 0x7fff), b0, b1, t0, t1) << (8 * b);
+            const uint32_t a1 = (e[b] >> 16) & 0x7fff;
+            v |= resize_px((2048u - a1) | (a1 << 16), b0, b1, t0, t1) << (8 * b);
         }
     }
     *reinterpret_cast<uint32_t *>(frame + L.off + (size_t)py * L.pitch + 4 * g4) = v;
