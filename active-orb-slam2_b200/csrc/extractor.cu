@@ -201,12 +201,14 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
             }
             for (int px = 0; px < L.pitch; px += 4) {   // group flag: 4 columns whose sources lie in one 12-byte window
                 uint32_t *q = &g.rxt[L.rx_off + px];
-                bool ok = px + 3 < L.w + 2 * ORBX_EDGE;
-                for (int b = 1; b < 4 && ok; b++) {
-                    const int d = (int)(q[b] & 0xffff) - (int)(q[0] & 0xffff);
-                    ok = d >= 0 && d <= 6;        // bytes d, d+1 of an 8-byte window (pyramid.cu)
+                int lo = 0xffff, hi = 0;
+                for (int b = 0; b < 4; b++) {
+                    const int sx = (int)(q[b] & 0xffff);
+                    lo = sx < lo ? sx : lo; hi = sx > hi ? sx : hi;
                 }
-                if (ok) q[0] |= 0x80000000u;
+                // bytes d, d+1 (d = sx - smallest sx of the group) must lie in an 8-byte window (pyramid.cu); order is free, so the
+                // groups that straddle a reflection point qualify too
+                if (hi - lo <= 6) q[0] |= 0x80000000u;
             }
             L.ry_off = (int)g.ryt.size();
             for (int py = 0; py < L.ph; py++) {

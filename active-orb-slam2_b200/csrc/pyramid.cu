@@ -60,16 +60,16 @@ __device__ __forceinline__ uint32_t resize_px(uint32_t coef, int b0, int b1, uin
     return (uint32_t)((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2);
 }
 
-// level l >= 1 from the interior of level l-1.  One thread = 4 consecutive bytes of one padded output row, so a warp
-// reads 128 consecutive table bytes and writes 128 consecutive output bytes.  Tables are indexed by padded output
-// coordinates (the reflected border is resolved on the host).  When the four source positions ascend and span at most 6
-// bytes (flag bit of the group; always true in the interior at ORB-SLAM's scale factors) each source row costs three
-// aligned 32-bit loads, two funnel shifts that bring bytes sx0 .. sx0+7 into a register pair, and one byte permute per
-// pixel; otherwise (the few reflected groups at the row ends) bytes are loaded one by one.
+// level l >= 1 from the interior of level l-1.  One thread = 16 consecutive bytes of one padded output row (one 128-bit
+// store), as four groups of four pixels.  Tables are indexed by padded output coordinates (the reflected border is resolved
+// on the host).  When the four source positions of a group span at most 6 bytes (flag bit of the group; always true at
+// ORB-SLAM's scale factors, also across the reflection points, because the window starts at the smallest position) each
+// source row costs three aligned 32-bit loads, two funnel shifts that bring bytes base .. base+7 into a register pair, and
+// one byte permute per pixel; otherwise bytes are loaded one by one.
 __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel S, OrbxLevel L,
-                                                    const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols4) {
+                                                    const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols16) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = id / cols4, g4 = id - py * cols4;
+    const int py = id / cols16, g16 = id - py * cols16;
     if (py >= L.ph) return;
     uint8_t *frame = pyr + (size_t)blockIdx.z * pyr_frame;
     const uint8_t *sint = frame + S.off + (size_t)ORBX_EDGE * S.pitch + ORBX_EDGE;  // interior origin of the source
@@ -77,37 +77,44 @@ __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, s
     const int sy0 = yy.x & 0xffff, sy1 = yy.x >> 16;
     const int b0 = (int)(short)(yy.y & 0xffff), b1 = yy.y >> 16;
     const uint8_t *r0 = sint + (size_t)sy0 * S.pitch;
-    const uint8_t *r1 = sint + (size_t)sy1 * S.pitch;
-    const uint4 e4 = __ldg(rx + g4);
-    const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
-    const int sx0 = (int)(e[0] & 0xffff);
-    uint32_t v = 0;
-    if (e[0] >> 31) {
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(r0 + sx0), a1 = reinterpret_cast<uintptr_t>(r1 + sx0);
-        const int mis = (int)(a0 & 3);                  // r0 and r1 differ by a multiple of the 16-byte pitch
-        const uint32_t *p0 = reinterpret_cast<const uint32_t *>(a0 - mis), *p1 = reinterpret_cast<const uint32_t *>(a1 - mis);
-        const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
-        const int sh = 8 * mis;
-        const uint32_t qa0 = __funnelshift_r(u0, u1, sh), qa1 = __funnelshift_r(u1, u2, sh);   // bytes sx0 .. sx0+7 of the upper row
-        const uint32_t qb0 = __funnelshift_r(v0, v1, sh), qb1 = __funnelshift_r(v1, v2, sh);   // ... of the lower row
+    const ptrdiff_t r10 = ((ptrdiff_t)sy1 - sy0) * S.pitch;      // lower source row relative to the upper one (multiple of 16)
+    uint32_t out[4];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint32_t d = (e[b] & 0xffff) - (uint32_t)sx0;         // 0 .. 6
-            const uint32_t sel = d * 0x11u + 0x10u;                     // PRMT selector: bytes d, d+1 of the 8-byte window
-            const uint32_t a1 = (e[b] >> 16) & 0x7fff;
-            const uint32_t coef = (2048u - a1) | (a1 << 16);
-            v |= resize_px(coef, b0, b1, __byte_perm(qa0, qa1, sel), __byte_perm(qb0, qb1, sel)) << (8 * b);
-        }
-    } else {
+    for (int g = 0; g < 4; g++) {
+        const uint4 e4 = __ldg(rx + 4 * g16 + g);
+        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t v = 0;
+        if (e[0] >> 31) {
+            const int base = (int)min(min(e[0] & 0xffff, e[1] & 0xffff), min(e[2] & 0xffff, e[3] & 0xffff));
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(r0 + base);
+            const int mis = (int)(a0 & 3);
+            const uint32_t *p0 = reinterpret_cast<const uint32_t *>(a0 - mis);
+            const uint32_t *p1 = reinterpret_cast<const uint32_t *>(a0 - mis + r10);
+            const uint32_t u0 = p0[0], u1 = p0[1], u2 = p0[2], v0 = p1[0], v1 = p1[1], v2 = p1[2];
+            const int sh = 8 * mis;
+            const uint32_t qa0 = __funnelshift_r(u0, u1, sh), qa1 = __funnelshift_r(u1, u2, sh);   // bytes base .. base+7, upper row
+            const uint32_t qb0 = __funnelshift_r(v0, v1, sh), qb1 = __funnelshift_r(v1, v2, sh);   // ... lower row
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int sx = (int)(e[b] & 0xffff);          // sx+1 may touch the pad: a1 == 0 there
-            const uint32_t t0 = (uint32_t)r0[sx] | ((uint32_t)r0[sx + 1] << 8), t1 = (uint32_t)r1[sx] | ((uint32_t)r1[sx + 1] << 8);
-            const uint32_t a1 = (e[b] >> 16) & 0x7fff;
-            v |= resize_px((2048u - a1) | (a1 << 16), b0, b1, t0, t1) << (8 * b);
+            for (int b = 0; b < 4; b++) {
+                const uint32_t d = (e[b] & 0xffff) - (uint32_t)base;      // 0 .. 6
+                const uint32_t sel = d * 0x11u + 0x10u;                   // PRMT selector: bytes d, d+1 of the 8-byte window
+                const uint32_t a1 = (e[b] >> 16) & 0x7fff;
+                const uint32_t coef = (2048u - a1) | (a1 << 16);
+                v |= resize_px(coef, b0, b1, __byte_perm(qa0, qa1, sel), __byte_perm(qb0, qb1, sel)) << (8 * b);
+            }
+        } else {
+            const uint8_t *r1 = r0 + r10;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int sx = (int)(e[b] & 0xffff);          // sx+1 may touch the pad: a1 == 0 there
+                const uint32_t t0 = (uint32_t)r0[sx] | ((uint32_t)r0[sx + 1] << 8), t1 = (uint32_t)r1[sx] | ((uint32_t)r1[sx + 1] << 8);
+                const uint32_t a1 = (e[b] >> 16) & 0x7fff;
+                v |= resize_px((2048u - a1) | (a1 << 16), b0, b1, t0, t1) << (8 * b);
+            }
         }
+        out[g] = v;
     }
-    *reinterpret_cast<uint32_t *>(frame + L.off + (size_t)py * L.pitch + 4 * g4) = v;
+    *reinterpret_cast<uint4 *>(frame + L.off + (size_t)py * L.pitch + 16 * g16) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size_t frame_pitch, int batch, int stride,
@@ -119,10 +126,10 @@ orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size
             dim3 grid((L.pitch / 16 + block.x - 1) / block.x, L.ph, batch);
             k_pyr_level0<<<grid, block, 0, s>>>(d_images, frame_pitch, stride, e->d_pyr, e->pyr_frame_cap, L);
         } else {
-            const int cols4 = L.pitch / 4, total = cols4 * L.ph;
+            const int cols16 = L.pitch / 16, total = cols16 * L.ph;
             dim3 grid((total + 255) / 256, 1, batch);
             k_pyr_resize<<<grid, 256, 0, s>>>(e->d_pyr, e->pyr_frame_cap, e->lv[l - 1], L,
-                                              reinterpret_cast<const uint4 *>(e->d_rxt + L.rx_off), e->d_ryt + L.ry_off, cols4);
+                                              reinterpret_cast<const uint4 *>(e->d_rxt + L.rx_off), e->d_ryt + L.ry_off, cols16);
         }
         e->last_launches++;
     }
