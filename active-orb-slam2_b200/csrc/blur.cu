@@ -4,60 +4,81 @@
 // The halo is read from the 19-pixel pad of the pyramid buffer, which already is the REFLECT_101 image of the
 // interior (ORBextractor.cc:1122-1128), so no border logic is needed.  One CTA = one 64x32 output tile of one
 // level of one frame (tile table built on the host); the result goes to an un-padded copy of the level.
+//
+// Both passes are integer dot products: a row sum is two DP4A (4 + 3 taps on bytes picked from the row's words by funnel
+// shifts); the row sums are stored TRANSPOSED as u16, so that a column sum is four DP2A on (u16, u16) pairs of vertical
+// neighbours, and two vertically adjacent outputs share their four words.  Shared-memory pitches (19 and 21 words) are odd,
+// which keeps every access of the three phases free of bank conflicts.
 #include "orbx_internal.cuh"
 
 #define BLUR_THREADS 256
-#define BLUR_IN_W (ORBX_BLUR_TW + 8)   // 70 bytes needed, padded to 72 (18 words)
-#define BLUR_IN_H (ORBX_BLUR_TH + 6)
+#define BLUR_IN_H (ORBX_BLUR_TH + 6)            // 38 input rows
+#define BLUR_IN_WORDS 18                        // 70 bytes needed per row, 72 loaded
+#define BLUR_IN_PITCH 19                        // words
+#define BLUR_HT_PITCH 42                        // u16 per column of the transposed row sums (38 used)
 
 __global__ void __launch_bounds__(BLUR_THREADS)
 k_blur(const uint8_t *__restrict__ pyr, size_t pyr_frame, uint8_t *__restrict__ blur, size_t blur_frame,
        const OrbxLevel *__restrict__ lv, const OrbxBlurTile *__restrict__ tiles) {
-    __shared__ __align__(16) uint8_t in[BLUR_IN_H][BLUR_IN_W];
-    __shared__ __align__(16) uint16_t hb[BLUR_IN_H][ORBX_BLUR_TW];
+    __shared__ __align__(16) uint32_t in[BLUR_IN_H * BLUR_IN_PITCH];
+    __shared__ __align__(16) uint16_t ht[ORBX_BLUR_TW * BLUR_HT_PITCH];
+    __shared__ __align__(16) uint8_t ob[ORBX_BLUR_TH][ORBX_BLUR_TW];
     const OrbxBlurTile t = tiles[blockIdx.x];
     const OrbxLevel &L = lv[t.level];
     const int frame = blockIdx.y, tid = threadIdx.x;
     const int pitch = L.pitch, ph = L.ph;
-    // padded-buffer position of in[0][0]: column 19 + x0 - 3 (16-byte aligned because x0 % 64 == 0), row 19 + y0 - 3
+    // padded-buffer position of the first input byte: column 19 + x0 - 3 (16-byte aligned because x0 % 64 == 0), row 19 + y0 - 3
     const uint8_t *src = pyr + (size_t)frame * pyr_frame + L.off;
     const int gx = ORBX_EDGE + t.x0 - 3, gy = ORBX_EDGE + t.y0 - 3;
-    for (int i = tid; i < BLUR_IN_H * (BLUR_IN_W / 4); i += BLUR_THREADS) {
-        const int r = i / (BLUR_IN_W / 4), c = i - r * (BLUR_IN_W / 4);
+    for (int i = tid; i < BLUR_IN_H * BLUR_IN_WORDS; i += BLUR_THREADS) {
+        const int r = i / BLUR_IN_WORDS, c = i - r * BLUR_IN_WORDS;
         uint32_t v = 0;
         if (gy + r < ph && gx + 4 * c + 3 < pitch)
             v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(gy + r) * pitch + gx) + c);
-        reinterpret_cast<uint32_t *>(&in[r][0])[c] = v;
+        in[r * BLUR_IN_PITCH + c] = v;
     }
     __syncthreads();
-    // rows: 4 consecutive outputs per thread
-    for (int i = tid; i < BLUR_IN_H * (ORBX_BLUR_TW / 4); i += BLUR_THREADS) {
-        const int r = i / (ORBX_BLUR_TW / 4), c4 = (i - r * (ORBX_BLUR_TW / 4)) * 4;
-        const uint8_t *p = &in[r][c4];
-        int v[10];
+    // rows: thread = (input row r, quarter qx of the 64 columns), 16 sums; lanes run over r
+    if (tid < BLUR_IN_H * 4) {
+        const int qx = tid / BLUR_IN_H, r = tid - qx * BLUR_IN_H;
+        const uint32_t *p = in + r * BLUR_IN_PITCH + 4 * qx;
+        uint32_t w[6];
 #pragma unroll
-        for (int k = 0; k < 10; k++) v[k] = p[k];
+        for (int k = 0; k < 6; k++) w[k] = p[k];
+        uint16_t *dst = ht + (16 * qx) * BLUR_HT_PITCH + r;
+        const uint32_t T0 = 0x38302212u, T1 = 0x00122230u;      // bytes {18,34,48,56}, {48,34,18,0}
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            const int acc = 18 * (v[o] + v[o + 6]) + 34 * (v[o + 1] + v[o + 5]) + 48 * (v[o + 2] + v[o + 4]) + 56 * v[o + 3];
-            hb[r][c4 + o] = (uint16_t)acc;
+        for (int o = 0; o < 16; o++) {
+            const int wq = o >> 2, sh = 8 * (o & 3);
+            const uint32_t lo4 = __funnelshift_r(w[wq], w[wq + 1], sh), hi4 = __funnelshift_r(w[wq + 1], w[wq + 2], sh);
+            dst[o * BLUR_HT_PITCH] = (uint16_t)__dp4a(lo4, T0, __dp4a(hi4, T1, 0u));
         }
     }
     __syncthreads();
-    // columns: 4 consecutive outputs per thread, one 32-bit store
+    // columns: thread = (column x, quarter yq of the 32 rows), 8 outputs from 7 words of the transposed sums; lanes run over x
+    {
+        const int yq = tid >> 6, x = tid & 63;
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(ht + x * BLUR_HT_PITCH + 8 * yq);
+        uint32_t w[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) w[k] = p[k];
+        const uint32_t T0 = 0x38302212u, T1 = 0x00122230u;      // even row of a pair: (18,34 | 48,56), (48,34 | 18,0)
+        const uint32_t C0 = 0x30221200u, C1 = 0x12223038u;      // odd row of a pair:  (0,18 | 34,48), (56,48 | 34,18)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t a = __dp2a_lo(w[j], T0, __dp2a_hi(w[j + 1], T0, __dp2a_lo(w[j + 2], T1, __dp2a_hi(w[j + 3], T1, 0u))));
+            const uint32_t b = __dp2a_lo(w[j], C0, __dp2a_hi(w[j + 1], C0, __dp2a_lo(w[j + 2], C1, __dp2a_hi(w[j + 3], C1, 0u))));
+            ob[8 * yq + 2 * j][x] = (uint8_t)((a + 32768u) >> 16);
+            ob[8 * yq + 2 * j + 1][x] = (uint8_t)((b + 32768u) >> 16);
+        }
+    }
+    __syncthreads();
     uint8_t *dst = blur + (size_t)frame * blur_frame + L.boff;
     for (int i = tid; i < ORBX_BLUR_TH * (ORBX_BLUR_TW / 4); i += BLUR_THREADS) {
         const int y = i / (ORBX_BLUR_TW / 4), c4 = (i - y * (ORBX_BLUR_TW / 4)) * 4;
         const int oy = t.y0 + y, ox = t.x0 + c4;
         if (oy >= L.h || ox >= L.bpitch) continue;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-            const uint32_t acc = 18u * (hb[y][c4 + o] + hb[y + 6][c4 + o]) + 34u * (hb[y + 1][c4 + o] + hb[y + 5][c4 + o]) +
-                                 48u * (hb[y + 2][c4 + o] + hb[y + 4][c4 + o]) + 56u * hb[y + 3][c4 + o];
-            packed |= ((acc + 32768u) >> 16) << (8 * o);
-        }
-        *reinterpret_cast<uint32_t *>(dst + (size_t)oy * L.bpitch + ox) = packed;
+        *reinterpret_cast<uint32_t *>(dst + (size_t)oy * L.bpitch + ox) = *reinterpret_cast<const uint32_t *>(&ob[y][c4]);
     }
 }
 
