@@ -278,6 +278,55 @@ def bench_pose(local_rank, with_cpu, n_frames=64, n_obs=500, reps=10):
     return out
 
 
+def bench_bow(local_rank, with_cpu, n_frames=64, n_feat=1000, reps=20):
+    """DBoW2 transform of n_frames x n_feat descriptors against a full 10-ary, 6-level vocabulary (1.1 M nodes, the
+    shape of ORBvoc; random descriptors and weights because the reference's vocabulary file does not travel to the GPU box)."""
+    import torch
+    from orbx.vocabulary import ORBVocabulary, tree_from_parents
+    rng = np.random.default_rng(0)
+    k, L = 10, 6
+    n = sum(k ** l for l in range(1, L + 1))
+    parent = (np.arange(1, n + 1, dtype=np.int64) - 1) // k          # breadth-first ids: children of a node are consecutive
+    first_leaf = n - k ** L
+    is_leaf = np.arange(n) >= first_leaf
+    tree = tree_from_parents(parent.astype(np.int32), rng.integers(0, 256, (n, 32), dtype=np.uint8), rng.uniform(0.1, 9.0, n).astype(np.float32),
+                             is_leaf, k, L)
+    voc = ORBVocabulary(tree, max_features=n_feat, device=local_rank)
+    desc = rng.integers(0, 256, (n_frames, n_feat, 32), dtype=np.uint8)
+    d_desc = torch.from_numpy(desc).cuda()
+    d_cnt = torch.full((n_frames,), n_feat, dtype=torch.int32, device="cuda")
+    d_word = torch.zeros((n_frames, n_feat), dtype=torch.int32, device="cuda")
+    d_node = torch.zeros((n_frames, n_feat), dtype=torch.int32, device="cuda")
+    d_wt = torch.zeros((n_frames, n_feat), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    run = lambda: voc.transform_device(4, d_desc.data_ptr(), d_cnt.data_ptr(), 1, n_feat, n_feat, n_frames, d_word.data_ptr(), d_node.data_ptr(),
+                                       d_wt.data_ptr(), st.cuda_stream)
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(reps):
+        run()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"config": "%d frames x %d descriptors, vocabulary k = 10, L = 6 (%d nodes, %.0f MB of node descriptors), levelsup = 4, device-resident" % (
+               n_frames, n_feat, n + 1, 32 * n / 1e6),
+           "frames_per_s": n_frames / (ms * 1e-3), "ms_per_batch": ms, "kernel_launches_per_batch": voc.last_launches(),
+           "api": "orbx_vocabulary_transform_device (CUDA events)"}
+    if with_cpu:
+        from oracle import oracle_py as O
+        t0 = time.perf_counter()
+        for f in range(4):
+            w_, n_, _ = O.bow_transform(tree, desc[f], 4)
+            assert np.array_equal(w_, d_word[f].cpu().numpy()) and np.array_equal(n_, d_node[f].cpu().numpy()), "bow: GPU and oracle disagree"
+        out["cpu_frames_per_s"] = 4 / (time.perf_counter() - t0)
+        out["cpu"] = "C oracle, 1 thread, 4 frames; identical word and node ids"
+    voc.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -593,10 +642,11 @@ def main():
             lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
         op.close()
 
-    stereo = pose = None
+    stereo = pose = bow = None
     if rank == 0:
         stereo = bench_stereo(local_rank, not args.no_cpu)
         pose = bench_pose(local_rank, not args.no_cpu)
+        bow = bench_bow(local_rank, not args.no_cpu)
 
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
@@ -641,6 +691,7 @@ def main():
             "lba": lba,
             "stereo": stereo,
             "pose": pose,
+            "bow": bow,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
