@@ -49,6 +49,10 @@ ALGO_BYTES = {
     "describe": NFEAT * (749 + 512 + 60),          # patch + 512 samples + outputs per keypoint
 }
 FRAME_ALGO_BYTES = W * H + PYR_PADDED + NFEAT * 60   # 1,525,212 B
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 64, from the one `ncu --set full` capture summarised in
+# profiles/r1_h_full.txt (the pyramid figure is the sum of its 8 launches)
+NCU_TRAFFIC_B64 = {"fast": 63.111680e6 + 1.766656e6, "blur": 71.203584e6 + 31.235584e6, "describe": 121.449728e6 + 5.571584e6,
+                   "pyramid": 85.3e6 + 0.03e6, "quadtree": 3.002880e6 + 0.052736e6}
 
 
 def peaks():
@@ -682,7 +686,8 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "launches_per_step": n_launch_dom,
+                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 else None, "traffic_source": "profiles/r1_h_full.txt (ncu --set full, bytes per launch at batch 64)",
+                         "peak_source": peak_src, "launches_per_step": n_launch_dom,
                          "algorithmic_bytes_per_frame": ALGO_BYTES[dom], "ms_per_step": dom_ms,
                          "whole_step": {"algorithmic_bytes_per_frame": FRAME_ALGO_BYTES,
                                         "achieved": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9,
