@@ -98,5 +98,10 @@ def _declare(L):
     L.orbx_vocabulary_transform_host.argtypes = [vp, vp, i, i, vp, vp, vp]
     L.orbx_vocabulary_transform_device.argtypes = [vp, i, vp, vp, i, i, i, i, vp, vp, vp, vp]
     L.orbx_vocabulary_last_launches.argtypes = [vp]
+    L.orbx_mappoints_create.argtypes = [C.POINTER(vp), i, i, i]
+    L.orbx_mappoints_destroy.restype = None
+    L.orbx_mappoints_destroy.argtypes = [vp]
+    L.orbx_mappoints_distinctive_host.argtypes = [vp, i, vp, vp, vp, vp]
+    L.orbx_mappoints_last_launches.argtypes = [vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

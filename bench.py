@@ -29,9 +29,17 @@ for p in (ROOT, os.path.join(ROOT, "active-orb-slam2_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints exactly one line on stdout.  Native libraries write there too (NCCL prints its version banner at every
+# NCCL_DEBUG level from VERSION up, and this image sets VERSION), so file descriptor 1 is pointed at stderr for the whole run
+# and the JSON line goes to the saved original descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -178,7 +186,7 @@ def run_reference(args, rank):
     v, n_frames, total = cpu_path(frames, total_budget, cores)
     budget = total / max(args.steps, 1)
     sample = "%d steps x %.1f s of G-rect VGA frames (extract + SearchByProjection vs predecessor) on %d host threads, one oracle extractor per thread" % (args.steps, budget, cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -188,7 +196,7 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference itself cannot be built here (needs OpenCV/Eigen/Pangolin); this is the dependency-free C oracle of its "
                 "path with scalar restatements of OpenCV's SIMD primitives",
-    }))
+    })
 
 
 def bench_stereo(local_rank, with_cpu, n_pairs=32, reps=20):
@@ -703,7 +711,7 @@ def main():
             fps, n, dt = cpu_path(hnp[:64], 12.0, cores)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": "%d G-rect VGA frames (extract + SearchByProjection vs predecessor) in %.1f s on %d host threads (C oracle, one extractor per thread)" % (n, dt, cores)}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -431,6 +431,21 @@ orbx_status orbx_vocabulary_transform_device(orbx_vocabulary *h, int levelsup, c
                                              double *d_weight, void *stream);
 int orbx_vocabulary_last_launches(const orbx_vocabulary *h);
 
+/* =====================================================================================================
+ * MapPoint::ComputeDistinctiveDescriptors  (reference include/MapPoint.h:73, src/MapPoint.cc:275-340),
+ * for many map points in one launch (LocalMapping calls it per new / fused point, LocalMapping.cc:195, :441, :651-667).
+ * The adapter gathers, per map point, the descriptors of its non-bad observations in the order the reference pushes them
+ * into vDescriptors (:293-299) and afterwards sets mDescriptor = vDescriptors[best_idx].clone() under mMutexFeatures.
+ * ===================================================================================================== */
+typedef struct orbx_mappoints orbx_mappoints;
+orbx_status orbx_mappoints_create(orbx_mappoints **out, int max_points, int max_descriptors, int device);
+void orbx_mappoints_destroy(orbx_mappoints *h);
+/* point p owns descriptors start[p] .. start[p+1] of desc (32 bytes each); best_idx[p] = the descriptor with the least
+ * median Hamming distance to the point's other descriptors (first among equals), -1 for an empty set; best_median may be NULL */
+orbx_status orbx_mappoints_distinctive_host(orbx_mappoints *h, int n_points, const int32_t *start, const uint8_t *desc,
+                                            int32_t *best_idx, int32_t *best_median);
+int orbx_mappoints_last_launches(const orbx_mappoints *h);
+
 #ifdef __cplusplus
 }
 #endif

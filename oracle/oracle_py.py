@@ -527,3 +527,17 @@ def bow_transform(voc, desc, levelsup=4):
     word, node, wt = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
     L.orbo_bow_transform(C.byref(V), _p(d), n, levelsup, _p(word), _p(node), _p(wt))
     return word[:n], node[:n], wt[:n]
+
+
+# ---- MapPoint::ComputeDistinctiveDescriptors (oracle/mappoint_oracle.c) -----------------------------------------
+def distinctive_descriptors(start, desc):
+    """start[n+1] CSR over desc[total,32] -> (best_idx[n], best_median[n])"""
+    L = lib()
+    L.orbo_distinctive_descriptors.restype = None
+    L.orbo_distinctive_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    st = np.ascontiguousarray(start, np.int32)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(st) - 1
+    bi, bm = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    L.orbo_distinctive_descriptors(n, _p(st), _p(d), _p(bi), _p(bm))
+    return bi[:n], bm[:n]

@@ -186,6 +186,11 @@ typedef struct {
 void orbo_bow_transform(const orbo_vocabulary *V, const uint8_t *desc, int n, int levelsup, int32_t *word, int32_t *node,
                         double *weight);
 
+/* ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:275-340), many map points at once ---- */
+/* point p owns descriptors start[p] .. start[p+1] of desc (32 bytes each, in the order the reference pushes them into
+ * vDescriptors); best_idx[p] = index inside the point's own set (-1 for an empty set); best_median optional */
+void orbo_distinctive_descriptors(int n_points, const int32_t *start, const uint8_t *desc, int32_t *best_idx, int32_t *best_median);
+
 /* ---- pose-only optimisation (src/Optimizer.cc:239-452 + g2o unary edges) ---- */
 typedef struct {
     int32_t n;                   /* keypoints with a map point (nInitialCorrespondences) */
