@@ -17,7 +17,8 @@
 __device__ __align__(16) int8_t g_pattern[1024] = {
 #include "orb_pattern.inc"
 };
-__device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:454-469
+// umax of the r = 15 circular patch, ORBextractor.cc:454-469 (compile-time, so that the row loop unrolls into predicated loads)
+__device__ constexpr int k_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 // cv::fastAtan2 (OpenCV mathfuncs_core atan_f32), degrees
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -100,14 +101,17 @@ k_describe(const uint8_t *__restrict__ pyr, size_t pyr_frame, const uint8_t *__r
     const int au = u < 0 ? -u : u;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-#pragma unroll 1
+        const uint8_t *col = center + u;
+        int colsum = 0;
+#pragma unroll
         for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = center[v * pitch + u];
-                m10 += u * val;
+            if (au <= k_umax[v < 0 ? -v : v]) {
+                const int val = col[v * pitch];
+                colsum += val;
                 m01 += v * val;
             }
         }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -103,5 +103,7 @@ def _declare(L):
     L.orbx_mappoints_destroy.argtypes = [vp]
     L.orbx_mappoints_distinctive_host.argtypes = [vp, i, vp, vp, vp, vp]
     L.orbx_mappoints_last_launches.argtypes = [vp]
+    L.orbx_frustum_host.argtypes = [vp, i, vp, vp, vp, i]
+    L.orbx_frustum_device.argtypes = [vp, i, vp, vp, vp, vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -433,3 +433,31 @@ def descriptors_near_words(rng, tree, n, flip=20):
     leaves = np.nonzero(tree["word_id"] >= 0)[0]
     pick = rng.choice(leaves, n)
     return flip_bits(rng, tree["desc"][pick].copy(), np.full(n, flip))
+
+
+def frustum_scene(seed, n=4000, w=640, h=480, nlevels=8, sf=1.2):
+    """A frame pose and n map points for Frame::isInFrustum: points scattered around the camera (in front, behind, outside the
+    image, too near / too far for their scale-invariance range, seen from behind), as float records.  Returns
+    (frame dict of orbx_frustum_frame fields, structured point array fields as a dict of arrays)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf, _ = TUM1_K
+    R = (_rot(1, rng.uniform(-0.5, 0.5)) @ _rot(0, rng.uniform(-0.2, 0.2))).astype(np.float32)
+    t = rng.uniform(-1, 1, 3).astype(np.float32)
+    Ow = (-R.T.astype(np.float64) @ t.astype(np.float64)).astype(np.float32)
+    frame = dict(Rcw=R.reshape(9), tcw=t, Ow=Ow, fx=fx, fy=fy, cx=cx, cy=cy, bf=bf, min_x=0.0, max_x=float(w), min_y=0.0, max_y=float(h),
+                 log_scale_factor=np.float32(np.log(np.float32(sf))), n_levels=nlevels, viewing_cos_limit=0.5)
+    Pc = np.stack([rng.uniform(-6, 6, n), rng.uniform(-4, 4, n), rng.uniform(-2, 12, n)], 1)
+    P = ((Pc - t.astype(np.float64)) @ R.astype(np.float64)).astype(np.float32)        # R^T (Pc - t)
+    d = np.linalg.norm(P.astype(np.float64) - Ow, axis=1)
+    ref_d = d * rng.uniform(0.4, 2.5, n)                                             # distance at which the point was created
+    lvl = rng.integers(0, nlevels, n)
+    max_d = (ref_d * np.float32(sf) ** lvl).astype(np.float32)                      # MapPoint::UpdateNormalAndDepth, MapPoint.cc:413-415
+    min_d = (max_d / np.float32(sf) ** (nlevels - 1)).astype(np.float32)
+    view = (Ow - P.astype(np.float64)); view /= np.maximum(np.linalg.norm(view, axis=1, keepdims=True), 1e-9)
+    nrm = -view + rng.normal(0, 0.6, (n, 3))                                         # normals roughly towards ... away from the camera
+    flip = rng.random(n) < 0.15
+    nrm[flip] = -nrm[flip]
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-9)
+    pts = dict(x=P[:, 0], y=P[:, 1], z=P[:, 2], nx=nrm[:, 0].astype(np.float32), ny=nrm[:, 1].astype(np.float32), nz=nrm[:, 2].astype(np.float32),
+               min_distance=min_d, max_distance=max_d, skip=(rng.random(n) < 0.05).astype(np.uint8), blocks=(rng.random(n) < 0.8).astype(np.uint8))
+    return frame, pts

@@ -446,6 +446,36 @@ orbx_status orbx_mappoints_distinctive_host(orbx_mappoints *h, int n_points, con
                                             int32_t *best_idx, int32_t *best_median);
 int orbx_mappoints_last_launches(const orbx_mappoints *h);
 
+/* =====================================================================================================
+ * Frame::isInFrustum  (reference include/Frame.h:80, src/Frame.cc:298-354) for all points of the local
+ * map at once (Tracking::SearchLocalPoints, Tracking.cc:1085-1103).  Produces the orbx_track_point records that
+ * orbx_match_projection_points_* consume (mbTrackInView, mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos).
+ * pad[0] of an output record is 1 when the predicted level could not be decided safely on the device (logf within a last bit
+ * of a level boundary): the adapter then sets level = pMP->PredictScale(cv::norm(P - mOw), this) for that point.
+ * ===================================================================================================== */
+typedef struct {
+    float x, y, z;               /* pMP->GetWorldPos() */
+    float nx, ny, nz;            /* pMP->GetNormal() */
+    float min_distance, max_distance;   /* mfMinDistance, mfMaxDistance (the 0.8 / 1.2 factors of the getters are applied inside) */
+    uint8_t skip;                /* pMP->isBad() || pMP->mnLastFrameSeen == mCurrentFrame.mnId: not evaluated, in_view = 0 */
+    uint8_t blocks;              /* Observations() > 0, copied to the output record */
+    uint8_t pad[2];
+} orbx_frustum_point;
+typedef struct {
+    float Rcw[9], tcw[3], Ow[3]; /* mRcw (row-major), mtcw, mOw */
+    float fx, fy, cx, cy, bf;    /* bf = mbf */
+    float min_x, max_x, min_y, max_y;   /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+    float log_scale_factor;      /* mfLogScaleFactor */
+    int32_t n_levels;            /* mnScaleLevels */
+    float viewing_cos_limit;     /* 0.5 at the reference's call site */
+} orbx_frustum_frame;
+/* host pointers, synchronous, no handle (stream-ordered temporary buffers); *n_ambiguous = number of records with pad[0] = 1 */
+orbx_status orbx_frustum_host(const orbx_frustum_frame *F, int n, const orbx_frustum_point *pts, orbx_track_point *out,
+                              int32_t *n_ambiguous, int device);
+/* device pointers; only enqueues on `stream` (d_n_ambiguous: one int32 on the device) */
+orbx_status orbx_frustum_device(const orbx_frustum_frame *F, int n, const orbx_frustum_point *d_pts, orbx_track_point *d_out,
+                                int32_t *d_n_ambiguous, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

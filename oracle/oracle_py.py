@@ -541,3 +541,30 @@ def distinctive_descriptors(start, desc):
     bi, bm = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
     L.orbo_distinctive_descriptors(n, _p(st), _p(d), _p(bi), _p(bm))
     return bi[:n], bm[:n]
+
+
+# ---- Frame::isInFrustum (oracle/frustum_oracle.c) ---------------------------------------------------------------
+FRUSTUM_POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                                ("min_distance", "<f4"), ("max_distance", "<f4"), ("skip", "u1"), ("blocks", "u1"), ("pad", "u1", (2,))])
+FRUSTUM_FRAME_DTYPE = np.dtype([("Rcw", "<f4", (9,)), ("tcw", "<f4", (3,)), ("Ow", "<f4", (3,)), ("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"),
+                                ("cy", "<f4"), ("bf", "<f4"), ("min_x", "<f4"), ("max_x", "<f4"), ("min_y", "<f4"), ("max_y", "<f4"),
+                                ("log_scale_factor", "<f4"), ("n_levels", "<i4"), ("viewing_cos_limit", "<f4")])
+assert FRUSTUM_POINT_DTYPE.itemsize == 36 and FRUSTUM_FRAME_DTYPE.itemsize == 108
+
+
+def is_in_frustum(frame, pts):
+    """frame: FRUSTUM_FRAME_DTYPE record, pts: FRUSTUM_POINT_DTYPE array -> TRACK_POINT_DTYPE array"""
+    L = lib()
+    L.orbo_is_in_frustum.restype = None
+    L.orbo_is_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    fr = np.ascontiguousarray(frame, FRUSTUM_FRAME_DTYPE).reshape(1)
+    p = np.ascontiguousarray(pts, FRUSTUM_POINT_DTYPE)
+    out = np.zeros(max(len(p), 1), TRACK_POINT_DTYPE)
+    L.orbo_is_in_frustum(_p(fr), len(p), _p(p), _p(out))
+    return out[:len(p)]
+
+
+def predict_scale(max_distance, dist, log_scale_factor, n_levels):
+    L = lib()
+    L.orbo_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+    return L.orbo_predict_scale(max_distance, dist, log_scale_factor, n_levels)

@@ -191,6 +191,19 @@ void orbo_bow_transform(const orbo_vocabulary *V, const uint8_t *desc, int n, in
  * vDescriptors); best_idx[p] = index inside the point's own set (-1 for an empty set); best_median optional */
 void orbo_distinctive_descriptors(int n_points, const int32_t *start, const uint8_t *desc, int32_t *best_idx, int32_t *best_median);
 
+/* ---- Frame::isInFrustum (src/Frame.cc:298-354) ---- */
+typedef struct {
+    float x, y, z, nx, ny, nz, min_distance, max_distance;   /* GetWorldPos, GetNormal, mfMinDistance, mfMaxDistance */
+    uint8_t skip, blocks, pad[2];
+} orbo_frustum_point;
+typedef struct {
+    float Rcw[9], tcw[3], Ow[3], fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y, log_scale_factor;
+    int32_t n_levels;
+    float viewing_cos_limit;
+} orbo_frustum_frame;
+void orbo_is_in_frustum(const orbo_frustum_frame *F, int n, const orbo_frustum_point *pts, orbo_track_point *out);
+int orbo_predict_scale(float max_distance, float dist, float log_scale_factor, int n_levels);
+
 /* ---- pose-only optimisation (src/Optimizer.cc:239-452 + g2o unary edges) ---- */
 typedef struct {
     int32_t n;                   /* keypoints with a map point (nInitialCorrespondences) */
