@@ -339,6 +339,44 @@ def bench_bow(local_rank, with_cpu, n_frames=64, n_feat=1000, reps=20):
     return out
 
 
+def bench_sequence(local_rank, with_cpu, n_frames=40):
+    """Config C4 in miniature: single-stream stereo tracking, one frame at a time through the host entry points, as the
+    adapter would call them from Tracking: extract L + R -> ComputeStereoMatches -> SearchByProjection(Cur, Last) -> PoseOptimization.
+    Latency-bound by design (batch 1, ~20 launches and ~15 small copies per frame); tools/replay.py is the chain."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import replay
+    seq = replay.StereoSequence(seed=1)
+    imgs = [seq.images(t) for t in range(n_frames)]
+    seq.images = lambda t: imgs[t]                        # rendering is not part of the measurement
+    gpu = replay.GpuBackend(device=local_rank)
+    rng = np.random.default_rng(7)
+    last = None
+    for t in range(3):                                    # warm-up
+        last = replay.track_frame(gpu, seq, t, last, rng)
+    t0 = time.perf_counter()
+    inl = []
+    for t in range(3, n_frames):
+        last = replay.track_frame(gpu, seq, t, last, rng)
+        inl.append(last["n_inliers"])
+    dt = time.perf_counter() - t0
+    err = float(np.linalg.norm(last["Tcw"][:3, 3] - seq.true_pose(n_frames - 1)[:3, 3]))
+    out = {"config": "%d rendered 640x480 stereo frames, 1000 features per image, camera translating 2 cm per frame; batch 1, host entry points" % (n_frames - 3),
+           "frames_per_s": (n_frames - 3) / dt, "ms_per_frame": 1e3 * dt / (n_frames - 3), "inliers_per_frame": float(np.mean(inl)),
+           "final_position_error_m": err,
+           "api": "orbx_extractor_run_host x2, orbx_stereo_matches_host, orbx_match_projection_frame_host, orbx_pose_optimize_host (+ numpy bookkeeping)"}
+    gpu.close()
+    if with_cpu:
+        orc = replay.OracleBackend()
+        rng = np.random.default_rng(7)
+        last = None
+        t0 = time.perf_counter()
+        for t in range(8):
+            last = replay.track_frame(orc, seq, t, last, rng)
+        out["cpu_frames_per_s"] = 8 / (time.perf_counter() - t0)
+        out["cpu"] = "the same chain on the C oracle, 1 thread (the reference runs the two extractors on two threads), 8 frames"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -654,11 +692,12 @@ def main():
             lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
         op.close()
 
-    stereo = pose = bow = None
+    stereo = pose = bow = sequence = None
     if rank == 0:
         stereo = bench_stereo(local_rank, not args.no_cpu)
         pose = bench_pose(local_rank, not args.no_cpu)
         bow = bench_bow(local_rank, not args.no_cpu)
+        sequence = bench_sequence(local_rank, not args.no_cpu)
 
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
@@ -705,6 +744,7 @@ def main():
             "stereo": stereo,
             "pose": pose,
             "bow": bow,
+            "sequence": sequence,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
