@@ -1,0 +1,61 @@
+// Frame::ComputeStereoMatches and Frame::ComputeBoW on top of the orbx C ABI (include/orbx.h); include/Frame.h stays as it is.
+//
+// Build: compile next to the reference's src/Frame.cc with the definitions of these two members removed there (or guarded
+// by #ifndef ORBX_ADAPTER).  orbxHandle() is exported by adapter/ORBextractor_orbx.cc; orbxVocabulary() returns the device copy
+// of the vocabulary, created once from the file System.cc loads.
+#include "Frame.h"
+
+#include <orbx.h>
+
+#include <stdexcept>
+
+namespace ORB_SLAM2
+{
+
+orbx_extractor* orbxHandle(const ORBextractor* e);
+orbx_vocabulary* orbxVocabulary(const ORBVocabulary* voc);
+
+namespace
+{
+void check(orbx_status s)
+{
+    if (s != ORBX_OK)
+        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
+}
+} // namespace
+
+// replaces Frame.cc:495-669: both pyramids are read where the two extractors left them on the device
+void Frame::ComputeStereoMatches()
+{
+    mvuRight = std::vector<float>(N, -1.0f);
+    mvDepth = std::vector<float>(N, -1.0f);
+    thread_local orbx_stereo* st = nullptr;
+    if (!st)
+        check(orbx_stereo_create(&st, 8192, 1, 0));
+    static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint is the 28-byte record of orbx_keypoint");
+    int32_t kept = 0;
+    check(orbx_stereo_matches_host(st, orbxHandle(mpORBextractorLeft), 0, orbxHandle(mpORBextractorRight), 0,
+                                   reinterpret_cast<const orbx_keypoint*>(mvKeys.data()), mDescriptors.data, N,
+                                   reinterpret_cast<const orbx_keypoint*>(mvKeysRight.data()), mDescriptorsRight.data,
+                                   (int)mvKeysRight.size(), mbf, mb, mvuRight.data(), mvDepth.data(), &kept));
+}
+
+// replaces Frame.cc:286-293: the tree descent of every descriptor runs on the device, the map bookkeeping of
+// TemplatedVocabulary::transform (TemplatedVocabulary.h:1160-1200) stays here, in feature order
+void Frame::ComputeBoW()
+{
+    if (!mBowVec.empty())
+        return;
+    std::vector<int32_t> word(N), node(N);
+    std::vector<double> weight(N);
+    check(orbx_vocabulary_transform_host(orbxVocabulary(mpORBvocabulary), mDescriptors.data, N, 4, word.data(), node.data(), weight.data()));
+    for (int i = 0; i < N; i++)
+        if (weight[i] > 0)
+        {
+            mBowVec.addWeight(word[i], weight[i]);
+            mFeatVec.addFeature(node[i], i);
+        }
+    mBowVec.normalize(DBoW2::L1);                    // ORBvoc.txt / ORBvoc.bin: TF_IDF weighting, L1 scoring
+}
+
+} // namespace ORB_SLAM2

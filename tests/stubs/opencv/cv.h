@@ -8,6 +8,17 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <cmath>
+#include <cstdlib>
+#include <sstream>
+#include <fstream>
+#include <iostream>
+#include <algorithm>
+#include <numeric>
+#include <limits>
+#include <map>
+#include <set>
+#include <list>
 #define CV_8U 0
 #define CV_8UC1 0
 #define CV_32F 5
@@ -38,6 +49,24 @@ struct Mat {
 };
 struct _InputArray { _InputArray() {} _InputArray(const Mat &) {} bool empty() const { return true; } Mat getMat() const { return Mat(); } };
 struct _OutputArray { _OutputArray() {} _OutputArray(Mat &) {} void release() const {} };
+struct FileNode {
+    FileNode operator[](const char *) const { return *this; }
+    FileNode operator[](const std::string &) const { return *this; }
+    FileNode operator[](int) const { return *this; }
+    size_t size() const { return 0; }
+    template <class T> operator T() const { return T(); }
+    template <class T> void operator>>(T &) const {}
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string &, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    template <class T> FileStorage &operator<<(const T &) { return *this; }
+};
 typedef const _InputArray &InputArray;
 typedef const _OutputArray &OutputArray;
 }
