@@ -48,15 +48,34 @@ METRIC = "frames/sec ORB extract+match (640x480, 1000 kpts)"
 # SURVEY.md §8(d) / DESIGN.md: compulsory bytes per VGA frame of each stage (level sizes of the 8-level pyramid)
 PYR_PADDED = 1158012
 PYR_INTERIOR = 950532
-ALGO_BYTES = {
-    "match": 2 * NFEAT * (32 + 24) + NFEAT * 8,    # both descriptor sets + points/keypoints in, match array out (~104 KB)
-    "pyramid": W * H + PYR_PADDED,                 # read the frame, write the padded pyramid
-    "fast": PYR_INTERIOR,                          # read every level once (+ a few KB of candidates)
-    "quadtree": 0,
-    "blur": 2 * PYR_INTERIOR,                      # read + write every level
-    "describe": NFEAT * (749 + 512 + 60),          # patch + 512 samples + outputs per keypoint
-}
-FRAME_ALGO_BYTES = W * H + PYR_PADDED + NFEAT * 60   # 1,525,212 B
+ALGO_BYTES, FRAME_ALGO_BYTES = {}, 0
+
+
+def set_workload(w, h, nfeat):
+    """byte model of SURVEY §8(d) for a w x h frame with nfeat features (pyramid sizes by the reference's float formulas)"""
+    global W, H, NFEAT, PYR_PADDED, PYR_INTERIOR, FRAME_ALGO_BYTES
+    W, H, NFEAT = w, h, nfeat
+    sf, PYR_PADDED, PYR_INTERIOR = np.float32(1.0), 0, 0
+    for l in range(NLEVELS):
+        if l:
+            sf = np.float32(np.float64(sf) * np.float64(np.float32(SCALE)))          # mvScaleFactor[i] = mvScaleFactor[i-1] * scaleFactor
+        inv = np.float32(1.0) / sf
+        lw, lh = int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))   # cvRound(cols * inv), ORBextractor.cc:1112
+        PYR_PADDED += (lw + 38) * (lh + 38)
+        PYR_INTERIOR += lw * lh
+    ALGO_BYTES.update({
+        "match": 2 * NFEAT * (32 + 24) + NFEAT * 8,    # both descriptor sets + points/keypoints in, match array out (SURVEY §8d: ~104 KB)
+        "pyramid": W * H + PYR_PADDED,                 # read the frame, write the padded pyramid
+        "fast": PYR_INTERIOR,                          # read every level once (+ a few KB of candidates)
+        "quadtree": 0,
+        "blur": 2 * PYR_INTERIOR,                      # read + write every level
+        "describe": NFEAT * (749 + 512 + 60),          # patch + 512 samples + outputs per keypoint
+    })
+    FRAME_ALGO_BYTES = W * H + PYR_PADDED + NFEAT * 60   # SURVEY §8(d): 1,525,212 B for VGA / 1000
+
+
+set_workload(W, H, NFEAT)
+assert (PYR_PADDED, PYR_INTERIOR, FRAME_ALGO_BYTES) == (1158012, 950532, 1525212)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 64, from the one `ncu --set full` capture summarised in
 # profiles/r1_h_full.txt (the pyramid figure is the sum of its 8 launches)
 NCU_TRAFFIC_B64 = {"fast": 63.111680e6 + 1.766656e6, "blur": 71.203584e6 + 31.235584e6, "describe": 121.449728e6 + 5.571584e6,
@@ -385,7 +404,14 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--width", type=int, default=W, help="frame width (default: the VGA workload BASELINE.json's metric is quoted on)")
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--features", type=int, default=NFEAT)
+    ap.add_argument("--extract-only", action="store_true", help="other frame shapes: time the extractor + matcher loop only (no LocalBA / stereo / ... sections)")
     args = ap.parse_args()
+    default_workload = (args.width, args.height, args.features) == (W, H, NFEAT)
+    if not default_workload:
+        set_workload(args.width, args.height, args.features)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -636,7 +662,8 @@ def main():
 
     # ---- LocalBA (20 keyframes x 3000 points x ~12k edges, 5 + 10 iterations), rank 0 only ----
     lba = None
-    if rank == 0:
+    side_sections = rank == 0 and default_workload and not args.extract_only
+    if side_sections:
         from orbx.optimizer import Optimizer
         prob = synth.lba_problem(0, n_kf=20, n_pts=3000, stereo=False, n_fixed=1)
         op = Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank)
@@ -693,7 +720,7 @@ def main():
         op.close()
 
     stereo = pose = bow = sequence = None
-    if rank == 0:
+    if side_sections:
         stereo = bench_stereo(local_rank, not args.no_cpu)
         pose = bench_pose(local_rank, not args.no_cpu)
         bow = bench_bow(local_rank, not args.no_cpu)
@@ -717,8 +744,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "C2 extract+match: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7; each frame matched against its "
-                                   "predecessor with SearchByProjection(Cur, Last, th=7) (%.0f matches/frame)" % matches_per_frame,
+            "config": {"workload": "C2 extract+match: %dx%d G-rect frames, %d features, 8 levels, th 20/7; each frame matched against its "
+                                   "predecessor with SearchByProjection(Cur, Last, th=7) (%.0f matches/frame)" % (W, H, NFEAT, matches_per_frame),
                        "batch_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective on the data path" % world,
                        "l2": "inputs cycle through a %d-frame pool (%.0f MB > 126 MB L2); per-step working set %.0f MB" % (
                            npool * B, npool * B * W * H / 1e6, B * 3.3),
@@ -733,7 +760,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 else None, "traffic_source": "profiles/r1_h_full.txt (ncu --set full, bytes per launch at batch 64)",
+                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 and default_workload else None, "traffic_source": "profiles/r1_h_full.txt (ncu --set full, bytes per launch at batch 64)",
                          "peak_source": peak_src, "launches_per_step": n_launch_dom,
                          "algorithmic_bytes_per_frame": ALGO_BYTES[dom], "ms_per_step": dom_ms,
                          "whole_step": {"algorithmic_bytes_per_frame": FRAME_ALGO_BYTES,
