@@ -10,8 +10,10 @@
 // fixed point equals the sequential result; conflicts are rare and 2-3 sweeps are typical.
 // Float arithmetic that decides a comparison is written with explicit round-to-nearest intrinsics in the
 // reference's operation order (cv::Mat products are sequential float multiply-adds without FMA).
+#include <cooperative_groups.h>
 #include "orbx_internal.cuh"
 #include "block_scan.cuh"
+namespace cg = cooperative_groups;
 
 #define M_THREADS 1024
 #define M_WARPS (M_THREADS / 32)
@@ -29,6 +31,8 @@ struct orbx_matcher {
     int *d_minclaim;  // [jobs][2][max_kp]
     int *d_owner;     // [jobs][max_kp]
     int *d_sweeps;    // [jobs] sweeps the claim resolution took (diagnostics)
+    int *d_novf;      // [jobs] overflow-list counters of the clustered frame kernel (zero between launches)
+    int sm_count;
     int2 *d_cand;     // [jobs][M_CAND][max_pts] candidate (key, pack) per point, entry-major
     int *d_lcount;    // [jobs][2][max_pts] candidates per point; overflow list
     // staging of the _host entry points (one job)
@@ -216,18 +220,17 @@ __device__ int eval_warp(const Eval &ev, int i, const int *minclaim) {
 // The reference's sequential claim semantics as a fixed point.  Candidate lists are built once (they do not depend
 // on claims); every sweep then lets each point pick among the candidates not claimed by a smaller index in the
 // previous sweep, until no choice changes.
+// Candidate lists of the points part, part + nparts, ... (warp per point).  With nparts > 1 the CTAs of a thread-block cluster
+// share the work of one job: the lists, their lengths and the overflow list live in global memory, the overflow counter is
+// *novf_global (zero on entry, reset by the caller after use).
 template <class Eval>
-__device__ void resolve_claims(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int2 *cand,
-                               int *lcount, int *ovf, int max_pts, int max_kp, MatchShared &sh, const Eval &ev, int &final_buf) {
+__device__ void build_candidates(int n_pts, int2 *cand, int *lcount, int *ovf, int max_pts, MatchShared &sh, const Eval &ev,
+                                 int part, int nparts, int *novf_global) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    int *mc[2] = {minclaim2, minclaim2 + max_kp};
-    int *ch[2] = {choice2, choice2 + max_pts};
-    for (int k = tid; k < n_kp; k += M_THREADS) mc[0][k] = (claimed && claimed[k]) ? -1 : 0x7fffffff;
-    for (int i = tid; i < n_pts; i += M_THREADS) ch[0][i] = -2;
     if (tid == 0) sh.novf = 0;
     __syncthreads();
-    for (int i = warp; i < n_pts; i += M_WARPS) {
+    for (int i = warp + part * M_WARPS; i < n_pts; i += M_WARPS * nparts) {
         int cnt = 0;
         ev.candidates(i, [&](bool valid, unsigned key, int pack) {
             const unsigned m = __ballot_sync(0xffffffffu, valid);
@@ -237,11 +240,32 @@ __device__ void resolve_claims(int n_kp, int n_pts, const uint8_t *claimed, int 
         });
         if (lane == 0) {
             lcount[i] = cnt;
-            if (cnt > M_CAND) ovf[atomicAdd(&sh.novf, 1)] = i;
+            if (cnt > M_CAND) ovf[atomicAdd(novf_global ? novf_global : &sh.novf, 1)] = i;
         }
     }
     __syncthreads();
-    const int novf = sh.novf;
+}
+
+template <class Eval>
+__device__ void run_sweeps(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int2 *cand,
+                           int *lcount, int *ovf, int max_pts, int max_kp, MatchShared &sh, const Eval &ev, int &final_buf, int novf);
+
+template <class Eval>
+__device__ void resolve_claims(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int2 *cand,
+                               int *lcount, int *ovf, int max_pts, int max_kp, MatchShared &sh, const Eval &ev, int &final_buf) {
+    build_candidates(n_pts, cand, lcount, ovf, max_pts, sh, ev, 0, 1, nullptr);
+    run_sweeps(n_kp, n_pts, claimed, choice2, minclaim2, cand, lcount, ovf, max_pts, max_kp, sh, ev, final_buf, sh.novf);
+}
+
+template <class Eval>
+__device__ void run_sweeps(int n_kp, int n_pts, const uint8_t *claimed, int *choice2, int *minclaim2, int2 *cand,
+                           int *lcount, int *ovf, int max_pts, int max_kp, MatchShared &sh, const Eval &ev, int &final_buf, int novf) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *mc[2] = {minclaim2, minclaim2 + max_kp};
+    int *ch[2] = {choice2, choice2 + max_pts};
+    for (int k = tid; k < n_kp; k += M_THREADS) mc[0][k] = (claimed && claimed[k]) ? -1 : 0x7fffffff;
+    for (int i = tid; i < n_pts; i += M_THREADS) ch[0][i] = -2;
+    __syncthreads();
     int cur = 0, sweeps = 0;
     for (int sweep = 0; sweep <= n_pts + 1; sweep++) {
         const int nxt = cur ^ 1;
@@ -330,12 +354,14 @@ struct FrameEval {
 __global__ void __launch_bounds__(M_THREADS)
 k_match_frame(const orbx_frame_match_job *__restrict__ jobs, int *__restrict__ choice_all, int *__restrict__ minclaim_all,
               int *__restrict__ owner_all, int *__restrict__ sweeps_all, int2 *__restrict__ cand_all, int *__restrict__ lcount_all,
-              int max_kp, int max_pts) {
+              int *__restrict__ novf_all, int max_kp, int max_pts) {
     extern __shared__ __align__(16) int dyn[];
     __shared__ MatchShared sh;
     __shared__ orbx_frame_match_job J;
     __shared__ MatchGrid g;
-    const int tid = threadIdx.x, job = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    const int tid = threadIdx.x, job = blockIdx.x / csize;
     if (tid == 0) { J = jobs[job]; g.carve(dyn, max_kp); }
     __syncthreads();
     const orbx_frame_view &F = J.cur;
@@ -346,8 +372,16 @@ k_match_frame(const orbx_frame_match_job *__restrict__ jobs, int *__restrict__ c
     __shared__ int2 lists[M_WARPS][M_LIST];
     FrameEval ev{J, F, g, lists[tid >> 5]};
     int fb;
-    resolve_claims(n, n_pts, F.claimed, choice2, minclaim2, cand_all + (size_t)job * M_CAND * max_pts,
-                   lcount_all + (size_t)job * 2 * max_pts, lcount_all + (size_t)job * 2 * max_pts + max_pts, max_pts, max_kp, sh, ev, fb);
+    // the CTAs of the cluster each build the grid and a share of the candidate lists; CTA 0 then resolves the claims alone
+    int2 *cand = cand_all + (size_t)job * M_CAND * max_pts;
+    int *lcount = lcount_all + (size_t)job * 2 * max_pts, *ovf = lcount + max_pts;
+    build_candidates(n_pts, cand, lcount, ovf, max_pts, sh, ev, crank, csize, &novf_all[job]);
+    cluster.sync();
+    if (crank != 0) return;
+    const int novf = novf_all[job];
+    __syncthreads();
+    if (tid == 0) novf_all[job] = 0;
+    run_sweeps(n, n_pts, F.claimed, choice2, minclaim2, cand, lcount, ovf, max_pts, max_kp, sh, ev, fb, novf);
     const int *choice = choice2 + (size_t)fb * max_pts;
     // owner = last point that wrote mvpMapPoints[k]; rotation histogram over every accepted point (:1431-1446)
     for (int k = tid; k < n; k += M_THREADS) owner[k] = -1;
@@ -887,7 +921,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
-    cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_sweeps); cudaFree(m->d_items); cudaFree(m->d_arena); cudaFree(m->d_cand); cudaFree(m->d_lcount); cudaFree(m->d_keys);
+    cudaFree(m->d_choice); cudaFree(m->d_minclaim); cudaFree(m->d_owner); cudaFree(m->d_sweeps); cudaFree(m->d_novf); cudaFree(m->d_items); cudaFree(m->d_arena); cudaFree(m->d_cand); cudaFree(m->d_lcount); cudaFree(m->d_keys);
     cudaFree(m->d_desc); cudaFree(m->d_uright); cudaFree(m->d_claimed); cudaFree(m->d_scale); cudaFree(m->d_pts);
     cudaFree(m->d_ptdesc); cudaFree(m->d_match); cudaFree(m->d_nm); cudaFree(m->d_job);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -928,6 +962,9 @@ extern "C" orbx_status orbx_matcher_create(orbx_matcher **out, int max_keypoints
     TRY(cudaMalloc((void **)&m->d_minclaim, sizeof(int) * 2 * kp * jb));
     TRY(cudaMalloc((void **)&m->d_owner, sizeof(int) * kp * jb));
     TRY(cudaMalloc((void **)&m->d_sweeps, sizeof(int) * jb));
+    TRY(cudaMalloc((void **)&m->d_novf, sizeof(int) * jb));
+    TRY(cudaMemset(m->d_novf, 0, sizeof(int) * jb));
+    m->sm_count = prop.multiProcessorCount;
     TRY(cudaMalloc((void **)&m->d_items, sizeof(int) * 2 * pt * jb));
     m->arena_cap = 2 * (kp + pt) * (28 + 32 + 4 + 1 + 4 + 8) + 4096;
     TRY(cudaMalloc((void **)&m->d_arena, m->arena_cap));
@@ -996,8 +1033,20 @@ extern "C" orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const
     ORBX_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
     if (n_jobs == 0) return ORBX_OK;
-    k_match_frame<<<n_jobs, M_THREADS, m->smem, (cudaStream_t)stream>>>(d_jobs, m->d_choice, m->d_minclaim, m->d_owner, m->d_sweeps, m->d_cand, m->d_lcount, m->max_kp,
-                                                                        m->max_pts);
+    // a thread-block cluster per job: as many CTAs as the SMs allow (1, 2 or 4) share the candidate lists of one frame
+    int csize = 1;
+    while (csize < 4 && 2 * csize * n_jobs <= m->sm_count) csize *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_jobs * csize));
+    cfg.blockDim = dim3(M_THREADS);
+    cfg.dynamicSmemBytes = (size_t)m->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_match_frame, d_jobs, m->d_choice, m->d_minclaim, m->d_owner, m->d_sweeps, m->d_cand, m->d_lcount,
+                                 m->d_novf, m->max_kp, m->max_pts));
     m->last_launches = 1;
     ORBX_CUDA(cudaGetLastError());
     return ORBX_OK;
