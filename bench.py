@@ -77,7 +77,7 @@ def set_workload(w, h, nfeat):
 set_workload(W, H, NFEAT)
 assert (PYR_PADDED, PYR_INTERIOR, FRAME_ALGO_BYTES) == (1158012, 950532, 1525212)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 64, from the one `ncu --set full` capture summarised in
-# profiles/r1_h_full.txt (the pyramid figure is the sum of its 8 launches)
+# profiles/r1_n_full.txt (the pyramid figure is the sum of its 8 launches)
 NCU_TRAFFIC_B64 = {"fast": 63.111680e6 + 1.766656e6, "blur": 71.203584e6 + 31.235584e6, "describe": 121.449728e6 + 5.571584e6,
                    "pyramid": 85.3e6 + 0.03e6, "quadtree": 3.002880e6 + 0.052736e6}
 
@@ -372,6 +372,8 @@ def bench_sequence(local_rank, with_cpu, n_frames=40):
     last = None
     for t in range(3):                                    # warm-up
         last = replay.track_frame(gpu, seq, t, last, rng)
+    for k in gpu.seconds:
+        gpu.seconds[k] = 0.0
     t0 = time.perf_counter()
     inl = []
     for t in range(3, n_frames):
@@ -382,6 +384,7 @@ def bench_sequence(local_rank, with_cpu, n_frames=40):
     out = {"config": "%d rendered 640x480 stereo frames, 1000 features per image, camera translating 2 cm per frame; batch 1, host entry points" % (n_frames - 3),
            "frames_per_s": (n_frames - 3) / dt, "ms_per_frame": 1e3 * dt / (n_frames - 3), "inliers_per_frame": float(np.mean(inl)),
            "final_position_error_m": err,
+           "ms_per_frame_by_call": {k: 1e3 * v / (n_frames - 3) for k, v in gpu.seconds.items()},
            "api": "orbx_extractor_run_host x2, orbx_stereo_matches_host, orbx_match_projection_frame_host, orbx_pose_optimize_host (+ numpy bookkeeping)"}
     gpu.close()
     if with_cpu:
@@ -760,7 +763,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 and default_workload else None, "traffic_source": "profiles/r1_h_full.txt (ncu --set full, bytes per launch at batch 64)",
+                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 and default_workload else None, "traffic_source": "profiles/r1_n_full.txt (ncu --set full, bytes per launch at batch 64)",
                          "peak_source": peak_src, "launches_per_step": n_launch_dom,
                          "algorithmic_bytes_per_frame": ALGO_BYTES[dom], "ms_per_step": dom_ms,
                          "whole_step": {"algorithmic_bytes_per_frame": FRAME_ALGO_BYTES,

@@ -25,19 +25,27 @@ class GpuBackend:
         self.st = StereoMatcher(max_keypoints=4096, device=device)
         self.po = PoseOptimizer(max_observations=4096, max_frames=1, device=device)
         self.scale, self.inv_sigma2 = self.ex[0].GetScaleFactors(), self.ex[0].GetInverseScaleSigmaSquares()
+        self.seconds = dict(extract=0.0, stereo=0.0, match=0.0, pose=0.0)      # wall time spent inside the backend calls
+
+    def _timed(self, key, fn, *a):
+        import time
+        t0 = time.perf_counter()
+        r = fn(*a)
+        self.seconds[key] += time.perf_counter() - t0
+        return r
 
     def extract(self, side, img):
-        return self.ex[side](img)
+        return self._timed("extract", self.ex[side], img)
 
     def stereo(self, kl, dl, kr, dr, bf, b):
-        ur, dp, _ = self.st.ComputeStereoMatches(self.ex[0], self.ex[1], kl, dl, kr, dr, bf, b)
+        ur, dp, _ = self._timed("stereo", self.st.ComputeStereoMatches, self.ex[0], self.ex[1], kl, dl, kr, dr, bf, b)
         return ur, dp
 
     def match_last(self, cur, pts, desc, R, t, fwd, bwd, th):
-        return self.mt.SearchByProjectionLast(cur, pts, desc, R, t, fwd, bwd, th)
+        return self._timed("match", self.mt.SearchByProjectionLast, cur, pts, desc, R, t, fwd, bwd, th)
 
     def pose(self, prob):
-        return self.po.PoseOptimization(prob)
+        return self._timed("pose", self.po.PoseOptimization, prob)
 
     def close(self):
         for h in (*self.ex, self.mt, self.st, self.po):
