@@ -29,6 +29,7 @@ struct orbx_pose {
     int device, max_obs, max_frames;
     double *d_Xw, *d_obs, *d_chi2; float *d_info; uint8_t *d_outlier;
     PoseProbDev *d_prob; PoseOutDev *d_out;
+    int32_t *d_index;          // [max_obs] keypoint of every listed observation (device-resident entry point)
     // pinned staging, same layout
     uint8_t *h_arena; size_t arena_bytes;
     cudaStream_t stream;
@@ -314,7 +315,7 @@ extern "C" void orbx_pose_destroy(orbx_pose *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_Xw); cudaFree(h->d_obs); cudaFree(h->d_chi2); cudaFree(h->d_info); cudaFree(h->d_outlier);
-    cudaFree(h->d_prob); cudaFree(h->d_out);
+    cudaFree(h->d_prob); cudaFree(h->d_out); cudaFree(h->d_index);
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->stream) cudaStreamDestroy(h->stream);
     free(h);
@@ -353,6 +354,7 @@ extern "C" orbx_status orbx_pose_create(orbx_pose **out, int max_observations, i
     TRY(cudaMalloc((void **)&h->d_outlier, no));
     TRY(cudaMalloc((void **)&h->d_prob, sizeof(PoseProbDev) * nf));
     TRY(cudaMalloc((void **)&h->d_out, sizeof(PoseOutDev) * nf));
+    TRY(cudaMalloc((void **)&h->d_index, sizeof(int32_t) * no));
     TRY(cudaMallocHost((void **)&h->h_arena, h->arena_bytes));
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 #undef TRY
@@ -422,6 +424,108 @@ extern "C" orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_pro
         if (probs[f].n) memcpy(res[f].outlier, aB + off, (size_t)probs[f].n);
         off += (size_t)probs[f].n;
     }
+    return ORBX_OK;
+}
+
+// ---- device-resident: PoseOptimization right after SearchByProjection(Cur, Last), nothing leaves HBM -------------------------
+// One CTA per frame lists the keypoints that received a map point (ascending keypoint index = the order in which the
+// reference adds its edges, Optimizer.cc:275-350): Xw = the matched last-frame point widened to double, obs = (kpUn.pt.x,
+// kpUn.pt.y, mvuRight[k] or -1), inv_sigma2 of the keypoint's octave; the initial estimate is Converter::toSE3Quat of the job's
+// float pose (Eigen::Quaterniond(R) + normalizeRotation).
+#define PG_THREADS 256
+__global__ void __launch_bounds__(PG_THREADS)
+k_pose_gather(const orbx_frame_match_job *__restrict__ jobs, const float *__restrict__ inv_sigma2, int nlevels, int pitch,
+              double fx, double fy, double cx, double cy, double bf, double *__restrict__ Xw_all, double *__restrict__ obs_all,
+              float *__restrict__ info_all, int32_t *__restrict__ index_all, PoseProbDev *__restrict__ probs) {
+    __shared__ int warp_cnt[PG_THREADS / 32];
+    __shared__ int base;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const orbx_frame_match_job &J = jobs[f];
+    const orbx_frame_view &F = J.cur;
+    const int n = F.n_dev ? *F.n_dev : F.n;
+    double *Xw = Xw_all + 3 * (size_t)f * pitch, *obs = obs_all + 3 * (size_t)f * pitch;
+    float *info = info_all + (size_t)f * pitch;
+    int32_t *index = index_all + (size_t)f * pitch;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += PG_THREADS) {
+        const int k = k0 + tid;
+        const int m = k < n ? J.match[k] : -1;
+        const bool has = m >= 0 && m < J.n_last;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; w++) off += warp_cnt[w];
+        off += __popc(bal & ((1u << lane) - 1u));
+        if (has && off < pitch) {
+            const orbx_last_point p = J.pts[m];
+            const orbx_keypoint kp = F.keys_un[k];
+            Xw[3 * off] = (double)p.x; Xw[3 * off + 1] = (double)p.y; Xw[3 * off + 2] = (double)p.z;
+            obs[3 * off] = (double)kp.x; obs[3 * off + 1] = (double)kp.y;
+            obs[3 * off + 2] = F.u_right ? (double)F.u_right[k] : -1.0;
+            const int oc = min(max(kp.octave, 0), nlevels - 1);
+            info[off] = inv_sigma2[oc];
+            index[off] = k;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < PG_THREADS / 32; w++) t += warp_cnt[w]; base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        PoseProbDev P;
+        P.off = f * pitch; P.n = min(base, pitch);
+        double R[9], q[4];
+        for (int i = 0; i < 9; i++) R[i] = (double)J.Rcw[i];
+        R_to_quat(R, q);
+        quat_normalize(q);
+        P.pose[0] = q[0]; P.pose[1] = q[1]; P.pose[2] = q[2]; P.pose[3] = q[3];
+        P.pose[4] = (double)J.tcw[0]; P.pose[5] = (double)J.tcw[1]; P.pose[6] = (double)J.tcw[2];
+        P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.bf = bf;
+        probs[f] = P;
+    }
+}
+
+// results back in the caller's terms: pose (7 doubles), counts, and mvbOutlier per KEYPOINT of the frame
+__global__ void __launch_bounds__(PG_THREADS)
+k_pose_scatter(const PoseProbDev *__restrict__ probs, const PoseOutDev *__restrict__ outs, const uint8_t *__restrict__ outlier_all,
+               const int32_t *__restrict__ index_all, double *__restrict__ pose_out, int32_t *__restrict__ n_inliers,
+               uint8_t *__restrict__ outlier_kp, int kp_pitch) {
+    const int f = blockIdx.x;
+    const PoseProbDev P = probs[f];
+    for (int j = threadIdx.x; j < P.n; j += PG_THREADS)
+        outlier_kp[(size_t)f * kp_pitch + index_all[P.off + j]] = outlier_all[P.off + j];
+    if (threadIdx.x < 7) pose_out[7 * f + threadIdx.x] = outs[f].pose[threadIdx.x];
+    if (threadIdx.x == 0 && n_inliers) n_inliers[f] = outs[f].n_inliers;
+}
+
+extern "C" orbx_status orbx_pose_from_matches_device(orbx_pose *h, const orbx_frame_match_job *d_jobs, int n_frames,
+                                                     const float *d_inv_sigma2, int nlevels, double fx, double fy, double cx, double cy,
+                                                     double bf, double *d_pose_out, int32_t *d_n_inliers, uint8_t *d_outlier_kp,
+                                                     int kp_pitch, void *stream) {
+    if (!h || n_frames < 0 || (n_frames && (!d_jobs || !d_inv_sigma2 || !d_pose_out || !d_outlier_kp)) || nlevels < 1 || kp_pitch < 1)
+        return ORBX_ERR_INVALID;
+    h->last_launches = 0;
+    if (n_frames == 0) return ORBX_OK;
+    if (n_frames > h->max_frames) {
+        orbx_set_error("orbx_pose: %d frames, handle was created for %d", n_frames, h->max_frames);
+        return ORBX_ERR_CAPACITY;
+    }
+    const int pitch = h->max_obs / n_frames;           // observations a frame may list
+    if (pitch < kp_pitch) {
+        orbx_set_error("orbx_pose: %d observations for %d frames of up to %d keypoints", h->max_obs, n_frames, kp_pitch);
+        return ORBX_ERR_CAPACITY;
+    }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ORBX_CUDA(cudaMemsetAsync(d_outlier_kp, 0, (size_t)n_frames * kp_pitch, s));
+    k_pose_gather<<<n_frames, PG_THREADS, 0, s>>>(d_jobs, d_inv_sigma2, nlevels, pitch, fx, fy, cx, cy, bf, h->d_Xw, h->d_obs, h->d_info,
+                                                  h->d_index, h->d_prob);
+    k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(h->d_prob, h->d_Xw, h->d_obs, h->d_info, h->d_outlier, h->d_chi2, h->d_out, 10);
+    k_pose_scatter<<<n_frames, PG_THREADS, 0, s>>>(h->d_prob, h->d_out, h->d_outlier, h->d_index, d_pose_out, d_n_inliers, d_outlier_kp,
+                                                   kp_pitch);
+    ORBX_CUDA(cudaGetLastError());
+    h->last_launches = 3;
     return ORBX_OK;
 }
 

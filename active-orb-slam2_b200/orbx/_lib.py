@@ -91,6 +91,7 @@ def _declare(L):
     L.orbx_pose_destroy.restype = None
     L.orbx_pose_destroy.argtypes = [vp]
     L.orbx_pose_optimize_host.argtypes = [vp, vp, i, vp]
+    L.orbx_pose_from_matches_device.argtypes = [vp, vp, i, vp, i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp, i, vp]
     L.orbx_pose_last_launches.argtypes = [vp]
     L.orbx_vocabulary_create.argtypes = [C.POINTER(vp), i, vp, vp, vp, vp, vp, i, i, i]
     L.orbx_vocabulary_destroy.restype = None

@@ -165,5 +165,11 @@ class PoseOptimizer:
                     trials=R[f].lm_trials) for f in range(nf)]
         return res[0] if single else res
 
+    def from_matches_device(self, d_jobs, n_frames, d_inv_sigma2, nlevels, K, d_pose_out, d_n_inliers, d_outlier_kp, kp_pitch, stream=0):
+        """PoseOptimization of a batch of frames from the device job array of ORBmatcher.search_frames_device (raw device pointers)"""
+        fx, fy, cx, cy, bf = (float(v) for v in K[:5])
+        check(self._L.orbx_pose_from_matches_device(self._h, d_jobs, n_frames, d_inv_sigma2, nlevels, fx, fy, cx, cy, bf, d_pose_out,
+                                                    d_n_inliers, d_outlier_kp, kp_pitch, stream))
+
     def last_launches(self):
         return self._L.orbx_pose_last_launches(self._h)

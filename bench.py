@@ -552,6 +552,38 @@ def main():
     runs, stage_ms = ex.stage_ms()
     stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / KP
     ex.profile(0)
+    # ---- the same step followed by PoseOptimization of every frame from the match arrays, still device-resident (the three
+    # calls Tracking::TrackWithMotionModel makes per frame: extract, SearchByProjection(Cur, Last), PoseOptimization) ----
+    track = None
+    if rank == 0:
+        from orbx.optimizer import PoseOptimizer
+        pz = PoseOptimizer(max_observations=B * cap, max_frames=B, device=local_rank)
+        d_is2 = torch.from_numpy(ex.GetInverseScaleSigmaSquares()).cuda()
+        d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
+        d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
+        d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+
+        def step_track(i):
+            step_device(i)
+            pz.from_matches_device(jobs_dev[i % npool].data_ptr(), B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, d_pose.data_ptr(), d_inl.data_ptr(),
+                                   d_outkp.data_ptr(), cap, stream.cuda_stream)
+
+        for i in range(3):
+            step_track(i)
+        torch.cuda.synchronize()
+        KT = min(K, 100)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(stream)
+        for i in range(KT):
+            step_track(3 + i)
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        ms_track = t0e.elapsed_time(t1e) / KT
+        track = {"config": "the `value` step + Optimizer::PoseOptimization of all %d frames from the match arrays (monocular observations), device-resident" % B,
+                 "frames_per_s": B / (ms_track * 1e-3), "ms_per_step": ms_track, "pose_ms_per_step": ms_track - ms_total / K,
+                 "inliers_per_frame": float(d_inl.float().mean().item()), "kernel_launches_per_step": launches_per_step + pz.last_launches(),
+                 "api": "orbx_extractor_run_device + orbx_match_projection_frame_device + orbx_pose_from_matches_device"}
+        pz.close()
     kp_per_frame = float(d_cnt.float().mean().item())
     matches_per_frame = float(d_nm.float().mean().item())
     match_sweeps = mt.last_sweeps(B).tolist()
@@ -775,6 +807,7 @@ def main():
             "pose": pose,
             "bow": bow,
             "sequence": sequence,
+            "track": track,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1

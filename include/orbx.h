@@ -403,6 +403,15 @@ void orbx_pose_destroy(orbx_pose *h);
  * block per frame; the four rounds, their Levenberg loops and the classifications run on the device).  Host pointers;
  * synchronous. */
 orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_problem *probs, int n_frames, orbx_pose_result *res);
+/* device-resident: PoseOptimization of every frame of a batch right after orbx_match_projection_frame_device, from the SAME
+ * device job array (the frame's keypoints and mvuRight, the last frame's points, the pose Rcw / tcw that the search used, and the
+ * match array it filled).  The observations are listed on the device in ascending keypoint index, like the reference adds its
+ * edges; d_inv_sigma2 = mvInvLevelSigma2 (nlevels floats).  Outputs (device): d_pose_out n_frames x 7, d_n_inliers n_frames
+ * (may be NULL), d_outlier_kp n_frames x kp_pitch = mvbOutlier per keypoint (0 for keypoints without a map point).  The handle
+ * must have been created with max_observations >= n_frames * kp_pitch.  Only enqueues on `stream` (3 launches). */
+orbx_status orbx_pose_from_matches_device(orbx_pose *h, const orbx_frame_match_job *d_jobs, int n_frames, const float *d_inv_sigma2,
+                                          int nlevels, double fx, double fy, double cx, double cy, double bf, double *d_pose_out,
+                                          int32_t *d_n_inliers, uint8_t *d_outlier_kp, int kp_pitch, void *stream);
 int orbx_pose_last_launches(const orbx_pose *h);
 
 /* =====================================================================================================

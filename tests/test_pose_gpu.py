@@ -79,3 +79,65 @@ def test_capacity_is_an_error(po):
     with pytest.raises(OrbxError):
         small.PoseOptimization([synth.pose_problem(s, n=10) for s in range(3)])
     small.close()
+
+
+def test_pose_from_matches_device_resident():
+    """SearchByProjection(Cur, Last) and PoseOptimization back to back on the device from ONE job array: poses, inlier counts and
+    per-keypoint outlier flags equal the oracle chain fed with the same inputs"""
+    import torch
+    from orbx.matcher import FrameMatchJob, ORBmatcher, fill_view
+    from tools_replay_shim import quat_pose
+    rng = np.random.default_rng(5)
+    B, cap = 6, 1200
+    mt = ORBmatcher(0.9, True, max_keypoints=cap, max_points=cap, max_jobs=B)
+    pz = PoseOptimizer(max_observations=B * cap, max_frames=B)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    keep, jobs, refs = [], (FrameMatchJob * B)(), []
+    sf = synth.scale_factors(8)
+    inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    d_match = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for j in range(B):
+        cur = synth.random_frame(rng, 700 + 60 * j)
+        pts, desc, R, t = synth.last_frame_points(rng, cur, 600 + 40 * j)
+        n = len(cur["keys_un"])
+        # the oracle chain on the host: match, list the matched keypoints in index order, optimise
+        nm, m = O.search_by_projection_frame(cur, pts, desc, R, t, False, False, 7.0, True)
+        idx = np.nonzero(m >= 0)[0]
+        prob = dict(Xw=np.stack([pts["x"], pts["y"], pts["z"]], 1)[m[idx]].astype(np.float64),
+                    obs=np.stack([cur["keys_un"]["x"][idx], cur["keys_un"]["y"][idx], cur["u_right"][idx]], 1).astype(np.float64),
+                    inv_sigma2=inv_sigma2[cur["keys_un"]["octave"][idx]], pose=quat_pose(R, t), K=cur["K"][:5])
+        refs.append((nm, m, idx, prob, O.pose_optimize(prob)))
+        t_keys, t_desc, t_ur, t_cl = dev(cur["keys_un"]), dev(cur["desc"]), dev(cur["u_right"]), dev(cur["claimed"])
+        t_sf, t_pts, t_pd = dev(cur["scale_factors"]), dev(pts), dev(desc)
+        keep += [t_keys, t_desc, t_ur, t_cl, t_sf, t_pts, t_pd]
+        J = jobs[j]
+        J.cur.n, J.cur.n_dev = n, None
+        J.cur.keys_un, J.cur.desc, J.cur.u_right, J.cur.claimed = t_keys.data_ptr(), t_desc.data_ptr(), t_ur.data_ptr(), t_cl.data_ptr()
+        J.cur.scale_factors = t_sf.data_ptr()
+        fill_view(J.cur, cur["bounds"], cur["K"], 8)
+        J.n_last, J.pts, J.last_desc = len(pts), t_pts.data_ptr(), t_pd.data_ptr()
+        J.Rcw[:] = R.reshape(9).tolist(); J.tcw[:] = t.tolist()
+        J.forward = J.backward = 0
+        J.th, J.check_ori = 7.0, 1
+        J.match, J.nmatches = d_match.data_ptr() + 4 * cap * j, d_nm.data_ptr() + 4 * j
+    d_jobs = torch.from_numpy(np.frombuffer(bytes(jobs), np.uint8).copy()).cuda()
+    d_is2 = torch.from_numpy(inv_sigma2).cuda()
+    d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
+    d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_out = torch.full((B, cap), 9, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    mt.search_frames_device(d_jobs.data_ptr(), B, s)
+    pz.from_matches_device(d_jobs.data_ptr(), B, d_is2.data_ptr(), 8, refs[0][3]["K"], d_pose.data_ptr(), d_inl.data_ptr(), d_out.data_ptr(), cap, s)
+    torch.cuda.synchronize()
+    assert pz.last_launches() == 3
+    pose, inl, out, match = d_pose.cpu().numpy(), d_inl.cpu().numpy(), d_out.cpu().numpy(), d_match.cpu().numpy()
+    for j in range(B):
+        nm, m, idx, prob, ref = refs[j]
+        assert np.array_equal(match[j, :len(m)], m) and len(idx) > 100
+        assert inl[j] == ref["n_inliers"]
+        exp = np.zeros(cap, np.uint8)
+        exp[idx] = ref["outlier"]
+        assert np.array_equal(out[j], exp)
+        assert update_rel(pose[j], ref["pose"], prob["pose"]) < TOL
+    mt.close(); pz.close()
