@@ -41,6 +41,9 @@ struct Mat {
     Mat colRange(int, int) const { return *this; }
     Mat row(int) const { return *this; }
     Mat clone() const { return *this; }
+    Mat col(int) const { return *this; }
+    Mat t() const { return *this; }
+    double dot(const Mat &) const { return 0.0; }
     void copyTo(struct _OutputArray) const;
     template <class T> T &at(int, int = 0) { return *reinterpret_cast<T *>(data); }
     template <class T> const T &at(int, int = 0) const { return *reinterpret_cast<const T *>(data); }
@@ -49,6 +52,14 @@ struct Mat {
 };
 struct _InputArray { _InputArray() {} _InputArray(const Mat &) {} bool empty() const { return true; } Mat getMat() const { return Mat(); } };
 struct _OutputArray { _OutputArray() {} _OutputArray(Mat &) {} void release() const {} };
+inline Mat operator*(const Mat &a, const Mat &) { return a; }
+inline Mat operator*(double, const Mat &a) { return a; }
+inline Mat operator*(const Mat &a, double) { return a; }
+inline Mat operator/(const Mat &a, double) { return a; }
+inline Mat operator+(const Mat &a, const Mat &) { return a; }
+inline Mat operator-(const Mat &a, const Mat &) { return a; }
+inline Mat operator-(const Mat &a) { return a; }
+inline double norm(const Mat &) { return 0.0; }
 struct FileNode {
     FileNode operator[](const char *) const { return *this; }
     FileNode operator[](const std::string &) const { return *this; }

@@ -13,7 +13,7 @@ REF_INC = "/root/reference/include"
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_INC) or shutil.which("g++") is None, reason="reference headers / g++ not available")
-@pytest.mark.parametrize("src", ["ORBextractor_orbx.cc", "ORBmatcher_orbx.cc", "ORBmatcher_bow_orbx.cc", "Frame_orbx.cc", "Vocabulary_orbx.cc"])
+@pytest.mark.parametrize("src", ["ORBextractor_orbx.cc", "ORBmatcher_orbx.cc", "ORBmatcher_bow_orbx.cc", "ORBmatcher_window_orbx.cc", "Frame_orbx.cc", "Vocabulary_orbx.cc"])
 def test_adapter_is_valid_cxx_against_the_reference_headers(src):
     cmd = ["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "stubs"), "-I", REF_INC,
            "-I", os.path.dirname(REF_INC), "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "active-orb-slam2_b200", "adapter", src)]
