@@ -21,16 +21,19 @@ const int ORBmatcher::TH_HIGH = 100;
 const int ORBmatcher::TH_LOW = 50;
 const int ORBmatcher::HISTO_LENGTH = 30;
 
-namespace
-{
-// ORBmatcher objects are stack temporaries in the reference (one per call); the device scratch lives per calling thread
-orbx_matcher* matcherOfThisThread()
+// ORBmatcher objects are stack temporaries in the reference (one per call); the device scratch lives per calling thread and is
+// shared by the three adapter files
+orbx_matcher* orbxMatcherOfThisThread()
 {
     thread_local orbx_matcher* m = nullptr;
     if (!m && orbx_matcher_create(&m, 8192, 8192, 1, 0) != ORBX_OK)
         throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
     return m;
 }
+
+namespace
+{
+orbx_matcher* matcherOfThisThread() { return orbxMatcherOfThisThread(); }
 
 void check(orbx_status s)
 {

@@ -22,15 +22,11 @@ using namespace std;
 namespace ORB_SLAM2
 {
 
+orbx_matcher* orbxMatcherOfThisThread();      // ORBmatcher_orbx.cc: one device scratch per calling thread
+
 namespace
 {
-orbx_matcher* matcherOfThisThread()
-{
-    thread_local orbx_matcher* m = nullptr;
-    if (!m && orbx_matcher_create(&m, 8192, 8192, 1, 0) != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-    return m;
-}
+orbx_matcher* matcherOfThisThread() { return orbxMatcherOfThisThread(); }
 
 void check(orbx_status s)
 {
