@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // Three phases per pass, so that only the few pixels that can be corners pay for the 16-arc score and the 3x3
 // suppression: (1) packed pre-test on every pixel (four per thread), survivors compacted into a list; (2) score of the
 // listed pixels; (3) suppression of the listed pixels with a non-zero score.
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, 5)
 k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv,
        const OrbxFastChunk *__restrict__ chunks, uint32_t *__restrict__ cand, size_t cand_frame, int *__restrict__ ncand,
        int *__restrict__ status, int ini_th, int min_th, int tp_max, int th_max, const __grid_constant__ OrbxTmaps maps) {
