@@ -104,3 +104,37 @@ def test_oracle_on_the_reference_vocabulary():
     for p in lvl1:
         par[tree["children"][tree["child_start"][p]:tree["child_start"][p + 1]]] = p
     assert all(int(par[n]) in lvl1 for n in node.tolist())
+
+
+REF_SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libdbow2_ref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libdbow2_ref.so is built from the reference tree (make -C oracle ref)")
+@pytest.mark.parametrize("weighting,scoring", [(0, 0), (1, 0), (0, 1), (0, 5), (2, 0), (3, 5)])
+def test_bookkeeping_against_the_reference_classes(weighting, scoring):
+    """bow_maps (the product's host bookkeeping) against the REFERENCE's compiled DBoW2::BowVector / FeatureVector: identical keys,
+    identical doubles bit for bit, identical feature lists -- for every weighting / normalisation branch of transform()"""
+    import ctypes as C
+    L = C.CDLL(REF_SO)
+    rng = np.random.default_rng(weighting * 7 + scoring)
+    n = 3000
+    word = rng.integers(0, 400, n).astype(np.uint32)
+    wts = rng.uniform(0.01, 9.0, 400)
+    wts[rng.random(400) < 0.1] = 0.0                                   # stopped words
+    weight = wts[word].astype(np.float64)
+    node = (word // 7).astype(np.uint32)
+    v, fv = bow_maps(word.astype(np.int64), node.astype(np.int64), weight, weighting, scoring)
+    v_ids, v_vals = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+    fv_ids, fv_start, fv_feat = np.zeros(n, np.uint32), np.zeros(n + 1, np.int32), np.zeros(n, np.uint32)
+    n_v, n_fv = C.c_int(), C.c_int()
+    must = scoring in (0, 1, 2, 3, 4)
+    L.dbow2_ref_maps(n, word.ctypes.data_as(C.c_void_p), node.ctypes.data_as(C.c_void_p), weight.ctypes.data_as(C.c_void_p),
+                     int(weighting in (0, 1)), int(must), int(scoring == 1), v_ids.ctypes.data_as(C.c_void_p), v_vals.ctypes.data_as(C.c_void_p),
+                     C.byref(n_v), fv_ids.ctypes.data_as(C.c_void_p), fv_start.ctypes.data_as(C.c_void_p), fv_feat.ctypes.data_as(C.c_void_p),
+                     C.byref(n_fv))
+    assert list(v) == v_ids[:n_v.value].tolist()
+    assert np.array(list(v.values()), np.float64).tobytes() == v_vals[:n_v.value].tobytes()
+    assert list(fv) == fv_ids[:n_fv.value].tolist()
+    for k, nid in enumerate(fv):
+        assert fv[nid] == fv_feat[fv_start[k]:fv_start[k + 1]].tolist()
+    assert n_v.value > 100 and n_fv.value > 20
