@@ -99,25 +99,25 @@ __device__ __forceinline__ void dinv3(const double *h, double lambda, double I[6
 
 __device__ __forceinline__ int upper_block(int p1, int p2, int np) { return p1 * np - p1 * (p1 - 1) / 2 + (p2 - p1); }
 
-// Eigen::Quaterniond(Matrix3d)
+// Eigen::Quaterniond(Matrix3d); static indexing only, so that everything stays in registers
 __device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
     double t = R[0] + R[4] + R[8];
     if (t > 0) {
         t = sqrt(t + 1.0);
         q[3] = 0.5 * t; t = 0.5 / t;
         q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
-    } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[4 * i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-        double qq[4];
-        qq[i] = 0.5 * t; t = 0.5 / t;
-        qq[3] = (R[3 * k + j] - R[3 * j + k]) * t;
-        qq[j] = (R[3 * j + i] + R[3 * i + j]) * t;
-        qq[k] = (R[3 * k + i] + R[3 * i + k]) * t;
-        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    } else if (R[0] >= R[4] && R[0] >= R[8]) {             // i = 0, j = 1, k = 2 (Eigen: i = 0; if (m11 > m00) i = 1; if (m22 > m(i,i)) i = 2)
+        t = sqrt(R[0] - R[4] - R[8] + 1.0);
+        q[0] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
+    } else if (R[4] > R[0] && R[4] >= R[8]) {              // i = 1, j = 2, k = 0
+        t = sqrt(R[4] - R[8] - R[0] + 1.0);
+        q[1] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
+    } else {                                               // i = 2, j = 0, k = 1
+        t = sqrt(R[8] - R[0] - R[4] + 1.0);
+        q[2] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
     }
 }
 __device__ __forceinline__ void quat_normalize(double q[4]) {
@@ -126,38 +126,41 @@ __device__ __forceinline__ void quat_normalize(double q[4]) {
     q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
 }
 
-// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*)
-__device__ inline void se3_oplus(double *T, const double *u) {
+// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*); every loop unrolled, registers only
+__device__ __forceinline__ void se3_oplus(double *T, const double *u) {
     const double wx = u[0], wy = u[1], wz = u[2];
     const double theta = sqrt(wx * wx + wy * wy + wz * wz);
     const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double O2[9], R[9], V[9];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
-    if (theta < 0.00001) {
-        for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
-    } else {
-        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
-        for (int i = 0; i < 9; i++) {
-            const double id = i % 4 == 0 ? 1.0 : 0.0;
-            R[i] = id + a * O[i] + b * O2[i];
-            V[i] = id + b * O[i] + c * O2[i];
-        }
+    double a = 1.0, b = 1.0, cc = 1.0;
+    const bool small = theta < 0.00001;                    // SE3Quat::exp: R = V = I + Omega + Omega^2 below this angle
+    if (!small) {
+        a = sin(theta) / theta; b = (1 - cos(theta)) / (theta * theta); cc = (theta - sin(theta)) / (theta * theta * theta);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+        R[i] = id + a * O[i] + b * O2[i];
+        V[i] = small ? R[i] : id + b * O[i] + cc * O2[i];
     }
     double eq[4], et[3];
     R_to_quat(R, eq);
     quat_normalize(eq);
+#pragma unroll
     for (int r = 0; r < 3; r++) et[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
-    const double *b = T;   // q2
     double nq[4];
-    nq[3] = eq[3] * b[3] - eq[0] * b[0] - eq[1] * b[1] - eq[2] * b[2];
-    nq[0] = eq[3] * b[0] + eq[0] * b[3] + eq[1] * b[2] - eq[2] * b[1];
-    nq[1] = eq[3] * b[1] + eq[1] * b[3] + eq[2] * b[0] - eq[0] * b[2];
-    nq[2] = eq[3] * b[2] + eq[2] * b[3] + eq[0] * b[1] - eq[1] * b[0];
+    nq[3] = eq[3] * T[3] - eq[0] * T[0] - eq[1] * T[1] - eq[2] * T[2];
+    nq[0] = eq[3] * T[0] + eq[0] * T[3] + eq[1] * T[2] - eq[2] * T[1];
+    nq[1] = eq[3] * T[1] + eq[1] * T[3] + eq[2] * T[0] - eq[0] * T[2];
+    nq[2] = eq[3] * T[2] + eq[2] * T[3] + eq[0] * T[1] - eq[1] * T[0];
     double Rq[9], nt[3];
     quat_to_R(eq, Rq);
+#pragma unroll
     for (int r = 0; r < 3; r++) nt[r] = et[r] + Rq[3 * r] * T[4] + Rq[3 * r + 1] * T[5] + Rq[3 * r + 2] * T[6];
     quat_normalize(nq);
     T[0] = nq[0]; T[1] = nq[1]; T[2] = nq[2]; T[3] = nq[3]; T[4] = nt[0]; T[5] = nt[1]; T[6] = nt[2];
 }
-

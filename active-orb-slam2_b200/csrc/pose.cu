@@ -151,68 +151,6 @@ __device__ __forceinline__ void po_pass(PoseShared &S, const PoseProbDev &P, con
     }
 }
 
-// Eigen::Quaterniond(Matrix3d) with static indexing only (registers, no local memory)
-__device__ __forceinline__ void po_R_to_quat(const double *R, double *q) {
-    double t = R[0] + R[4] + R[8];
-    if (t > 0) {
-        t = sqrt(t + 1.0);
-        q[3] = 0.5 * t; t = 0.5 / t;
-        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
-    } else if (R[0] >= R[4] && R[0] >= R[8]) {             // i = 0, j = 1, k = 2
-        t = sqrt(R[0] - R[4] - R[8] + 1.0);
-        q[0] = 0.5 * t; t = 0.5 / t;
-        q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
-    } else if (R[4] > R[0] && R[4] >= R[8]) {              // i = 1, j = 2, k = 0
-        t = sqrt(R[4] - R[8] - R[0] + 1.0);
-        q[1] = 0.5 * t; t = 0.5 / t;
-        q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
-    } else {                                               // i = 2, j = 0, k = 1
-        t = sqrt(R[8] - R[0] - R[4] + 1.0);
-        q[2] = 0.5 * t; t = 0.5 / t;
-        q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
-    }
-}
-
-// T <- exp(u) * T (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*), same arithmetic as se3_oplus of
-// lba_common.cuh with every loop unrolled so that the one thread the block waits for works from registers
-__device__ __forceinline__ void po_oplus(double *T, const double *u) {
-    const double wx = u[0], wy = u[1], wz = u[2];
-    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
-    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-    double O2[9], R[9], V[9];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
-    double a = 1.0, b = 1.0, cc = 1.0;
-    const bool small = theta < 0.00001;
-    if (!small) {
-        a = sin(theta) / theta; b = (1 - cos(theta)) / (theta * theta); cc = (theta - sin(theta)) / (theta * theta * theta);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-        const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
-        R[i] = id + a * O[i] + b * O2[i];
-        V[i] = small ? R[i] : id + b * O[i] + cc * O2[i];
-    }
-    double eq[4], et[3];
-    po_R_to_quat(R, eq);
-    quat_normalize(eq);
-#pragma unroll
-    for (int r = 0; r < 3; r++) et[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
-    double nq[4];
-    nq[3] = eq[3] * T[3] - eq[0] * T[0] - eq[1] * T[1] - eq[2] * T[2];
-    nq[0] = eq[3] * T[0] + eq[0] * T[3] + eq[1] * T[2] - eq[2] * T[1];
-    nq[1] = eq[3] * T[1] + eq[1] * T[3] + eq[2] * T[0] - eq[0] * T[2];
-    nq[2] = eq[3] * T[2] + eq[2] * T[3] + eq[0] * T[1] - eq[1] * T[0];
-    double Rq[9], nt[3];
-    quat_to_R(eq, Rq);
-#pragma unroll
-    for (int r = 0; r < 3; r++) nt[r] = et[r] + Rq[3 * r] * T[4] + Rq[3 * r + 1] * T[5] + Rq[3 * r + 2] * T[6];
-    quat_normalize(nq);
-    T[0] = nq[0]; T[1] = nq[1]; T[2] = nq[2]; T[3] = nq[3]; T[4] = nt[0]; T[5] = nt[1]; T[6] = nt[2];
-}
-
 // (H + lambda I) x = b for the 6x6 system, upper-triangular H (21 entries); returns 0 if not positive definite
 __device__ __forceinline__ int po_solve6(const double *Hu, const double *b, double lambda, double *x) {
     // every loop has compile-time bounds and is unrolled, so that A lives in registers (no local-memory round trips on the one
@@ -314,7 +252,7 @@ k_pose_optimize(const PoseProbDev *__restrict__ probs, const double *__restrict_
                             for (int i = 0; i < 7; i++) S.Tbak[i] = S.T[i];   // push
                             const int ok = po_solve6(S.H, S.b, S.lambda, S.x);
                             if (!ok) for (int i = 0; i < 6; i++) S.x[i] = 0;
-                            if (ok) { po_oplus(S.T, S.x); po_set_pose(S); }
+                            if (ok) { se3_oplus(S.T, S.x); po_set_pose(S); }
                             S.again = ok;                                     // reused as "solve ok" until the decision below
                         }
                         __syncthreads();
