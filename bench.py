@@ -399,6 +399,30 @@ def bench_sequence(local_rank, with_cpu, n_frames=40):
     return out
 
 
+def bench_lba_batched(local_rank, rank, NW=16, rounds=3):
+    """batched many-window mode: NW independent C3 windows in flight on this rank, one handle + stream each.
+    Every rank runs its own windows (no data-path collective); returns (windows, Levenberg trials, seconds)."""
+    from orbx import synth
+    from orbx.optimizer import Optimizer
+    ops = [Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank) for _ in range(NW)]
+    probs = [synth.lba_problem(100 + NW * rank + i, n_kf=20, n_pts=3000, stereo=False, n_fixed=1) for i in range(NW)]
+    for o_, p_ in zip(ops, probs):
+        o_.begin(p_)
+    for o_ in ops:
+        o_.end()
+    t0 = time.perf_counter()
+    trials = 0
+    for _ in range(rounds):
+        for o_, p_ in zip(ops, probs):
+            o_.begin(p_)
+        for o_ in ops:
+            trials += o_.end()["trials"]
+    dt = time.perf_counter() - t0
+    for o_ in ops:
+        o_.close()
+    return rounds * NW, trials, dt
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -716,26 +740,7 @@ def main():
                "schur_build_us": 1e3 * ms_build / 50, "kernel_launches_per_window": launches_lba,
                "api": "orbx_lba_solve_host (host buffers in and out, synchronous)",
                "schur_build": "residuals + Jacobians + quadratic form + Schur complement of one Levenberg trial, device time (CUDA events)"}
-        # batched many-window mode: independent windows in flight, one handle + stream each
-        NW = 16
-        ops = [Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank) for _ in range(NW)]
-        probs = [synth.lba_problem(100 + i, n_kf=20, n_pts=3000, stereo=False, n_fixed=1) for i in range(NW)]
-        for o_, p_ in zip(ops, probs):
-            o_.begin(p_)
-        for o_ in ops:
-            o_.end()
-        t0 = time.perf_counter()
-        tr_b = 0
-        for _ in range(3):
-            for o_, p_ in zip(ops, probs):
-                o_.begin(p_)
-            for o_ in ops:
-                tr_b += o_.end()["trials"]
-        bat_s = time.perf_counter() - t0
-        lba["batched"] = {"windows_in_flight": NW, "windows_per_s": 3 * NW / bat_s, "lm_trials_per_s": tr_b / bat_s,
-                          "api": "orbx_lba_solve_begin / orbx_lba_solve_end, one handle per window"}
-        for o_ in ops:
-            o_.close()
+        lba["batched"] = None      # filled below from every rank's share
         if not args.no_cpu:
             from oracle import oracle_py as O
             t0 = time.perf_counter()
@@ -754,6 +759,11 @@ def main():
             lba["cpu"] = "C oracle (g2o restated), 1 thread, as g2o runs in the reference (OpenMP off)"
         op.close()
 
+    # LocalBA windows sharded over the ranks: every rank solves its own 16 windows in flight
+    lba_local = (0, 0, 0.0)
+    if default_workload and not args.extract_only:
+        barrier()
+        lba_local = bench_lba_batched(local_rank, rank)
     stereo = pose = bow = sequence = None
     if side_sections:
         stereo = bench_stereo(local_rank, not args.no_cpu)
@@ -764,11 +774,17 @@ def main():
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
     ms_total, e2e_s, ms_two_lanes = shard.max_over_ranks([ms_total, e2e_s, ms_two_lanes], device="cuda")
-    counters = shard.gather_counters([B * K, int(round(kp_per_frame * B)), int(round(matches_per_frame * B))], device="cuda")
+    counters = shard.gather_counters([B * K, int(round(kp_per_frame * B)), int(round(matches_per_frame * B)), lba_local[0], lba_local[1],
+                                      int(lba_local[2] * 1e6)], device="cuda")
     frames_total = sum(c[0] for c in counters)
     value = frames_total / (ms_total * 1e-3)
     e2e = frames_total / e2e_s
 
+    if rank == 0 and lba is not None:
+        lw, lt, ls = sum(c[3] for c in counters), sum(c[4] for c in counters), max(c[5] for c in counters) * 1e-6
+        lba["batched"] = {"windows_in_flight_per_gpu": 16, "windows_per_s": lw / ls if ls > 0 else 0.0, "lm_trials_per_s": lt / ls if ls > 0 else 0.0,
+                          "n_gpus": world, "windows_per_rank": [c[3] for c in counters],
+                          "api": "orbx_lba_solve_begin / orbx_lba_solve_end, one handle per window; every rank solves its own windows, time = max over ranks"}
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(stage_ms, key=stage_ms.get)
