@@ -828,7 +828,27 @@ def main():
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             fps, n, dt = cpu_path(hnp[:64], 12.0, cores)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            cv_note = None
+            try:                                          # context only: OpenCV's own SIMD ORB (not the reference's quadtree extractor)
+                import cv2
+                cv2.setNumThreads(1)
+                orb = cv2.ORB_create(nfeatures=NFEAT, scaleFactor=SCALE, nlevels=NLEVELS, scoreType=cv2.ORB_FAST_SCORE, fastThreshold=INI_TH)
+                bf_ = cv2.BFMatcher(cv2.NORM_HAMMING)
+                prev_ = None
+                t0 = time.perf_counter()
+                ncv = 0
+                while time.perf_counter() - t0 < 3.0:
+                    k_, d_ = orb.detectAndCompute(hnp[ncv % 64], None)
+                    if prev_ is not None and d_ is not None:
+                        bf_.match(d_, prev_)
+                    prev_ = d_
+                    ncv += 1
+                cv_note = {"frames_per_s_1_thread": ncv / (time.perf_counter() - t0),
+                           "what": "cv2.ORB (FAST score, no quadtree distribution) detectAndCompute + brute-force Hamming match against the previous "
+                                   "frame, one thread, cv2 %s; a different algorithm with SIMD kernels, shown for scale only" % cv2.__version__}
+            except Exception as ex_:                      # noqa: BLE001
+                cv_note = {"unavailable": str(ex_)[:100]}
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "opencv_orb": cv_note,
                                    "sample": "%d G-rect VGA frames (extract + SearchByProjection vs predecessor) in %.1f s on %d host threads (C oracle, one extractor per thread)" % (n, dt, cores)}
         emit(out)
     if dist is not None:
