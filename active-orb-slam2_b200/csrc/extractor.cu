@@ -326,6 +326,7 @@ static orbx_status configure(orbx_extractor *e, int w, int h) {
     orbx_status st = build_geometry(e, w, h, g);
     if (st != ORBX_OK) return st;
     ORBX_CUDA(cudaDeviceSynchronize());   // nothing may still be reading the old tables
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }   // it holds the old geometry and tensor maps
     const size_t mb = (size_t)e->max_batch;
     if (g.pyr_bytes > e->pyr_frame_cap || !e->d_pyr) {
         size_t cap = 0;
@@ -480,6 +481,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor *e) {
     free(e->prof_ev);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->graph) cudaGraphExecDestroy(e->graph);
     if (e->aux) cudaStreamDestroy(e->aux);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -586,8 +588,32 @@ extern "C" orbx_status orbx_extractor_run_host(orbx_extractor *e, const uint8_t 
         if (!images[b]) return ORBX_ERR_INVALID;
         ORBX_CUDA(cudaMemcpy2DAsync(e->d_img + fp * b, width, images[b], stride, width, height, cudaMemcpyHostToDevice, s));
     }
-    orbx_status st = orbx_extractor_run_device(e, e->d_img, fp, batch, width, height, width, e->d_kps, e->d_desc, e->d_counts, s);
-    if (st) return st;
+    orbx_status st = ORBX_OK;
+    static const bool use_graph = getenv("ORBX_NO_GRAPH") == nullptr;
+    if (use_graph && !e->prof_ev) {
+        // replay the captured stage sequence (same buffers, same geometry); capture it on first use
+        if ((st = configure(e, width, height))) return st;
+        if (!e->graph || e->graph_w != width || e->graph_h != height || e->graph_batch != batch) {
+            if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            ORBX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            st = orbx_extractor_run_device(e, e->d_img, fp, batch, width, height, width, e->d_kps, e->d_desc, e->d_counts, s);
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (st) { if (g) cudaGraphDestroy(g); return st; }
+            if (ce != cudaSuccess) { orbx_set_error("stream capture of the extractor failed: %s", cudaGetErrorString(ce)); return ORBX_ERR_CUDA; }
+            const cudaError_t ci = cudaGraphInstantiate(&e->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ci != cudaSuccess) { e->graph = nullptr; orbx_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ci)); return ORBX_ERR_CUDA; }
+            e->graph_w = width; e->graph_h = height; e->graph_batch = batch;
+        }
+        const int launches = e->last_launches;           // what the capture counted
+        ORBX_CUDA(cudaGraphLaunch(e->graph, s));
+        e->last_launches = launches;
+        e->last_batch = batch;
+    } else {
+        st = orbx_extractor_run_device(e, e->d_img, fp, batch, width, height, width, e->d_kps, e->d_desc, e->d_counts, s);
+        if (st) return st;
+    }
     const size_t cap = (size_t)e->capacity;
     ORBX_CUDA(cudaMemcpyAsync(kps, e->d_kps, sizeof(orbx_keypoint) * cap * batch, cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaMemcpyAsync(desc, e->d_desc, 32 * cap * batch, cudaMemcpyDeviceToHost, s));

@@ -131,6 +131,10 @@ struct orbx_extractor {
     cudaStream_t stream;      // private stream of the _host entry point
     cudaStream_t aux;         // side stream: the blur runs next to the (under-filled) quadtree kernel
     cudaEvent_t ev_fork, ev_join;
+    // CUDA graph of the whole stage sequence on the handle's own buffers (the _host entry point: a dozen small launches per
+    // frame are launch-bound at batch 1); valid for one (width, height, batch), rebuilt when any of them changes
+    cudaGraphExec_t graph;
+    int graph_w, graph_h, graph_batch;
     cudaEvent_t ev_h2d[2];
     int last_launches;
     int last_batch;
