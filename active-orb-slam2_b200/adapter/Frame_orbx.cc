@@ -32,12 +32,11 @@ void Frame::ComputeStereoMatches()
     thread_local orbx_stereo* st = nullptr;
     if (!st)
         check(orbx_stereo_create(&st, 8192, 1, 0));
-    static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint is the 28-byte record of orbx_keypoint");
     int32_t kept = 0;
-    check(orbx_stereo_matches_host(st, orbxHandle(mpORBextractorLeft), 0, orbxHandle(mpORBextractorRight), 0,
-                                   reinterpret_cast<const orbx_keypoint*>(mvKeys.data()), mDescriptors.data, N,
-                                   reinterpret_cast<const orbx_keypoint*>(mvKeysRight.data()), mDescriptorsRight.data,
-                                   (int)mvKeysRight.size(), mbf, mb, mvuRight.data(), mvDepth.data(), &kept));
+    // mvKeys / mDescriptors and their right counterparts are exactly what the two extractors returned for this frame
+    // (Frame.cc:103-108), so the device reads them where the extractors left them
+    check(orbx_stereo_matches_extractors_host(st, orbxHandle(mpORBextractorLeft), 0, orbxHandle(mpORBextractorRight), 0, N, mbf, mb,
+                                              mvuRight.data(), mvDepth.data(), &kept));
 }
 
 // replaces Frame.cc:286-293: the tree descent of every descriptor runs on the device, the map bookkeeping of

@@ -400,4 +400,41 @@ extern "C" orbx_status orbx_stereo_matches_host(orbx_stereo *h, const orbx_extra
     return ORBX_OK;
 }
 
+// the same for the pair the two extractors' _host entry points just processed: keypoints, descriptors and counts are read from
+// the extractors' own device output buffers (mvKeys / mDescriptors are exactly what operator() returned), nothing is uploaded
+extern "C" orbx_status orbx_stereo_matches_extractors_host(orbx_stereo *h, const orbx_extractor *left, int left_slot,
+                                                           const orbx_extractor *right, int right_slot, int n_left, float bf, float b,
+                                                           float *u_right, float *depth, int32_t *n_kept) {
+    if (!h || !left || !right || n_left < 0 || (n_left && (!u_right || !depth))) return ORBX_ERR_INVALID;
+    if (n_kept) *n_kept = 0;
+    if (n_left == 0) return ORBX_OK;
+    if (left_slot < 0 || left_slot >= left->last_batch || right_slot < 0 || right_slot >= right->last_batch) {
+        orbx_set_error("orbx_stereo: slot outside the extractor's last batch");
+        return ORBX_ERR_INVALID;
+    }
+    if (left->capacity > h->max_kp || right->capacity > h->max_kp || n_left > left->capacity) {
+        orbx_set_error("orbx_stereo: extractor capacity %d / %d, handle was created for %d keypoints", left->capacity, right->capacity, h->max_kp);
+        return ORBX_ERR_CAPACITY;
+    }
+    ORBX_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    orbx_stereo_side sl = {left->d_kps + (size_t)left_slot * left->capacity, left->d_desc + (size_t)32 * left_slot * left->capacity,
+                           left->d_counts + left_slot, left->capacity, 0, left, left_slot, 0, 0};
+    orbx_stereo_side sr = {right->d_kps + (size_t)right_slot * right->capacity, right->d_desc + (size_t)32 * right_slot * right->capacity,
+                           right->d_counts + right_slot, right->capacity, 0, right, right_slot, 0, 0};
+    StereoSideDev L, R;
+    orbx_status st;
+    if ((st = stereo_side(&sl, &L, 1)) != ORBX_OK || (st = stereo_side(&sr, &R, 1)) != ORBX_OK) return st;
+    // the extractors' _host calls have returned, so their outputs and pyramids are complete; this handle's stream starts after them
+    st = stereo_launch(h, L, R, left, right, 1, left->capacity, right->capacity, bf, b, h->d_out[0], h->d_out[1], h->max_kp, h->d_kept, s);
+    if (st != ORBX_OK) return st;
+    ORBX_CUDA(cudaMemcpyAsync(u_right, h->d_out[0], sizeof(float) * n_left, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaMemcpyAsync(depth, h->d_out[1], sizeof(float) * n_left, cudaMemcpyDeviceToHost, s));
+    int32_t kept = 0;
+    ORBX_CUDA(cudaMemcpyAsync(&kept, h->d_kept, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    if (n_kept) *n_kept = kept;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_stereo_last_launches(const orbx_stereo *h) { return h ? h->last_launches : 0; }

@@ -86,6 +86,7 @@ def _declare(L):
     L.orbx_stereo_destroy.argtypes = [vp]
     L.orbx_stereo_matches_device.argtypes = [vp, vp, vp, i, f, f, vp, vp, i, vp, vp]
     L.orbx_stereo_matches_host.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, f, f, vp, vp, vp]
+    L.orbx_stereo_matches_extractors_host.argtypes = [vp, vp, i, vp, i, i, f, f, vp, vp, vp]
     L.orbx_stereo_last_launches.argtypes = [vp]
     L.orbx_pose_create.argtypes = [C.POINTER(vp), i, i, i]
     L.orbx_pose_destroy.restype = None

@@ -42,6 +42,15 @@ class StereoMatcher:
                                                C.byref(kept)))
         return ur[:n], dp[:n], kept.value
 
+    def ComputeStereoMatchesFromExtractors(self, left, right, n_left, bf, b, left_slot=0, right_slot=0):
+        """the same, for the pair the two extractor mirrors just processed through their host entry point: keypoints and descriptors
+        are read from the extractors' device buffers instead of being uploaded again"""
+        ur, dp = np.full(max(n_left, 1), -1, np.float32), np.full(max(n_left, 1), -1, np.float32)
+        kept = C.c_int32()
+        check(self._L.orbx_stereo_matches_extractors_host(self._h, left._h, left_slot, right._h, right_slot, n_left, bf, b, ur.ctypes.data,
+                                                          dp.ctypes.data, C.byref(kept)))
+        return ur[:n_left], dp[:n_left], kept.value
+
     def matches_device(self, left: StereoSide, right: StereoSide, n_pairs, bf, b, d_u_right, d_depth, out_pitch, d_kept=None, stream=0):
         check(self._L.orbx_stereo_matches_device(self._h, C.byref(left), C.byref(right), n_pairs, bf, b, d_u_right, d_depth, out_pitch,
                                                  d_kept, stream))

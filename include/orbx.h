@@ -307,6 +307,12 @@ orbx_status orbx_stereo_matches_host(orbx_stereo *h, const orbx_extractor *left,
                                      int right_slot, const orbx_keypoint *keys_l, const uint8_t *desc_l, int n_left,
                                      const orbx_keypoint *keys_r, const uint8_t *desc_r, int n_right, float bf, float b,
                                      float *u_right, float *depth, int32_t *n_kept);
+/* the same for the pair that the two extractors' orbx_extractor_run_host calls just returned: keypoints, descriptors and counts
+ * are read from the extractors' own device buffers (mvKeys / mDescriptors ARE what operator() returned), so nothing is uploaded.
+ * n_left = number of left keypoints (the count the left extractor returned for that slot). */
+orbx_status orbx_stereo_matches_extractors_host(orbx_stereo *h, const orbx_extractor *left, int left_slot, const orbx_extractor *right,
+                                                int right_slot, int n_left, float bf, float b, float *u_right, float *depth,
+                                                int32_t *n_kept);
 int orbx_stereo_last_launches(const orbx_stereo *h);
 
 /* =====================================================================================================

@@ -48,6 +48,9 @@ def test_host_entry_point(seed, w, h, nfeat, K):
     assert same_bits(ur, ref["u_right"]), np.nonzero(ur != ref["u_right"])[0][:8]
     assert same_bits(dp, ref["depth"])
     assert kept == ref["kept"] and sm.last_launches() == 2
+    # the variant that reads keypoints and descriptors from the extractors' own device buffers
+    ur2, dp2, kept2 = sm.ComputeStereoMatchesFromExtractors(el, er, len(kl), bf, b)
+    assert same_bits(ur2, ref["u_right"]) and same_bits(dp2, ref["depth"]) and kept2 == ref["kept"]
     sm.close(); el.close(); er.close()
 
 

@@ -38,7 +38,7 @@ class GpuBackend:
         return self._timed("extract", self.ex[side], img)
 
     def stereo(self, kl, dl, kr, dr, bf, b):
-        ur, dp, _ = self._timed("stereo", self.st.ComputeStereoMatches, self.ex[0], self.ex[1], kl, dl, kr, dr, bf, b)
+        ur, dp, _ = self._timed("stereo", self.st.ComputeStereoMatchesFromExtractors, self.ex[0], self.ex[1], len(kl), bf, b)
         return ur, dp
 
     def match_last(self, cur, pts, desc, R, t, fwd, bwd, th):
