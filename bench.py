@@ -672,6 +672,44 @@ def main():
         t2_1.append(ev)
     torch.cuda.synchronize()
     ms_two_lanes = max(t2_0.elapsed_time(ev) for ev in t2_1)
+    # the tracking step (extract + match + PoseOptimization) with two batches in flight: the pose kernel (one CTA per frame, a serial
+    # Levenberg chain on 64 of the 148 SMs) runs under the other lane's extraction
+    if track is not None:
+        from orbx.optimizer import PoseOptimizer
+        for L in lanes:
+            L.pz = PoseOptimizer(max_observations=B * cap, max_frames=B, device=local_rank)
+            L.d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
+            L.d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
+            L.d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+        d_is2_l = torch.from_numpy(ex.GetInverseScaleSigmaSquares()).cuda()
+
+        def step_track_lane(i):
+            step_device_lane(i)
+            L = lanes[i % 2]
+            L.pz.from_matches_device(L.jobs_dev[i % npool].data_ptr(), B, d_is2_l.data_ptr(), NLEVELS, synth.TUM1_K, L.d_pose.data_ptr(),
+                                     L.d_inl.data_ptr(), L.d_outkp.data_ptr(), cap, L.stream.cuda_stream)
+
+        for i in range(4):
+            step_track_lane(i)
+        torch.cuda.synchronize()
+        KT2 = min(K, 100)
+        t3_0 = torch.cuda.Event(enable_timing=True)
+        t3_0.record(torch.cuda.current_stream())
+        for L in lanes:
+            L.stream.wait_event(t3_0)
+        for i in range(KT2):
+            step_track_lane(i)
+        t3_1 = []
+        for L in lanes:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(L.stream)
+            t3_1.append(ev)
+        torch.cuda.synchronize()
+        ms_t2 = max(t3_0.elapsed_time(ev) for ev in t3_1) / KT2
+        track["two_lanes"] = {"frames_per_s": B / (ms_t2 * 1e-3), "ms_per_step": ms_t2,
+                              "note": "two batches in flight on two streams (two extractor / matcher / pose handles), like `value_two_lanes`"}
+        for L in lanes:
+            L.pz.close()
     h2d = B * W * H + B * ps_ + B * ds_
     d2h = B * cap * 28 + B * cap * 32 + 4 * B + 4 * B * cap + 4 * B
 
