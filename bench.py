@@ -620,7 +620,8 @@ def main():
         pass
 
     lanes = []
-    for li in range(2):
+    NLANES = 4                                          # the end-to-end loop keeps this many batches in flight; the device-resident two-lane figures use the first two
+    for li in range(NLANES):
         L = Lane()
         L.ex = ex if li == 0 else ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local_rank)
         L.mt = mt if li == 0 else ORBmatcher(0.9, True, max_keypoints=cap, max_points=cap, max_jobs=B, device=local_rank)
@@ -722,7 +723,7 @@ def main():
         return int(L.h_nm.sum())
 
     def step_host(i):
-        slot, L = i % npool, lanes[i % 2]
+        slot, L = i % npool, lanes[i % NLANES]
         got = collect(L)
         with torch.cuda.stream(L.stream):
             L.e_img.copy_(host[slot * B:(slot + 1) * B], non_blocking=True)
@@ -841,7 +842,7 @@ def main():
                        "keypoints_per_frame": kp_per_frame, "frames_per_rank": [c[0] for c in counters], "match_sweeps_max": max(match_sweeps), "match_sweeps_mean": sum(match_sweeps) / B},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pinned host frames + last-frame points -> H2D -> orbx_extractor_run_device + orbx_match_projection_frame_device -> D2H of "
-                           "keypoints, descriptors, counts, matches; two batches in flight on two streams (copies of one overlap kernels of the other), "
+                           "keypoints, descriptors, counts, matches; %d batches in flight on as many streams (copies of one overlap kernels of the others), " % NLANES +
                            "every step's results are read on the host", "matches_per_step": nm_e2e / K},
             "value_two_lanes": {"value": frames_total / (ms_two_lanes * 1e-3), "unit": "frames/s",
                                 "note": "device-resident like `value`, but two batches in flight on two streams like `e2e`; `value` itself is "
@@ -892,8 +893,9 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    lanes[1].mt.close()
-    lanes[1].ex.close()
+    for L in lanes[1:]:
+        L.mt.close()
+        L.ex.close()
     mt.close()
     ex.close()
 
