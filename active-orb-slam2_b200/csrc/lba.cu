@@ -33,7 +33,7 @@ size_t orbx_lba_fused_smem(int np);
 bool orbx_lba_fused_fits(int n_kf, int np);
 orbx_status orbx_lba_fused_init();
 orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
-                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s);
+                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s, int wide);
 
 // computeLambdaInit: max |diagonal| over every active vertex (optimization_algorithm_levenberg.cpp:166-180)
 __global__ void __launch_bounds__(LBA_THREADS) k_lba_maxdiag(LbaDev D) {
@@ -483,7 +483,7 @@ static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lb
         const bool want = capture && (res->first_Hschur || res->first_bschur || res->first_xp);
         ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 2, h->stream));   // scal[6..11]: phase timers, cleared per solve
         if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
-                                        D.scal + 4, h->stream)))
+                                        D.scal + 4, h->stream, 1)))     // one window at a time: the 16-CTA cluster
             return st;
         h->launches++;
         ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -621,10 +621,11 @@ extern "C" orbx_status orbx_lba_solve_begin(orbx_lba *h, const orbx_lba_problem 
     if (h->pending == 2) return ORBX_OK;
     cudaStream_t s = h->stream;
     ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 8, s));
-    if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its1, 1, 0, nullptr, nullptr, nullptr, D.scal + 4, s))) return st;
+    // many windows in flight: the portable 8-CTA cluster, so that 16 of them fit the device side by side
+    if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its1, 1, 0, nullptr, nullptr, nullptr, D.scal + 4, s, 0))) return st;
     if (its2 > 0) {
         k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, s>>>(D, D.level1);
-        if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its2, 0, 0, nullptr, nullptr, nullptr, D.scal + 4, s))) return st;
+        if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, its2, 0, 0, nullptr, nullptr, nullptr, D.scal + 4, s, 0))) return st;
     }
     k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, s>>>(D, h->d_flag);
     h->launches = its2 > 0 ? 4 : 2;

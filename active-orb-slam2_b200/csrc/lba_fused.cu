@@ -20,7 +20,8 @@ namespace cg = cooperative_groups;
 
 #define LF_THREADS 256
 #define LF_WARPS (LF_THREADS / 32)
-#define LF_CTAS 8
+#define LF_CTAS 8          // portable cluster size: many windows in flight
+#define LF_CTAS_WIDE 16    // opt-in (non-portable) cluster size: one window at a time, twice the warps per phase
 #define LF_MAX_KF 64
 #define LF_SLOTS 4
 
@@ -34,7 +35,7 @@ struct LfParams {
 };
 
 struct LfShared {
-    double red[LF_SLOTS][LF_CTAS][4];   // cluster reductions land in CTA 0's copy
+    double red[LF_SLOTS][LF_CTAS_WIDE][4];   // cluster reductions land in CTA 0's copy
     double tmp[32];
     double bc[4];                        // values gathered by thread 0 for the whole CTA
     double invd[6];                      // 1 / diag(U_kk) of the current pivot block
@@ -555,24 +556,42 @@ size_t orbx_lba_fused_smem(int np) {
 
 bool orbx_lba_fused_fits(int n_kf, int np) { return n_kf <= LF_MAX_KF && np >= 1 && orbx_lba_fused_smem(np) <= 200 * 1024; }
 
+static int g_wide_ok = -1;     // can this device co-schedule a 16-CTA cluster of this kernel?
+
 orbx_status orbx_lba_fused_init() {
     ORBX_CUDA(ORBX_RAISE_SMEM(k_lba_fused));
+    if (g_wide_ok < 0) {
+        g_wide_ok = 0;
+        if (cudaFuncSetAttribute(k_lba_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(LF_CTAS_WIDE); cfg.blockDim = dim3(LF_THREADS); cfg.dynamicSmemBytes = orbx_lba_fused_smem(36);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = LF_CTAS_WIDE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_lba_fused, &cfg) == cudaSuccess && n >= 1) g_wide_ok = 1;
+        }
+        cudaGetLastError();
+    }
     return ORBX_OK;
 }
 
 orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
-                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s) {
+                                  double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s, int wide) {
+    static const bool no_wide = getenv("ORBX_LBA_CLUSTER8") != nullptr;
+    const int ctas = (wide && g_wide_ok == 1 && !no_wide) ? LF_CTAS_WIDE : LF_CTAS;
     LfParams P;
     P.D = D; P.kf_bak = kf_bak; P.pt_bak = pt_bak; P.iterations = iterations; P.robust = robust; P.capture = capture;
     P.cap_Hs = cap_Hs; P.cap_bs = cap_bs; P.cap_xp = cap_xp; P.out = out;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(LF_CTAS);
+    cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(LF_THREADS);
     cfg.dynamicSmemBytes = orbx_lba_fused_smem(D.np);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = LF_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_lba_fused, P));
