@@ -315,9 +315,11 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             __threadfence();
             cl.sync();
             tick(1);
-            // (3) CTA 0: H_schur = H_pp + lambda I - sum, b_schur = b_p - sum, partials of a block in chunk order
-            if (rank == 0) {
-                for (int i = tid; i < nblk * 36; i += LF_THREADS) {
+            // (3) H_schur = H_pp + lambda I - sum, b_schur = b_p - sum, partials of a block in chunk order: every CTA finalises a
+            //     share of the entries and stores them into CTA 0's shared memory (distributed shared memory), where the solve runs
+            {
+                const double *hpp0 = cl.map_shared_rank(hpp, 0);
+                for (int i = rank * LF_THREADS + tid; i < nblk * 36; i += C * LF_THREADS) {
                     const int blk = i / 36, ab = i - 36 * blk;
                     double v = 0;
                     for (int ch = D.blk_cstart[blk]; ch < D.blk_cstart[blk + 1]; ch++) v -= __ldcg(D.part + (size_t)ch * 42 + ab);
@@ -327,15 +329,15 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                         int a = ab / 6, b = ab - 6 * a;
                         const bool dg = a == b;
                         if (a > b) { const int t = a; a = b; b = t; }
-                        v += hpp[27 * p1 + a * 6 - a * (a - 1) / 2 + (b - a)] + (dg ? lambda : 0.0);
+                        v += hpp0[27 * p1 + a * 6 - a * (a - 1) / 2 + (b - a)] + (dg ? lambda : 0.0);
                     }
-                    hs[i] = v;
+                    hs0[i] = v;
                 }
-                for (int k = tid; k < n; k += LF_THREADS) {
+                for (int k = rank * LF_THREADS + tid; k < n; k += C * LF_THREADS) {
                     const int p = k / 6, a = k - 6 * p, blk = upper_block(p, p, np);
-                    double v = hpp[27 * p + 21 + a];
+                    double v = hpp0[27 * p + 21 + a];
                     for (int ch = D.blk_cstart[blk]; ch < D.blk_cstart[blk + 1]; ch++) v -= __ldcg(D.part + (size_t)ch * 42 + 36 + a);
-                    hs[nblk * 36 + k] = v;
+                    hs0[nblk * 36 + k] = v;
                 }
             }
             cl.sync();
