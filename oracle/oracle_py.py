@@ -568,3 +568,66 @@ def predict_scale(max_distance, dist, log_scale_factor, n_levels):
     L = lib()
     L.orbo_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
     return L.orbo_predict_scale(max_distance, dist, log_scale_factor, n_levels)
+
+
+# ---- the reference's own ORBextractor (oracle/_ref/liborbextractor_ref.so, `make -C oracle ref`) ----
+REF_EXTRACTOR_SO = os.path.join(_HERE, "_ref", "liborbextractor_ref.so")
+_REF = None
+
+
+def ref_extractor_lib():
+    """The reference's src/ORBextractor.cc compiled against oracle/cvmini (None when it has not been built: the
+    reference tree exists only in the build container; the built file travels with the snapshot)."""
+    global _REF
+    if _REF is None and os.path.exists(REF_EXTRACTOR_SO):
+        lib()                                               # liborbx_oracle.so first: the stand-in's primitives live there
+        _REF = C.CDLL(REF_EXTRACTOR_SO)
+        _REF.orbref_extractor_create.restype = C.c_void_p
+        _REF.orbref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _REF.orbref_extractor_destroy.argtypes = [C.c_void_p]
+        _REF.orbref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _REF.orbref_levels.argtypes = [C.c_void_p]
+        _REF.orbref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _REF.orbref_level.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_void_p)]
+    return _REF
+
+
+class RefExtractor:
+    """ORB_SLAM2::ORBextractor itself (reference src/ORBextractor.cc:410-1132), for pinning `Extractor` above."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.R = ref_extractor_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/liborbextractor_ref.so is missing (make -C oracle ref, needs /root/reference)")
+        self.h = self.R.orbref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.nlevels, self.cap = nlevels, 4 * nfeatures + 1024
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.R.orbref_extractor_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def tables(self):
+        a = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        self.R.orbref_tables(self.h, *[_p(x) for x in a])
+        return dict(zip(["scale", "inv_scale", "sigma2", "inv_sigma2"], a))
+
+    def __call__(self, img):
+        img = np.asarray(img, np.uint8)
+        h, w = img.shape if img.ndim == 2 and img.size else (0, 0)
+        assert h == 0 or img.strides[1] == 1
+        kps, desc = np.zeros(self.cap, KP_DTYPE), np.zeros((self.cap, 32), np.uint8)
+        n = self.R.orbref_extract(self.h, img.ctypes.data if h else None, w, h, img.strides[0] if h else 0, _p(kps), _p(desc), self.cap)
+        assert n <= self.cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        """mvImagePyramid[l] with its 19-pixel pad (the view's parent buffer)"""
+        w, h, st, ptr = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+        if self.R.orbref_level(self.h, l, C.byref(w), C.byref(h), C.byref(st), C.byref(ptr)):
+            raise IndexError(l)
+        base = ptr.value - 19 * st.value - 19
+        buf = (C.c_uint8 * (st.value * (h.value + 38))).from_address(base)
+        return np.frombuffer(buf, np.uint8).reshape(h.value + 38, st.value)[:, : w.value + 38].copy()

@@ -6,11 +6,16 @@
  * include/orbx.h) links, imports or executes this code.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may use it, as the checker / CPU baseline.
  *
- * PARITY PINNING: the reference has no tests, golden vectors or fixtures and cannot be compiled
- * in this image (needs OpenCV + Eigen + Pangolin headers) => "parity unpinned" by the reference
- * itself.  What IS pinned (tests/test_oracle_cv2.py): every OpenCV primitive the extractor
- * delegates to (resize, copyMakeBorder, FAST, GaussianBlur, fastAtan2, ORB descriptor of
- * cv2.ORB.compute at octave 0) is checked bit-for-bit against cv2 4.13.
+ * PARITY PINNING: the reference has no tests, golden vectors or fixtures, and its own build (cmake + OpenCV +
+ * Eigen + Pangolin) does not run in this image.
+ *  - extractor: PINNED against the reference's own src/ORBextractor.cc, compiled unmodified against the OpenCV
+ *    stand-in oracle/cvmini into oracle/_ref/liborbextractor_ref.so (make ref): identical keypoints, descriptors
+ *    and pyramid levels (tests/test_oracle_ref_extractor.py, tests/golden/ref_extract_digests.txt).  The OpenCV
+ *    primitives behind the stand-in (resize, copyMakeBorder, FAST, GaussianBlur, fastAtan2, and cv2.ORB.compute's
+ *    descriptor at octave 0) are checked bit-for-bit against cv2 4.13 (tests/test_oracle_cv2.py).
+ *  - vocabulary bookkeeping: pinned against the reference's DBoW2 BowVector / FeatureVector (oracle/_ref/libdbow2_ref.so).
+ *  - matchers, stereo association, optimisers: "parity unpinned" by the reference (their sources need Eigen / g2o);
+ *    each file's header names the independent restatement it is checked against.
  */
 #ifndef ORBX_ORACLE_H
 #define ORBX_ORACLE_H
