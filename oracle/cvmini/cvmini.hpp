@@ -13,16 +13,30 @@
 // cv::Mat semantics that the reference relies on are kept: reference-counted buffers, ROI views that share them,
 // `create()` as a no-op on a matrix that already has the requested shape (so resize / copyMakeBorder / Mat::zeros
 // write THROUGH a view into its parent buffer, ORBextractor.cc:1037,1120,1122), clone() = compact copy of the view.
+//
+// The same header also carries what src/ORBmatcher.cc, src/Frame.cc and src/MapPoint.cc need (make ref builds them into
+// oracle/_ref/liborbmatcher_ref.so): typed matrices (8U / 32S / 32F / 64F), the small CV_32F algebra those files write with cv::Mat
+// (product, sum, difference, transpose, scaling, norm, convertTo, Mat_<float> comma initialiser), with OpenCV's arithmetic as
+// the oracle states it and tests/test_oracle_cv2.py / test_frustum_oracle.py check it against cv2: a CV_32F product of small
+// matrices is evaluated in float, left to right, without contraction; cv::norm accumulates in double.
 #pragma once
 #include <cassert>
 #include <cmath>
+#include <climits>
 #include <cstddef>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <fstream>
+#include <iostream>
 #include <list>
+#include <map>
 #include <memory>
+#include <set>
+#include <sstream>
+#include <string>
 #include <vector>
 #include "../orbx_oracle.h"
 
@@ -30,6 +44,9 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32S 4
+#define CV_32F 5
+#define CV_64F 6
 
 inline int cvRound(double v) { return (int)lrint(v); }   // round half to even, as SSE2 cvtsd2si
 inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
@@ -60,53 +77,143 @@ struct KeyPoint {                       // 28 bytes, as OpenCV's
 enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
 enum { INTER_LINEAR = 1 };
 
+inline size_t cvm_elem_size(int type) {
+    switch (type) { case CV_8U: return 1; case CV_32S: case CV_32F: return 4; case CV_64F: return 8; }
+    std::fprintf(stderr, "cvmini: unsupported matrix type %d\n", type); std::abort();
+}
+enum { NORM_L1 = 2, NORM_L2 = 4 };
+struct _OutputArray;
 struct Mat {
     std::shared_ptr<uchar> buf;         // owning buffer (shared by views)
     uchar *data;
     int rows, cols;
     size_t step;
-    struct Zeros { int rows, cols, type; };
+    int tp;                             // CV_8U, CV_32S, CV_32F or CV_64F (single channel)
+    struct Zeros { int rows, cols, type; operator Mat() const { Mat m; m = *this; return m; } };
 
-    Mat() : data(nullptr), rows(0), cols(0), step(0) {}
-    Mat(int r, int c, int) : data(nullptr), rows(0), cols(0), step(0) { create(r, c, CV_8UC1); }
-    Mat(Size s, int) : data(nullptr), rows(0), cols(0), step(0) { create(s.height, s.width, CV_8UC1); }
+    Mat() : data(nullptr), rows(0), cols(0), step(0), tp(CV_8U) {}
+    Mat(int r, int c, int t) : data(nullptr), rows(0), cols(0), step(0), tp(CV_8U) { create(r, c, t); }
+    Mat(Size s, int t) : data(nullptr), rows(0), cols(0), step(0), tp(CV_8U) { create(s.height, s.width, t); }
     // user data, not owned (cv::Mat(rows, cols, type, void *data, size_t step))
-    Mat(int r, int c, int, void *d, size_t st) : data((uchar *)d), rows(r), cols(c), step(st) {}
+    Mat(int r, int c, int t, void *d, size_t st = 0) : data((uchar *)d), rows(r), cols(c), step(st ? st : c * cvm_elem_size(t)), tp(t) {}
 
-    void create(int r, int c, int) {
-        if (data && r == rows && c == cols) return;   // cv::Mat::create keeps a matrix of the requested shape
-        buf.reset((uchar *)std::malloc((size_t)std::max(r, 1) * std::max(c, 1)), std::free);
-        data = buf.get(); rows = r; cols = c; step = (size_t)c;
+    size_t elemSize() const { return cvm_elem_size(tp); }
+    void create(int r, int c, int t) {
+        if (data && r == rows && c == cols && t == tp) return;   // cv::Mat::create keeps a matrix of the requested shape
+        const size_t e = cvm_elem_size(t);
+        buf.reset((uchar *)std::malloc((size_t)std::max(r, 1) * std::max(c, 1) * e), std::free);
+        data = buf.get(); rows = r; cols = c; step = (size_t)c * e; tp = t;
     }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
-    int type() const { return CV_8UC1; }
+    int type() const { return tp; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    size_t step1() const { return step; }
+    size_t step1() const { return step / elemSize(); }
     Mat view(int y, int x, int h, int w) const {
-        Mat m; m.buf = buf; m.data = data + (size_t)y * step + x; m.rows = h; m.cols = w; m.step = step; return m;
+        Mat m; m.buf = buf; m.data = data + (size_t)y * step + (size_t)x * elemSize(); m.rows = h; m.cols = w; m.step = step; m.tp = tp; return m;
     }
     Mat rowRange(int a, int b) const { return view(a, 0, b - a, cols); }
     Mat colRange(int a, int b) const { return view(0, a, rows, b - a); }
+    Mat row(int y) const { return view(y, 0, 1, cols); }
+    Mat col(int x) const { return view(0, x, rows, 1); }
     Mat operator()(const Rect &r) const { return view(r.y, r.x, r.height, r.width); }
-    Mat clone() const {
-        Mat m; if (empty()) return m;
-        m.create(rows, cols, CV_8UC1);
-        for (int y = 0; y < rows; y++) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, cols);
-        return m;
+    void copyTo(Mat &m) const {
+        if (empty()) { m.release(); return; }
+        m.create(rows, cols, tp);
+        for (int y = 0; y < rows; y++) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, cols * elemSize());
     }
+    inline void copyTo(const _OutputArray &o) const;
+    Mat clone() const { Mat m; copyTo(m); return m; }
+    inline void convertTo(const _OutputArray &o, int type) const;
     static Zeros zeros(int r, int c, int t) { Zeros z = {r, c, t}; return z; }
     Mat &operator=(const Zeros &z) {     // MatExpr assignment: create() (a no-op on a matching view), then fill
         create(z.rows, z.cols, z.type);
-        for (int y = 0; y < rows; y++) std::memset(data + (size_t)y * step, 0, cols);
+        for (int y = 0; y < rows; y++) std::memset(data + (size_t)y * step, 0, cols * elemSize());
         return *this;
+    }
+    static Mat ones(int r, int c, int t) {
+        assert(t == CV_32F);
+        Mat m(r, c, t);
+        for (int i = 0; i < r * c; i++) reinterpret_cast<float *>(m.data)[i] = 1.f;
+        return m;
+    }
+    static Mat eye(int r, int c, int t) {
+        assert(t == CV_32F);
+        Mat m; m = zeros(r, c, t);
+        for (int i = 0; i < std::min(r, c); i++) m.at<float>(i, i) = 1.f;
+        return m;
     }
     template <class T> T &at(int y, int x) { return *reinterpret_cast<T *>(data + (ptrdiff_t)y * (ptrdiff_t)step + x * (ptrdiff_t)sizeof(T)); }
     template <class T> const T &at(int y, int x) const { return *reinterpret_cast<const T *>(data + (ptrdiff_t)y * (ptrdiff_t)step + x * (ptrdiff_t)sizeof(T)); }
+    // single index: element i of a row or column vector (of the row-major sequence in general)
+    template <class T> T &at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
+    template <class T> const T &at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(i / cols, i % cols); }
     uchar *ptr(int y = 0) { return data + (size_t)y * step; }
     const uchar *ptr(int y = 0) const { return data + (size_t)y * step; }
     template <class T> T *ptr(int y = 0) { return reinterpret_cast<T *>(data + (size_t)y * step); }
     template <class T> const T *ptr(int y = 0) const { return reinterpret_cast<const T *>(data + (size_t)y * step); }
+    Mat t() const {
+        assert(tp == CV_32F);
+        Mat m(cols, rows, tp);
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) m.at<float>(x, y) = at<float>(y, x);
+        return m;
+    }
+    double dot(const Mat &o) const {
+        assert(tp == CV_32F && o.tp == CV_32F && rows == o.rows && cols == o.cols);
+        double s = 0;
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) s += (double)at<float>(y, x) * o.at<float>(y, x);
+        return s;
+    }
+    Mat reshape(int, int = 0) const { std::fprintf(stderr, "cvmini: Mat::reshape is not provided\n"); std::abort(); }
 };
+
+// Mat_<float>(r, c) << a, b, c ...
+template <class T> struct Mat_ : Mat {
+    Mat_(int r, int c) : Mat(r, c, sizeof(T) == 4 ? CV_32F : CV_64F) {}
+    struct Init {
+        Mat m; int i;
+        Init &operator,(T v) { reinterpret_cast<T *>(m.data)[i++] = v; return *this; }
+        operator Mat() const { return m; }
+    };
+    Init operator<<(T v) { Init it; it.m = *this; it.i = 0; it, v; return it; }
+};
+
+// CV_32F algebra.  Products of small matrices: float, left to right, every operation rounded (OpenCV's small-matrix gemm path).
+inline Mat operator*(const Mat &a, const Mat &b) {
+    assert(a.tp == CV_32F && b.tp == CV_32F && a.cols == b.rows);
+    Mat m(a.rows, b.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++)
+        for (int x = 0; x < b.cols; x++) {
+            float s = a.at<float>(y, 0) * b.at<float>(0, x);
+            for (int k = 1; k < a.cols; k++) s = s + a.at<float>(y, k) * b.at<float>(k, x);
+            m.at<float>(y, x) = s;
+        }
+    return m;
+}
+template <class F> inline Mat cvm_map2(const Mat &a, const Mat &b, F f) {
+    assert(a.tp == CV_32F && b.tp == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) m.at<float>(y, x) = f(a.at<float>(y, x), b.at<float>(y, x));
+    return m;
+}
+inline Mat operator+(const Mat &a, const Mat &b) { return cvm_map2(a, b, [](float p, float q) { return p + q; }); }
+inline Mat operator-(const Mat &a, const Mat &b) { return cvm_map2(a, b, [](float p, float q) { return p - q; }); }
+inline Mat operator*(const Mat &a, double s) { const float f = (float)s; return cvm_map2(a, a, [f](float p, float) { return p * f; }); }
+inline Mat operator*(double s, const Mat &a) { return a * s; }
+inline Mat operator/(const Mat &a, double s) { return a * (1. / s); }
+inline Mat operator-(const Mat &a) { return a * -1.0; }
+inline double norm(const Mat &a, int kind = NORM_L2) {
+    assert(a.tp == CV_32F);
+    double s = 0;
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) { const double v = a.at<float>(y, x); s += kind == NORM_L1 ? std::fabs(v) : v * v; }
+    return kind == NORM_L1 ? s : std::sqrt(s);
+}
+inline double norm(const Mat &a, const Mat &b, int kind = NORM_L2) {
+    assert(a.tp == CV_32F && b.tp == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    double s = 0;
+    for (int y = 0; y < a.rows; y++)
+        for (int x = 0; x < a.cols; x++) { const double v = (double)a.at<float>(y, x) - (double)b.at<float>(y, x); s += kind == NORM_L1 ? std::fabs(v) : v * v; }
+    return kind == NORM_L1 ? s : std::sqrt(s);
+}
 
 struct _InputArray {
     const Mat *m;
@@ -119,6 +226,7 @@ struct _OutputArray {
     Mat *m;
     _OutputArray() : m(nullptr) {}
     _OutputArray(Mat &a) : m(&a) {}
+    _OutputArray(const Mat &a) : m(const_cast<Mat *>(&a)) {}   // OpenCV has it too: lets a temporary view be a destination
     void create(int r, int c, int t) const { m->create(r, c, t); }
     void create(Size s, int t) const { m->create(s.height, s.width, t); }
     void release() const { if (m) m->release(); }
@@ -127,6 +235,43 @@ struct _OutputArray {
 typedef const _InputArray &InputArray;
 typedef const _OutputArray &OutputArray;
 inline InputArray noArray() { static _InputArray a; return a; }
+
+inline void Mat::copyTo(const _OutputArray &o) const { copyTo(*o.m); }
+inline void Mat::convertTo(const _OutputArray &o, int type) const {
+    const Mat src = *this;                              // the destination may be this very header (IL.convertTo(IL, CV_32F))
+    assert(src.tp == CV_8U && type == CV_32F);
+    Mat dst(src.rows, src.cols, type);
+    for (int y = 0; y < src.rows; y++) for (int x = 0; x < src.cols; x++) dst.at<float>(y, x) = (float)src.at<uchar>(y, x);
+    *o.m = dst;
+}
+inline std::ostream &operator<<(std::ostream &os, const Mat &m) {      // debug prints in the reference; the format is not OpenCV's
+    os << "[";
+    for (int y = 0; y < m.rows; y++) for (int x = 0; x < m.cols; x++) os << (m.tp == CV_32F ? m.at<float>(y, x) : (float)m.at<uchar>(y, x)) << (x + 1 < m.cols ? ", " : y + 1 < m.rows ? ";\n " : "");
+    return os << "]";
+}
+inline void undistortPoints(InputArray, OutputArray, InputArray, InputArray, InputArray, InputArray) {
+    std::fprintf(stderr, "cvmini: cv::undistortPoints is not provided (use zero distortion)\n"); std::abort();
+}
+
+// parsed by DBoW2's TemplatedVocabulary.h (save / load), never called by the pinned path
+struct FileNode {
+    FileNode operator[](const char *) const { return *this; }
+    FileNode operator[](const std::string &) const { return *this; }
+    FileNode operator[](int) const { return *this; }
+    size_t size() const { return 0; }
+    template <class T> operator T() const { return T(); }
+    template <class T> void operator>>(T &) const {}
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string &, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    template <class T> FileStorage &operator<<(const T &) { return *this; }
+};
 
 inline float fastAtan2(float y, float x) { return orbo_fast_atan2(y, x); }
 

@@ -631,3 +631,58 @@ class RefExtractor:
         base = ptr.value - 19 * st.value - 19
         buf = (C.c_uint8 * (st.value * (h.value + 38))).from_address(base)
         return np.frombuffer(buf, np.uint8).reshape(h.value + 38, st.value)[:, : w.value + 38].copy()
+
+
+# ---- the reference's own ORBmatcher / Frame / MapPoint (oracle/_ref/liborbmatcher_ref.so, `make -C oracle ref`) ----
+REF_MATCHER_SO = os.path.join(_HERE, "_ref", "liborbmatcher_ref.so")
+_REFM = None
+
+
+def ref_matcher_lib():
+    """src/ORBmatcher.cc + Frame.cc + MapPoint.cc + KeyFrame.cc of the reference compiled against oracle/cvmini (None if not built)."""
+    global _REFM
+    if _REFM is None and os.path.exists(REF_MATCHER_SO):
+        lib()
+        _REFM = C.CDLL(REF_MATCHER_SO)
+        _REFM.orbmref_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+        _REFM.orbmref_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        _REFM.orbmref_search_by_projection_frame.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 6 + [
+            C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        _REFM.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                                              C.c_void_p]
+    return _REFM
+
+
+def ref_hamming256(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return ref_matcher_lib().orbmref_hamming256(_p(a), _p(b))
+
+
+def ref_features_in_area(fr, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea of the reference on a grid built by its AssignFeaturesToGrid"""
+    f, keep = _oframe(fr)
+    out = np.zeros(max(f.n, 1), np.int32)
+    n = ref_matcher_lib().orbmref_features_in_area(C.byref(f), x, y, r, min_level, max_level, _p(out))
+    return out[:n].copy()
+
+
+def ref_search_by_projection_frame(cur, last_pts, last_desc, Rcw, tcw, Rlw, tlw, mono, th, nnratio=0.9, check_ori=True):
+    """the reference's ORBmatcher::SearchByProjection(Cur, Last, th, mono) -> (nmatches, match[Cur.n]); Tlw decides forward / backward"""
+    f, keep = _oframe(cur)
+    pts = np.ascontiguousarray(last_pts, LAST_POINT_DTYPE)
+    pd = np.ascontiguousarray(last_desc, np.uint8)
+    a = [np.ascontiguousarray(v, np.float32).reshape(-1) for v in (Rcw, tcw, Rlw, tlw)]
+    m = np.full(f.n, -1, np.int32)
+    n = ref_matcher_lib().orbmref_search_by_projection_frame(C.byref(f), len(pts), _p(pts), _p(pd), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]),
+                                                            int(mono), th, nnratio, int(check_ori), _p(m))
+    return n, m
+
+
+def ref_search_by_projection_points(fr, pts, pt_desc, th, nnratio=0.8):
+    """the reference's ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) -> (nmatches, match[F.n])"""
+    f, keep = _oframe(fr)
+    pts = np.ascontiguousarray(pts, TRACK_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    m = np.full(f.n, -1, np.int32)
+    n = ref_matcher_lib().orbmref_search_by_projection_points(C.byref(f), len(pts), _p(pts), _p(pd), th, nnratio, _p(m))
+    return n, m

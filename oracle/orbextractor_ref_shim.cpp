@@ -9,49 +9,18 @@
 // library (and only it: linked with -Bsymbolic) replaces operator new with a bump allocator over one reserved region,
 // so that inside the reference's code a later allocation always has the larger address.  Single-threaded by design.
 #include "ORBextractor.h"
-#include <cstdio>
 #include <cstring>
-#include <new>
-#include <sys/mman.h>
-
-namespace {
-const size_t kArenaBytes = size_t(4) << 30;        // virtual reservation; pages are touched only as they are used
-char *g_arena = nullptr;
-size_t g_used = 0;
-int g_live = 0;                                    // extractor handles alive; the arena rewinds when none is left
-void *arena_alloc(size_t n) {
-    if (!g_arena) {
-        void *p = mmap(nullptr, kArenaBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-        if (p == MAP_FAILED) { std::fprintf(stderr, "orbref: cannot reserve the arena\n"); std::abort(); }
-        g_arena = static_cast<char *>(p);
-    }
-    n = (n + 15) & ~size_t(15);
-    if (g_used + n > kArenaBytes) { std::fprintf(stderr, "orbref: arena exhausted\n"); std::abort(); }
-    void *r = g_arena + g_used;
-    g_used += n;
-    return r;
-}
-bool in_arena(void *p) { return g_arena && p >= g_arena && p < g_arena + kArenaBytes; }
-}  // namespace
-void *operator new(size_t n) { return arena_alloc(n ? n : 1); }
-void *operator new[](size_t n) { return arena_alloc(n ? n : 1); }
-void operator delete(void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete(void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+#include "ref_bump_alloc.h"
 
 extern "C" {
 void *orbref_extractor_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th) {
-    g_live++;
+    orbref_arena_retain();
     return new ORB_SLAM2::ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
 }
 void orbref_extractor_destroy(void *h) {
     if (!h) return;
     delete static_cast<ORB_SLAM2::ORBextractor *>(h);
-    if (--g_live == 0 && g_arena) {                // nothing allocated through operator new is alive any more
-        madvise(g_arena, (g_used + 4095) & ~size_t(4095), MADV_DONTNEED);
-        g_used = 0;
-    }
+    orbref_arena_release();
 }
 
 // ORBextractor::operator(): returns the number of keypoints; the first min(n, cap) are copied out (28-byte cv::KeyPoint

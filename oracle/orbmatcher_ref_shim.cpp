@@ -1,0 +1,206 @@
+// C entry points around the REFERENCE's own ORB_SLAM2::ORBmatcher, Frame and MapPoint (src/ORBmatcher.cc, src/Frame.cc,
+// src/MapPoint.cc, src/KeyFrame.cc, src/ORBextractor.cc and DBoW2's BowVector / FeatureVector, compiled unmodified from where they
+// lie under /root/reference against the OpenCV stand-in oracle/cvmini; oracle/cvmini/shadow/Converter.h replaces the one header that
+// needs Eigen).  TEST INFRASTRUCTURE ONLY: tests/test_oracle_ref_matcher.py drives it to pin oracle/match_oracle.c against the
+// reference's code.
+//
+// The entry points take the oracle's own input records (orbx_oracle.h: orbo_frame, orbo_last_point, orbo_track_point) and
+// build the reference's objects from them: a default-constructed Frame whose public members are filled in and whose grid is
+// built by the reference's AssignFeaturesToGrid(); MapPoints made by the reference's constructor from a frame row (world
+// position, descriptor) with nObs / mTrack* set.  What runs afterwards — the search loops, Frame::GetFeaturesInArea, PosInGrid,
+// DescriptorDistance, ComputeThreeMaxima, the pose algebra on cv::Mat — is the reference's code.
+#include "ORBmatcher.h"
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "KeyFrameDatabase.h"
+#include "Map.h"
+#include "MapPoint.h"
+#include "Converter.h"
+#include <cstring>
+#include <map>
+#include "ref_bump_alloc.h"
+#include "orbx_oracle.h"
+
+namespace ORB_SLAM2 {
+// Converter.cc:31-39 needs nothing but cv::Mat; the rest of that file needs Eigen
+std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat &Descriptors) {
+    std::vector<cv::Mat> v;
+    for (int j = 0; j < Descriptors.rows; j++) v.push_back(Descriptors.row(j));
+    return v;
+}
+// referenced by SetBadFlag paths that the pinned calls never reach (src/Map.cc and src/KeyFrameDatabase.cc are not built)
+static void not_built(const char *what) { std::fprintf(stderr, "orbmref: %s is not part of this build\n", what); std::abort(); }
+void Map::EraseMapPoint(MapPoint *) { not_built("Map::EraseMapPoint"); }
+void Map::EraseKeyFrame(KeyFrame *) { not_built("Map::EraseKeyFrame"); }
+void KeyFrameDatabase::erase(KeyFrame *) { not_built("KeyFrameDatabase::erase"); }
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+namespace {
+Map *the_map() {                                   // only its creation mutex is ever touched (MapPoint.cc:55,69,98)
+    static Map *m = static_cast<Map *>(std::calloc(1, sizeof(Map)));
+    return m;
+}
+cv::Mat pose4(const float R[9], const float t[3]) {
+    cv::Mat T = cv::Mat::eye(4, 4, CV_32F);
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T.at<float>(i, j) = R[3 * i + j]; T.at<float>(i, 3) = t[i]; }
+    return T;
+}
+const float kI[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, kZ[3] = {0, 0, 0};
+
+// a Frame as Frame.cc's constructors leave it, from the oracle's record
+Frame *make_frame(const orbo_frame *F) {
+    Frame *f = new Frame();
+    f->N = F->n;
+    f->mvKeys.resize(F->n);
+    if (F->n) std::memcpy(f->mvKeys.data(), F->keys_un, sizeof(cv::KeyPoint) * F->n);
+    f->mvKeysUn = f->mvKeys;
+    f->mDescriptors = cv::Mat(F->n, 32, CV_8U, const_cast<uint8_t *>(F->desc)).clone();
+    f->mvuRight.assign(F->n, -1.f);
+    if (F->u_right) f->mvuRight.assign(F->u_right, F->u_right + F->n);
+    f->mvDepth.assign(F->n, -1.f);
+    f->mvpMapPoints.assign(F->n, static_cast<MapPoint *>(NULL));
+    f->mvbOutlier.assign(F->n, false);
+    Frame::fx = F->fx; Frame::fy = F->fy; Frame::cx = F->cx; Frame::cy = F->cy;
+    Frame::invfx = 1.0f / F->fx; Frame::invfy = 1.0f / F->fy;
+    f->mbf = F->bf; f->mb = F->b;
+    Frame::mnMinX = F->min_x; Frame::mnMinY = F->min_y; Frame::mnMaxX = F->max_x; Frame::mnMaxY = F->max_y;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (Frame::mnMaxX - Frame::mnMinX);     // Frame.cc:52-53
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (Frame::mnMaxY - Frame::mnMinY);
+    Frame::mbInitialComputations = false;
+    f->mnScaleLevels = F->nlevels;
+    f->mvScaleFactors.assign(F->scale_factors, F->scale_factors + F->nlevels);
+    f->mfScaleFactor = F->nlevels > 1 ? F->scale_factors[1] : 1.2f;
+    f->mfLogScaleFactor = std::log(f->mfScaleFactor);
+    f->mvInvScaleFactors.resize(F->nlevels); f->mvLevelSigma2.resize(F->nlevels); f->mvInvLevelSigma2.resize(F->nlevels);
+    for (int l = 0; l < F->nlevels; l++) {
+        f->mvInvScaleFactors[l] = 1.0f / f->mvScaleFactors[l];
+        f->mvLevelSigma2[l] = f->mvScaleFactors[l] * f->mvScaleFactors[l];
+        f->mvInvLevelSigma2[l] = 1.0f / f->mvLevelSigma2[l];
+    }
+    f->mnId = Frame::nNextId++;
+    f->SetPose(pose4(kI, kZ));
+    f->AssignFeaturesToGrid();                     // the reference's (Frame.cc:259-274)
+    return f;
+}
+// a frame that only carries n descriptor rows (+ octaves) for MapPoint's constructor to copy from (MapPoint.cc:76-100)
+Frame *make_carrier(int n, const uint8_t *desc, const orbo_frame *like) {
+    Frame *f = new Frame();
+    f->N = n;
+    f->mvKeysUn.assign(n, cv::KeyPoint());
+    f->mDescriptors = cv::Mat(n, 32, CV_8U, const_cast<uint8_t *>(desc)).clone();
+    f->mnScaleLevels = like->nlevels;
+    f->mvScaleFactors.assign(like->scale_factors, like->scale_factors + like->nlevels);
+    f->mnId = Frame::nNextId++;
+    f->SetPose(pose4(kI, kZ));
+    return f;
+}
+MapPoint *make_point(float x, float y, float z, Frame *carrier, int row, int n_obs) {
+    cv::Mat P = (cv::Mat_<float>(3, 1) << x, y, z);
+    MapPoint *p = new MapPoint(P, the_map(), carrier, row);
+    p->nObs = n_obs;
+    return p;
+}
+// keypoints of `f` that already hold a map point with observations (the oracle's `claimed`)
+void claim(Frame *f, const orbo_frame *F, Frame *carrier, std::vector<MapPoint *> &owned) {
+    if (!F->claimed) return;
+    for (int k = 0; k < F->n; k++)
+        if (F->claimed[k]) { owned.push_back(make_point(1, 1, 1, carrier, 0, 1)); f->mvpMapPoints[k] = owned.back(); }
+}
+}  // namespace
+
+extern "C" {
+int orbmref_hamming256(const uint8_t *a, const uint8_t *b) {
+    return ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, const_cast<uint8_t *>(a)), cv::Mat(1, 32, CV_8U, const_cast<uint8_t *>(b)));
+}
+
+// Frame::GetFeaturesInArea (Frame.cc:356-409) on the grid built by Frame::AssignFeaturesToGrid
+int orbmref_features_in_area(const orbo_frame *F, float x, float y, float r, int min_level, int max_level, int *out) {
+    orbref_arena_retain();
+    Frame *f = make_frame(F);
+    const std::vector<size_t> v = f->GetFeaturesInArea(x, y, r, min_level, max_level);
+    for (size_t i = 0; i < v.size(); i++) out[i] = (int)v[i];
+    const int n = (int)v.size();
+    delete f;
+    orbref_arena_release();
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), ORBmatcher.cc:1328-1470.
+// Tlw (the last frame's pose) only decides bForward / bBackward (:1346-1351); bMono is passed through.
+int orbmref_search_by_projection_frame(const orbo_frame *Cur, int n_last, const orbo_last_point *Lp, const uint8_t *last_desc,
+                                       const float Rcw[9], const float tcw[3], const float Rlw[9], const float tlw[3], int mono,
+                                       float th, float nnratio, int check_ori, int32_t *match) {
+    orbref_arena_retain();
+    Frame *cur = make_frame(Cur);
+    cur->SetPose(pose4(Rcw, tcw));
+    // the last frame: one keypoint per record, carrying the descriptor its map point was made from
+    orbo_frame L = *Cur;
+    std::vector<orbo_keypoint> keys(n_last > 0 ? n_last : 1);
+    for (int i = 0; i < n_last; i++) { orbo_keypoint k = {0, 0, 31.f, Lp[i].angle, 0, Lp[i].octave, -1}; keys[i] = k; }
+    L.n = n_last; L.keys_un = keys.data(); L.desc = last_desc; L.u_right = NULL; L.claimed = NULL;
+    Frame *last = make_frame(&L);
+    std::vector<MapPoint *> owned;
+    std::map<MapPoint *, int> index_of;
+    for (int i = 0; i < n_last; i++) {
+        if (!Lp[i].valid) continue;                // pMP == NULL or mvbOutlier[i]: alternate between the two
+        MapPoint *p = make_point(Lp[i].x, Lp[i].y, Lp[i].z, last, i, Lp[i].blocks ? 1 : 0);
+        owned.push_back(p);
+        last->mvpMapPoints[i] = p;
+        index_of[p] = i;
+    }
+    for (int i = 0, flip = 0; i < n_last; i++)
+        if (!Lp[i].valid && (flip ^= 1)) {         // every other invalid record: a map point flagged as an outlier (:1358)
+            MapPoint *p = make_point(Lp[i].x, Lp[i].y, Lp[i].z, last, i, 1);
+            owned.push_back(p);
+            last->mvpMapPoints[i] = p;
+            last->mvbOutlier[i] = true;
+        }
+    claim(cur, Cur, last, owned);
+    last->SetPose(pose4(Rlw, tlw));
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchByProjection(*cur, *last, th, mono != 0);
+    for (int k = 0; k < Cur->n; k++) {
+        std::map<MapPoint *, int>::const_iterator it = index_of.find(cur->mvpMapPoints[k]);
+        match[k] = it == index_of.end() ? -1 : it->second;
+    }
+    for (size_t i = 0; i < owned.size(); i++) delete owned[i];
+    delete last;
+    delete cur;
+    orbref_arena_release();
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th), ORBmatcher.cc:45-129
+int orbmref_search_by_projection_points(const orbo_frame *F, int n_pts, const orbo_track_point *P, const uint8_t *pt_desc, float th,
+                                        float nnratio, int32_t *match) {
+    orbref_arena_retain();
+    Frame *f = make_frame(F);
+    Frame *carrier = make_carrier(n_pts > 0 ? n_pts : 1, pt_desc, F);
+    std::vector<MapPoint *> pts, owned;
+    std::map<MapPoint *, int> index_of;
+    for (int i = 0; i < n_pts; i++) {
+        MapPoint *p = make_point(0, 0, 1 + i, carrier, i, P[i].blocks ? 1 : 0);
+        p->mbTrackInView = P[i].in_view != 0;
+        p->mnTrackScaleLevel = P[i].level;
+        p->mTrackViewCos = P[i].view_cos;
+        p->mTrackProjX = P[i].proj_x; p->mTrackProjY = P[i].proj_y; p->mTrackProjXR = P[i].proj_xr;
+        pts.push_back(p);
+        index_of[p] = i;
+    }
+    claim(f, F, carrier, owned);
+    ORBmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(*f, pts, th);
+    for (int k = 0; k < F->n; k++) {
+        std::map<MapPoint *, int>::const_iterator it = index_of.find(f->mvpMapPoints[k]);
+        match[k] = it == index_of.end() ? -1 : it->second;
+    }
+    for (size_t i = 0; i < pts.size(); i++) delete pts[i];
+    for (size_t i = 0; i < owned.size(); i++) delete owned[i];
+    delete carrier;
+    delete f;
+    orbref_arena_release();
+    return n;
+}
+}

@@ -1,0 +1,140 @@
+"""Pins the matcher oracle (and the CUDA matcher) against the REFERENCE'S OWN ORBmatcher / Frame / MapPoint.
+
+oracle/_ref/liborbmatcher_ref.so is the reference's src/ORBmatcher.cc, Frame.cc, MapPoint.cc and KeyFrame.cc compiled unmodified
+(make -C oracle ref) against the OpenCV stand-in oracle/cvmini; the shim builds the reference's Frame and MapPoint objects from
+the oracle's input records, and the reference's code does the rest: AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea, the pose
+algebra on cv::Mat, the search loops, DescriptorDistance, the rotation histogram and ComputeThreeMaxima.
+
+ - live comparison (needs the .so, i.e. a snapshot taken from the build container): oracle == reference;
+ - tests/golden/ref_match.npz (tools/make_ref_golden.py, written from the reference build): the oracle on CPU and the CUDA
+   matcher on the GPU reproduce the reference's match arrays without the reference being present.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from orbx import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from make_ref_golden import MATCH_CASES, POINT_CASES, match_inputs, point_inputs  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "ref_match.npz")
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liborbmatcher_ref.so")),
+                               reason="oracle/_ref/liborbmatcher_ref.so is built from the reference tree (make -C oracle ref)")
+
+
+def flags(cur, R, t, Rlw, tlw, mono):
+    """bForward / bBackward as ORBmatcher.cc:1340-1351 computes them, in float"""
+    f = np.float32
+    R, t, Rlw, tlw = (np.asarray(v, f) for v in (R, t, Rlw, tlw))
+    twc = np.array([-(f(f(R[0, i] * t[0]) + f(R[1, i] * t[1])) + f(R[2, i] * t[2])) for i in range(3)], f)
+    tlc2 = f(f(f(f(Rlw[2, 0] * twc[0]) + f(Rlw[2, 1] * twc[1])) + f(Rlw[2, 2] * twc[2])) + tlw[2])
+    b = f(cur["K"][5])
+    return bool(tlc2 > b and not mono), bool(-tlc2 > b and not mono)
+
+
+def test_oracle_reproduces_the_reference_matches():
+    from oracle import oracle_py as O
+    g = np.load(GOLD)
+    for case in MATCH_CASES:
+        cur, pts, desc, R, t, Rlw, tlw = match_inputs(case)
+        fwd, bwd = flags(cur, R, t, Rlw, tlw, case[5])
+        n, m = O.search_by_projection_frame(cur, pts, desc, R, t, fwd, bwd, case[6], True)
+        assert n == int(g[case[0] + "/n"]) and np.array_equal(m, g[case[0] + "/match"]) and n > 200, case[0]
+    for case in POINT_CASES:
+        cur, tp, tdesc = point_inputs(case)
+        n, m = O.search_by_projection_points(cur, tp, tdesc, case[4], 0.8)
+        assert n == int(g[case[0] + "/n"]) and np.array_equal(m, g[case[0] + "/match"]) and n > 200, case[0]
+    for case, want in ((MATCH_CASES[1], (True, False)), (MATCH_CASES[2], (False, True)), (MATCH_CASES[3], (False, False))):
+        cur, pts, desc, R, t, Rlw, tlw = match_inputs(case)
+        assert flags(cur, R, t, Rlw, tlw, case[5]) == want
+
+
+@needs_ref
+def test_descriptor_distance_equals_the_reference():
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+        assert O.ref_hamming256(a, b) == O.hamming256(a, b)
+    z = np.zeros(32, np.uint8)
+    assert O.ref_hamming256(z, ~z) == 256 and O.ref_hamming256(z, z) == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_features_in_area_equals_the_reference(seed):
+    """Frame::AssignFeaturesToGrid + GetFeaturesInArea: same members in the same order, incl. windows that leave the image"""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    fr = synth.random_frame(rng, 1500 if seed else 300)
+    if seed == 2:                                  # undistorted bounds that do not start at 0 (Frame::ComputeImageBounds)
+        fr["bounds"] = (-12.5, -7.25, 655.0, 490.5)
+    nonempty = 0
+    for i in range(400):
+        x, y, r = rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(0.5, 80)
+        lv = [(-1, -1), (0, 3), (2, -1), (1, 2), (3, 3), (0, 0), (7, 7)][i % 7]
+        a, b = O.ref_features_in_area(fr, x, y, r, *lv), O.features_in_area(fr, x, y, r, *lv)
+        assert np.array_equal(a, b), (x, y, r, lv)
+        nonempty += len(a) > 0
+    assert nonempty > 100
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,dz,mono,th,check_ori", [(3, 0.0, 0, 7.0, 1), (4, 1.0, 0, 7.0, 1), (5, -1.0, 0, 15.0, 1), (6, 1.0, 1, 7.0, 1),
+                                                       (7, 0.0, 0, 15.0, 0), (8, 0.02, 0, 3.0, 1), (9, -0.3, 0, 7.0, 0)])
+def test_search_by_projection_last_frame_equals_the_reference(seed, dz, mono, th, check_ori):
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    cur = synth.random_frame(rng, int(rng.integers(500, 1600)))
+    pts, desc, R, t = synth.last_frame_points(rng, cur, int(rng.integers(400, 1400)))
+    Rlw, tlw = R.copy(), (t + np.array([0, 0, dz], np.float32)).astype(np.float32)
+    fwd, bwd = flags(cur, R, t, Rlw, tlw, mono)
+    n1, m1 = O.ref_search_by_projection_frame(cur, pts, desc, R, t, Rlw, tlw, mono, th, 0.9, check_ori)
+    n2, m2 = O.search_by_projection_frame(cur, pts, desc, R, t, fwd, bwd, th, check_ori)
+    assert n1 == n2 and np.array_equal(m1, m2) and n1 > 100, (n1, n2)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th,nnratio", [(10, 1.0, 0.8), (11, 3.0, 0.8), (12, 5.0, 0.8), (13, 3.0, 0.6), (14, 1.0, 0.9)])
+def test_search_by_projection_map_points_equals_the_reference(seed, th, nnratio):
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    cur = synth.random_frame(rng, int(rng.integers(500, 1600)))
+    tp, tdesc = synth.track_points(rng, cur, int(rng.integers(400, 1800)))
+    n1, m1 = O.ref_search_by_projection_points(cur, tp, tdesc, th, nnratio)
+    n2, m2 = O.search_by_projection_points(cur, tp, tdesc, th, nnratio)
+    assert n1 == n2 and np.array_equal(m1, m2) and n1 > 100, (n1, n2)
+
+
+@needs_ref
+def test_reference_still_produces_its_match_vectors():
+    from oracle import oracle_py as O
+    g = np.load(GOLD)
+    cur, pts, desc, R, t, Rlw, tlw = match_inputs(MATCH_CASES[1])
+    n, m = O.ref_search_by_projection_frame(cur, pts, desc, R, t, Rlw, tlw, 0, 7.0)
+    assert n == int(g["frame/forward/n"]) and np.array_equal(m, g["frame/forward/match"])
+
+
+@pytest.mark.gpu
+def test_cuda_matcher_reproduces_the_reference_matches():
+    """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
+    from orbx.matcher import ORBmatcher
+    g = np.load(GOLD)
+    m = ORBmatcher(0.9, True, max_keypoints=2048, max_points=2048)
+    try:
+        for case in MATCH_CASES:
+            cur, pts, desc, R, t, Rlw, tlw = match_inputs(case)
+            fwd, bwd = flags(cur, R, t, Rlw, tlw, case[5])
+            n, mm = m.SearchByProjectionLast(cur, pts, desc, R, t, fwd, bwd, case[6])
+            assert n == int(g[case[0] + "/n"]) and np.array_equal(mm, g[case[0] + "/match"]), case[0]
+        m.mfNNratio = 0.8
+        for case in POINT_CASES:
+            cur, tp, tdesc = point_inputs(case)
+            n, mm = m.SearchByProjection(cur, tp, tdesc, case[4])
+            assert n == int(g[case[0] + "/n"]) and np.array_equal(mm, g[case[0] + "/match"]), case[0]
+    finally:
+        m.close()
