@@ -650,6 +650,8 @@ def ref_matcher_lib():
             C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
         _REFM.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                               C.c_void_p]
+        _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _REFM
 
 
@@ -686,3 +688,16 @@ def ref_search_by_projection_points(fr, pts, pt_desc, th, nnratio=0.8):
     m = np.full(f.n, -1, np.int32)
     n = ref_matcher_lib().orbmref_search_by_projection_points(C.byref(f), len(pts), _p(pts), _p(pd), th, nnratio, _p(m))
     return n, m
+
+
+def ref_stereo(left, right, bf, b, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """the reference's two ORBextractors + Frame::ComputeStereoMatches on a rectified pair -> dict(keys, desc, u_right, depth)"""
+    left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+    h, w = left.shape
+    cap = 4 * nfeatures + 1024
+    k, d = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    n = ref_matcher_lib().orbmref_stereo(_p(left), _p(right), w, h, w, nfeatures, scale_factor, nlevels, ini_th, min_th, bf, b,
+                                         _p(k), _p(d), cap, _p(ur), _p(dp))
+    assert n <= cap
+    return dict(keys=k[:n].copy(), desc=d[:n].copy(), u_right=ur[:n].copy(), depth=dp[:n].copy())

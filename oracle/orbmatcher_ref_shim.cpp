@@ -203,4 +203,35 @@ int orbmref_search_by_projection_points(const orbo_frame *F, int n_pts, const or
     orbref_arena_release();
     return n;
 }
+
+// Frame::ComputeStereoMatches (Frame.cc:495-669) after the reference's two ORBextractors have run on the rectified pair, as
+// Frame's stereo constructor does (Frame.cc:95-130, without its two threads).  Outputs: the left keypoints / descriptors,
+// mvuRight and mvDepth.  Returns the number of left keypoints.
+int orbmref_stereo(const uint8_t *left, const uint8_t *right, int w, int h, int stride, int nfeatures, float scale_factor, int nlevels,
+                   int ini_th, int min_th, float bf, float b, void *keys_left, uint8_t *desc_left, int cap, float *u_right, float *depth) {
+    orbref_arena_retain();
+    ORBextractor *el = new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
+    ORBextractor *er = new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
+    Frame *f = new Frame();
+    f->mpORBextractorLeft = el; f->mpORBextractorRight = er;
+    (*el)(cv::Mat(h, w, CV_8U, const_cast<uint8_t *>(left), (size_t)stride), cv::Mat(), f->mvKeys, f->mDescriptors);
+    (*er)(cv::Mat(h, w, CV_8U, const_cast<uint8_t *>(right), (size_t)stride), cv::Mat(), f->mvKeysRight, f->mDescriptorsRight);
+    f->N = (int)f->mvKeys.size();
+    f->mvKeysUn = f->mvKeys;
+    f->mnScaleLevels = el->GetLevels();
+    f->mvScaleFactors = el->GetScaleFactors();
+    f->mvInvScaleFactors = el->GetInverseScaleFactors();
+    f->mbf = bf; f->mb = b;
+    f->ComputeStereoMatches();
+    const int n = f->N;
+    if (n <= cap) {
+        std::memcpy(keys_left, f->mvKeys.data(), sizeof(cv::KeyPoint) * n);
+        for (int i = 0; i < n; i++) std::memcpy(desc_left + 32 * (size_t)i, f->mDescriptors.ptr(i), 32);
+        std::memcpy(u_right, f->mvuRight.data(), sizeof(float) * n);
+        std::memcpy(depth, f->mvDepth.data(), sizeof(float) * n);
+    }
+    delete f; delete el; delete er;
+    orbref_arena_release();
+    return n;
+}
 }

@@ -119,6 +119,30 @@ def test_reference_still_produces_its_match_vectors():
     assert n == int(g["frame/forward/n"]) and np.array_equal(m, g["frame/forward/match"])
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,w,h,nf", [(0, 640, 480, 1000), (1, 640, 480, 1000), (2, 1241, 376, 2000), (3, 752, 480, 1200)])
+def test_compute_stereo_matches_equals_the_reference(seed, w, h, nf):
+    """the reference's two extractors + Frame::ComputeStereoMatches (Frame.cc:495-669: row table, Hamming search, 11x11 SAD over
+    +-5 px on the pyramid level, parabola fit, median cut) against the oracle chain: mvuRight / mvDepth bit for bit"""
+    from oracle import oracle_py as O
+    world = synth.stereo_world(seed, w, h)
+    left, right = world.render(0.0, 0.01, 0.0), world.render(0.0, 0.01, 0.0, right=True)
+    b = world.bf / world.fx
+    r = O.ref_stereo(left, right, world.bf, b, nf)
+    exl, exr = O.Extractor(nf), O.Extractor(nf)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    t = exl.tables()
+    o = O.stereo_matches(kl, dl, kr, dr, [exl.level(l) for l in range(8)], [exr.level(l) for l in range(8)], t["scale"], t["inv_scale"],
+                         world.bf, b)
+    assert r["keys"].tobytes() == kl.tobytes() and np.array_equal(r["desc"], dl)
+    assert r["u_right"].tobytes() == o["u_right"].tobytes() and r["depth"].tobytes() == o["depth"].tobytes()
+    assert int((r["depth"] > 0).sum()) == o["kept"] and o["kept"] > nf // 4
+    if seed == 0:                                  # the committed vector that the -m gpu stereo test reproduces is the reference's result
+        g = np.load(os.path.join(ROOT, "tests", "golden", "stereo_seed0.npz"))
+        assert r["u_right"].tobytes() == g["u_right"].tobytes() and r["depth"].tobytes() == g["depth"].tobytes()
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
