@@ -650,6 +650,7 @@ def ref_matcher_lib():
             C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
         _REFM.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                               C.c_void_p]
+        _REFM.orbmref_is_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _REFM
@@ -701,3 +702,13 @@ def ref_stereo(left, right, bf, b, nfeatures=1000, scale_factor=1.2, nlevels=8, 
                                          _p(k), _p(d), cap, _p(ur), _p(dp))
     assert n <= cap
     return dict(keys=k[:n].copy(), desc=d[:n].copy(), u_right=ur[:n].copy(), depth=dp[:n].copy())
+
+
+def ref_is_in_frustum(frame, pts):
+    """the reference's Frame::isInFrustum (+ MapPoint::PredictScale) on every record -> (TRACK_POINT_DTYPE array, the camera
+    centre mOw that the reference's Frame::UpdatePoseMatrices derived from the pose)"""
+    fr = np.ascontiguousarray(frame, FRUSTUM_FRAME_DTYPE).reshape(1)
+    p = np.ascontiguousarray(pts, FRUSTUM_POINT_DTYPE)
+    out, ow = np.zeros(max(len(p), 1), TRACK_POINT_DTYPE), np.zeros(3, np.float32)
+    ref_matcher_lib().orbmref_is_in_frustum(_p(fr), len(p), _p(p), _p(out), _p(ow))
+    return out[:len(p)], ow

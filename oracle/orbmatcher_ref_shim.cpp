@@ -9,7 +9,21 @@
 // built by the reference's AssignFeaturesToGrid(); MapPoints made by the reference's constructor from a frame row (world
 // position, descriptor) with nObs / mTrack* set.  What runs afterwards — the search loops, Frame::GetFeaturesInArea, PosInGrid,
 // DescriptorDistance, ComputeThreeMaxima, the pose algebra on cv::Mat — is the reference's code.
+#include <opencv2/core/core.hpp>                   // every standard header first: the two defines below must not reach them
+#include <mutex>
+#include <thread>
+#include <cstring>
+#include <map>
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#include "ORBVocabulary.h"
+// the shim fills in state that the reference only reaches through its map / keyframe graph (a map point's normal, distance range
+// and descriptor).  Access specifiers do not change layout or mangling, so the reference's own objects are unaffected.
+#define protected public
+#define private public
 #include "ORBmatcher.h"
+#undef protected
+#undef private
 #include "Frame.h"
 #include "KeyFrame.h"
 #include "KeyFrameDatabase.h"
@@ -233,5 +247,52 @@ int orbmref_stereo(const uint8_t *left, const uint8_t *right, int w, int h, int 
     delete f; delete el; delete er;
     orbref_arena_release();
     return n;
+}
+
+// Frame::isInFrustum (Frame.cc:298-354; MapPoint::GetMin/MaxDistanceInvariance, PredictScale MapPoint.cc:427-459) for every record.
+// Ow_out = the camera centre the reference derived from the pose (Frame::UpdatePoseMatrices).
+void orbmref_is_in_frustum(const orbo_frustum_frame *F, int n, const orbo_frustum_point *pts, orbo_track_point *out, float Ow_out[3]) {
+    orbref_arena_retain();
+    Frame *f = new Frame();
+    Frame::fx = F->fx; Frame::fy = F->fy; Frame::cx = F->cx; Frame::cy = F->cy;
+    Frame::mnMinX = F->min_x; Frame::mnMaxX = F->max_x; Frame::mnMinY = F->min_y; Frame::mnMaxY = F->max_y;
+    f->mbf = F->bf;
+    f->mnScaleLevels = F->n_levels;
+    f->mfLogScaleFactor = F->log_scale_factor;
+    f->mvScaleFactors.assign(F->n_levels, 1.f);
+    f->mnId = Frame::nNextId++;
+    f->SetPose(pose4(F->Rcw, F->tcw));
+    const cv::Mat Ow = f->GetCameraCenter();
+    for (int i = 0; i < 3; i++) Ow_out[i] = Ow.at<float>(i);
+    Frame *carrier = new Frame();
+    const uint8_t zero[32] = {0};
+    carrier->N = 1;
+    carrier->mvKeysUn.assign(1, cv::KeyPoint());
+    carrier->mDescriptors = cv::Mat(1, 32, CV_8U, const_cast<uint8_t *>(zero)).clone();
+    carrier->mnScaleLevels = F->n_levels;
+    carrier->mvScaleFactors.assign(F->n_levels, 1.f);
+    carrier->SetPose(pose4(kI, kZ));
+    for (int i = 0; i < n; i++) {
+        orbo_track_point t;
+        std::memset(&t, 0, sizeof t);
+        t.blocks = pts[i].blocks;
+        out[i] = t;
+        if (pts[i].skip) continue;                 // the caller's gates (Tracking.cc:1085-1093: isBad / already seen in this frame)
+        MapPoint *p = make_point(pts[i].x, pts[i].y, pts[i].z, carrier, 0, pts[i].blocks ? 1 : 0);
+        p->mNormalVector = (cv::Mat_<float>(3, 1) << pts[i].nx, pts[i].ny, pts[i].nz);
+        p->mfMinDistance = pts[i].min_distance;
+        p->mfMaxDistance = pts[i].max_distance;
+        if (f->isInFrustum(p, F->viewing_cos_limit)) {
+            t.in_view = p->mbTrackInView;
+            t.proj_x = p->mTrackProjX; t.proj_y = p->mTrackProjY; t.proj_xr = p->mTrackProjXR;
+            t.level = p->mnTrackScaleLevel;
+            t.view_cos = p->mTrackViewCos;
+            out[i] = t;
+        }
+        delete p;
+    }
+    delete carrier;
+    delete f;
+    orbref_arena_release();
 }
 }

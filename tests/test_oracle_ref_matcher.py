@@ -143,6 +143,27 @@ def test_compute_stereo_matches_equals_the_reference(seed, w, h, nf):
         assert r["u_right"].tobytes() == g["u_right"].tobytes() and r["depth"].tobytes() == g["depth"].tobytes()
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_is_in_frustum_equals_the_reference(seed):
+    """Frame::isInFrustum + MapPoint::PredictScale (Frame.cc:298-354, MapPoint.cc:427-459) on 4000 map points around the camera:
+    every record bit-equal (projection, stereo coordinate, viewing cosine, predicted level, all five gates)"""
+    from oracle import oracle_py as O
+    frame, pts = synth.frustum_scene(seed)
+    fr = np.zeros(1, O.FRUSTUM_FRAME_DTYPE)
+    for k, v in frame.items():
+        fr[k] = v
+    p = np.zeros(len(pts["x"]), O.FRUSTUM_POINT_DTYPE)
+    for k, v in pts.items():
+        p[k] = v
+    ref, ow = O.ref_is_in_frustum(fr[0], p)
+    assert np.allclose(ow, fr["Ow"][0], atol=1e-6)
+    fr["Ow"][0] = ow                               # mOw as the reference computes it (float; the scene generator used double)
+    got = O.is_in_frustum(fr[0], p)
+    assert got.tobytes() == ref.tobytes()
+    assert 500 < got["in_view"].sum() < 3000 and len(set(got["level"][got["in_view"] == 1].tolist())) >= 6
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
