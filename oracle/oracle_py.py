@@ -377,8 +377,11 @@ def bucket_valid(mode, A, B):
     return A["has_mp"], B["has_mp"]
 
 
-def match_buckets(mode, A, B, nnratio=0.75, check_ori=True, only_stereo=False, F12=None, epipole=(0, 0), sigma2=None, scale=None):
-    """mode 0 SearchByBoW(KF,F), 1 SearchByBoW(KF,KF), 2 SearchForTriangulation -> (nmatches, match_a)"""
+def match_buckets(mode, A, B, nnratio=0.75, check_ori=True, only_stereo=False, F12=None, epipole=(0, 0), sigma2=None, scale=None,
+                  use_reference=False):
+    """mode 0 SearchByBoW(KF,F), 1 SearchByBoW(KF,KF), 2 SearchForTriangulation -> (nmatches, match_a).
+    use_reference: run the reference's own functions on KeyFrames built from the same records (oracle/_ref/liborbmatcher_ref.so)
+    -> (nmatches, match_a, the epipole the reference derived from its two poses, to be given to the oracle for mode 2)"""
     L = lib()
     L.orbo_match_buckets.argtypes = [C.POINTER(OBucketJob), C.c_void_p]
     J, keep = OBucketJob(), []
@@ -392,6 +395,10 @@ def match_buckets(mode, A, B, nnratio=0.75, check_ori=True, only_stereo=False, F
     sc = np.ascontiguousarray(scale if scale is not None else np.ones(8), np.float32)
     J.sigma2_b, J.scale_b = s2.ctypes.data, sc.ctypes.data
     m = np.zeros(max(J.a.n, 1), np.int32)
+    if use_reference:
+        epi = np.zeros(2, np.float32)
+        n = ref_matcher_lib().orbmref_match_buckets(C.byref(J), len(sc), _p(m), _p(epi))
+        return n, m[:J.a.n], (float(epi[0]), float(epi[1]))
     n = L.orbo_match_buckets(C.byref(J), _p(m))
     return n, m[:J.a.n]
 
@@ -651,6 +658,11 @@ def ref_matcher_lib():
         _REFM.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                               C.c_void_p]
         _REFM.orbmref_is_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _REFM.orbmref_match_buckets.argtypes = [C.POINTER(OBucketJob), C.c_int, C.c_void_p, C.c_void_p]
+        _REFM.orbmref_search_for_initialization.argtypes = [C.POINTER(OFrame), C.POINTER(OFrame), C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                                            C.c_void_p]
+        _REFM.orbmref_distinctive_descriptors.restype = None
+        _REFM.orbmref_distinctive_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _REFM
@@ -712,3 +724,22 @@ def ref_is_in_frustum(frame, pts):
     out, ow = np.zeros(max(len(p), 1), TRACK_POINT_DTYPE), np.zeros(3, np.float32)
     ref_matcher_lib().orbmref_is_in_frustum(_p(fr), len(p), _p(p), _p(out), _p(ow))
     return out[:len(p)], ow
+
+
+def ref_search_for_initialization(F1, F2, prev_xy, window_size=100, nnratio=0.9, check_ori=True):
+    """the reference's ORBmatcher::SearchForInitialization -> (nmatches, match12)"""
+    f1, k1 = _oframe(F1)
+    f2, k2 = _oframe(F2)
+    pv = np.ascontiguousarray(prev_xy, np.float32)
+    m = np.full(max(f1.n, 1), -1, np.int32)
+    n = ref_matcher_lib().orbmref_search_for_initialization(C.byref(f1), C.byref(f2), _p(pv), window_size, nnratio, int(check_ori), _p(m))
+    return n, m[:f1.n]
+
+
+def ref_distinctive_descriptors(start, desc):
+    """the reference's MapPoint::ComputeDistinctiveDescriptors per CSR group -> chosen descriptors [n, 32]"""
+    st = np.ascontiguousarray(start, np.int32)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    out = np.zeros((max(len(st) - 1, 1), 32), np.uint8)
+    ref_matcher_lib().orbmref_distinctive_descriptors(len(st) - 1, _p(st), _p(d), _p(out))
+    return out[:len(st) - 1]

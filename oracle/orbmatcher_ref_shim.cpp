@@ -295,4 +295,131 @@ void orbmref_is_in_frustum(const orbo_frustum_frame *F, int n, const orbo_frustu
     delete f;
     orbref_arena_release();
 }
+
+// ---- the vocabulary-node matchers on KeyFrames built by the reference's KeyFrame(Frame&, Map*, KeyFrameDatabase*) ----
+namespace {
+const float kK[6] = {517.306408f, 516.469215f, 318.643040f, 255.313989f, 40.0f, 40.0f / 517.306408f};   // TUM1, like orbx.synth
+Frame *frame_from_set(const orbo_bow_set *S, int nlevels, const float *scale, const float *sigma2) {
+    orbo_frame F;
+    std::memset(&F, 0, sizeof F);
+    F.n = S->n; F.keys_un = S->keys_un; F.desc = S->desc; F.u_right = S->u_right;
+    F.min_x = 0; F.min_y = 0; F.max_x = 640; F.max_y = 480;
+    F.fx = kK[0]; F.fy = kK[1]; F.cx = kK[2]; F.cy = kK[3]; F.bf = kK[4]; F.b = kK[5];
+    F.scale_factors = scale; F.nlevels = nlevels;
+    Frame *f = make_frame(&F);
+    f->mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+    for (int j = 0; j < S->n_nodes; j++)
+        for (int k = S->node_start[j]; k < S->node_start[j + 1]; k++) f->mFeatVec.addFeature(S->node_id[j], (unsigned)S->node_feat[k]);
+    return f;
+}
+void give_points(Frame *f, const orbo_bow_set *S, bool where_valid, std::vector<MapPoint *> &owned, std::map<MapPoint *, int> &index_of) {
+    for (int i = 0; i < S->n; i++)
+        if ((S->valid[i] != 0) == where_valid) {
+            MapPoint *p = make_point(1, 1, 1 + i, f, i, 1);
+            owned.push_back(p);
+            f->mvpMapPoints[i] = p;
+            index_of[p] = i;
+        }
+}
+}  // namespace
+
+// mode 0 SearchByBoW(KF, F) :159-288, 1 SearchByBoW(KF, KF) :522-655, 2 SearchForTriangulation :657-823.  match_a as the oracle defines
+// it.  Mode 2 places camera 1 at the origin and camera 2 at a translation whose epipole is near (J->ex, J->ey); the epipole the
+// reference then derives from the two poses (:663-669) is returned in epipole_out for the oracle to use.
+int orbmref_match_buckets(const orbo_bucket_job *J, int nlevels, int32_t *match_a, float epipole_out[2]) {
+    orbref_arena_retain();
+    Frame *fa = frame_from_set(&J->a, nlevels, J->scale_b, J->sigma2_b), *fb = frame_from_set(&J->b, nlevels, J->scale_b, J->sigma2_b);
+    std::vector<MapPoint *> owned;
+    std::map<MapPoint *, int> in_a, in_b;
+    give_points(fa, &J->a, J->mode != 2, owned, in_a);
+    if (J->mode != 0) give_points(fb, &J->b, J->mode != 2, owned, in_b);
+    if (J->mode == 2) {
+        const float t[3] = {(J->ex - kK[2]) / kK[0], (J->ey - kK[3]) / kK[1], 1.0f};
+        fb->SetPose(pose4(kI, t));
+    }
+    KeyFrame *ka = new KeyFrame(*fa, the_map(), NULL), *kb = J->mode != 0 ? new KeyFrame(*fb, the_map(), NULL) : NULL;
+    ORBmatcher matcher(J->nnratio, J->check_ori != 0);
+    for (int i = 0; i < J->a.n; i++) match_a[i] = -1;
+    int n = 0;
+    if (J->mode == 0) {
+        std::vector<MapPoint *> m;
+        n = matcher.SearchByBoW(ka, *fb, m);
+        for (int k = 0; k < (int)m.size(); k++)
+            if (m[k]) match_a[in_a.at(m[k])] = k;
+    } else if (J->mode == 1) {
+        std::vector<MapPoint *> m;
+        n = matcher.SearchByBoW(ka, kb, m);
+        for (int i = 0; i < (int)m.size(); i++)
+            if (m[i]) match_a[i] = in_b.at(m[i]);
+    } else {
+        cv::Mat F12(3, 3, CV_32F);
+        for (int i = 0; i < 9; i++) F12.at<float>(i / 3, i % 3) = J->F12[i];
+        std::vector<std::pair<size_t, size_t> > pairs;
+        n = matcher.SearchForTriangulation(ka, kb, F12, pairs, J->only_stereo != 0);
+        for (size_t i = 0; i < pairs.size(); i++) match_a[pairs[i].first] = (int32_t)pairs[i].second;
+        const cv::Mat C2 = kb->GetRotation() * ka->GetCameraCenter() + kb->GetTranslation();    // as :663-669
+        const float invz = 1.0f / C2.at<float>(2);
+        epipole_out[0] = kb->fx * C2.at<float>(0) * invz + kb->cx;
+        epipole_out[1] = kb->fy * C2.at<float>(1) * invz + kb->cy;
+    }
+    delete ka; delete kb;
+    for (size_t i = 0; i < owned.size(); i++) delete owned[i];
+    delete fa; delete fb;
+    orbref_arena_release();
+    return n;
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:405-520
+int orbmref_search_for_initialization(const orbo_frame *F1, const orbo_frame *F2, const float *prev_xy, int window_size, float nnratio,
+                                      int check_ori, int32_t *match12) {
+    orbref_arena_retain();
+    Frame *f1 = make_frame(F1), *f2 = make_frame(F2);
+    std::vector<cv::Point2f> prev(F1->n);
+    for (int i = 0; i < F1->n; i++) prev[i] = cv::Point2f(prev_xy[2 * i], prev_xy[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchForInitialization(*f1, *f2, prev, m12, window_size);
+    for (int i = 0; i < F1->n; i++) match12[i] = m12[i];
+    delete f1; delete f2;
+    orbref_arena_release();
+    return n;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:275-340) for n map points; observation j of point i is row start[i] + j of
+// desc.  Keyframe j holds, in row i, the descriptor of point i's j-th observation; mObservations is keyed by KeyFrame*, so its
+// iteration order is pointer order = creation order under this library's allocator = j.  best_desc[i] = the chosen descriptor.
+void orbmref_distinctive_descriptors(int n, const int32_t *start, const uint8_t *desc, uint8_t *best_desc) {
+    orbref_arena_retain();
+    int max_obs = 0;
+    for (int i = 0; i < n; i++) max_obs = std::max(max_obs, start[i + 1] - start[i]);
+    const float sf[1] = {1.f};
+    std::vector<orbo_keypoint> keys(std::max(n, 1));
+    std::memset(keys.data(), 0, sizeof(orbo_keypoint) * keys.size());
+    std::vector<Frame *> frames;
+    std::vector<KeyFrame *> kfs;
+    std::vector<uint8_t> rows((size_t)std::max(n, 1) * 32);
+    for (int j = 0; j < max_obs; j++) {
+        for (int i = 0; i < n; i++)
+            if (j < start[i + 1] - start[i]) std::memcpy(&rows[(size_t)i * 32], desc + (size_t)(start[i] + j) * 32, 32);
+        orbo_frame F;
+        std::memset(&F, 0, sizeof F);
+        F.n = n; F.keys_un = keys.data(); F.desc = rows.data();
+        F.max_x = 640; F.max_y = 480; F.fx = F.fy = 500; F.scale_factors = sf; F.nlevels = 1;
+        frames.push_back(make_frame(&F));
+        kfs.push_back(new KeyFrame(*frames.back(), the_map(), NULL));
+    }
+    for (int i = 0; i < n; i++) {
+        const int cnt = start[i + 1] - start[i];
+        std::memset(best_desc + (size_t)i * 32, 0, 32);
+        if (cnt == 0) continue;
+        MapPoint *p = make_point(1, 1, 1, frames[0], i, 0);
+        for (int j = 0; j < cnt; j++) p->mObservations[kfs[j]] = (size_t)i;
+        p->ComputeDistinctiveDescriptors();
+        const cv::Mat d = p->GetDescriptor();
+        std::memcpy(best_desc + (size_t)i * 32, d.ptr(0), 32);
+        delete p;
+    }
+    for (size_t j = 0; j < kfs.size(); j++) { delete kfs[j]; delete frames[j]; }
+    orbref_arena_release();
+}
 }

@@ -164,6 +164,52 @@ def test_is_in_frustum_equals_the_reference(seed):
     assert 500 < got["in_view"].sum() < 3000 and len(set(got["level"][got["in_view"] == 1].tolist())) >= 6
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_vocabulary_node_matchers_equal_the_reference(seed):
+    """SearchByBoW(KF, F), SearchByBoW(KF, KF) and SearchForTriangulation (+ CheckDistEpipolarLine) on KeyFrames that the reference's
+    own KeyFrame constructor built from the records; the epipole is the one the reference derives from its two poses"""
+    from oracle import oracle_py as O
+    A, B, F12, epi, s2, sc = synth.bow_pair(seed, 900, 1000, 500)
+    total = 0
+    for mode, kw in [(0, {}), (1, {}), (2, dict(only_stereo=False)), (2, dict(only_stereo=True)), (0, dict(check_ori=False, nnratio=0.9)),
+                     (1, dict(nnratio=0.6)), (2, dict(check_ori=False))]:
+        for e_in in ((epi,) if mode != 2 else (epi, (300.0, 200.0))):       # second epipole: inside the image, so the :743-749 gate bites
+            n1, m1, e = O.match_buckets(mode, A, B, F12=F12, epipole=e_in, sigma2=s2, scale=sc, use_reference=True, **kw)
+            n2, m2 = O.match_buckets(mode, A, B, F12=F12, epipole=e if mode == 2 else e_in, sigma2=s2, scale=sc, **kw)
+            assert n1 == n2 and np.array_equal(m1, m2), (mode, kw, e_in)
+            total += n1
+    assert total > 500
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_for_initialization_equals_the_reference(seed):
+    from oracle import oracle_py as O
+    from test_match_oracle import init_pair
+    F1, F2, prev = init_pair(80 + seed, 700)
+    for win, ratio, ori in ((30, 0.9, True), (100, 0.9, True), (100, 0.7, False)):
+        n1, m1 = O.ref_search_for_initialization(F1, F2, prev, win, ratio, ori)
+        n2, m2 = O.search_for_initialization(F1, F2, prev, win, ratio, ori)
+        assert n1 == n2 and np.array_equal(m1, m2) and n1 > 20
+
+
+@needs_ref
+def test_distinctive_descriptors_equal_the_reference():
+    """MapPoint::ComputeDistinctiveDescriptors over observations held by the reference's KeyFrames: the chosen descriptor"""
+    from oracle import oracle_py as O
+    from test_mappoint_oracle import observation_sets, to_csr
+    for seed in range(2):
+        sets = observation_sets(seed, n_points=150, max_obs=30)
+        start, desc = to_csr(sets)
+        bi, bm = O.distinctive_descriptors(start, desc)
+        ref = O.ref_distinctive_descriptors(start, desc)
+        for i in range(len(sets)):
+            if bi[i] >= 0:
+                assert np.array_equal(ref[i], desc[start[i] + bi[i]]), i
+        assert (bi > 0).sum() > 30
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
