@@ -6,7 +6,11 @@
  * `d < best_d`), remember the node passed at level L - levelsup, stop at a leaf; return its word id and weight.
  * The caller-side loop (TemplatedVocabulary.h:1138-1200: addWeight / addFeature per feature, L1 normalisation) is map
  * bookkeeping on these per-feature results and is done by the host adapter in the reference's own order.
- * PARITY PINNING: unpinned by the reference's tests (it has none); tests/test_bow_oracle.py checks this file against an
+ * PARITY PINNING: the reference has no tests.  PINNED against the reference's own ORBVocabulary (DBoW2 TemplatedVocabulary<FORB>,
+ * its loadFromTextFile and transform, compiled into oracle/_ref/liborbmatcher_ref.so): same word per feature, bit-identical
+ * BowVector, same FeatureVector for every weighting / scoring pair tried (tests/test_oracle_ref_matcher.py).  One defined choice:
+ * for a branch that ends above level L - levelsup the reference never writes `nid` (an uninitialised NodeId in the caller,
+ * TemplatedVocabulary.h:1160-1170); oracle and kernel return node 0.  tests/test_bow_oracle.py also checks this file against an
  * independent numpy statement on synthetic trees and on the reference's own Vocabulary/ORBvoc.bin.
  */
 #include "orbx_oracle.h"

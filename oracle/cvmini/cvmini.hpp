@@ -259,7 +259,10 @@ struct FileNode {
     FileNode operator[](const std::string &) const { return *this; }
     FileNode operator[](int) const { return *this; }
     size_t size() const { return 0; }
-    template <class T> operator T() const { return T(); }
+    operator int() const { return 0; }
+    operator float() const { return 0.f; }
+    operator double() const { return 0.; }
+    operator std::string() const { return std::string(); }
     template <class T> void operator>>(T &) const {}
 };
 struct FileStorage {

@@ -8,7 +8,9 @@
  *                     fewer than 4 elements) -- NOT reachable from Python, so this one is restated from the OpenCV source
  *   PredictScale      ceil(log(ratio)/mfLogScaleFactor) with float arguments = logf / ceilf (MapPoint.cc includes <math.h>)
  * Compile with -ffp-contract=off.  logf is libm's.
- * PARITY PINNING: unpinned by the reference (no test for this function).
+ * PARITY PINNING: the reference holds no test for this function.  PINNED against the reference's own Frame::isInFrustum +
+ * MapPoint::PredictScale run from source (oracle/_ref/liborbmatcher_ref.so): bit-equal records on 16 k map points
+ * (tests/test_oracle_ref_matcher.py::test_is_in_frustum_equals_the_reference).
  */
 #include "orbx_oracle.h"
 #include <math.h>

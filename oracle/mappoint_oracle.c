@@ -4,7 +4,9 @@
  * observations, keep the one with the least median Hamming distance to the others.  Restated as the reference does it:
  * the full N x N distance matrix (float entries holding integers), every row sorted, median = vDists[0.5*(N-1)], the
  * first row with a strictly smaller median wins (BestMedian starts at INT_MAX).
- * PARITY PINNING: unpinned by the reference (no test); tests/test_mappoint_oracle.py checks it against numpy.
+ * PARITY PINNING: the reference holds no test.  PINNED against the reference's own MapPoint::ComputeDistinctiveDescriptors run
+ * from source over observations held by its KeyFrames (oracle/_ref/liborbmatcher_ref.so, tests/test_oracle_ref_matcher.py): the
+ * same descriptor is chosen.  tests/test_mappoint_oracle.py also checks it against numpy.
  */
 #include "orbx_oracle.h"
 #include <limits.h>

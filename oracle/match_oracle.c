@@ -8,9 +8,14 @@
  *   ORBmatcher::ComputeThreeMaxima                                          src/ORBmatcher.cc:1601-1642
  * cv::Mat float products are plain sequential float arithmetic (verified against cv2.gemm):
  * ((r0*x0 + r1*x1) + r2*x2) + t.  Compile with -ffp-contract=off.
- * PARITY PINNING: the reference holds no tests or vectors for this path => unpinned by the reference; the
- * restatement is line-by-line and tests/test_match_oracle.py cross-checks it against an independent numpy
- * brute-force statement of the same rules.
+ * PARITY PINNING: the reference holds no tests or vectors for this path.  PINNED against the reference's own code run here:
+ * src/ORBmatcher.cc, Frame.cc, MapPoint.cc and KeyFrame.cc compile unmodified against the OpenCV stand-in oracle/cvmini into
+ * oracle/_ref/liborbmatcher_ref.so (make ref), and tests/test_oracle_ref_matcher.py gets identical results from the reference's
+ * DescriptorDistance, AssignFeaturesToGrid + GetFeaturesInArea, SearchByProjection(Cur, Last) (all forward / backward / mono
+ * modes), SearchByProjection(Frame, MapPoints), SearchByBoW x2, SearchForTriangulation and SearchForInitialization.  Still
+ * unpinned by the reference: the relocalisation / loop-closing / Fuse / Sim3 window searches (orbo_search_by_projection_kf,
+ * orbo_match_window), whose oracle entry points take gates that the adapter evaluates on the host.  tests/test_match_oracle.py
+ * additionally cross-checks every function against an independent numpy brute-force statement of the same rules.
  */
 #include "orbx_oracle.h"
 #include <math.h>

@@ -663,6 +663,10 @@ def ref_matcher_lib():
                                                             C.c_void_p]
         _REFM.orbmref_distinctive_descriptors.restype = None
         _REFM.orbmref_distinctive_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _REFM.orbvref_load_text.restype = C.c_void_p
+        _REFM.orbvref_load_text.argtypes = [C.c_char_p]
+        _REFM.orbvref_destroy.argtypes = [C.c_void_p]
+        _REFM.orbvref_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _REFM
@@ -743,3 +747,43 @@ def ref_distinctive_descriptors(start, desc):
     out = np.zeros((max(len(st) - 1, 1), 32), np.uint8)
     ref_matcher_lib().orbmref_distinctive_descriptors(len(st) - 1, _p(st), _p(d), _p(out))
     return out[:len(st) - 1]
+
+
+def write_vocabulary_text(path, parent, desc, weight, is_leaf, k, L, scoring=0, weighting=0):
+    """a vocabulary in the text format of TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1349-1440): header `k L scoring
+    weighting`, then one line per node `parent is_leaf d0 .. d31 weight`.  No trailing newline (the loader's eof() loop would
+    otherwise append an empty node); weights are printed with 17 digits so that the parsed double is the float32 value."""
+    lines = ["%d %d %d %d" % (k, L, scoring, weighting)]
+    for p, d, w, lf in zip(parent.tolist(), np.asarray(desc, np.uint8).tolist(), np.asarray(weight, np.float32).tolist(), is_leaf.tolist()):
+        lines.append("%d %d %s %.17g" % (p, int(lf), " ".join(str(x) for x in d), w))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    """ORB_SLAM2::ORBVocabulary (DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>) loaded by the reference's own loader"""
+
+    def __init__(self, path):
+        self.R = ref_matcher_lib()
+        self.h = self.R.orbvref_load_text(path.encode())
+        if not self.h:
+            raise RuntimeError("the reference could not load %s" % path)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.R.orbvref_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def transform(self, desc, levelsup=4):
+        """-> (word id per feature, BowVector dict, FeatureVector dict) as Frame::ComputeBoW obtains them"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word = np.zeros(max(n, 1), np.int32)
+        bid, bval, nb = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64), C.c_int32()
+        fid, fst, ff, nf = np.zeros(max(n, 1), np.uint32), np.zeros(n + 2, np.int32), np.zeros(max(n, 1), np.uint32), C.c_int32()
+        self.R.orbvref_transform(self.h, _p(d), n, levelsup, _p(word), _p(bid), _p(bval), C.byref(nb), _p(fid), _p(fst), _p(ff), C.byref(nf))
+        bow = {int(bid[i]): float(bval[i]) for i in range(nb.value)}
+        fv = {int(fid[i]): ff[fst[i]:fst[i + 1]].astype(int).tolist() for i in range(nf.value)}
+        return word[:n].copy(), bow, fv

@@ -422,4 +422,40 @@ void orbmref_distinctive_descriptors(int n, const int32_t *start, const uint8_t 
     for (size_t j = 0; j < kfs.size(); j++) { delete kfs[j]; delete frames[j]; }
     orbref_arena_release();
 }
+
+// ---- DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB> (ORBVocabulary): the reference's loader and transform ----
+void *orbvref_load_text(const char *path) {
+    orbref_arena_retain();
+    ORBVocabulary *v = new ORBVocabulary();
+    if (!v->loadFromTextFile(path)) { delete v; orbref_arena_release(); return NULL; }
+    return v;
+}
+void orbvref_destroy(void *h) {
+    if (!h) return;
+    delete static_cast<ORBVocabulary *>(h);
+    orbref_arena_release();
+}
+// transform(features, BowVector, FeatureVector, levelsup) (TemplatedVocabulary.h:1138-1219) as Frame::ComputeBoW calls it, plus the
+// per-feature word id (transform(feature), :1061-1074).  BowVector -> (bow_id, bow_val)[*n_bow]; FeatureVector -> node ids
+// fv_id[*n_fv], CSR starts fv_start[*n_fv + 1], feature indices fv_feat.
+void orbvref_transform(void *h, const uint8_t *desc, int n, int levelsup, int32_t *word, uint32_t *bow_id, double *bow_val, int32_t *n_bow,
+                       uint32_t *fv_id, int32_t *fv_start, uint32_t *fv_feat, int32_t *n_fv) {
+    const ORBVocabulary &voc = *static_cast<ORBVocabulary *>(h);
+    const std::vector<cv::Mat> feats = Converter::toDescriptorVector(cv::Mat(n, 32, CV_8U, const_cast<uint8_t *>(desc)));
+    for (int i = 0; i < n; i++) word[i] = (int32_t)voc.transform(feats[i]);
+    DBoW2::BowVector bv;
+    DBoW2::FeatureVector fv;
+    voc.transform(feats, bv, fv, levelsup);
+    int k = 0;
+    for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++k) { bow_id[k] = it->first; bow_val[k] = it->second; }
+    *n_bow = k;
+    k = 0;
+    int at = 0;
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++k) {
+        fv_id[k] = it->first; fv_start[k] = at;
+        for (size_t j = 0; j < it->second.size(); j++) fv_feat[at++] = it->second[j];
+    }
+    fv_start[k] = at;
+    *n_fv = k;
+}
 }

@@ -13,9 +13,12 @@
  *    and pyramid levels (tests/test_oracle_ref_extractor.py, tests/golden/ref_extract_digests.txt).  The OpenCV
  *    primitives behind the stand-in (resize, copyMakeBorder, FAST, GaussianBlur, fastAtan2, and cv2.ORB.compute's
  *    descriptor at octave 0) are checked bit-for-bit against cv2 4.13 (tests/test_oracle_cv2.py).
- *  - vocabulary bookkeeping: pinned against the reference's DBoW2 BowVector / FeatureVector (oracle/_ref/libdbow2_ref.so).
- *  - matchers, stereo association, optimisers: "parity unpinned" by the reference (their sources need Eigen / g2o);
- *    each file's header names the independent restatement it is checked against.
+ *  - matchers, Frame grid, stereo association, isInFrustum, distinctive descriptors, vocabulary transform: PINNED against
+ *    the reference's own src/ORBmatcher.cc, Frame.cc, MapPoint.cc, KeyFrame.cc and DBoW2 sources, compiled unmodified into
+ *    oracle/_ref/liborbmatcher_ref.so (tests/test_oracle_ref_matcher.py, tests/golden/ref_match.npz); vocabulary bookkeeping
+ *    also against oracle/_ref/libdbow2_ref.so.  See each file's header for the exact functions.
+ *  - the two optimisers (lba_oracle.c, pose_oracle.c): "parity unpinned" by the reference — src/Optimizer.cc needs g2o, which
+ *    needs Eigen, absent from this image; their headers name the independent restatements they are checked against.
  */
 #ifndef ORBX_ORACLE_H
 #define ORBX_ORACLE_H

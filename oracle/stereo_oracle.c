@@ -9,8 +9,10 @@
  * OpenCV arithmetic on the path: Mat::convertTo(CV_32F), IL - IL(w,w)*ones, cv::norm(IL, IR, NORM_L1).  All operands are
  * integer-valued floats below 2^24, so the L1 norm is an exact integer whatever the accumulation order or width
  * (tests/test_stereo_oracle.py checks the SAD against cv2.norm on float patches).  Compile with -ffp-contract=off.
- * PARITY PINNING: unpinned by the reference (it holds no test for this function); cross-checked against an independent
- * numpy / cv2 statement of the same rules.
+ * PARITY PINNING: the reference holds no test for this function.  PINNED against the reference's own code run here: its two
+ * ORBextractors + Frame::ComputeStereoMatches, compiled unmodified into oracle/_ref/liborbmatcher_ref.so, give bit-identical
+ * mvuRight / mvDepth on VGA-, EuRoC- and KITTI-shaped pairs (tests/test_oracle_ref_matcher.py).  Also cross-checked against an
+ * independent numpy / cv2 statement of the same rules.
  *
  * Where the reference has undefined behaviour the oracle (and the CUDA path) define it:
  *   - a row-table index outside [0, nRows) (:518-521) is skipped (cannot happen for extractor keypoints: they keep 19 px

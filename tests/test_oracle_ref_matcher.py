@@ -210,6 +210,33 @@ def test_distinctive_descriptors_equal_the_reference():
         assert (bi > 0).sum() > 30
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,k,L,levelsup,scoring,weighting", [(0, 10, 4, 2, 0, 0), (1, 10, 3, 4, 0, 0), (2, 4, 6, 4, 0, 0), (3, 10, 5, 1, 1, 1),
+                                                                 (4, 2, 7, 3, 0, 2), (5, 10, 4, 0, 4, 3), (6, 10, 6, 4, 0, 0)])
+def test_vocabulary_transform_equals_the_reference(seed, k, L, levelsup, scoring, weighting, tmp_path):
+    """ORBVocabulary (DBoW2 TemplatedVocabulary<FORB>) loaded by the reference's loadFromTextFile; transform() as Frame::ComputeBoW
+    calls it.  Oracle descent + orbx.vocabulary.bow_maps give the same word per feature, the same BowVector (keys and bit-identical
+    doubles, every weighting / scoring pair tried) and the same FeatureVector.  Trees list parents before children (the text loader
+    indexes m_nodes[parent] while it grows it) and have no leaf above level L - levelsup (the reference leaves `nid` uninitialised
+    for such a branch, TemplatedVocabulary.h:1160-1170 + :1231-1262; the oracle and the kernel define it as 0)."""
+    from oracle import oracle_py as O
+    from orbx.vocabulary import bow_maps, tree_from_parents
+    args = synth.random_vocabulary(seed, k=k if L < 6 or k < 10 else 4, L=L, shuffle=False, prune=0.0)
+    tree = tree_from_parents(*args, scoring=scoring, weighting=weighting)
+    rng = np.random.default_rng(seed)
+    feats = np.concatenate([synth.descriptors_near_words(rng, tree, 700), rng.integers(0, 256, (300, 32)).astype(np.uint8)])
+    path = str(tmp_path / "voc.txt")
+    O.write_vocabulary_text(path, *args, scoring=scoring, weighting=weighting)
+    rv = O.RefVocabulary(path)
+    w_ref, bow_ref, fv_ref = rv.transform(feats, levelsup)
+    rv.close()
+    word, node, wt = O.bow_transform(tree, feats, levelsup)
+    v, fv = bow_maps(word, node, wt, weighting, scoring)
+    assert np.array_equal(w_ref, word) and len(set(word.tolist())) > 20
+    assert list(v.keys()) == list(bow_ref.keys()) and v == bow_ref
+    assert fv == fv_ref
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
