@@ -314,10 +314,13 @@ inline void FAST(InputArray img_, std::vector<KeyPoint> &kps, int threshold, boo
     Mat img = img_.getMat();
     assert(nms);
     kps.clear();
-    const int cap = std::max(img.rows * img.cols, 1);
-    std::vector<int> xs(cap), ys(cap), sc(cap);
-    const int n = orbo_fast9(img.data, img.cols, img.rows, (int)img.step, threshold, xs.data(), ys.data(), sc.data(), cap);
+    const int cap = std::max(img.rows * img.cols / 4, 16);             // survivors of the 3x3 suppression: at most one per 2x2 block
+    int *xs = static_cast<int *>(std::malloc(sizeof(int) * 3 * cap)), *ys = xs + cap, *sc = ys + cap;   // scratch outside operator new
+    const int n = orbo_fast9(img.data, img.cols, img.rows, (int)img.step, threshold, xs, ys, sc, cap);
+    assert(n <= cap);
+    kps.reserve(n);
     for (int i = 0; i < n; i++) kps.push_back(KeyPoint((float)xs[i], (float)ys[i], 7.f, -1, (float)sc[i]));
+    std::free(xs);
 }
 
 // only ComputeKeyPointsOld (dead code, ORBextractor.cc:855) uses this

@@ -165,12 +165,19 @@ static const int k_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 
 static inline int fast_score_at(const uint8_t *p, const int off[16], int threshold) {
     const int v = p[0];
     int d[25];
-    /* quick reject like OpenCV's first test on ring pixels 0 and 8 */
-    int d0 = v - p[off[0]], d8 = v - p[off[8]];
-    if (!((d0 > threshold || d0 < -threshold) || (d8 > threshold || d8 < -threshold))) {
-        /* a 9-arc always covers pixel 0 or pixel 8 */
-        return 0;
+    /* quick reject like OpenCV's cascade (fast.cpp: d = tab[0] | tab[8]; d &= tab[2] | tab[10]; ...): a 9-arc covers at least one
+     * pixel of every opposite pair (k, k + 8), with the arc's polarity.  bit 0 = darker ring pixel (v - p > t), bit 1 = brighter.
+     * Only a necessary condition; the arc scan below decides. */
+    int m = 3;
+    for (int k = 0; k < 8 && m; k += 2) {          /* even pairs first, like OpenCV */
+        const int a = v - p[off[k]], b = v - p[off[k + 8]];
+        m &= ((a > threshold) | ((a < -threshold) << 1)) | ((b > threshold) | ((b < -threshold) << 1));
     }
+    for (int k = 1; k < 8 && m; k += 2) {
+        const int a = v - p[off[k]], b = v - p[off[k + 8]];
+        m &= ((a > threshold) | ((a < -threshold) << 1)) | ((b > threshold) | ((b < -threshold) << 1));
+    }
+    if (!m) return 0;
     for (int k = 0; k < 16; k++) d[k] = v - p[off[k]];
     for (int k = 16; k < 25; k++) d[k] = d[k - 16];
     int best = 0; /* max over arcs of min(d) (darker ring) and of min(-d) (brighter ring) */
