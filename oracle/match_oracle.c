@@ -12,9 +12,9 @@
  * src/ORBmatcher.cc, Frame.cc, MapPoint.cc and KeyFrame.cc compile unmodified against the OpenCV stand-in oracle/cvmini into
  * oracle/_ref/liborbmatcher_ref.so (make ref), and tests/test_oracle_ref_matcher.py gets identical results from the reference's
  * DescriptorDistance, AssignFeaturesToGrid + GetFeaturesInArea, SearchByProjection(Cur, Last) (all forward / backward / mono
- * modes), SearchByProjection(Frame, MapPoints), SearchByBoW x2, SearchForTriangulation and SearchForInitialization.  Still
- * unpinned by the reference: the relocalisation / loop-closing / Fuse / Sim3 window searches (orbo_search_by_projection_kf,
- * orbo_match_window), whose oracle entry points take gates that the adapter evaluates on the host.  tests/test_match_oracle.py
+ * modes), SearchByProjection(Frame, MapPoints), the relocalisation SearchByProjection(Cur, KF, sAlreadyFound), SearchByBoW x2,
+ * SearchForTriangulation and SearchForInitialization.  Still unpinned by the reference: the loop-closing / Fuse / Sim3 window
+ * searches (orbo_match_window), whose oracle entry point takes projections and gates that the adapter evaluates on the host.  tests/test_match_oracle.py
  * additionally cross-checks every function against an independent numpy brute-force statement of the same rules.
  */
 #include "orbx_oracle.h"

@@ -667,6 +667,8 @@ def ref_matcher_lib():
         _REFM.orbvref_load_text.argtypes = [C.c_char_p]
         _REFM.orbvref_destroy.argtypes = [C.c_void_p]
         _REFM.orbvref_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
+        _REFM.orbmref_search_by_projection_kf.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 5 + [
+            C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _REFM
@@ -787,3 +789,18 @@ class RefVocabulary:
         bow = {int(bid[i]): float(bval[i]) for i in range(nb.value)}
         fv = {int(fid[i]): ff[fst[i]:fst[i + 1]].astype(int).tolist() for i in range(nf.value)}
         return word[:n].copy(), bow, fv
+
+
+def ref_search_by_projection_kf(cur, pts, pt_desc, dist_range, Rcw, tcw, th, orb_dist, nnratio=0.9, check_ori=True):
+    """the reference's relocalisation SearchByProjection(Cur, KF, sAlreadyFound, th, ORBdist) -> (nmatches, match[Cur.n], gate[n_pts],
+    level[n_pts]); gate / level are the distance-invariance gate and MapPoint::PredictScale the adapter evaluates for the oracle"""
+    f, keep = _oframe(cur)
+    pts = np.ascontiguousarray(pts, LAST_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    dr = np.ascontiguousarray(dist_range, np.float32).reshape(-1)
+    R, t = np.ascontiguousarray(Rcw, np.float32).reshape(9), np.ascontiguousarray(tcw, np.float32).reshape(3)
+    m = np.full(f.n, -1, np.int32)
+    gate, level = np.zeros(max(len(pts), 1), np.uint8), np.zeros(max(len(pts), 1), np.int32)
+    n = ref_matcher_lib().orbmref_search_by_projection_kf(C.byref(f), len(pts), _p(pts), _p(pd), _p(dr), _p(R), _p(t), th, orb_dist, nnratio,
+                                                         int(check_ori), _p(m), _p(gate), _p(level))
+    return n, m, gate[:len(pts)], level[:len(pts)]

@@ -14,6 +14,7 @@
 #include <thread>
 #include <cstring>
 #include <map>
+#include <set>
 #include "Thirdparty/DBoW2/DBoW2/BowVector.h"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 #include "ORBVocabulary.h"
@@ -457,5 +458,55 @@ void orbvref_transform(void *h, const uint8_t *desc, int n, int levelsup, int32_
     }
     fv_start[k] = at;
     *n_fv = k;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist), :1472-1599
+// (relocalisation).  Lp[i].valid = the keyframe holds a good map point there that is not in sAlreadyFound (records with valid == 0
+// alternate between NULL, bad and already-found).  dist_range[2 i .. 2 i + 1] = mfMinDistance, mfMaxDistance of point i.
+// gate_out[i] / level_out[i] = what the adapter evaluates on the host for the oracle's entry point: the distance-invariance gate
+// (:1514-1521) and MapPoint::PredictScale (:1523), computed here by the reference's own members.
+int orbmref_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo_last_point *Lp, const uint8_t *pt_desc,
+                                    const float *dist_range, const float Rcw[9], const float tcw[3], float th, int orb_dist, float nnratio,
+                                    int check_ori, int32_t *match, uint8_t *gate_out, int32_t *level_out) {
+    orbref_arena_retain();
+    Frame *cur = make_frame(Cur);
+    cur->SetPose(pose4(Rcw, tcw));
+    orbo_frame K = *Cur;
+    std::vector<orbo_keypoint> keys(n_pts > 0 ? n_pts : 1);
+    for (int i = 0; i < n_pts; i++) { orbo_keypoint k = {0, 0, 31.f, Lp[i].angle, 0, 0, -1}; keys[i] = k; }
+    K.n = n_pts; K.keys_un = keys.data(); K.desc = pt_desc; K.u_right = NULL; K.claimed = NULL;
+    Frame *kframe = make_frame(&K);
+    std::vector<MapPoint *> owned;
+    std::map<MapPoint *, int> index_of;
+    std::set<MapPoint *> found;
+    const cv::Mat R = cur->mTcw.rowRange(0, 3).colRange(0, 3), t = cur->mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -R.t() * t;                                  // as :1478
+    for (int i = 0, kind = 0; i < n_pts; i++) {
+        gate_out[i] = 0; level_out[i] = 0;
+        if (!Lp[i].valid && (kind = (kind + 1) % 3) == 0) continue;  // NULL entry
+        MapPoint *p = make_point(Lp[i].x, Lp[i].y, Lp[i].z, kframe, i, 1);
+        p->mfMinDistance = dist_range[2 * i]; p->mfMaxDistance = dist_range[2 * i + 1];
+        owned.push_back(p);
+        kframe->mvpMapPoints[i] = p;
+        index_of[p] = i;
+        if (!Lp[i].valid) { if (kind == 1) p->mbBad = true; else found.insert(p); continue; }
+        const cv::Mat PO = p->GetWorldPos() - Ow;
+        const float dist3D = cv::norm(PO);
+        gate_out[i] = !(dist3D < p->GetMinDistanceInvariance() || dist3D > p->GetMaxDistanceInvariance());
+        if (gate_out[i]) level_out[i] = p->PredictScale(dist3D, cur);
+    }
+    claim(cur, Cur, kframe, owned);
+    KeyFrame *kf = new KeyFrame(*kframe, the_map(), NULL);
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchByProjection(*cur, kf, found, th, orb_dist);
+    for (int k = 0; k < Cur->n; k++) {
+        std::map<MapPoint *, int>::const_iterator it = index_of.find(cur->mvpMapPoints[k]);
+        match[k] = it == index_of.end() ? -1 : it->second;
+    }
+    delete kf;
+    for (size_t i = 0; i < owned.size(); i++) delete owned[i];
+    delete kframe; delete cur;
+    orbref_arena_release();
+    return n;
 }
 }

@@ -237,6 +237,31 @@ def test_vocabulary_transform_equals_the_reference(seed, k, L, levelsup, scoring
     assert fv == fv_ref
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,th,orb_dist,check_ori", [(1, 10.0, 100, True), (2, 3.0, 64, True), (3, 10.0, 100, False)])
+def test_relocalisation_search_equals_the_reference(seed, th, orb_dist, check_ori):
+    """SearchByProjection(CurrentFrame, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1472-1599).  The oracle's entry point
+    takes the distance-invariance gate and the predicted level from its caller (the adapter); here both come from the reference's
+    own MapPoint::GetMin/MaxDistanceInvariance and PredictScale, so the whole function is compared, NULL / bad / already-found
+    map points included."""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    cur = synth.random_frame(rng, 1200)
+    pts, desc, R, t = synth.last_frame_points(rng, cur, 1000)
+    Ow = -(R.T.astype(np.float64) @ t.astype(np.float64))
+    d = np.linalg.norm(np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float64) - Ow, axis=1)
+    sf = np.float32(1.2)
+    max_d = (d * rng.uniform(0.6, 1.6, len(d)) * sf ** np.clip(pts["octave"], 0, 7)).astype(np.float32)
+    min_d = (max_d / sf ** 7).astype(np.float32)
+    n1, m1, gate, level = O.ref_search_by_projection_kf(cur, pts, desc, np.stack([min_d, max_d], 1), R, t, th, orb_dist, 0.9, check_ori)
+    p2 = pts.copy()
+    p2["valid"] = (pts["valid"] != 0) & (gate != 0)
+    p2["octave"] = level
+    n2, m2 = O.search_by_projection_kf(cur, p2, desc, R, t, th, orb_dist, check_ori)
+    assert n1 == n2 and np.array_equal(m1, m2) and n1 > 100
+    assert 600 < gate.sum() < 1000 and len(set(level[gate != 0].tolist())) == 8
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
