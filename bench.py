@@ -898,10 +898,11 @@ def main():
         lba_local = bench_lba_batched(local_rank, rank)
     stereo = pose = bow = sequence = None
     if side_sections:
-        stereo = bench_stereo(local_rank, not args.no_cpu)
-        pose = bench_pose(local_rank, not args.no_cpu)
-        bow = bench_bow(local_rank, not args.no_cpu)
-        sequence = bench_sequence(local_rank, not args.no_cpu)
+        with_cpu = not args.no_cpu and world == 1      # CPU legs are timed on rank 0 at N = 1 only
+        stereo = bench_stereo(local_rank, with_cpu)
+        pose = bench_pose(local_rank, with_cpu)
+        bow = bench_bow(local_rank, with_cpu)
+        sequence = bench_sequence(local_rank, with_cpu)
 
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
@@ -957,7 +958,7 @@ def main():
             "sequence": sequence,
             "track": track,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             fps, n, dt = cpu_path(hnp[:64], 12.0, cores)
             ref_run = cpu_path_reference(10.0, cores) if default_workload else None
