@@ -642,15 +642,32 @@ class RefExtractor:
 
 # ---- the reference's own ORBmatcher / Frame / MapPoint (oracle/_ref/liborbmatcher_ref.so, `make -C oracle ref`) ----
 REF_MATCHER_SO = os.path.join(_HERE, "_ref", "liborbmatcher_ref.so")
+ADAPTER_SO = os.path.join(_HERE, "_ref", "liborbmatcher_adapter.so")
 _REFM = None
+_ADPM = None
+USE_ADAPTER = False          # tests flip this: every ref_* function below then runs the DROP-IN build (adapters + liborbx.so, needs a GPU)
 
 
 def ref_matcher_lib():
-    """src/ORBmatcher.cc + Frame.cc + MapPoint.cc + KeyFrame.cc of the reference compiled against oracle/cvmini (None if not built)."""
-    global _REFM
+    """src/ORBmatcher.cc + Frame.cc + MapPoint.cc + KeyFrame.cc of the reference compiled against oracle/cvmini (None if not built).
+    With USE_ADAPTER set: the same shim and reference objects, but ORBextractor / ORBmatcher / Frame::ComputeStereoMatches /
+    Frame::ComputeBoW are the product's adapters on top of the CUDA library (oracle/_ref/liborbmatcher_adapter.so)."""
+    global _REFM, _ADPM
+    if USE_ADAPTER:
+        if _ADPM is None and os.path.exists(ADAPTER_SO):
+            lib()
+            _ADPM = C.CDLL(ADAPTER_SO)
+            _declare_refm(_ADPM)
+        return _ADPM
     if _REFM is None and os.path.exists(REF_MATCHER_SO):
         lib()
         _REFM = C.CDLL(REF_MATCHER_SO)
+        _declare_refm(_REFM)
+    return _REFM
+
+
+def _declare_refm(_REFM):
+    if True:
         _REFM.orbmref_hamming256.argtypes = [C.c_void_p, C.c_void_p]
         _REFM.orbmref_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
         _REFM.orbmref_search_by_projection_frame.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 6 + [
@@ -671,7 +688,10 @@ def ref_matcher_lib():
             C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-    return _REFM
+        _REFM.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_int]
+        _REFM.orbvref_compute_bow.restype = None
+        _REFM.orbvref_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
 
 
 def ref_hamming256(a, b):
@@ -778,6 +798,16 @@ class RefVocabulary:
 
     __del__ = close
 
+    def compute_bow(self, desc):
+        """Frame::ComputeBoW of a frame with these descriptors -> (BowVector dict, FeatureVector dict)"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        bid, bval, nb = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64), C.c_int32()
+        fid, fst, ff, nf = np.zeros(max(n, 1), np.uint32), np.zeros(n + 2, np.int32), np.zeros(max(n, 1), np.uint32), C.c_int32()
+        self.R.orbvref_compute_bow(self.h, _p(d), n, _p(bid), _p(bval), C.byref(nb), _p(fid), _p(fst), _p(ff), C.byref(nf))
+        return ({int(bid[i]): float(bval[i]) for i in range(nb.value)},
+                {int(fid[i]): ff[fst[i]:fst[i + 1]].astype(int).tolist() for i in range(nf.value)})
+
     def transform(self, desc, levelsup=4):
         """-> (word id per feature, BowVector dict, FeatureVector dict) as Frame::ComputeBoW obtains them"""
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
@@ -804,3 +834,14 @@ def ref_search_by_projection_kf(cur, pts, pt_desc, dist_range, Rcw, tcw, th, orb
     n = ref_matcher_lib().orbmref_search_by_projection_kf(C.byref(f), len(pts), _p(pts), _p(pd), _p(dr), _p(R), _p(t), th, orb_dist, nnratio,
                                                          int(check_ori), _p(m), _p(gate), _p(level))
     return n, m, gate[:len(pts)], level[:len(pts)]
+
+
+def ref_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """ORBextractor::operator() through the matcher-side library (the reference's class, or with USE_ADAPTER the adapter's)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = 4 * nfeatures + 1024
+    k, d = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+    n = ref_matcher_lib().orbmref_extract(_p(img), w, h, w, nfeatures, scale_factor, nlevels, ini_th, min_th, _p(k), _p(d), cap)
+    assert n <= cap
+    return k[:n].copy(), d[:n].copy()

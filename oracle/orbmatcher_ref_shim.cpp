@@ -509,4 +509,46 @@ int orbmref_search_by_projection_kf(const orbo_frame *Cur, int n_pts, const orbo
     orbref_arena_release();
     return n;
 }
+
+// ORBextractor::operator() through whatever ORBextractor this library was linked with (the reference's, or the adapter's)
+int orbmref_extract(const uint8_t *img, int w, int h, int stride, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                    void *kps, uint8_t *desc, int cap) {
+    orbref_arena_retain();
+    ORBextractor *e = new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat d;
+    (*e)(cv::Mat(h, w, CV_8U, const_cast<uint8_t *>(img), (size_t)stride), cv::Mat(), keys, d);
+    const int n = (int)keys.size();
+    if (n <= cap && n > 0) {
+        std::memcpy(kps, keys.data(), sizeof(cv::KeyPoint) * n);
+        for (int i = 0; i < n; i++) std::memcpy(desc + 32 * (size_t)i, d.ptr(i), 32);
+    }
+    delete e;
+    orbref_arena_release();
+    return n;
+}
+
+// Frame::ComputeBoW (Frame.cc:423-431: transform(vCurrentDesc, mBowVec, mFeatVec, 4)) of a frame holding these descriptors, through
+// whatever Frame::ComputeBoW this library was linked with (the reference's, or adapter/Frame_orbx.cc on the device vocabulary)
+void orbvref_compute_bow(void *h, const uint8_t *desc, int n, uint32_t *bow_id, double *bow_val, int32_t *n_bow, uint32_t *fv_id,
+                         int32_t *fv_start, uint32_t *fv_feat, int32_t *n_fv) {
+    orbref_arena_retain();
+    Frame *f = new Frame();
+    f->N = n;
+    f->mDescriptors = cv::Mat(n, 32, CV_8U, const_cast<uint8_t *>(desc)).clone();
+    f->mpORBvocabulary = static_cast<ORBVocabulary *>(h);
+    f->ComputeBoW();
+    int k = 0, at = 0;
+    for (DBoW2::BowVector::const_iterator it = f->mBowVec.begin(); it != f->mBowVec.end(); ++it, ++k) { bow_id[k] = it->first; bow_val[k] = it->second; }
+    *n_bow = k;
+    k = 0;
+    for (DBoW2::FeatureVector::const_iterator it = f->mFeatVec.begin(); it != f->mFeatVec.end(); ++it, ++k) {
+        fv_id[k] = it->first; fv_start[k] = at;
+        for (size_t j = 0; j < it->second.size(); j++) fv_feat[at++] = it->second[j];
+    }
+    fv_start[k] = at;
+    *n_fv = k;
+    delete f;
+    orbref_arena_release();
+}
 }
