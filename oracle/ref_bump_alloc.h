@@ -5,7 +5,14 @@
 // expansion order depends on where malloc put the list nodes.  The oracle and the CUDA path define that order as CREATION
 // order; under this allocator a later allocation always has the larger address, so the reference's code follows the same
 // definition.  Handles retain / release the arena; it rewinds when the last one is gone.
+//
+// -DORBREF_SYSTEM_ALLOCATOR (the drop-in build, liborbmatcher_adapter.so): no replacement at all.  The adapters keep handles in
+// static tables that must outlive a rewind, and nothing in that build depends on pointer order.
 #pragma once
+#ifdef ORBREF_SYSTEM_ALLOCATOR
+inline void orbref_arena_retain() {}
+inline void orbref_arena_release() {}
+#else
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -37,9 +44,12 @@ inline void orbref_arena_release() {
         g_used = 0;
     }
 }
-void *operator new(size_t n) { return arena_alloc(n ? n : 1); }
-void *operator new[](size_t n) { return arena_alloc(n ? n : 1); }
-void operator delete(void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete(void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+// hidden: a library loaded as a dependency of this one (liborbx.so in the drop-in build) must keep libstdc++'s operators
+#define ORBREF_LOCAL __attribute__((visibility("hidden")))
+ORBREF_LOCAL void *operator new(size_t n) { return arena_alloc(n ? n : 1); }
+ORBREF_LOCAL void *operator new[](size_t n) { return arena_alloc(n ? n : 1); }
+ORBREF_LOCAL void operator delete(void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
+ORBREF_LOCAL void operator delete[](void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
+ORBREF_LOCAL void operator delete(void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+ORBREF_LOCAL void operator delete[](void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+#endif

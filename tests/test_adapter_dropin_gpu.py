@@ -23,6 +23,7 @@ def adapter():
     from oracle import oracle_py as O
     O.USE_ADAPTER = True
     try:
+        assert O.ref_matcher_lib()._name.endswith("liborbmatcher_adapter.so")     # the drop-in build, not the reference library
         yield O
     finally:
         O.USE_ADAPTER = False
