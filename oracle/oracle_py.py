@@ -688,6 +688,8 @@ def _declare_refm(_REFM):
             C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _REFM.orbmref_window.argtypes = [C.c_int, C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 8
         _REFM.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_int]
         _REFM.orbvref_compute_bow.restype = None
@@ -845,3 +847,22 @@ def ref_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min
     n = ref_matcher_lib().orbmref_extract(_p(img), w, h, w, nfeatures, scale_factor, nlevels, ini_th, min_th, _p(k), _p(d), cap)
     assert n <= cap
     return k[:n].copy(), d[:n].copy()
+
+
+def ref_window(which, kf, R, t, scale, kf_has, kf_extra, pts, pt_desc, th):
+    """the map-mutating window searches on a KeyFrame built by the reference's constructor: which = 0 Fuse(pKF, vpMapPoints, th),
+    1 Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), 2 SearchByProjection(pKF, Scw, vpPoints, vpMatched, th); see orbmref_window in
+    oracle/orbmatcher_ref_shim.cpp for the scene and the MapPoint* codes.  Returns a dict of the map state afterwards."""
+    f, keep = _oframe(kf)
+    n = f.n
+    p = np.ascontiguousarray(pts, FRUSTUM_POINT_DTYPE)
+    pd = np.ascontiguousarray(pt_desc, np.uint8)
+    Rm, tv = np.ascontiguousarray(R, np.float32).reshape(9), np.ascontiguousarray(t, np.float32).reshape(3)
+    has, extra = np.ascontiguousarray(kf_has, np.uint8), np.ascontiguousarray(kf_extra, np.int32)
+    o = dict(kf_slot=np.zeros(n, np.int32), pt_bad=np.zeros(len(p), np.uint8), pt_obs=np.zeros(len(p), np.int32),
+             pt_replaced=np.zeros(len(p), np.int32), kfmp_bad=np.zeros(n, np.uint8), kfmp_obs=np.zeros(n, np.int32),
+             kfmp_replaced=np.zeros(n, np.int32), aux=np.full(max(n, len(p)), -1, np.int32))
+    o["ret"] = ref_matcher_lib().orbmref_window(which, C.byref(f), _p(Rm), _p(tv), scale, _p(has), _p(extra), len(p), _p(p), _p(pd), th,
+                                                *[_p(o[k]) for k in ("kf_slot", "pt_bad", "pt_obs", "pt_replaced", "kfmp_bad", "kfmp_obs",
+                                                                     "kfmp_replaced", "aux")])
+    return o

@@ -43,9 +43,10 @@ std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat &Descriptors) {
     for (int j = 0; j < Descriptors.rows; j++) v.push_back(Descriptors.row(j));
     return v;
 }
-// referenced by SetBadFlag paths that the pinned calls never reach (src/Map.cc and src/KeyFrameDatabase.cc are not built)
+// src/Map.cc and src/KeyFrameDatabase.cc are not built (Map.cc needs Eigen through Converter.h).  MapPoint::Replace ends in
+// mpMap->EraseMapPoint(this) (MapPoint.cc:247), which only removes the point from the map's own set: nothing the tests look at
 static void not_built(const char *what) { std::fprintf(stderr, "orbmref: %s is not part of this build\n", what); std::abort(); }
-void Map::EraseMapPoint(MapPoint *) { not_built("Map::EraseMapPoint"); }
+void Map::EraseMapPoint(MapPoint *) {}
 void Map::EraseKeyFrame(KeyFrame *) { not_built("Map::EraseKeyFrame"); }
 void KeyFrameDatabase::erase(KeyFrame *) { not_built("KeyFrameDatabase::erase"); }
 }  // namespace ORB_SLAM2
@@ -550,5 +551,103 @@ void orbvref_compute_bow(void *h, const uint8_t *desc, int n, uint32_t *bow_id, 
     *n_fv = k;
     delete f;
     orbref_arena_release();
+}
+
+// ---- the window searches that mutate the map: Fuse (:825-975), Fuse with a Sim3 (:977-1100), SearchByProjection(KF, Scw, ...) (:290-403)
+// A keyframe built by the reference's constructor from `KFrec` at pose (R, t); kf_has[k] != 0: keypoint k holds a map point that
+// this keyframe (and kf_extra[k] further keyframes) observes.  Candidate i: pts[i] (position, normal, distance range; `skip` = 0
+// good, 1 NULL, 2 bad, 3 already observed by the keyframe; `blocks` = number of other keyframes observing it) with descriptor row i.
+// which = 0 Fuse(pKF, vpMapPoints, th); 1 Fuse(pKF, Scw, vpPoints, th, vpReplacePoint); 2 SearchByProjection(pKF, Scw, vpPoints, vpMatched, th)
+// with vpMatched preset to the keyframe's own points where kf_has[k] == 2.  Scw = [s R | s t].
+// A MapPoint* is reported as -1 (NULL), i (candidate i) or 1000000 + k (the point keypoint k held at the start).
+// Outputs: kf_slot[k] = pKF->GetMapPoint(k) afterwards; pt_bad / pt_obs / pt_replaced per candidate; kfmp_bad / kfmp_obs / kfmp_replaced per
+// keypoint's original point; aux = vpReplacePoint (which 1, per candidate) or vpMatched (which 2, per keypoint).
+int orbmref_window(int which, const orbo_frame *KFrec, const float R[9], const float t[3], float scale, const uint8_t *kf_has,
+                   const int32_t *kf_extra, int n_pts, const orbo_frustum_point *pts, const uint8_t *pt_desc, float th, int32_t *kf_slot,
+                   uint8_t *pt_bad, int32_t *pt_obs, int32_t *pt_replaced, uint8_t *kfmp_bad, int32_t *kfmp_obs, int32_t *kfmp_replaced,
+                   int32_t *aux) {
+    orbref_arena_retain();
+    const int n = KFrec->n;
+    Frame *f = make_frame(KFrec);
+    f->SetPose(pose4(R, t));
+    f->mvDepth.assign(n, -1.f);
+    KeyFrame *kf = new KeyFrame(*f, the_map(), NULL);
+    std::vector<KeyFrame *> others;
+    for (int j = 0; j < 4; j++) others.push_back(new KeyFrame(*f, the_map(), NULL));     // further observers (same descriptors)
+    orbo_frame C = *KFrec;
+    std::vector<orbo_keypoint> ckeys(n_pts > 0 ? n_pts : 1);
+    std::memset(ckeys.data(), 0, sizeof(orbo_keypoint) * ckeys.size());
+    C.n = n_pts; C.keys_un = ckeys.data(); C.desc = pt_desc; C.u_right = NULL; C.claimed = NULL;
+    Frame *carrier = make_frame(&C);
+    std::vector<MapPoint *> kfmp(n, static_cast<MapPoint *>(NULL)), cand(n_pts, static_cast<MapPoint *>(NULL));
+    std::map<MapPoint *, int> code;
+    for (int k = 0; k < n; k++)
+        if (kf_has[k]) {
+            MapPoint *p = make_point(0, 0, 1 + k, f, k, 0);
+            p->AddObservation(kf, k);
+            kf->AddMapPoint(p, k);
+            for (int j = 0; j < kf_extra[k] && j < 4; j++) { p->AddObservation(others[j], k); others[j]->AddMapPoint(p, k); }
+            kfmp[k] = p;
+            code[p] = 1000000 + k;
+        }
+    int free_slot = 0;
+    for (int i = 0; i < n_pts; i++) {
+        if (pts[i].skip == 1) continue;                      // a NULL entry of vpMapPoints
+        MapPoint *p = make_point(pts[i].x, pts[i].y, pts[i].z, carrier, i, 0);
+        p->mNormalVector = (cv::Mat_<float>(3, 1) << pts[i].nx, pts[i].ny, pts[i].nz);
+        p->mfMinDistance = pts[i].min_distance; p->mfMaxDistance = pts[i].max_distance;
+        for (int j = 0; j < pts[i].blocks && j < 4; j++) {   // seen from other keyframes, at keypoints those do not use otherwise
+            while (free_slot < n && kf_has[free_slot]) free_slot++;
+            if (free_slot >= n) break;
+            p->AddObservation(others[j], free_slot);
+        }
+        if (pts[i].blocks) free_slot++;
+        if (pts[i].skip == 3) {                              // already observed by this keyframe (IsInKeyFrame)
+            while (free_slot < n && kf_has[free_slot]) free_slot++;
+            if (free_slot < n) { p->AddObservation(kf, free_slot); kf->AddMapPoint(p, free_slot); free_slot++; }
+        }
+        if (pts[i].skip == 2) p->mbBad = true;
+        cand[i] = p;
+        code[p] = i;
+    }
+    struct Code { std::map<MapPoint *, int> &c; int operator()(MapPoint *p) const { if (!p) return -1; std::map<MapPoint *, int>::const_iterator it = c.find(p); return it == c.end() ? -2 : it->second; } } of = {code};
+    cv::Mat Scw = cv::Mat::eye(4, 4, CV_32F);
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Scw.at<float>(i, j) = scale * R[3 * i + j]; Scw.at<float>(i, 3) = scale * t[i]; }
+    ORBmatcher matcher(0.8f, true);
+    int ret = 0;
+    if (which == 0) {
+        ret = matcher.Fuse(kf, cand, th);
+    } else if (which == 1) {
+        std::vector<MapPoint *> good, replace;
+        std::vector<int> idx;
+        for (int i = 0; i < n_pts; i++) if (cand[i]) { good.push_back(cand[i]); idx.push_back(i); }      // LoopClosing passes no NULLs here
+        replace.assign(good.size(), static_cast<MapPoint *>(NULL));
+        ret = matcher.Fuse(kf, Scw, good, th, replace);
+        for (int i = 0; i < n_pts; i++) aux[i] = -1;
+        for (size_t j = 0; j < good.size(); j++) aux[idx[j]] = of(replace[j]);
+    } else {
+        std::vector<MapPoint *> good, matched(n, static_cast<MapPoint *>(NULL));
+        for (int i = 0; i < n_pts; i++) if (cand[i]) good.push_back(cand[i]);
+        for (int k = 0; k < n; k++) if (kf_has[k] == 2) matched[k] = kfmp[k];
+        ret = matcher.SearchByProjection(kf, Scw, good, matched, (int)th);
+        for (int k = 0; k < n; k++) aux[k] = of(matched[k]);
+    }
+    for (int k = 0; k < n; k++) {
+        kf_slot[k] = of(kf->GetMapPoint(k));
+        kfmp_bad[k] = kfmp[k] ? kfmp[k]->isBad() : 0;
+        kfmp_obs[k] = kfmp[k] ? kfmp[k]->Observations() : -1;
+        kfmp_replaced[k] = kfmp[k] ? of(kfmp[k]->GetReplaced()) : -1;
+    }
+    for (int i = 0; i < n_pts; i++) {
+        pt_bad[i] = cand[i] ? cand[i]->isBad() : 0;
+        pt_obs[i] = cand[i] ? cand[i]->Observations() : -1;
+        pt_replaced[i] = cand[i] ? of(cand[i]->GetReplaced()) : -1;
+    }
+    for (int k = 0; k < n; k++) delete kfmp[k];
+    for (int i = 0; i < n_pts; i++) delete cand[i];
+    for (size_t j = 0; j < others.size(); j++) delete others[j];
+    delete kf; delete carrier; delete f;
+    orbref_arena_release();
+    return ret;
 }
 }

@@ -83,6 +83,29 @@ def test_adapter_compute_stereo_matches(adapter):
         T.test_compute_stereo_matches_equals_the_reference(*args)
 
 
+@pytest.mark.parametrize("which,scale,th", [(0, 1.0, 3.0), (0, 1.0, 6.0), (1, 1.0, 4.0), (1, 1.3, 4.0), (2, 1.0, 10.0), (2, 0.8, 10.0)])
+def test_adapter_window_searches_equal_the_reference_library(which, scale, th):
+    """Fuse(pKF, vpMapPoints, th), Fuse(pKF, Scw, ...) and SearchByProjection(pKF, Scw, ...): the adapter (projection and gates on the host,
+    window + Hamming on the device, map mutations on the host in reference order) against the reference's own functions on the
+    same KeyFrame / MapPoint graph: return value, every keypoint's map point, every point's bad flag / observation count /
+    replacement, vpReplacePoint / vpMatched"""
+    from oracle import oracle_py as O
+    import test_oracle_ref_matcher as T
+    if O.ref_matcher_lib() is None:
+        pytest.skip("needs oracle/_ref/liborbmatcher_ref.so as well")
+    for seed in (7, 8):
+        scene = T.window_scene(seed)
+        ref = O.ref_window(which, *scene[:2], scene[2], scale, *scene[3:], th)
+        O.USE_ADAPTER = True
+        try:
+            got = O.ref_window(which, *scene[:2], scene[2], scale, *scene[3:], th)
+        finally:
+            O.USE_ADAPTER = False
+        assert got["ret"] == ref["ret"] and ref["ret"] > 100, (got["ret"], ref["ret"])
+        for k in ("kf_slot", "pt_bad", "pt_obs", "pt_replaced", "kfmp_bad", "kfmp_obs", "kfmp_replaced", "aux"):
+            assert np.array_equal(got[k], ref[k]), (k, int((got[k] != ref[k]).sum()))
+
+
 def test_adapter_compute_bow_equals_the_reference_library(tmp_path):
     """Frame::ComputeBoW: the adapter (device tree descent + the reference's BowVector / FeatureVector bookkeeping) against the
     reference's own Frame::ComputeBoW on the same ORBVocabulary object file"""

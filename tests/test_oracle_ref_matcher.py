@@ -262,6 +262,68 @@ def test_relocalisation_search_equals_the_reference(seed, th, orb_dist, check_or
     assert 600 < gate.sum() < 1000 and len(set(level[gate != 0].tolist())) == 8
 
 
+def window_scene(seed, n=1200, n_pts=900):
+    """a keyframe, its own map points, and candidate map points that project near its keypoints (position, normal, distance
+    range, descriptor), some NULL / bad / already observed by the keyframe, with varying observation counts"""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    kf = synth.random_frame(rng, n, claimed_frac=0.0)
+    fx, fy, cx, cy, bf, b = kf["K"]
+    sf = kf["scale_factors"]
+    yaw = rng.uniform(-0.05, 0.05)
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    t = rng.uniform(-0.1, 0.1, 3)
+    tgt = rng.integers(0, n, n_pts)
+    tgt[-n_pts // 6:] = tgt[:n_pts // 6]                      # several candidates aim at the same keypoint
+    k = kf["keys_un"][tgt]
+    z = rng.uniform(1.0, 8.0, n_pts)
+    stereo = kf["u_right"][tgt] > 0
+    kf["u_right"][tgt[stereo]] = (k["x"][stereo] - bf / z[stereo] + rng.normal(0, 0.5, stereo.sum())).astype(np.float32)
+    z = np.where(kf["u_right"][tgt] > 0, bf / np.maximum(k["x"] - kf["u_right"][tgt], 1e-3), z)      # duplicates: the depth that was kept
+    z[rng.random(n_pts) < 0.03] *= -1
+    s = sf[k["octave"]]
+    u = k["x"] + rng.normal(0, 0.8, n_pts) * s
+    v = k["y"] + rng.normal(0, 0.8, n_pts) * s
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    pw = (pc - t) @ R
+    Ow = -(R.T @ t)
+    d = np.linalg.norm(pw - Ow, axis=1)
+    p = np.zeros(n_pts, O.FRUSTUM_POINT_DTYPE)
+    p["x"], p["y"], p["z"] = pw[:, 0], pw[:, 1], pw[:, 2]
+    nrm = (pw - Ow) / d[:, None] + rng.normal(0, 0.3, (n_pts, 3))
+    nrm[rng.random(n_pts) < 0.08] *= -1
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    p["nx"], p["ny"], p["nz"] = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+    p["max_distance"] = d * np.float32(1.2) ** k["octave"] * rng.uniform(0.8, 1.2, n_pts)
+    p["min_distance"] = p["max_distance"] / np.float32(1.2) ** 7
+    p["skip"] = rng.choice(4, n_pts, p=[0.8, 0.05, 0.05, 0.1])
+    p["blocks"] = rng.integers(0, 4, n_pts)
+    desc = synth.flip_bits(rng, kf["desc"][tgt], rng.integers(0, 70, n_pts))
+    has = (rng.random(n) < 0.5).astype(np.uint8)
+    has[(has == 1) & (rng.random(n) < 0.2)] = 2
+    extra = rng.integers(0, 4, n).astype(np.int32)
+    return kf, R.astype(np.float32), t.astype(np.float32), has, extra, p, desc
+
+
+@needs_ref
+@pytest.mark.parametrize("which,scale,th", [(0, 1.0, 3.0), (1, 1.0, 4.0), (1, 1.3, 4.0), (2, 1.0, 10.0), (2, 0.8, 10.0)])
+def test_reference_window_searches_run_on_the_scene(which, scale, th):
+    """Fuse / Fuse(Scw) / SearchByProjection(KF, Scw) of the reference on the scene that tests/test_adapter_dropin_gpu.py compares the
+    drop-in build on: the scene exercises every outcome (new observation, replacement in both directions, skips)"""
+    from oracle import oracle_py as O
+    kf, R, t, has, extra, p, desc = window_scene(7)
+    o = O.ref_window(which, kf, R, t, scale, has, extra, p, desc, th)
+    assert o["ret"] > 150
+    if which == 0:
+        assert o["pt_bad"][p["skip"] != 2].sum() > 10 and o["kfmp_bad"].sum() > 10          # replaced in both directions
+        assert ((o["kf_slot"] >= 0) & (o["kf_slot"] < 1000000)).sum() > 50                 # candidates now held by the keyframe
+    elif which == 1:
+        assert (o["aux"][:len(p)] >= 1000000).sum() > 20 and ((o["kf_slot"] >= 0) & (o["kf_slot"] < 1000000)).sum() > 50
+        assert o["pt_bad"][p["skip"] != 2].sum() == 0                                       # this overload leaves the replacing to its caller
+    else:
+        assert ((o["aux"][:len(has)] >= 0) & (o["aux"][:len(has)] < 1000000)).sum() == o["ret"]
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
