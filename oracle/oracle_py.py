@@ -690,6 +690,8 @@ def _declare_refm(_REFM):
                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _REFM.orbmref_window.argtypes = [C.c_int, C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 8
+        _REFM.orbmref_search_by_sim3.argtypes = [C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OFrame), C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
         _REFM.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_int]
         _REFM.orbvref_compute_bow.restype = None
@@ -866,3 +868,16 @@ def ref_window(which, kf, R, t, scale, kf_has, kf_extra, pts, pt_desc, th):
                                                 *[_p(o[k]) for k in ("kf_slot", "pt_bad", "pt_obs", "pt_replaced", "kfmp_bad", "kfmp_obs",
                                                                      "kfmp_replaced", "aux")])
     return o
+
+
+def ref_search_by_sim3(kf1, R1, t1, p1, kf2, R2, t2, p2, preset12, s12, R12, t12, th):
+    """the reference's ORBmatcher::SearchBySim3 on two KeyFrames built by its constructor -> (nFound, match12[kf1.n] = keypoint of kf2)"""
+    f1, keep1 = _oframe(kf1)
+    f2, keep2 = _oframe(kf2)
+    a = [np.ascontiguousarray(v, np.float32).reshape(-1) for v in (R1, t1, R2, t2, R12, t12)]
+    q1, q2 = np.ascontiguousarray(p1, FRUSTUM_POINT_DTYPE), np.ascontiguousarray(p2, FRUSTUM_POINT_DTYPE)
+    pre = np.ascontiguousarray(preset12, np.int32)
+    m = np.full(f1.n, -1, np.int32)
+    n = ref_matcher_lib().orbmref_search_by_sim3(C.byref(f1), _p(a[0]), _p(a[1]), _p(q1), C.byref(f2), _p(a[2]), _p(a[3]), _p(q2), _p(pre),
+                                                s12, _p(a[4]), _p(a[5]), th, _p(m))
+    return n, m

@@ -650,4 +650,53 @@ int orbmref_window(int which, const orbo_frame *KFrec, const float R[9], const f
     orbref_arena_release();
     return ret;
 }
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th), ORBmatcher.cc:1102-1326 (loop closing).  Two keyframes built by the
+// reference's constructor at poses (R1, t1), (R2, t2); keypoint k of keyframe j holds a map point where pj[k].skip == 0 (position
+// and distance range from pj[k]; skip == 2: the point is bad).  preset12[i1] >= 0: vpMatches12[i1] starts as keyframe 2's point at that
+// keypoint.  match12[i1] = keypoint of keyframe 2 whose point vpMatches12[i1] is afterwards, or -1.
+int orbmref_search_by_sim3(const orbo_frame *K1, const float R1[9], const float t1[3], const orbo_frustum_point *p1, const orbo_frame *K2,
+                           const float R2[9], const float t2[3], const orbo_frustum_point *p2, const int32_t *preset12, float s12,
+                           const float R12[9], const float t12[3], float th, int32_t *match12) {
+    orbref_arena_retain();
+    Frame *f1 = make_frame(K1), *f2 = make_frame(K2);
+    f1->SetPose(pose4(R1, t1));
+    f2->SetPose(pose4(R2, t2));
+    KeyFrame *k1 = new KeyFrame(*f1, the_map(), NULL), *k2 = new KeyFrame(*f2, the_map(), NULL);
+    std::vector<MapPoint *> m1(K1->n, static_cast<MapPoint *>(NULL)), m2(K2->n, static_cast<MapPoint *>(NULL));
+    std::map<MapPoint *, int> in2;
+    for (int side = 0; side < 2; side++) {
+        const orbo_frame *K = side ? K2 : K1;
+        const orbo_frustum_point *P = side ? p2 : p1;
+        Frame *f = side ? f2 : f1;
+        KeyFrame *kf = side ? k2 : k1;
+        std::vector<MapPoint *> &m = side ? m2 : m1;
+        for (int k = 0; k < K->n; k++) {
+            if (P[k].skip == 1) continue;
+            MapPoint *p = make_point(P[k].x, P[k].y, P[k].z, f, k, 0);
+            p->mfMinDistance = P[k].min_distance; p->mfMaxDistance = P[k].max_distance;
+            p->AddObservation(kf, k);
+            kf->AddMapPoint(p, k);
+            if (P[k].skip == 2) p->mbBad = true;
+            m[k] = p;
+            if (side) in2[p] = k;
+        }
+    }
+    std::vector<MapPoint *> matches(K1->n, static_cast<MapPoint *>(NULL));
+    for (int i = 0; i < K1->n; i++)
+        if (preset12[i] >= 0 && preset12[i] < K2->n) matches[i] = m2[preset12[i]];
+    cv::Mat R(3, 3, CV_32F), t(3, 1, CV_32F);
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R.at<float>(i, j) = R12[3 * i + j]; t.at<float>(i) = t12[i]; }
+    ORBmatcher matcher(0.75f, true);
+    const int n = matcher.SearchBySim3(k1, k2, matches, s12, R, t, th);
+    for (int i = 0; i < K1->n; i++) {
+        std::map<MapPoint *, int>::const_iterator it = in2.find(matches[i]);
+        match12[i] = it == in2.end() ? -1 : it->second;
+    }
+    for (int k = 0; k < K1->n; k++) delete m1[k];
+    for (int k = 0; k < K2->n; k++) delete m2[k];
+    delete k1; delete k2; delete f1; delete f2;
+    orbref_arena_release();
+    return n;
+}
 }

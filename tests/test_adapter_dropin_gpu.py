@@ -106,6 +106,23 @@ def test_adapter_window_searches_equal_the_reference_library(which, scale, th):
             assert np.array_equal(got[k], ref[k]), (k, int((got[k] != ref[k]).sum()))
 
 
+def test_adapter_search_by_sim3_equals_the_reference_library():
+    """SearchBySim3 (both projection directions, preset matches, mutual-consistency check) on two KeyFrames of two maps"""
+    from oracle import oracle_py as O
+    import test_oracle_ref_matcher as T
+    if O.ref_matcher_lib() is None:
+        pytest.skip("needs oracle/_ref/liborbmatcher_ref.so as well")
+    for seed, s12, th in ((11, 1.15, 7.5), (12, 0.9, 7.5), (13, 1.0, 3.0)):
+        scene = T.sim3_scene(seed, s12=s12)
+        n_ref, m_ref = O.ref_search_by_sim3(*scene, th)
+        O.USE_ADAPTER = True
+        try:
+            n_got, m_got = O.ref_search_by_sim3(*scene, th)
+        finally:
+            O.USE_ADAPTER = False
+        assert n_got == n_ref and np.array_equal(m_got, m_ref) and n_ref > 40, (n_got, n_ref)
+
+
 def test_adapter_compute_bow_equals_the_reference_library(tmp_path):
     """Frame::ComputeBoW: the adapter (device tree descent + the reference's BowVector / FeatureVector bookkeeping) against the
     reference's own Frame::ComputeBoW on the same ORBVocabulary object file"""

@@ -324,6 +324,65 @@ def test_reference_window_searches_run_on_the_scene(which, scale, th):
         assert ((o["aux"][:len(has)] >= 0) & (o["aux"][:len(has)] < 1000000)).sum() == o["ret"]
 
 
+def sim3_scene(seed, n=1000, n_common=600, s12=1.15):
+    """two keyframes of two maps related by a Sim3: keyframe 2's points, moved by (s12, R12, t12), project near keyframe 1's keypoints"""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    k2 = synth.random_frame(rng, n, claimed_frac=0.0)
+    k1 = synth.random_frame(rng, n, claimed_frac=0.0)
+    fx, fy, cx, cy, bf, b = k2["K"]
+    sf = k2["scale_factors"]
+
+    def rot(yaw, pitch):
+        Ry = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(pitch), -np.sin(pitch)], [0, np.sin(pitch), np.cos(pitch)]])
+        return Ry @ Rx
+    R1, t1 = rot(rng.uniform(-0.1, 0.1), rng.uniform(-0.05, 0.05)), rng.uniform(-0.3, 0.3, 3)
+    R2, t2 = rot(rng.uniform(-0.1, 0.1), rng.uniform(-0.05, 0.05)), rng.uniform(-0.3, 0.3, 3)
+    R12, t12 = rot(rng.uniform(-0.05, 0.05), rng.uniform(-0.03, 0.03)), rng.uniform(-0.1, 0.1, 3)
+    a = rng.permutation(n)[:n_common]                       # keypoints of keyframe 2 with a counterpart ...
+    c = rng.permutation(n)[:n_common]                       # ... at these keypoints of keyframe 1
+    z = rng.uniform(1.5, 8.0, n)
+    Xc2 = np.stack([(k2["keys_un"]["x"] - cx) / fx * z, (k2["keys_un"]["y"] - cy) / fy * z, z], 1)
+    Xc1 = s12 * (Xc2[a] @ R12.T) + t12                      # camera-1 coordinates of keyframe 2's points
+    ok = Xc1[:, 2] > 0.5
+    u1, v1 = fx * Xc1[:, 0] / Xc1[:, 2] + cx, fy * Xc1[:, 1] / Xc1[:, 2] + cy
+    ok &= (u1 > 20) & (u1 < 620) & (v1 > 20) & (v1 < 460)
+    a, c, Xc1, u1, v1 = a[ok], c[ok], Xc1[ok], u1[ok], v1[ok]
+    k1["keys_un"]["x"][c] = u1 + rng.normal(0, 1.0, len(c))
+    k1["keys_un"]["y"][c] = v1 + rng.normal(0, 1.0, len(c))
+    k1["keys_un"]["octave"][c] = np.clip(k2["keys_un"]["octave"][a] + rng.integers(-1, 2, len(c)), 0, 7)
+    k1["desc"][c] = synth.flip_bits(rng, k2["desc"][a], rng.integers(0, 80, len(c)))
+    z1 = rng.uniform(1.5, 8.0, n)
+    X1c = np.stack([(k1["keys_un"]["x"] - cx) / fx * z1, (k1["keys_un"]["y"] - cy) / fy * z1, z1], 1)
+    X1c[c] = Xc1 + rng.normal(0, 0.01, Xc1.shape)
+    pts = []
+    for Xc, R, t, kk in ((X1c, R1, t1, k1), (Xc2, R2, t2, k2)):
+        Xw = (Xc - t) @ R
+        d = np.linalg.norm(Xc, axis=1)
+        p = np.zeros(n, O.FRUSTUM_POINT_DTYPE)
+        p["x"], p["y"], p["z"] = Xw[:, 0], Xw[:, 1], Xw[:, 2]
+        p["max_distance"] = d * np.float32(1.2) ** kk["keys_un"]["octave"] * rng.uniform(0.8, 1.25, n)
+        p["min_distance"] = p["max_distance"] / np.float32(1.2) ** 7
+        p["skip"] = rng.choice(3, n, p=[0.85, 0.1, 0.05])
+        pts.append(p)
+    preset = np.full(n, -1, np.int32)
+    pick = rng.random(len(c)) < 0.1
+    preset[c[pick]] = a[pick]
+    preset[c[pick][pts[1]["skip"][a[pick]] == 1]] = -1       # no point there to preset
+    f = np.float32
+    return (k1, R1.astype(f), t1.astype(f), pts[0], k2, R2.astype(f), t2.astype(f), pts[1], preset, float(s12), R12.astype(f), t12.astype(f))
+
+
+@needs_ref
+def test_reference_search_by_sim3_runs_on_the_scene():
+    from oracle import oracle_py as O
+    for seed, s12 in ((11, 1.15), (12, 0.9)):
+        scene = sim3_scene(seed, s12=s12)
+        n, m = O.ref_search_by_sim3(*scene, 7.5)
+        assert n > 60 and (m >= 0).sum() >= n
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_reproduces_the_reference_matches():
     """no oracle and no reference at run time: the CUDA matcher against the vectors written from the reference build"""
