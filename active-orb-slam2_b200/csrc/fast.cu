@@ -56,6 +56,45 @@ __device__ __forceinline__ int fast_score(const uint8_t *p, int tp, int th) {
     return best > th ? best - 1 : 0;
 }
 
+// Two pixels at once: their ring values side by side in the 16-bit halves of a word, so that every min / max of the sliding
+// 9-window is one VIMNMX.U16x2 (or VIMNMX3.U16x2) for both.  Same arithmetic as fast_score(); returns the scores in sa / sb.
+__device__ __forceinline__ void fast_score_pair(const uint8_t *pa, const uint8_t *pb, int tp, int th, int &sa, int &sb) {
+    uint32_t r[16];
+#define ORBX_RING(k, off) r[k] = __byte_perm((uint32_t)pa[off], (uint32_t)pb[off], 0x5410)
+    ORBX_RING(0, 3 * tp); ORBX_RING(1, 3 * tp + 1); ORBX_RING(2, 2 * tp + 2); ORBX_RING(3, tp + 3);
+    ORBX_RING(4, 3); ORBX_RING(5, -tp + 3); ORBX_RING(6, -2 * tp + 2); ORBX_RING(7, -3 * tp + 1);
+    ORBX_RING(8, -3 * tp); ORBX_RING(9, -3 * tp - 1); ORBX_RING(10, -2 * tp - 2); ORBX_RING(11, -tp - 3);
+    ORBX_RING(12, -3); ORBX_RING(13, tp - 3); ORBX_RING(14, 2 * tp - 2); ORBX_RING(15, 3 * tp - 1);
+#undef ORBX_RING
+    uint32_t mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn2[k] = __vminu2(r[k], r[(k + 1) & 15]);
+        mx2[k] = __vmaxu2(r[k], r[(k + 1) & 15]);
+    }
+    uint32_t mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn4[k] = __vminu2(mn2[k], mn2[(k + 2) & 15]);
+        mx4[k] = __vmaxu2(mx2[k], mx2[(k + 2) & 15]);
+    }
+    uint32_t lo_of_max = 0x00ff00ffu, hi_of_min = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t mn9a = __vimin3_u16x2(mn4[k], mn4[(k + 4) & 15], r[(k + 8) & 15]);
+        const uint32_t mn9b = __vimin3_u16x2(mn4[k + 1], mn4[(k + 5) & 15], r[(k + 9) & 15]);
+        const uint32_t mx9a = __vimax3_u16x2(mx4[k], mx4[(k + 4) & 15], r[(k + 8) & 15]);
+        const uint32_t mx9b = __vimax3_u16x2(mx4[k + 1], mx4[(k + 5) & 15], r[(k + 9) & 15]);
+        hi_of_min = __vimax3_u16x2(hi_of_min, mn9a, mn9b);
+        lo_of_max = __vimin3_u16x2(lo_of_max, mx9a, mx9b);
+    }
+    const int va = pa[0], vb = pb[0];
+    const int ba = max(va - (int)(lo_of_max & 0xffffu), (int)(hi_of_min & 0xffffu) - va);
+    const int bb = max(vb - (int)(lo_of_max >> 16), (int)(hi_of_min >> 16) - vb);
+    sa = ba > th ? ba - 1 : 0;
+    sb = bb > th ? bb - 1 : 0;
+}
+
 struct FastShared {
     int cnt[ORBX_FAST_CELLS];     // survivors per cell in the current pass
     int empty[ORBX_FAST_CELLS];
@@ -197,10 +236,14 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
         }
         __syncthreads();
         const int n_list = sh.n_list;
-        // (2) scores of the listed pixels
-        for (int i = tid; i < n_list; i += FAST_THREADS) {
-            const int pos = list[i], x = pos & 0xff, y = pos >> 8;
-            s0[y * tp + x] = (uint8_t)fast_score(t0 + y * tp + x, tp, thr);
+        // (2) scores of the listed pixels, two per thread (their rings packed as u16x2)
+        for (int i = 2 * tid; i < n_list; i += 2 * FAST_THREADS) {
+            const int pa = list[i], pb = list[min(i + 1, n_list - 1)];
+            const int oa = (pa >> 8) * tp + (pa & 0xff), ob = (pb >> 8) * tp + (pb & 0xff);
+            int sa, sb;
+            fast_score_pair(t0 + oa, t0 + ob, tp, thr, sa, sb);
+            s0[oa] = (uint8_t)sa;
+            s0[ob] = (uint8_t)sb;
         }
         __syncthreads();
         // (3) 3x3 non-max suppression inside the cell's detection region
