@@ -14,8 +14,16 @@
 
 #define FAST_THREADS 256
 
+// Shared-memory budget beyond the two tile planes.  A tile row pitch tp = align16(tw + 15), so the detection region is at most
+// (tp - 21) x (th - 6) pixels.  Survivors of the 3x3 suppression: no two of them are neighbours inside a cell, i.e. at most
+// ceil(w/2) x ceil(h/2) per cell region -> (vw/2 + cells) x ceil(vh/2) per tile (the second pass only adds to cells that had none).
+// The list of pre-test survivors holds at most every detection pixel.  Sized tightly because this decides how many CTAs fit an SM
+// (47.8 KB -> 4 CTAs; 40.6 KB -> 5).
 __host__ __device__ inline int orbx_fast_out_words(int tp_max, int th_max) {
-    return (tp_max / 2 + ORBX_FAST_CELLS + 2) * (th_max / 2 + 2);
+    return ((tp_max - 20) / 2 + ORBX_FAST_CELLS) * ((th_max - 5) / 2);
+}
+__host__ __device__ inline int orbx_fast_list_entries(int tp_max, int th_max) {
+    return (tp_max - 21) * (th_max - 6);
 }
 
 // The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
@@ -303,9 +311,10 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     }
 }
 
-// tile + score planes, then the survivor list: at most one survivor per 2x2 block of a cell's detection region
+// tile + score planes, the survivor words and the list of pre-test survivors (see orbx_fast_out_words)
 size_t orbx_fast_smem_bytes(int tp_max, int th_max) {
-    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * orbx_fast_out_words(tp_max, th_max) + sizeof(uint16_t) * tp_max * th_max;
+    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * orbx_fast_out_words(tp_max, th_max) +
+           sizeof(uint16_t) * orbx_fast_list_entries(tp_max, th_max);
 }
 
 orbx_status orbx_launch_fast(orbx_extractor *e, int batch, cudaStream_t s) {
