@@ -25,6 +25,10 @@ __host__ __device__ inline int orbx_fast_out_words(int tp_max, int th_max) {
 __host__ __device__ inline int orbx_fast_list_entries(int tp_max, int th_max) {
     return (tp_max - 21) * (th_max - 6);
 }
+// the score plane holds detection pixels only: pitch tp - 16 (>= the widest detection row, a multiple of 16), th - 6 rows
+__host__ __device__ inline int orbx_fast_score_bytes(int tp_max, int th_max) {
+    return (tp_max - 16) * (th_max - 6);
+}
 
 // The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
 // (0,-3),(-1,-3),(-2,-2),(-3,-1),(-3,0),(-3,1),(-2,2),(-1,3).
@@ -115,7 +119,7 @@ struct FastShared {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// dynamic smem layout: [tile bytes th x tp][score bytes th x tp][out words][list u16 th x tp]
+// dynamic smem layout: [tile bytes th x tp][score bytes (th - 6) x (tp - 16)][out words][list u16]
 // The tile arrives by TMA: one cp.async.bulk.tensor of the (tp x th_max) box of the level's tensor map whose first column
 // is (19 + x0) rounded down to 16 (TMA wants 16-byte aligned row starts) and first row 19 + y0, completion on an mbarrier;
 // rows / columns past the level read as zero and are never looked at.
@@ -141,7 +145,8 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     const int shift = gx0 & 15;                        // the box starts at the aligned column gx0 - shift
     uint8_t *tile = smem;
     uint8_t *score = smem + (size_t)tp * th_max;
-    uint32_t *out = reinterpret_cast<uint32_t *>(score + (size_t)tp * th_max);
+    const int sp = tp - 16;                            // pitch of the score plane
+    uint32_t *out = reinterpret_cast<uint32_t *>(score + orbx_fast_score_bytes(tp_max, th_max));
     uint16_t *list = reinterpret_cast<uint16_t *>(out + orbx_fast_out_words(tp_max, th_max));
     const uint32_t mbar_a = smem_u32(&mbar);
     if (tid == 0) {
@@ -157,7 +162,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
                      ::"r"(smem_u32(tile)), "l"(tmap), "r"(gx0 - shift), "r"(ORBX_EDGE + (int)ck.y0), "r"(frame), "r"(mbar_a)
                      : "memory");
     }
-    for (int i = tid; i < (tp * th) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
+    for (int i = tid; i < (sp * (th - 6)) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
     const int vw = tw - 6, vh = th - 6;                // detection region
     const int wcell = ck.wcell;
     for (int x = tid; x < vw; x += FAST_THREADS) sh.cellof[x] = (uint8_t)(x / wcell);
@@ -169,7 +174,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
                  ::"r"(mbar_a) : "memory");
     const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
-    uint8_t *s0 = score + shift + 3 * tp + 3;
+    uint8_t *s0 = score;                               // score of detection pixel (x,y) = s0[y*sp + x]
 
     // words of a tile row that hold detection pixels, and the magic number that divides an item index by their count
     const int w_first = (shift + 3) >> 2, n_words = ((shift + 3 + vw - 1) >> 2) - w_first + 1;
@@ -250,32 +255,32 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
             const int oa = (pa >> 8) * tp + (pa & 0xff), ob = (pb >> 8) * tp + (pb & 0xff);
             int sa, sb;
             fast_score_pair(t0 + oa, t0 + ob, tp, thr, sa, sb);
-            s0[oa] = (uint8_t)sa;
-            s0[ob] = (uint8_t)sb;
+            s0[(pa >> 8) * sp + (pa & 0xff)] = (uint8_t)sa;
+            s0[(pb >> 8) * sp + (pb & 0xff)] = (uint8_t)sb;
         }
         __syncthreads();
         // (3) 3x3 non-max suppression inside the cell's detection region
         for (int i = tid; i < n_list; i += FAST_THREADS) {
             const int pos = list[i], x = pos & 0xff, y = pos >> 8;
-            const uint8_t *sp = s0 + y * tp + x;
-            const int s = sp[0];
+            const uint8_t *sq = s0 + y * sp + x;
+            const int s = sq[0];
             if (s == 0) continue;
             const int cell = sh.cellof[x];
             const int cx0 = cell * wcell;                                   // first detection column of the cell
             const int cx1 = cell == ck.ncells - 1 ? vw : cx0 + wcell;      // one past the last
             const bool l = x > cx0, r = x + 1 < cx1, u = y > 0, d = y + 1 < vh;
             bool keep = true;
-            if (l) keep = keep && s > sp[-1];
-            if (r) keep = keep && s > sp[1];
+            if (l) keep = keep && s > sq[-1];
+            if (r) keep = keep && s > sq[1];
             if (u) {
-                keep = keep && s > sp[-tp];
-                if (l) keep = keep && s > sp[-tp - 1];
-                if (r) keep = keep && s > sp[-tp + 1];
+                keep = keep && s > sq[-sp];
+                if (l) keep = keep && s > sq[-sp - 1];
+                if (r) keep = keep && s > sq[-sp + 1];
             }
             if (d) {
-                keep = keep && s > sp[tp];
-                if (l) keep = keep && s > sp[tp - 1];
-                if (r) keep = keep && s > sp[tp + 1];
+                keep = keep && s > sq[sp];
+                if (l) keep = keep && s > sq[sp - 1];
+                if (r) keep = keep && s > sq[sp + 1];
             }
             if (keep) {
                 atomicAdd(&sh.cnt[cell], 1);
@@ -313,7 +318,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
 
 // tile + score planes, the survivor words and the list of pre-test survivors (see orbx_fast_out_words)
 size_t orbx_fast_smem_bytes(int tp_max, int th_max) {
-    return (size_t)2 * tp_max * th_max + sizeof(uint32_t) * orbx_fast_out_words(tp_max, th_max) +
+    return (size_t)tp_max * th_max + orbx_fast_score_bytes(tp_max, th_max) + sizeof(uint32_t) * orbx_fast_out_words(tp_max, th_max) +
            sizeof(uint16_t) * orbx_fast_list_entries(tp_max, th_max);
 }
 
