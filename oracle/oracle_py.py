@@ -666,36 +666,36 @@ def ref_matcher_lib():
     return _REFM
 
 
-def _declare_refm(_REFM):
-    if True:
-        _REFM.orbmref_hamming256.argtypes = [C.c_void_p, C.c_void_p]
-        _REFM.orbmref_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
-        _REFM.orbmref_search_by_projection_frame.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 6 + [
-            C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
-        _REFM.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                                              C.c_void_p]
-        _REFM.orbmref_is_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        _REFM.orbmref_match_buckets.argtypes = [C.POINTER(OBucketJob), C.c_int, C.c_void_p, C.c_void_p]
-        _REFM.orbmref_search_for_initialization.argtypes = [C.POINTER(OFrame), C.POINTER(OFrame), C.c_void_p, C.c_int, C.c_float, C.c_int,
-                                                            C.c_void_p]
-        _REFM.orbmref_distinctive_descriptors.restype = None
-        _REFM.orbmref_distinctive_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        _REFM.orbvref_load_text.restype = C.c_void_p
-        _REFM.orbvref_load_text.argtypes = [C.c_char_p]
-        _REFM.orbvref_destroy.argtypes = [C.c_void_p]
-        _REFM.orbvref_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
-        _REFM.orbmref_search_by_projection_kf.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 5 + [
-            C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        _REFM.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
-                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        _REFM.orbmref_window.argtypes = [C.c_int, C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
-                                         C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 8
-        _REFM.orbmref_search_by_sim3.argtypes = [C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OFrame), C.c_void_p, C.c_void_p,
-                                                 C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
-        _REFM.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                          C.c_void_p, C.c_int]
-        _REFM.orbvref_compute_bow.restype = None
-        _REFM.orbvref_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+def _declare_refm(R):
+    """argument / result types of the C entry points of oracle/orbmatcher_ref_shim.cpp (same for both builds)"""
+    R.orbmref_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+    R.orbmref_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    R.orbmref_search_by_projection_frame.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 6 + [
+        C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    R.orbmref_search_by_projection_points.argtypes = [C.POINTER(OFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                                          C.c_void_p]
+    R.orbmref_is_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.orbmref_match_buckets.argtypes = [C.POINTER(OBucketJob), C.c_int, C.c_void_p, C.c_void_p]
+    R.orbmref_search_for_initialization.argtypes = [C.POINTER(OFrame), C.POINTER(OFrame), C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                                        C.c_void_p]
+    R.orbmref_distinctive_descriptors.restype = None
+    R.orbmref_distinctive_descriptors.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.orbvref_load_text.restype = C.c_void_p
+    R.orbvref_load_text.argtypes = [C.c_char_p]
+    R.orbvref_destroy.argtypes = [C.c_void_p]
+    R.orbvref_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
+    R.orbmref_search_by_projection_kf.argtypes = [C.POINTER(OFrame), C.c_int] + [C.c_void_p] * 5 + [
+        C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.orbmref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    R.orbmref_window.argtypes = [C.c_int, C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 8
+    R.orbmref_search_by_sim3.argtypes = [C.POINTER(OFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OFrame), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    R.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int]
+    R.orbvref_compute_bow.restype = None
+    R.orbvref_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
 
 
 def ref_hamming256(a, b):
