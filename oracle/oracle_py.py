@@ -694,6 +694,12 @@ def _declare_refm(R):
                                              C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
     R.orbmref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_int]
+    if hasattr(R, "orbmref_three_maxima"):          # reference build only
+        R.orbmref_three_maxima.restype = None
+        R.orbmref_three_maxima.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int32)] * 3
+    R.orbmref_keyframe_features_in_area.argtypes = [C.POINTER(OFrame), C.c_float, C.c_float, C.c_float, C.c_void_p]
+    R.orbmref_extractor_quota_umax.restype = None
+    R.orbmref_extractor_quota_umax.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     R.orbvref_compute_bow.restype = None
     R.orbvref_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
 
@@ -881,3 +887,26 @@ def ref_search_by_sim3(kf1, R1, t1, p1, kf2, R2, t2, p2, preset12, s12, R12, t12
     n = ref_matcher_lib().orbmref_search_by_sim3(C.byref(f1), _p(a[0]), _p(a[1]), _p(q1), C.byref(f2), _p(a[2]), _p(a[3]), _p(q2), _p(pre),
                                                 s12, _p(a[4]), _p(a[5]), th, _p(m))
     return n, m
+
+
+def ref_three_maxima(hist):
+    """the reference's ORBmatcher::ComputeThreeMaxima on a histogram of bin sizes"""
+    h = np.ascontiguousarray(hist, np.int32)
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    ref_matcher_lib().orbmref_three_maxima(_p(h), len(h), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def ref_keyframe_features_in_area(fr, x, y, r):
+    """the reference's KeyFrame::GetFeaturesInArea on a KeyFrame built from the record by its constructor"""
+    f, keep = _oframe(fr)
+    out = np.zeros(max(f.n, 1), np.int32)
+    n = ref_matcher_lib().orbmref_keyframe_features_in_area(C.byref(f), x, y, r, _p(out))
+    return out[:n].copy()
+
+
+def ref_extractor_quota_umax(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """mnFeaturesPerLevel and umax as the reference's ORBextractor constructor computes them"""
+    q, u = np.zeros(nlevels, np.int32), np.zeros(16, np.int32)
+    ref_matcher_lib().orbmref_extractor_quota_umax(nfeatures, scale_factor, nlevels, ini_th, min_th, _p(q), _p(u))
+    return q, u

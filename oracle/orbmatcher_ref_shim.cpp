@@ -699,4 +699,43 @@ int orbmref_search_by_sim3(const orbo_frame *K1, const float R1[9], const float 
     orbref_arena_release();
     return n;
 }
+
+// ---- small members ----
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:1601-1642; protected): histo[k] = number of entries of bin k.  Reference build only:
+// the adapters run the histogram on the device and do not define this helper.
+#ifndef ORBREF_SYSTEM_ALLOCATOR
+void orbmref_three_maxima(const int32_t *histo, int L, int32_t *ind1, int32_t *ind2, int32_t *ind3) {
+    orbref_arena_retain();
+    {
+        std::vector<std::vector<int> > h(L);
+        for (int k = 0; k < L; k++) h[k].assign(histo[k], 0);
+        ORBmatcher m(0.6f, true);
+        int a = -1, b = -1, c = -1;
+        m.ComputeThreeMaxima(h.data(), L, a, b, c);
+        *ind1 = a; *ind2 = b; *ind3 = c;
+    }
+    orbref_arena_release();
+}
+#endif
+// KeyFrame::GetFeaturesInArea(x, y, r) (KeyFrame.cc:630-669) on a keyframe built from the record
+int orbmref_keyframe_features_in_area(const orbo_frame *F, float x, float y, float r, int *out) {
+    orbref_arena_retain();
+    Frame *f = make_frame(F);
+    KeyFrame *kf = new KeyFrame(*f, the_map(), NULL);
+    const std::vector<size_t> v = kf->GetFeaturesInArea(x, y, r);
+    for (size_t i = 0; i < v.size(); i++) out[i] = (int)v[i];
+    const int n = (int)v.size();
+    delete kf; delete f;
+    orbref_arena_release();
+    return n;
+}
+// the protected constructor tables of ORBextractor (ORBextractor.cc:436-469): features per level and umax[0..15]
+void orbmref_extractor_quota_umax(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int32_t *quota, int32_t *umax16) {
+    orbref_arena_retain();
+    ORBextractor *e = new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
+    for (int l = 0; l < nlevels; l++) quota[l] = e->mnFeaturesPerLevel[l];
+    for (int v = 0; v < 16; v++) umax16[v] = v < (int)e->umax.size() ? e->umax[v] : -1;
+    delete e;
+    orbref_arena_release();
+}
 }

@@ -262,6 +262,66 @@ def test_relocalisation_search_equals_the_reference(seed, th, orb_dist, check_or
     assert 600 < gate.sum() < 1000 and len(set(level[gate != 0].tolist())) == 8
 
 
+@needs_ref
+def test_every_ref_library_loads_and_exports_its_entry_points():
+    """no compute: dlopen with RTLD_NOW (ctypes) fails on any undefined symbol, which is how a broken drop-in build would show up
+    on the GPU box; the drop-in library must load here too (liborbx.so loads without a device)"""
+    import ctypes
+    from oracle import oracle_py as O
+    O.lib()
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    want = {"liborbextractor_ref.so": ["orbref_extractor_create", "orbref_extract", "orbref_level"],
+            "liborbmatcher_ref.so": ["orbmref_search_by_projection_frame", "orbmref_window", "orbmref_search_by_sim3", "orbmref_stereo",
+                                     "orbvref_compute_bow", "orbmref_three_maxima"],
+            "liborbmatcher_adapter.so": ["orbmref_search_by_projection_frame", "orbmref_window", "orbmref_search_by_sim3", "orbmref_stereo",
+                                         "orbvref_compute_bow", "orbmref_extract"]}
+    for name, syms in want.items():
+        path = os.path.join(ref_dir, name)
+        if not os.path.exists(path):
+            assert name == "liborbmatcher_adapter.so"       # only built where liborbx.so exists
+            continue
+        L = ctypes.CDLL(path)
+        for s_ in syms:
+            assert hasattr(L, s_), (name, s_)
+
+
+@needs_ref
+def test_three_maxima_equal_the_reference():
+    """ORBmatcher::ComputeThreeMaxima incl. ties, empty histograms and the 10 % rule"""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(0)
+    cases = [np.zeros(30, np.int32), np.full(30, 5, np.int32), np.array([10] + [0] * 29, np.int32), np.array([100, 9, 10, 11] + [0] * 26, np.int32)]
+    cases += [rng.integers(0, 6, 30).astype(np.int32) for _ in range(100)] + [rng.integers(0, 200, 30).astype(np.int32) for _ in range(100)]
+    for h in cases:
+        assert O.ref_three_maxima(h) == O.three_maxima(h), h.tolist()
+
+
+@needs_ref
+def test_keyframe_features_in_area_equals_the_reference():
+    """KeyFrame::GetFeaturesInArea (KeyFrame.cc:630-669) = the frame window search without a level filter"""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(4)
+    fr = synth.random_frame(rng, 1500)
+    hits = 0
+    for _ in range(300):
+        x, y, r = rng.uniform(-30, 670), rng.uniform(-30, 510), rng.uniform(0.5, 80)
+        a, b = O.ref_keyframe_features_in_area(fr, x, y, r), O.features_in_area(fr, x, y, r, -1, -1)
+        assert np.array_equal(a, b), (x, y, r)
+        hits += len(a) > 0
+    assert hits > 100
+
+
+@needs_ref
+@pytest.mark.parametrize("params", [(1000, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (500, 1.3, 5, 25, 9), (1500, 1.1, 10, 12, 4), (123, 1.5, 3, 20, 7)])
+def test_extractor_quota_and_umax_equal_the_reference(params):
+    """mnFeaturesPerLevel (ORBextractor.cc:436-446) and umax (:454-469), protected members of the reference's class"""
+    from oracle import oracle_py as O
+    q, u = O.ref_extractor_quota_umax(*params)
+    t = O.Extractor(*params).tables()
+    assert q.tolist() == t["quota"][:params[2]].tolist() and u.tolist() == t["umax"].tolist()
+    assert q.sum() == params[0] or q[-1] == 0
+
+
 def window_scene(seed, n=1200, n_pts=900):
     """a keyframe, its own map points, and candidate map points that project near its keypoints (position, normal, distance
     range, descriptor), some NULL / bad / already observed by the keyframe, with varying observation counts"""
