@@ -37,7 +37,7 @@ __device__ __forceinline__ void k2_linearize_body(const LbaDev &D, int robust, i
             D.chi2[e] = c;
             double rho1 = 1.0, cr = c;
             if (robust) {
-                const double d = D.stereo[e] ? D.d_stereo : D.d_mono, dsqr = d * d;
+                const double d = D.stereo[e] ? D.d_stereo : D.d_mono, dsqr = (double)(float)(d * d);   // RobustKernelHuber keeps dsqr in a float member (robust_kernel_impl.h:84)
                 if (c > dsqr) { const double sq = sqrt(c); cr = 2 * sq * d - dsqr; rho1 = d / sq; }
             }
             chi += cr;

@@ -109,7 +109,7 @@ __device__ __forceinline__ void po_pass(PoseShared &S, const PoseProbDev &P, con
         chi2[e] = c;
         double rho1 = 1.0, cr = c;
         if (robust) {
-            const double d = st ? d_stereo : d_mono, dsqr = d * d;
+            const double d = st ? d_stereo : d_mono, dsqr = (double)(float)(d * d);   // RobustKernelHuber keeps dsqr in a float member (robust_kernel_impl.h:84)
             if (c > dsqr) { const double sq = sqrt(c); cr = 2 * sq * d - dsqr; rho1 = d / sq; }
         }
         acc[27] += cr;

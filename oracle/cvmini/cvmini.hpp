@@ -64,6 +64,9 @@ template <class T> struct Point_ {
 typedef Point_<int> Point2i;
 typedef Point2i Point;
 typedef Point_<float> Point2f;
+template <class T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 struct Rect { int x, y, width, height; Rect(int a, int b, int w, int h) : x(a), y(b), width(w), height(h) {} };
 

@@ -11,9 +11,13 @@
  *   SparseOptimizer::optimize / push / pop / update    core/sparse_optimizer.cpp:354-435, 600-613
  * The reduced camera system is solved by a dense Cholesky instead of Eigen's SimplicialLDLT with AMD ordering
  * (solvers/linear_solver_eigen.h:94-124): same solution up to rounding.
- * PARITY PINNING: the reference has no tests or vectors for this path and g2o/Eigen cannot be built here =>
- * unpinned by the reference; tests/test_lba_oracle.py checks this file against an independent numpy/scipy
- * implementation of the same LM schedule (dense normal equations).
+ * PARITY PINNING: pinned against the reference's own code.  The reference has no tests or vectors for this path, but its
+ * src/Optimizer.cc, src/Converter.cc and the whole vendored g2o compile unmodified against the Eigen stand-in oracle/eigenmini
+ * (oracle/_ref/liboptimizer_ref.so, `make -C oracle ref_opt`).  tests/test_oracle_ref_optimizer.py: the edge / exp-map / Huber /
+ * Converter leaves of this file return the same bits as the reference's classes on 10^4 inputs, and
+ * Optimizer::LocalBundleAdjustment run on KeyFrame / MapPoint graphs built by the reference's constructors gives the same erased
+ * observations and bad points, poses equal to float rounding and points within 1e-5 relative.  tests/test_lba_oracle.py
+ * additionally checks this file against an independent numpy/scipy implementation of the same LM schedule.
  */
 #include "orbx_oracle.h"
 #include <math.h>
@@ -61,7 +65,8 @@ static double edge_error(const lba *S, int e, double err[3], double *chi2) {
         const double ur = u - (double)((float)P->bf * invz);
         err[0] = P->e_obs[3 * e] - u; err[1] = P->e_obs[3 * e + 1] - v; err[2] = P->e_obs[3 * e + 2] - ur;
     }
-    *chi2 = info * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+    /* chi2() = _error.dot(information() * _error) with information = I * invSigma2 (base_edge.h:58-61) */
+    *chi2 = (err[0] * (info * err[0]) + err[1] * (info * err[1])) + err[2] * (info * err[2]);
     return Xc[2];
 }
 
@@ -72,12 +77,38 @@ static double compute_errors(lba *S) {   /* computeActiveErrors + activeRobustCh
         edge_error(S, e, S->err + 3 * e, &S->chi2[e]);
         double c = S->chi2[e];
         if (S->robust) {
-            const double d = huber_delta(S->P->e_stereo[e]), dsqr = d * d;
+            const double d = huber_delta(S->P->e_stereo[e]), dsqr = (double)(float)(d * d);   /* `float dsqr`, robust_kernel_impl.h:84 */
             if (c > dsqr) c = 2 * sqrt(c) * d - dsqr;
         }
         total += c;
     }
     return total;
+}
+
+/* linearizeOplus of EdgeSE3ProjectXYZ (types_six_dof_expmap.cpp:103-139) and EdgeStereoSE3ProjectXYZ (:188-234):
+ * A = dE/dX (D x 3), B = dE/dxi (D x 6), row-major */
+static void edge_jacobians(const se3 *T, const double *X, int D, double fx, double fy, double bf, double A[9], double B[18]) {
+    double R[9], Xc[3];
+    memset(A, 0, sizeof(double) * 9); memset(B, 0, sizeof(double) * 18);
+    quat_to_R(T->q, R);
+    se3_map(T, X, Xc);
+    const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z;
+    if (D == 2) {   /* _jacobianOplusXi = -1./z * tmp * R with tmp = [fx 0 -x/z*fx; 0 fy -y/z*fy] (.cpp:116-126): ((-1/z) tmp) R, k ascending */
+        const double s = -1. / z, t00 = s * fx, t01 = s * 0., t02 = s * (-x / z * fx), t10 = s * 0., t11 = s * fy, t12 = s * (-y / z * fy);
+        for (int c = 0; c < 3; c++) {
+            A[c] = (t00 * R[c] + t01 * R[3 + c]) + t02 * R[6 + c];
+            A[3 + c] = (t10 * R[c] + t11 * R[3 + c]) + t12 * R[6 + c];
+        }
+    } else {        /* written out per coefficient in the stereo edge (.cpp:203-213) */
+        for (int c = 0; c < 3; c++) {
+            A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+            A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+            A[6 + c] = A[c] - bf * R[6 + c] / z2;
+        }
+    }
+    B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
+    B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
+    if (D == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
 }
 
 static void build_system(lba *S) {   /* BlockSolver::buildSystem */
@@ -87,25 +118,13 @@ static void build_system(lba *S) {   /* BlockSolver::buildSystem */
     for (int e = 0; e < P->n_edges; e++) {
         if (!edge_active(S, e)) continue;
         const int D = P->e_stereo[e] ? 3 : 2;
-        const se3 *T = &S->kf[P->e_kf[e]];
-        double R[9], Xc[3];
-        quat_to_R(T->q, R);
-        se3_map(T, S->pt + 3 * P->e_pt[e], Xc);
-        const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = P->fx, fy = P->fy, bf = P->bf;
-        double A[9] = {0}, B[18] = {0};   /* A = dE/dX (D x 3), B = dE/dxi (D x 6) */
-        for (int c = 0; c < 3; c++) {
-            A[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
-            A[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
-            if (D == 3) A[6 + c] = A[c] - bf * R[6 + c] / z2;
-        }
-        B[0] = x * y / z2 * fx; B[1] = -(1 + (x * x / z2)) * fx; B[2] = y / z * fx; B[3] = -1. / z * fx; B[4] = 0; B[5] = x / z2 * fx;
-        B[6] = (1 + y * y / z2) * fy; B[7] = -x * y / z2 * fy; B[8] = -x / z * fy; B[9] = 0; B[10] = -1. / z * fy; B[11] = y / z2 * fy;
-        if (D == 3) { B[12] = B[0] - bf * y / z2; B[13] = B[1] + bf * x / z2; B[14] = B[2]; B[15] = B[3]; B[16] = 0; B[17] = B[5] - bf / z2; }
+        double A[9], B[18];   /* A = dE/dX (D x 3), B = dE/dxi (D x 6) */
+        edge_jacobians(&S->kf[P->e_kf[e]], S->pt + 3 * P->e_pt[e], D, P->fx, P->fy, P->bf, A, B);
         const double info = (double)P->e_inv_sigma2[e];
         double rho1 = 1.0;
         if (S->robust) {
             const double d = huber_delta(P->e_stereo[e]);
-            if (S->chi2[e] > d * d) rho1 = d / sqrt(S->chi2[e]);
+            if (S->chi2[e] > (double)(float)(d * d)) rho1 = d / sqrt(S->chi2[e]);
         }
         const double w = rho1 * info;
         const double *er = S->err + 3 * e;
@@ -343,4 +362,61 @@ int orbo_lba_solve(const orbo_lba_problem *P, int its1, int its2, double *kf_out
     free(S.kf); free(S.pt); free(S.level1); free(S.kf_idx); free(S.pt_idx); free(S.Hpp); free(S.bp); free(S.Hll); free(S.bl);
     free(S.Hpl); free(S.err); free(S.chi2);
     return rc;
+}
+
+/* ---- leaf entry points: the same static functions as above on one edge / one vertex, for tests/test_oracle_ref_optimizer.py,
+ * which compares them with the reference's g2o classes compiled from /root/reference (oracle/_ref/liboptimizer_ref.so) ---- */
+void orbo_lba_edge_eval(int stereo, const double pose[7], const double X[3], const double obs[3], const double K[5], float inv_sigma2,
+                        double *err, double *chi2, int *depth_positive, double *A, double *B) {
+    orbo_lba_problem P;
+    memset(&P, 0, sizeof(P));
+    const int32_t zero = 0;
+    const uint8_t st = (uint8_t)(stereo != 0), fixed = 0;
+    P.n_kf = 1; P.kf_pose = pose; P.kf_fixed = &fixed; P.n_pts = 1; P.pts = X; P.n_edges = 1; P.e_kf = &zero; P.e_pt = &zero;
+    P.e_obs = obs; P.e_inv_sigma2 = &inv_sigma2; P.e_stereo = &st; P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = K[4];
+    lba S;
+    memset(&S, 0, sizeof(S));
+    se3 T;
+    memcpy(T.q, pose, sizeof(double) * 4); memcpy(T.t, pose + 4, sizeof(double) * 3);
+    double pt[3] = {X[0], X[1], X[2]}, e3[3];
+    S.P = &P; S.kf = &T; S.pt = pt;
+    const double z = edge_error(&S, 0, e3, chi2);
+    for (int i = 0; i < (stereo ? 3 : 2); i++) err[i] = e3[i];
+    *depth_positive = z > 0;
+    double A9[9], B18[18];
+    edge_jacobians(&T, pt, stereo ? 3 : 2, P.fx, P.fy, P.bf, A9, B18);
+    memcpy(A, A9, sizeof(double) * 3 * (stereo ? 3 : 2)); memcpy(B, B18, sizeof(double) * 6 * (stereo ? 3 : 2));
+}
+void orbo_se3_oplus(const double pose[7], const double update[6], double out[7]) {
+    se3 T;
+    memcpy(T.q, pose, sizeof(double) * 4); memcpy(T.t, pose + 4, sizeof(double) * 3);
+    se3_oplus(&T, update);
+    memcpy(out, T.q, sizeof(double) * 4); memcpy(out + 4, T.t, sizeof(double) * 3);
+}
+void orbo_se3_map(const double pose[7], const double X[3], double out[3]) {
+    se3 T;
+    memcpy(T.q, pose, sizeof(double) * 4); memcpy(T.t, pose + 4, sizeof(double) * 3);
+    se3_map(&T, X, out);
+}
+/* RobustKernelHuber::robustify as the two optimiser oracles use it: rho[0] enters the robust chi2 (compute_errors), rho[1] scales
+ * the information and the right-hand side (build_system); rho[2] is dropped by g2o (base_edge.h:96-102) */
+void orbo_huber(double e2, double delta, double rho[3]) {
+    const double dsqr = (double)(float)(delta * delta);   /* `float dsqr`, robust_kernel_impl.h:84 */
+    if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; }
+    else { const double sqrte = sqrt(e2); rho[0] = 2 * sqrte * delta - dsqr; rho[1] = delta / sqrte; rho[2] = -0.5 * rho[1] / e2; }
+}
+/* Converter::toSE3Quat(cv::Mat) (src/Converter.cc:41-51): float entries widened, Quaterniond(R), normalizeRotation */
+void orbo_to_se3quat(const float Tcw[16], double pose[7]) {
+    double R[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = (double)Tcw[4 * r + c];
+    R_to_quat(R, pose);
+    quat_normalize(pose);
+    for (int r = 0; r < 3; r++) pose[4 + r] = (double)Tcw[4 * r + 3];
+}
+/* Converter::toCvMat(SE3Quat) (src/Converter.cc:53-57, 67-75): to_homogeneous_matrix narrowed to float */
+void orbo_to_cvmat(const double pose[7], float Tcw[16]) {
+    double R[9];
+    quat_to_R(pose, R);
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Tcw[4 * r + c] = (float)R[3 * r + c]; Tcw[4 * r + 3] = (float)pose[4 + r]; }
+    Tcw[12] = Tcw[13] = Tcw[14] = 0.f; Tcw[15] = 1.f;
 }

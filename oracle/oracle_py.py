@@ -910,3 +910,170 @@ def ref_extractor_quota_umax(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th
     q, u = np.zeros(nlevels, np.int32), np.zeros(16, np.int32)
     ref_matcher_lib().orbmref_extractor_quota_umax(nfeatures, scale_factor, nlevels, ini_th, min_th, _p(q), _p(u))
     return q, u
+
+
+# ---- the reference's own Optimizer + g2o (oracle/_ref/liboptimizer_ref.so, `make -C oracle ref_opt`) -----------------------
+REF_OPTIMIZER_SO = os.path.join(_HERE, "_ref", "liboptimizer_ref.so")
+OPT_ADAPTER_SO = os.path.join(_HERE, "_ref", "liboptimizer_adapter.so")
+_REFO = None
+_ADPO = None
+
+
+class OptrefLbaGraph(C.Structure):
+    """optref_lba_graph (oracle/optimizer_ref_shim.cpp)"""
+    _fields_ = [("n_kf", C.c_int32), ("kf_Tcw", C.c_void_p), ("kf_start", C.c_void_p), ("kp_xy_ur", C.c_void_p), ("kp_octave", C.c_void_p),
+                ("kp_point", C.c_void_p), ("n_pts", C.c_int32), ("pts", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("nlevels", C.c_int32), ("scale_factor", C.c_float), ("center_kf", C.c_int32), ("first_kf_id", C.c_int32),
+                ("stop_before", C.c_int32)]
+
+
+class OptrefPoseFrame(C.Structure):
+    """optref_pose_frame (oracle/optimizer_ref_shim.cpp)"""
+    _fields_ = [("n", C.c_int32), ("kp_xy_ur", C.c_void_p), ("kp_octave", C.c_void_p), ("Xw", C.c_void_p), ("has_point", C.c_void_p),
+                ("Tcw", C.c_float * 16), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("nlevels", C.c_int32), ("scale_factor", C.c_float)]
+
+
+def _declare_refo(R):
+    dp, ip = C.c_void_p, C.POINTER(C.c_int)
+    R.optref_edge_binary.argtypes = [C.c_int, dp, dp, dp, dp, C.c_float, dp, dp, ip, dp, dp]
+    R.optref_edge_pose_only.argtypes = [C.c_int, dp, dp, dp, dp, C.c_float, dp, dp, ip, dp]
+    R.optref_se3_oplus.argtypes = [dp, dp, dp]
+    R.optref_se3_map.argtypes = [dp, dp, dp]
+    R.optref_huber.argtypes = [C.c_double, C.c_double, dp]
+    R.optref_to_se3quat.argtypes = [dp, dp]
+    R.optref_to_cvmat.argtypes = [dp, dp]
+    R.optref_local_ba.argtypes = [C.POINTER(OptrefLbaGraph), dp, dp, dp, dp, dp]
+    R.optref_pose_optimization.argtypes = [C.POINTER(OptrefPoseFrame), dp, dp, C.POINTER(C.c_int32)]
+
+
+def ref_optimizer_lib(adapter=False):
+    """The reference's src/Optimizer.cc + src/Converter.cc + Thirdparty/g2o compiled against oracle/eigenmini + oracle/cvmini (None
+    if not built).  adapter=True: the drop-in build, where Optimizer::LocalBundleAdjustment / PoseOptimization are the product's
+    adapter/Optimizer_orbx.cc on the CUDA library (needs a GPU); the leaf entry points are the reference's in both."""
+    global _REFO, _ADPO
+    if adapter:
+        if _ADPO is None and os.path.exists(OPT_ADAPTER_SO):
+            lib()
+            _ADPO = C.CDLL(OPT_ADAPTER_SO)
+            _declare_refo(_ADPO)
+        return _ADPO
+    if _REFO is None and os.path.exists(REF_OPTIMIZER_SO):
+        lib()
+        _REFO = C.CDLL(REF_OPTIMIZER_SO)
+        _declare_refo(_REFO)
+    return _REFO
+
+
+def _leaf_decl():
+    L = lib()
+    dp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.orbo_lba_edge_eval.argtypes = [C.c_int, dp, dp, dp, dp, C.c_float, dp, dp, ip, dp, dp]
+    L.orbo_pose_edge_eval.argtypes = [dp, dp, dp, dp, C.c_float, dp, dp, ip, dp]
+    L.orbo_se3_oplus.argtypes = [dp, dp, dp]
+    L.orbo_se3_map.argtypes = [dp, dp, dp]
+    L.orbo_huber.argtypes = [C.c_double, C.c_double, dp]
+    L.orbo_to_se3quat.argtypes = [dp, dp]
+    L.orbo_to_cvmat.argtypes = [dp, dp]
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def edge_binary(stereo, pose, X, obs, K, inv_sigma2, ref=False):
+    """EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ on one (pose, point, observation): dict(err, chi2, depth_positive, JX, Jxi);
+    ref=True evaluates the reference's g2o classes, otherwise the oracle's restatement"""
+    D = 3 if stereo else 2
+    pose, X, obs, K = _f64(pose), _f64(X), _f64(obs), _f64(K)
+    err, chi2, JX, Jxi, dpos = np.zeros(D), np.zeros(1), np.zeros((D, 3)), np.zeros((D, 6)), C.c_int()
+    f = ref_optimizer_lib().optref_edge_binary if ref else _leaf_decl().orbo_lba_edge_eval
+    f(int(stereo), _p(pose), _p(X), _p(obs), _p(K), float(inv_sigma2), _p(err), _p(chi2), C.byref(dpos), _p(JX), _p(Jxi))
+    return dict(err=err, chi2=chi2[0], depth_positive=dpos.value, JX=JX, Jxi=Jxi)
+
+
+def edge_pose_only(pose, X, obs, K, inv_sigma2, ref=False):
+    """EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose (obs[2] < 0: monocular): dict(err, chi2, depth_positive, Jxi)"""
+    stereo = not (obs[2] < 0)
+    D = 3 if stereo else 2
+    pose, X, obs, K = _f64(pose), _f64(X), _f64(obs), _f64(K)
+    err, chi2, Jxi, dpos = np.zeros(D), np.zeros(1), np.zeros((D, 6)), C.c_int()
+    if ref:
+        ref_optimizer_lib().optref_edge_pose_only(int(stereo), _p(pose), _p(X), _p(obs), _p(K), float(inv_sigma2), _p(err), _p(chi2), C.byref(dpos), _p(Jxi))
+    else:
+        _leaf_decl().orbo_pose_edge_eval(_p(pose), _p(X), _p(obs), _p(K), float(inv_sigma2), _p(err), _p(chi2), C.byref(dpos), _p(Jxi))
+    return dict(err=err, chi2=chi2[0], depth_positive=dpos.value, Jxi=Jxi)
+
+
+def se3_oplus(pose, update, ref=False):
+    pose, update, out = _f64(pose), _f64(update), np.zeros(7)
+    (ref_optimizer_lib().optref_se3_oplus if ref else _leaf_decl().orbo_se3_oplus)(_p(pose), _p(update), _p(out))
+    return out
+
+
+def se3_map(pose, X, ref=False):
+    pose, X, out = _f64(pose), _f64(X), np.zeros(3)
+    (ref_optimizer_lib().optref_se3_map if ref else _leaf_decl().orbo_se3_map)(_p(pose), _p(X), _p(out))
+    return out
+
+
+def huber(e2, delta, ref=False):
+    rho = np.zeros(3)
+    (ref_optimizer_lib().optref_huber if ref else _leaf_decl().orbo_huber)(float(e2), float(delta), _p(rho))
+    return rho
+
+
+def to_se3quat(Tcw, ref=False):
+    T, out = np.ascontiguousarray(Tcw, np.float32).reshape(16), np.zeros(7)
+    (ref_optimizer_lib().optref_to_se3quat if ref else _leaf_decl().orbo_to_se3quat)(_p(T), _p(out))
+    return out
+
+
+def to_cvmat(pose, ref=False):
+    pose, out = _f64(pose), np.zeros(16, np.float32)
+    (ref_optimizer_lib().optref_to_cvmat if ref else _leaf_decl().orbo_to_cvmat)(_p(pose), _p(out))
+    return out.reshape(4, 4)
+
+
+def ref_local_ba(g, adapter=False):
+    """Optimizer::LocalBundleAdjustment of the reference (or, adapter=True, of the drop-in build) on a KeyFrame / MapPoint graph
+    built by the reference's constructors from g = dict(kf_Tcw[n,4,4] f32, kf_start[n+1], kp_xy_ur[m,3] f32, kp_octave[m], kp_point[m],
+    pts[L,3] f32, K=(fx,fy,cx,cy,bf), center_kf, first_kf_id[, nlevels, scale_factor, stop_before])
+    -> dict(Tcw, pts, kp_kept, pt_bad, kf_role)"""
+    R = ref_optimizer_lib(adapter)
+    G = OptrefLbaGraph()
+    keep = dict(kf_Tcw=np.ascontiguousarray(g["kf_Tcw"], np.float32), kf_start=np.ascontiguousarray(g["kf_start"], np.int32),
+                kp_xy_ur=np.ascontiguousarray(g["kp_xy_ur"], np.float32), kp_octave=np.ascontiguousarray(g["kp_octave"], np.int32),
+                kp_point=np.ascontiguousarray(g["kp_point"], np.int32), pts=np.ascontiguousarray(g["pts"], np.float32))
+    for k, v in keep.items():
+        setattr(G, k, v.ctypes.data)
+    G.n_kf, G.n_pts = len(keep["kf_Tcw"]), len(keep["pts"])
+    G.fx, G.fy, G.cx, G.cy, G.bf = (float(v) for v in g["K"][:5])
+    G.nlevels, G.scale_factor = int(g.get("nlevels", 8)), float(g.get("scale_factor", 1.2))
+    G.center_kf, G.first_kf_id, G.stop_before = int(g["center_kf"]), int(g.get("first_kf_id", 1)), int(g.get("stop_before", 0))
+    m = len(keep["kp_point"])
+    Tcw, pts = np.zeros((G.n_kf, 4, 4), np.float32), np.zeros((G.n_pts, 3), np.float32)
+    kept, bad, role = np.zeros(max(m, 1), np.uint8), np.zeros(max(G.n_pts, 1), np.uint8), np.zeros(max(G.n_kf, 1), np.uint8)
+    R.optref_local_ba(C.byref(G), _p(Tcw), _p(pts), _p(kept), _p(bad), _p(role))
+    return dict(Tcw=Tcw, pts=pts, kp_kept=kept[:m], pt_bad=bad[:G.n_pts], kf_role=role[:G.n_kf])
+
+
+def ref_pose_optimization(f, adapter=False):
+    """Optimizer::PoseOptimization of the reference (or of the drop-in build) on a Frame built from f = dict(kp_xy_ur[n,3] f32,
+    kp_octave[n], Xw[n,3] f32, has_point[n], Tcw[4,4] f32, K) -> dict(ret, Tcw, outlier, n_bad)"""
+    R = ref_optimizer_lib(adapter)
+    F = OptrefPoseFrame()
+    keep = dict(kp_xy_ur=np.ascontiguousarray(f["kp_xy_ur"], np.float32), kp_octave=np.ascontiguousarray(f["kp_octave"], np.int32),
+                Xw=np.ascontiguousarray(f["Xw"], np.float32), has_point=np.ascontiguousarray(f["has_point"], np.uint8))
+    for k, v in keep.items():
+        setattr(F, k, v.ctypes.data)
+    F.n = len(keep["kp_octave"])
+    for i, v in enumerate(np.asarray(f["Tcw"], np.float32).reshape(16)):
+        F.Tcw[i] = v
+    F.fx, F.fy, F.cx, F.cy, F.bf = (float(v) for v in f["K"][:5])
+    F.nlevels, F.scale_factor = int(f.get("nlevels", 8)), float(f.get("scale_factor", 1.2))
+    Tcw, out, nb = np.zeros((4, 4), np.float32), np.zeros(max(F.n, 1), np.uint8), C.c_int32()
+    r = R.optref_pose_optimization(C.byref(F), _p(Tcw), _p(out), C.byref(nb))
+    return dict(ret=r, Tcw=Tcw, outlier=out[:F.n].copy(), n_bad=nb.value)

@@ -17,8 +17,11 @@
  *    the reference's own src/ORBmatcher.cc, Frame.cc, MapPoint.cc, KeyFrame.cc and DBoW2 sources, compiled unmodified into
  *    oracle/_ref/liborbmatcher_ref.so (tests/test_oracle_ref_matcher.py, tests/golden/ref_match.npz); vocabulary bookkeeping
  *    also against oracle/_ref/libdbow2_ref.so.  See each file's header for the exact functions.
- *  - the two optimisers (lba_oracle.c, pose_oracle.c): "parity unpinned" by the reference — src/Optimizer.cc needs g2o, which
- *    needs Eigen, absent from this image; their headers name the independent restatements they are checked against.
+ *  - the two optimisers (lba_oracle.c, pose_oracle.c): PINNED against the reference's own src/Optimizer.cc, src/Converter.cc and the
+ *    whole vendored Thirdparty/g2o, compiled unmodified against the Eigen stand-in oracle/eigenmini into
+ *    oracle/_ref/liboptimizer_ref.so (tests/test_oracle_ref_optimizer.py: leaf arithmetic bit-equal, whole functions equal on
+ *    reference-built KeyFrame / MapPoint / Frame objects).  What the stand-in decides and Eigen might decide differently is
+ *    rounding only (evaluation order of small products, LDLT ordering), three orders of magnitude below the 1e-4 tolerance.
  */
 #ifndef ORBX_ORACLE_H
 #define ORBX_ORACLE_H
@@ -223,6 +226,19 @@ typedef struct {
 } orbo_pose_problem;
 /* returns nInitialCorrespondences - nBad; outlier[n] = mvbOutlier of the observations; pose_out = the recovered SE3Quat */
 int orbo_pose_optimize(const orbo_pose_problem *P, double pose_out[7], uint8_t *outlier, int32_t *n_bad, int32_t *lm_trials);
+
+/* ---- leaf evaluators of the two optimiser oracles (lba_oracle.c / pose_oracle.c): the same static functions the solvers use, on
+ * one edge / vertex; tests/test_oracle_ref_optimizer.py compares them with the reference's g2o classes (oracle/_ref/liboptimizer_ref.so).
+ * Jacobians are row-major: A = dE/dX (D x 3), B / J = dE/dxi (D x 6), D = 2 (monocular) or 3 (stereo). */
+void orbo_lba_edge_eval(int stereo, const double pose[7], const double X[3], const double obs[3], const double K[5], float inv_sigma2,
+                        double *err, double *chi2, int *depth_positive, double *A, double *B);
+void orbo_pose_edge_eval(const double pose[7], const double X[3], const double obs[3], const double K[5], float inv_sigma2,
+                         double *err, double *chi2, int *depth_positive, double *J);
+void orbo_se3_oplus(const double pose[7], const double update[6], double out[7]);   /* VertexSE3Expmap::oplusImpl */
+void orbo_se3_map(const double pose[7], const double X[3], double out[3]);          /* SE3Quat::map */
+void orbo_huber(double e2, double delta, double rho[3]);                            /* RobustKernelHuber::robustify */
+void orbo_to_se3quat(const float Tcw[16], double pose[7]);                          /* Converter::toSE3Quat(cv::Mat) */
+void orbo_to_cvmat(const double pose[7], float Tcw[16]);                            /* Converter::toCvMat(SE3Quat) */
 
 #ifdef __cplusplus
 }

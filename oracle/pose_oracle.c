@@ -12,8 +12,11 @@
  * (setLevel(1)), classifies every edge with FLOAT chi2 against 5.991f / 7.815f (:377-379, :401-403), drops the Huber kernel
  * after the third round (:391, :416) and stops early when the graph has fewer than 10 edges (:419).
  * The 6x6 system is solved by Cholesky (LL^T) where the reference uses Eigen's LDLT: same solution up to rounding.
- * PARITY PINNING: unpinned by the reference (no test for this function, g2o / Eigen cannot be built here);
- * tests/test_pose_oracle.py checks this file against an independent numpy implementation of the same schedule.
+ * PARITY PINNING: pinned against the reference's own code: src/Optimizer.cc + g2o compiled unmodified against the Eigen stand-in
+ * oracle/eigenmini (oracle/_ref/liboptimizer_ref.so).  tests/test_oracle_ref_optimizer.py: the OnlyPose edges of this file return
+ * the same bits as the reference's classes, and Optimizer::PoseOptimization run on a reference-built Frame gives the same
+ * mvbOutlier flags, return value and nBadPoseOpt and a float pose identical to this file's.  tests/test_pose_oracle.py also
+ * checks it against an independent numpy implementation of the same schedule.
  */
 #include "orbx_oracle.h"
 #include "se3_oracle.h"
@@ -49,7 +52,7 @@ static void edge_error(const pose_opt *S, int e, double err[3], double *chi2, do
          * unlike EdgeStereoSE3ProjectXYZ::cam_project, whose bf parameter is a float */
         err[2] = P->obs[3 * e + 2] - (u - (double)(float)P->bf * (double)invz);
     }
-    *chi2 = info * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+    *chi2 = (err[0] * (info * err[0]) + err[1] * (info * err[1])) + err[2] * (info * err[2]);   /* _error.dot(information() * _error) */
 }
 
 static double compute_errors(pose_opt *S) {
@@ -60,12 +63,22 @@ static double compute_errors(pose_opt *S) {
         edge_error(S, e, S->err + 3 * e, &S->chi2[e], Xc);
         double c = S->chi2[e];
         if (S->robust) {
-            const double d = delta_of(is_stereo(S->P, e)), dsqr = d * d;
+            const double d = delta_of(is_stereo(S->P, e)), dsqr = (double)(float)(d * d);   /* `float dsqr`, robust_kernel_impl.h:84 */
             if (c > dsqr) c = 2 * sqrt(c) * d - dsqr;
         }
         total += c;
     }
     return total;
+}
+
+/* linearizeOplus of EdgeSE3ProjectXYZOnlyPose (types_six_dof_expmap.cpp:266-288) and EdgeStereoSE3ProjectXYZOnlyPose (:335-364):
+ * J = dE/dxi (D x 6), row-major, from the point in camera coordinates */
+static void pose_edge_jacobian(const double Xc[3], int st, double fx, double fy, double bf, double J[18]) {
+    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz;
+    memset(J, 0, sizeof(double) * 18);
+    J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+    J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+    if (st) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
 }
 
 static void build_system(pose_opt *S) {
@@ -76,16 +89,13 @@ static void build_system(pose_opt *S) {
         const int st = is_stereo(P, e), D = st ? 3 : 2;
         double Xc[3];
         se3_map(&S->T, P->Xw + 3 * e, Xc);
-        const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = P->fx, fy = P->fy, bf = (double)(float)P->bf;
-        double J[18] = {0};
-        J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
-        J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
-        if (st) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
+        double J[18];
+        pose_edge_jacobian(Xc, st, P->fx, P->fy, (double)(float)P->bf, J);
         const double info = (double)P->inv_sigma2[e];
         double rho1 = 1.0;
         if (S->robust) {
             const double d = delta_of(st);
-            if (S->chi2[e] > d * d) rho1 = d / sqrt(S->chi2[e]);
+            if (S->chi2[e] > (double)(float)(d * d)) rho1 = d / sqrt(S->chi2[e]);
         }
         const double *er = S->err + 3 * e;
         for (int a = 0; a < 6; a++) {
@@ -191,4 +201,26 @@ int orbo_pose_optimize(const orbo_pose_problem *P, double pose_out[7], uint8_t *
     if (lm_trials) *lm_trials = trials;
     free(S.level1); free(S.err); free(S.chi2);
     return n - nBad;
+}
+
+/* leaf entry point: the same static functions on one edge (compared with the reference's g2o classes in
+ * tests/test_oracle_ref_optimizer.py); obs[2] < 0 selects the monocular edge like mvuRight */
+void orbo_pose_edge_eval(const double pose[7], const double X[3], const double obs[3], const double K[5], float inv_sigma2,
+                         double *err, double *chi2, int *depth_positive, double *J) {
+    orbo_pose_problem P;
+    memset(&P, 0, sizeof(P));
+    P.n = 1; P.Xw = X; P.obs = obs; P.inv_sigma2 = &inv_sigma2;
+    memcpy(P.pose, pose, sizeof(double) * 7);
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = K[4];
+    pose_opt S;
+    memset(&S, 0, sizeof(S));
+    S.P = &P;
+    memcpy(S.T.q, pose, sizeof(double) * 4); memcpy(S.T.t, pose + 4, sizeof(double) * 3);
+    double e3[3], Xc[3], J18[18];
+    edge_error(&S, 0, e3, chi2, Xc);
+    const int st = is_stereo(&P, 0);
+    for (int i = 0; i < (st ? 3 : 2); i++) err[i] = e3[i];
+    *depth_positive = Xc[2] > 0;
+    pose_edge_jacobian(Xc, st, P.fx, P.fy, (double)(float)P.bf, J18);
+    memcpy(J, J18, sizeof(double) * 6 * (st ? 3 : 2));
 }

@@ -47,10 +47,18 @@ static inline void quat_mul(const double a[4], const double b[4], double o[4]) {
     o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
     o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
 }
+/* Eigen's Quaternion * Vector3 (QuaternionBase::_transformVector): uv = 2 (q.vec x v); v + w uv + q.vec x uv */
+static inline void quat_rotate(const double q[4], const double v[3], double o[3]) {
+    double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+    for (int i = 0; i < 3; i++) uv[i] += uv[i];
+    const double c[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+    for (int i = 0; i < 3; i++) o[i] = (v[i] + q[3] * uv[i]) + c[i];
+}
+/* SE3Quat::map: _r*xyz + _t (se3quat.h:217-220) */
 static inline void se3_map(const se3 *T, const double X[3], double o[3]) {
-    double R[9];
-    quat_to_R(T->q, R);
-    for (int r = 0; r < 3; r++) o[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + T->t[r];
+    double r[3];
+    quat_rotate(T->q, X, r);
+    for (int i = 0; i < 3; i++) o[i] = r[i] + T->t[i];
 }
 /* T <- exp(update) * T, VertexSE3Expmap::oplusImpl */
 static inline void se3_oplus(se3 *T, const double u[6]) {
@@ -76,9 +84,9 @@ static inline void se3_oplus(se3 *T, const double u[6]) {
     /* SE3Quat::operator*: r = r1*r2, t = t1 + r1*t2, normalize */
     se3 N;
     quat_mul(E.q, T->q, N.q);
-    double Rq[9];
-    quat_to_R(E.q, Rq);
-    for (int r = 0; r < 3; r++) N.t[r] = E.t[r] + Rq[3 * r] * T->t[0] + Rq[3 * r + 1] * T->t[1] + Rq[3 * r + 2] * T->t[2];
+    double rt[3];
+    quat_rotate(E.q, T->t, rt);
+    for (int r = 0; r < 3; r++) N.t[r] = E.t[r] + rt[r];
     quat_normalize(N.q);
     *T = N;
 }
