@@ -107,5 +107,16 @@ def _declare(L):
     L.orbx_mappoints_last_launches.argtypes = [vp]
     L.orbx_frustum_host.argtypes = [vp, i, vp, vp, vp, i]
     L.orbx_frustum_device.argtypes = [vp, i, vp, vp, vp, vp]
+    L.orbx_sequences_create.argtypes = [C.POINTER(vp), vp]
+    L.orbx_sequences_destroy.restype = None
+    L.orbx_sequences_destroy.argtypes = [vp]
+    L.orbx_sequences_capacity.argtypes = [vp]
+    L.orbx_sequences_reset.argtypes = [vp]
+    L.orbx_sequences_step_begin.argtypes = [vp, vp, sz, i, vp, vp]
+    L.orbx_sequences_step_end.argtypes = [vp]
+    L.orbx_sequences_step_host.argtypes = [vp, vp, sz, i, vp, vp]
+    L.orbx_sequences_last_launches.argtypes = [vp]
+    L.orbx_sequences_step_device.argtypes = [vp, vp, sz, i, vp, vp]
+    L.orbx_sequences_device_view.argtypes = [vp, vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -76,11 +76,6 @@ def set_workload(w, h, nfeat):
 
 set_workload(W, H, NFEAT)
 assert (PYR_PADDED, PYR_INTERIOR, FRAME_ALGO_BYTES) == (1158012, 950532, 1525212)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 64, from the one `ncu --set full` capture summarised in
-# profiles/r1_n_full.txt (the pyramid figure is the sum of its 8 launches)
-NCU_TRAFFIC_B64 = {"fast": 63.111680e6 + 1.766656e6, "blur": 71.203584e6 + 31.235584e6, "describe": 121.449728e6 + 5.571584e6,
-                   "pyramid": 85.3e6 + 0.03e6, "quadtree": 3.002880e6 + 0.052736e6}
-
 
 def peaks():
     try:
@@ -88,6 +83,51 @@ def peaks():
         return float(p["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def workload_config(batch):
+    """the `config` of the JSON line: identical in both arms (orbx and --impl reference), nothing run-dependent in it"""
+    return {"workload": "C2 extract+match: %dx%d G-rect frames, %d features, 8 levels, th 20/7; each frame matched against its predecessor "
+                        "(same scene shifted by (13, 7) px, map points on a plane at z = 4 m) with SearchByProjection(Cur, Last, th=7)" % (W, H, NFEAT),
+            "batch": batch,
+            "l2": "inputs larger than L2: every step reads a fresh batch from a pool of 8 x batch frames (157 MB at batch 64 > 126 MB L2)"}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 64 of every kernel of the step, from the committed summary of the
+    round's `ncu --set full` capture (profiles/r2_traffic.json, written by tools/ncu_summary.py traffic <report>); None if absent"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        return None
+
+
+def binary_identity():
+    """which liborbx.so ran: its hash, and whether it was built from the sources in this tree (build() records their hash next to it)"""
+    import hashlib
+    pkg = os.path.join(ROOT, "active-orb-slam2_b200")
+    out = {}
+    try:
+        out["liborbx_sha16"] = hashlib.sha256(open(os.path.join(pkg, "liborbx.so"), "rb").read()).hexdigest()[:16]
+        sys.path.insert(0, ROOT)
+        from __graft_entry__ import source_hash
+        out["source_sha16"] = source_hash()
+        out["built_from_sha16"] = json.load(open(os.path.join(pkg, "liborbx.build.json"))).get("source_sha16")
+        out["binary_matches_source"] = out["source_sha16"] == out["built_from_sha16"]
+    except Exception as ex_:                             # noqa: BLE001
+        out["error"] = str(ex_)[:120]
+    return out
+
+
+def bind_rank_to_cores(local_rank, world):
+    """one slice of the host cores per rank: the feeding thread of a rank and its pinned allocations stay on its own cores"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(len(cores) // max(world, 1), 1)
+        mine = cores[(local_rank * per) % len(cores):][:per] or cores
+        os.sched_setaffinity(0, mine)
+    except Exception:                                    # noqa: BLE001
+        pass
 
 
 def make_frames(n, seed0=0):
@@ -281,8 +321,7 @@ def run_reference(args, rank):
             "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2 extract+match: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7; each frame matched against its "
-                                   "predecessor with SearchByProjection(Cur, Last, th=7)", "batch": args.batch},
+            "config": workload_config(args.batch),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's src/ORBextractor.cc, ORBmatcher.cc, Frame.cc and MapPoint.cc compiled unmodified (oracle/Makefile, target "
@@ -302,8 +341,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2 extract+match: 640x480 G-rect frames, 1000 features, 8 levels, th 20/7; each frame matched against its "
-                               "predecessor with SearchByProjection(Cur, Last, th=7)", "batch": args.batch},
+        "config": workload_config(args.batch),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference itself cannot be built here (needs OpenCV/Eigen/Pangolin); this is the dependency-free C oracle of its "
@@ -527,6 +565,8 @@ def main():
     ap.add_argument("--width", type=int, default=W, help="frame width (default: the VGA workload BASELINE.json's metric is quoted on)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--features", type=int, default=NFEAT)
+    ap.add_argument("--profile-steps", type=int, default=0, help="ncu runs: after the warm-up, bracket this many device-resident steps with "
+                    "cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
     ap.add_argument("--extract-only", action="store_true", help="other frame shapes: time the extractor + matcher loop only (no LocalBA / stereo / ... sections)")
     args = ap.parse_args()
     default_workload = (args.width, args.height, args.features) == (W, H, NFEAT)
@@ -542,8 +582,7 @@ def main():
     import torch
     from orbx import synth
     from orbx._lib import KP_DTYPE
-    from orbx.extractor import ORBextractor
-    from orbx.matcher import LAST_POINT_DTYPE, FrameMatchJob, ORBmatcher, fill_view
+    from orbx.sequences import Sequences
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the orbx hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -552,99 +591,60 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
-    npool = 8                                           # 8 x 64 x 300 KB = 157 MB of inputs > 126 MB L2
-    NBASE = 16
-    frames_np = make_frames(npool * B, seed0=100 * rank)
-    host = torch.from_numpy(frames_np).pin_memory()
-    dev = host.cuda()
-    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local_rank)
-    mt = ORBmatcher(0.9, True, max_keypoints=ex.capacity, max_points=ex.capacity, max_jobs=B, device=local_rank)
-    cap = ex.capacity
-    d_kps = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
-    d_desc = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
-    d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_match = torch.empty(B * cap, dtype=torch.int32, device="cuda")
-    d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_sf = torch.from_numpy(ex.GetScaleFactors()).cuda()
-    stream = torch.cuda.current_stream()
-
-    def extract_device(slot, src=None):
-        src = dev[slot * B:(slot + 1) * B] if src is None else src
-        ex.run_device(src.data_ptr(), W * H, B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
-
-    # ---- setup (untimed): extract the whole pool once to build every frame's "last frame" (its predecessor) ----
+    bind_rank_to_cores(local_rank, world)
+    npool = 8                                           # 8 time steps x 64 sequences x 300 KB = 157 MB of inputs > 126 MB L2
+    # The workload: B independent sequences per handle advance in lockstep.  Sequence j shows G-rect scene j % 16 on a plane
+    # at z = 4 m; time step s shifts it by SHIFT[s] x (13, 7) px (np.roll), i.e. the camera translates; every frame is matched against
+    # its predecessor (the previous time step of the same sequence) with SearchByProjection(Cur, Last, th = 7), the predecessor's map
+    # points being its own keypoints unprojected at z = 4 m (Frame::UnprojectStereo) -- all inside orbx_sequences_step_*.
+    SHIFT = [0, 1, 2, 3, 4, 3, 2, 1]                   # a palindrome: cycling through the pool always moves by one step
     fx, fy, cx, cy, bf, bb = synth.TUM1_K
     Z = 4.0
-    last_pts = np.zeros((npool * B, cap), LAST_POINT_DTYPE)      # predecessor's keypoints as map points
-    last_desc = np.zeros((npool * B, cap, 32), np.uint8)
-    last_n = np.zeros(npool * B, np.int32)
-    pose_t = np.zeros((npool * B, 3), np.float32)
-    pool_kps, pool_desc, pool_cnt = [], [], []
-    for slot in range(npool):
-        extract_device(slot)
-        torch.cuda.synchronize()
-        pool_kps.append(d_kps.cpu().numpy().view(KP_DTYPE).reshape(B, cap).copy())
-        pool_desc.append(d_desc.cpu().numpy().reshape(B, cap, 32).copy())
-        pool_cnt.append(d_cnt.cpu().numpy().copy())
-    for g in range(npool * B):
-        p = g - NBASE if g >= NBASE else g               # same base image, previous shift (itself for the first variant)
-        ps, pj = divmod(p, B)
-        n = int(pool_cnt[ps][pj])
-        k = pool_kps[ps][pj][:n]
-        last_n[g] = n
-        last_pts[g, :n]["x"] = (k["x"].astype(np.float64) - cx) / fx * Z
-        last_pts[g, :n]["y"] = (k["y"].astype(np.float64) - cy) / fy * Z
-        last_pts[g, :n]["z"] = Z
-        last_pts[g, :n]["angle"] = k["angle"]
-        last_pts[g, :n]["octave"] = k["octave"]
-        last_pts[g, :n]["valid"] = 1
-        last_pts[g, :n]["blocks"] = 1
-        last_desc[g, :n] = pool_desc[ps][pj][:n]
-        if g >= NBASE:
-            pose_t[g] = (13.0 * Z / fx, 7.0 * Z / fy, 0.0)   # np.roll by (7, 13): the scene moves +13 px in x, +7 px in y
-    h_last_pts = torch.from_numpy(last_pts.view(np.uint8).reshape(npool * B, -1)).pin_memory()
-    h_last_desc = torch.from_numpy(last_desc.reshape(npool * B, -1)).pin_memory()
-    d_last_pts, d_last_desc = h_last_pts.cuda(), h_last_desc.cuda()
-
-    def build_jobs(pts_ptr, pts_stride, desc_ptr, desc_stride, slot, bufs=None):
-        b_cnt, b_kps, b_desc, b_match, b_nm = bufs if bufs is not None else (d_cnt, d_kps, d_desc, d_match, d_nm)
-        jobs = (FrameMatchJob * B)()
+    base = [synth.g_rect(100 * rank + i, W, H) for i in range(16)]
+    frames_np = np.empty((npool, B, H, W), np.uint8)
+    poses = np.zeros((npool, B, 3, 4), np.float32)
+    for s_ in range(npool):
         for j in range(B):
-            g = slot * B + j
-            J = jobs[j]
-            J.cur.n, J.cur.n_dev = 0, b_cnt.data_ptr() + 4 * j
-            J.cur.keys_un, J.cur.desc = b_kps.data_ptr() + 28 * cap * j, b_desc.data_ptr() + 32 * cap * j
-            J.cur.u_right, J.cur.claimed, J.cur.scale_factors = None, None, d_sf.data_ptr()
-            fill_view(J.cur, (0.0, 0.0, float(W), float(H)), synth.TUM1_K, NLEVELS)
-            J.n_last = int(last_n[g])
-            J.pts, J.last_desc = pts_ptr + pts_stride * j, desc_ptr + desc_stride * j
-            J.Rcw[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1]
-            J.tcw[:] = pose_t[g].tolist()
-            J.forward = J.backward = 0
-            J.th, J.check_ori = 7.0, 1
-            J.match, J.nmatches = b_match.data_ptr() + 4 * cap * j, b_nm.data_ptr() + 4 * j
-        return torch.from_numpy(np.frombuffer(bytes(jobs), np.uint8).copy()).cuda()
+            k = SHIFT[s_] + (j // 16)
+            frames_np[s_, j] = np.roll(base[j % 16], (7 * k, 13 * k), (0, 1)) if k else base[j % 16]
+            poses[s_, j, :, :3] = np.eye(3)
+            poses[s_, j, :, 3] = (13.0 * k * Z / fx, 7.0 * k * Z / fy, 0.0)     # np.roll by (7k, 13k): the scene moves +13k px in x, +7k px in y
+    host = torch.from_numpy(frames_np).pin_memory()
+    dev = host.cuda()
 
-    ps_, ds_ = cap * LAST_POINT_DTYPE.itemsize, cap * 32
-    jobs_dev = [build_jobs(d_last_pts.data_ptr() + ps_ * B * s_, ps_, d_last_desc.data_ptr() + ds_ * B * s_, ds_, s_) for s_ in range(npool)]
+    def new_handle():
+        return Sequences(B, W, H, synth.TUM1_K, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, stereo=False, th=7.0, check_ori=True, mono=False,
+                         const_depth=Z, device=local_rank)
 
-    def step_device(i):
+    sq = new_handle()
+    cap = sq.capacity
+    stream = torch.cuda.Stream()                        # the device-resident loops run on this stream; the timing events are recorded on it
+
+    def step_device(i, h=None, st=None):
         slot = i % npool
-        extract_device(slot)
-        d_match.fill_(-1)
-        mt.search_frames_device(jobs_dev[slot].data_ptr(), B, stream.cuda_stream)
+        (h or sq).step_device(dev[slot].data_ptr(), W * H, W, poses[slot], (st or stream).cuda_stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
     clocks.start()                                      # sampled from the warm-up to the end of the end-to-end loop
     for i in range(Wm):
         step_device(i)
     torch.cuda.synchronize()
-    launches_per_step = ex.last_launches() + 1 + 1      # + fill kernel + matcher kernel
+    launches_per_step = sq.last_launches() + 2          # + the two memset nodes of the match arrays
+    if args.profile_steps:
+        torch.cuda.cudart().cudaProfilerStart()
+        for i in range(args.profile_steps):
+            step_device(Wm + i)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        clocks.stop()
+        sq.close()
+        return
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -653,36 +653,36 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
+    view = sq.device_view()
+
     # per-stage times come from a second, untimed-for-`value` loop: with stage events on, the extractor keeps its stages on one
     # stream back to back (in the loop above the blur runs on a side stream next to the quadtree kernel)
     KP = min(K, 100)
-    ex.profile(KP)
+    sq.profile(KP)
     ev_m = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KP)]
     for i in range(KP):
-        slot = (Wm + i) % npool
-        extract_device(slot)
         ev_m[i][0].record(stream)
-        d_match.fill_(-1)
-        mt.search_frames_device(jobs_dev[slot].data_ptr(), B, stream.cuda_stream)
+        step_device(Wm + i)
         ev_m[i][1].record(stream)
     torch.cuda.synchronize()
-    runs, stage_ms = ex.stage_ms()
-    stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / KP
-    ex.profile(0)
+    runs, stage_ms = sq.stage_ms()
+    # everything of the step that is not the extractor: unprojection of the last frame, the projection search and its memsets
+    stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / KP - sum(stage_ms.values())
+    sq.profile(0)
     # ---- the same step followed by PoseOptimization of every frame from the match arrays, still device-resident (the three
     # calls Tracking::TrackWithMotionModel makes per frame: extract, SearchByProjection(Cur, Last), PoseOptimization) ----
     track = None
+    d_is2 = torch.from_numpy(np.float32(1.0) / (synth.scale_factors(NLEVELS, SCALE) ** 2)).cuda()      # mvInvLevelSigma2
     if rank == 0:
         from orbx.optimizer import PoseOptimizer
         pz = PoseOptimizer(max_observations=B * cap, max_frames=B, device=local_rank)
-        d_is2 = torch.from_numpy(ex.GetInverseScaleSigmaSquares()).cuda()
         d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
         d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
         d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
 
         def step_track(i):
             step_device(i)
-            pz.from_matches_device(jobs_dev[i % npool].data_ptr(), B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, d_pose.data_ptr(), d_inl.data_ptr(),
+            pz.from_matches_device(view.jobs, B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, d_pose.data_ptr(), d_inl.data_ptr(),
                                    d_outkp.data_ptr(), cap, stream.cuda_stream)
 
         for i in range(3):
@@ -699,56 +699,35 @@ def main():
         track = {"config": "the `value` step + Optimizer::PoseOptimization of all %d frames from the match arrays (monocular observations), device-resident" % B,
                  "frames_per_s": B / (ms_track * 1e-3), "ms_per_step": ms_track, "pose_ms_per_step": ms_track - ms_total / K,
                  "inliers_per_frame": float(d_inl.float().mean().item()), "kernel_launches_per_step": launches_per_step + pz.last_launches(),
-                 "api": "orbx_extractor_run_device + orbx_match_projection_frame_device + orbx_pose_from_matches_device"}
+                 "api": "orbx_sequences_step_device + orbx_pose_from_matches_device"}
         pz.close()
-    kp_per_frame = float(d_cnt.float().mean().item())
-    matches_per_frame = float(d_nm.float().mean().item())
-    match_sweeps = mt.last_sweeps(B).tolist()
 
-    # ---- end to end with HOST buffers: every step copies its frames and last-frame points from pinned host memory,
-    # runs extract + match through the C ABI, and reads keypoints, descriptors, counts and matches back ----
-    # Two lanes (extractor + matcher handle, device and pinned buffers, stream each) alternate, so the copies of one batch
-    # overlap the kernels of the other; every byte of every step still crosses the bus inside the timed region.
+    # ---- end to end with HOST buffers through the C ABI: every step hands pinned host frames and poses to orbx_sequences_step_begin
+    # (upload, kernels, download of keypoints, descriptors, counts and match arrays) and reads the results after
+    # orbx_sequences_step_end.  NLANES handles (B sequences each) are in flight, so the copies of one overlap the kernels of the
+    # others; every byte of every step crosses the bus inside the timed region. ----
     class Lane:
         pass
 
+    def pinned(shape, dtype):
+        return torch.zeros(shape, dtype={np.uint8: torch.uint8, np.int32: torch.int32, np.float32: torch.float32}[dtype]).pin_memory().numpy()
+
     lanes = []
-    NLANES = 4                                          # the end-to-end loop keeps this many batches in flight; the device-resident two-lane figures use the first two
+    NLANES = 4
     for li in range(NLANES):
         L = Lane()
-        L.ex = ex if li == 0 else ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local_rank)
-        L.mt = mt if li == 0 else ORBmatcher(0.9, True, max_keypoints=cap, max_points=cap, max_jobs=B, device=local_rank)
+        L.sq = sq if li == 0 else new_handle()
         L.stream = torch.cuda.Stream()
-        L.e_img = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
-        L.e_pts = torch.empty((B, ps_), dtype=torch.uint8, device="cuda")
-        L.e_desc = torch.empty((B, ds_), dtype=torch.uint8, device="cuda")
-        L.d_kps = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
-        L.d_desc = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
-        L.d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
-        L.d_match = torch.empty(B * cap, dtype=torch.int32, device="cuda")
-        L.d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
-        L.h_kps = torch.empty(B * cap * 28, dtype=torch.uint8).pin_memory()
-        L.h_desc = torch.empty(B * cap * 32, dtype=torch.uint8).pin_memory()
-        L.h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
-        L.h_match = torch.empty(B * cap, dtype=torch.int32).pin_memory()
-        L.h_nm = torch.zeros(B, dtype=torch.int32).pin_memory()
-        L.jobs = [build_jobs(L.e_pts.data_ptr(), ps_, L.e_desc.data_ptr(), ds_, s_, (L.d_cnt, L.d_kps, L.d_desc, L.d_match, L.d_nm))
-                  for s_ in range(npool)]
-        L.jobs_dev = [build_jobs(d_last_pts.data_ptr() + ps_ * B * s_, ps_, d_last_desc.data_ptr() + ds_ * B * s_, ds_, s_,
-                                 (L.d_cnt, L.d_kps, L.d_desc, L.d_match, L.d_nm)) for s_ in range(npool)]
-        L.busy = False
+        L.out = L.sq.alloc_outputs(pinned)
+        L.t, L.busy = 0, False
         lanes.append(L)
     torch.cuda.synchronize()
 
-    # device-resident again, but with the two lanes alternating like the end-to-end loop below (for comparison with `value`,
-    # which is one stream: its quadtree and matcher kernels launch 512 / 64 CTAs and leave SMs idle that a second batch fills)
+    # device-resident again, but with two handles alternating on two streams (for comparison with `value`, which is one stream)
     def step_device_lane(i):
-        slot, L = i % npool, lanes[i % 2]
-        with torch.cuda.stream(L.stream):
-            src = dev[slot * B:(slot + 1) * B]
-            L.ex.run_device(src.data_ptr(), W * H, B, W, H, W, L.d_kps.data_ptr(), L.d_desc.data_ptr(), L.d_cnt.data_ptr(), L.stream.cuda_stream)
-            L.d_match.fill_(-1)
-            L.mt.search_frames_device(L.jobs_dev[slot].data_ptr(), B, L.stream.cuda_stream)
+        L = lanes[i % 2]
+        step_device(L.t, L.sq, L.stream)
+        L.t += 1
 
     for i in range(4):
         step_device_lane(i)
@@ -760,28 +739,26 @@ def main():
     for i in range(K):
         step_device_lane(i)
     t2_1 = []
-    for L in lanes:
+    for L in lanes[:2]:
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(L.stream)
         t2_1.append(ev)
     torch.cuda.synchronize()
     ms_two_lanes = max(t2_0.elapsed_time(ev) for ev in t2_1)
-    # the tracking step (extract + match + PoseOptimization) with two batches in flight: the pose kernel (one CTA per frame, a serial
-    # Levenberg chain on 64 of the 148 SMs) runs under the other lane's extraction
     if track is not None:
         from orbx.optimizer import PoseOptimizer
-        for L in lanes:
+        for L in lanes[:2]:
             L.pz = PoseOptimizer(max_observations=B * cap, max_frames=B, device=local_rank)
             L.d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
             L.d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
             L.d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
-        d_is2_l = torch.from_numpy(ex.GetInverseScaleSigmaSquares()).cuda()
+            L.jobs = L.sq.device_view().jobs
 
         def step_track_lane(i):
             step_device_lane(i)
             L = lanes[i % 2]
-            L.pz.from_matches_device(L.jobs_dev[i % npool].data_ptr(), B, d_is2_l.data_ptr(), NLEVELS, synth.TUM1_K, L.d_pose.data_ptr(),
-                                     L.d_inl.data_ptr(), L.d_outkp.data_ptr(), cap, L.stream.cuda_stream)
+            L.pz.from_matches_device(L.jobs, B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, L.d_pose.data_ptr(), L.d_inl.data_ptr(),
+                                     L.d_outkp.data_ptr(), cap, L.stream.cuda_stream)
 
         for i in range(4):
             step_track_lane(i)
@@ -794,47 +771,42 @@ def main():
         for i in range(KT2):
             step_track_lane(i)
         t3_1 = []
-        for L in lanes:
+        for L in lanes[:2]:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(L.stream)
             t3_1.append(ev)
         torch.cuda.synchronize()
         ms_t2 = max(t3_0.elapsed_time(ev) for ev in t3_1) / KT2
         track["two_lanes"] = {"frames_per_s": B / (ms_t2 * 1e-3), "ms_per_step": ms_t2,
-                              "note": "two batches in flight on two streams (two extractor / matcher / pose handles), like `value_two_lanes`"}
-        for L in lanes:
+                              "note": "two handles in flight on two streams, like `value_two_lanes`"}
+        for L in lanes[:2]:
             L.pz.close()
-    h2d = B * W * H + B * ps_ + B * ds_
-    d2h = B * cap * 28 + B * cap * 32 + 4 * B + 4 * B * cap + 4 * B
+    JOB_BYTES = 208                                     # sizeof(orbx_frame_match_job): the per-step job array and last-frame poses the handle uploads
+    h2d = B * W * H + B * JOB_BYTES + B * 48
+    d2h = B * cap * 28 + B * cap * 32 + 4 * B + 4 * B * cap + 4 * B + 4 * B
 
     def collect(L):
         """wait for the lane's step in flight; its results are then in the lane's pinned host buffers"""
         if not L.busy:
             return 0
-        L.stream.synchronize()
+        L.sq.end()
         L.busy = False
-        return int(L.h_nm.sum())
+        return int(L.out["nmatches"].sum())
 
     def step_host(i):
-        slot, L = i % npool, lanes[i % NLANES]
+        L = lanes[i % NLANES]
         got = collect(L)
-        with torch.cuda.stream(L.stream):
-            L.e_img.copy_(host[slot * B:(slot + 1) * B], non_blocking=True)
-            L.e_pts.copy_(h_last_pts[slot * B:(slot + 1) * B], non_blocking=True)
-            L.e_desc.copy_(h_last_desc[slot * B:(slot + 1) * B], non_blocking=True)
-            L.ex.run_device(L.e_img.data_ptr(), W * H, B, W, H, W, L.d_kps.data_ptr(), L.d_desc.data_ptr(), L.d_cnt.data_ptr(),
-                            L.stream.cuda_stream)
-            L.d_match.fill_(-1)
-            L.mt.search_frames_device(L.jobs[slot].data_ptr(), B, L.stream.cuda_stream)
-            L.h_kps.copy_(L.d_kps, non_blocking=True)
-            L.h_desc.copy_(L.d_desc, non_blocking=True)
-            L.h_cnt.copy_(L.d_cnt, non_blocking=True)
-            L.h_match.copy_(L.d_match, non_blocking=True)
-            L.h_nm.copy_(L.d_nm, non_blocking=True)
+        slot = L.t % npool
+        L.sq.begin(frames_host[slot], poses[slot], L.out)
+        L.t += 1
         L.busy = True
         return got
 
-    for i in range(Wm):
+    frames_host = host.numpy()                          # the pinned pool, as numpy views
+    for L in lanes:
+        L.sq.reset()
+        L.t = 0
+    for i in range(max(Wm, 2) * NLANES):
         step_host(i)
     for L in lanes:
         collect(L)
@@ -842,14 +814,39 @@ def main():
     t0 = time.perf_counter()
     nm_e2e = 0
     for i in range(K):
-        nm_e2e += step_host(Wm + i)
+        nm_e2e += step_host(i)
     for L in lanes:
         nm_e2e += collect(L)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # ---- what the host side of this box can feed: the same bytes per step as plain cudaMemcpyAsync on the same number of streams,
+    # no kernels, all ranks at once (the ceiling any end-to-end figure on this box lives under) ----
+    ceil_in = [torch.empty((B, H, W), dtype=torch.uint8, device="cuda") for _ in range(NLANES)]
+    ceil_out_d = [torch.empty(d2h, dtype=torch.uint8, device="cuda") for _ in range(NLANES)]
+    ceil_out_h = [torch.empty(d2h, dtype=torch.uint8).pin_memory() for _ in range(NLANES)]
+
+    def copy_step(i):
+        L = lanes[i % NLANES]
+        with torch.cuda.stream(L.stream):
+            ceil_in[i % NLANES].copy_(host[i % npool], non_blocking=True)
+            ceil_out_h[i % NLANES].copy_(ceil_out_d[i % NLANES], non_blocking=True)
+
+    for i in range(2 * NLANES):
+        copy_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        if i >= NLANES:
+            lanes[i % NLANES].stream.synchronize()     # like collect(): a lane is reused only after its previous step has landed
+        copy_step(i)
+    torch.cuda.synchronize()
+    ceil_s = time.perf_counter() - t0
+    del ceil_in, ceil_out_d, ceil_out_h
     clk = clocks.stop()
     barrier()
-    hnp = frames_np
+    kp_per_frame = float(np.mean([L.out["counts"].mean() for L in lanes]))
+    matches_per_frame = float(np.mean([L.out["nmatches"].mean() for L in lanes]))
+    hnp = make_frames(64, seed0=100 * rank)          # the CPU legs' frames: 16 scenes x 4 shifts, same generator
 
     # ---- LocalBA (20 keyframes x 3000 points x ~12k edges, 5 + 10 iterations), rank 0 only ----
     lba = None
@@ -906,7 +903,7 @@ def main():
 
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
-    ms_total, e2e_s, ms_two_lanes = shard.max_over_ranks([ms_total, e2e_s, ms_two_lanes], device="cuda")
+    ms_total, e2e_s, ms_two_lanes, ceil_s = shard.max_over_ranks([ms_total, e2e_s, ms_two_lanes, ceil_s], device="cuda")
     counters = shard.gather_counters([B * K, int(round(kp_per_frame * B)), int(round(matches_per_frame * B)), lba_local[0], lba_local[1],
                                       int(lba_local[2] * 1e6)], device="cuda")
     frames_total = sum(c[0] for c in counters)
@@ -924,32 +921,42 @@ def main():
         dom_ms = stage_ms[dom] / max(runs, 1)
         n_launch_dom = 8 if dom == "pyramid" else 1
         achieved = ALGO_BYTES[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        tr = ncu_traffic() if B == 64 and default_workload else None
+        traffic_dom = tr["kernels"].get(dom, {}).get("dram_bytes") if tr else None
+        traffic_step = tr.get("step_dram_bytes") if tr else None
+        traffic_src = tr.get("source") if tr else None
         out = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "C2 extract+match: %dx%d G-rect frames, %d features, 8 levels, th 20/7; each frame matched against its "
-                                   "predecessor with SearchByProjection(Cur, Last, th=7) (%.0f matches/frame)" % (W, H, NFEAT, matches_per_frame),
-                       "batch_per_gpu": B, "parallelism": "frames sharded over %d GPU(s), no collective on the data path" % world,
-                       "l2": "inputs cycle through a %d-frame pool (%.0f MB > 126 MB L2); per-step working set %.0f MB" % (
-                           npool * B, npool * B * W * H / 1e6, B * 3.3),
-                       "keypoints_per_frame": kp_per_frame, "frames_per_rank": [c[0] for c in counters], "match_sweeps_max": max(match_sweeps), "match_sweeps_mean": sum(match_sweeps) / B},
+            "config": workload_config(B),
+            "run": {"batch_per_gpu": B, "parallelism": "%d independent sequences per GPU in lockstep, sharded over %d GPU(s), no collective on the data path" % (B, world),
+                    "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame, "frames_per_rank": [c[0] for c in counters],
+                    "per_step_working_set_mb": B * 3.3, "binary": binary_identity()},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "pinned host frames + last-frame points -> H2D -> orbx_extractor_run_device + orbx_match_projection_frame_device -> D2H of "
-                           "keypoints, descriptors, counts, matches; %d batches in flight on as many streams (copies of one overlap kernels of the others), " % NLANES +
-                           "every step's results are read on the host", "matches_per_step": nm_e2e / K},
+                    "api": "orbx_sequences_step_begin / orbx_sequences_step_end (include/orbx.h): pinned HOST frames + poses in, H2D, "
+                           "extract + unprojection of the last frame + SearchByProjection(Cur, Last) on the device, D2H of keypoints, descriptors, "
+                           "counts and match arrays into HOST buffers; %d handles (%d sequences each) in flight so copies of one overlap kernels of "
+                           "the others; every step's results are read on the host" % (NLANES, B),
+                    "matches_per_step": nm_e2e / K,
+                    "gbs_per_gpu": (h2d + d2h) * K / e2e_s / 1e9,
+                    "host_ceiling": {"frames_per_s": frames_total / ceil_s, "gbs_per_gpu": (B * W * H + d2h) * K / ceil_s / 1e9,
+                                     "e2e_fraction_of_ceiling": ceil_s / e2e_s,
+                                     "what": "the same bytes per step (frames in, results out) as plain cudaMemcpyAsync on the same %d streams, "
+                                             "no kernels, all %d rank(s) copying at once, ranks bound to disjoint host cores" % (NLANES, world)}},
             "value_two_lanes": {"value": frames_total / (ms_two_lanes * 1e-3), "unit": "frames/s",
-                                "note": "device-resident like `value`, but two batches in flight on two streams like `e2e`; `value` itself is "
-                                        "one stream, whose quadtree / matcher kernels (512 / 64 CTAs) leave SMs idle"},
+                                "note": "device-resident like `value`, but two handles in flight on two streams like `e2e`; `value` itself is "
+                                        "one handle on one stream"},
             "gpu_launches": launches_per_step * K,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_B64.get(dom) if B == 64 and default_workload else None, "traffic_source": "profiles/r1_n_full.txt (ncu --set full, bytes per launch at batch 64)",
+                         "traffic": traffic_dom, "traffic_source": traffic_src,
                          "peak_source": peak_src, "launches_per_step": n_launch_dom,
                          "algorithmic_bytes_per_frame": ALGO_BYTES[dom], "ms_per_step": dom_ms,
                          "whole_step": {"algorithmic_bytes_per_frame": FRAME_ALGO_BYTES,
                                         "achieved": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9,
-                                        "frac": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9 / peak}},
+                                        "frac": FRAME_ALGO_BYTES * B / (ms_total / K * 1e-3) / 1e9 / peak,
+                                        "traffic": traffic_step}},
             "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
             "lba": lba,
             "stereo": stereo,
@@ -993,11 +1000,8 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    for L in lanes[1:]:
-        L.mt.close()
-        L.ex.close()
-    mt.close()
-    ex.close()
+    for L in lanes:
+        L.sq.close()
 
 
 if __name__ == "__main__":

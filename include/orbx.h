@@ -316,6 +316,67 @@ orbx_status orbx_stereo_matches_extractors_host(orbx_stereo *h, const orbx_extra
 int orbx_stereo_last_launches(const orbx_stereo *h);
 
 /* =====================================================================================================
+ * Batched many-sequence mode (BASELINE.json configs 2 and 5): n independent sequences advance in lockstep, one new
+ * frame (or rectified pair) per sequence per step, through the per-frame chain of Tracking::TrackWithMotionModel
+ * (Tracking.cc:857-880): ORBextractor::operator(), Frame::ComputeStereoMatches (stereo input), and
+ * ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono), where the last frame's map points are its own keypoints
+ * unprojected with their depth by Frame::UnprojectStereo (Frame.cc:695-709), as Tracking::UpdateLastFrame creates them
+ * (Tracking.cc:941-947; here for every keypoint that has a depth).  The previous frame's keypoints, descriptors and depths stay on
+ * the device between steps; a step takes HOST images and poses in and gives HOST results back.  Sequences are independent, so
+ * handles on one GPU or on several shard them with no exchange.
+ * ===================================================================================================== */
+typedef struct {
+    int32_t nfeatures; float scale_factor; int32_t nlevels, ini_th, min_th;   /* ORBextractor constructor */
+    int32_t width, height, n_sequences;
+    int32_t stereo;              /* 1: every step brings a left and a right image per sequence (order L0 R0 L1 R1 ...) */
+    float fx, fy, cx, cy, bf;    /* Frame::fx ... mbf; mb = bf / fx; the input is undistorted (mnMinX = 0 ... mnMaxX = width) */
+    float th;                    /* SearchByProjection's th */
+    int32_t check_ori, mono;     /* mbCheckOrientation, bMono */
+    float const_depth;           /* stereo == 0 only: the depth (> 0) every keypoint of the last frame is unprojected with (mvDepth of an
+                                    RGB-D style input whose scene is a fronto-parallel plane; bench.py's config C2) */
+    int32_t device;
+} orbx_sequences_config;
+typedef struct {                 /* host pointers, filled when orbx_sequences_step_end returns; capacity = orbx_sequences_capacity() */
+    orbx_keypoint *kps;          /* [n_images][capacity]      mvKeys of every new image (may be NULL) */
+    uint8_t *desc;               /* [n_images][capacity][32]  mDescriptors (may be NULL) */
+    int32_t *counts;             /* [n_images] */
+    int32_t *match;              /* [n_sequences][capacity]   CurrentFrame.mvpMapPoints as indices of last-frame keypoints, -1 = none */
+    int32_t *nmatches;           /* [n_sequences]             the return value of SearchByProjection (0 at a sequence's first step) */
+    float *u_right, *depth;      /* [n_sequences][capacity]   mvuRight / mvDepth of the left image (stereo; may be NULL) */
+} orbx_sequences_outputs;
+typedef struct orbx_sequences orbx_sequences;
+orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_sequences_config *cfg);
+void orbx_sequences_destroy(orbx_sequences *h);
+int orbx_sequences_capacity(const orbx_sequences *h);
+/* forget the last frames: the next step is every sequence's first */
+orbx_status orbx_sequences_reset(orbx_sequences *h);
+/* one step.  images: n_images frames `image_pitch` bytes apart, rows `stride` bytes apart (pinned memory makes the upload
+ * asynchronous); Tcw: [n_sequences][12], rows of [Rcw | tcw] of the new frames (the motion-model prediction that
+ * SearchByProjection projects with).  _begin enqueues upload, kernels and downloads on the handle's stream and returns; _end waits
+ * for them and reports device-side overflow.  One step in flight per handle. */
+orbx_status orbx_sequences_step_begin(orbx_sequences *h, const uint8_t *images, size_t image_pitch, int stride, const float *Tcw,
+                                      const orbx_sequences_outputs *out);
+orbx_status orbx_sequences_step_end(orbx_sequences *h);
+orbx_status orbx_sequences_step_host(orbx_sequences *h, const uint8_t *images, size_t image_pitch, int stride, const float *Tcw,
+                                     const orbx_sequences_outputs *out);   /* _begin + _end */
+/* the same step with the new images already in device memory and the results left there (bench.py's device-resident figure; chaining
+ * into orbx_pose_from_matches_device): only enqueues on `stream` (taken as it is: NULL is the legacy default stream;
+ * orbx_sequences_device_view gives the handle's own).  The job / pose staging of the handle is
+ * rewritten by the next step, so the caller orders steps on one stream.  orbx_sequences_device_view gives the device buffers of the
+ * last step (valid until the step after the next one starts) and the handle's extractor (stage timing, pyramids). */
+orbx_status orbx_sequences_step_device(orbx_sequences *h, const uint8_t *d_images, size_t frame_pitch, int stride, const float *Tcw,
+                                       void *stream);
+typedef struct {
+    orbx_extractor *extractor;
+    const orbx_keypoint *kps; const uint8_t *desc; const int32_t *counts;      /* [n_images][capacity] ... */
+    const int32_t *match, *nmatches; const float *u_right, *depth;             /* [n_sequences][capacity] ... */
+    const orbx_frame_match_job *jobs;                                          /* [n_sequences], the jobs of the last projection search */
+    void *stream;
+} orbx_sequences_device;
+orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_sequences_device *view);
+int orbx_sequences_last_launches(const orbx_sequences *h);
+
+/* =====================================================================================================
  * Optimizer::LocalBundleAdjustment  (reference include/Optimizer.h:45, src/Optimizer.cc:454-779, and the g2o
  * pieces it drives: types_six_dof_expmap.{h,cpp}, base_binary_edge.hpp:55-120, robust_kernel_impl.cpp:78-91,
  * block_solver.hpp:354-486, optimization_algorithm_levenberg.cpp:61-189).

@@ -3,6 +3,8 @@
 
   tools/ncu_summary.py launches <launches.csv>            -> per-kernel count / mean us / share of the step
   tools/ncu_summary.py full <report.ncu-rep or raw.csv>   -> per-launch table of the metrics DESIGN.md cites
+  tools/ncu_summary.py traffic <report.ncu-rep> [batch]   -> JSON: dram bytes per launch (read + write) of every kernel of one step,
+                                                              the file bench.py reads roofline.traffic from (profiles/r2_traffic.json)
 """
 import csv
 import subprocess
@@ -57,5 +59,42 @@ def full(path):
         print("%-14s " % r[ki].split("(")[0][:14] + " ".join("%14s" % r[i][:14] for i, _ in cols))
 
 
+STAGE_OF = {"k_pyr_level0": "pyramid", "k_pyr_resize": "pyramid", "k_pyr_chain": "pyramid", "k_fast": "fast", "k_octree": "quadtree", "k_blur": "blur",
+            "k_describe": "describe", "k_match_frame": "match", "k_unproject_last": "match"}
+
+
+def traffic(path, batch=64):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel (mean over the captured launches of that kernel), and per
+    stage of one step (a stage = its kernels x launches per step; the pyramid's launches are distinct levels, so they are summed over
+    one step's worth = captured launches / captured steps, taken from the count of k_fast launches)."""
+    import json
+    import os
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    H, U = rows[0], rows[1]
+    ki, ri, wi = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
+
+    def to_bytes(v, unit):
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+    per = OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0]
+        per.setdefault(name, []).append(to_bytes(r[ri], U[ri]) + to_bytes(r[wi], U[wi]))
+    steps = max(len(per.get("k_fast", [1])), 1)      # the capture brackets whole steps (bench.py --profile-steps), one k_fast launch per step
+    stages = {}
+    for name, v in per.items():
+        st = STAGE_OF.get(name)
+        if st:
+            d = stages.setdefault(st, {"dram_bytes": 0.0, "launches_per_step": 0.0, "kernels": []})
+            d["dram_bytes"] += sum(v) / steps
+            d["launches_per_step"] += len(v) / steps
+            d["kernels"].append(name)
+    out = {"source": "profiles/%s (ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum per launch at batch %d, "
+                     "summed over a stage's launches of one step)" % (os.path.basename(path).replace(".ncu-rep", "_full.txt"), int(batch)),
+           "batch": int(batch), "captured_steps": steps, "kernels": stages, "step_dram_bytes": sum(d["dram_bytes"] for d in stages.values())}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
