@@ -12,15 +12,29 @@
 #include "orbx_internal.cuh"
 
 #define SEQ_SLOTS 4
+#define SEQ_MAX_SUBS 8
+
+// The sequences of a handle are cut into sub-batches that run the per-step chain on streams of their own and meet again at the end
+// of the step: the under-filled kernels of one sub-batch (the quadtree kernel has one CTA per frame and level, the matcher one small
+// cluster per frame) and every kernel's tail run under the other sub-batches' kernels, a sub-batch's pyramid is still in L2 when its
+// FAST / blur / descriptor kernels read it, and with host buffers the upload of one sub-batch overlaps the kernels of another.
+struct SeqSub {
+    orbx_extractor *ex;
+    orbx_matcher *mt;
+    orbx_stereo *st;
+    cudaStream_t stream;
+    cudaEvent_t done;
+    int q0, nq;                // sequences [q0, q0 + nq)
+};
 
 struct orbx_sequences {
     orbx_sequences_config c;
     int n_img;                 // images per step: n_sequences x (stereo ? 2 : 1), order L0 R0 L1 R1 ...
     int cap;                   // keypoint slots per frame
-    orbx_extractor *ex;
-    orbx_matcher *mt;
-    orbx_stereo *st;
+    int n_sub;
+    SeqSub sub[SEQ_MAX_SUBS];
     cudaStream_t stream;
+    cudaEvent_t ev_fork;
     uint8_t *d_img;            // [n_img][height][width]
     // two generations of extractor outputs: cur = gen, last = gen ^ 1
     orbx_keypoint *d_kps[2];   // [n_img][cap]
@@ -29,64 +43,118 @@ struct orbx_sequences {
     float *d_ur, *d_depth[2];  // [n_seq][cap] mvuRight of the current frame; mvDepth per generation
     int32_t *d_kept;
     orbx_last_point *d_pts;    // [n_seq][cap] last frame's keypoints as map points
-    int32_t *d_match, *d_nm;   // [n_seq][cap], [n_seq]
+    int32_t *d_match, *d_nm;   // [n_seq][cap] followed by [n_seq] (one allocation, one memset)
     float *d_sf;               // mvScaleFactors
-    // pinned staging of the per-step job array and last-frame poses: a ring, so that steps can be enqueued ahead of the device
-    // (a slot is rewritten only after the copies that read it have run)
-    orbx_frame_match_job *d_jobs, *h_jobs_ring;   // [n_seq], [SEQ_SLOTS][n_seq]
+    // per-step staging of the poses, [n_seq][24] floats (Tcw of the new frame, Tcw of the last): mapped pinned memory that the
+    // preparation kernel reads directly; a ring, so that steps can be enqueued ahead of the device (a slot is rewritten only after
+    // the kernel that reads it has run)
+    float *h_pose_ring, *d_pose_ring;
+    orbx_frame_match_job *d_jobs;   // [n_seq], filled by the preparation kernel
     float *h_pose_last;        // [n_seq][12] Tcw of the previous step
-    float *d_Twc, *h_Twc_ring; // [n_seq][12] Rwc | Ow of the last frame, for the unprojection; [SEQ_SLOTS][n_seq][12]
-    cudaEvent_t slot_ev[4];
+    int *h_status;             // pinned, [n_img]
+    cudaEvent_t slot_ev[SEQ_SLOTS];
     int slot;
     int gen, steps, in_flight;
     int last_launches;
 };
 
-// Frame::UnprojectStereo for every keypoint of the last frame of every sequence (Frame.cc:695-709): x = (u-cx)*z*invfx,
-// y = (v-cy)*z*invfy, X = Rwc*(x,y,z) + Ow in float, each product-sum left to right like cv::Mat's CV_32F gemm.  Keypoints
-// without depth get no map point (valid = 0).  One thread per keypoint slot.
-__global__ void k_unproject_last(const orbx_keypoint *__restrict__ kps, const int32_t *__restrict__ cnt, int kp_pitch, int cnt_step,
-                                 const float *__restrict__ depth, int depth_pitch, float const_depth, const float *__restrict__ Twc,
-                                 float cx, float cy, float invfx, float invfy, orbx_last_point *__restrict__ out, int cap) {
+// Everything a step needs before its kernels run, in one launch and without a copy: per sequence (blockIdx.y)
+//   * the last frame's keypoints as map points, Frame::UnprojectStereo (Frame.cc:695-709): x = (u-cx)*z*invfx, y = (v-cy)*z*invfy,
+//     X = Rwc*(x,y,z) + Ow with mRwc = mRcw.t(), mOw = -mRcw.t()*mtcw (Frame::UpdatePoseMatrices, Frame.cc:290-296), in float, each
+//     product-sum left to right like cv::Mat's CV_32F gemm; keypoints without depth get no map point (valid = 0);
+//   * CurrentFrame.mvpMapPoints all NULL (match = -1), nmatches = 0;
+//   * the job of the projection search: the new frame's pose and bForward / bBackward (ORBmatcher.cc:1340-1351: twc = -Rcw.t()*tcw,
+//     tlc = Rlw*twc + tlw).
+// The poses are read straight from the mapped pinned staging slot of the step ([n_seq][24]: Tcw of the new frame, Tcw of the last).
+struct SeqPrep {
+    const orbx_keypoint *kps_last, *kps_cur;  const int32_t *cnt_last, *cnt_cur;  const uint8_t *desc_last, *desc_cur;
+    const float *depth_last, *ur_cur, *sf;
+    orbx_last_point *pts;  int32_t *match, *nm;  orbx_frame_match_job *jobs;
+    int cap, per, nlevels, have_last, mono, check_ori;
+    float const_depth, fx, fy, cx, cy, bf, b, width, height, th;
+};
+__global__ void k_prep_step(const SeqPrep P, const float *__restrict__ poses) {
     const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cap) return;
+    const float *T = poses + 24 * s, *Tl = T + 12;         // rows of [Rcw | tcw] of the new and of the last frame
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.nm[s] = 0;
+        orbx_frame_match_job J;
+        memset(&J, 0, sizeof(J));
+        J.cur.n = 0;
+        J.cur.n_dev = P.cnt_cur + P.per * s;
+        J.cur.keys_un = P.kps_cur + (size_t)P.per * P.cap * s;
+        J.cur.desc = P.desc_cur + (size_t)32 * P.per * P.cap * s;
+        J.cur.u_right = P.ur_cur ? P.ur_cur + (size_t)P.cap * s : nullptr;
+        J.cur.claimed = nullptr;
+        J.cur.min_x = 0.f; J.cur.min_y = 0.f; J.cur.max_x = P.width; J.cur.max_y = P.height;   // undistorted input (Frame.cc:423-437)
+        J.cur.grid_w_inv = __fdiv_rn(64.f, P.width);                                           // Frame.cc:127-128
+        J.cur.grid_h_inv = __fdiv_rn(48.f, P.height);
+        J.cur.fx = P.fx; J.cur.fy = P.fy; J.cur.cx = P.cx; J.cur.cy = P.cy; J.cur.bf = P.bf; J.cur.b = P.b;
+        J.cur.scale_factors = P.sf;
+        J.cur.nlevels = P.nlevels;
+        J.n_last = P.have_last ? P.cnt_last[P.per * s] : 0;
+        J.pts = P.pts + (size_t)P.cap * s;
+        J.last_desc = P.desc_last + (size_t)32 * P.per * P.cap * s;
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) J.Rcw[3 * r + k] = T[4 * r + k]; J.tcw[r] = T[4 * r + 3]; }
+        float twc[3];
+        for (int r = 0; r < 3; r++) twc[r] = -__fadd_rn(__fadd_rn(__fmul_rn(T[r], T[3]), __fmul_rn(T[4 + r], T[7])), __fmul_rn(T[8 + r], T[11]));
+        const float tlc2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tl[8], twc[0]), __fmul_rn(Tl[9], twc[1])), __fmul_rn(Tl[10], twc[2])), Tl[11]);
+        J.forward = tlc2 > P.b && !P.mono;
+        J.backward = -tlc2 > P.b && !P.mono;
+        J.th = P.th;
+        J.check_ori = P.check_ori;
+        J.match = P.match + (size_t)P.cap * s;
+        J.nmatches = P.nm + s;
+        J.max_dist = 0;
+        J.variant = 0;
+        P.jobs[s] = J;
+    }
+    if (i >= P.cap) return;
+    P.match[(size_t)s * P.cap + i] = -1;
     orbx_last_point p;
     p.x = p.y = p.z = p.angle = 0.f;
     p.octave = 0;
     p.valid = p.blocks = 0;
     p.pad[0] = p.pad[1] = 0;
-    if (i < cnt[s * cnt_step]) {
-        const orbx_keypoint k = kps[(size_t)s * kp_pitch + i];
-        const float z = depth ? depth[(size_t)s * depth_pitch + i] : const_depth;
+    if (P.have_last && i < P.cnt_last[P.per * s]) {
+        const orbx_keypoint k = P.kps_last[(size_t)s * P.per * P.cap + i];
+        const float z = P.depth_last ? P.depth_last[(size_t)s * P.cap + i] : P.const_depth;
         if (z > 0) {
-            const float x = __fmul_rn(__fmul_rn(__fsub_rn(k.x, cx), z), invfx);
-            const float y = __fmul_rn(__fmul_rn(__fsub_rn(k.y, cy), z), invfy);
-            const float *T = Twc + 12 * s;
-            p.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[9]);
-            p.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[3], x), __fmul_rn(T[4], y)), __fmul_rn(T[5], z)), T[10]);
-            p.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[6], x), __fmul_rn(T[7], y)), __fmul_rn(T[8], z)), T[11]);
+            const float x = __fmul_rn(__fmul_rn(__fsub_rn(k.x, P.cx), z), __fdiv_rn(1.0f, P.fx));
+            const float y = __fmul_rn(__fmul_rn(__fsub_rn(k.y, P.cy), z), __fdiv_rn(1.0f, P.fy));
+            float X[3];
+            for (int r = 0; r < 3; r++) {
+                const float Ow = -__fadd_rn(__fadd_rn(__fmul_rn(Tl[r], Tl[3]), __fmul_rn(Tl[4 + r], Tl[7])), __fmul_rn(Tl[8 + r], Tl[11]));
+                X[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tl[r], x), __fmul_rn(Tl[4 + r], y)), __fmul_rn(Tl[8 + r], z)), Ow);   // row r of Rwc = column r of Rcw
+            }
+            p.x = X[0]; p.y = X[1]; p.z = X[2];
             p.angle = k.angle;
             p.octave = k.octave;
             p.valid = 1;
             p.blocks = 1;
         }
     }
-    out[(size_t)s * cap + i] = p;
+    P.pts[(size_t)s * P.cap + i] = p;
 }
 
 extern "C" void orbx_sequences_destroy(orbx_sequences *h) {
     if (!h) return;
     cudaSetDevice(h->c.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->ex) orbx_extractor_destroy(h->ex);
-    if (h->mt) orbx_matcher_destroy(h->mt);
-    if (h->st) orbx_stereo_destroy(h->st);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < h->n_sub; k++) {
+        SeqSub &S = h->sub[k];
+        if (S.ex) orbx_extractor_destroy(S.ex);
+        if (S.mt) orbx_matcher_destroy(S.mt);
+        if (S.st) orbx_stereo_destroy(S.st);
+        if (S.stream) cudaStreamDestroy(S.stream);
+        if (S.done) cudaEventDestroy(S.done);
+    }
     cudaFree(h->d_img);
     for (int g = 0; g < 2; g++) { cudaFree(h->d_kps[g]); cudaFree(h->d_desc[g]); cudaFree(h->d_cnt[g]); cudaFree(h->d_depth[g]); }
-    cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_nm); cudaFree(h->d_sf);
-    cudaFree(h->d_jobs); cudaFree(h->d_Twc);
-    cudaFreeHost(h->h_jobs_ring); cudaFreeHost(h->h_Twc_ring);
+    cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_sf); cudaFree(h->d_jobs);
+    cudaFreeHost(h->h_pose_ring); cudaFreeHost(h->h_status);
     for (int i = 0; i < SEQ_SLOTS; i++) if (h->slot_ev[i]) cudaEventDestroy(h->slot_ev[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     free(h->h_pose_last);
     if (h->stream) cudaStreamDestroy(h->stream);
     free(h);
@@ -101,17 +169,32 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     orbx_sequences *h = (orbx_sequences *)calloc(1, sizeof(orbx_sequences));
     if (!h) return ORBX_ERR_NOMEM;
     h->c = *cfg;
-    const int ns = cfg->n_sequences;
-    h->n_img = ns * (cfg->stereo ? 2 : 1);
-    orbx_status st = orbx_extractor_create(&h->ex, cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th, cfg->min_th, cfg->width,
-                                           cfg->height, h->n_img, cfg->device);
-    if (st) { orbx_sequences_destroy(h); return st; }
-    h->cap = orbx_extractor_capacity(h->ex);
-    if ((st = orbx_matcher_create(&h->mt, h->cap, h->cap, ns, cfg->device))) { orbx_sequences_destroy(h); return st; }
-    if (cfg->stereo && (st = orbx_stereo_create(&h->st, h->cap, ns, cfg->device))) { orbx_sequences_destroy(h); return st; }
+    const int ns = cfg->n_sequences, per = cfg->stereo ? 2 : 1;
+    h->n_img = ns * per;
+    // one stream unless asked otherwise (config n_sub > 0 or the environment variable ORBX_SEQ_SUBS): measured on the B200 at 64 VGA
+    // sequences, the fork / join of every step costs more than the overlap returns (91.8 k frames/s with 1, 89.8 k with 2, 90.3 k
+    // with 4, 85.9 k with 8 sub-batches; profiles/r2_f_subbatch_sweep.txt)
+    int n_sub = cfg->n_sub > 0 ? cfg->n_sub : (getenv("ORBX_SEQ_SUBS") ? atoi(getenv("ORBX_SEQ_SUBS")) : 1);
+    n_sub = n_sub < 1 ? 1 : (n_sub > SEQ_MAX_SUBS ? SEQ_MAX_SUBS : n_sub);
+    if (n_sub > ns) n_sub = ns;
+    h->n_sub = n_sub;
+    orbx_status st = ORBX_OK;
 #define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { orbx_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); orbx_sequences_destroy(h); return ORBX_ERR_CUDA; } } while (0)
     TRY(cudaSetDevice(cfg->device));
+    for (int k = 0; k < n_sub; k++) {
+        SeqSub &S = h->sub[k];
+        S.q0 = (int)((long long)ns * k / n_sub);
+        S.nq = (int)((long long)ns * (k + 1) / n_sub) - S.q0;
+        if ((st = orbx_extractor_create(&S.ex, cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th, cfg->min_th, cfg->width, cfg->height,
+                                        S.nq * per, cfg->device))) { orbx_sequences_destroy(h); return st; }
+        h->cap = orbx_extractor_capacity(S.ex);
+        if ((st = orbx_matcher_create(&S.mt, h->cap, h->cap, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
+        if (cfg->stereo && (st = orbx_stereo_create(&S.st, h->cap, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
+        TRY(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    }
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     const size_t cap = (size_t)h->cap;
     TRY(cudaMalloc(&h->d_img, (size_t)h->n_img * cfg->width * cfg->height));
     for (int g = 0; g < 2; g++) {
@@ -124,18 +207,18 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     TRY(cudaMalloc(&h->d_ur, sizeof(float) * cap * ns));
     TRY(cudaMalloc(&h->d_kept, sizeof(int32_t) * ns));
     TRY(cudaMalloc(&h->d_pts, sizeof(orbx_last_point) * cap * ns));
-    TRY(cudaMalloc(&h->d_match, sizeof(int32_t) * cap * ns));
-    TRY(cudaMalloc(&h->d_nm, sizeof(int32_t) * ns));
+    TRY(cudaMalloc(&h->d_match, sizeof(int32_t) * (cap + 1) * ns));
+    h->d_nm = h->d_match + cap * ns;
     TRY(cudaMalloc(&h->d_sf, sizeof(float) * ORBX_MAX_LEVELS));
     TRY(cudaMalloc(&h->d_jobs, sizeof(orbx_frame_match_job) * ns));
-    TRY(cudaMalloc(&h->d_Twc, sizeof(float) * 12 * ns));
-    TRY(cudaMallocHost(&h->h_jobs_ring, sizeof(orbx_frame_match_job) * ns * SEQ_SLOTS));
-    TRY(cudaMallocHost(&h->h_Twc_ring, sizeof(float) * 12 * ns * SEQ_SLOTS));
+    TRY(cudaHostAlloc(&h->h_pose_ring, sizeof(float) * 24 * ns * SEQ_SLOTS, cudaHostAllocMapped));
+    TRY(cudaHostGetDevicePointer(&h->d_pose_ring, h->h_pose_ring, 0));
+    TRY(cudaMallocHost(&h->h_status, sizeof(int) * h->n_img));
     for (int i = 0; i < SEQ_SLOTS; i++) TRY(cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming));
     h->h_pose_last = (float *)calloc((size_t)12 * ns, sizeof(float));
     if (!h->h_pose_last) { orbx_sequences_destroy(h); return ORBX_ERR_NOMEM; }
     float sf[ORBX_MAX_LEVELS] = {0};
-    if ((st = orbx_extractor_tables(h->ex, sf, nullptr, nullptr, nullptr, nullptr))) { orbx_sequences_destroy(h); return st; }
+    if ((st = orbx_extractor_tables(h->sub[0].ex, sf, nullptr, nullptr, nullptr, nullptr))) { orbx_sequences_destroy(h); return st; }
     TRY(cudaMemcpy(h->d_sf, sf, sizeof(sf), cudaMemcpyHostToDevice));
 #undef TRY
     *out = h;
@@ -148,95 +231,99 @@ extern "C" int orbx_sequences_last_launches(const orbx_sequences *h) { return h 
 extern "C" orbx_status orbx_sequences_reset(orbx_sequences *h) {
     if (!h) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
-    ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(cudaDeviceSynchronize());
     h->steps = 0;
+    h->in_flight = 0;
     return ORBX_OK;
 }
 
-// the device part of one step on stream s: unprojection of the last frame, extraction, stereo association, projection search
-static orbx_status step_core(orbx_sequences *h, const uint8_t *d_images, size_t frame_pitch, int stride, const float *Tcw, cudaStream_t s) {
+// One step on stream s.  images: device pointer (host_images = false) or host pointer (true: every sub-batch uploads its own images
+// on its own stream); o: host buffers every sub-batch downloads its results into (NULL: results stay on the device).
+static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_images, size_t image_pitch, int stride, const float *Tcw,
+                            const orbx_sequences_outputs *o, cudaStream_t s) {
     const orbx_sequences_config &c = h->c;
     const int ns = c.n_sequences, per = c.stereo ? 2 : 1, cap = h->cap;
     const int g = h->gen, gl = g ^ 1;
+    const float b = c.bf / c.fx;
     h->last_launches = 0;
     const int slot = h->slot;
     h->slot = (slot + 1) % SEQ_SLOTS;
-    ORBX_CUDA(cudaEventSynchronize(h->slot_ev[slot]));          // the copies of the step that used this staging slot have run
-    orbx_frame_match_job *h_jobs = h->h_jobs_ring + (size_t)slot * ns;
-    float *h_Twc = h->h_Twc_ring + (size_t)12 * ns * slot;
-    // ---- the last frame's map points: Frame::UnprojectStereo with the last frame's pose (Frame.cc:290-296, 695-709) ----
+    ORBX_CUDA(cudaEventSynchronize(h->slot_ev[slot]));          // the kernel of the step that used this staging slot has run
+    float *h_pose = h->h_pose_ring + (size_t)24 * ns * slot;
+    for (int q = 0; q < ns; q++) {
+        memcpy(h_pose + 24 * q, Tcw + 12 * q, sizeof(float) * 12);
+        memcpy(h_pose + 24 * q + 12, h->h_pose_last + 12 * q, sizeof(float) * 12);
+    }
     const bool have_last = h->steps > 0;
-    if (have_last) {
-        for (int q = 0; q < ns; q++) {
-            const float *T = h->h_pose_last + 12 * q;      // rows of [Rcw | tcw]
-            float *W = h_Twc + 12 * q;                  // Rwc (row-major 3x3), then Ow
-            for (int r = 0; r < 3; r++)
-                for (int k = 0; k < 3; k++) W[3 * r + k] = T[4 * k + r];                          // mRwc = mRcw.t()
-            for (int r = 0; r < 3; r++)                                                            // mOw = -mRcw.t()*mtcw
-                W[9 + r] = -((T[r] * T[3] + T[4 + r] * T[7]) + T[8 + r] * T[11]);
-        }
-        ORBX_CUDA(cudaMemcpyAsync(h->d_Twc, h_Twc, sizeof(float) * 12 * ns, cudaMemcpyHostToDevice, s));
+    SeqPrep P;
+    P.kps_last = h->d_kps[gl]; P.kps_cur = h->d_kps[g]; P.cnt_last = h->d_cnt[gl]; P.cnt_cur = h->d_cnt[g];
+    P.desc_last = h->d_desc[gl]; P.desc_cur = h->d_desc[g];
+    P.depth_last = c.stereo ? h->d_depth[gl] : nullptr; P.ur_cur = c.stereo ? h->d_ur : nullptr; P.sf = h->d_sf;
+    P.pts = h->d_pts; P.match = h->d_match; P.nm = h->d_nm; P.jobs = h->d_jobs;
+    P.cap = cap; P.per = per; P.nlevels = c.nlevels; P.have_last = have_last; P.mono = c.mono; P.check_ori = c.check_ori;
+    P.const_depth = c.const_depth; P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.bf = c.bf; P.b = b;
+    P.width = (float)c.width; P.height = (float)c.height; P.th = c.th;
+    {
         dim3 grid((cap + 255) / 256, ns);
-        k_unproject_last<<<grid, 256, 0, s>>>(h->d_kps[gl], h->d_cnt[gl], per * cap, per, c.stereo ? h->d_depth[gl] : nullptr, cap,
-                                              c.const_depth, h->d_Twc, c.cx, c.cy, 1.0f / c.fx, 1.0f / c.fy, h->d_pts, cap);
+        k_prep_step<<<grid, 256, 0, s>>>(P, h->d_pose_ring + (size_t)24 * ns * slot);
         ORBX_CUDA(cudaGetLastError());
         h->last_launches++;
     }
-    // ---- ORBextractor::operator() on every new image ------------------------------------------------------------------------
-    orbx_status st = orbx_extractor_run_device(h->ex, d_images, frame_pitch, h->n_img, c.width, c.height, stride,
-                                               h->d_kps[g], h->d_desc[g], h->d_cnt[g], s);
-    if (st) return st;
-    h->last_launches += orbx_extractor_last_launches(h->ex);
-    // ---- Frame::ComputeStereoMatches ------------------------------------------------------------------------------------------
-    const float b = c.bf / c.fx;
-    if (c.stereo) {
-        orbx_stereo_side L = {h->d_kps[g], h->d_desc[g], h->d_cnt[g], 2 * cap, 2, h->ex, 0, 2, cap};
-        orbx_stereo_side R = {h->d_kps[g] + cap, h->d_desc[g] + (size_t)32 * cap, h->d_cnt[g] + 1, 2 * cap, 2, h->ex, 1, 2, cap};
-        if ((st = orbx_stereo_matches_device(h->st, &L, &R, ns, c.bf, b, h->d_ur, h->d_depth[g], cap, h->d_kept, s))) return st;
-        h->last_launches += orbx_stereo_last_launches(h->st);
-    }
-    // ---- SearchByProjection(CurrentFrame, LastFrame, th, bMono) -------------------------------------------------------------
-    ORBX_CUDA(cudaMemsetAsync(h->d_match, 0xff, sizeof(int32_t) * cap * ns, s));     // mvpMapPoints all NULL
-    ORBX_CUDA(cudaMemsetAsync(h->d_nm, 0, sizeof(int32_t) * ns, s));
-    if (have_last) {
-        for (int q = 0; q < ns; q++) {
-            orbx_frame_match_job &J = h_jobs[q];
-            memset(&J, 0, sizeof(J));
-            J.cur.n = 0;
-            J.cur.n_dev = h->d_cnt[g] + per * q;
-            J.cur.keys_un = h->d_kps[g] + (size_t)per * cap * q;
-            J.cur.desc = h->d_desc[g] + (size_t)32 * per * cap * q;
-            J.cur.u_right = c.stereo ? h->d_ur + (size_t)cap * q : nullptr;
-            J.cur.claimed = nullptr;
-            J.cur.min_x = 0.f; J.cur.min_y = 0.f; J.cur.max_x = (float)c.width; J.cur.max_y = (float)c.height;   // undistorted input (Frame.cc:423-437)
-            J.cur.grid_w_inv = 64.f / (J.cur.max_x - J.cur.min_x);                                                // Frame.cc:127-128
-            J.cur.grid_h_inv = 48.f / (J.cur.max_y - J.cur.min_y);
-            J.cur.fx = c.fx; J.cur.fy = c.fy; J.cur.cx = c.cx; J.cur.cy = c.cy; J.cur.bf = c.bf; J.cur.b = b;
-            J.cur.scale_factors = h->d_sf;
-            J.cur.nlevels = c.nlevels;
-            J.n_last = cap;                                 // slots past the last frame's count are written invalid by k_unproject_last
-            J.pts = h->d_pts + (size_t)cap * q;
-            J.last_desc = h->d_desc[gl] + (size_t)32 * per * cap * q;
-            const float *T = Tcw + 12 * q, *Tl = h->h_pose_last + 12 * q;
-            for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) J.Rcw[3 * r + k] = T[4 * r + k]; J.tcw[r] = T[4 * r + 3]; }
-            // bForward / bBackward (ORBmatcher.cc:1340-1351): twc = -Rcw.t()*tcw; tlc = Rlw*twc + tlw, in float left to right
-            float twc[3], tlc2;
-            for (int r = 0; r < 3; r++) twc[r] = -((T[r] * T[3] + T[4 + r] * T[7]) + T[8 + r] * T[11]);
-            tlc2 = ((Tl[8] * twc[0] + Tl[9] * twc[1]) + Tl[10] * twc[2]) + Tl[11];
-            J.forward = tlc2 > b && !c.mono;
-            J.backward = -tlc2 > b && !c.mono;
-            J.th = c.th;
-            J.check_ori = c.check_ori;
-            J.match = h->d_match + (size_t)cap * q;
-            J.nmatches = h->d_nm + q;
-            J.max_dist = 0;
-            J.variant = 0;
-        }
-        ORBX_CUDA(cudaMemcpyAsync(h->d_jobs, h_jobs, sizeof(orbx_frame_match_job) * ns, cudaMemcpyHostToDevice, s));
-        if ((st = orbx_match_projection_frame_device(h->mt, h->d_jobs, ns, s))) return st;
-        h->last_launches += orbx_matcher_last_launches(h->mt);
-    }
     ORBX_CUDA(cudaEventRecord(h->slot_ev[slot], s));
+    orbx_frame_match_job *d_jobs = h->d_jobs;
+    const bool fork = h->n_sub > 1;
+    if (fork) ORBX_CUDA(cudaEventRecord(h->ev_fork, s));
+    const size_t img_bytes = (size_t)c.width * c.height;
+    for (int k = 0; k < h->n_sub; k++) {
+        SeqSub &S = h->sub[k];
+        cudaStream_t ss = fork ? S.stream : s;
+        if (fork) ORBX_CUDA(cudaStreamWaitEvent(ss, h->ev_fork, 0));
+        const int i0 = per * S.q0, ni = per * S.nq;
+        const uint8_t *d_in = images + (size_t)i0 * image_pitch;
+        size_t in_pitch = image_pitch;
+        int in_stride = stride;
+        if (host_images) {                                   // this sub-batch's images: rows `stride` apart on the host, packed on the device
+            uint8_t *dst = h->d_img + img_bytes * i0;
+            if (image_pitch == (size_t)stride * c.height)
+                ORBX_CUDA(cudaMemcpy2DAsync(dst, c.width, d_in, stride, c.width, (size_t)c.height * ni, cudaMemcpyHostToDevice, ss));
+            else
+                for (int i = 0; i < ni; i++)
+                    ORBX_CUDA(cudaMemcpy2DAsync(dst + img_bytes * i, c.width, d_in + i * image_pitch, stride, c.width, c.height, cudaMemcpyHostToDevice, ss));
+            d_in = dst; in_pitch = img_bytes; in_stride = c.width;
+        }
+        // ORBextractor::operator() on every new image of the sub-batch
+        orbx_status st = orbx_extractor_run_device(S.ex, d_in, in_pitch, ni, c.width, c.height, in_stride, h->d_kps[g] + (size_t)cap * i0,
+                                                   h->d_desc[g] + (size_t)32 * cap * i0, h->d_cnt[g] + i0, ss);
+        if (st) return st;
+        h->last_launches += orbx_extractor_last_launches(S.ex);
+        // Frame::ComputeStereoMatches
+        if (c.stereo) {
+            orbx_stereo_side L = {h->d_kps[g] + (size_t)cap * i0, h->d_desc[g] + (size_t)32 * cap * i0, h->d_cnt[g] + i0, 2 * cap, 2, S.ex, 0, 2, cap};
+            orbx_stereo_side R = {L.keys + cap, L.desc + (size_t)32 * cap, L.counts + 1, 2 * cap, 2, S.ex, 1, 2, cap};
+            if ((st = orbx_stereo_matches_device(S.st, &L, &R, S.nq, c.bf, b, h->d_ur + (size_t)cap * S.q0, h->d_depth[g] + (size_t)cap * S.q0, cap,
+                                                 h->d_kept + S.q0, ss))) return st;
+            h->last_launches += orbx_stereo_last_launches(S.st);
+        }
+        // SearchByProjection(CurrentFrame, LastFrame, th, bMono)
+        if (have_last) {
+            if ((st = orbx_match_projection_frame_device(S.mt, d_jobs + S.q0, S.nq, ss))) return st;
+            h->last_launches += orbx_matcher_last_launches(S.mt);
+        }
+        if (o) {                                             // the sub-batch's results back to the caller's buffers
+            ORBX_CUDA(cudaMemcpyAsync(o->counts + i0, h->d_cnt[g] + i0, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, ss));
+            if (o->kps) ORBX_CUDA(cudaMemcpyAsync(o->kps + (size_t)cap * i0, h->d_kps[g] + (size_t)cap * i0, sizeof(orbx_keypoint) * cap * ni, cudaMemcpyDeviceToHost, ss));
+            if (o->desc) ORBX_CUDA(cudaMemcpyAsync(o->desc + (size_t)32 * cap * i0, h->d_desc[g] + (size_t)32 * cap * i0, (size_t)32 * cap * ni, cudaMemcpyDeviceToHost, ss));
+            ORBX_CUDA(cudaMemcpyAsync(o->match + (size_t)cap * S.q0, h->d_match + (size_t)cap * S.q0, sizeof(int32_t) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
+            ORBX_CUDA(cudaMemcpyAsync(o->nmatches + S.q0, h->d_nm + S.q0, sizeof(int32_t) * S.nq, cudaMemcpyDeviceToHost, ss));
+            if (c.stereo && o->u_right) ORBX_CUDA(cudaMemcpyAsync(o->u_right + (size_t)cap * S.q0, h->d_ur + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
+            if (c.stereo && o->depth) ORBX_CUDA(cudaMemcpyAsync(o->depth + (size_t)cap * S.q0, h->d_depth[g] + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
+            ORBX_CUDA(cudaMemcpyAsync(h->h_status + i0, S.ex->d_status, sizeof(int) * ni, cudaMemcpyDeviceToHost, ss));
+        }
+        if (fork) {
+            ORBX_CUDA(cudaEventRecord(S.done, ss));
+            ORBX_CUDA(cudaStreamWaitEvent(s, S.done, 0));
+        }
+    }
     memcpy(h->h_pose_last, Tcw, sizeof(float) * 12 * ns);
     h->gen ^= 1;
     h->steps++;
@@ -246,31 +333,11 @@ static orbx_status step_core(orbx_sequences *h, const uint8_t *d_images, size_t 
 extern "C" orbx_status orbx_sequences_step_begin(orbx_sequences *h, const uint8_t *images, size_t image_pitch, int stride,
                                                  const float *Tcw, const orbx_sequences_outputs *o) {
     if (!h || !images || !Tcw || !o || !o->counts || !o->nmatches || !o->match) return ORBX_ERR_INVALID;
-    const orbx_sequences_config &c = h->c;
-    if (stride < c.width) return ORBX_ERR_INVALID;
-    ORBX_CUDA(cudaSetDevice(c.device));
-    cudaStream_t s = h->stream;
-    const int ns = c.n_sequences, cap = h->cap;
-    if (h->in_flight) ORBX_CUDA(cudaStreamSynchronize(s));     // one step in flight per handle: the pinned job / pose staging is reused
-    // ---- upload the new images (one 2-D copy: rows `stride` apart on the host, packed on the device) -------------------
-    if (image_pitch == (size_t)stride * c.height)
-        ORBX_CUDA(cudaMemcpy2DAsync(h->d_img, c.width, images, stride, c.width, (size_t)c.height * h->n_img, cudaMemcpyHostToDevice, s));
-    else
-        for (int i = 0; i < h->n_img; i++)
-            ORBX_CUDA(cudaMemcpy2DAsync(h->d_img + (size_t)i * c.width * c.height, c.width, images + i * image_pitch, stride, c.width,
-                                        c.height, cudaMemcpyHostToDevice, s));
-    const orbx_status st = step_core(h, h->d_img, (size_t)c.width * c.height, c.width, Tcw, s);
+    if (stride < h->c.width) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->c.device));
+    if (h->in_flight) ORBX_CUDA(cudaStreamSynchronize(h->stream));     // one step in flight per handle
+    const orbx_status st = run_step(h, images, true, image_pitch, stride, Tcw, o, h->stream);
     if (st) return st;
-    const int g = h->gen ^ 1;                                   // the generation step_core just filled
-    // ---- the step's results back to the caller's buffers -------------------------------------------------------------------
-    ORBX_CUDA(cudaMemcpyAsync(o->counts, h->d_cnt[g], sizeof(int32_t) * h->n_img, cudaMemcpyDeviceToHost, s));
-    if (o->kps) ORBX_CUDA(cudaMemcpyAsync(o->kps, h->d_kps[g], sizeof(orbx_keypoint) * (size_t)cap * h->n_img, cudaMemcpyDeviceToHost, s));
-    if (o->desc) ORBX_CUDA(cudaMemcpyAsync(o->desc, h->d_desc[g], (size_t)32 * cap * h->n_img, cudaMemcpyDeviceToHost, s));
-    ORBX_CUDA(cudaMemcpyAsync(o->match, h->d_match, sizeof(int32_t) * (size_t)cap * ns, cudaMemcpyDeviceToHost, s));
-    ORBX_CUDA(cudaMemcpyAsync(o->nmatches, h->d_nm, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, s));
-    if (c.stereo && o->u_right) ORBX_CUDA(cudaMemcpyAsync(o->u_right, h->d_ur, sizeof(float) * (size_t)cap * ns, cudaMemcpyDeviceToHost, s));
-    if (c.stereo && o->depth) ORBX_CUDA(cudaMemcpyAsync(o->depth, h->d_depth[g], sizeof(float) * (size_t)cap * ns, cudaMemcpyDeviceToHost, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->ex->h_status, h->ex->d_status, sizeof(int) * h->n_img, cudaMemcpyDeviceToHost, s));
     h->in_flight = 1;
     return ORBX_OK;
 }
@@ -279,13 +346,13 @@ extern "C" orbx_status orbx_sequences_step_device(orbx_sequences *h, const uint8
                                                   const float *Tcw, void *stream) {
     if (!h || !d_images || !Tcw || stride < h->c.width) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
-    return step_core(h, d_images, frame_pitch, stride, Tcw, (cudaStream_t)stream);
+    return run_step(h, d_images, false, frame_pitch, stride, Tcw, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_sequences_device *v) {
     if (!h || !v) return ORBX_ERR_INVALID;
     const int g = h->gen ^ 1;                                   // the generation the last step filled
-    v->extractor = h->ex;
+    v->extractor = h->sub[0].ex;
     v->kps = h->d_kps[g]; v->desc = h->d_desc[g]; v->counts = h->d_cnt[g];
     v->match = h->d_match; v->nmatches = h->d_nm; v->u_right = h->d_ur; v->depth = h->d_depth[g];
     v->jobs = h->d_jobs;
@@ -300,8 +367,8 @@ extern "C" orbx_status orbx_sequences_step_end(orbx_sequences *h) {
     if (h->in_flight) {
         h->in_flight = 0;
         for (int i = 0; i < h->n_img; i++)
-            if (h->ex->h_status[i]) {
-                orbx_set_error("image %d: device status 0x%x (1 = candidate list overflow, 2 = quadtree depth, 4 = node overflow)", i, h->ex->h_status[i]);
+            if (h->h_status[i]) {
+                orbx_set_error("image %d: device status 0x%x (1 = candidate list overflow, 2 = quadtree depth, 4 = node overflow)", i, h->h_status[i]);
                 return ORBX_ERR_CAPACITY;
             }
     }

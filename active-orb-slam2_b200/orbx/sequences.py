@@ -15,7 +15,8 @@ class SequencesConfig(C.Structure):
     _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32), ("ini_th", C.c_int32), ("min_th", C.c_int32),
                 ("width", C.c_int32), ("height", C.c_int32), ("n_sequences", C.c_int32), ("stereo", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
-                ("th", C.c_float), ("check_ori", C.c_int32), ("mono", C.c_int32), ("const_depth", C.c_float), ("device", C.c_int32)]
+                ("th", C.c_float), ("check_ori", C.c_int32), ("mono", C.c_int32), ("const_depth", C.c_float), ("device", C.c_int32),
+                ("n_sub", C.c_int32)]
 
 
 class SequencesOutputs(C.Structure):
@@ -35,13 +36,13 @@ class Sequences:
     outputs() (numpy, or pinned torch tensors viewed through .numpy()) and reused every step."""
 
     def __init__(self, n_sequences, width, height, K, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, stereo=False,
-                 th=7.0, check_ori=True, mono=False, const_depth=0.0, device=0):
+                 th=7.0, check_ori=True, mono=False, const_depth=0.0, device=0, n_sub=0):
         self._L = lib()
         c = SequencesConfig()
         c.nfeatures, c.scale_factor, c.nlevels, c.ini_th, c.min_th = nfeatures, scale_factor, nlevels, ini_th, min_th
         c.width, c.height, c.n_sequences, c.stereo = width, height, n_sequences, int(stereo)
         c.fx, c.fy, c.cx, c.cy, c.bf = (float(v) for v in K[:5])
-        c.th, c.check_ori, c.mono, c.const_depth, c.device = th, int(check_ori), int(mono), const_depth, device
+        c.th, c.check_ori, c.mono, c.const_depth, c.device, c.n_sub = th, int(check_ori), int(mono), const_depth, device, n_sub
         self.config = c
         self._h = C.c_void_p()
         check(self._L.orbx_sequences_create(C.byref(self._h), C.byref(c)))

@@ -335,6 +335,7 @@ typedef struct {
     float const_depth;           /* stereo == 0 only: the depth (> 0) every keypoint of the last frame is unprojected with (mvDepth of an
                                     RGB-D style input whose scene is a fronto-parallel plane; bench.py's config C2) */
     int32_t device;
+    int32_t n_sub;               /* sub-batches that run the chain on streams of their own inside a step (0 or 1 = one stream, the default: measured faster at 64 VGA sequences) */
 } orbx_sequences_config;
 typedef struct {                 /* host pointers, filled when orbx_sequences_step_end returns; capacity = orbx_sequences_capacity() */
     orbx_keypoint *kps;          /* [n_images][capacity]      mvKeys of every new image (may be NULL) */
@@ -363,7 +364,8 @@ orbx_status orbx_sequences_step_host(orbx_sequences *h, const uint8_t *images, s
  * into orbx_pose_from_matches_device): only enqueues on `stream` (taken as it is: NULL is the legacy default stream;
  * orbx_sequences_device_view gives the handle's own).  The job / pose staging of the handle is
  * rewritten by the next step, so the caller orders steps on one stream.  orbx_sequences_device_view gives the device buffers of the
- * last step (valid until the step after the next one starts) and the handle's extractor (stage timing, pyramids). */
+ * last step (valid until the step after the next one starts) and the extractor of the
+ * first sub-batch (stage timing when the handle was created with n_sub = 1; pyramids of its images). */
 orbx_status orbx_sequences_step_device(orbx_sequences *h, const uint8_t *d_images, size_t frame_pitch, int stride, const float *Tcw,
                                        void *stream);
 typedef struct {

@@ -52,13 +52,13 @@ def pose_of(tx, ty, yaw):
     return T.astype(f32)
 
 
-@pytest.mark.parametrize("stereo", [False, True])
-def test_steps_match_the_oracle_chain(stereo):
+@pytest.mark.parametrize("stereo,n_sub", [(False, 1), (True, 1), (False, 2), (True, 3)])
+def test_steps_match_the_oracle_chain(stereo, n_sub):
     from oracle import oracle_py as O
     w, h, ns, steps = 640, 480, 3, 4
     K = synth.TUM1_K
     worlds = [synth.stereo_world(s) for s in range(2)]
-    seq = Sequences(ns, w, h, K, stereo=stereo, th=7.0, mono=False, const_depth=0.0 if stereo else 4.0)
+    seq = Sequences(ns, w, h, K, stereo=stereo, th=7.0, mono=False, const_depth=0.0 if stereo else 4.0, n_sub=n_sub)
     cap = seq.capacity
     oex = [O.Extractor(1000, 1.2, 8, 20, 7) for _ in range(2)]
     sf = synth.scale_factors(8)

@@ -3,7 +3,7 @@
 
   tools/ncu_summary.py launches <launches.csv>            -> per-kernel count / mean us / share of the step
   tools/ncu_summary.py full <report.ncu-rep or raw.csv>   -> per-launch table of the metrics DESIGN.md cites
-  tools/ncu_summary.py traffic <report.ncu-rep> [batch]   -> JSON: dram bytes per launch (read + write) of every kernel of one step,
+  tools/ncu_summary.py traffic <report.ncu-rep> [batch] [steps] -> JSON: dram bytes per launch (read + write) of every kernel of one step,
                                                               the file bench.py reads roofline.traffic from (profiles/r2_traffic.json)
 """
 import csv
@@ -63,7 +63,7 @@ STAGE_OF = {"k_pyr_level0": "pyramid", "k_pyr_resize": "pyramid", "k_pyr_chain":
             "k_describe": "describe", "k_match_frame": "match", "k_unproject_last": "match"}
 
 
-def traffic(path, batch=64):
+def traffic(path, batch=64, steps=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel (mean over the captured launches of that kernel), and per
     stage of one step (a stage = its kernels x launches per step; the pyramid's launches are distinct levels, so they are summed over
     one step's worth = captured launches / captured steps, taken from the count of k_fast launches)."""
@@ -81,7 +81,7 @@ def traffic(path, batch=64):
     for r in rows[2:]:
         name = r[ki].split("(")[0]
         per.setdefault(name, []).append(to_bytes(r[ri], U[ri]) + to_bytes(r[wi], U[wi]))
-    steps = max(len(per.get("k_fast", [1])), 1)      # the capture brackets whole steps (bench.py --profile-steps), one k_fast launch per step
+    steps = int(steps) if steps else max(len(per.get("k_fast", [1])), 1)      # the capture brackets whole steps (bench.py --profile-steps N)
     stages = {}
     for name, v in per.items():
         st = STAGE_OF.get(name)
