@@ -52,7 +52,7 @@ struct orbx_sequences {
     orbx_frame_match_job *d_jobs;   // [n_seq], filled by the preparation kernel
     float *h_pose_last;        // [n_seq][12] Tcw of the previous step
     int *h_status;             // pinned, [n_img]
-    cudaEvent_t slot_ev[SEQ_SLOTS];
+    cudaEvent_t slot_ev[SEQ_SLOTS][SEQ_MAX_SUBS];
     int slot;
     int gen, steps, in_flight;
     int last_launches;
@@ -73,8 +73,8 @@ struct SeqPrep {
     int cap, per, nlevels, have_last, mono, check_ori;
     float const_depth, fx, fy, cx, cy, bf, b, width, height, th;
 };
-__global__ void k_prep_step(const SeqPrep P, const float *__restrict__ poses) {
-    const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_prep_step(const SeqPrep P, const float *__restrict__ poses, int q0) {
+    const int s = q0 + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     const float *T = poses + 24 * s, *Tl = T + 12;         // rows of [Rcw | tcw] of the new and of the last frame
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.nm[s] = 0;
@@ -153,7 +153,7 @@ extern "C" void orbx_sequences_destroy(orbx_sequences *h) {
     for (int g = 0; g < 2; g++) { cudaFree(h->d_kps[g]); cudaFree(h->d_desc[g]); cudaFree(h->d_cnt[g]); cudaFree(h->d_depth[g]); }
     cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_sf); cudaFree(h->d_jobs);
     cudaFreeHost(h->h_pose_ring); cudaFreeHost(h->h_status);
-    for (int i = 0; i < SEQ_SLOTS; i++) if (h->slot_ev[i]) cudaEventDestroy(h->slot_ev[i]);
+    for (int i = 0; i < SEQ_SLOTS; i++) for (int k = 0; k < SEQ_MAX_SUBS; k++) if (h->slot_ev[i][k]) cudaEventDestroy(h->slot_ev[i][k]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     free(h->h_pose_last);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -171,9 +171,9 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     h->c = *cfg;
     const int ns = cfg->n_sequences, per = cfg->stereo ? 2 : 1;
     h->n_img = ns * per;
-    // one stream unless asked otherwise (config n_sub > 0 or the environment variable ORBX_SEQ_SUBS): measured on the B200 at 64 VGA
-    // sequences, the fork / join of every step costs more than the overlap returns (91.8 k frames/s with 1, 89.8 k with 2, 90.3 k
-    // with 4, 85.9 k with 8 sub-batches; profiles/r2_f_subbatch_sweep.txt)
+    // one stream unless asked otherwise (config n_sub > 0 or the environment variable ORBX_SEQ_SUBS).  A first version joined the
+    // sub-batches at the end of every step: on the B200 at 64 VGA sequences that cost more than the overlap returned (91.8 k frames/s
+    // with 1, 89.8 k with 2, 90.3 k with 4, 85.9 k with 8 sub-batches; profiles/r2_f_subbatch_sweep.txt), so they now run unjoined
     int n_sub = cfg->n_sub > 0 ? cfg->n_sub : (getenv("ORBX_SEQ_SUBS") ? atoi(getenv("ORBX_SEQ_SUBS")) : 1);
     n_sub = n_sub < 1 ? 1 : (n_sub > SEQ_MAX_SUBS ? SEQ_MAX_SUBS : n_sub);
     if (n_sub > ns) n_sub = ns;
@@ -214,7 +214,7 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     TRY(cudaHostAlloc(&h->h_pose_ring, sizeof(float) * 24 * ns * SEQ_SLOTS, cudaHostAllocMapped));
     TRY(cudaHostGetDevicePointer(&h->d_pose_ring, h->h_pose_ring, 0));
     TRY(cudaMallocHost(&h->h_status, sizeof(int) * h->n_img));
-    for (int i = 0; i < SEQ_SLOTS; i++) TRY(cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < SEQ_SLOTS; i++) for (int k = 0; k < n_sub; k++) TRY(cudaEventCreateWithFlags(&h->slot_ev[i][k], cudaEventDisableTiming));
     h->h_pose_last = (float *)calloc((size_t)12 * ns, sizeof(float));
     if (!h->h_pose_last) { orbx_sequences_destroy(h); return ORBX_ERR_NOMEM; }
     float sf[ORBX_MAX_LEVELS] = {0};
@@ -248,7 +248,7 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
     h->last_launches = 0;
     const int slot = h->slot;
     h->slot = (slot + 1) % SEQ_SLOTS;
-    ORBX_CUDA(cudaEventSynchronize(h->slot_ev[slot]));          // the kernel of the step that used this staging slot has run
+    for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaEventSynchronize(h->slot_ev[slot][k]));   // the kernels of the step that used this staging slot have run
     float *h_pose = h->h_pose_ring + (size_t)24 * ns * slot;
     for (int q = 0; q < ns; q++) {
         memcpy(h_pose + 24 * q, Tcw + 12 * q, sizeof(float) * 12);
@@ -263,14 +263,10 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
     P.cap = cap; P.per = per; P.nlevels = c.nlevels; P.have_last = have_last; P.mono = c.mono; P.check_ori = c.check_ori;
     P.const_depth = c.const_depth; P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.bf = c.bf; P.b = b;
     P.width = (float)c.width; P.height = (float)c.height; P.th = c.th;
-    {
-        dim3 grid((cap + 255) / 256, ns);
-        k_prep_step<<<grid, 256, 0, s>>>(P, h->d_pose_ring + (size_t)24 * ns * slot);
-        ORBX_CUDA(cudaGetLastError());
-        h->last_launches++;
-    }
-    ORBX_CUDA(cudaEventRecord(h->slot_ev[slot], s));
     orbx_frame_match_job *d_jobs = h->d_jobs;
+    // n_sub > 1: the sub-batches are independent pipelines on streams of their own.  Each waits for what the caller's stream holds
+    // at this point (the new images), then runs its whole step; nothing joins them until orbx_sequences_join / _step_end, so a
+    // sub-batch's step i + 1 starts as soon as its own step i is done.
     const bool fork = h->n_sub > 1;
     if (fork) ORBX_CUDA(cudaEventRecord(h->ev_fork, s));
     const size_t img_bytes = (size_t)c.width * c.height;
@@ -278,6 +274,13 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
         SeqSub &S = h->sub[k];
         cudaStream_t ss = fork ? S.stream : s;
         if (fork) ORBX_CUDA(cudaStreamWaitEvent(ss, h->ev_fork, 0));
+        {   // preparation: last frame's map points, match reset, jobs (reads the mapped pinned poses of this step's slot)
+            dim3 grid((cap + 255) / 256, S.nq);
+            k_prep_step<<<grid, 256, 0, ss>>>(P, h->d_pose_ring + (size_t)24 * ns * slot, S.q0);
+            ORBX_CUDA(cudaGetLastError());
+            h->last_launches++;
+            ORBX_CUDA(cudaEventRecord(h->slot_ev[slot][k], ss));
+        }
         const int i0 = per * S.q0, ni = per * S.nq;
         const uint8_t *d_in = images + (size_t)i0 * image_pitch;
         size_t in_pitch = image_pitch;
@@ -319,10 +322,7 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
             if (c.stereo && o->depth) ORBX_CUDA(cudaMemcpyAsync(o->depth + (size_t)cap * S.q0, h->d_depth[g] + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
             ORBX_CUDA(cudaMemcpyAsync(h->h_status + i0, S.ex->d_status, sizeof(int) * ni, cudaMemcpyDeviceToHost, ss));
         }
-        if (fork) {
-            ORBX_CUDA(cudaEventRecord(S.done, ss));
-            ORBX_CUDA(cudaStreamWaitEvent(s, S.done, 0));
-        }
+        if (fork) ORBX_CUDA(cudaEventRecord(S.done, ss));
     }
     memcpy(h->h_pose_last, Tcw, sizeof(float) * 12 * ns);
     h->gen ^= 1;
@@ -335,7 +335,10 @@ extern "C" orbx_status orbx_sequences_step_begin(orbx_sequences *h, const uint8_
     if (!h || !images || !Tcw || !o || !o->counts || !o->nmatches || !o->match) return ORBX_ERR_INVALID;
     if (stride < h->c.width) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
-    if (h->in_flight) ORBX_CUDA(cudaStreamSynchronize(h->stream));     // one step in flight per handle
+    if (h->in_flight) {                                                // one step in flight per handle
+        ORBX_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->n_sub > 1) for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaStreamSynchronize(h->sub[k].stream));
+    }
     const orbx_status st = run_step(h, images, true, image_pitch, stride, Tcw, o, h->stream);
     if (st) return st;
     h->in_flight = 1;
@@ -347,6 +350,14 @@ extern "C" orbx_status orbx_sequences_step_device(orbx_sequences *h, const uint8
     if (!h || !d_images || !Tcw || stride < h->c.width) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
     return run_step(h, d_images, false, frame_pitch, stride, Tcw, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" orbx_status orbx_sequences_join(orbx_sequences *h, void *stream) {
+    if (!h) return ORBX_ERR_INVALID;
+    ORBX_CUDA(cudaSetDevice(h->c.device));
+    if (h->n_sub > 1 && h->steps > 0)
+        for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->sub[k].done, 0));
+    return ORBX_OK;
 }
 
 extern "C" orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_sequences_device *v) {
@@ -364,6 +375,7 @@ extern "C" orbx_status orbx_sequences_step_end(orbx_sequences *h) {
     if (!h) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->n_sub > 1) for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaStreamSynchronize(h->sub[k].stream));
     if (h->in_flight) {
         h->in_flight = 0;
         for (int i = 0; i < h->n_img; i++)

@@ -100,6 +100,10 @@ class Sequences:
         Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(self.n_sequences, 12)
         check(self._L.orbx_sequences_step_device(self._h, d_images, frame_pitch, stride, Tcw.ctypes.data, stream))
 
+    def join(self, stream=None):
+        """n_sub > 1: `stream` waits for every sub-batch's last step"""
+        check(self._L.orbx_sequences_join(self._h, stream))
+
     def device_view(self):
         v = SequencesDevice()
         check(self._L.orbx_sequences_device_view(self._h, C.byref(v)))

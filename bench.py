@@ -567,6 +567,8 @@ def main():
     ap.add_argument("--features", type=int, default=NFEAT)
     ap.add_argument("--profile-steps", type=int, default=0, help="ncu runs: after the warm-up, bracket this many device-resident steps with "
                     "cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
+    ap.add_argument("--subs", type=int, default=4, help="sub-batch pipelines inside the handle of the device-resident `value` loop "
+                    "(orbx_sequences_config.n_sub; 1 = the whole step on one stream)")
     ap.add_argument("--extract-only", action="store_true", help="other frame shapes: time the extractor + matcher loop only (no LocalBA / stereo / ... sections)")
     args = ap.parse_args()
     default_workload = (args.width, args.height, args.features) == (W, H, NFEAT)
@@ -616,7 +618,7 @@ def main():
         return Sequences(B, W, H, synth.TUM1_K, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, stereo=False, th=7.0, check_ori=True, mono=False,
                          const_depth=Z, device=local_rank, n_sub=n_sub)
 
-    sq = new_handle()
+    sq = new_handle(args.subs)
     cap = sq.capacity
     stream = torch.cuda.Stream()                        # the device-resident loops run on this stream; the timing events are recorded on it
 
@@ -650,10 +652,10 @@ def main():
     e0.record(stream)
     for i in range(K):
         step_device(Wm + i)
+    sq.join(stream.cuda_stream)                         # (a handle with sub-batch pipelines: the stream waits for all of them)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    view = sq.device_view()
 
     # per-stage times come from a second, untimed-for-`value` loop: with stage events on, the extractor keeps its stages on one
     # stream back to back (in the loop above the blur runs on a side stream next to the quadtree kernel)
@@ -674,7 +676,15 @@ def main():
     # everything of the step that is not the extractor: unprojection of the last frame, the projection search and its memsets
     stage_ms["match"] = sum(a.elapsed_time(b) for a, b in ev_m) * runs / KP - sum(stage_ms.values())
     sq1.profile(0)
-    sq1.close()
+    view = sq1.device_view()
+    # the same handle without stage events: the step on ONE stream (what `value` is when the handle has no sub-batch pipelines)
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record(stream)
+    for i in range(K):
+        step_device(i, sq1)
+    o1.record(stream)
+    torch.cuda.synchronize()
+    ms_one_stream = o0.elapsed_time(o1) / K
     # ---- the same step followed by PoseOptimization of every frame from the match arrays, still device-resident (the three
     # calls Tracking::TrackWithMotionModel makes per frame: extract, SearchByProjection(Cur, Last), PoseOptimization) ----
     track = None
@@ -687,7 +697,7 @@ def main():
         d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
 
         def step_track(i):
-            step_device(i)
+            step_device(i, sq1)
             pz.from_matches_device(view.jobs, B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, d_pose.data_ptr(), d_inl.data_ptr(),
                                    d_outkp.data_ptr(), cap, stream.cuda_stream)
 
@@ -703,7 +713,7 @@ def main():
         torch.cuda.synchronize()
         ms_track = t0e.elapsed_time(t1e) / KT
         track = {"config": "the `value` step + Optimizer::PoseOptimization of all %d frames from the match arrays (monocular observations), device-resident" % B,
-                 "frames_per_s": B / (ms_track * 1e-3), "ms_per_step": ms_track, "pose_ms_per_step": ms_track - ms_total / K,
+                 "frames_per_s": B / (ms_track * 1e-3), "ms_per_step": ms_track, "pose_ms_per_step": ms_track - ms_one_stream,
                  "inliers_per_frame": float(d_inl.float().mean().item()), "kernel_launches_per_step": launches_per_step + pz.last_launches(),
                  "api": "orbx_sequences_step_device + orbx_pose_from_matches_device"}
         pz.close()
@@ -722,7 +732,8 @@ def main():
     NLANES = 4
     for li in range(NLANES):
         L = Lane()
-        L.sq = sq if li == 0 else new_handle()
+        L.sq = sq1 if li == 0 else new_handle(n_sub=1)       # the end-to-end lanes are one-stream handles: the lanes themselves overlap
+        L.sq1 = L.sq
         L.stream = torch.cuda.Stream()
         L.out = L.sq.alloc_outputs(pinned)
         L.t, L.busy = 0, False
@@ -730,9 +741,9 @@ def main():
     torch.cuda.synchronize()
 
     # device-resident again, but with two handles alternating on two streams (for comparison with `value`, which is one stream)
-    def step_device_lane(i):
+    def step_device_lane(i, one_stream=False):
         L = lanes[i % 2]
-        step_device(L.t, L.sq, L.stream)
+        step_device(L.t, L.sq1 if one_stream else L.sq, L.stream)
         L.t += 1
 
     for i in range(4):
@@ -746,6 +757,7 @@ def main():
         step_device_lane(i)
     t2_1 = []
     for L in lanes[:2]:
+        L.sq.join(L.stream.cuda_stream)
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(L.stream)
         t2_1.append(ev)
@@ -758,10 +770,10 @@ def main():
             L.d_pose = torch.zeros((B, 7), dtype=torch.float64, device="cuda")
             L.d_inl = torch.zeros(B, dtype=torch.int32, device="cuda")
             L.d_outkp = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
-            L.jobs = L.sq.device_view().jobs
+            L.jobs = L.sq1.device_view().jobs
 
         def step_track_lane(i):
-            step_device_lane(i)
+            step_device_lane(i, one_stream=True)
             L = lanes[i % 2]
             L.pz.from_matches_device(L.jobs, B, d_is2.data_ptr(), NLEVELS, synth.TUM1_K, L.d_pose.data_ptr(), L.d_inl.data_ptr(),
                                      L.d_outkp.data_ptr(), cap, L.stream.cuda_stream)
@@ -937,6 +949,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(B),
             "run": {"batch_per_gpu": B, "parallelism": "%d independent sequences per GPU in lockstep, sharded over %d GPU(s), no collective on the data path" % (B, world),
+                    "value_handle": "one orbx_sequences handle per GPU with n_sub = %d sub-batch pipelines (streams of their own, joined at the end of the timed region)" % args.subs,
                     "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame, "frames_per_rank": [c[0] for c in counters],
                     "per_step_working_set_mb": B * 3.3, "binary": binary_identity()},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -950,6 +963,8 @@ def main():
                                      "e2e_fraction_of_ceiling": ceil_s / e2e_s,
                                      "what": "the same bytes per step (frames in, results out) as plain cudaMemcpyAsync on the same %d streams, "
                                              "no kernels, all %d rank(s) copying at once, ranks bound to disjoint host cores" % (NLANES, world)}},
+            "value_one_stream": {"value": B * world / (ms_one_stream * 1e-3), "unit": "frames/s", "ms_per_step": ms_one_stream,
+                                 "note": "rank 0's handle with n_sub = 1 (the whole step on one stream), times the number of ranks"},
             "value_two_lanes": {"value": frames_total / (ms_two_lanes * 1e-3), "unit": "frames/s",
                                 "note": "device-resident like `value`, but two handles in flight on two streams like `e2e`; `value` itself is "
                                         "one handle on one stream"},
@@ -1008,6 +1023,7 @@ def main():
         dist.destroy_process_group()
     for L in lanes:
         L.sq.close()
+    sq.close()
 
 
 if __name__ == "__main__":

@@ -335,7 +335,9 @@ typedef struct {
     float const_depth;           /* stereo == 0 only: the depth (> 0) every keypoint of the last frame is unprojected with (mvDepth of an
                                     RGB-D style input whose scene is a fronto-parallel plane; bench.py's config C2) */
     int32_t device;
-    int32_t n_sub;               /* sub-batches that run the chain on streams of their own inside a step (0 or 1 = one stream, the default: measured faster at 64 VGA sequences) */
+    int32_t n_sub;               /* 0 or 1: the whole step runs on one stream.  > 1: the sequences are cut into n_sub sub-batches that run as
+                                    independent pipelines on streams of their own (a sub-batch's next step starts when its own last one is done);
+                                    a step's device results are then complete after orbx_sequences_join / orbx_sequences_step_end */
 } orbx_sequences_config;
 typedef struct {                 /* host pointers, filled when orbx_sequences_step_end returns; capacity = orbx_sequences_capacity() */
     orbx_keypoint *kps;          /* [n_images][capacity]      mvKeys of every new image (may be NULL) */
@@ -376,6 +378,8 @@ typedef struct {
     void *stream;
 } orbx_sequences_device;
 orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_sequences_device *view);
+/* n_sub > 1: makes `stream` wait for every sub-batch's last step (a no-op for n_sub <= 1, where steps run on the caller's stream) */
+orbx_status orbx_sequences_join(orbx_sequences *h, void *stream);
 int orbx_sequences_last_launches(const orbx_sequences *h);
 
 /* =====================================================================================================
