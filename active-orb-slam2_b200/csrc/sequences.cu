@@ -22,6 +22,7 @@ struct SeqSub {
     orbx_extractor *ex;
     orbx_matcher *mt;
     orbx_stereo *st;
+    orbx_pose *pz;
     cudaStream_t stream;
     cudaEvent_t done;
     int q0, nq;                // sequences [q0, q0 + nq)
@@ -44,7 +45,10 @@ struct orbx_sequences {
     int32_t *d_kept;
     orbx_last_point *d_pts;    // [n_seq][cap] last frame's keypoints as map points
     int32_t *d_match, *d_nm;   // [n_seq][cap] followed by [n_seq] (one allocation, one memset)
-    float *d_sf;               // mvScaleFactors
+    float *d_sf, *d_is2;       // mvScaleFactors, mvInvLevelSigma2
+    double *d_pose;            // [n_seq][7] optimised SE3Quat (config pose)
+    int32_t *d_inl;            // [n_seq]
+    uint8_t *d_outkp;          // [n_seq][cap] mvbOutlier
     // per-step staging of the poses, [n_seq][24] floats (Tcw of the new frame, Tcw of the last): mapped pinned memory that the
     // preparation kernel reads directly; a ring, so that steps can be enqueued ahead of the device (a slot is rewritten only after
     // the kernel that reads it has run)
@@ -146,12 +150,13 @@ extern "C" void orbx_sequences_destroy(orbx_sequences *h) {
         if (S.ex) orbx_extractor_destroy(S.ex);
         if (S.mt) orbx_matcher_destroy(S.mt);
         if (S.st) orbx_stereo_destroy(S.st);
+        if (S.pz) orbx_pose_destroy(S.pz);
         if (S.stream) cudaStreamDestroy(S.stream);
         if (S.done) cudaEventDestroy(S.done);
     }
     cudaFree(h->d_img);
     for (int g = 0; g < 2; g++) { cudaFree(h->d_kps[g]); cudaFree(h->d_desc[g]); cudaFree(h->d_cnt[g]); cudaFree(h->d_depth[g]); }
-    cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_sf); cudaFree(h->d_jobs);
+    cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_sf); cudaFree(h->d_is2); cudaFree(h->d_pose); cudaFree(h->d_inl); cudaFree(h->d_outkp); cudaFree(h->d_jobs);
     cudaFreeHost(h->h_pose_ring); cudaFreeHost(h->h_status);
     for (int i = 0; i < SEQ_SLOTS; i++) for (int k = 0; k < SEQ_MAX_SUBS; k++) if (h->slot_ev[i][k]) cudaEventDestroy(h->slot_ev[i][k]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -190,6 +195,7 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
         h->cap = orbx_extractor_capacity(S.ex);
         if ((st = orbx_matcher_create(&S.mt, h->cap, h->cap, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
         if (cfg->stereo && (st = orbx_stereo_create(&S.st, h->cap, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
+        if (cfg->pose && (st = orbx_pose_create(&S.pz, h->cap * S.nq, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
         TRY(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
         TRY(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
     }
@@ -210,6 +216,12 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     TRY(cudaMalloc(&h->d_match, sizeof(int32_t) * (cap + 1) * ns));
     h->d_nm = h->d_match + cap * ns;
     TRY(cudaMalloc(&h->d_sf, sizeof(float) * ORBX_MAX_LEVELS));
+    TRY(cudaMalloc(&h->d_is2, sizeof(float) * ORBX_MAX_LEVELS));
+    if (cfg->pose) {
+        TRY(cudaMalloc(&h->d_pose, sizeof(double) * 7 * ns));
+        TRY(cudaMalloc(&h->d_inl, sizeof(int32_t) * ns));
+        TRY(cudaMalloc(&h->d_outkp, cap * ns));
+    }
     TRY(cudaMalloc(&h->d_jobs, sizeof(orbx_frame_match_job) * ns));
     TRY(cudaHostAlloc(&h->h_pose_ring, sizeof(float) * 24 * ns * SEQ_SLOTS, cudaHostAllocMapped));
     TRY(cudaHostGetDevicePointer(&h->d_pose_ring, h->h_pose_ring, 0));
@@ -217,9 +229,10 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
     for (int i = 0; i < SEQ_SLOTS; i++) for (int k = 0; k < n_sub; k++) TRY(cudaEventCreateWithFlags(&h->slot_ev[i][k], cudaEventDisableTiming));
     h->h_pose_last = (float *)calloc((size_t)12 * ns, sizeof(float));
     if (!h->h_pose_last) { orbx_sequences_destroy(h); return ORBX_ERR_NOMEM; }
-    float sf[ORBX_MAX_LEVELS] = {0};
-    if ((st = orbx_extractor_tables(h->sub[0].ex, sf, nullptr, nullptr, nullptr, nullptr))) { orbx_sequences_destroy(h); return st; }
+    float sf[ORBX_MAX_LEVELS] = {0}, is2[ORBX_MAX_LEVELS] = {0};
+    if ((st = orbx_extractor_tables(h->sub[0].ex, sf, nullptr, nullptr, is2, nullptr))) { orbx_sequences_destroy(h); return st; }
     TRY(cudaMemcpy(h->d_sf, sf, sizeof(sf), cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(h->d_is2, is2, sizeof(is2), cudaMemcpyHostToDevice));
 #undef TRY
     *out = h;
     return ORBX_OK;
@@ -312,6 +325,12 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
             if ((st = orbx_match_projection_frame_device(S.mt, d_jobs + S.q0, S.nq, ss))) return st;
             h->last_launches += orbx_matcher_last_launches(S.mt);
         }
+        // Optimizer::PoseOptimization from the match array, starting at the pose the search projected with (Tracking.cc:868-870)
+        if (c.pose && have_last) {
+            if ((st = orbx_pose_from_matches_device(S.pz, d_jobs + S.q0, S.nq, h->d_is2, c.nlevels, c.fx, c.fy, c.cx, c.cy, c.bf, h->d_pose + 7 * S.q0,
+                                                    h->d_inl + S.q0, h->d_outkp + (size_t)cap * S.q0, cap, ss))) return st;
+            h->last_launches += orbx_pose_last_launches(S.pz);
+        }
         if (o) {                                             // the sub-batch's results back to the caller's buffers
             ORBX_CUDA(cudaMemcpyAsync(o->counts + i0, h->d_cnt[g] + i0, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, ss));
             if (o->kps) ORBX_CUDA(cudaMemcpyAsync(o->kps + (size_t)cap * i0, h->d_kps[g] + (size_t)cap * i0, sizeof(orbx_keypoint) * cap * ni, cudaMemcpyDeviceToHost, ss));
@@ -320,6 +339,11 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
             ORBX_CUDA(cudaMemcpyAsync(o->nmatches + S.q0, h->d_nm + S.q0, sizeof(int32_t) * S.nq, cudaMemcpyDeviceToHost, ss));
             if (c.stereo && o->u_right) ORBX_CUDA(cudaMemcpyAsync(o->u_right + (size_t)cap * S.q0, h->d_ur + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
             if (c.stereo && o->depth) ORBX_CUDA(cudaMemcpyAsync(o->depth + (size_t)cap * S.q0, h->d_depth[g] + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
+            if (c.pose && have_last) {
+                if (o->pose) ORBX_CUDA(cudaMemcpyAsync(o->pose + 7 * S.q0, h->d_pose + 7 * S.q0, sizeof(double) * 7 * S.nq, cudaMemcpyDeviceToHost, ss));
+                if (o->n_inliers) ORBX_CUDA(cudaMemcpyAsync(o->n_inliers + S.q0, h->d_inl + S.q0, sizeof(int32_t) * S.nq, cudaMemcpyDeviceToHost, ss));
+                if (o->outlier) ORBX_CUDA(cudaMemcpyAsync(o->outlier + (size_t)cap * S.q0, h->d_outkp + (size_t)cap * S.q0, (size_t)cap * S.nq, cudaMemcpyDeviceToHost, ss));
+            }
             ORBX_CUDA(cudaMemcpyAsync(h->h_status + i0, S.ex->d_status, sizeof(int) * ni, cudaMemcpyDeviceToHost, ss));
         }
         if (fork) ORBX_CUDA(cudaEventRecord(S.done, ss));
@@ -352,6 +376,12 @@ extern "C" orbx_status orbx_sequences_step_device(orbx_sequences *h, const uint8
     return run_step(h, d_images, false, frame_pitch, stride, Tcw, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" orbx_status orbx_sequences_set_last_poses(orbx_sequences *h, const float *Tcw_last) {
+    if (!h || !Tcw_last) return ORBX_ERR_INVALID;
+    memcpy(h->h_pose_last, Tcw_last, sizeof(float) * 12 * h->c.n_sequences);
+    return ORBX_OK;
+}
+
 extern "C" orbx_status orbx_sequences_join(orbx_sequences *h, void *stream) {
     if (!h) return ORBX_ERR_INVALID;
     ORBX_CUDA(cudaSetDevice(h->c.device));
@@ -367,6 +397,7 @@ extern "C" orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_
     v->kps = h->d_kps[g]; v->desc = h->d_desc[g]; v->counts = h->d_cnt[g];
     v->match = h->d_match; v->nmatches = h->d_nm; v->u_right = h->d_ur; v->depth = h->d_depth[g];
     v->jobs = h->d_jobs;
+    v->pose = h->d_pose; v->n_inliers = h->d_inl; v->outlier = h->d_outkp;
     v->stream = h->stream;
     return ORBX_OK;
 }

@@ -119,5 +119,6 @@ def _declare(L):
     L.orbx_sequences_step_device.argtypes = [vp, vp, sz, i, vp, vp]
     L.orbx_sequences_device_view.argtypes = [vp, vp]
     L.orbx_sequences_join.argtypes = [vp, vp]
+    L.orbx_sequences_set_last_poses.argtypes = [vp, vp]
     L.orbx_extractor_profile.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, C.POINTER(i), vp]

@@ -16,19 +16,20 @@ class SequencesConfig(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32), ("n_sequences", C.c_int32), ("stereo", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
                 ("th", C.c_float), ("check_ori", C.c_int32), ("mono", C.c_int32), ("const_depth", C.c_float), ("device", C.c_int32),
-                ("n_sub", C.c_int32)]
+                ("pose", C.c_int32), ("n_sub", C.c_int32)]
 
 
 class SequencesOutputs(C.Structure):
     """orbx_sequences_outputs (include/orbx.h)"""
     _fields_ = [("kps", C.c_void_p), ("desc", C.c_void_p), ("counts", C.c_void_p), ("match", C.c_void_p), ("nmatches", C.c_void_p),
-                ("u_right", C.c_void_p), ("depth", C.c_void_p)]
+                ("u_right", C.c_void_p), ("depth", C.c_void_p), ("pose", C.c_void_p), ("n_inliers", C.c_void_p), ("outlier", C.c_void_p)]
 
 
 class SequencesDevice(C.Structure):
     """orbx_sequences_device (include/orbx.h): device buffers of the last step"""
     _fields_ = [("extractor", C.c_void_p), ("kps", C.c_void_p), ("desc", C.c_void_p), ("counts", C.c_void_p), ("match", C.c_void_p),
-                ("nmatches", C.c_void_p), ("u_right", C.c_void_p), ("depth", C.c_void_p), ("jobs", C.c_void_p), ("stream", C.c_void_p)]
+                ("nmatches", C.c_void_p), ("u_right", C.c_void_p), ("depth", C.c_void_p), ("jobs", C.c_void_p),
+                ("pose", C.c_void_p), ("n_inliers", C.c_void_p), ("outlier", C.c_void_p), ("stream", C.c_void_p)]
 
 
 class Sequences:
@@ -36,13 +37,13 @@ class Sequences:
     outputs() (numpy, or pinned torch tensors viewed through .numpy()) and reused every step."""
 
     def __init__(self, n_sequences, width, height, K, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, stereo=False,
-                 th=7.0, check_ori=True, mono=False, const_depth=0.0, device=0, n_sub=0):
+                 th=7.0, check_ori=True, mono=False, const_depth=0.0, device=0, n_sub=0, pose=False):
         self._L = lib()
         c = SequencesConfig()
         c.nfeatures, c.scale_factor, c.nlevels, c.ini_th, c.min_th = nfeatures, scale_factor, nlevels, ini_th, min_th
         c.width, c.height, c.n_sequences, c.stereo = width, height, n_sequences, int(stereo)
         c.fx, c.fy, c.cx, c.cy, c.bf = (float(v) for v in K[:5])
-        c.th, c.check_ori, c.mono, c.const_depth, c.device, c.n_sub = th, int(check_ori), int(mono), const_depth, device, n_sub
+        c.th, c.check_ori, c.mono, c.const_depth, c.device, c.n_sub, c.pose = th, int(check_ori), int(mono), const_depth, device, n_sub, int(pose)
         self.config = c
         self._h = C.c_void_p()
         check(self._L.orbx_sequences_create(C.byref(self._h), C.byref(c)))
@@ -66,12 +67,14 @@ class Sequences:
             o["desc"] = alloc((ni, cap, 32), np.uint8)
         if self.config.stereo:
             o["u_right"], o["depth"] = alloc((ns, cap), np.float32), alloc((ns, cap), np.float32)
+        if self.config.pose:
+            o["pose"], o["n_inliers"], o["outlier"] = alloc((ns, 7), np.float64), alloc((ns,), np.int32), alloc((ns, cap), np.uint8)
         return o
 
     @staticmethod
     def _pack(o):
         S = SequencesOutputs()
-        for k in ("kps", "desc", "counts", "match", "nmatches", "u_right", "depth"):
+        for k in ("kps", "desc", "counts", "match", "nmatches", "u_right", "depth", "pose", "n_inliers", "outlier"):
             if o.get(k) is not None:
                 setattr(S, k, o[k].ctypes.data)
         return S
@@ -99,6 +102,11 @@ class Sequences:
         """the step with the new images already on the device and the results left there; only enqueues (raw device pointer in)"""
         Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(self.n_sequences, 12)
         check(self._L.orbx_sequences_step_device(self._h, d_images, frame_pitch, stride, Tcw.ctypes.data, stream))
+
+    def set_last_poses(self, Tcw_last):
+        """the (optimised) poses of the frames of the last step, [n_sequences, 3, 4]: the next step unprojects the last frame with them"""
+        T = np.ascontiguousarray(Tcw_last, np.float32).reshape(self.n_sequences, 12)
+        check(self._L.orbx_sequences_set_last_poses(self._h, T.ctypes.data))
 
     def join(self, stream=None):
         """n_sub > 1: `stream` waits for every sub-batch's last step"""

@@ -518,6 +518,7 @@ def bench_sequence(local_rank, with_cpu, n_frames=40):
            "ms_per_frame_by_call": {k: 1e3 * v / (n_frames - 3) for k, v in gpu.seconds.items()},
            "api": "orbx_extractor_run_host x2, orbx_stereo_matches_host, orbx_match_projection_frame_host, orbx_pose_optimize_host (+ numpy bookkeeping)"}
     gpu.close()
+    out["one_call_per_frame"] = bench_single_stream(local_rank, seq, imgs, n_frames)
     if with_cpu:
         orc = replay.OracleBackend()
         rng = np.random.default_rng(7)
@@ -528,6 +529,206 @@ def bench_sequence(local_rank, with_cpu, n_frames=40):
         out["cpu_frames_per_s"] = 8 / (time.perf_counter() - t0)
         out["cpu"] = "the same chain on the C oracle, 1 thread (the reference runs the two extractors on two threads), 8 frames"
     return out
+
+
+def bench_single_stream(local_rank, seq, imgs, n_frames, reps=6):
+    """The same single-stream chains with ONE C-ABI call per frame (orbx_sequences_step_host on a handle of one sequence): the frame's
+    host image(s) and predicted pose in; keypoints, descriptors, mvuRight / mvDepth, match array, optimised pose and mvbOutlier out;
+    the last frame stays on the device.  Strictly serial: a frame is submitted after the previous one has been read on the host."""
+    import replay
+    from orbx import synth
+    from orbx.sequences import Sequences
+    K = seq.K
+    res = {}
+    # (1) stereo chain: extract L + R -> ComputeStereoMatches -> SearchByProjection(Cur, Last) -> PoseOptimization
+    sq = Sequences(1, seq.w, seq.h, K, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, stereo=True, th=7.0, mono=False, device=local_rank, pose=True)
+    o = sq.alloc_outputs()
+    pairs = [np.stack(imgs[t]) for t in range(n_frames)]
+    rng = np.random.default_rng(7)
+    order = list(range(n_frames)) + list(range(n_frames - 2, 0, -1))       # there and back again: every step moves by one frame
+    Tl, n_done, inl, errs = None, 0, [], []
+
+    def quat_to_T(p):
+        """Converter::toCvMat(SE3Quat): Eigen's toRotationMatrix, narrowed to float"""
+        x, y, z, w_ = p[0], p[1], p[2], p[3]
+        T = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w_), 2 * (x * z + y * w_), p[4]],
+                      [2 * (x * y + z * w_), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w_), p[5]],
+                      [2 * (x * z - y * w_), 2 * (y * z + x * w_), 1 - 2 * (x * x + y * y), p[6]], [0, 0, 0, 1]], np.float32)
+        return T
+    t0 = None
+    for r_ in range(reps):
+        for t in order:
+            if r_ == 1 and t0 is None:                                       # the first pass is the warm-up
+                t0 = time.perf_counter()
+            Tcw = seq.true_pose(t).copy()
+            Tcw[:3, 3] += rng.normal(0, 0.01, 3).astype(np.float32)          # motion-model guess: the true pose off by ~1 cm / 0.2 deg
+            Tcw[:3, :3] = (synth._rot(1, np.deg2rad(rng.normal(0, 0.2))) @ Tcw[:3, :3].astype(np.float64)).astype(np.float32)
+            if Tl is not None:
+                sq.set_last_poses(Tl[:3])                                    # the optimised pose of the last frame, like Tracking's mLastFrame
+            sq.step(pairs[t], Tcw[:3], o)
+            Tl = quat_to_T(o["pose"][0]) if n_done else seq.true_pose(t)
+            n_done += 1
+            if t0 is not None:
+                inl.append(int(o["n_inliers"][0]))
+                errs.append(float(np.linalg.norm(Tl[:3, 3] - seq.true_pose(t)[:3, 3])))
+    dt = time.perf_counter() - t0
+    n_timed = (reps - 1) * len(order)
+    res["stereo_chain"] = {"frames_per_s": n_timed / dt, "ms_per_frame": 1e3 * dt / n_timed, "inliers_per_frame": float(np.mean(inl)),
+                           "mean_position_error_m": float(np.mean(errs)), "max_position_error_m": float(np.max(errs)), "kernel_launches_per_frame": sq.last_launches(),
+                           "api": "orbx_sequences_step_host, n_sequences = 1, stereo = 1, pose = 1 (+ orbx_sequences_set_last_poses)"}
+    sq.close()
+    # (2) monocular extract + SearchByProjection(Cur, Last): the chain BASELINE.json's >= 3000 frames/s target names, one frame at a time
+    sq = Sequences(1, W, H, synth.TUM1_K, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, stereo=False, th=7.0, mono=False, const_depth=4.0, device=local_rank)
+    o = sq.alloc_outputs()
+    fx, fy = synth.TUM1_K[0], synth.TUM1_K[1]
+    base = synth.g_rect(5, W, H)
+    shifts = [0, 1, 2, 3, 4, 3, 2, 1]
+    frames = [np.ascontiguousarray(np.roll(base, (7 * k, 13 * k), (0, 1)))[None] for k in shifts]
+    poses = []
+    for k in shifts:
+        T = np.zeros((3, 4), np.float32)
+        T[:, :3] = np.eye(3)
+        T[:, 3] = (13.0 * k * 4.0 / fx, 7.0 * k * 4.0 / fy, 0.0)
+        poses.append(T)
+    for i in range(16):
+        sq.step(frames[i % 8], poses[i % 8], o)
+    n_mono = 400
+    t0 = time.perf_counter()
+    nm = 0
+    for i in range(n_mono):
+        sq.step(frames[i % 8], poses[i % 8], o)
+        nm += int(o["nmatches"][0])
+    dt = time.perf_counter() - t0
+    res["mono_extract_match"] = {"frames_per_s": n_mono / dt, "ms_per_frame": 1e3 * dt / n_mono, "matches_per_frame": nm / n_mono,
+                                 "kernel_launches_per_frame": sq.last_launches(),
+                                 "api": "orbx_sequences_step_host, n_sequences = 1 (host image + pose in; keypoints, descriptors, match array out)"}
+    sq.close()
+    return res
+
+
+def bench_c5(local_rank, rank, world, n_seq_total=64, steps=40, w=1241, h=376, nfeat=2000):
+    """BASELINE.json config 5: 64 independent KITTI-stereo-shaped sequences (1241x376, 2000 features; intrinsics of
+    Examples/Stereo/KITTI00-02.yaml) sharded over the ranks, sequence s -> rank s mod N, through the per-frame stereo chain (extract L + R ->
+    ComputeStereoMatches -> SearchByProjection(Cur, Last)) with HOST buffers in and out (orbx_sequences_step_begin/_end, two handles in
+    flight per rank).  Strong scaling: the 64 sequences are fixed, every rank takes its share.  Returns (pairs done, seconds, matches)."""
+    import torch
+    from orbx import synth
+    from orbx.sequences import Sequences
+    mine = [s_ for s_ in range(n_seq_total) if s_ % world == rank]
+    if not mine:
+        return 0, 0.0, 0
+    K = (718.856, 718.856, 607.1928, 185.2157, 386.1448, 386.1448 / 718.856)   # Camera.fx, fy, cx, cy, bf (KITTI00-02.yaml:8-25)
+    nh = 2 if len(mine) >= 2 else 1
+    groups = [mine[i::nh] for i in range(nh)]
+    # a sequence = a G-rect scene on a fronto-parallel plane at z = bf / d (disparity d px): the right image is the left shifted by d, the
+    # camera translates sideways by 9 px per frame (there and back again)
+    SH = [0, 1, 2, 3, 4, 3, 2, 1]
+    pool = {}
+
+    def scene(s_):
+        if s_ % 8 not in pool:
+            pool[s_ % 8] = synth.g_rect(1000 + s_ % 8, w, h, nrect=1800)
+        return pool[s_ % 8]
+
+    handles = []
+    for grp in groups:
+        n = len(grp)
+        sq = Sequences(n, w, h, K, nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, stereo=True, th=7.0, mono=False, device=local_rank)
+        imgs = torch.empty((len(SH), 2 * n, h, w), dtype=torch.uint8).pin_memory()
+        poses = np.zeros((len(SH), n, 3, 4), np.float32)
+        for j, s_ in enumerate(grp):
+            d = 12 + 4 * (s_ % 5)                                            # disparity in pixels -> depth bf / d
+            z = K[4] / d
+            sc = scene(s_)
+            for t, k in enumerate(SH):
+                left = np.roll(sc, 9 * k + 3 * (s_ // 8), 1)
+                imgs[t, 2 * j] = torch.from_numpy(left)
+                imgs[t, 2 * j + 1] = torch.from_numpy(np.roll(left, -d, 1))
+                poses[t, j, :, :3] = np.eye(3)
+                poses[t, j, 0, 3] = 9.0 * k * z / K[0]
+        handles.append((sq, imgs.numpy(), poses, sq.alloc_outputs(lambda shape, dtype: torch.zeros(shape, dtype={np.uint8: torch.uint8, np.int32: torch.int32, np.float32: torch.float32, np.float64: torch.float64}[dtype]).pin_memory().numpy())))
+    busy = [False] * nh
+    nm = 0
+
+    def run(n_steps, count):
+        nonlocal nm
+        for i in range(n_steps):
+            for hi, (sq, imgs, poses, o) in enumerate(handles):
+                if busy[hi]:
+                    sq.end()
+                    if count:
+                        nm += int(o["nmatches"].sum())
+                sq.begin(imgs[i % len(SH)], poses[i % len(SH)], o)
+                busy[hi] = True
+        for hi, (sq, imgs, poses, o) in enumerate(handles):
+            if busy[hi]:
+                sq.end()
+                busy[hi] = False
+                if count:
+                    nm += int(o["nmatches"].sum())
+
+    run(3, False)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(steps, True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    for sq, _, _, _ in handles:
+        sq.close()
+    return steps * len(mine), dt, nm
+
+
+def cpu_c5(seconds_budget, threads, w=1241, h=376, nfeat=2000):
+    """the config-5 chain (extract L + R, ComputeStereoMatches, SearchByProjection(Cur, Last)) on the CPU oracle, `threads` host threads,
+    one sequence per thread; returns (pairs/s, pairs, seconds)"""
+    from oracle import oracle_py as O
+    from orbx import synth
+    O.lib()
+    K = (718.856, 718.856, 607.1928, 185.2157, 386.1448, 386.1448 / 718.856)
+    sf = synth.scale_factors(NLEVELS, SCALE)
+    done = [0] * threads
+    stop_at = [None]
+    scenes = [synth.g_rect(1000 + i, w, h, nrect=1800) for i in range(min(threads, 8))]
+    SH = [0, 1, 2, 3, 4, 3, 2, 1]
+
+    def work(t):
+        exl, exr = O.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH), O.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH)
+        tb = exl.tables()
+        d = 12 + 4 * (t % 5)
+        z = K[4] / d
+        last, i = None, 0
+        while time.perf_counter() < stop_at[0]:
+            k = SH[i % 8]
+            left = np.roll(scenes[t % len(scenes)], 9 * k, 1)
+            kl, dl = exl(left)
+            kr, dr = exr(np.roll(left, -d, 1))
+            st = O.stereo_matches(kl, dl, kr, dr, [exl.level(l) for l in range(NLEVELS)], [exr.level(l) for l in range(NLEVELS)], tb["scale"],
+                                  tb["inv_scale"], K[4], K[5])
+            tx = np.float32(9.0 * k * z / K[0])
+            if last is not None:
+                lk, ld, lz, ltx = last
+                pts = np.zeros(len(lk), O.LAST_POINT_DTYPE)
+                ok = lz > 0
+                pts["x"] = (lk["x"] - np.float32(K[2])) * lz / np.float32(K[0]) - ltx
+                pts["y"] = (lk["y"] - np.float32(K[3])) * lz / np.float32(K[1])
+                pts["z"], pts["angle"], pts["octave"], pts["valid"], pts["blocks"] = lz, lk["angle"], lk["octave"], ok, ok
+                cur = dict(keys_un=kl, desc=dl, u_right=st["u_right"], claimed=None, bounds=(0.0, 0.0, float(w), float(h)), K=K, scale_factors=sf)
+                O.search_by_projection_frame(cur, pts, ld, np.eye(3, dtype=np.float32), np.array([tx, 0, 0], np.float32), False, False, 7.0, True)
+            last = (kl, dl, st["depth"], tx)
+            i += 1
+            done[t] += 1
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    stop_at[0] = t0 + seconds_budget
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, sum(done), dt
 
 
 def bench_lba_batched(local_rank, rank, NW=16, rounds=3):
@@ -911,6 +1112,10 @@ def main():
     if default_workload and not args.extract_only:
         barrier()
         lba_local = bench_lba_batched(local_rank, rank)
+    c5_local = (0, 0.0, 0)
+    if default_workload and not args.extract_only:
+        barrier()
+        c5_local = bench_c5(local_rank, rank, world)
     stereo = pose = bow = sequence = None
     if side_sections:
         with_cpu = not args.no_cpu and world == 1      # CPU legs are timed on rank 0 at N = 1 only
@@ -923,7 +1128,7 @@ def main():
     from orbx import shard
     ms_total, e2e_s, ms_two_lanes, ceil_s = shard.max_over_ranks([ms_total, e2e_s, ms_two_lanes, ceil_s], device="cuda")
     counters = shard.gather_counters([B * K, int(round(kp_per_frame * B)), int(round(matches_per_frame * B)), lba_local[0], lba_local[1],
-                                      int(lba_local[2] * 1e6)], device="cuda")
+                                      int(lba_local[2] * 1e6), c5_local[0], int(c5_local[1] * 1e6), c5_local[2]], device="cuda")
     frames_total = sum(c[0] for c in counters)
     value = frames_total / (ms_total * 1e-3)
     e2e = frames_total / e2e_s
@@ -933,6 +1138,16 @@ def main():
         lba["batched"] = {"windows_in_flight_per_gpu": 16, "windows_per_s": lw / ls if ls > 0 else 0.0, "lm_trials_per_s": lt / ls if ls > 0 else 0.0,
                           "n_gpus": world, "windows_per_rank": [c[3] for c in counters],
                           "api": "orbx_lba_solve_begin / orbx_lba_solve_end, one handle per window; every rank solves its own windows, time = max over ranks"}
+    c5 = None
+    if rank == 0 and sum(c[6] for c in counters) > 0:
+        pairs, secs = sum(c[6] for c in counters), max(c[7] for c in counters) * 1e-6
+        c5 = {"config": "BASELINE.json config 5: 64 independent KITTI-stereo-shaped synthetic sequences (1241x376 rectified pairs, 2000 features, "
+                        "Examples/Stereo/KITTI00-02.yaml intrinsics), sequence s -> rank s mod N; per pair: extract L + R, ComputeStereoMatches, "
+                        "SearchByProjection(Cur, Last); host images + poses in, host results out",
+              "pairs_per_s": pairs / secs, "n_gpus": world, "scaling": "strong (the 64 sequences are fixed)", "pairs_per_rank": [c[6] for c in counters],
+              "seconds": secs, "matches_per_pair": sum(c[8] for c in counters) / max(pairs, 1),
+              "h2d_bytes_per_pair": 2 * 1241 * 376,
+              "api": "orbx_sequences_step_begin / orbx_sequences_step_end, stereo = 1, two handles in flight per rank; time = max over ranks"}
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(stage_ms, key=stage_ms.get)
@@ -980,12 +1195,18 @@ def main():
                                         "traffic": traffic_step}},
             "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
             "lba": lba,
+            "c5": c5,
             "stereo": stereo,
             "pose": pose,
             "bow": bow,
             "sequence": sequence,
             "track": track,
         }
+        if not args.no_cpu and world == 1 and c5 is not None:
+            cores_ = os.cpu_count() or 1
+            cps, cn, cdt = cpu_c5(6.0, cores_)
+            c5["cpu_pairs_per_s"] = cps
+            c5["cpu"] = "the same chain on the C oracle, %d host threads (one sequence per thread), %d pairs in %.1f s" % (cores_, cn, cdt)
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             fps, n, dt = cpu_path(hnp[:64], 12.0, cores)

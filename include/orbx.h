@@ -335,6 +335,7 @@ typedef struct {
     float const_depth;           /* stereo == 0 only: the depth (> 0) every keypoint of the last frame is unprojected with (mvDepth of an
                                     RGB-D style input whose scene is a fronto-parallel plane; bench.py's config C2) */
     int32_t device;
+    int32_t pose;                /* 1: Optimizer::PoseOptimization of every new frame from its match array, starting at the given Tcw (Tracking.cc:868-870) */
     int32_t n_sub;               /* 0 or 1: the whole step runs on one stream.  > 1: the sequences are cut into n_sub sub-batches that run as
                                     independent pipelines on streams of their own (a sub-batch's next step starts when its own last one is done);
                                     a step's device results are then complete after orbx_sequences_join / orbx_sequences_step_end */
@@ -346,6 +347,10 @@ typedef struct {                 /* host pointers, filled when orbx_sequences_st
     int32_t *match;              /* [n_sequences][capacity]   CurrentFrame.mvpMapPoints as indices of last-frame keypoints, -1 = none */
     int32_t *nmatches;           /* [n_sequences]             the return value of SearchByProjection (0 at a sequence's first step) */
     float *u_right, *depth;      /* [n_sequences][capacity]   mvuRight / mvDepth of the left image (stereo; may be NULL) */
+    double *pose;                /* [n_sequences][7]          config pose: the optimised SE3Quat (quaternion x,y,z,w, translation); untouched at a
+                                                               sequence's first step (may be NULL) */
+    int32_t *n_inliers;          /* [n_sequences]             PoseOptimization's return value (may be NULL) */
+    uint8_t *outlier;            /* [n_sequences][capacity]   mvbOutlier (may be NULL) */
 } orbx_sequences_outputs;
 typedef struct orbx_sequences orbx_sequences;
 orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_sequences_config *cfg);
@@ -375,9 +380,14 @@ typedef struct {
     const orbx_keypoint *kps; const uint8_t *desc; const int32_t *counts;      /* [n_images][capacity] ... */
     const int32_t *match, *nmatches; const float *u_right, *depth;             /* [n_sequences][capacity] ... */
     const orbx_frame_match_job *jobs;                                          /* [n_sequences], the jobs of the last projection search */
+    const double *pose; const int32_t *n_inliers; const uint8_t *outlier;      /* config pose */
     void *stream;
 } orbx_sequences_device;
 orbx_status orbx_sequences_device_view(const orbx_sequences *h, orbx_sequences_device *view);
+/* replaces the poses the handle keeps of the frames of the last step (it keeps the Tcw that step was given): a caller that optimises
+ * poses (config pose, or its own PoseOptimization) hands the optimised Tcw back before the next step, so that the last frame's points
+ * are unprojected with them, like Tracking's mLastFrame.  [n_sequences][12] */
+orbx_status orbx_sequences_set_last_poses(orbx_sequences *h, const float *Tcw_last);
 /* n_sub > 1: makes `stream` wait for every sub-batch's last step (a no-op for n_sub <= 1, where steps run on the caller's stream) */
 orbx_status orbx_sequences_join(orbx_sequences *h, void *stream);
 int orbx_sequences_last_launches(const orbx_sequences *h);

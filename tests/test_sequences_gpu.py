@@ -58,12 +58,16 @@ def test_steps_match_the_oracle_chain(stereo, n_sub):
     w, h, ns, steps = 640, 480, 3, 4
     K = synth.TUM1_K
     worlds = [synth.stereo_world(s) for s in range(2)]
-    seq = Sequences(ns, w, h, K, stereo=stereo, th=7.0, mono=False, const_depth=0.0 if stereo else 4.0, n_sub=n_sub)
+    sf = synth.scale_factors(8)
+    seq = Sequences(ns, w, h, K, stereo=stereo, th=7.0, mono=False, const_depth=0.0 if stereo else 4.0, n_sub=n_sub, pose=True)
+    is2 = (f32(1.0) / (sf * sf)).astype(f32)
+    n_pose = 0
     cap = seq.capacity
     oex = [O.Extractor(1000, 1.2, 8, 20, 7) for _ in range(2)]
     sf = synth.scale_factors(8)
     last = [None] * ns
     total = 0
+    rng = np.random.default_rng(5)
     for t in range(steps):
         imgs, poses = [], []
         for q in range(ns):
@@ -72,7 +76,8 @@ def test_steps_match_the_oracle_chain(stereo, n_sub):
             imgs.append(wd.render(tx, ty, yaw))
             if stereo:
                 imgs.append(wd.render(tx, ty, yaw, right=True))
-            poses.append(pose_of(tx, ty, yaw))
+            # the pose the step is given = the motion-model prediction: the true pose off by ~5 mm / 0.1 deg
+            poses.append(pose_of(tx + rng.normal(0, 0.005), ty + rng.normal(0, 0.005), yaw + np.deg2rad(rng.normal(0, 0.1))))
         out = seq.step(np.stack(imgs), np.stack([p[:3] for p in poses]))
         per = 2 if stereo else 1
         for q in range(ns):
@@ -101,8 +106,20 @@ def test_steps_match_the_oracle_chain(stereo, n_sub):
                 nref, mref = O.search_by_projection_frame(cur, pts, ld, poses[q][:3, :3], poses[q][:3, 3], fwd, bwd, 7.0, True)
                 assert out["nmatches"][q] == nref and np.array_equal(out["match"][q, :len(kl)], mref) and (out["match"][q, len(kl):] == -1).all()
                 total += nref
+                # Optimizer::PoseOptimization from that match array, starting at the pose the search projected with
+                m = np.nonzero(mref >= 0)[0]
+                prob = dict(Xw=np.stack([pts["x"], pts["y"], pts["z"]], 1)[mref[m]].astype(np.float64),
+                            obs=np.stack([kl["x"][m], kl["y"][m], ur[m] if ur is not None else np.full(len(m), -1, f32)], 1).astype(np.float64),
+                            inv_sigma2=is2[kl["octave"][m]], pose=O.to_se3quat(np.vstack([poses[q][:3], [0, 0, 0, 1]])), K=K[:5])
+                pref = O.pose_optimize(prob)
+                assert out["n_inliers"][q] == pref["n_inliers"] and np.array_equal(out["outlier"][q][m], pref["outlier"])
+                assert not out["outlier"][q][:len(mref)][mref < 0].any() and not out["outlier"][q][len(mref):].any()
+                upd = np.linalg.norm(pref["pose"] - prob["pose"])
+                assert np.linalg.norm(out["pose"][q] - pref["pose"]) <= 1e-4 * upd + 1e-7
+                n_pose += 1
             last[q] = (kl.copy(), dl.copy(), depth.copy(), poses[q])
-    assert total > 150 * ns * (steps - 1) * (0.3 if stereo else 1.0), total
+    assert total > 100 * ns * (steps - 1) * (0.3 if stereo else 1.0), total
+    assert n_pose == ns * (steps - 1)
     seq.reset()
     out = seq.step(np.stack(imgs), np.stack([p[:3] for p in poses]))
     assert (out["nmatches"] == 0).all()
