@@ -219,6 +219,56 @@ __global__ void __launch_bounds__(K2_THREADS) k2_pairs(LbaDev D, double lambda, 
     D.part[(size_t)ch * 42 + lane] = mine;
 }
 
+
+// The tensor-core form of k2_pairs, kept for the measurement BASELINE.json's north star asks for (LocalBA): for a pose-pair
+// block the sum over shared landmarks of (B_i D^-1) B_j^T is a 6 x K by K x 6 product with K = 3 per landmark, issued here as one
+// mma.sync.aligned.m8n8k4.f64 (DMMA) per (edge, edge) pair: rows = the six pose-i coordinates (two idle), columns = the six pose-j
+// coordinates, k = the landmark's three coordinates; the fourth k slot carries D^-1 b_l against a unit column, so the coefficient
+// vector B_i D^-1 b_l accumulates in column 6 of the same fragment.  A warp walks its chunk pair by pair with the 8 x 8 accumulator in
+// registers, so the 42 warp-shuffle reductions of the scalar kernel disappear -- but each DMMA carries 108 useful multiply-adds and
+// needs seven loads per lane to feed it, and B200's f64 tensor rate equals its f64 FMA rate.  Needs D^-1 precomputed (k2_hpp_final_dinv).
+__global__ void __launch_bounds__(K2_THREADS) k2_pairs_mma(LbaDev D, int nb_pairs) {
+    if ((int)blockIdx.x >= nb_pairs) {      // the remaining blocks: H_pp / b_p from the keyframe chunk partials
+        const int i = (blockIdx.x - nb_pairs) * K2_THREADS + threadIdx.x;
+        if (i < 27 * D.np) {
+            const int p = i / 27, c = i - 27 * p;
+            double v = 0;
+            for (int ch = D.kf_cstart[p]; ch < D.kf_cstart[p + 1]; ch++) v += D.hppart[(size_t)ch * 27 + c];
+            D.Hpp[i] = v;
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31, ch = blockIdx.x * (K2_THREADS / 32) + (threadIdx.x >> 5);
+    if (ch >= D.n_pchunks) return;
+    const int4 cd = D.pchunk[ch];
+    const int ra = lane >> 2, ka = lane & 3;               // A fragment: row ra (pose-i coordinate), k = ka
+    const int kb = lane & 3, nb = lane >> 2;               // B fragment: k = kb, column nb (pose-j coordinate)
+    // D^-1 is stored as its six distinct entries (00 01 02 11 12 22) followed by D^-1 b_l: entry (m, ka) of the 3 x 4 matrix [D^-1 | D^-1 b_l]
+    const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    const int d0 = ka < 3 ? sym[0][ka] : 6, d1 = ka < 3 ? sym[1][ka] : 7, d2 = ka < 3 ? sym[2][ka] : 8;
+    const double unit = (kb == 3 && nb == 6 && cd.w) ? 1.0 : 0.0;
+    double c0 = 0, c1 = 0;
+    for (int q = 0; q < cd.z; q++) {
+        const int4 pe = D.pairs[cd.y + q];
+        if (D.level1[pe.x] || D.level1[pe.y]) continue;
+        double a = 0, b = unit;
+        if (ra < 6) {
+            const double *B1 = D.Hpl + 18 * (size_t)pe.x + 3 * ra;
+            const double *Di = D.dinv + 10 * (size_t)pe.z;
+            a = B1[0] * Di[d0] + B1[1] * Di[d1] + B1[2] * Di[d2];
+        }
+        if (kb < 3 && nb < 6) b = D.Hpl[18 * (size_t)pe.y + 3 * nb + kb];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    }
+    // C fragment: lane holds C[ra][2 * (lane & 3)] and the next column; columns 0..5 = the block, column 6 = the coefficients
+    const int col = 2 * (lane & 3);
+    double *out = D.part + (size_t)ch * 42;
+    if (ra < 6) {
+        if (col < 6) { out[6 * ra + col] = c0; out[6 * ra + col + 1] = c1; }
+        else out[36 + ra] = c0;
+    }
+}
+
 // H_schur (upper block triangle of the n x n row-major matrix, the rest zero) and b_schur
 __global__ void __launch_bounds__(K2_THREADS) k2_final(LbaDev D, double lambda) {
     const int np = D.np, n = D.n, nblk = np * (np + 1) / 2;
@@ -266,7 +316,13 @@ orbx_status orbx_lba_chunk_linearize(const LbaDev &D, int robust, int build, int
 // BlockSolver::solve up to the linear solve (also finishes H_pp / b_p from the partials of the last build)
 orbx_status orbx_lba_chunk_schur(const LbaDev &D, double lambda, cudaStream_t s, int *launches) {
     const int nb_pairs = D.n_pchunks > 0 ? k2_blocks((long long)D.n_pchunks * 32) : 0;
-    k2_pairs<<<nb_pairs + k2_blocks((long long)27 * D.np), K2_THREADS, 0, s>>>(D, lambda, nb_pairs);
+    static const bool use_dmma = getenv("ORBX_LBA_DMMA") != nullptr;      // measurement only: the tensor-core form is slower
+    if (use_dmma) {
+        k2_hpp_final_dinv<<<k2_blocks(D.n_pts), K2_THREADS, 0, s>>>(D, lambda, 0, 1);
+        k2_pairs_mma<<<nb_pairs + k2_blocks((long long)27 * D.np), K2_THREADS, 0, s>>>(D, nb_pairs);
+        *launches += 1;
+    } else
+        k2_pairs<<<nb_pairs + k2_blocks((long long)27 * D.np), K2_THREADS, 0, s>>>(D, lambda, nb_pairs);
     k2_final<<<k2_blocks((long long)D.n * D.n > D.n ? (long long)D.n * D.n : D.n), K2_THREADS, 0, s>>>(D, lambda);
     *launches += 2;
     ORBX_CUDA(cudaGetLastError());

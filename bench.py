@@ -1088,6 +1088,15 @@ def main():
                "schur_build_us": 1e3 * ms_build / 50, "kernel_launches_per_window": launches_lba,
                "api": "orbx_lba_solve_host (host buffers in and out, synchronous)",
                "schur_build": "residuals + Jacobians + quadratic form + Schur complement of one Levenberg trial, device time (CUDA events)"}
+        # one Levenberg trial's system build moves ~2.59 MB (inputs + Hschur + bschur + D^-1 + Hpl + b_l) and does ~14 MFLOP (f64)
+        pk, pk_src = peaks()
+        lba["roofline"] = {"bound": "latency", "kernel": "Schur build of one Levenberg trial (k2_build + k2_pairs + k2_final)",
+                           "algorithmic_bytes": 2.59e6, "achieved": 2.59e6 / (ms_build / 50 * 1e-3) / 1e9, "unit": "GB/s", "peak": pk,
+                           "frac": 2.59e6 / (ms_build / 50 * 1e-3) / 1e9 / pk, "peak_source": pk_src,
+                           "f64_tflops": 14e6 / (ms_build / 50 * 1e-3) / 1e12,
+                           "note": "neither HBM- nor FMA-bound: three ~10 us launches at 9-12 % occupancy, a chain of dependent L2 round trips; "
+                                   "the tensor-core (DMMA) form of the pair accumulation was built and measured 2.8x slower "
+                                   "(profiles/r2_n_lba_dmma.txt)"}
         lba["batched"] = None      # filled below from every rank's share
         if not args.no_cpu:
             from oracle import oracle_py as O
