@@ -606,6 +606,50 @@ def bench_single_stream(local_rank, seq, imgs, n_frames, reps=6):
     return res
 
 
+def bench_c4(local_rank, with_cpu, n_frames=2000):
+    """BASELINE.json config 4: a TUM-RGBD-shaped sequence (640x480, 2000 frames) through the Tracking + LocalMapping call mix on a live map
+    (tools/replay_c4.py): per frame extract x2, ComputeStereoMatches, SearchByProjection(Cur, Last), PoseOptimization, isInFrustum over
+    the local map, SearchByProjection(Frame, local map points), PoseOptimization; every 10th frame a keyframe: new map points, vocabulary
+    transform, SearchForTriangulation against up to 10 earlier keyframes, LocalBundleAdjustment over the last 10 keyframes.  Single
+    stream, batch 1, host entry points; the numpy map bookkeeping between the calls is inside the wall time."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import replay_c4
+    tree = replay_c4.make_vocabulary()
+    seq = replay_c4.LoopSequence(seed=1, n_poses=40)
+    for t in range(40):
+        seq.images(t)                                     # rendering is not part of the measurement
+    gpu = replay_c4.GpuBackend(tree, device=local_rank)
+    rp = replay_c4.Replay(gpu, seq, kf_every=10)
+    for t in range(20):                                   # warm-up (two keyframes)
+        rp.step(t)
+    for k in gpu.seconds:
+        gpu.seconds[k] = 0.0
+    t0 = time.perf_counter()
+    for t in range(20, 20 + n_frames):
+        rp.step(t)
+    dt = time.perf_counter() - t0
+    out = {"config": "%d frames of a 640x480 stereo sequence (camera moving there and back over 40 rendered views, 2 cm per frame), 1000 features "
+                     "per image, a keyframe every 10th frame; batch 1, host entry points" % n_frames,
+           "frames_per_s": n_frames / dt, "ms_per_frame": 1e3 * dt / n_frames, "realtime_factor_at_30fps": n_frames / dt / 30.0,
+           "ms_per_frame_by_call": {k: 1e3 * v / n_frames for k, v in gpu.seconds.items()},
+           "ms_per_frame_in_library_calls": 1e3 * sum(gpu.seconds.values()) / n_frames}
+    out.update(rp.summary())
+    out["api"] = ("orbx_extractor_run_host x2, orbx_stereo_matches_extractors_host, orbx_match_projection_frame_host, orbx_pose_optimize_host x2, "
+                  "orbx_frustum_host, orbx_match_projection_points_host; per keyframe orbx_vocabulary_transform_host, orbx_match_buckets_host "
+                  "(SearchForTriangulation) x <= 10, orbx_lba_solve_host")
+    gpu.close()
+    if with_cpu:
+        orc = replay_c4.OracleBackend(tree)
+        rq = replay_c4.Replay(orc, seq, kf_every=10)
+        t0 = time.perf_counter()
+        n_cpu = 41
+        for t in range(n_cpu):
+            rq.step(t)
+        out["cpu_frames_per_s"] = n_cpu / (time.perf_counter() - t0)
+        out["cpu"] = "the same replay on the C oracle, 1 thread, %d frames (5 keyframes)" % n_cpu
+    return out
+
+
 def bench_c5(local_rank, rank, world, n_seq_total=64, steps=40, w=1241, h=376, nfeat=2000):
     """BASELINE.json config 5: 64 independent KITTI-stereo-shaped sequences (1241x376, 2000 features; intrinsics of
     Examples/Stereo/KITTI00-02.yaml) sharded over the ranks, sequence s -> rank s mod N, through the per-frame stereo chain (extract L + R ->
@@ -1125,13 +1169,14 @@ def main():
     if default_workload and not args.extract_only:
         barrier()
         c5_local = bench_c5(local_rank, rank, world)
-    stereo = pose = bow = sequence = None
+    stereo = pose = bow = sequence = c4 = None
     if side_sections:
         with_cpu = not args.no_cpu and world == 1      # CPU legs are timed on rank 0 at N = 1 only
         stereo = bench_stereo(local_rank, with_cpu)
         pose = bench_pose(local_rank, with_cpu)
         bow = bench_bow(local_rank, with_cpu)
         sequence = bench_sequence(local_rank, with_cpu)
+        c4 = bench_c4(local_rank, with_cpu)
 
     # the only collectives of the run: max of the timers, all-gather of per-rank counters
     from orbx import shard
@@ -1204,6 +1249,7 @@ def main():
                                         "traffic": traffic_step}},
             "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage_ms.items()},
             "lba": lba,
+            "c4": c4,
             "c5": c5,
             "stereo": stereo,
             "pose": pose,

@@ -1,0 +1,67 @@
+"""Config C4: the Tracking + LocalMapping call mix on a live map -- extract x2, ComputeStereoMatches, SearchByProjection(Cur,
+Last), PoseOptimization, isInFrustum, SearchByProjection(Frame, local map points), vocabulary transform, SearchForTriangulation,
+LocalBundleAdjustment -- run on the CUDA mirrors (tools/replay_c4.py) and compared with the CPU oracle CALL BY CALL on the inputs the
+GPU run actually produced, plus the sanity check that the chain tracks and that LocalBA windows come out of the live map."""
+import os
+import sys
+from collections import Counter
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import replay_c4  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_call_mix_matches_oracle_call_by_call():
+    tree = replay_c4.make_vocabulary()
+    seq = replay_c4.LoopSequence(seed=0, n_poses=10)
+    gpu, orc = replay_c4.GpuBackend(tree), replay_c4.OracleBackend(tree)
+    rec = []
+    rp = replay_c4.Replay(gpu, seq, kf_every=3, record=rec)
+    n_frames = 16
+    for t in range(n_frames):
+        rp.step(t)
+    calls = Counter()
+    for name, inp, out in rec:
+        calls[name] += 1
+        if name == "extract":
+            kl, dl = orc.extract(0, inp[0]); kr, dr = orc.extract(1, inp[1])
+            assert out[0].tobytes() == kl.tobytes() and np.array_equal(out[1], dl) and out[2].tobytes() == kr.tobytes() and np.array_equal(out[3], dr)
+        elif name == "stereo":
+            ur, dp = orc.stereo(*inp, seq.K[4], seq.K[5])          # the oracle extractors still hold this frame's pyramids
+            assert out[0].tobytes() == ur.tobytes() and out[1].tobytes() == dp.tobytes()
+        elif name == "match":
+            cur, pts, ld, Tcw, fwd, bwd = inp
+            n, m = orc.match_last(cur, pts, ld, Tcw[:3, :3], Tcw[:3, 3], fwd, bwd, 7.0)
+            assert n == out[0] and np.array_equal(m, out[1]) and n > 150
+        elif name == "pose":
+            ref = orc.pose(inp)
+            assert np.array_equal(ref["outlier"], out["outlier"]) and ref["n_inliers"] == out["n_inliers"]
+            upd = np.linalg.norm((out["pose"] - inp["pose"]) - (ref["pose"] - inp["pose"])) / max(np.linalg.norm(ref["pose"] - inp["pose"]), 1e-9)
+            assert upd < 1e-4 or np.linalg.norm(out["pose"] - ref["pose"]) < 1e-7, upd
+        elif name == "frustum":
+            ref = orc.frustum(*inp)
+            assert ref.tobytes() == out.tobytes() and out["in_view"].sum() > 50
+        elif name == "match_map":
+            n, m = orc.match_map(*inp, 3.0)
+            assert n == out[0] and np.array_equal(m, out[1])
+        elif name == "bow":
+            w, nd, wt = orc.bow(inp)
+            assert np.array_equal(w, out[0]) and np.array_equal(nd, out[1]) and np.array_equal(wt, out[2])
+        elif name == "triangulation":
+            A, B, F12, epi = inp
+            n, pairs = orc.triangulation(A, B, F12, epi, rp.sigma2, orc.scale)
+            assert n == out[0] and np.array_equal(pairs, out[1])
+        elif name == "lba":
+            ref = orc.lba(inp)
+            assert np.array_equal(ref["erase"], out["erase"])
+            rel = np.linalg.norm((out["pts"] - inp["pts"]) - (ref["pts"] - inp["pts"])) / np.linalg.norm(ref["pts"] - inp["pts"])
+            assert rel < 1e-4, rel
+    s = rp.summary()
+    assert calls["extract"] == n_frames and calls["match"] == n_frames - 1 and calls["match_map"] == n_frames - 1
+    assert calls["bow"] == s["keyframes"] == 6 and calls["triangulation"] >= 3 and calls["lba"] >= 3
+    assert s["a11_matches_per_frame"] > 100 and s["max_position_error_m"] < 0.03, s
+    gpu.close()
