@@ -5,24 +5,13 @@
 // of the vocabulary, created once from the file System.cc loads.
 #include "Frame.h"
 
-#include <orbx.h>
-
-#include <stdexcept>
+#include "orbx_adapter.h"
 
 namespace ORB_SLAM2
 {
 
 orbx_extractor* orbxHandle(const ORBextractor* e);
-orbx_vocabulary* orbxVocabulary(const ORBVocabulary* voc);
-
-namespace
-{
-void check(orbx_status s)
-{
-    if (s != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-}
-} // namespace
+bool orbxVocabularyTransform(const ORBVocabulary* voc, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight);
 
 // replaces Frame.cc:495-669: both pyramids are read where the two extractors left them on the device
 void Frame::ComputeStereoMatches()
@@ -30,13 +19,20 @@ void Frame::ComputeStereoMatches()
     mvuRight = std::vector<float>(N, -1.0f);
     mvDepth = std::vector<float>(N, -1.0f);
     thread_local orbx_stereo* st = nullptr;
-    if (!st)
-        check(orbx_stereo_create(&st, 8192, 1, 0));
+    if (!st && orbxFailed(orbx_stereo_create(&st, 8192, 1, orbxDevice()), "orbx_stereo_create"))
+    {
+        st = nullptr;
+        return;                                            // no depths: the frame is tracked as monocular observations
+    }
     int32_t kept = 0;
     // mvKeys / mDescriptors and their right counterparts are exactly what the two extractors returned for this frame
     // (Frame.cc:103-108), so the device reads them where the extractors left them
-    check(orbx_stereo_matches_extractors_host(st, orbxHandle(mpORBextractorLeft), 0, orbxHandle(mpORBextractorRight), 0, N, mbf, mb,
-                                              mvuRight.data(), mvDepth.data(), &kept));
+    if (orbxFailed(orbx_stereo_matches_extractors_host(st, orbxHandle(mpORBextractorLeft), 0, orbxHandle(mpORBextractorRight), 0, N, mbf, mb,
+                                                       mvuRight.data(), mvDepth.data(), &kept), "Frame::ComputeStereoMatches"))
+    {
+        mvuRight.assign(N, -1.0f);
+        mvDepth.assign(N, -1.0f);
+    }
 }
 
 // replaces Frame.cc:286-293: the tree descent of every descriptor runs on the device, the map bookkeeping of
@@ -47,7 +43,8 @@ void Frame::ComputeBoW()
         return;
     std::vector<int32_t> word(N), node(N);
     std::vector<double> weight(N);
-    check(orbx_vocabulary_transform_host(orbxVocabulary(mpORBvocabulary), mDescriptors.data, N, 4, word.data(), node.data(), weight.data()));
+    if (!orbxVocabularyTransform(mpORBvocabulary, mDescriptors.data, N, 4, word.data(), node.data(), weight.data()))
+        return;                                            // empty BowVector / FeatureVector, like a frame without features
     for (int i = 0; i < N; i++)
         if (weight[i] > 0)
         {

@@ -9,10 +9,9 @@
 // is empty and inline in the header), so entries are never removed.
 #include "ORBextractor.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
 #include <mutex>
-#include <stdexcept>
 #include <unordered_map>
 
 namespace ORB_SLAM2
@@ -33,11 +32,6 @@ orbx_extractor* handleOf(const ORBextractor* self)
     return it == gTable.end() ? nullptr : it->second;
 }
 
-void check(orbx_status s)
-{
-    if (s != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-}
 } // namespace
 
 // replaces ORBextractor::ORBextractor, src/ORBextractor.cc:410-470
@@ -45,7 +39,9 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST)
 {
     orbx_extractor* h = nullptr;
-    check(orbx_extractor_create(&h, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, kMaxWidth, kMaxHeight, 1, 0));
+    if (orbxFailed(orbx_extractor_create(&h, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, kMaxWidth, kMaxHeight, 1, orbxDevice()),
+                   "orbx_extractor_create"))
+        h = nullptr;                                      // operator() then returns no keypoints
     {
         std::lock_guard<std::mutex> lock(gTableMutex);
         gTable[this] = h;
@@ -55,8 +51,13 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     mvLevelSigma2.resize(nlevels);
     mvInvLevelSigma2.resize(nlevels);
     mnFeaturesPerLevel.resize(nlevels);
-    check(orbx_extractor_tables(h, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
-                                mnFeaturesPerLevel.data()));
+    if (!h || orbxFailed(orbx_extractor_tables(h, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                                               mnFeaturesPerLevel.data()), "orbx_extractor_tables"))
+    {   // the scale tables of ORBextractor.cc:417-431, so that Frame's copies of them stay meaningful
+        mvScaleFactor[0] = 1.0f; mvLevelSigma2[0] = 1.0f;
+        for (int i = 1; i < nlevels; i++) { mvScaleFactor[i] = mvScaleFactor[i - 1] * scaleFactor; mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i]; }
+        for (int i = 0; i < nlevels; i++) { mvInvScaleFactor[i] = 1.0f / mvScaleFactor[i]; mvInvLevelSigma2[i] = 1.0f / mvLevelSigma2[i]; }
+    }
     mvImagePyramid.resize(nlevels);
     // `pattern` and `umax` (ORBextractor.cc:448-469) live in the device library; nothing on the host reads them
 }
@@ -71,14 +72,21 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
     assert(image.type() == CV_8UC1);                      // :1049
 
     orbx_extractor* h = handleOf(this);
+    if (!h)
+    {
+        _keypoints.clear();
+        _descriptors.release();
+        return;
+    }
     static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint is the 28-byte record of orbx_keypoint");
     const int cap = orbx_extractor_capacity(h);
     _keypoints.resize(cap);
     cv::Mat desc(cap, 32, CV_8U);
     const uint8_t* img = image.data;
     int32_t n = 0;
-    check(orbx_extractor_run_host(h, &img, 1, image.cols, image.rows, (int)image.step,
-                                  reinterpret_cast<orbx_keypoint*>(_keypoints.data()), desc.data, &n));
+    if (orbxFailed(orbx_extractor_run_host(h, &img, 1, image.cols, image.rows, (int)image.step, reinterpret_cast<orbx_keypoint*>(_keypoints.data()),
+                                           desc.data, &n), "ORBextractor::operator()"))
+        n = 0;
     _keypoints.resize(n);
     if (n == 0)
         _descriptors.release();                           // :1064-1065
@@ -92,9 +100,11 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
     {
         int w = 0, hgt = 0, pitch = 0;
         const uint8_t* d = nullptr;
-        check(orbx_extractor_pyramid(h, 0, l, &d, &w, &hgt, &pitch));
+        if (orbxFailed(orbx_extractor_pyramid(h, 0, l, &d, &w, &hgt, &pitch), "orbx_extractor_pyramid"))
+            break;
         mvImagePyramid[l].create(hgt, w, CV_8U);
-        check(orbx_extractor_pyramid_host(h, 0, l, 0, mvImagePyramid[l].data, (int)mvImagePyramid[l].step));
+        if (orbxFailed(orbx_extractor_pyramid_host(h, 0, l, 0, mvImagePyramid[l].data, (int)mvImagePyramid[l].step), "orbx_extractor_pyramid_host"))
+            break;
     }
 #endif
 }

@@ -3,26 +3,17 @@
 // (these definitions removed from / guarded in the reference's src/ORBmatcher.cc).
 #include "ORBmatcher.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
-#include <stdexcept>
+#include <algorithm>
 
 using namespace std;
 
 namespace ORB_SLAM2
 {
 
-orbx_matcher* orbxMatcherOfThisThread();      // ORBmatcher_orbx.cc: one device scratch per calling thread
-
 namespace
 {
-orbx_matcher* matcherOfThisThread() { return orbxMatcherOfThisThread(); }
-
-void check(orbx_status s)
-{
-    if (s != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-}
 
 // a DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>) as ascending node ids + CSR lists
 struct FeatCsr
@@ -78,7 +69,9 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPoi
     job.sigma2_b = F.mvLevelSigma2.data(); job.scale_b = F.mvScaleFactors.data(); job.nlevels = F.mnScaleLevels;
     std::vector<int32_t> matchKF(pKF->N > 0 ? pKF->N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_buckets_host(matcherOfThisThread(), &job, matchKF.data(), &nmatches));
+    orbx_matcher* m = orbxMatcherOfThisThread(std::max(job.a.n, job.b.n), std::max(job.a.n, job.b.n));
+    if (!m || orbxFailed(orbx_match_buckets_host(m, &job, matchKF.data(), &nmatches), "SearchByBoW(KeyFrame, Frame)"))
+        return 0;
     for (int i = 0; i < pKF->N; i++)
         if (matchKF[i] >= 0)
             vpMapPointMatches[matchKF[i]] = vpMapPointsKF[i];                    // :256
@@ -99,7 +92,9 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& v
     job.sigma2_b = pKF2->mvLevelSigma2.data(); job.scale_b = pKF2->mvScaleFactors.data(); job.nlevels = pKF2->mnScaleLevels;
     std::vector<int32_t> match12(pKF1->N > 0 ? pKF1->N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_buckets_host(matcherOfThisThread(), &job, match12.data(), &nmatches));
+    orbx_matcher* m = orbxMatcherOfThisThread(std::max(job.a.n, job.b.n), std::max(job.a.n, job.b.n));
+    if (!m || orbxFailed(orbx_match_buckets_host(m, &job, match12.data(), &nmatches), "SearchByBoW(KeyFrame, KeyFrame)"))
+        return 0;
     for (int i = 0; i < pKF1->N; i++)
         if (match12[i] >= 0)
             vpMatches12[i] = vpMapPoints2[match12[i]];                           // :610
@@ -135,8 +130,10 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     job.sigma2_b = pKF2->mvLevelSigma2.data(); job.scale_b = pKF2->mvScaleFactors.data(); job.nlevels = pKF2->mnScaleLevels;
     std::vector<int32_t> match12(pKF1->N > 0 ? pKF1->N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_buckets_host(matcherOfThisThread(), &job, match12.data(), &nmatches));
     vMatchedPairs.clear();
+    orbx_matcher* m = orbxMatcherOfThisThread(std::max(job.a.n, job.b.n), std::max(job.a.n, job.b.n));
+    if (!m || orbxFailed(orbx_match_buckets_host(m, &job, match12.data(), &nmatches), "SearchForTriangulation"))
+        return 0;
     vMatchedPairs.reserve(nmatches);
     for (int i = 0; i < pKF1->N; i++)                                            // :812-820
         if (match12[i] >= 0)
@@ -169,8 +166,10 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f
     static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "vbPrevMatched is passed as (x, y) float pairs");
     std::vector<int32_t> match12(F1.N > 0 ? F1.N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_initialization_host(matcherOfThisThread(), &v[0], &v[1], reinterpret_cast<const float*>(vbPrevMatched.data()), windowSize,
-                                         mfNNratio, mbCheckOrientation, match12.data(), &nmatches));
+    orbx_matcher* m = orbxMatcherOfThisThread(std::max(F1.N, F2.N), std::max(F1.N, F2.N));
+    if (!m || orbxFailed(orbx_match_initialization_host(m, &v[0], &v[1], reinterpret_cast<const float*>(vbPrevMatched.data()), windowSize,
+                                                        mfNNratio, mbCheckOrientation, match12.data(), &nmatches), "SearchForInitialization"))
+        nmatches = 0;                                                        // match12 stays all -1
     for (int i1 = 0; i1 < F1.N; i1++)
     {
         vnMatches12[i1] = match12[i1];

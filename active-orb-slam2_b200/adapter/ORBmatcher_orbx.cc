@@ -7,10 +7,10 @@
 // (table in INTEGRATION.md) and keep using the reference's code until they are moved over.
 #include "ORBmatcher.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
+#include <algorithm>
 #include <cmath>
-#include <stdexcept>
 
 using namespace std;
 
@@ -21,26 +21,30 @@ const int ORBmatcher::TH_HIGH = 100;
 const int ORBmatcher::TH_LOW = 50;
 const int ORBmatcher::HISTO_LENGTH = 30;
 
-// ORBmatcher objects are stack temporaries in the reference (one per call); the device scratch lives per calling thread and is
-// shared by the three adapter files
-orbx_matcher* orbxMatcherOfThisThread()
+orbx_matcher* orbxMatcherOfThisThread(int nKeypoints, int nPoints)
 {
-    thread_local orbx_matcher* m = nullptr;
-    if (!m && orbx_matcher_create(&m, 8192, 8192, 1, 0) != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-    return m;
+    struct Scratch
+    {
+        orbx_matcher* m = nullptr;
+        int kp = 0, pts = 0;
+        ~Scratch() { if (m) orbx_matcher_destroy(m); }
+    };
+    thread_local Scratch sc;
+    if (sc.m && nKeypoints <= sc.kp && nPoints <= sc.pts)
+        return sc.m;
+    if (sc.m) { orbx_matcher_destroy(sc.m); sc.m = nullptr; }
+    sc.kp = std::max(8192, nKeypoints + nKeypoints / 2);
+    sc.pts = std::max(8192, nPoints + nPoints / 2);
+    if (orbxFailed(orbx_matcher_create(&sc.m, sc.kp, sc.pts, 1, orbxDevice()), "orbx_matcher_create"))
+    {
+        sc.m = nullptr;
+        sc.kp = sc.pts = 0;
+    }
+    return sc.m;
 }
 
 namespace
 {
-orbx_matcher* matcherOfThisThread() { return orbxMatcherOfThisThread(); }
-
-void check(orbx_status s)
-{
-    if (s != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-}
-
 // the Frame members the matchers read, as the POD view of include/orbx.h; `claimed` must outlive the call
 orbx_frame_view viewOf(const Frame& F, std::vector<uint8_t>& claimed, bool byObservations)
 {
@@ -77,35 +81,42 @@ int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b)
 // replaces ORBmatcher.cc:45-129 (track the local map): the points were prepared by Frame::isInFrustum
 int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)
 {
-    const int n = (int)vpMapPoints.size();
-    std::vector<orbx_track_point> pts(n);
+    // only the points Frame::isInFrustum left in view take part (:53-57): they are packed, with an index back into vpMapPoints
+    const int nAll = (int)vpMapPoints.size();
+    std::vector<int> source;
+    source.reserve(nAll);
+    for (int i = 0; i < nAll; i++)
+        if (vpMapPoints[i]->mbTrackInView && !vpMapPoints[i]->isBad())
+            source.push_back(i);
+    const int n = (int)source.size();
+    std::vector<orbx_track_point> pts(n > 0 ? n : 1);
     std::vector<uint8_t> desc((size_t)32 * (n ? n : 1));
-    for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
     {
-        MapPoint* pMP = vpMapPoints[i];
-        orbx_track_point& t = pts[i];
+        MapPoint* pMP = vpMapPoints[source[j]];
+        orbx_track_point& t = pts[j];
         t = orbx_track_point();
-        if (!pMP->mbTrackInView || pMP->isBad())                                 // :53-57
-            continue;
         t.proj_x = pMP->mTrackProjX; t.proj_y = pMP->mTrackProjY; t.proj_xr = pMP->mTrackProjXR;
         t.view_cos = pMP->mTrackViewCos;
         t.level = pMP->mnTrackScaleLevel;
         t.in_view = 1;
         t.blocks = pMP->Observations() > 0;
         const cv::Mat d = pMP->GetDescriptor();
-        for (int k = 0; k < 32; k++) desc[(size_t)32 * i + k] = d.data[k];
+        for (int k = 0; k < 32; k++) desc[(size_t)32 * j + k] = d.data[k];
     }
     std::vector<uint8_t> claimed;
     const orbx_frame_view view = viewOf(F, claimed, true);
-    std::vector<int32_t> match(F.N, -1);
+    std::vector<int32_t> match(F.N > 0 ? F.N : 1, -1);
     int32_t nmatches = 0;
+    orbx_matcher* m = orbxMatcherOfThisThread(F.N, n);
     // th is multiplied by RadiusByViewingCos and the level's scale factor inside (:63-69); the caller's bFactor logic
     // (`if(bFactor) r*=th`) is th itself
-    check(orbx_match_projection_points_host(matcherOfThisThread(), &view, n, pts.data(), desc.data(), th, mfNNratio, match.data(),
-                                            &nmatches));
+    if (!m || orbxFailed(orbx_match_projection_points_host(m, &view, n, pts.data(), desc.data(), th, mfNNratio, match.data(), &nmatches),
+                         "SearchByProjection(Frame, MapPoints)"))
+        return 0;
     for (int k = 0; k < F.N; k++)
         if (match[k] >= 0)
-            F.mvpMapPoints[k] = vpMapPoints[match[k]];                           // :123
+            F.mvpMapPoints[k] = vpMapPoints[source[match[k]]];                   // :123
     return nmatches;
 }
 
@@ -148,10 +159,12 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     }
     std::vector<uint8_t> claimed;
     const orbx_frame_view view = viewOf(CurrentFrame, claimed, true);
-    std::vector<int32_t> match(CurrentFrame.N, -1);
+    std::vector<int32_t> match(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_projection_frame_host(matcherOfThisThread(), &view, n, pts.data(), desc.data(), Rcw, tcw, bForward, bBackward, th,
-                                           mbCheckOrientation, match.data(), &nmatches));
+    orbx_matcher* m = orbxMatcherOfThisThread(CurrentFrame.N, n);
+    if (!m || orbxFailed(orbx_match_projection_frame_host(m, &view, n, pts.data(), desc.data(), Rcw, tcw, bForward, bBackward, th,
+                                                          mbCheckOrientation, match.data(), &nmatches), "SearchByProjection(Cur, Last)"))
+        return 0;
     // write-back: entries the rotation check rejected were set by this very call and come back as -1 (:1456-1462)
     for (int k = 0; k < CurrentFrame.N; k++)
         if (match[k] >= 0)

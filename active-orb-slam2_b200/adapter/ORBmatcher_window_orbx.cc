@@ -11,28 +11,18 @@
 // include/ORBmatcher.h stays as it is; build like ORBmatcher_orbx.cc.
 #include "ORBmatcher.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
 #include <climits>
 #include <cmath>
-#include <stdexcept>
 
 using namespace std;
 
 namespace ORB_SLAM2
 {
 
-orbx_matcher* orbxMatcherOfThisThread();      // ORBmatcher_orbx.cc: one device scratch per calling thread
-
 namespace
 {
-orbx_matcher* matcherOfThisThread() { return orbxMatcherOfThisThread(); }
-
-void check(orbx_status s)
-{
-    if (s != ORBX_OK)
-        throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
-}
 
 // a KeyFrame as the window searches read it (KeyFrame::GetFeaturesInArea has no level filter, KeyFrame.cc:630-669)
 orbx_frame_view viewOf(const KeyFrame* pKF, const std::vector<uint8_t>& claimed)
@@ -80,8 +70,10 @@ std::vector<int32_t> search(const KeyFrame* pKF, const std::vector<uint8_t>& cla
         return best;
     const orbx_frame_view view = viewOf(pKF, claimed);
     int32_t accepted = 0;
-    check(orbx_match_window_host(matcherOfThisThread(), &view, n, c.pts.data(), c.desc.data(), flags, pKF->mvInvLevelSigma2.data(), maxDist,
-                                 best.data(), dist.data(), &accepted));
+    orbx_matcher* m = orbxMatcherOfThisThread(pKF->N, n);
+    if (!m || orbxFailed(orbx_match_window_host(m, &view, n, c.pts.data(), c.desc.data(), flags, pKF->mvInvLevelSigma2.data(), maxDist, best.data(),
+                                                dist.data(), &accepted), "window search (Fuse / SearchBySim3 / SearchByProjection(KeyFrame, Scw))"))
+        best.assign(best.size(), -1);                                        // nothing found: the callers then change nothing
     return best;
 }
 
@@ -367,8 +359,10 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set
     }
     std::vector<int32_t> match(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
     int32_t nmatches = 0;
-    check(orbx_match_projection_keyframe_host(matcherOfThisThread(), &view, n, pts.data(), desc.data(), R, t, th, ORBdist, mbCheckOrientation,
-                                              match.data(), &nmatches));
+    orbx_matcher* m = orbxMatcherOfThisThread(CurrentFrame.N, n);
+    if (!m || orbxFailed(orbx_match_projection_keyframe_host(m, &view, n, pts.data(), desc.data(), R, t, th, ORBdist, mbCheckOrientation, match.data(),
+                                                             &nmatches), "SearchByProjection(Frame, KeyFrame)"))
+        return 0;
     for (int k = 0; k < CurrentFrame.N; k++)
         if (match[k] >= 0)
             CurrentFrame.mvpMapPoints[k] = vpMPs[match[k]];

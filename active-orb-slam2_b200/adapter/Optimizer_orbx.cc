@@ -18,10 +18,9 @@
 
 #include "Converter.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
-#include <cstdio>
-#include <cstdlib>
+#include <algorithm>
 #include <list>
 #include <mutex>
 #include <vector>
@@ -33,20 +32,6 @@ namespace ORB_SLAM2
 
 namespace
 {
-int deviceOfThisProcess()
-{
-    const char* e = std::getenv("ORBX_DEVICE");
-    return e ? std::atoi(e) : 0;
-}
-
-bool failed(orbx_status s, const char* where)
-{
-    if (s == ORBX_OK)
-        return false;
-    std::fprintf(stderr, "orbx: %s failed (%d): %s\n", where, (int)s, orbx_last_error());
-    return true;
-}
-
 // LocalBundleAdjustment runs on the LocalMapping thread, PoseOptimization on the Tracking thread: one handle per calling thread,
 // sized by the largest window / frame seen so far (the reference allocates a fresh g2o graph per call)
 struct LbaHandle
@@ -60,7 +45,7 @@ struct LbaHandle
             return h;
         if (h) { orbx_lba_destroy(h); h = nullptr; }
         kf = std::max(64, nKF + nKF / 2); pts = std::max(8192, nPts + nPts / 2); edges = std::max(65536, nEdges + nEdges / 2);
-        if (failed(orbx_lba_create(&h, kf, pts, edges, deviceOfThisProcess()), "orbx_lba_create"))
+        if (orbxFailed(orbx_lba_create(&h, kf, pts, edges, orbxDevice()), "orbx_lba_create"))
         {
             h = nullptr;
             kf = pts = edges = 0;
@@ -79,7 +64,7 @@ struct PoseHandle
             return h;
         if (h) { orbx_pose_destroy(h); h = nullptr; }
         obs = std::max(8192, nObs + nObs / 2);
-        if (failed(orbx_pose_create(&h, obs, 1, deviceOfThisProcess()), "orbx_pose_create"))
+        if (orbxFailed(orbx_pose_create(&h, obs, 1, orbxDevice()), "orbx_pose_create"))
         {
             h = nullptr;
             obs = 0;
@@ -224,7 +209,7 @@ void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap
     orbx_lba_result R = orbx_lba_result();
     R.kf_pose = kfOut.data(); R.pts = ptOut.data(); R.erase = erase.data();
     // optimize(5) with Huber kernels, classification, optimize(10) without them, final classification (:659-735)
-    if (failed(orbx_lba_solve_host(h, &P, 5, 10, &R), "orbx_lba_solve_host") || R.stopped)
+    if (orbxFailed(orbx_lba_solve_host(h, &P, 5, 10, &R), "orbx_lba_solve_host") || R.stopped)
         return;
 
     // the erase list in the reference's order: monocular edges first, then stereo edges (:709-743)
@@ -295,7 +280,7 @@ int Optimizer::PoseOptimization(Frame* pFrame)
     orbx_pose_result R = orbx_pose_result();
     R.outlier = outlier.data();
     // four rounds of optimize(10) with re-classification (:358-421)
-    if (failed(orbx_pose_optimize_host(h, &P, 1, &R), "orbx_pose_optimize_host"))
+    if (orbxFailed(orbx_pose_optimize_host(h, &P, 1, &R), "orbx_pose_optimize_host"))
         return 0;
     for (int k = 0; k < nInitialCorrespondences; k++)
         pFrame->mvbOutlier[index[k]] = outlier[k] != 0;

@@ -4,11 +4,10 @@
 // derived accessor.  One device copy per vocabulary object, made on first use (System.cc loads the vocabulary once).
 #include "ORBVocabulary.h"
 
-#include <orbx.h>
+#include "orbx_adapter.h"
 
 #include <map>
 #include <mutex>
-#include <stdexcept>
 #include <vector>
 
 namespace ORB_SLAM2
@@ -39,9 +38,9 @@ struct VocabularyAccess : public ORBVocabulary
         }
         childStart[n] = (int32_t)children.size();
         orbx_vocabulary* h = nullptr;
-        if (orbx_vocabulary_create(&h, n, childStart.data(), children.data(), desc.data(), weight.data(), wordId.data(), m_L, 8192, 0) !=
-            ORBX_OK)
-            throw std::runtime_error(std::string("orbx: ") + orbx_last_error());
+        if (orbxFailed(orbx_vocabulary_create(&h, n, childStart.data(), children.data(), desc.data(), weight.data(), wordId.data(), m_L, 8192,
+                                              orbxDevice()), "orbx_vocabulary_create"))
+            return nullptr;
         return h;
     }
 };
@@ -59,6 +58,19 @@ orbx_vocabulary* orbxVocabulary(const ORBVocabulary* voc)
     orbx_vocabulary* h = static_cast<const VocabularyAccess*>(voc)->toDevice();
     gDevice[voc] = h;
     return h;
+}
+
+// orbx_vocabulary_transform_host stages through the handle's own buffers and stream (include/orbx.h: handles are not re-entrant), and
+// one device copy serves every caller of a vocabulary object: Frame::ComputeBoW on the Tracking thread, KeyFrame::ComputeBoW on the
+// LocalMapping thread once it is moved over.  The calls are serialised here; the tree arrays are shared and read-only.
+bool orbxVocabularyTransform(const ORBVocabulary* voc, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight)
+{
+    orbx_vocabulary* h = orbxVocabulary(voc);
+    if (!h)
+        return false;
+    static std::mutex gTransformMutex;
+    std::lock_guard<std::mutex> lock(gTransformMutex);
+    return !orbxFailed(orbx_vocabulary_transform_host(h, desc, n, levelsup, word, node, weight), "orbx_vocabulary_transform_host");
 }
 
 } // namespace ORB_SLAM2

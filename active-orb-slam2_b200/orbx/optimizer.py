@@ -74,15 +74,17 @@ class Optimizer:
         return out
 
     def begin(self, prob, its1=5, its2=10):
-        """asynchronous LocalBundleAdjustment: enqueue the whole window on this handle's stream and return"""
-        self._pending = pack_problem(prob)
+        """asynchronous LocalBundleAdjustment: enqueue the whole window on this handle's stream and return.  prob: the problem dict,
+        or the (struct, keepalive) pair pack_problem(prob) returned (a caller that submits the same arrays again packs once)"""
+        self._pending = prob if isinstance(prob, tuple) else pack_problem(prob)
         check(self._L.orbx_lba_solve_begin(self._h, C.byref(self._pending[0]), its1, its2))
 
     def end(self):
         """wait for begin() and return the same dict as LocalBundleAdjustment()"""
         P, keep = self._pending
-        kf, pt = np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3))
-        chi2, erase = np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8)
+        if getattr(self, "_out", None) is None or self._out[0].shape[0] != P.n_kf or self._out[1].shape[0] != P.n_pts or len(self._out[2]) != max(P.n_edges, 1):
+            self._out = (np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3)), np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8))
+        kf, pt, chi2, erase = self._out                  # reused between calls of the same shape: the caller copies what it keeps
         R = LbaResult()
         R.kf_pose, R.pts, R.chi2, R.erase = kf.ctypes.data, pt.ctypes.data, chi2.ctypes.data, erase.ctypes.data
         check(self._L.orbx_lba_solve_end(self._h, C.byref(P), C.byref(R)))

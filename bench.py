@@ -781,7 +781,8 @@ def bench_lba_batched(local_rank, rank, NW=16, rounds=3):
     from orbx import synth
     from orbx.optimizer import Optimizer
     ops = [Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank) for _ in range(NW)]
-    probs = [synth.lba_problem(100 + NW * rank + i, n_kf=20, n_pts=3000, stereo=False, n_fixed=1) for i in range(NW)]
+    from orbx.optimizer import pack_problem
+    probs = [pack_problem(synth.lba_problem(100 + NW * rank + i, n_kf=20, n_pts=3000, stereo=False, n_fixed=1)) for i in range(NW)]   # packed once: the arrays do not change
     for o_, p_ in zip(ops, probs):
         o_.begin(p_)
     for o_ in ops:
