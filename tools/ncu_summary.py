@@ -3,7 +3,7 @@
 
   tools/ncu_summary.py launches <launches.csv>            -> per-kernel count / mean us / share of the step
   tools/ncu_summary.py full <report.ncu-rep or raw.csv>   -> per-launch table of the metrics DESIGN.md cites
-  tools/ncu_summary.py traffic <report.ncu-rep> [batch] [steps] -> JSON: dram bytes per launch (read + write) of every kernel of one step,
+  tools/ncu_summary.py traffic <metrics.csv> [batch] [steps] [what] -> JSON: dram bytes (read + write) per step and stage,
                                                               the file bench.py reads roofline.traffic from (profiles/r2_traffic.json)
 """
 import csv
@@ -63,36 +63,41 @@ STAGE_OF = {"k_pyr_level0": "pyramid", "k_pyr_resize": "pyramid", "k_pyr_chain":
             "k_describe": "describe", "k_match_frame": "match", "k_unproject_last": "match"}
 
 
-def traffic(path, batch=64, steps=None):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel (mean over the captured launches of that kernel), and per
-    stage of one step (a stage = its kernels x launches per step; the pyramid's launches are distinct levels, so they are summed over
-    one step's worth = captured launches / captured steps, taken from the count of k_fast launches)."""
+def _metric_log(path):
+    """rows of an `ncu --metrics ... --csv --log-file` capture -> {(launch id, kernel): {metric: value in bytes / us / count}}"""
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    H = rows[h]
+    ki, mi, vi, ui, ii = H.index("Kernel Name"), H.index("Metric Name"), H.index("Metric Value"), H.index("Metric Unit"), H.index("ID")
+    d = OrderedDict()
+    for r in rows[h + 1:]:
+        if len(r) > vi:
+            v = float(r[vi].replace(",", "")) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "ms": 1e3}.get(r[ui], 1)
+            d.setdefault((r[ii], r[ki].split("(")[0]), {})[r[mi]] = v
+    return d
+
+
+def traffic(path, batch=64, steps=2, what=""):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step and stage from a metrics capture that brackets `steps` whole steps
+    (bench.py --profile-steps N under ncu --profile-from-start off): the JSON bench.py reads roofline.traffic from."""
     import json
     import os
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
-    H, U = rows[0], rows[1]
-    ki, ri, wi = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
-
-    def to_bytes(v, unit):
-        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-
-    per = OrderedDict()
-    for r in rows[2:]:
-        name = r[ki].split("(")[0]
-        per.setdefault(name, []).append(to_bytes(r[ri], U[ri]) + to_bytes(r[wi], U[wi]))
-    steps = int(steps) if steps else max(len(per.get("k_fast", [1])), 1)      # the capture brackets whole steps (bench.py --profile-steps N)
+    d = _metric_log(path)
+    steps = int(steps)
     stages = {}
-    for name, v in per.items():
+    for (_, name), m in d.items():
         st = STAGE_OF.get(name)
         if st:
-            d = stages.setdefault(st, {"dram_bytes": 0.0, "launches_per_step": 0.0, "kernels": []})
-            d["dram_bytes"] += sum(v) / steps
-            d["launches_per_step"] += len(v) / steps
-            d["kernels"].append(name)
-    out = {"source": "profiles/%s (ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum per launch at batch %d, "
-                     "summed over a stage's launches of one step)" % (os.path.basename(path).replace(".ncu-rep", "_full.txt"), int(batch)),
-           "batch": int(batch), "captured_steps": steps, "kernels": stages, "step_dram_bytes": sum(d["dram_bytes"] for d in stages.values())}
+            a = stages.setdefault(st, {"dram_bytes": 0.0, "dram_read": 0.0, "dram_write": 0.0, "launches_per_step": 0.0, "time_us": 0.0, "kernels": []})
+            a["dram_read"] += m["dram__bytes_read.sum"] / steps
+            a["dram_write"] += m["dram__bytes_write.sum"] / steps
+            a["dram_bytes"] += (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / steps
+            a["launches_per_step"] += 1.0 / steps
+            a["time_us"] += m.get("gpu__time_duration.sum", 0.0) / steps
+            if name not in a["kernels"]:
+                a["kernels"].append(name)
+    out = {"source": "profiles/%s: %s" % (os.path.basename(path), what), "batch": int(batch), "captured_steps": steps, "kernels": stages,
+           "step_dram_bytes": sum(a["dram_bytes"] for a in stages.values())}
     print(json.dumps(out, indent=1))
 
 
