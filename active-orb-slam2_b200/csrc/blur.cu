@@ -30,12 +30,15 @@ k_blur(const uint8_t *__restrict__ pyr, size_t pyr_frame, uint8_t *__restrict__ 
     // padded-buffer position of the first input byte: column 19 + x0 - 3 (16-byte aligned because x0 % 64 == 0), row 19 + y0 - 3
     const uint8_t *src = pyr + (size_t)frame * pyr_frame + L.off;
     const int gx = ORBX_EDGE + t.x0 - 3, gy = ORBX_EDGE + t.y0 - 3;
-    for (int i = tid; i < BLUR_IN_H * BLUR_IN_WORDS; i += BLUR_THREADS) {
-        const int r = i / BLUR_IN_WORDS, c = i - r * BLUR_IN_WORDS;
-        uint32_t v = 0;
-        if (gy + r < ph && gx + 4 * c + 3 < pitch)
-            v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(gy + r) * pitch + gx) + c);
-        in[r * BLUR_IN_PITCH + c] = v;
+    // 38 rows x 72 bytes as 16-byte loads: the first input column 19 + x0 - 3 is 16-byte aligned (x0 % 64 == 0), the row pitch a
+    // multiple of 16, so a 16-byte group that starts inside a row lies inside it; 4.5 groups per row -> 5 (the last one half used)
+    if (tid < BLUR_IN_H * 5) {
+        const int r = tid / 5, c = tid - r * 5;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gy + r < ph && gx + 16 * c < pitch) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(gy + r) * pitch + gx) + c);
+        uint32_t *d = in + r * BLUR_IN_PITCH + 4 * c;
+        d[0] = v.x; d[1] = v.y;
+        if (c < 4) { d[2] = v.z; d[3] = v.w; }
     }
     __syncthreads();
     // rows: thread = (input row r, quarter qx of the 64 columns), 16 sums; lanes run over r
@@ -74,11 +77,12 @@ k_blur(const uint8_t *__restrict__ pyr, size_t pyr_frame, uint8_t *__restrict__ 
     }
     __syncthreads();
     uint8_t *dst = blur + (size_t)frame * blur_frame + L.boff;
-    for (int i = tid; i < ORBX_BLUR_TH * (ORBX_BLUR_TW / 4); i += BLUR_THREADS) {
-        const int y = i / (ORBX_BLUR_TW / 4), c4 = (i - y * (ORBX_BLUR_TW / 4)) * 4;
-        const int oy = t.y0 + y, ox = t.x0 + c4;
-        if (oy >= L.h || ox >= L.bpitch) continue;
-        *reinterpret_cast<uint32_t *>(dst + (size_t)oy * L.bpitch + ox) = *reinterpret_cast<const uint32_t *>(&ob[y][c4]);
+    // 32 rows x 64 bytes as 16-byte stores (the blurred level's pitch is a multiple of 16, x0 of 64)
+    if (tid < ORBX_BLUR_TH * (ORBX_BLUR_TW / 16)) {
+        const int y = tid >> 2, c16 = (tid & 3) * 16;
+        const int oy = t.y0 + y, ox = t.x0 + c16;
+        if (oy < L.h && ox < L.bpitch)
+            *reinterpret_cast<uint4 *>(dst + (size_t)oy * L.bpitch + ox) = *reinterpret_cast<const uint4 *>(&ob[y][c16]);
     }
 }
 

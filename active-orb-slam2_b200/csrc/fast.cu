@@ -25,9 +25,11 @@ __host__ __device__ inline int orbx_fast_out_words(int tp_max, int th_max) {
 __host__ __device__ inline int orbx_fast_list_entries(int tp_max, int th_max) {
     return (tp_max - 21) * (th_max - 6);
 }
-// the score plane holds detection pixels only: pitch tp - 16 (>= the widest detection row, a multiple of 16), th - 6 rows
+// the score plane holds detection pixels only: pitch tp - 16 (a multiple of 16, at least 5 more than the widest detection row), th - 6
+// rows, plus one zero row above and one below: with the zero spare columns at the end of every row, all eight neighbours of a detection
+// pixel can be read without a bounds test
 __host__ __device__ inline int orbx_fast_score_bytes(int tp_max, int th_max) {
-    return (tp_max - 16) * (th_max - 6);
+    return (tp_max - 16) * (th_max - 6 + 2);
 }
 
 // The ring is OpenCV's 16-pixel Bresenham circle, (dx,dy) = (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),
@@ -162,7 +164,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
                      ::"r"(smem_u32(tile)), "l"(tmap), "r"(gx0 - shift), "r"(ORBX_EDGE + (int)ck.y0), "r"(frame), "r"(mbar_a)
                      : "memory");
     }
-    for (int i = tid; i < (sp * (th - 6)) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
+    for (int i = tid; i < (sp * (th - 6 + 2)) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
     const int vw = tw - 6, vh = th - 6;                // detection region
     const int wcell = ck.wcell;
     for (int x = tid; x < vw; x += FAST_THREADS) sh.cellof[x] = (uint8_t)(x / wcell);
@@ -174,7 +176,7 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
                  ::"r"(mbar_a) : "memory");
     const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
-    uint8_t *s0 = score;                               // score of detection pixel (x,y) = s0[y*sp + x]
+    uint8_t *s0 = score + sp;                          // score of detection pixel (x,y) = s0[y*sp + x]; rows -1 and vh stay zero
 
     // words of a tile row that hold detection pixels, and the magic number that divides an item index by their count
     const int w_first = (shift + 3) >> 2, n_words = ((shift + 3 + vw - 1) >> 2) - w_first + 1;
@@ -268,20 +270,13 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
             const int cell = sh.cellof[x];
             const int cx0 = cell * wcell;                                   // first detection column of the cell
             const int cx1 = cell == ck.ncells - 1 ? vw : cx0 + wcell;      // one past the last
-            const bool l = x > cx0, r = x + 1 < cx1, u = y > 0, d = y + 1 < vh;
-            bool keep = true;
-            if (l) keep = keep && s > sq[-1];
-            if (r) keep = keep && s > sq[1];
-            if (u) {
-                keep = keep && s > sq[-sp];
-                if (l) keep = keep && s > sq[-sp - 1];
-                if (r) keep = keep && s > sq[-sp + 1];
-            }
-            if (d) {
-                keep = keep && s > sq[sp];
-                if (l) keep = keep && s > sq[sp - 1];
-                if (r) keep = keep && s > sq[sp + 1];
-            }
+            // neighbours outside the cell's detection region count as 0: above / below the plane has zero rows, past the row's end
+            // zero spare columns (which also serve x = 0 of the next row); only the cell's own left / right edge needs a test
+            const bool l = x > cx0, r = x + 1 < cx1;
+            const int lm = max(max((int)sq[-1], (int)sq[-sp - 1]), (int)sq[sp - 1]);
+            const int rm = max(max((int)sq[1], (int)sq[-sp + 1]), (int)sq[sp + 1]);
+            const int m = max(max((int)sq[-sp], (int)sq[sp]), max(l ? lm : 0, r ? rm : 0));
+            const bool keep = s > m;
             if (keep) {
                 atomicAdd(&sh.cnt[cell], 1);
                 const int o = atomicAdd(&sh.n_out, 1);

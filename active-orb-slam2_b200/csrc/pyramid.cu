@@ -66,12 +66,9 @@ __device__ __forceinline__ uint32_t resize_px(uint32_t coef, int b0, int b1, uin
 // ORB-SLAM's scale factors, also across the reflection points, because the window starts at the smallest position) each
 // source row costs three aligned 32-bit loads, two funnel shifts that bring bytes base .. base+7 into a register pair, and
 // one byte permute per pixel; otherwise bytes are loaded one by one.
-__global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel S, OrbxLevel L,
-                                                    const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols16) {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = id / cols16, g16 = id - py * cols16;
-    if (py >= L.ph) return;
-    uint8_t *frame = pyr + (size_t)blockIdx.z * pyr_frame;
+// one item = 16 consecutive bytes of padded row py of level L of one frame, from the interior of level S (see k_pyr_resize)
+__device__ __forceinline__ void pyr_resize_item(uint8_t *__restrict__ frame, const OrbxLevel &S, const OrbxLevel &L, const uint4 *__restrict__ rx,
+                                                const int2 *__restrict__ ry, int py, int g16) {
     const uint8_t *sint = frame + S.off + (size_t)ORBX_EDGE * S.pitch + ORBX_EDGE;  // interior origin of the source
     const int2 yy = __ldg(ry + py);
     const int sy0 = yy.x & 0xffff, sy1 = yy.x >> 16;
@@ -117,9 +114,48 @@ __global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, s
     *reinterpret_cast<uint4 *>(frame + L.off + (size_t)py * L.pitch + 16 * g16) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+__global__ void __launch_bounds__(256) k_pyr_resize(uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel S, OrbxLevel L,
+                                                    const uint4 *__restrict__ rx, const int2 *__restrict__ ry, int cols16) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = id / cols16, g16 = id - py * cols16;
+    if (py >= L.ph) return;
+    pyr_resize_item(pyr + (size_t)blockIdx.z * pyr_frame, S, L, rx, ry, py, g16);
+}
+
+// The small levels in one launch: a thread-block cluster of PYR_TAIL_CTAS CTAs owns one frame and walks levels first .. nlevels-1 one
+// after the other, every level spread over all threads of the cluster, with a cluster barrier (release / acquire: the level just
+// written to global memory is visible to the whole cluster) before the next one reads it.  Level by level launches of these levels
+// are latency- and tail-bound (8-15 us each for a few hundred thousand pixels); chained here they cost one launch.  Kept for the
+// measurement (see orbx_launch_pyramid): it did not pay.
+#define PYR_TAIL_CTAS 8
+__global__ void __launch_bounds__(256) k_pyr_tail(uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__restrict__ lv, int first, int nlevels,
+                                                  const uint32_t *__restrict__ rxt, const int2 *__restrict__ ryt) {
+    uint8_t *frame = pyr + (size_t)blockIdx.z * pyr_frame;
+    const int t = blockIdx.x * 256 + threadIdx.x, nt = PYR_TAIL_CTAS * 256;
+    for (int l = first; l < nlevels; l++) {
+        const OrbxLevel S = lv[l - 1], L = lv[l];
+        const int cols16 = L.pitch / 16, total = cols16 * L.ph;
+        const uint4 *rx = reinterpret_cast<const uint4 *>(rxt + L.rx_off);
+        const int2 *ry = ryt + L.ry_off;
+        for (int id = t; id < total; id += nt) {
+            const int py = id / cols16;
+            pyr_resize_item(frame, S, L, rx, ry, py, id - py * cols16);
+        }
+        if (l + 1 < nlevels) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+    }
+}
+
 orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size_t frame_pitch, int batch, int stride,
                                 cudaStream_t s) {
-    for (int l = 0; l < e->nlevels; l++) {
+    // levels from `tail` on would go through the chained cluster kernel; off by default (ORBX_PYR_TAIL=<first level> switches it on):
+    // measured on the B200 it is no faster than the level-by-level launches (64 VGA frames: pyramid 0.134 ms with levels 3-7 chained
+    // against 0.128 ms; one frame: 0.044 against 0.036 ms) -- 2048 threads per frame leave the chain latency-bound
+    static const int tail_env = getenv("ORBX_PYR_TAIL") ? atoi(getenv("ORBX_PYR_TAIL")) : ORBX_MAX_LEVELS;
+    const int tail = tail_env < 1 ? 1 : tail_env;
+    for (int l = 0; l < e->nlevels && l < tail; l++) {
         const OrbxLevel &L = e->lv[l];
         if (l == 0) {
             dim3 block(64);
@@ -131,6 +167,19 @@ orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size
             k_pyr_resize<<<grid, 256, 0, s>>>(e->d_pyr, e->pyr_frame_cap, e->lv[l - 1], L,
                                               reinterpret_cast<const uint4 *>(e->d_rxt + L.rx_off), e->d_ryt + L.ry_off, cols16);
         }
+        e->last_launches++;
+    }
+    if (tail < e->nlevels) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(PYR_TAIL_CTAS, 1, batch);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = PYR_TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ORBX_CUDA(cudaLaunchKernelEx(&cfg, k_pyr_tail, e->d_pyr, e->pyr_frame_cap, (const OrbxLevel *)e->d_lv, tail, e->nlevels,
+                                     (const uint32_t *)e->d_rxt, (const int2 *)e->d_ryt));
         e->last_launches++;
     }
     ORBX_CUDA(cudaGetLastError());
