@@ -902,6 +902,12 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
+    # host time to enqueue a step: a few steps into an empty queue, no synchronisation (the queue never fills)
+    t_enq = time.perf_counter()
+    for i in range(8):
+        step_device(i)
+    t_enq = (time.perf_counter() - t_enq) / 8
+    torch.cuda.synchronize()
 
     # per-stage times come from a second, untimed-for-`value` loop: with stage events on, the extractor keeps its stages on one
     # stream back to back (in the loop above the blur runs on a side stream next to the quadtree kernel)
@@ -1219,6 +1225,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(B),
             "run": {"batch_per_gpu": B, "parallelism": "%d independent sequences per GPU in lockstep, sharded over %d GPU(s), no collective on the data path" % (B, world),
+                    "host_enqueue_ms_per_step": 1e3 * t_enq,
                     "value_handle": "one orbx_sequences handle per GPU with n_sub = %d sub-batch pipelines (streams of their own, joined at the end of the timed region)" % args.subs,
                     "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame, "frames_per_rank": [c[0] for c in counters],
                     "per_step_working_set_mb": B * 3.3, "binary": binary_identity()},
