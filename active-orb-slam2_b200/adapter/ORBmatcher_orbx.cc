@@ -165,7 +165,10 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     if (!m || orbxFailed(orbx_match_projection_frame_host(m, &view, n, pts.data(), desc.data(), Rcw, tcw, bForward, bBackward, th,
                                                           mbCheckOrientation, match.data(), &nmatches), "SearchByProjection(Cur, Last)"))
         return 0;
-    // write-back: entries the rotation check rejected were set by this very call and come back as -1 (:1456-1462)
+    // write-back: entries the rotation check rejected were set by this very call and come back as -1 (:1456-1462).
+    // Precondition (holds at every call site of the reference: Tracking.cc:973 and :986 fill mvpMapPoints with NULL right before the
+    // calls at :981 and :987): on entry every CurrentFrame.mvpMapPoints[k] is NULL or has Observations() > 0.  A keypoint that held a map
+    // point WITHOUT observations, got matched and was then rejected would end as NULL in the reference and keeps its old pointer here.
     for (int k = 0; k < CurrentFrame.N; k++)
         if (match[k] >= 0)
             CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[match[k]];

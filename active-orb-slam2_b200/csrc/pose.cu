@@ -457,13 +457,15 @@ extern "C" orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_pro
 __global__ void __launch_bounds__(PG_THREADS)
 k_pose_gather(const orbx_frame_match_job *__restrict__ jobs, const float *__restrict__ inv_sigma2, int nlevels, int pitch,
               double fx, double fy, double cx, double cy, double bf, double *__restrict__ Xw_all, double *__restrict__ obs_all,
-              float *__restrict__ info_all, int32_t *__restrict__ index_all, PoseProbDev *__restrict__ probs) {
+              float *__restrict__ info_all, int32_t *__restrict__ index_all, PoseProbDev *__restrict__ probs, int kp_pitch) {
     __shared__ int warp_cnt[PG_THREADS / 32];
     __shared__ int base;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const orbx_frame_match_job &J = jobs[f];
     const orbx_frame_view &F = J.cur;
-    const int n = F.n_dev ? *F.n_dev : F.n;
+    // the caller's outlier row has kp_pitch entries (<= pitch, checked by the host): a count beyond it is a caller error, never an
+    // out-of-bounds write
+    const int n = min(F.n_dev ? *F.n_dev : F.n, kp_pitch);
     double *Xw = Xw_all + 3 * (size_t)f * pitch, *obs = obs_all + 3 * (size_t)f * pitch;
     float *info = info_all + (size_t)f * pitch;
     int32_t *index = index_all + (size_t)f * pitch;
@@ -541,7 +543,7 @@ extern "C" orbx_status orbx_pose_from_matches_device(orbx_pose *h, const orbx_fr
     cudaStream_t s = (cudaStream_t)stream;
     ORBX_CUDA(cudaMemsetAsync(d_outlier_kp, 0, (size_t)n_frames * kp_pitch, s));
     k_pose_gather<<<n_frames, PG_THREADS, 0, s>>>(d_jobs, d_inv_sigma2, nlevels, pitch, fx, fy, cx, cy, bf, h->d_Xw, h->d_obs, h->d_info,
-                                                  h->d_index, h->d_prob);
+                                                  h->d_index, h->d_prob, kp_pitch);
     k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(h->d_prob, h->d_Xw, h->d_obs, h->d_info, h->d_outlier, h->d_chi2, h->d_out, 10);
     k_pose_scatter<<<n_frames, PG_THREADS, 0, s>>>(h->d_prob, h->d_out, h->d_outlier, h->d_index, d_pose_out, d_n_inliers, d_outlier_kp,
                                                    kp_pitch);

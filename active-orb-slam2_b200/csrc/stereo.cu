@@ -290,6 +290,16 @@ extern "C" orbx_status orbx_stereo_create(orbx_stereo **out, int max_keypoints, 
         orbx_stereo_destroy(h);
         return ORBX_ERR_CUDA;
     }
+    // k_stereo_search keeps 8 bytes per right keypoint in shared memory: refuse here what its launch could not get
+    cudaFuncAttributes fa;
+    ORBX_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_stereo_search));
+    if ((size_t)8 * ((kp + 31) & ~(size_t)31) > (size_t)fa.maxDynamicSharedSizeBytes) {
+        orbx_set_error("orbx_stereo_create: %d keypoints per image need %zu bytes of shared memory, %d available (at most %d keypoints)",
+                       max_keypoints, (size_t)8 * ((kp + 31) & ~(size_t)31), fa.maxDynamicSharedSizeBytes,
+                       (fa.maxDynamicSharedSizeBytes / 8) & ~31);
+        orbx_stereo_destroy(h);
+        return ORBX_ERR_CAPACITY;
+    }
     *out = h;
     return ORBX_OK;
 }

@@ -277,6 +277,8 @@ orbx_status orbx_matcher_last_sweeps(orbx_matcher *m, int32_t *out, int n_jobs);
  * level, parabola fit, disparity gates, median-distance cut.  Fills mvuRight / mvDepth (-1 = no association).
  * ===================================================================================================== */
 typedef struct orbx_stereo orbx_stereo;
+/* max_keypoints per image: bound by the search kernel's shared memory (8 bytes per right keypoint: about 28,000 on a B200);
+ * ORBX_ERR_CAPACITY beyond it */
 orbx_status orbx_stereo_create(orbx_stereo **out, int max_keypoints, int max_pairs, int device);
 void orbx_stereo_destroy(orbx_stereo *h);
 

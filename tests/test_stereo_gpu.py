@@ -79,6 +79,11 @@ def test_edge_cases():
     from orbx._lib import OrbxError
     with pytest.raises(OrbxError):
         small.ComputeStereoMatches(el, er, kl, dl, kr, dr, bf, b)
+    # more keypoints per image than the search kernel's shared memory holds (8 bytes per right keypoint) is refused at create
+    with pytest.raises(OrbxError) as e:
+        StereoMatcher(max_keypoints=40000)
+    assert e.value.status == -4 or "CAPACITY" in str(e.value)
+    StereoMatcher(max_keypoints=20000).close()
     small.close(); sm.close(); el.close(); er.close()
 
 
