@@ -126,10 +126,19 @@ __device__ __forceinline__ void quat_normalize(double q[4]) {
     q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
 }
 
-// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*); every loop unrolled, registers only
+// q / |q| with w >= 0: one rsqrt and four products instead of a square root and four divisions (this sits on the serial chain of every
+// Levenberg trial)
+__device__ __forceinline__ void quat_normalize_fast(double q[4]) {
+    const double rn = rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), sg = q[3] < 0 ? -rn : rn;
+    q[0] *= sg; q[1] *= sg; q[2] *= sg; q[3] *= sg;
+}
+
+// T <- exp(u) * T  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*); every loop unrolled, registers only.  Same
+// formulas as g2o; reciprocals are taken once (1 / theta from one rsqrt, the quaternion norms likewise), so results agree with the
+// oracle to rounding, not to the bit (the optimisers are held to 1e-4 relative).
 __device__ __forceinline__ void se3_oplus(double *T, const double *u) {
     const double wx = u[0], wy = u[1], wz = u[2];
-    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+    const double t2 = wx * wx + wy * wy + wz * wz;
     const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double O2[9], R[9], V[9];
 #pragma unroll
@@ -137,9 +146,12 @@ __device__ __forceinline__ void se3_oplus(double *T, const double *u) {
 #pragma unroll
         for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
     double a = 1.0, b = 1.0, cc = 1.0;
-    const bool small = theta < 0.00001;                    // SE3Quat::exp: R = V = I + Omega + Omega^2 below this angle
+    const bool small = !(t2 >= 0.00001 * 0.00001);         // SE3Quat::exp: R = V = I + Omega + Omega^2 below theta = 1e-5
     if (!small) {
-        a = sin(theta) / theta; b = (1 - cos(theta)) / (theta * theta); cc = (theta - sin(theta)) / (theta * theta * theta);
+        const double it = rsqrt(t2), theta = t2 * it, it2 = it * it;
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        a = sn * it; b = (1 - cs) * it2; cc = (theta - sn) * (it2 * it);
     }
 #pragma unroll
     for (int i = 0; i < 9; i++) {
@@ -148,8 +160,15 @@ __device__ __forceinline__ void se3_oplus(double *T, const double *u) {
         V[i] = small ? R[i] : id + b * O[i] + cc * O2[i];
     }
     double eq[4], et[3];
-    R_to_quat(R, eq);
-    quat_normalize(eq);
+    {   // Eigen::Quaterniond(R); the trace branch with 1 / sqrt taken once
+        const double t = R[0] + R[4] + R[8];
+        if (t > 0) {
+            const double rs = rsqrt(t + 1.0), h = 0.5 * rs;
+            eq[3] = 0.5 * (t + 1.0) * rs;
+            eq[0] = (R[7] - R[5]) * h; eq[1] = (R[2] - R[6]) * h; eq[2] = (R[3] - R[1]) * h;
+        } else R_to_quat(R, eq);
+    }
+    quat_normalize_fast(eq);
 #pragma unroll
     for (int r = 0; r < 3; r++) et[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
     double nq[4];
@@ -161,6 +180,6 @@ __device__ __forceinline__ void se3_oplus(double *T, const double *u) {
     quat_to_R(eq, Rq);
 #pragma unroll
     for (int r = 0; r < 3; r++) nt[r] = et[r] + Rq[3 * r] * T[4] + Rq[3 * r + 1] * T[5] + Rq[3 * r + 2] * T[6];
-    quat_normalize(nq);
+    quat_normalize_fast(nq);
     T[0] = nq[0]; T[1] = nq[1]; T[2] = nq[2]; T[3] = nq[3]; T[4] = nt[0]; T[5] = nt[1]; T[6] = nt[2];
 }

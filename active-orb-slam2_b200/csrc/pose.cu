@@ -31,7 +31,7 @@ struct orbx_pose {
     PoseProbDev *d_prob; PoseOutDev *d_out;
     int32_t *d_index;          // [max_obs] keypoint of every listed observation (device-resident entry point)
     // pinned staging, same layout
-    uint8_t *h_arena; size_t arena_bytes;
+    uint8_t *h_arena, *d_arena; size_t arena_bytes;     // host entry point: one upload and one download per call, same layout both sides
     cudaStream_t stream;
     int last_launches;
 };
@@ -151,58 +151,7 @@ __device__ __forceinline__ void po_pass(PoseShared &S, const PoseProbDev &P, con
     }
 }
 
-// (H + lambda I) x = b for the 6x6 system, upper-triangular H (21 entries); returns 0 if not positive definite
-__device__ __forceinline__ int po_solve6(const double *Hu, const double *b, double lambda, double *x) {
-    // every loop has compile-time bounds and is unrolled, so that A lives in registers (no local-memory round trips on the one
-    // thread everybody else is waiting for)
-    double A[36];
-    {
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int c = a; c < 6; c++) { A[6 * a + c] = Hu[k]; A[6 * c + a] = Hu[k]; k++; }
-    }
-#pragma unroll
-    for (int a = 0; a < 6; a++) A[7 * a] += lambda;
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-        double d = A[j * 6 + j];
-#pragma unroll
-        for (int q = 0; q < j; q++) d -= A[j * 6 + q] * A[j * 6 + q];
-        ok = ok && (d > 0);
-        d = sqrt(d);
-        A[j * 6 + j] = d;
-        const double inv = 1.0 / d;
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
-            double s = A[i * 6 + j];
-#pragma unroll
-            for (int q = 0; q < j; q++) s -= A[i * 6 + q] * A[j * 6 + q];
-            A[i * 6 + j] = s * inv;
-        }
-    }
-    if (!ok) return 0;
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double s = b[i];
-#pragma unroll
-        for (int q = 0; q < i; q++) s -= A[i * 6 + q] * y[q];
-        y[i] = s / A[i * 6 + i];
-    }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-        double s = y[i];
-#pragma unroll
-        for (int q = i + 1; q < 6; q++) s -= A[q * 6 + i] * y[q];
-        y[i] = s / A[i * 6 + i];
-    }
-#pragma unroll
-    for (int i = 0; i < 6; i++) x[i] = y[i];
-    return 1;
-}
+__device__ __forceinline__ int po2_solve6(const double (&Hu)[21], const double (&b)[6], double lambda, double (&x)[6]);
 
 __global__ void __launch_bounds__(PO_THREADS)
 k_pose_optimize(const PoseProbDev *__restrict__ probs, const double *__restrict__ Xw_all, const double *__restrict__ obs_all,
@@ -250,7 +199,7 @@ k_pose_optimize(const PoseProbDev *__restrict__ probs, const double *__restrict_
                     do {
                         if (tid == 0) {
                             for (int i = 0; i < 7; i++) S.Tbak[i] = S.T[i];   // push
-                            const int ok = po_solve6(S.H, S.b, S.lambda, S.x);
+                            const int ok = po2_solve6(S.H, S.b, S.lambda, S.x);
                             if (!ok) for (int i = 0; i < 6; i++) S.x[i] = 0;
                             if (ok) { se3_oplus(S.T, S.x); po_set_pose(S); }
                             S.again = ok;                                     // reused as "solve ok" until the decision below
@@ -331,12 +280,672 @@ k_pose_optimize(const PoseProbDev *__restrict__ probs, const double *__restrict_
     }
 }
 
+// ---- second form of the same optimisation: the latency chain shortened ---------------------------------------------------------
+// The kernel above leaves every decision to thread 0 and meets at ~9 barriers per Levenberg trial; a trial costs ~7.5 us, nearly all
+// of it waiting.  Here EVERY thread carries the pose, the 6x6 system and the Levenberg state in registers and repeats the (identical)
+// solve / exp-map / decision arithmetic, so a trial needs only the barriers of its reductions; the 28 sums of a pass are reduced by a
+// transposing butterfly (28 64-bit shuffles per warp instead of 140); the Cholesky keeps 1/L_jj from one rsqrt per column instead of a
+// sqrt and a division; and with FUSE the pass that evaluates a trial also builds the quadratic form at the trial pose, which IS the
+// next iteration's system when the trial is accepted (same observations, same pose, same robust weights), so an accepted iteration
+// makes one pass instead of two.  Same sums, same decisions; only the order of additions inside a reduction differs.
+struct Po2Shared {
+    double red[PO_WARPS][PO_NACC];
+    double sum[PO_NACC];
+    double red1[2][PO_WARPS];
+};
+
+// every lane ends with ONE of the 28 warp totals: lane l holds total number po2_slot(l) (lanes with slot 28 hold padding)
+__device__ __forceinline__ double po2_bfly28(const double (&v)[PO_NACC], int lane) {
+    double a[14], b[7], c[4], d[2];
+    bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+        const double send = up ? v[i] : v[14 + i], keep = up ? v[14 + i] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        const double send = up ? a[i] : a[7 + i], keep = up ? a[7 + i] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double lo = b[i], hi = i < 3 ? b[4 + (i < 3 ? i : 0)] : 0.0;
+        const double send = up ? lo : hi, keep = up ? hi : lo;
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    up = (lane & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double send = up ? c[i] : c[2 + i], keep = up ? c[2 + i] : c[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    up = (lane & 1) != 0;
+    const double send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+__device__ __forceinline__ int po2_slot(int lane) {
+    if ((lane & 7) == 7) return PO_NACC;                   // the padded fourth entry of the upper 3-element half
+    return ((lane & 16) ? 14 : 0) + ((lane & 8) ? 7 : 0) + ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);
+}
+
+struct Po2Cam { double fx, fy, cx, cy, bf; };
+
+__device__ __forceinline__ double po2_error(const double (&R)[12], const Po2Cam &K, const double *X, const double *o, bool stereo, double info,
+                                            double er[3], double Xc[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) Xc[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + R[9 + r];
+    if (!stereo) {
+        er[0] = o[0] - (Xc[0] / Xc[2] * K.fx + K.cx);
+        er[1] = o[1] - (Xc[1] / Xc[2] * K.fy + K.cy);
+        er[2] = 0;
+    } else {   // cam_project: `const float invz = 1.0f/trans_xyz[2]` (double quotient narrowed once), bf is the edge's double member
+        const double invz = (double)__double2float_rn(1.0 / Xc[2]);
+        const double u = Xc[0] * invz * K.fx + K.cx;
+        er[0] = o[0] - u;
+        er[1] = o[1] - (Xc[1] * invz * K.fy + K.cy);
+        er[2] = o[2] - (u - K.bf * invz);
+    }
+    return info * (er[0] * er[0] + er[1] * er[1] + er[2] * er[2]);
+}
+
+// one pass over the frame's observations at the pose in R: chi2 of every active edge is stored, the robust chi2 (and with BUILD the
+// quadratic form) is summed into out[0..28): H upper triangle 0..20, b 21..26, chi2 27.  Every thread returns with all of them.
+template <bool BUILD>
+__device__ __forceinline__ void po2_pass(Po2Shared &S, int &flip, const double (&R)[12], const Po2Cam &K, int n, const double *__restrict__ Xw,
+                                         const double *__restrict__ obs, const float *__restrict__ info_f, const uint8_t *__restrict__ outlier,
+                                         double *__restrict__ chi2, bool robust, double d_mono, double d_stereo, double (&out)[PO_NACC]) {
+    double acc[PO_NACC];
+#pragma unroll
+    for (int i = 0; i < PO_NACC; i++) acc[i] = 0;
+    for (int e = threadIdx.x; e < n; e += PO_THREADS) {
+        if (outlier[e]) continue;                          // level 1: not part of this round
+        const double *X = Xw + 3 * (size_t)e, *o = obs + 3 * (size_t)e;
+        const bool st = !(o[2] < 0);                      // mvuRight[i] < 0 -> monocular edge (Optimizer.cc:281)
+        const double info = (double)info_f[e];
+        double er[3], Xc[3];
+        const double c = po2_error(R, K, X, o, st, info, er, Xc);
+        chi2[e] = c;
+        double rho1 = 1.0, cr = c;
+        if (robust) {
+            const double d = st ? d_stereo : d_mono, dsqr = (double)(float)(d * d);   // RobustKernelHuber keeps dsqr in a float member
+            if (c > dsqr) { const double rs = rsqrt(c), sq = c * rs; cr = 2 * sq * d - dsqr; rho1 = d * rs; }
+        }
+        acc[27] += cr;
+        if (!BUILD) continue;
+        const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = K.fx, fy = K.fy, bf = K.bf;
+        double J[18];
+        J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+        J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+        if (st) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
+        else {
+#pragma unroll
+            for (int i = 12; i < 18; i++) J[i] = 0;
+        }
+        const double w = rho1 * info;
+        const double w0 = info * er[0] * rho1, w1 = info * er[1] * rho1, w2 = info * er[2] * rho1;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) acc[k++] += w * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] -= J[a] * w0 + J[6 + a] * w1 + J[12 + a] * w2;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (BUILD) {
+        const double mine = po2_bfly28(acc, lane);
+        const int slot = po2_slot(lane);
+        if (slot < PO_NACC) S.red[w][slot] = mine;
+        __syncthreads();
+        if (threadIdx.x < PO_NACC) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < PO_WARPS; k++) s += S.red[k][threadIdx.x];
+            S.sum[threadIdx.x] = s;
+        }
+        __syncthreads();                                   // the next pass writes S.red only after its own loop: S.sum is read right here
+#pragma unroll
+        for (int i = 0; i < PO_NACC; i++) out[i] = S.sum[i];
+    } else {
+        double v = acc[27];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) S.red1[flip][w] = v;
+        __syncthreads();                                   // two buffers: the pass after the next one is two barriers away
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < PO_WARPS; k++) s += S.red1[flip][k];
+        out[27] = s;
+        flip ^= 1;
+    }
+}
+
+// (H + lambda I) x = b, H as its 21 upper-triangular entries; L L^T with 1 / L_jj kept from one rsqrt per column; 0 if not positive definite
+__device__ __forceinline__ int po2_solve6(const double (&Hu)[21], const double (&b)[6], double lambda, double (&x)[6]) {
+    // every loop runs 0..5 with compile-time guards: loops whose bounds depend on an outer unrolled index are only partially unrolled by
+    // nvcc, which would put A into local memory on the one chain every thread is waiting for
+    double A[36], inv[6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                if (c >= a) { const double v = Hu[k] + (a == c ? lambda : 0.0); A[6 * a + c] = v; A[6 * c + a] = v; k++; }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = A[j * 6 + j];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            if (q < j) d -= A[j * 6 + q] * A[j * 6 + q];
+        ok = ok && (d > 0);
+        inv[j] = rsqrt(d);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (i > j) {
+                double s = A[i * 6 + j];
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                    if (q < j) s -= A[i * 6 + q] * A[j * 6 + q];
+                A[i * 6 + j] = s * inv[j];
+            }
+    }
+    if (!ok) return 0;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = b[i];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            if (q < i) s -= A[i * 6 + q] * y[q];
+        y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int ii = 0; ii < 6; ii++) {
+        const int i = 5 - ii;
+        double s = y[i];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            if (q > i) s -= A[q * 6 + i] * y[q];
+        y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = y[i];
+    return 1;
+}
+
+__device__ __forceinline__ void po2_set_pose(const double (&T)[7], double (&R)[12]) {
+    quat_to_R(T, R);
+    R[9] = T[4]; R[10] = T[5]; R[11] = T[6];
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(PO_THREADS, 1)
+k_pose_optimize2(const PoseProbDev *__restrict__ probs, const double *__restrict__ Xw_all, const double *__restrict__ obs_all,
+                 const float *__restrict__ info_all, uint8_t *__restrict__ outlier_all, double *__restrict__ chi2_all,
+                 PoseOutDev *__restrict__ out, int iterations) {
+    __shared__ Po2Shared S;
+    __shared__ PoseProbDev P;
+    const int tid = threadIdx.x;
+    if (tid == 0) P = probs[blockIdx.x];
+    __syncthreads();
+    const double *Xw = Xw_all + 3 * (size_t)P.off, *obs = obs_all + 3 * (size_t)P.off;
+    const float *info = info_all + P.off;
+    uint8_t *outlier = outlier_all + P.off;
+    double *chi2 = chi2_all + P.off;
+    const int n = P.n;
+    const Po2Cam K = {P.fx, P.fy, P.cx, P.cy, P.bf};
+    const double d_mono = (double)(float)sqrt(5.991), d_stereo = (double)(float)sqrt(7.815);   // const float deltaMono / deltaStereo
+    for (int e = tid; e < n; e += PO_THREADS) outlier[e] = 0;      // every thread only ever touches its own observations' flags
+    double T[7], R[12], sums[PO_NACC];
+#pragma unroll
+    for (int i = 0; i < 7; i++) T[i] = P.pose[i];
+    int n_bad = 0, trials = 0, flip = 0;
+    if (n >= 3) {                                                              // :355-356
+        bool robust = true;
+        for (int round = 0; round < 4; round++) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) T[i] = P.pose[i];                      // setEstimate(mTcw), :366
+            po2_set_pose(T, R);
+            if (n - n_bad > 0) {                                               // otherwise "0 vertices to optimize"
+                // ---- OptimizationAlgorithmLevenberg, `iterations` iterations ----
+                double H[21], b[6], x[6], chiB = 0, lambda = 0, ni = 2;
+                int nbad_lm = 0;
+                bool have = false;                                             // H, b, chiB already hold the system at T
+                for (int it = 0; it < iterations; it++) {
+                    if (!FUSE || !have) {
+                        po2_pass<true>(S, flip, R, K, n, Xw, obs, info, outlier, chi2, robust, d_mono, d_stereo, sums);
+#pragma unroll
+                        for (int i = 0; i < 21; i++) H[i] = sums[i];
+#pragma unroll
+                        for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
+                        chiB = sums[27];
+                    }
+                    double currentChi = chiB;
+                    const double iniChi = chiB;
+                    if (it == 0) {
+                        const double mx = fmax(fmax(fmax(fabs(H[0]), fabs(H[6])), fmax(fabs(H[11]), fabs(H[15]))), fmax(fabs(H[18]), fabs(H[20])));
+                        lambda = 1e-5 * mx; ni = 2; nbad_lm = 0;
+                    }
+                    double rho = 0;
+                    int qmax = 0;
+                    bool accepted = false;
+                    do {
+                        double Tbak[7];
+#pragma unroll
+                        for (int i = 0; i < 7; i++) Tbak[i] = T[i];            // push
+                        const int ok = po2_solve6(H, b, lambda, x);
+                        if (!ok) {
+#pragma unroll
+                            for (int i = 0; i < 6; i++) x[i] = 0;
+                        } else { se3_oplus(T, x); po2_set_pose(T, R); }
+                        po2_pass<FUSE>(S, flip, R, K, n, Xw, obs, info, outlier, chi2, robust, d_mono, d_stereo, sums);
+                        double tempChi = sums[27];
+                        if (!ok) tempChi = DBL_MAX;
+                        double scale = 0;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
+                        scale += 1e-3;
+                        rho = (currentChi - tempChi) / scale;
+                        trials++;
+                        accepted = rho > 0 && isfinite(tempChi);
+                        if (accepted) {
+                            const double t = 2 * rho - 1;
+                            double alpha = 1. - t * t * t;
+                            alpha = fmin(alpha, 2. / 3.);
+                            lambda *= fmax(1. / 3., alpha);
+                            ni = 2;
+                            currentChi = tempChi;
+                        } else {
+                            lambda *= ni; ni *= 2;
+#pragma unroll
+                            for (int i = 0; i < 7; i++) T[i] = Tbak[i];        // pop
+                            po2_set_pose(T, R);
+                        }
+                        qmax++;
+                    } while (rho < 0 && qmax < 10);
+                    bool stop = false;
+                    if (qmax == 10 || rho == 0) stop = true;
+                    else {
+                        if ((iniChi - currentChi) * 1e3 < iniChi) nbad_lm++; else nbad_lm = 0;
+                        if (nbad_lm >= 3) stop = true;
+                    }
+                    if (stop) break;
+                    if (FUSE) {
+                        have = accepted;
+                        if (accepted) {                                        // the trial pass built the system at the pose that was kept
+#pragma unroll
+                            for (int i = 0; i < 21; i++) H[i] = sums[i];
+#pragma unroll
+                            for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
+                            chiB = sums[27];
+                        }
+                    }
+                }
+            }
+            // ---- classification, :371-417 ----
+            const float th_mono = 5.991f, th_stereo = 7.815f;
+            int cnt = 0;
+            for (int e = tid; e < n; e += PO_THREADS) {
+                const double *o = obs + 3 * (size_t)e;
+                const bool st = !(o[2] < 0);
+                double c = chi2[e];
+                if (outlier[e]) {                                             // left out of this round: e->computeError()
+                    double er[3], Xc[3];
+                    c = po2_error(R, K, Xw + 3 * (size_t)e, o, st, (double)info[e], er, Xc);
+                    chi2[e] = c;
+                }
+                const bool bad = (float)c > (st ? th_stereo : th_mono);
+                outlier[e] = bad ? 1 : 0;
+                cnt += bad ? 1 : 0;
+            }
+            n_bad = 0;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if ((tid & 31) == 0) S.red1[flip][tid >> 5] = (double)cnt;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < PO_WARPS; k++) n_bad += (int)S.red1[flip][k];
+            flip ^= 1;
+            if (round == 2) robust = false;                                   // setRobustKernel(0), :391, :416
+            if (n < 10) break;                                                // optimizer.edges().size() < 10, :419
+        }
+    }
+    if (tid == 0) {
+        PoseOutDev o;
+        for (int i = 0; i < 7; i++) o.pose[i] = T[i];
+        o.n_bad = n_bad; o.n_inliers = n >= 3 ? n - n_bad : 0; o.trials = trials; o.pad = 0;
+        out[blockIdx.x] = o;
+    }
+}
+
+// ---- third form: a thread-block cluster per frame ---------------------------------------------------------------------------------
+// ncu on the forms above (profiles/r2_af_pose.txt): one frame of 400 observations runs 59 Levenberg trials in 650 k cycles on ONE SM,
+// issue-active 26 %, no memory stalls worth naming -- the SM's FP64 pipe (64 lanes) is the resource: a pass over 400 observations is
+// ~3 k cycles of it and the serial solve / exp-map chain another ~4 k per trial, while 147 SMs idle.  Here a cluster of C CTAs (C = 8, 4,
+// 2 or 1, the largest that still gives every frame of the batch its own SMs) shares a frame: CTA r stages observations
+// [n r / C, n (r + 1) / C) in its shared memory once (nothing is read from global memory inside the Levenberg loop), every CTA runs the
+// pass over its share, the partial sums are exchanged through distributed shared memory (each CTA stores its 28 sums into every
+// peer's buffer, one cluster barrier) and added in rank order by everybody, so all CTAs take the same decisions from the same numbers
+// without a broadcast.  One warp per scheduler (128 threads) makes the redundant serial chain free: the FP64 lanes it uses would idle.
+#define P3_THREADS 128
+#define P3_WARPS (P3_THREADS / 32)
+#define P3_MAXC 8
+#define P3_CAP_MAX 3072            // observations a CTA can stage: 61 bytes each
+
+struct Po3Shared {
+    double red[P3_WARPS][PO_NACC];
+    double part[2][P3_MAXC][PO_NACC];      // [buffer][rank]: written by every CTA of the cluster (its own copy included)
+    double sum[PO_NACC];
+    double red1[P3_WARPS];
+    double part1[2][P3_MAXC];
+};
+
+__device__ __forceinline__ void po3_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned po3_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned po3_cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// store a double into the same shared-memory variable of CTA `rank` of the cluster
+__device__ __forceinline__ void po3_store_remote(double *local, unsigned rank, double v) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+struct Po3Obs {                    // this CTA's observations, structure of arrays in shared memory
+    const double *X, *O; double *chi2; const float *info; uint8_t *outl; int cap, n;
+};
+
+template <bool BUILD>
+__device__ __forceinline__ void po3_pass(Po3Shared &S, int &b28, int &b1, unsigned rank, unsigned C, const double (&R)[12], const Po2Cam &K,
+                                         const Po3Obs &Q, bool robust, double d_mono, double d_stereo, double (&out)[PO_NACC]) {
+    double acc[PO_NACC];
+#pragma unroll
+    for (int i = 0; i < PO_NACC; i++) acc[i] = 0;
+    for (int j = threadIdx.x; j < Q.n; j += P3_THREADS) {
+        if (Q.outl[j]) continue;                           // level 1: not part of this round
+        const double X[3] = {Q.X[j], Q.X[Q.cap + j], Q.X[2 * Q.cap + j]}, o[3] = {Q.O[j], Q.O[Q.cap + j], Q.O[2 * Q.cap + j]};
+        const bool st = !(o[2] < 0);                      // mvuRight[i] < 0 -> monocular edge (Optimizer.cc:281)
+        const double info = (double)Q.info[j];
+        double er[3], Xc[3];
+        const double c = po2_error(R, K, X, o, st, info, er, Xc);
+        Q.chi2[j] = c;
+        double rho1 = 1.0, cr = c;
+        if (robust) {
+            const double d = st ? d_stereo : d_mono, dsqr = (double)(float)(d * d);   // RobustKernelHuber keeps dsqr in a float member
+            if (c > dsqr) { const double rs = rsqrt(c), sq = c * rs; cr = 2 * sq * d - dsqr; rho1 = d * rs; }
+        }
+        acc[27] += cr;
+        if (!BUILD) continue;
+        const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = K.fx, fy = K.fy, bf = K.bf;
+        double J[18];
+        J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+        J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+        if (st) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
+        else {
+#pragma unroll
+            for (int i = 12; i < 18; i++) J[i] = 0;
+        }
+        const double w = rho1 * info;
+        const double w0 = info * er[0] * rho1, w1 = info * er[1] * rho1, w2 = info * er[2] * rho1;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) acc[k++] += w * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] -= J[a] * w0 + J[6 + a] * w1 + J[12 + a] * w2;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (BUILD) {
+        const double mine = po2_bfly28(acc, lane);
+        const int slot = po2_slot(lane);
+        if (slot < PO_NACC) S.red[w][slot] = mine;
+        __syncthreads();
+        if (tid < PO_NACC) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < P3_WARPS; k++) s += S.red[k][tid];
+            for (unsigned r = 0; r < C; r++) po3_store_remote(&S.part[b28][rank][tid], r, s);
+        }
+        po3_cluster_sync();
+        if (tid < PO_NACC) {
+            double s = 0;
+            for (unsigned r = 0; r < C; r++) s += S.part[b28][r][tid];        // rank order: the same sum in every CTA
+            S.sum[tid] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PO_NACC; i++) out[i] = S.sum[i];
+        b28 ^= 1;
+    } else {
+        double v = acc[27];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) S.red1[w] = v;
+        __syncthreads();
+        if (tid < (int)C) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < P3_WARPS; k++) s += S.red1[k];
+            po3_store_remote(&S.part1[b1][rank], (unsigned)tid, s);
+        }
+        po3_cluster_sync();
+        double s = 0;
+        for (unsigned r = 0; r < C; r++) s += S.part1[b1][r];
+        out[27] = s;
+        b1 ^= 1;
+    }
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(P3_THREADS, 1)
+k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict__ Xw_all, const double *__restrict__ obs_all,
+                 const float *__restrict__ info_all, uint8_t *__restrict__ outlier_all, PoseOutDev *__restrict__ out, int iterations, int cap) {
+    extern __shared__ __align__(16) uint8_t po3_dyn[];
+    __shared__ Po3Shared S;
+    __shared__ PoseProbDev P;
+    const int tid = threadIdx.x;
+    const unsigned rank = po3_cluster_rank(), C = po3_cluster_size();
+    const int frame = blockIdx.x / C;
+    if (tid == 0) P = probs[frame];
+    __syncthreads();
+    const int n = P.n;
+    const int e0 = (int)((long long)n * rank / C), e1 = (int)((long long)n * (rank + 1) / C);
+    double *sX = reinterpret_cast<double *>(po3_dyn), *sO = sX + 3 * cap, *sChi = sO + 3 * cap;
+    float *sInfo = reinterpret_cast<float *>(sChi + cap);
+    uint8_t *sOut = reinterpret_cast<uint8_t *>(sInfo + cap);
+    Po3Obs Q = {sX, sO, sChi, sInfo, sOut, cap, e1 - e0};
+    {
+        const double *Xw = Xw_all + 3 * ((size_t)P.off + e0), *obs = obs_all + 3 * ((size_t)P.off + e0);
+        const float *info = info_all + P.off + e0;
+        for (int i = tid; i < 3 * Q.n; i += P3_THREADS) {
+            const int j = i / 3, c = i - 3 * j;
+            sX[c * cap + j] = Xw[i];
+            sO[c * cap + j] = obs[i];
+        }
+        for (int j = tid; j < Q.n; j += P3_THREADS) { sInfo[j] = info[j]; sOut[j] = 0; sChi[j] = 0; }
+    }
+    __syncthreads();
+    const Po2Cam K = {P.fx, P.fy, P.cx, P.cy, P.bf};
+    const double d_mono = (double)(float)sqrt(5.991), d_stereo = (double)(float)sqrt(7.815);   // const float deltaMono / deltaStereo
+    double T[7], R[12], sums[PO_NACC];
+#pragma unroll
+    for (int i = 0; i < 7; i++) T[i] = P.pose[i];
+    int n_bad = 0, trials = 0, b28 = 0, b1 = 0;
+    if (n >= 3) {                                                              // :355-356
+        bool robust = true;
+        for (int round = 0; round < 4; round++) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) T[i] = P.pose[i];                      // setEstimate(mTcw), :366
+            po2_set_pose(T, R);
+            if (n - n_bad > 0) {                                               // otherwise "0 vertices to optimize"
+                // ---- OptimizationAlgorithmLevenberg, `iterations` iterations ----
+                double H[21], b[6], x[6], chiB = 0, lambda = 0, ni = 2;
+                int nbad_lm = 0;
+                bool have = false;                                             // H, b, chiB already hold the system at T
+                for (int it = 0; it < iterations; it++) {
+                    if (!FUSE || !have) {
+                        po3_pass<true>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
+#pragma unroll
+                        for (int i = 0; i < 21; i++) H[i] = sums[i];
+#pragma unroll
+                        for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
+                        chiB = sums[27];
+                    }
+                    double currentChi = chiB;
+                    const double iniChi = chiB;
+                    if (it == 0) {
+                        const double mx = fmax(fmax(fmax(fabs(H[0]), fabs(H[6])), fmax(fabs(H[11]), fabs(H[15]))), fmax(fabs(H[18]), fabs(H[20])));
+                        lambda = 1e-5 * mx; ni = 2; nbad_lm = 0;
+                    }
+                    double rho = 0;
+                    int qmax = 0;
+                    bool accepted = false;
+                    do {
+                        double Tbak[7];
+#pragma unroll
+                        for (int i = 0; i < 7; i++) Tbak[i] = T[i];            // push
+                        const int ok = po2_solve6(H, b, lambda, x);
+                        if (!ok) {
+#pragma unroll
+                            for (int i = 0; i < 6; i++) x[i] = 0;
+                        } else { se3_oplus(T, x); po2_set_pose(T, R); }
+                        po3_pass<FUSE>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
+                        double tempChi = sums[27];
+                        if (!ok) tempChi = DBL_MAX;
+                        double scale = 0;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
+                        scale += 1e-3;
+                        rho = (currentChi - tempChi) / scale;
+                        trials++;
+                        accepted = rho > 0 && isfinite(tempChi);
+                        if (accepted) {
+                            const double t = 2 * rho - 1;
+                            double alpha = 1. - t * t * t;
+                            alpha = fmin(alpha, 2. / 3.);
+                            lambda *= fmax(1. / 3., alpha);
+                            ni = 2;
+                            currentChi = tempChi;
+                        } else {
+                            lambda *= ni; ni *= 2;
+#pragma unroll
+                            for (int i = 0; i < 7; i++) T[i] = Tbak[i];        // pop
+                            po2_set_pose(T, R);
+                        }
+                        qmax++;
+                    } while (rho < 0 && qmax < 10);
+                    bool stop = false;
+                    if (qmax == 10 || rho == 0) stop = true;
+                    else {
+                        if ((iniChi - currentChi) * 1e3 < iniChi) nbad_lm++; else nbad_lm = 0;
+                        if (nbad_lm >= 3) stop = true;
+                    }
+                    if (stop) break;
+                    if (FUSE) {
+                        have = accepted;
+                        if (accepted) {                                        // the trial pass built the system at the pose that was kept
+#pragma unroll
+                            for (int i = 0; i < 21; i++) H[i] = sums[i];
+#pragma unroll
+                            for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
+                            chiB = sums[27];
+                        }
+                    }
+                }
+            }
+            // ---- classification, :371-417 ----
+            const float th_mono = 5.991f, th_stereo = 7.815f;
+            int cnt = 0;
+            for (int j = tid; j < Q.n; j += P3_THREADS) {
+                const double X[3] = {Q.X[j], Q.X[cap + j], Q.X[2 * cap + j]}, o[3] = {Q.O[j], Q.O[cap + j], Q.O[2 * cap + j]};
+                const bool st = !(o[2] < 0);
+                double c = sChi[j];
+                if (sOut[j]) {                                                // left out of this round: e->computeError()
+                    double er[3], Xc[3];
+                    c = po2_error(R, K, X, o, st, (double)sInfo[j], er, Xc);
+                    sChi[j] = c;
+                }
+                const bool bad = (float)c > (st ? th_stereo : th_mono);
+                sOut[j] = bad ? 1 : 0;
+                cnt += bad ? 1 : 0;
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if ((tid & 31) == 0) S.red1[tid >> 5] = (double)cnt;
+            __syncthreads();
+            if (tid < (int)C) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < P3_WARPS; k++) s += S.red1[k];
+                po3_store_remote(&S.part1[b1][rank], (unsigned)tid, s);
+            }
+            po3_cluster_sync();
+            n_bad = 0;
+            for (unsigned r = 0; r < C; r++) n_bad += (int)S.part1[b1][r];
+            b1 ^= 1;
+            if (round == 2) robust = false;                                   // setRobustKernel(0), :391, :416
+            if (n < 10) break;                                                // optimizer.edges().size() < 10, :419
+        }
+    }
+    uint8_t *outlier = outlier_all + P.off + e0;
+    for (int j = tid; j < Q.n; j += P3_THREADS) outlier[j] = sOut[j];
+    if (tid == 0 && rank == 0) {
+        PoseOutDev o;
+        for (int i = 0; i < 7; i++) o.pose[i] = T[i];
+        o.n_bad = n_bad; o.n_inliers = n >= 3 ? n - n_bad : 0; o.trials = trials; o.pad = 0;
+        out[frame] = o;
+    }
+    po3_cluster_sync();                                                       // no CTA leaves while a peer may still store into its shared memory
+}
+
+// ORBX_POSE_KERNEL = 1: the first form, 2 / 3: the second (plain / fused trial pass), 4 / 5 (default): the cluster form (plain / fused).
+// n_max = upper bound of a frame's observations (the cluster form stages a frame's share in shared memory; larger frames take form 1)
+static cudaError_t po_launch(int n_frames, int n_max, cudaStream_t s, const PoseProbDev *probs, const double *Xw, const double *obs,
+                             const float *info, uint8_t *outlier, double *chi2, PoseOutDev *out) {
+    static int which = -1;
+    if (which < 0) { const char *e = getenv("ORBX_POSE_KERNEL"); which = e ? atoi(e) : 5; }
+    int C = 1;
+    while (C < P3_MAXC && n_frames * 2 * C <= 148) C *= 2;          // every frame of the batch keeps its own SMs
+    while (C > 1 && n_max <= P3_THREADS * (C / 2)) C /= 2;             // no more CTAs than one observation per thread asks for
+    int cap = ((n_max + C - 1) / C + 1 + 31) & ~31;
+    int kind = which;
+    if (kind >= 4 && cap > P3_CAP_MAX) kind = 1;
+    if (kind == 1) k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
+    else if (kind == 2) k_pose_optimize2<false><<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
+    else if (kind == 3) k_pose_optimize2<true><<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
+    else {
+        static bool raised = false;
+        if (!raised) {
+            cudaError_t e = ORBX_RAISE_SMEM(k_pose_optimize3<false>);
+            if (e == cudaSuccess) e = ORBX_RAISE_SMEM(k_pose_optimize3<true>);
+            if (e != cudaSuccess) return e;
+            raised = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_frames * C)); cfg.blockDim = dim3(P3_THREADS);
+        cfg.dynamicSmemBytes = (size_t)cap * 61 + 64; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (kind == 4) return cudaLaunchKernelEx(&cfg, k_pose_optimize3<false>, probs, Xw, obs, info, outlier, out, 10, cap);
+        return cudaLaunchKernelEx(&cfg, k_pose_optimize3<true>, probs, Xw, obs, info, outlier, out, 10, cap);
+    }
+    return cudaGetLastError();
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 extern "C" void orbx_pose_destroy(orbx_pose *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_Xw); cudaFree(h->d_obs); cudaFree(h->d_chi2); cudaFree(h->d_info); cudaFree(h->d_outlier);
-    cudaFree(h->d_prob); cudaFree(h->d_out); cudaFree(h->d_index);
+    cudaFree(h->d_prob); cudaFree(h->d_out); cudaFree(h->d_index); cudaFree(h->d_arena);
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->stream) cudaStreamDestroy(h->stream);
     free(h);
@@ -377,6 +986,7 @@ extern "C" orbx_status orbx_pose_create(orbx_pose **out, int max_observations, i
     TRY(cudaMalloc((void **)&h->d_out, sizeof(PoseOutDev) * nf));
     TRY(cudaMalloc((void **)&h->d_index, sizeof(int32_t) * no));
     TRY(cudaMallocHost((void **)&h->h_arena, h->arena_bytes));
+    TRY(cudaMalloc((void **)&h->d_arena, h->arena_bytes));
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 #undef TRY
     if (ce != cudaSuccess) {
@@ -425,18 +1035,20 @@ extern "C" orbx_status orbx_pose_optimize_host(orbx_pose *h, const orbx_pose_pro
         off += (size_t)p.n;
     }
     cudaStream_t s = h->stream;
-    ORBX_CUDA(cudaMemcpyAsync(h->d_Xw, aX, 24 * nt, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_obs, aO, 24 * nt, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_info, aI, 4 * nt, cudaMemcpyHostToDevice, s));
-    ORBX_CUDA(cudaMemcpyAsync(h->d_prob, aP, sizeof(PoseProbDev) * n_frames, cudaMemcpyHostToDevice, s));
-    k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(h->d_prob, h->d_Xw, h->d_obs, h->d_info, h->d_outlier, h->d_chi2, h->d_out, 10);
-    ORBX_CUDA(cudaGetLastError());
-    h->last_launches = 1;
     // results come back through the same arena (after the problems)
     PoseOutDev *aR = reinterpret_cast<PoseOutDev *>(aP + n_frames);
     uint8_t *aB = reinterpret_cast<uint8_t *>(aR + n_frames);
-    ORBX_CUDA(cudaMemcpyAsync(aR, h->d_out, sizeof(PoseOutDev) * n_frames, cudaMemcpyDeviceToHost, s));
-    ORBX_CUDA(cudaMemcpyAsync(aB, h->d_outlier, nt, cudaMemcpyDeviceToHost, s));
+    const size_t in_bytes = (size_t)(reinterpret_cast<uint8_t *>(aR) - h->h_arena), out_bytes = sizeof(PoseOutDev) * n_frames + nt;
+    uint8_t *dA = h->d_arena;
+    auto dev = [&](const void *host) { return dA + (reinterpret_cast<const uint8_t *>(host) - h->h_arena); };
+    ORBX_CUDA(cudaMemcpyAsync(dA, h->h_arena, in_bytes, cudaMemcpyHostToDevice, s));
+    int n_max = 0;
+    for (int f = 0; f < n_frames; f++) n_max = probs[f].n > n_max ? probs[f].n : n_max;
+    ORBX_CUDA(po_launch(n_frames, n_max, s, reinterpret_cast<const PoseProbDev *>(dev(aP)), reinterpret_cast<const double *>(dev(aX)),
+                        reinterpret_cast<const double *>(dev(aO)), reinterpret_cast<const float *>(dev(aI)), dev(aB), h->d_chi2,
+                        reinterpret_cast<PoseOutDev *>(dev(aR))));
+    h->last_launches = 1;
+    ORBX_CUDA(cudaMemcpyAsync(aR, dev(aR), out_bytes, cudaMemcpyDeviceToHost, s));
     ORBX_CUDA(cudaStreamSynchronize(s));
     off = 0;
     for (int f = 0; f < n_frames; f++) {
@@ -544,7 +1156,7 @@ extern "C" orbx_status orbx_pose_from_matches_device(orbx_pose *h, const orbx_fr
     ORBX_CUDA(cudaMemsetAsync(d_outlier_kp, 0, (size_t)n_frames * kp_pitch, s));
     k_pose_gather<<<n_frames, PG_THREADS, 0, s>>>(d_jobs, d_inv_sigma2, nlevels, pitch, fx, fy, cx, cy, bf, h->d_Xw, h->d_obs, h->d_info,
                                                   h->d_index, h->d_prob, kp_pitch);
-    k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(h->d_prob, h->d_Xw, h->d_obs, h->d_info, h->d_outlier, h->d_chi2, h->d_out, 10);
+    ORBX_CUDA(po_launch(n_frames, kp_pitch, s, h->d_prob, h->d_Xw, h->d_obs, h->d_info, h->d_outlier, h->d_chi2, h->d_out));
     k_pose_scatter<<<n_frames, PG_THREADS, 0, s>>>(h->d_prob, h->d_out, h->d_outlier, h->d_index, d_pose_out, d_n_inliers, d_outlier_kp,
                                                    kp_pitch);
     ORBX_CUDA(cudaGetLastError());

@@ -24,7 +24,8 @@ struct SeqSub {
     orbx_stereo *st;
     orbx_pose *pz;
     cudaStream_t stream;
-    cudaEvent_t done;
+    cudaStream_t copy;         // keypoints / descriptors go back to the host here while stereo, search and pose optimisation still run
+    cudaEvent_t done, ex_done, copy_done;
     int q0, nq;                // sequences [q0, q0 + nq)
 };
 
@@ -60,7 +61,74 @@ struct orbx_sequences {
     int slot;
     int gen, steps, in_flight;
     int last_launches;
+    // results for callers whose buffers are ordinary (pageable) memory: a device-to-host copy into pageable memory goes through the
+    // driver's own staging and blocks the host once per copy (0.1 ms per step of one stereo frame, measured).  Such callers get the
+    // step's results by DMA into this pinned block (allocated on first use) and a host copy of the valid rows in _step_end.
+    uint8_t *h_stage;
+    orbx_sequences_outputs stage;          // views into h_stage, same shapes as the caller's arrays
+    orbx_sequences_outputs checked;        // the last caller struct whose pointers were classified ...
+    int checked_valid, checked_pageable;   // ... and what they were
+    orbx_sequences_outputs pending;        // caller buffers the staged step still has to be copied into
+    int pending_valid, pending_pose;
 };
+
+// 1 if any of the caller's output buffers is not page-locked (cudaHostAlloc / cudaHostRegister) memory
+static int outputs_pageable(orbx_sequences *h, const orbx_sequences_outputs *o) {
+    if (h->checked_valid && !memcmp(&h->checked, o, sizeof(*o))) return h->checked_pageable;
+    const void *ptrs[] = {o->kps, o->desc, o->counts, o->match, o->nmatches, o->u_right, o->depth, o->pose, o->n_inliers, o->outlier};
+    int pageable = 0;
+    for (const void *q : ptrs) {
+        if (!q) continue;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); pageable = 1; break; }
+        if (a.type != cudaMemoryTypeHost && a.type != cudaMemoryTypeManaged) { pageable = 1; break; }
+    }
+    h->checked = *o; h->checked_valid = 1; h->checked_pageable = pageable;
+    return pageable;
+}
+
+static cudaError_t stage_alloc(orbx_sequences *h) {
+    if (h->h_stage) return cudaSuccess;
+    const size_t cap = (size_t)h->cap, ni = (size_t)h->n_img, ns = (size_t)h->c.n_sequences;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 63) & ~(size_t)63; return at; };
+    const size_t o_kps = take(sizeof(orbx_keypoint) * cap * ni), o_desc = take(32 * cap * ni), o_cnt = take(4 * ni), o_match = take(4 * cap * ns),
+                 o_nm = take(4 * ns), o_ur = take(4 * cap * ns), o_dp = take(4 * cap * ns), o_pose = take(56 * ns), o_inl = take(4 * ns),
+                 o_out = take(cap * ns);
+    cudaError_t e = cudaMallocHost((void **)&h->h_stage, off);
+    if (e != cudaSuccess) return e;
+    uint8_t *b = h->h_stage;
+    h->stage.kps = reinterpret_cast<orbx_keypoint *>(b + o_kps); h->stage.desc = b + o_desc; h->stage.counts = reinterpret_cast<int32_t *>(b + o_cnt);
+    h->stage.match = reinterpret_cast<int32_t *>(b + o_match); h->stage.nmatches = reinterpret_cast<int32_t *>(b + o_nm);
+    h->stage.u_right = reinterpret_cast<float *>(b + o_ur); h->stage.depth = reinterpret_cast<float *>(b + o_dp);
+    h->stage.pose = reinterpret_cast<double *>(b + o_pose); h->stage.n_inliers = reinterpret_cast<int32_t *>(b + o_inl); h->stage.outlier = b + o_out;
+    return cudaSuccess;
+}
+
+// the staged step's results into the caller's arrays (after the streams have been synchronised): keypoints / descriptors up to each
+// image's count, the per-sequence rows whole
+static void unstage(orbx_sequences *h) {
+    if (!h->pending_valid) return;
+    h->pending_valid = 0;
+    const orbx_sequences_outputs &o = h->pending, &t = h->stage;
+    const size_t cap = (size_t)h->cap, ns = (size_t)h->c.n_sequences;
+    for (int i = 0; i < h->n_img; i++) {
+        const int32_t c = t.counts[i];
+        const size_t n = c < 0 ? 0 : ((size_t)c > cap ? cap : (size_t)c);
+        o.counts[i] = c;
+        if (o.kps) memcpy(o.kps + cap * i, t.kps + cap * i, sizeof(orbx_keypoint) * n);
+        if (o.desc) memcpy(o.desc + 32 * cap * i, t.desc + 32 * cap * i, 32 * n);
+    }
+    memcpy(o.match, t.match, 4 * cap * ns);
+    memcpy(o.nmatches, t.nmatches, 4 * ns);
+    if (h->c.stereo && o.u_right) memcpy(o.u_right, t.u_right, 4 * cap * ns);
+    if (h->c.stereo && o.depth) memcpy(o.depth, t.depth, 4 * cap * ns);
+    if (h->pending_pose) {
+        if (o.pose) memcpy(o.pose, t.pose, 56 * ns);
+        if (o.n_inliers) memcpy(o.n_inliers, t.n_inliers, 4 * ns);
+        if (o.outlier) memcpy(o.outlier, t.outlier, cap * ns);
+    }
+}
 
 // Everything a step needs before its kernels run, in one launch and without a copy: per sequence (blockIdx.y)
 //   * the last frame's keypoints as map points, Frame::UnprojectStereo (Frame.cc:695-709): x = (u-cx)*z*invfx, y = (v-cy)*z*invfy,
@@ -152,12 +220,15 @@ extern "C" void orbx_sequences_destroy(orbx_sequences *h) {
         if (S.st) orbx_stereo_destroy(S.st);
         if (S.pz) orbx_pose_destroy(S.pz);
         if (S.stream) cudaStreamDestroy(S.stream);
+        if (S.copy) cudaStreamDestroy(S.copy);
         if (S.done) cudaEventDestroy(S.done);
+        if (S.ex_done) cudaEventDestroy(S.ex_done);
+        if (S.copy_done) cudaEventDestroy(S.copy_done);
     }
     cudaFree(h->d_img);
     for (int g = 0; g < 2; g++) { cudaFree(h->d_kps[g]); cudaFree(h->d_desc[g]); cudaFree(h->d_cnt[g]); cudaFree(h->d_depth[g]); }
     cudaFree(h->d_ur); cudaFree(h->d_kept); cudaFree(h->d_pts); cudaFree(h->d_match); cudaFree(h->d_sf); cudaFree(h->d_is2); cudaFree(h->d_pose); cudaFree(h->d_inl); cudaFree(h->d_outkp); cudaFree(h->d_jobs);
-    cudaFreeHost(h->h_pose_ring); cudaFreeHost(h->h_status);
+    cudaFreeHost(h->h_pose_ring); cudaFreeHost(h->h_status); if (h->h_stage) cudaFreeHost(h->h_stage);
     for (int i = 0; i < SEQ_SLOTS; i++) for (int k = 0; k < SEQ_MAX_SUBS; k++) if (h->slot_ev[i][k]) cudaEventDestroy(h->slot_ev[i][k]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     free(h->h_pose_last);
@@ -197,7 +268,10 @@ extern "C" orbx_status orbx_sequences_create(orbx_sequences **out, const orbx_se
         if (cfg->stereo && (st = orbx_stereo_create(&S.st, h->cap, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
         if (cfg->pose && (st = orbx_pose_create(&S.pz, h->cap * S.nq, S.nq, cfg->device))) { orbx_sequences_destroy(h); return st; }
         TRY(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+        TRY(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
         TRY(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&S.ex_done, cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&S.copy_done, cudaEventDisableTiming));
     }
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -268,6 +342,24 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
         memcpy(h_pose + 24 * q + 12, h->h_pose_last + 12 * q, sizeof(float) * 12);
     }
     const bool have_last = h->steps > 0;
+    orbx_sequences_outputs tgt;                          // where the copies of this step land: the caller's arrays, or the pinned block
+    if (o) {
+        tgt = *o;
+        if (outputs_pageable(h, o)) {
+            ORBX_CUDA(stage_alloc(h));
+            const orbx_sequences_outputs &t = h->stage;
+            tgt.counts = t.counts; tgt.match = t.match; tgt.nmatches = t.nmatches;
+            if (o->kps) tgt.kps = t.kps;
+            if (o->desc) tgt.desc = t.desc;
+            if (o->u_right) tgt.u_right = t.u_right;
+            if (o->depth) tgt.depth = t.depth;
+            if (o->pose) tgt.pose = t.pose;
+            if (o->n_inliers) tgt.n_inliers = t.n_inliers;
+            if (o->outlier) tgt.outlier = t.outlier;
+            h->pending = *o; h->pending_valid = 1; h->pending_pose = c.pose && have_last;
+        }
+        o = &tgt;
+    }
     SeqPrep P;
     P.kps_last = h->d_kps[gl]; P.kps_cur = h->d_kps[g]; P.cnt_last = h->d_cnt[gl]; P.cnt_cur = h->d_cnt[g];
     P.desc_last = h->d_desc[gl]; P.desc_cur = h->d_desc[g];
@@ -312,6 +404,15 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
                                                    h->d_desc[g] + (size_t)32 * cap * i0, h->d_cnt[g] + i0, ss);
         if (st) return st;
         h->last_launches += orbx_extractor_last_launches(S.ex);
+        if (o) {     // the extractor's results start their way back now, on the copy stream; the rest of the step does not wait for them
+            ORBX_CUDA(cudaEventRecord(S.ex_done, ss));
+            ORBX_CUDA(cudaStreamWaitEvent(S.copy, S.ex_done, 0));
+            ORBX_CUDA(cudaMemcpyAsync(o->counts + i0, h->d_cnt[g] + i0, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, S.copy));
+            if (o->kps) ORBX_CUDA(cudaMemcpyAsync(o->kps + (size_t)cap * i0, h->d_kps[g] + (size_t)cap * i0, sizeof(orbx_keypoint) * cap * ni, cudaMemcpyDeviceToHost, S.copy));
+            if (o->desc) ORBX_CUDA(cudaMemcpyAsync(o->desc + (size_t)32 * cap * i0, h->d_desc[g] + (size_t)32 * cap * i0, (size_t)32 * cap * ni, cudaMemcpyDeviceToHost, S.copy));
+            ORBX_CUDA(cudaMemcpyAsync(h->h_status + i0, S.ex->d_status, sizeof(int) * ni, cudaMemcpyDeviceToHost, S.copy));
+            ORBX_CUDA(cudaEventRecord(S.copy_done, S.copy));
+        }
         // Frame::ComputeStereoMatches
         if (c.stereo) {
             orbx_stereo_side L = {h->d_kps[g] + (size_t)cap * i0, h->d_desc[g] + (size_t)32 * cap * i0, h->d_cnt[g] + i0, 2 * cap, 2, S.ex, 0, 2, cap};
@@ -332,9 +433,6 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
             h->last_launches += orbx_pose_last_launches(S.pz);
         }
         if (o) {                                             // the sub-batch's results back to the caller's buffers
-            ORBX_CUDA(cudaMemcpyAsync(o->counts + i0, h->d_cnt[g] + i0, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, ss));
-            if (o->kps) ORBX_CUDA(cudaMemcpyAsync(o->kps + (size_t)cap * i0, h->d_kps[g] + (size_t)cap * i0, sizeof(orbx_keypoint) * cap * ni, cudaMemcpyDeviceToHost, ss));
-            if (o->desc) ORBX_CUDA(cudaMemcpyAsync(o->desc + (size_t)32 * cap * i0, h->d_desc[g] + (size_t)32 * cap * i0, (size_t)32 * cap * ni, cudaMemcpyDeviceToHost, ss));
             ORBX_CUDA(cudaMemcpyAsync(o->match + (size_t)cap * S.q0, h->d_match + (size_t)cap * S.q0, sizeof(int32_t) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
             ORBX_CUDA(cudaMemcpyAsync(o->nmatches + S.q0, h->d_nm + S.q0, sizeof(int32_t) * S.nq, cudaMemcpyDeviceToHost, ss));
             if (c.stereo && o->u_right) ORBX_CUDA(cudaMemcpyAsync(o->u_right + (size_t)cap * S.q0, h->d_ur + (size_t)cap * S.q0, sizeof(float) * cap * S.nq, cudaMemcpyDeviceToHost, ss));
@@ -344,7 +442,7 @@ static orbx_status run_step(orbx_sequences *h, const uint8_t *images, bool host_
                 if (o->n_inliers) ORBX_CUDA(cudaMemcpyAsync(o->n_inliers + S.q0, h->d_inl + S.q0, sizeof(int32_t) * S.nq, cudaMemcpyDeviceToHost, ss));
                 if (o->outlier) ORBX_CUDA(cudaMemcpyAsync(o->outlier + (size_t)cap * S.q0, h->d_outkp + (size_t)cap * S.q0, (size_t)cap * S.nq, cudaMemcpyDeviceToHost, ss));
             }
-            ORBX_CUDA(cudaMemcpyAsync(h->h_status + i0, S.ex->d_status, sizeof(int) * ni, cudaMemcpyDeviceToHost, ss));
+            ORBX_CUDA(cudaStreamWaitEvent(ss, S.copy_done, 0));               // whoever waits for this stream waits for the copy stream too
         }
         if (fork) ORBX_CUDA(cudaEventRecord(S.done, ss));
     }
@@ -362,6 +460,7 @@ extern "C" orbx_status orbx_sequences_step_begin(orbx_sequences *h, const uint8_
     if (h->in_flight) {                                                // one step in flight per handle
         ORBX_CUDA(cudaStreamSynchronize(h->stream));
         if (h->n_sub > 1) for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaStreamSynchronize(h->sub[k].stream));
+        unstage(h);
     }
     const orbx_status st = run_step(h, images, true, image_pitch, stride, Tcw, o, h->stream);
     if (st) return st;
@@ -407,6 +506,7 @@ extern "C" orbx_status orbx_sequences_step_end(orbx_sequences *h) {
     ORBX_CUDA(cudaSetDevice(h->c.device));
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
     if (h->n_sub > 1) for (int k = 0; k < h->n_sub; k++) ORBX_CUDA(cudaStreamSynchronize(h->sub[k].stream));
+    unstage(h);
     if (h->in_flight) {
         h->in_flight = 0;
         for (int i = 0; i < h->n_img; i++)

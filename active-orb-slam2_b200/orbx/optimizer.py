@@ -142,11 +142,10 @@ class PoseOptimizer:
 
     __del__ = close
 
-    def PoseOptimization(self, probs):
-        """probs: one dict or a list of dicts(Xw[n,3], obs[n,3] (third < 0 = monocular), inv_sigma2[n], pose[7], K=(fx,fy,cx,cy,bf))
-        -> dict(pose, outlier, n_inliers, n_bad, trials) per problem"""
-        single = isinstance(probs, dict)
-        plist = [probs] if single else list(probs)
+    def pack(self, probs):
+        """the argument arrays of orbx_pose_optimize_host for a list of problem dicts (reusable: a caller that times the C call alone
+        packs once)"""
+        plist = list(probs)
         nf = len(plist)
         P, R = (PoseProblem * max(nf, 1))(), (PoseResult * max(nf, 1))()
         keep, outs = [], []
@@ -162,9 +161,24 @@ class PoseOptimizer:
                 P[f].pose[i] = v
             P[f].fx, P[f].fy, P[f].cx, P[f].cy, P[f].bf = (float(v) for v in p["K"][:5])
             R[f].outlier = out.ctypes.data
+        return P, R, nf, keep, outs
+
+    def run(self, packed):
+        """orbx_pose_optimize_host on pack()'s arrays -> dict(pose, outlier, n_inliers, n_bad, trials) per problem"""
+        P, R, nf, _, outs = packed
         check(self._L.orbx_pose_optimize_host(self._h, P, nf, R))
-        res = [dict(pose=np.array(list(R[f].pose)), outlier=outs[f][:P[f].n].copy(), n_inliers=R[f].n_inliers, n_bad=R[f].n_bad,
-                    trials=R[f].lm_trials) for f in range(nf)]
+        return [dict(pose=np.array(list(R[f].pose)), outlier=outs[f][:P[f].n].copy(), n_inliers=R[f].n_inliers, n_bad=R[f].n_bad,
+                     trials=R[f].lm_trials) for f in range(nf)]
+
+    def call(self, packed):
+        """the C call alone (results stay in pack()'s arrays)"""
+        check(self._L.orbx_pose_optimize_host(self._h, packed[0], packed[2], packed[1]))
+
+    def PoseOptimization(self, probs):
+        """probs: one dict or a list of dicts(Xw[n,3], obs[n,3] (third < 0 = monocular), inv_sigma2[n], pose[7], K=(fx,fy,cx,cy,bf))
+        -> dict(pose, outlier, n_inliers, n_bad, trials) per problem"""
+        single = isinstance(probs, dict)
+        res = self.run(self.pack([probs] if single else probs))
         return res[0] if single else res
 
     def from_matches_device(self, d_jobs, n_frames, d_inv_sigma2, nlevels, K, d_pose_out, d_n_inliers, d_outlier_kp, kp_pitch, stream=0):

@@ -363,7 +363,10 @@ orbx_status orbx_sequences_reset(orbx_sequences *h);
 /* one step.  images: n_images frames `image_pitch` bytes apart, rows `stride` bytes apart (pinned memory makes the upload
  * asynchronous); Tcw: [n_sequences][12], rows of [Rcw | tcw] of the new frames (the motion-model prediction that
  * SearchByProjection projects with).  _begin enqueues upload, kernels and downloads on the handle's stream and returns; _end waits
- * for them and reports device-side overflow.  One step in flight per handle. */
+ * for them and reports device-side overflow.  One step in flight per handle.  The output arrays may be page-locked (the results
+ * are written there by DMA, whole rows) or ordinary memory (the results go to a pinned block of the handle and _end copies the valid
+ * part into the arrays: keypoints / descriptors up to counts[i], the per-sequence rows whole); either way they are complete only
+ * when _end has returned. */
 orbx_status orbx_sequences_step_begin(orbx_sequences *h, const uint8_t *images, size_t image_pitch, int stride, const float *Tcw,
                                       const orbx_sequences_outputs *out);
 orbx_status orbx_sequences_step_end(orbx_sequences *h);

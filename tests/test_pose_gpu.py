@@ -59,7 +59,8 @@ def test_heavy_outliers_and_bad_start(po):
 
 
 def test_batch_of_frames(po):
-    """64 frames in one launch: every frame equals its own single-frame run and the oracle"""
+    """64 frames in one launch: every frame equals the oracle and its own single-frame run (which spreads the frame over a larger
+    thread-block cluster, so the sums are added in another order: same decisions, poses equal to rounding)"""
     probs = [synth.pose_problem(100 + f, n=200 + 7 * f, stereo_frac=(f % 3) / 2) for f in range(64)]
     rs = po.PoseOptimization(probs)
     assert po.last_launches() == 1
@@ -68,7 +69,10 @@ def test_batch_of_frames(po):
         assert np.array_equal(rs[f]["outlier"], ref["outlier"]) and rs[f]["n_inliers"] == ref["n_inliers"]
         assert update_rel(rs[f]["pose"], ref["pose"], probs[f]["pose"]) < TOL
     one = po.PoseOptimization(probs[17])
-    assert np.array_equal(one["pose"], rs[17]["pose"]) and np.array_equal(one["outlier"], rs[17]["outlier"])
+    assert update_rel(one["pose"], rs[17]["pose"], probs[17]["pose"]) < 1e-9 and np.array_equal(one["outlier"], rs[17]["outlier"])
+    assert one["n_inliers"] == rs[17]["n_inliers"]
+    again = po.PoseOptimization(probs)
+    assert all(np.array_equal(a["pose"], b["pose"]) for a, b in zip(again, rs)), "the same batch twice must give the same bits"
 
 
 def test_capacity_is_an_error(po):

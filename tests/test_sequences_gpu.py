@@ -52,9 +52,13 @@ def pose_of(tx, ty, yaw):
     return T.astype(f32)
 
 
-@pytest.mark.parametrize("stereo,n_sub", [(False, 1), (True, 1), (False, 2), (True, 3)])
-def test_steps_match_the_oracle_chain(stereo, n_sub):
+@pytest.mark.parametrize("stereo,n_sub,pinned", [(False, 1, False), (True, 1, False), (False, 2, True), (True, 3, True)])
+def test_steps_match_the_oracle_chain(stereo, n_sub, pinned):
+    """pinned: the caller's output arrays are page-locked (results land there by DMA); otherwise ordinary numpy arrays (results go
+    through the handle's pinned block and are copied out in _step_end)"""
     from oracle import oracle_py as O
+    import torch
+    pin = (lambda shape, dtype: torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()) if pinned else None
     w, h, ns, steps = 640, 480, 3, 4
     K = synth.TUM1_K
     worlds = [synth.stereo_world(s) for s in range(2)]
@@ -78,7 +82,7 @@ def test_steps_match_the_oracle_chain(stereo, n_sub):
                 imgs.append(wd.render(tx, ty, yaw, right=True))
             # the pose the step is given = the motion-model prediction: the true pose off by ~5 mm / 0.1 deg
             poses.append(pose_of(tx + rng.normal(0, 0.005), ty + rng.normal(0, 0.005), yaw + np.deg2rad(rng.normal(0, 0.1))))
-        out = seq.step(np.stack(imgs), np.stack([p[:3] for p in poses]))
+        out = seq.step(np.stack(imgs), np.stack([p[:3] for p in poses]), seq.alloc_outputs(pin))
         per = 2 if stereo else 1
         for q in range(ns):
             kl, dl = oex[0](imgs[per * q])
