@@ -11,7 +11,8 @@
 //   partial block, CTA 0 adds the partials of a block in chunk order.  No atomics anywhere, so the sums are
 //   deterministic and every CTA takes the same Levenberg decision from the same numbers without a broadcast;
 //   the reduced camera system lives in CTA 0's shared memory in upper block-triangular layout and is factorised there
-//   (blocked 6x6 Cholesky, A = U^T U) without ever touching global memory.
+//   (blocked 6x6 Cholesky, A = U^T U, diagonal blocks kept as their inverses, right-hand side carried along) without ever
+//   touching global memory.
 // Used when the upper block triangle of H_schur fits shared memory (<= 36 free keyframes); larger windows take lba.cu.
 #include <cooperative_groups.h>
 #include "lba_common.cuh"
@@ -38,7 +39,6 @@ struct LfShared {
     double red[LF_SLOTS][LF_CTAS_WIDE][4];   // cluster reductions land in CTA 0's copy
     double tmp[32];
     double bc[4];                        // values gathered by thread 0 for the whole CTA
-    double invd[6];                      // 1 / diag(U_kk) of the current pivot block
     int ok;
 };
 
@@ -71,13 +71,22 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
     double *kfRt = dyn;                               // [n_kf][12]  R (row-major) and t of every keyframe
     double *hpp = kfRt + 12 * LF_MAX_KF;              // [np][27]    H_pp / b_p (used in CTA 0)
     double *hs = hpp + 27 * np;                       // [nblk][36] + [n]  the reduced system (used in CTA 0)
-    double *xp = hs + nblk * 36 + 2 * n;              // [n]   (hs is followed by b_schur [n] and 1/diag(U) [n])
+    double *xp = hs + nblk * 36 + 2 * n;              // [n]   (hs is followed by b_schur [n] and the block table of the solve, np (np + 1) bytes in [n] doubles)
     LfShared *sh0 = cl.map_shared_rank(&sh, 0);
     double *hs0 = cl.map_shared_rank(hs, 0), *xp0 = cl.map_shared_rank(xp, 0);
     const int total_warps = C * LF_WARPS, gwarp = rank * LF_WARPS + warp;
 
     const int l0 = (int)((long long)D.n_pts * rank / C), l1 = (int)((long long)D.n_pts * (rank + 1) / C);
     int slot = 0;
+    if (rank == 0) {     // the blocks (i, j), i <= j, ordered by descending i: the trailing update of pivot k touches the first T (T + 1) / 2, T = np - 1 - k
+        uint16_t *ptab = reinterpret_cast<uint16_t *>(hs + nblk * 36 + n);
+        for (int pr = tid; pr < nblk; pr += LF_THREADS) {
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= pr) r++;
+            const int bi = np - 1 - r, bj = bi + (pr - r * (r + 1) / 2);
+            ptab[pr] = (uint16_t)(bi | (bj << 8));
+        }
+    }
 
     // residuals (+ optionally the quadratic form) of this CTA's landmarks; returns nothing, partial sums go to CTA 0
     auto linearize = [&](bool build) {
@@ -230,9 +239,11 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
             }
             __syncthreads();
             if (it == 0) {   // computeLambdaInit also looks at the pose diagonals
-                const int diag6[6] = {0, 6, 11, 15, 18, 20};
                 double mx = 0;
-                for (int i = tid; i < 6 * np; i += LF_THREADS) mx = fmax(mx, fabs(hpp[27 * (i / 6) + diag6[i % 6]]));
+                for (int i = tid; i < 6 * np; i += LF_THREADS) {
+                    const int a = i % 6;                                  // diagonal entry a of the packed upper triangle: 0, 6, 11, 15, 18, 20
+                    mx = fmax(mx, fabs(hpp[27 * (i / 6) + 6 * a - a * (a - 1) / 2]));
+                }
                 mx = block_max(mx, sh.tmp);
                 if (tid == 0) sh.red[slot][0][2] = mx;
             }
@@ -351,117 +362,147 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 cl.sync();
             }
             tick(2);
-            // ---- reduced solve in CTA 0: A = U^T U on the upper block triangle, then U^T y = b, U x = y -----------------
+            // ---- reduced solve in CTA 0: A = U^T U on the upper block triangle with the right-hand side carried along (U^T y = b comes
+            //      out of the factorisation), then U x = y.  A diagonal block is replaced by W_k = U_kk^-1 as soon as it is factorised, so
+            //      that everything after the 6x6 pivot is products, not triangular solves: U_kj = W_k^T A_kj and y_k = W_k^T b_k (one
+            //      thread per column), A_ij -= U_ki^T U_kj and b_j -= U_kj^T y_k (one thread per row of a block; the blocks (i, j) of a
+            //      step are a prefix of a table ordered by descending i, so no thread searches for its block), x_k = W_k y_k.
             if (rank == 0) {
+                double *bs = hs + nblk * 36;                                  // b_schur, then y, then x
+                uint16_t *ptab = reinterpret_cast<uint16_t *>(hs + nblk * 36 + n);   // [nblk] (i | j << 8), rows i = np - 1, np - 2, ...
                 if (tid == 0) sh.ok = 1;
                 __syncthreads();
                 for (int k = 0; k < np; k++) {
-                    double *Ukk = hs + upper_block(k, k, np) * 36;
+                    const int rowk = upper_block(k, k, np);
+                    double *Ukk = hs + rowk * 36;
                     if (warp == 0) {
-                        // 6x6 pivot block: lane b owns column b; 1/U_aa is kept so that every later solve multiplies
+                        // 6x6 pivot block: lane b owns column b of U
                         double c[6];
                         const int b = lane < 6 ? lane : 0;
 #pragma unroll
                         for (int a = 0; a < 6; a++) c[a] = Ukk[6 * a + b];
                         bool good = true;
+                        double isd[6];
 #pragma unroll
                         for (int a = 0; a < 6; a++) {
                             double v = c[a];
 #pragma unroll
-                            for (int m = 0; m < a; m++) v -= __shfl_sync(0xffffffffu, c[m], a) * c[m];
+                            for (int m = 0; m < 6; m++)
+                                if (m < a) v -= __shfl_sync(0xffffffffu, c[m], a) * c[m];
                             const double d = __shfl_sync(0xffffffffu, v, a);
                             if (!(d > 0)) good = false;
                             const double is = rsqrt(d);
+                            isd[a] = is;
                             c[a] = b == a ? d * is : v * is;           // U_aa = sqrt(d); U_ab = v / U_aa
-                            if (lane == a) sh.invd[a] = is;
+                        }
+                        // W = U^-1, lane b owns column b: w_b = 1 / U_bb, w_a = -(sum_{a < m <= b} U_am w_m) / U_aa; row a of U sits in
+                        // the lanes m > a as their c[a]
+                        double w[6];
+#pragma unroll
+                        for (int a = 5; a >= 0; a--) {
+                            double v = b == a ? 1.0 : 0.0;
+#pragma unroll
+                            for (int m = 5; m >= 0; m--)
+                                if (m > a) {
+                                    const double u_am = __shfl_sync(0xffffffffu, c[a], m);      // U[a][m]
+                                    v -= u_am * w[m];
+                                }
+                            w[a] = a <= b ? v * isd[a] : 0.0;
                         }
                         if (lane < 6) {
 #pragma unroll
-                            for (int a = 0; a < 6; a++) if (a <= b) Ukk[6 * a + b] = c[a];
+                            for (int a = 0; a < 6; a++) Ukk[6 * a + b] = w[a];
                         }
                         if (lane == 0 && !good) sh.ok = 0;
                     }
                     __syncthreads();
                     if (!sh.ok) break;
                     const int T = np - k - 1;
-                    for (int t = tid; t < T * 6; t += LF_THREADS) {        // U_kj = U_kk^-T A_kj, one thread per column
+                    for (int t = tid; t < T * 6 + 1; t += LF_THREADS) {    // U_kj = W^T A_kj column by column; the last item is y_k = W^T b_k
+                        const bool rhs = t == T * 6;
                         const int j = k + 1 + t / 6, b = t % 6;
-                        double *Akj = hs + upper_block(k, j, np) * 36;
-                        double y[6];
+                        double *col = rhs ? bs + 6 * k : hs + (rowk + (j - k)) * 36 + b;
+                        const int st = rhs ? 1 : 6;
+                        double o[6], y[6];
+#pragma unroll
+                        for (int a = 0; a < 6; a++) o[a] = col[st * a];
 #pragma unroll
                         for (int a = 0; a < 6; a++) {
-                            double v = Akj[6 * a + b];
+                            double v = 0;
 #pragma unroll
-                            for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * y[m];
-                            y[a] = v * sh.invd[a];
+                            for (int m = 0; m < 6; m++)
+                                if (m <= a) v += Ukk[6 * m + a] * o[m];
+                            y[a] = v;
                         }
 #pragma unroll
-                        for (int a = 0; a < 6; a++) Akj[6 * a + b] = y[a];
+                        for (int a = 0; a < 6; a++) col[st * a] = y[a];
                     }
-                    if (tid < 6) hs[nblk * 36 + n + 6 * k + tid] = sh.invd[tid];   // 1/diag(U) for the triangular solves
                     __syncthreads();
-                    const int npair = T * (T + 1) / 2;                       // A_ij -= U_ki^T U_kj for k < i <= j
-                    for (int t = tid; t < npair * 36; t += LF_THREADS) {
-                        const int pr = t / 36, ab = t - 36 * pr, a = ab / 6, b = ab - 6 * a;
-                        int i = 0, rem = pr;
-                        while (rem >= T - i) { rem -= T - i; i++; }
-                        const int bi = k + 1 + i, bj = bi + rem;
-                        const double *Uki = hs + upper_block(k, bi, np) * 36, *Ukj = hs + upper_block(k, bj, np) * 36;
-                        double v = 0;
+                    const int npair = T * (T + 1) / 2, nit = npair * 6 + T;  // A_ij -= U_ki^T U_kj (row a of a block per item); b_j -= U_kj^T y_k
+                    for (int t = tid; t < nit; t += LF_THREADS) {
+                        if (t < npair * 6) {
+                            const int pr = t / 6, a = t - 6 * pr;
+                            const unsigned e = ptab[pr];
+                            const int bi = e & 0xff, bj = e >> 8;
+                            const double *Uki = hs + (rowk + (bi - k)) * 36 + a, *Ukj = hs + (rowk + (bj - k)) * 36;
+                            double *out = hs + upper_block(bi, bj, np) * 36 + 6 * a;
+                            double u[6], v[6];
 #pragma unroll
-                        for (int m = 0; m < 6; m++) v += Uki[6 * m + a] * Ukj[6 * m + b];
-                        hs[upper_block(bi, bj, np) * 36 + ab] -= v;
+                            for (int m = 0; m < 6; m++) u[m] = Uki[6 * m];
+#pragma unroll
+                            for (int c2 = 0; c2 < 6; c2++) v[c2] = out[c2];
+#pragma unroll
+                            for (int m = 0; m < 6; m++)
+#pragma unroll
+                                for (int c2 = 0; c2 < 6; c2++) v[c2] -= u[m] * Ukj[6 * m + c2];
+#pragma unroll
+                            for (int c2 = 0; c2 < 6; c2++) out[c2] = v[c2];
+                        } else {
+                            const int j = k + 1 + (t - npair * 6);
+                            const double *Ukj = hs + (rowk + (j - k)) * 36;
+                            double v[6];
+#pragma unroll
+                            for (int c2 = 0; c2 < 6; c2++) v[c2] = bs[6 * j + c2];
+#pragma unroll
+                            for (int m = 0; m < 6; m++)
+#pragma unroll
+                                for (int c2 = 0; c2 < 6; c2++) v[c2] -= Ukj[6 * m + c2] * bs[6 * k + m];
+#pragma unroll
+                            for (int c2 = 0; c2 < 6; c2++) bs[6 * j + c2] = v[c2];
+                        }
                     }
                     __syncthreads();
                 }
                 if (sh.ok) {
-                    if (warp == 0) {
-                        double *b = hs + nblk * 36;
-                        const double *invd = hs + nblk * 36 + n;
-                        for (int k = 0; k < np; k++) {                      // forward: U^T y = b
-                            const double *Ukk = hs + upper_block(k, k, np) * 36;
-                            if (lane == 0) {
+                    for (int k = np - 1; k >= 0; k--) {                      // backward: x_k = W_k y_k, then y_i -= U_ik x_k for i < k
+                        const double *Wk = hs + upper_block(k, k, np) * 36;
+                        double xk[6];
 #pragma unroll
-                                for (int a = 0; a < 6; a++) {
-                                    double v = b[6 * k + a];
-                                    for (int m = 0; m < a; m++) v -= Ukk[6 * m + a] * b[6 * k + m];
-                                    b[6 * k + a] = v * invd[6 * k + a];
-                                }
-                            }
-                            __syncwarp();
-                            for (int t = lane; t < (np - k - 1) * 6; t += 32) {
-                                const int j = k + 1 + t / 6, c = t % 6;
-                                const double *Ukj = hs + upper_block(k, j, np) * 36;
-                                double v = 0;
+                        for (int a = 0; a < 6; a++) {                          // every thread: 21 products from shared memory, no barrier for x_k
+                            double v = 0;
 #pragma unroll
-                                for (int a = 0; a < 6; a++) v += Ukj[6 * a + c] * b[6 * k + a];
-                                b[6 * j + c] -= v;
-                            }
-                            __syncwarp();
+                            for (int m = 0; m < 6; m++)
+                                if (m >= a) v += Wk[6 * a + m] * bs[6 * k + m];
+                            xk[a] = v;
                         }
-                        for (int k = np - 1; k >= 0; k--) {                 // backward: U x = y
-                            const double *Ukk = hs + upper_block(k, k, np) * 36;
-                            if (lane == 0) {
+                        __syncthreads();                                       // everybody has read y_k
+                        if (tid < 6) {
+                            double mine = xk[0];                                // static indices only: xk stays in registers
 #pragma unroll
-                                for (int a = 5; a >= 0; a--) {
-                                    double v = b[6 * k + a];
-                                    for (int m = a + 1; m < 6; m++) v -= Ukk[6 * a + m] * b[6 * k + m];
-                                    b[6 * k + a] = v * invd[6 * k + a];
-                                }
-                            }
-                            __syncwarp();
-                            for (int t = lane; t < k * 6; t += 32) {
-                                const int i = t / 6, a = t % 6;
-                                const double *Uik = hs + upper_block(i, k, np) * 36;
-                                double v = 0;
-#pragma unroll
-                                for (int c = 0; c < 6; c++) v += Uik[6 * a + c] * b[6 * k + c];
-                                b[6 * i + a] -= v;
-                            }
-                            __syncwarp();
+                            for (int a = 1; a < 6; a++) mine = tid == a ? xk[a] : mine;
+                            bs[6 * k + tid] = mine;
                         }
-                        for (int i = lane; i < n; i += 32) xp[i] = b[i];
+                        for (int t = tid; t < k * 6; t += LF_THREADS) {
+                            const int i = t / 6, a = t - 6 * i;
+                            const double *Uik = hs + (upper_block(i, i, np) + (k - i)) * 36 + 6 * a;
+                            double v = bs[6 * i + a];
+#pragma unroll
+                            for (int c2 = 0; c2 < 6; c2++) v -= Uik[c2] * xk[c2];
+                            bs[6 * i + a] = v;
+                        }
+                        __syncthreads();
                     }
+                    for (int i = tid; i < n; i += LF_THREADS) xp[i] = bs[i];
                 } else {
                     for (int i = tid; i < n; i += LF_THREADS) xp[i] = 0;     // failed factorisation: no step, the trial is rejected
                 }

@@ -280,20 +280,9 @@ k_pose_optimize(const PoseProbDev *__restrict__ probs, const double *__restrict_
     }
 }
 
-// ---- second form of the same optimisation: the latency chain shortened ---------------------------------------------------------
-// The kernel above leaves every decision to thread 0 and meets at ~9 barriers per Levenberg trial; a trial costs ~7.5 us, nearly all
-// of it waiting.  Here EVERY thread carries the pose, the 6x6 system and the Levenberg state in registers and repeats the (identical)
-// solve / exp-map / decision arithmetic, so a trial needs only the barriers of its reductions; the 28 sums of a pass are reduced by a
-// transposing butterfly (28 64-bit shuffles per warp instead of 140); the Cholesky keeps 1/L_jj from one rsqrt per column instead of a
-// sqrt and a division; and with FUSE the pass that evaluates a trial also builds the quadratic form at the trial pose, which IS the
-// next iteration's system when the trial is accepted (same observations, same pose, same robust weights), so an accepted iteration
-// makes one pass instead of two.  Same sums, same decisions; only the order of additions inside a reduction differs.
-struct Po2Shared {
-    double red[PO_WARPS][PO_NACC];
-    double sum[PO_NACC];
-    double red1[2][PO_WARPS];
-};
-
+// ---- the cluster form (the one that normally runs; the kernel above takes frames too large to stage in shared memory) -----------------
+// Shared pieces first: a transposing butterfly for the 28 sums of a pass (28 64-bit shuffles per warp instead of 140), the error of one
+// observation with the pose in registers, and the 6x6 solve.
 // every lane ends with ONE of the 28 warp totals: lane l holds total number po2_slot(l) (lanes with slot 28 hold padding)
 __device__ __forceinline__ double po2_bfly28(const double (&v)[PO_NACC], int lane) {
     double a[14], b[7], c[4], d[2];
@@ -349,78 +338,6 @@ __device__ __forceinline__ double po2_error(const double (&R)[12], const Po2Cam 
         er[2] = o[2] - (u - K.bf * invz);
     }
     return info * (er[0] * er[0] + er[1] * er[1] + er[2] * er[2]);
-}
-
-// one pass over the frame's observations at the pose in R: chi2 of every active edge is stored, the robust chi2 (and with BUILD the
-// quadratic form) is summed into out[0..28): H upper triangle 0..20, b 21..26, chi2 27.  Every thread returns with all of them.
-template <bool BUILD>
-__device__ __forceinline__ void po2_pass(Po2Shared &S, int &flip, const double (&R)[12], const Po2Cam &K, int n, const double *__restrict__ Xw,
-                                         const double *__restrict__ obs, const float *__restrict__ info_f, const uint8_t *__restrict__ outlier,
-                                         double *__restrict__ chi2, bool robust, double d_mono, double d_stereo, double (&out)[PO_NACC]) {
-    double acc[PO_NACC];
-#pragma unroll
-    for (int i = 0; i < PO_NACC; i++) acc[i] = 0;
-    for (int e = threadIdx.x; e < n; e += PO_THREADS) {
-        if (outlier[e]) continue;                          // level 1: not part of this round
-        const double *X = Xw + 3 * (size_t)e, *o = obs + 3 * (size_t)e;
-        const bool st = !(o[2] < 0);                      // mvuRight[i] < 0 -> monocular edge (Optimizer.cc:281)
-        const double info = (double)info_f[e];
-        double er[3], Xc[3];
-        const double c = po2_error(R, K, X, o, st, info, er, Xc);
-        chi2[e] = c;
-        double rho1 = 1.0, cr = c;
-        if (robust) {
-            const double d = st ? d_stereo : d_mono, dsqr = (double)(float)(d * d);   // RobustKernelHuber keeps dsqr in a float member
-            if (c > dsqr) { const double rs = rsqrt(c), sq = c * rs; cr = 2 * sq * d - dsqr; rho1 = d * rs; }
-        }
-        acc[27] += cr;
-        if (!BUILD) continue;
-        const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = K.fx, fy = K.fy, bf = K.bf;
-        double J[18];
-        J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
-        J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
-        if (st) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
-        else {
-#pragma unroll
-            for (int i = 12; i < 18; i++) J[i] = 0;
-        }
-        const double w = rho1 * info;
-        const double w0 = info * er[0] * rho1, w1 = info * er[1] * rho1, w2 = info * er[2] * rho1;
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int b = a; b < 6; b++) acc[k++] += w * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
-#pragma unroll
-        for (int a = 0; a < 6; a++) acc[21 + a] -= J[a] * w0 + J[6 + a] * w1 + J[12 + a] * w2;
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (BUILD) {
-        const double mine = po2_bfly28(acc, lane);
-        const int slot = po2_slot(lane);
-        if (slot < PO_NACC) S.red[w][slot] = mine;
-        __syncthreads();
-        if (threadIdx.x < PO_NACC) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < PO_WARPS; k++) s += S.red[k][threadIdx.x];
-            S.sum[threadIdx.x] = s;
-        }
-        __syncthreads();                                   // the next pass writes S.red only after its own loop: S.sum is read right here
-#pragma unroll
-        for (int i = 0; i < PO_NACC; i++) out[i] = S.sum[i];
-    } else {
-        double v = acc[27];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) S.red1[flip][w] = v;
-        __syncthreads();                                   // two buffers: the pass after the next one is two barriers away
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < PO_WARPS; k++) s += S.red1[flip][k];
-        out[27] = s;
-        flip ^= 1;
-    }
 }
 
 // (H + lambda I) x = b, H as its 21 upper-triangular entries; L L^T with 1 / L_jj kept from one rsqrt per column; 0 if not positive definite
@@ -484,154 +401,20 @@ __device__ __forceinline__ void po2_set_pose(const double (&T)[7], double (&R)[1
     R[9] = T[4]; R[10] = T[5]; R[11] = T[6];
 }
 
-template <bool FUSE>
-__global__ void __launch_bounds__(PO_THREADS, 1)
-k_pose_optimize2(const PoseProbDev *__restrict__ probs, const double *__restrict__ Xw_all, const double *__restrict__ obs_all,
-                 const float *__restrict__ info_all, uint8_t *__restrict__ outlier_all, double *__restrict__ chi2_all,
-                 PoseOutDev *__restrict__ out, int iterations) {
-    __shared__ Po2Shared S;
-    __shared__ PoseProbDev P;
-    const int tid = threadIdx.x;
-    if (tid == 0) P = probs[blockIdx.x];
-    __syncthreads();
-    const double *Xw = Xw_all + 3 * (size_t)P.off, *obs = obs_all + 3 * (size_t)P.off;
-    const float *info = info_all + P.off;
-    uint8_t *outlier = outlier_all + P.off;
-    double *chi2 = chi2_all + P.off;
-    const int n = P.n;
-    const Po2Cam K = {P.fx, P.fy, P.cx, P.cy, P.bf};
-    const double d_mono = (double)(float)sqrt(5.991), d_stereo = (double)(float)sqrt(7.815);   // const float deltaMono / deltaStereo
-    for (int e = tid; e < n; e += PO_THREADS) outlier[e] = 0;      // every thread only ever touches its own observations' flags
-    double T[7], R[12], sums[PO_NACC];
-#pragma unroll
-    for (int i = 0; i < 7; i++) T[i] = P.pose[i];
-    int n_bad = 0, trials = 0, flip = 0;
-    if (n >= 3) {                                                              // :355-356
-        bool robust = true;
-        for (int round = 0; round < 4; round++) {
-#pragma unroll
-            for (int i = 0; i < 7; i++) T[i] = P.pose[i];                      // setEstimate(mTcw), :366
-            po2_set_pose(T, R);
-            if (n - n_bad > 0) {                                               // otherwise "0 vertices to optimize"
-                // ---- OptimizationAlgorithmLevenberg, `iterations` iterations ----
-                double H[21], b[6], x[6], chiB = 0, lambda = 0, ni = 2;
-                int nbad_lm = 0;
-                bool have = false;                                             // H, b, chiB already hold the system at T
-                for (int it = 0; it < iterations; it++) {
-                    if (!FUSE || !have) {
-                        po2_pass<true>(S, flip, R, K, n, Xw, obs, info, outlier, chi2, robust, d_mono, d_stereo, sums);
-#pragma unroll
-                        for (int i = 0; i < 21; i++) H[i] = sums[i];
-#pragma unroll
-                        for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
-                        chiB = sums[27];
-                    }
-                    double currentChi = chiB;
-                    const double iniChi = chiB;
-                    if (it == 0) {
-                        const double mx = fmax(fmax(fmax(fabs(H[0]), fabs(H[6])), fmax(fabs(H[11]), fabs(H[15]))), fmax(fabs(H[18]), fabs(H[20])));
-                        lambda = 1e-5 * mx; ni = 2; nbad_lm = 0;
-                    }
-                    double rho = 0;
-                    int qmax = 0;
-                    bool accepted = false;
-                    do {
-                        double Tbak[7];
-#pragma unroll
-                        for (int i = 0; i < 7; i++) Tbak[i] = T[i];            // push
-                        const int ok = po2_solve6(H, b, lambda, x);
-                        if (!ok) {
-#pragma unroll
-                            for (int i = 0; i < 6; i++) x[i] = 0;
-                        } else { se3_oplus(T, x); po2_set_pose(T, R); }
-                        po2_pass<FUSE>(S, flip, R, K, n, Xw, obs, info, outlier, chi2, robust, d_mono, d_stereo, sums);
-                        double tempChi = sums[27];
-                        if (!ok) tempChi = DBL_MAX;
-                        double scale = 0;
-#pragma unroll
-                        for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
-                        scale += 1e-3;
-                        rho = (currentChi - tempChi) / scale;
-                        trials++;
-                        accepted = rho > 0 && isfinite(tempChi);
-                        if (accepted) {
-                            const double t = 2 * rho - 1;
-                            double alpha = 1. - t * t * t;
-                            alpha = fmin(alpha, 2. / 3.);
-                            lambda *= fmax(1. / 3., alpha);
-                            ni = 2;
-                            currentChi = tempChi;
-                        } else {
-                            lambda *= ni; ni *= 2;
-#pragma unroll
-                            for (int i = 0; i < 7; i++) T[i] = Tbak[i];        // pop
-                            po2_set_pose(T, R);
-                        }
-                        qmax++;
-                    } while (rho < 0 && qmax < 10);
-                    bool stop = false;
-                    if (qmax == 10 || rho == 0) stop = true;
-                    else {
-                        if ((iniChi - currentChi) * 1e3 < iniChi) nbad_lm++; else nbad_lm = 0;
-                        if (nbad_lm >= 3) stop = true;
-                    }
-                    if (stop) break;
-                    if (FUSE) {
-                        have = accepted;
-                        if (accepted) {                                        // the trial pass built the system at the pose that was kept
-#pragma unroll
-                            for (int i = 0; i < 21; i++) H[i] = sums[i];
-#pragma unroll
-                            for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
-                            chiB = sums[27];
-                        }
-                    }
-                }
-            }
-            // ---- classification, :371-417 ----
-            const float th_mono = 5.991f, th_stereo = 7.815f;
-            int cnt = 0;
-            for (int e = tid; e < n; e += PO_THREADS) {
-                const double *o = obs + 3 * (size_t)e;
-                const bool st = !(o[2] < 0);
-                double c = chi2[e];
-                if (outlier[e]) {                                             // left out of this round: e->computeError()
-                    double er[3], Xc[3];
-                    c = po2_error(R, K, Xw + 3 * (size_t)e, o, st, (double)info[e], er, Xc);
-                    chi2[e] = c;
-                }
-                const bool bad = (float)c > (st ? th_stereo : th_mono);
-                outlier[e] = bad ? 1 : 0;
-                cnt += bad ? 1 : 0;
-            }
-            n_bad = 0;
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if ((tid & 31) == 0) S.red1[flip][tid >> 5] = (double)cnt;
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < PO_WARPS; k++) n_bad += (int)S.red1[flip][k];
-            flip ^= 1;
-            if (round == 2) robust = false;                                   // setRobustKernel(0), :391, :416
-            if (n < 10) break;                                                // optimizer.edges().size() < 10, :419
-        }
-    }
-    if (tid == 0) {
-        PoseOutDev o;
-        for (int i = 0; i < 7; i++) o.pose[i] = T[i];
-        o.n_bad = n_bad; o.n_inliers = n >= 3 ? n - n_bad : 0; o.trials = trials; o.pad = 0;
-        out[blockIdx.x] = o;
-    }
-}
-
-// ---- third form: a thread-block cluster per frame ---------------------------------------------------------------------------------
-// ncu on the forms above (profiles/r2_af_pose.txt): one frame of 400 observations runs 59 Levenberg trials in 650 k cycles on ONE SM,
-// issue-active 26 %, no memory stalls worth naming -- the SM's FP64 pipe (64 lanes) is the resource: a pass over 400 observations is
-// ~3 k cycles of it and the serial solve / exp-map chain another ~4 k per trial, while 147 SMs idle.  Here a cluster of C CTAs (C = 8, 4,
-// 2 or 1, the largest that still gives every frame of the batch its own SMs) shares a frame: CTA r stages observations
-// [n r / C, n (r + 1) / C) in its shared memory once (nothing is read from global memory inside the Levenberg loop), every CTA runs the
-// pass over its share, the partial sums are exchanged through distributed shared memory (each CTA stores its 28 sums into every
-// peer's buffer, one cluster barrier) and added in rank order by everybody, so all CTAs take the same decisions from the same numbers
-// without a broadcast.  One warp per scheduler (128 threads) makes the redundant serial chain free: the FP64 lanes it uses would idle.
+// ---- a thread-block cluster per frame ------------------------------------------------------------------------------------------------
+// ncu on the one-block form (profiles/r2_af_pose.txt): one frame of 400 observations runs 59 Levenberg trials in 650 k cycles on ONE SM,
+// issue-active 26 %, no memory stalls worth naming; 82 k instructions per warp, all on one dependent f64 chain: a pass over the
+// observations (the SM's 64 FP64 lanes are the resource), then thread 0's solve / exp map / decision with everybody else at a barrier.
+// Here a cluster of C CTAs (C = 8, 4, 2 or 1: the largest that still gives every frame of the batch its own SMs and at least one
+// observation per thread) shares a frame: CTA r stages observations [n r / C, n (r + 1) / C) in its shared memory once (nothing is read
+// from global memory inside the Levenberg loop) and runs the passes over its share; the partial sums are exchanged through distributed
+// shared memory (each CTA stores its 28 sums into every peer's buffer, one cluster barrier) and added in rank order by everybody; and
+// EVERY thread carries the pose, the 6x6 system and the Levenberg state in registers and repeats the (identical) solve / exp map /
+// decision, so all CTAs take the same decisions from the same numbers without a broadcast and a trial needs only the barriers of its
+// reductions.  One warp per scheduler (128 threads) makes that redundancy free: the FP64 lanes it uses would idle.
+// Measured and dropped: building the next iteration's quadratic form inside the pass that evaluates a trial (one pass per accepted
+// iteration instead of two, but every rejected trial then pays the 28-sum exchange: 0.189 -> 0.200 ms at 400 observations / 58 trials,
+// 0.160 -> 0.151 ms at 1500 / 29, 0.367 -> 0.375 ms for 64 frames x 500; profiles/r2_ah_pose_ab.txt, kernels 4 / 5).
 #define P3_THREADS 128
 #define P3_WARPS (P3_THREADS / 32)
 #define P3_MAXC 8
@@ -743,7 +526,6 @@ __device__ __forceinline__ void po3_pass(Po3Shared &S, int &b28, int &b1, unsign
     }
 }
 
-template <bool FUSE>
 __global__ void __launch_bounds__(P3_THREADS, 1)
 k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict__ Xw_all, const double *__restrict__ obs_all,
                  const float *__restrict__ info_all, uint8_t *__restrict__ outlier_all, PoseOutDev *__restrict__ out, int iterations, int cap) {
@@ -788,16 +570,13 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
                 // ---- OptimizationAlgorithmLevenberg, `iterations` iterations ----
                 double H[21], b[6], x[6], chiB = 0, lambda = 0, ni = 2;
                 int nbad_lm = 0;
-                bool have = false;                                             // H, b, chiB already hold the system at T
                 for (int it = 0; it < iterations; it++) {
-                    if (!FUSE || !have) {
-                        po3_pass<true>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
+                    po3_pass<true>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
 #pragma unroll
-                        for (int i = 0; i < 21; i++) H[i] = sums[i];
+                    for (int i = 0; i < 21; i++) H[i] = sums[i];
 #pragma unroll
-                        for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
-                        chiB = sums[27];
-                    }
+                    for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
+                    chiB = sums[27];
                     double currentChi = chiB;
                     const double iniChi = chiB;
                     if (it == 0) {
@@ -806,7 +585,6 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
                     }
                     double rho = 0;
                     int qmax = 0;
-                    bool accepted = false;
                     do {
                         double Tbak[7];
 #pragma unroll
@@ -816,7 +594,7 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
 #pragma unroll
                             for (int i = 0; i < 6; i++) x[i] = 0;
                         } else { se3_oplus(T, x); po2_set_pose(T, R); }
-                        po3_pass<FUSE>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
+                        po3_pass<false>(S, b28, b1, rank, C, R, K, Q, robust, d_mono, d_stereo, sums);
                         double tempChi = sums[27];
                         if (!ok) tempChi = DBL_MAX;
                         double scale = 0;
@@ -825,8 +603,7 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
                         scale += 1e-3;
                         rho = (currentChi - tempChi) / scale;
                         trials++;
-                        accepted = rho > 0 && isfinite(tempChi);
-                        if (accepted) {
+                        if (rho > 0 && isfinite(tempChi)) {
                             const double t = 2 * rho - 1;
                             double alpha = 1. - t * t * t;
                             alpha = fmin(alpha, 2. / 3.);
@@ -848,16 +625,6 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
                         if (nbad_lm >= 3) stop = true;
                     }
                     if (stop) break;
-                    if (FUSE) {
-                        have = accepted;
-                        if (accepted) {                                        // the trial pass built the system at the pose that was kept
-#pragma unroll
-                            for (int i = 0; i < 21; i++) H[i] = sums[i];
-#pragma unroll
-                            for (int i = 0; i < 6; i++) b[i] = sums[21 + i];
-                            chiB = sums[27];
-                        }
-                    }
                 }
             }
             // ---- classification, :371-417 ----
@@ -904,40 +671,34 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
     po3_cluster_sync();                                                       // no CTA leaves while a peer may still store into its shared memory
 }
 
-// ORBX_POSE_KERNEL = 1: the first form, 2 / 3: the second (plain / fused trial pass), 4 / 5 (default): the cluster form (plain / fused).
-// n_max = upper bound of a frame's observations (the cluster form stages a frame's share in shared memory; larger frames take form 1)
+// ORBX_POSE_KERNEL = 1 forces the one-block form (A/B runs).  n_max = upper bound of a frame's observations: the cluster form stages a
+// frame's share in shared memory, larger frames take the one-block form.
 static cudaError_t po_launch(int n_frames, int n_max, cudaStream_t s, const PoseProbDev *probs, const double *Xw, const double *obs,
                              const float *info, uint8_t *outlier, double *chi2, PoseOutDev *out) {
-    static int which = -1;
-    if (which < 0) { const char *e = getenv("ORBX_POSE_KERNEL"); which = e ? atoi(e) : 5; }
+    static int one_block = -1;
+    if (one_block < 0) { const char *e = getenv("ORBX_POSE_KERNEL"); one_block = e && atoi(e) == 1; }
     int C = 1;
     while (C < P3_MAXC && n_frames * 2 * C <= 148) C *= 2;          // every frame of the batch keeps its own SMs
     while (C > 1 && n_max <= P3_THREADS * (C / 2)) C /= 2;             // no more CTAs than one observation per thread asks for
-    int cap = ((n_max + C - 1) / C + 1 + 31) & ~31;
-    int kind = which;
-    if (kind >= 4 && cap > P3_CAP_MAX) kind = 1;
-    if (kind == 1) k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
-    else if (kind == 2) k_pose_optimize2<false><<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
-    else if (kind == 3) k_pose_optimize2<true><<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
-    else {
-        static bool raised = false;
-        if (!raised) {
-            cudaError_t e = ORBX_RAISE_SMEM(k_pose_optimize3<false>);
-            if (e == cudaSuccess) e = ORBX_RAISE_SMEM(k_pose_optimize3<true>);
-            if (e != cudaSuccess) return e;
-            raised = true;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n_frames * C)); cfg.blockDim = dim3(P3_THREADS);
-        cfg.dynamicSmemBytes = (size_t)cap * 61 + 64; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (kind == 4) return cudaLaunchKernelEx(&cfg, k_pose_optimize3<false>, probs, Xw, obs, info, outlier, out, 10, cap);
-        return cudaLaunchKernelEx(&cfg, k_pose_optimize3<true>, probs, Xw, obs, info, outlier, out, 10, cap);
+    const int cap = ((n_max + C - 1) / C + 1 + 31) & ~31;
+    if (one_block || cap > P3_CAP_MAX) {
+        k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
+    static bool raised = false;
+    if (!raised) {
+        const cudaError_t e = ORBX_RAISE_SMEM(k_pose_optimize3);
+        if (e != cudaSuccess) return e;
+        raised = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_frames * C)); cfg.blockDim = dim3(P3_THREADS);
+    cfg.dynamicSmemBytes = (size_t)cap * 61 + 64; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_pose_optimize3, probs, Xw, obs, info, outlier, out, 10, cap);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------

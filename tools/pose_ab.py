@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the pose-optimisation kernels (ORBX_POSE_KERNEL = 1: first form, 2: register-resident state, 3: + fused trial pass) on the GPU:
+"""A/B of the pose-optimisation kernels (ORBX_POSE_KERNEL = 1: the one-block form, otherwise the cluster form) on the GPU:
 batch of 64 frames and a single frame through orbx_pose_optimize_host, outlier sets checked against the oracle.  Prints one JSON line
 per variant.  Usage: python tools/pose_ab.py            (spawns itself once per variant)"""
 import json
@@ -48,6 +48,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         one()
     else:
-        for k in ("1", "2", "4", "5"):
+        for k in ("1", "0"):
             env = dict(os.environ, ORBX_POSE_KERNEL=k)
             subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=env, check=False)
