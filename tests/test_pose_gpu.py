@@ -75,6 +75,14 @@ def test_batch_of_frames(po):
     assert all(np.array_equal(a["pose"], b["pose"]) for a, b in zip(again, rs)), "the same batch twice must give the same bits"
 
 
+def test_frame_too_large_to_stage_takes_the_one_block_form(po):
+    """more observations than a cluster of 8 CTAs can stage in shared memory (8 x 3072): the kernel that reads global memory runs"""
+    prob = synth.pose_problem(9, n=30000)
+    r, ref = po.PoseOptimization(prob), O.pose_optimize(prob)
+    assert np.array_equal(r["outlier"], ref["outlier"]) and r["n_inliers"] == ref["n_inliers"]
+    assert update_rel(r["pose"], ref["pose"], prob["pose"]) < TOL
+
+
 def test_capacity_is_an_error(po):
     from orbx._lib import OrbxError
     small = PoseOptimizer(max_observations=100, max_frames=2)
