@@ -22,6 +22,7 @@
 #include <vector>
 #include "orbx_internal.cuh"
 
+#include <chrono>
 #include "lba_common.cuh"
 
 // lba_chunk.cu
@@ -32,6 +33,11 @@ orbx_status orbx_lba_chunk_init();
 size_t orbx_lba_fused_smem(int np);
 bool orbx_lba_fused_fits(int n_kf, int np);
 orbx_status orbx_lba_fused_init();
+orbx_status orbx_lba_grid_init();
+bool orbx_lba_grid_available(int n_kf, int np);
+size_t orbx_lba_grid_scratch(int n_pts, int n_kf);
+orbx_status orbx_lba_grid_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture, double *cap_Hs,
+                                 double *cap_bs, double *cap_xp, double *out, double *slots, int max_pts, int max_kf, cudaStream_t s);
 orbx_status orbx_lba_fused_launch(const LbaDev &D, double *kf_bak, double *pt_bak, int iterations, int robust, int capture,
                                   double *cap_Hs, double *cap_bs, double *cap_xp, double *out, cudaStream_t s, int wide);
 
@@ -179,6 +185,8 @@ struct orbx_lba {
     double *h_kf, *h_pt, *h_chi; uint8_t *h_flag;   // pinned result staging of the asynchronous form
     double *d_hppart, *d_part, *d_dinv;
     size_t cap_hppart, cap_part;
+    double *d_slots;    // block-level partial sums of the whole-GPU kernel (lba_chunk.cu, k_lba_grid)
+    int use_grid;       // a single window (orbx_lba_solve_host) takes the whole-GPU kernel; ORBX_LBA_GRID=0 keeps it on the cluster kernel
 };
 
 extern "C" void orbx_lba_destroy(orbx_lba *h) {
@@ -189,7 +197,7 @@ extern "C" void orbx_lba_destroy(orbx_lba *h) {
     cudaFree(h->D.Hpp); cudaFree(h->D.Hll); cudaFree(h->D.Hs); cudaFree(h->D.bs); cudaFree(h->D.xp); cudaFree(h->D.xl);
     cudaFree(h->D.scal); cudaFree(h->d_kf_bak); cudaFree(h->d_pt_bak); cudaFree(h->d_flag); cudaFree(h->arena_d);
     if (h->arena_h) cudaFreeHost(h->arena_h);
-    cudaFree(h->d_hppart); cudaFree(h->d_part); cudaFree(h->d_dinv);
+    cudaFree(h->d_hppart); cudaFree(h->d_part); cudaFree(h->d_dinv); cudaFree(h->d_slots);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->h_kf) cudaFreeHost(h->h_kf);
     if (h->h_pt) cudaFreeHost(h->h_pt);
@@ -227,7 +235,8 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     h->arena_h = h->arena_d = nullptr; h->arena_cap = h->arena_used = 0;
     h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->stop = nullptr; h->launches = 0; h->loaded = 0;
     { const char *mk = getenv("ORBX_LBA_MULTIKERNEL"); h->use_fused = !(mk && mk[0] == '1'); }
-    h->d_hppart = h->d_part = h->d_dinv = nullptr;
+    h->d_hppart = h->d_part = h->d_dinv = h->d_slots = nullptr;
+    { const char *g = getenv("ORBX_LBA_GRID"); h->use_grid = !(g && g[0] == '0'); }
     h->pending = 0; h->h_kf = h->h_pt = h->h_chi = nullptr; h->h_flag = nullptr;
     h->cap_hppart = h->cap_part = 0;
     const size_t K = max_keyframes, L = max_points, E = max_edges, N = 6 * K;
@@ -248,6 +257,8 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     TRY(cudaMalloc((void **)&h->D.xp, sizeof(double) * N));
     TRY(cudaMalloc((void **)&h->D.xl, sizeof(double) * 3 * L));
     TRY(cudaMalloc((void **)&h->D.scal, sizeof(double) * 16));
+    TRY(cudaMalloc((void **)&h->d_slots, sizeof(double) * orbx_lba_grid_scratch(max_points, max_keyframes)));
+    TRY(cudaMemset(h->d_slots, 0, sizeof(double) * orbx_lba_grid_scratch(max_points, max_keyframes)));     // the arrival counters start at zero
     TRY(cudaMallocHost((void **)&h->h_scal, sizeof(double) * 16));
     TRY(cudaMallocHost((void **)&h->h_kf, sizeof(double) * 7 * K));
     TRY(cudaMallocHost((void **)&h->h_pt, sizeof(double) * 3 * L));
@@ -259,6 +270,7 @@ extern "C" orbx_status orbx_lba_create(orbx_lba **out, int max_keyframes, int ma
     TRY(ORBX_RAISE_SMEM(k_lba_solve));
     if (ce == cudaSuccess && orbx_lba_fused_init() != ORBX_OK) ce = cudaErrorUnknown;
     if (ce == cudaSuccess && orbx_lba_chunk_init() != ORBX_OK) ce = cudaErrorUnknown;
+    if (ce == cudaSuccess && orbx_lba_grid_init() != ORBX_OK) ce = cudaErrorUnknown;
 #undef TRY
     if (ce != cudaSuccess) {
         orbx_set_error("orbx_lba_create: %s", cudaGetErrorString(ce));
@@ -344,15 +356,23 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         kcount.assign(np + 1, 0);
         bcount.assign(nblk + 1, 0);
         for (int e = 0; e < E; e++) { const int p = kfidx[P->e_kf[e]]; if (p >= 0) kcount[p + 1]++; }
+        // every unordered pair of a landmark's edges once (a landmark has one edge per keyframe, so two different edges lie in different
+        // keyframes and the pair belongs to exactly one block of the upper triangle), and every edge with itself
         for (int l = 0; l < L; l++)
-            for (int i = start[l]; i < start[l + 1]; i++)
-                for (int j = start[l]; j < start[l + 1]; j++) {
-                    const int p1 = kfidx[P->e_kf[h->perm[i]]], p2 = kfidx[P->e_kf[h->perm[j]]];
-                    if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
-                    bcount[ub(p1, p2) + 1]++;
+            for (int i = start[l]; i < start[l + 1]; i++) {
+                const int p1 = kfidx[P->e_kf[h->perm[i]]];
+                if (p1 < 0) continue;
+                bcount[ub(p1, p1) + 1]++;
+                for (int j = i + 1; j < start[l + 1]; j++) {
+                    const int p2 = kfidx[P->e_kf[h->perm[j]]];
+                    if (p2 < 0 || p2 == p1) continue;
+                    bcount[(p1 < p2 ? ub(p1, p2) : ub(p2, p1)) + 1]++;
                 }
-        for (int p = 0; p < np; p++) { n_kchunks += (kcount[p + 1] + LBA_CHUNK - 1) / LBA_CHUNK; kcount[p + 1] += kcount[p]; }
-        for (int b = 0; b < nblk; b++) { n_pchunks += (bcount[b + 1] + LBA_CHUNK - 1) / LBA_CHUNK; bcount[b + 1] += bcount[b]; }
+            }
+        // every keyframe and every block gets at least one chunk (an empty one if it has no entries): the warp that owns a chunk also
+        // reports it done, and whoever completes a keyframe / block writes its sum (lba_chunk.cu)
+        for (int p = 0; p < np; p++) { n_kchunks += std::max(1, (kcount[p + 1] + LBA_CHUNK - 1) / LBA_CHUNK); kcount[p + 1] += kcount[p]; }
+        for (int b = 0; b < nblk; b++) { n_pchunks += std::max(1, (bcount[b + 1] + LBA_CHUNK - 1) / LBA_CHUNK); bcount[b + 1] += bcount[b]; }
         npairs = (size_t)bcount[nblk];
     }
     const size_t bytes = 8 * (size_t)(7 * K + 3 * L + 3 * E + E) + 4 * (size_t)(K + L + 1 + 2 * E) + E +
@@ -393,23 +413,30 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         int nc = 0;
         for (int p = 0; p < np; p++) {
             kfc[p] = nc;
+            if (kcount[p] == kcount[p + 1]) kchunk[nc++] = make_int4(p, kcount[p], 0, 0);
             for (int b = kcount[p]; b < kcount[p + 1]; b += LBA_CHUNK) kchunk[nc++] = make_int4(p, b, std::min(LBA_CHUNK, kcount[p + 1] - b), 0);
         }
         kfc[np] = nc;
         D.n_kchunks = nc;
         cur.assign(bcount.begin(), bcount.end() - 1);
-        for (int l = 0; l < L; l++)
-            for (int i = start[l]; i < start[l + 1]; i++)
-                for (int j = start[l]; j < start[l + 1]; j++) {
-                    const int p1 = kfidx[ekf[i]], p2 = kfidx[ekf[j]];
-                    if (p1 < 0 || p2 < 0 || p1 > p2 || (p1 == p2 && i != j)) continue;
-                    pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
+        for (int l = 0; l < L; l++)            // within a block the pairs come out in landmark order, whichever edge comes first
+            for (int i = start[l]; i < start[l + 1]; i++) {
+                const int p1 = kfidx[ekf[i]];
+                if (p1 < 0) continue;
+                pairs[cur[ub(p1, p1)]++] = make_int4(i, i, l, 0);
+                for (int j = i + 1; j < start[l + 1]; j++) {
+                    const int p2 = kfidx[ekf[j]];
+                    if (p2 < 0 || p2 == p1) continue;
+                    if (p1 < p2) pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
+                    else pairs[cur[ub(p2, p1)]++] = make_int4(j, i, l, 0);
                 }
+            }
         nc = 0;
         int blk = 0;
         for (int p1 = 0; p1 < np; p1++)
             for (int p2 = p1; p2 < np; p2++, blk++) {
                 blkc[blk] = nc;
+                if (bcount[blk] == bcount[blk + 1]) pchunk[nc++] = make_int4(blk, bcount[blk], 0, p1 == p2);
                 for (int b = bcount[blk]; b < bcount[blk + 1]; b += LBA_CHUNK)
                     pchunk[nc++] = make_int4(blk, b, std::min(LBA_CHUNK, bcount[blk + 1] - b), p1 == p2);
             }
@@ -482,8 +509,12 @@ static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lb
         const int capture = *first ? 1 : 0;
         const bool want = capture && (res->first_Hschur || res->first_bschur || res->first_xp);
         ORBX_CUDA(cudaMemsetAsync(D.scal + 4, 0, sizeof(double) * 2, h->stream));   // scal[6..11]: phase timers, cleared per solve
-        if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
-                                        D.scal + 4, h->stream, 1)))     // one window at a time: the 16-CTA cluster
+        if (h->use_grid && orbx_lba_grid_available(D.n_kf, D.np)) {     // one window at a time: the whole GPU
+            if ((st = orbx_lba_grid_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
+                                           D.scal + 4, h->d_slots, h->max_pts, h->max_kf, h->stream)))
+                return st;
+        } else if ((st = orbx_lba_fused_launch(D, h->d_kf_bak, h->d_pt_bak, iterations, robust, capture, want ? D.Hs : nullptr, D.bs, D.xp,
+                                               D.scal + 4, h->stream, 1)))     // the 16-CTA cluster
             return st;
         h->launches++;
         ORBX_CUDA(cudaMemcpyAsync(h->h_scal + 4, D.scal + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -561,11 +592,19 @@ static orbx_status lba_optimize(orbx_lba *h, int iterations, int robust, orbx_lb
 
 extern "C" orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *prob, int its1, int its2, orbx_lba_result *res) {
     if (!h || !prob || !res || !res->kf_pose || !res->pts || its1 < 0 || its2 < 0) return ORBX_ERR_INVALID;
+    if (h->pending) {
+        orbx_set_error("orbx_lba_solve_host: a window submitted with orbx_lba_solve_begin is still in flight on this handle");
+        return ORBX_ERR_INVALID;
+    }
     ORBX_CUDA(cudaSetDevice(h->device));
     h->launches = 0;
     res->lm_trials = 0; res->stopped = 0; res->first_lambda = 0;
-    orbx_status st = lba_load(h, prob);
+    static const bool trace = getenv("ORBX_LBA_TRACE") != nullptr;     // host-side timing of the call's stages to stderr
+    const auto t_0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count(); };
+    orbx_status st = lba_load(h, prob, h->use_grid != 0);      // short chunks: the whole GPU works on this window
     if (st) return st;
+    const double us_load = since(t_0);
     LbaDev &D = h->D;
     const int E = D.n_edges;
     ORBX_CUDA(cudaMemsetAsync(D.scal + 6, 0, sizeof(double) * 6, h->stream));
@@ -587,19 +626,22 @@ extern "C" orbx_status orbx_lba_solve_host(orbx_lba *h, const orbx_lba_problem *
     k_lba_classify<<<blocks_for(E), LBA_THREADS, 0, h->stream>>>(D, h->d_flag);        // vToErase, Optimizer.cc:709-735
     h->launches++;
     ORBX_CUDA(cudaGetLastError());
-    std::vector<double> chi(E);
-    std::vector<uint8_t> fl(E);
-    ORBX_CUDA(cudaMemcpyAsync(res->kf_pose, D.kf, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(cudaMemcpyAsync(res->pts, D.pt, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToHost, h->stream));
+    const double us_opt = since(t_0) - us_load;
+    // through the handle's pinned staging: a copy into the caller's (pageable) arrays would block the host once per array
+    ORBX_CUDA(cudaMemcpyAsync(h->h_kf, D.kf, sizeof(double) * 7 * D.n_kf, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(cudaMemcpyAsync(h->h_pt, D.pt, sizeof(double) * 3 * D.n_pts, cudaMemcpyDeviceToHost, h->stream));
     if (E) {
-        ORBX_CUDA(cudaMemcpyAsync(chi.data(), D.chi2, sizeof(double) * E, cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(cudaMemcpyAsync(fl.data(), h->d_flag, E, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_chi, D.chi2, sizeof(double) * E, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(cudaMemcpyAsync(h->h_flag, h->d_flag, E, cudaMemcpyDeviceToHost, h->stream));
     }
     ORBX_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(res->kf_pose, h->h_kf, sizeof(double) * 7 * D.n_kf);
+    memcpy(res->pts, h->h_pt, sizeof(double) * 3 * D.n_pts);
     for (int s = 0; s < E; s++) {
-        if (res->chi2) res->chi2[h->perm[s]] = chi[s];
-        if (res->erase) res->erase[h->perm[s]] = fl[s];
+        if (res->chi2) res->chi2[h->perm[s]] = h->h_chi[s];
+        if (res->erase) res->erase[h->perm[s]] = h->h_flag[s];
     }
+    if (trace) fprintf(stderr, "orbx_lba_solve_host: load %.0f us, optimize %.0f us, download %.0f us\n", us_load, us_opt, since(t_0) - us_load - us_opt);
     return ORBX_OK;
 }
 

@@ -16,6 +16,7 @@
 // Used when the upper block triangle of H_schur fits shared memory (<= 36 free keyframes); larger windows take lba.cu.
 #include <cooperative_groups.h>
 #include "lba_common.cuh"
+#include "lba_solve.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -78,15 +79,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
 
     const int l0 = (int)((long long)D.n_pts * rank / C), l1 = (int)((long long)D.n_pts * (rank + 1) / C);
     int slot = 0;
-    if (rank == 0) {     // the blocks (i, j), i <= j, ordered by descending i: the trailing update of pivot k touches the first T (T + 1) / 2, T = np - 1 - k
-        uint16_t *ptab = reinterpret_cast<uint16_t *>(hs + nblk * 36 + n);
-        for (int pr = tid; pr < nblk; pr += LF_THREADS) {
-            int r = 0;
-            while ((r + 1) * (r + 2) / 2 <= pr) r++;
-            const int bi = np - 1 - r, bj = bi + (pr - r * (r + 1) / 2);
-            ptab[pr] = (uint16_t)(bi | (bj << 8));
-        }
-    }
+    if (rank == 0) lba_solve_table<LF_THREADS>(hs, np);
 
     // residuals (+ optionally the quadratic form) of this CTA's landmarks; returns nothing, partial sums go to CTA 0
     auto linearize = [&](bool build) {
@@ -362,150 +355,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
                 cl.sync();
             }
             tick(2);
-            // ---- reduced solve in CTA 0: A = U^T U on the upper block triangle with the right-hand side carried along (U^T y = b comes
-            //      out of the factorisation), then U x = y.  A diagonal block is replaced by W_k = U_kk^-1 as soon as it is factorised, so
-            //      that everything after the 6x6 pivot is products, not triangular solves: U_kj = W_k^T A_kj and y_k = W_k^T b_k (one
-            //      thread per column), A_ij -= U_ki^T U_kj and b_j -= U_kj^T y_k (one thread per row of a block; the blocks (i, j) of a
-            //      step are a prefix of a table ordered by descending i, so no thread searches for its block), x_k = W_k y_k.
+            // ---- reduced solve in CTA 0 (lba_solve.cuh) ----------------------------------------------------------------------
             if (rank == 0) {
-                double *bs = hs + nblk * 36;                                  // b_schur, then y, then x
-                uint16_t *ptab = reinterpret_cast<uint16_t *>(hs + nblk * 36 + n);   // [nblk] (i | j << 8), rows i = np - 1, np - 2, ...
-                if (tid == 0) sh.ok = 1;
-                __syncthreads();
-                for (int k = 0; k < np; k++) {
-                    const int rowk = upper_block(k, k, np);
-                    double *Ukk = hs + rowk * 36;
-                    if (warp == 0) {
-                        // 6x6 pivot block: lane b owns column b of U
-                        double c[6];
-                        const int b = lane < 6 ? lane : 0;
-#pragma unroll
-                        for (int a = 0; a < 6; a++) c[a] = Ukk[6 * a + b];
-                        bool good = true;
-                        double isd[6];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) {
-                            double v = c[a];
-#pragma unroll
-                            for (int m = 0; m < 6; m++)
-                                if (m < a) v -= __shfl_sync(0xffffffffu, c[m], a) * c[m];
-                            const double d = __shfl_sync(0xffffffffu, v, a);
-                            if (!(d > 0)) good = false;
-                            const double is = rsqrt(d);
-                            isd[a] = is;
-                            c[a] = b == a ? d * is : v * is;           // U_aa = sqrt(d); U_ab = v / U_aa
-                        }
-                        // W = U^-1, lane b owns column b: w_b = 1 / U_bb, w_a = -(sum_{a < m <= b} U_am w_m) / U_aa; row a of U sits in
-                        // the lanes m > a as their c[a]
-                        double w[6];
-#pragma unroll
-                        for (int a = 5; a >= 0; a--) {
-                            double v = b == a ? 1.0 : 0.0;
-#pragma unroll
-                            for (int m = 5; m >= 0; m--)
-                                if (m > a) {
-                                    const double u_am = __shfl_sync(0xffffffffu, c[a], m);      // U[a][m]
-                                    v -= u_am * w[m];
-                                }
-                            w[a] = a <= b ? v * isd[a] : 0.0;
-                        }
-                        if (lane < 6) {
-#pragma unroll
-                            for (int a = 0; a < 6; a++) Ukk[6 * a + b] = w[a];
-                        }
-                        if (lane == 0 && !good) sh.ok = 0;
-                    }
-                    __syncthreads();
-                    if (!sh.ok) break;
-                    const int T = np - k - 1;
-                    for (int t = tid; t < T * 6 + 1; t += LF_THREADS) {    // U_kj = W^T A_kj column by column; the last item is y_k = W^T b_k
-                        const bool rhs = t == T * 6;
-                        const int j = k + 1 + t / 6, b = t % 6;
-                        double *col = rhs ? bs + 6 * k : hs + (rowk + (j - k)) * 36 + b;
-                        const int st = rhs ? 1 : 6;
-                        double o[6], y[6];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) o[a] = col[st * a];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) {
-                            double v = 0;
-#pragma unroll
-                            for (int m = 0; m < 6; m++)
-                                if (m <= a) v += Ukk[6 * m + a] * o[m];
-                            y[a] = v;
-                        }
-#pragma unroll
-                        for (int a = 0; a < 6; a++) col[st * a] = y[a];
-                    }
-                    __syncthreads();
-                    const int npair = T * (T + 1) / 2, nit = npair * 6 + T;  // A_ij -= U_ki^T U_kj (row a of a block per item); b_j -= U_kj^T y_k
-                    for (int t = tid; t < nit; t += LF_THREADS) {
-                        if (t < npair * 6) {
-                            const int pr = t / 6, a = t - 6 * pr;
-                            const unsigned e = ptab[pr];
-                            const int bi = e & 0xff, bj = e >> 8;
-                            const double *Uki = hs + (rowk + (bi - k)) * 36 + a, *Ukj = hs + (rowk + (bj - k)) * 36;
-                            double *out = hs + upper_block(bi, bj, np) * 36 + 6 * a;
-                            double u[6], v[6];
-#pragma unroll
-                            for (int m = 0; m < 6; m++) u[m] = Uki[6 * m];
-#pragma unroll
-                            for (int c2 = 0; c2 < 6; c2++) v[c2] = out[c2];
-#pragma unroll
-                            for (int m = 0; m < 6; m++)
-#pragma unroll
-                                for (int c2 = 0; c2 < 6; c2++) v[c2] -= u[m] * Ukj[6 * m + c2];
-#pragma unroll
-                            for (int c2 = 0; c2 < 6; c2++) out[c2] = v[c2];
-                        } else {
-                            const int j = k + 1 + (t - npair * 6);
-                            const double *Ukj = hs + (rowk + (j - k)) * 36;
-                            double v[6];
-#pragma unroll
-                            for (int c2 = 0; c2 < 6; c2++) v[c2] = bs[6 * j + c2];
-#pragma unroll
-                            for (int m = 0; m < 6; m++)
-#pragma unroll
-                                for (int c2 = 0; c2 < 6; c2++) v[c2] -= Ukj[6 * m + c2] * bs[6 * k + m];
-#pragma unroll
-                            for (int c2 = 0; c2 < 6; c2++) bs[6 * j + c2] = v[c2];
-                        }
-                    }
-                    __syncthreads();
-                }
-                if (sh.ok) {
-                    for (int k = np - 1; k >= 0; k--) {                      // backward: x_k = W_k y_k, then y_i -= U_ik x_k for i < k
-                        const double *Wk = hs + upper_block(k, k, np) * 36;
-                        double xk[6];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) {                          // every thread: 21 products from shared memory, no barrier for x_k
-                            double v = 0;
-#pragma unroll
-                            for (int m = 0; m < 6; m++)
-                                if (m >= a) v += Wk[6 * a + m] * bs[6 * k + m];
-                            xk[a] = v;
-                        }
-                        __syncthreads();                                       // everybody has read y_k
-                        if (tid < 6) {
-                            double mine = xk[0];                                // static indices only: xk stays in registers
-#pragma unroll
-                            for (int a = 1; a < 6; a++) mine = tid == a ? xk[a] : mine;
-                            bs[6 * k + tid] = mine;
-                        }
-                        for (int t = tid; t < k * 6; t += LF_THREADS) {
-                            const int i = t / 6, a = t - 6 * i;
-                            const double *Uik = hs + (upper_block(i, i, np) + (k - i)) * 36 + 6 * a;
-                            double v = bs[6 * i + a];
-#pragma unroll
-                            for (int c2 = 0; c2 < 6; c2++) v -= Uik[c2] * xk[c2];
-                            bs[6 * i + a] = v;
-                        }
-                        __syncthreads();
-                    }
-                    for (int i = tid; i < n; i += LF_THREADS) xp[i] = bs[i];
-                } else {
-                    for (int i = tid; i < n; i += LF_THREADS) xp[i] = 0;     // failed factorisation: no step, the trial is rejected
-                }
+                lba_reduced_solve<LF_THREADS>(hs, xp, np, &sh.ok);
                 __syncthreads();
                 if (tid == 0) sh.red[slot][0][2] = sh.ok ? 1.0 : 0.0;
             }

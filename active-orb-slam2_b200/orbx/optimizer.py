@@ -57,8 +57,9 @@ class Optimizer:
     __del__ = close
 
     def LocalBundleAdjustment(self, prob, its1=5, its2=10, want_system=False):
-        """-> dict(kf, pts, chi2, erase, trials, stopped[, Hschur, bschur, xp, lambda0])"""
-        P, keep = pack_problem(prob)
+        """-> dict(kf, pts, chi2, erase, trials, stopped[, Hschur, bschur, xp, lambda0]); prob: the problem dict, or what
+        pack_problem(prob) returned (a caller that times the C call packs once)"""
+        P, keep = prob if isinstance(prob, tuple) else pack_problem(prob)
         kf, pt = np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3))
         chi2, erase = np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8)
         R = LbaResult()
