@@ -174,6 +174,7 @@ struct orbx_lba {
     uint8_t *d_flag;
     uint8_t *arena_h, *arena_d; size_t arena_cap, arena_used;   // the window as uploaded (see lba_load)
     std::vector<int> v_start, v_kfidx, v_kcount, v_bcount, v_cur;
+    std::vector<int4> v_plist;
     double *h_scal;
     std::vector<int> perm;      // sorted position -> caller's edge index
     const volatile uint8_t *stop;
@@ -357,16 +358,23 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         bcount.assign(nblk + 1, 0);
         for (int e = 0; e < E; e++) { const int p = kfidx[P->e_kf[e]]; if (p >= 0) kcount[p + 1]++; }
         // every unordered pair of a landmark's edges once (a landmark has one edge per keyframe, so two different edges lie in different
-        // keyframes and the pair belongs to exactly one block of the upper triangle), and every edge with itself
+        // keyframes and the pair belongs to exactly one block of the upper triangle), and every edge with itself; the pairs are listed
+        // here with their block and scattered into block order below (a counting sort: within a block they stay in landmark order)
+        std::vector<int4> &plist = h->v_plist;
+        plist.clear();
         for (int l = 0; l < L; l++)
             for (int i = start[l]; i < start[l + 1]; i++) {
                 const int p1 = kfidx[P->e_kf[h->perm[i]]];
                 if (p1 < 0) continue;
-                bcount[ub(p1, p1) + 1]++;
+                int b = ub(p1, p1);
+                bcount[b + 1]++;
+                plist.push_back(make_int4(i, i, l, b));
                 for (int j = i + 1; j < start[l + 1]; j++) {
                     const int p2 = kfidx[P->e_kf[h->perm[j]]];
                     if (p2 < 0 || p2 == p1) continue;
-                    bcount[(p1 < p2 ? ub(p1, p2) : ub(p2, p1)) + 1]++;
+                    if (p1 < p2) { b = ub(p1, p2); plist.push_back(make_int4(i, j, l, b)); }
+                    else { b = ub(p2, p1); plist.push_back(make_int4(j, i, l, b)); }
+                    bcount[b + 1]++;
                 }
             }
         // every keyframe and every block gets at least one chunk (an empty one if it has no entries): the warp that owns a chunk also
@@ -419,18 +427,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         kfc[np] = nc;
         D.n_kchunks = nc;
         cur.assign(bcount.begin(), bcount.end() - 1);
-        for (int l = 0; l < L; l++)            // within a block the pairs come out in landmark order, whichever edge comes first
-            for (int i = start[l]; i < start[l + 1]; i++) {
-                const int p1 = kfidx[ekf[i]];
-                if (p1 < 0) continue;
-                pairs[cur[ub(p1, p1)]++] = make_int4(i, i, l, 0);
-                for (int j = i + 1; j < start[l + 1]; j++) {
-                    const int p2 = kfidx[ekf[j]];
-                    if (p2 < 0 || p2 == p1) continue;
-                    if (p1 < p2) pairs[cur[ub(p1, p2)]++] = make_int4(i, j, l, 0);
-                    else pairs[cur[ub(p2, p1)]++] = make_int4(j, i, l, 0);
-                }
-            }
+        for (const int4 &q : h->v_plist) pairs[cur[q.w]++] = make_int4(q.x, q.y, q.z, 0);
         nc = 0;
         int blk = 0;
         for (int p1 = 0; p1 < np; p1++)

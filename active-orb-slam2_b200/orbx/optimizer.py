@@ -74,6 +74,19 @@ class Optimizer:
             out.update(Hschur=Hs, bschur=bs, xp=xp, lambda0=R.first_lambda)
         return out
 
+    def prepare(self, prob):
+        """argument and result structs of orbx_lba_solve_host with their arrays, built once (a caller that times the C call alone)"""
+        P, keep = prob if isinstance(prob, tuple) else pack_problem(prob)
+        arrays = (np.zeros((P.n_kf, 7)), np.zeros((P.n_pts, 3)), np.zeros(max(P.n_edges, 1)), np.zeros(max(P.n_edges, 1), np.uint8))
+        R = LbaResult()
+        R.kf_pose, R.pts, R.chi2, R.erase = (a.ctypes.data for a in arrays)
+        return P, keep, R, arrays
+
+    def call(self, prepared, its1=5, its2=10):
+        """orbx_lba_solve_host on prepare()'s structs; the results stay in its arrays -> Levenberg trials"""
+        check(self._L.orbx_lba_solve_host(self._h, C.byref(prepared[0]), its1, its2, C.byref(prepared[2])))
+        return prepared[2].lm_trials
+
     def begin(self, prob, its1=5, its2=10):
         """asynchronous LocalBundleAdjustment: enqueue the whole window on this handle's stream and return.  prob: the problem dict,
         or the (struct, keepalive) pair pack_problem(prob) returned (a caller that submits the same arrays again packs once)"""

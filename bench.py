@@ -1129,25 +1129,29 @@ def main():
         prob = synth.lba_problem(0, n_kf=20, n_pts=3000, stereo=False, n_fixed=1)
         op = Optimizer(max_keyframes=32, max_points=4096, max_edges=20000, device=local_rank)
         from orbx.optimizer import pack_problem
-        packed = pack_problem(prob)                       # the argument struct of orbx_lba_solve_host, built once
-        op.LocalBundleAdjustment(packed)                  # warm-up
+        prepared = op.prepare(pack_problem(prob))         # the argument and result structs of orbx_lba_solve_host, built once
+        op.call(prepared)                                 # warm-up
         reps, trials = 10, 0
         t0 = time.perf_counter()
         for _ in range(reps):
-            r_ = op.LocalBundleAdjustment(packed)
-            trials += r_["trials"]
+            trials += op.call(prepared)                   # the C call alone
         lba_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            op.LocalBundleAdjustment(prob)
+        lba_mirror_s = time.perf_counter() - t0
         launches_lba = op.last_launches()
         lba_phase = op.phase_us()
         ms_build, _, _ = op.build_schur_timed(prob, 100.0, reps=50)
         lba = {"config": "C3: 20 keyframes (1 fixed), 3000 points, %d mono edges, optimize(5) + optimize(10)" % len(prob["e_kf"]),
                "lm_trials_per_s": trials / lba_s, "ms_per_window": 1e3 * lba_s / reps, "lm_trials_per_window": trials / reps,
                "schur_build_us": 1e3 * ms_build / 50, "kernel_launches_per_window": launches_lba,
-               "api": "orbx_lba_solve_host (host buffers in and out, synchronous)",
+               "api": "orbx_lba_solve_host (host buffers in and out, synchronous; the C call alone, argument structs built once)",
+               "ms_per_window_python_mirror": 1e3 * lba_mirror_s / reps,
                "device_us_per_window_by_phase": {k: round(v, 1) for k, v in lba_phase.items()},
-               "phase_note": "the cluster kernel's own timers over the window's 15 trials: quadratic form, Schur accumulation, block finalisation, "
-                             "reduced solve (one CTA), update, trial residuals; the rest of ms_per_window is the host's list building, one upload, "
-                             "two launches and the download",
+               "phase_note": "the whole-GPU kernel's own timers over the window's 15 trials: first quadratic form, Schur accumulation, collecting the "
+                             "reduced system, reduced solve (one CTA), update, residuals + quadratic form at the trial state; the rest of "
+                             "ms_per_window is the host's list building, one upload, two cooperative launches and the download",
                "schur_build": "residuals + Jacobians + quadratic form + Schur complement of one Levenberg trial, device time (CUDA events)"}
         # one Levenberg trial's system build moves ~2.59 MB (inputs + Hschur + bschur + D^-1 + Hpl + b_l) and does ~14 MFLOP (f64)
         pk, pk_src = peaks()
