@@ -175,6 +175,7 @@ struct orbx_lba {
     uint8_t *arena_h, *arena_d; size_t arena_cap, arena_used;   // the window as uploaded (see lba_load)
     std::vector<int> v_start, v_kfidx, v_kcount, v_bcount, v_cur;
     std::vector<int4> v_plist;
+    std::vector<int> v_kp;
     double *h_scal;
     std::vector<int> perm;      // sorted position -> caller's edge index
     const volatile uint8_t *stop;
@@ -361,16 +362,20 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         // keyframes and the pair belongs to exactly one block of the upper triangle), and every edge with itself; the pairs are listed
         // here with their block and scattered into block order below (a counting sort: within a block they stay in landmark order)
         std::vector<int4> &plist = h->v_plist;
+        std::vector<int> &kp = h->v_kp;                  // reduced keyframe index of every edge in landmark order
         plist.clear();
+        plist.reserve((size_t)E * 4);
+        kp.resize(E);
+        for (int s = 0; s < E; s++) kp[s] = kfidx[P->e_kf[h->perm[s]]];
         for (int l = 0; l < L; l++)
             for (int i = start[l]; i < start[l + 1]; i++) {
-                const int p1 = kfidx[P->e_kf[h->perm[i]]];
+                const int p1 = kp[i];
                 if (p1 < 0) continue;
                 int b = ub(p1, p1);
                 bcount[b + 1]++;
                 plist.push_back(make_int4(i, i, l, b));
                 for (int j = i + 1; j < start[l + 1]; j++) {
-                    const int p2 = kfidx[P->e_kf[h->perm[j]]];
+                    const int p2 = kp[j];
                     if (p2 < 0 || p2 == p1) continue;
                     if (p1 < p2) { b = ub(p1, p2); plist.push_back(make_int4(i, j, l, b)); }
                     else { b = ub(p2, p1); plist.push_back(make_int4(j, i, l, b)); }

@@ -50,6 +50,28 @@ def test_c3_config(opt, stereo, n_fixed):
     assert ref["erase"].sum() > 100 and got["trials"] >= 10
 
 
+@pytest.mark.parametrize("stereo", [False, True])
+def test_single_window_on_the_cluster_kernel(stereo, monkeypatch):
+    """orbx_lba_solve_host normally gives a single window the whole GPU (the cooperative kernel); ORBX_LBA_GRID=0 at handle creation
+    keeps it on the 16-CTA cluster kernel, the path a deployment picks when other threads' kernels must not wait for the window"""
+    monkeypatch.setenv("ORBX_LBA_GRID", "0")
+    o = Optimizer(max_keyframes=40, max_points=4000, max_edges=20000)
+    monkeypatch.delenv("ORBX_LBA_GRID")
+    p = synth.lba_problem(3, n_kf=20, n_pts=3000, stereo=stereo, n_fixed=1)
+    ref, got = check_against_oracle(o, p)
+    assert got["trials"] >= 10
+    both = opt_result_pair(o, p)
+    assert rel(both[0]["pts"] - p["pts"], both[1]["pts"] - p["pts"]) < 1e-6      # cluster kernel against whole-GPU kernel: summation order only
+    o.close()
+
+
+def opt_result_pair(o_cluster, p):
+    o_grid = Optimizer(max_keyframes=40, max_points=4000, max_edges=20000)
+    r = (o_cluster.LocalBundleAdjustment(p), o_grid.LocalBundleAdjustment(p))
+    o_grid.close()
+    return r
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_small_and_mixed(opt, seed):
     p = synth.lba_problem(10 + seed, n_kf=4 + seed, n_pts=80 + 40 * seed, obs_per_pt=2 + seed % 3, n_fixed=1)
