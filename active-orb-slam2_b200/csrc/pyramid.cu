@@ -14,14 +14,17 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i >= n ? 2 * n - 2 - i : i;
 }
 
-// level 0: copy with reflection from the caller's image
-__global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t *__restrict__ src, size_t frame_pitch, int stride,
-                                                    uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel L) {
-    const int gx = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int py = blockIdx.y;
-    if (gx >= L.pitch) return;
-    const uint8_t *img = src + (size_t)blockIdx.z * frame_pitch;
-    uint8_t *dst = pyr + (size_t)blockIdx.z * pyr_frame + L.off + (size_t)py * L.pitch + gx;
+// level 0: copy with reflection from the caller's image.  One item = 16 consecutive bytes of one padded row (one 128-bit store).
+// The first two and the last three items of a row touch the reflected border and assemble their bytes one by one (~300 instructions);
+// the others are five aligned loads and four funnel shifts.  With a warp over consecutive items of a row every warp contained border
+// items and paid for both paths (406 instructions per warp, ncu r2_ab); so a block takes L0_ROWS rows, its first warps take the interior
+// items and ONE warp takes all the border items of those rows.
+#define L0_ROWS 6
+#define L0_EDGE_ITEMS 5                      // per row: items 0, 1 and the last three
+__device__ __forceinline__ void pyr_level0_item(const uint8_t *__restrict__ img, int stride, uint8_t *__restrict__ lvl, const OrbxLevel &L, int py,
+                                                int item) {
+    const int gx = item * 16;
+    uint8_t *dst = lvl + (size_t)py * L.pitch + gx;
     const int iy = reflect101(py - ORBX_EDGE, L.h);
     const uint8_t *row = img + (size_t)iy * stride;
     uint32_t w[4];
@@ -50,6 +53,29 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t *__restrict__ 
         w[q] = v;
     }
     *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// grid (row groups, 1, frames); block = (interior warps + 1) x 32 threads
+__global__ void __launch_bounds__(1024) k_pyr_level0(const uint8_t *__restrict__ src, size_t frame_pitch, int stride,
+                                                     uint8_t *__restrict__ pyr, size_t pyr_frame, OrbxLevel L) {
+    const int n_items = L.pitch / 16, n_mid = n_items - L0_EDGE_ITEMS;          // items per row, interior items per row
+    const int row0 = blockIdx.x * L0_ROWS;
+    const uint8_t *img = src + (size_t)blockIdx.z * frame_pitch;
+    uint8_t *lvl = pyr + (size_t)blockIdx.z * pyr_frame + L.off;
+    const int edge_warp = blockDim.x / 32 - 1, warp = threadIdx.x >> 5;
+    if (warp < edge_warp) {
+        for (int t = threadIdx.x; t < L0_ROWS * n_mid; t += edge_warp * 32) {
+            const int r = t / n_mid, py = row0 + r;
+            if (py < L.ph) pyr_level0_item(img, stride, lvl, L, py, 2 + (t - r * n_mid));
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        if (lane < L0_ROWS * L0_EDGE_ITEMS) {
+            const int r = lane / L0_EDGE_ITEMS, k = lane - r * L0_EDGE_ITEMS, py = row0 + r;
+            const int item = k < 2 ? k : n_items - L0_EDGE_ITEMS + k;
+            if (py < L.ph && item < n_items && (k < 2 || item >= 2)) pyr_level0_item(img, stride, lvl, L, py, item);
+        }
+    }
 }
 
 // OpenCV's fixed-point bilinear for one pixel: t0 / t1 hold the two horizontal neighbours of the upper / lower source row
@@ -158,8 +184,12 @@ orbx_status orbx_launch_pyramid(orbx_extractor *e, const uint8_t *d_images, size
     for (int l = 0; l < e->nlevels && l < tail; l++) {
         const OrbxLevel &L = e->lv[l];
         if (l == 0) {
-            dim3 block(64);
-            dim3 grid((L.pitch / 16 + block.x - 1) / block.x, L.ph, batch);
+            // interior warps for L0_ROWS rows of (items - 5) interior items each, plus the warp of the border items
+            const int n_mid = L.pitch / 16 - L0_EDGE_ITEMS;
+            int warps = (L0_ROWS * (n_mid > 0 ? n_mid : 0) + 31) / 32;
+            warps = warps < 1 ? 1 : (warps > 31 ? 31 : warps);
+            dim3 block((warps + 1) * 32);
+            dim3 grid((L.ph + L0_ROWS - 1) / L0_ROWS, 1, batch);
             k_pyr_level0<<<grid, block, 0, s>>>(d_images, frame_pitch, stride, e->d_pyr, e->pyr_frame_cap, L);
         } else {
             const int cols16 = L.pitch / 16, total = cols16 * L.ph;
