@@ -779,9 +779,10 @@ def cpu_c5(seconds_budget, threads, w=1241, h=376, nfeat=2000):
 
 
 def lba_host_threads():
-    """host threads that submit and collect LocalBA windows: the cores this rank is bound to, at most 8"""
+    """host threads that submit and collect LocalBA windows: 4 (the same at every N, so that the per-N numbers compare), fewer if this
+    rank is bound to fewer cores"""
     try:
-        return max(1, min(8, len(os.sched_getaffinity(0))))
+        return max(1, min(4, len(os.sched_getaffinity(0))))
     except Exception:                                    # noqa: BLE001
         return 1
 
