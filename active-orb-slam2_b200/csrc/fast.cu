@@ -164,17 +164,26 @@ k_fast(const uint8_t *__restrict__ pyr, size_t pyr_frame, const OrbxLevel *__res
                      ::"r"(smem_u32(tile)), "l"(tmap), "r"(gx0 - shift), "r"(ORBX_EDGE + (int)ck.y0), "r"(frame), "r"(mbar_a)
                      : "memory");
     }
-    for (int i = tid; i < (sp * (th - 6 + 2)) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(score)[i] = 0;
+    // the score plane starts at zero (16 bytes per store; the plane is 16-byte aligned and a multiple of 4 bytes long, the few bytes
+    // a rounded-up last store reaches into the survivor words behind it are written later)
+    for (int i = tid; i < (sp * (th - 6 + 2) + 15) >> 4; i += FAST_THREADS) reinterpret_cast<uint4 *>(score)[i] = make_uint4(0u, 0u, 0u, 0u);
     const int vw = tw - 6, vh = th - 6;                // detection region
     const int wcell = ck.wcell;
-    for (int x = tid; x < vw; x += FAST_THREADS) sh.cellof[x] = (uint8_t)(x / wcell);
+    {   // detection column -> cell: x / wcell by a 16.16 reciprocal (x < 256, wcell <= 255: exact), instead of an integer division
+        const uint32_t cmagic = (65536u + (uint32_t)wcell - 1u) / (uint32_t)wcell;
+        for (int x = tid; x < vw; x += FAST_THREADS) sh.cellof[x] = (uint8_t)(((uint32_t)x * cmagic) >> 16);
+    }
     if (tid < ORBX_FAST_CELLS) { sh.cnt[tid] = 0; sh.empty[tid] = 1; }
     if (tid == 0) { sh.n_out = 0; sh.any_empty = 0; sh.n_list = 0; }
     __syncthreads();
 
     // everything above overlapped the copy; now wait for the tile (phase 0 of the barrier)
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-                 ::"r"(mbar_a) : "memory");
+    // (one warp polls the barrier, the others sleep at the block barrier behind it: the polls of eight warps were 4 % of the kernel's
+    //  instructions)
+    if (warp == 0)
+        asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                     ::"r"(mbar_a) : "memory");
+    __syncthreads();
     const uint8_t *t0 = tile + shift + 3 * tp + 3;     // detection pixel (x,y) = t0[y*tp + x]
     uint8_t *s0 = score + sp;                          // score of detection pixel (x,y) = s0[y*sp + x]; rows -1 and vh stay zero
 
