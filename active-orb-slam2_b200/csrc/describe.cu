@@ -101,14 +101,18 @@ k_describe(const uint8_t *__restrict__ pyr, size_t pyr_frame, const uint8_t *__r
     const int au = u < 0 ? -u : u;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const uint8_t *col = center + u;
-        int colsum = 0;
+        // column u of the circular patch: rows +v and -v together (IC_Angle's own symmetry, ORBextractor.cc:80-102), two running row
+        // pointers instead of a 64-bit v * pitch per row: the sums are integers, so the order does not matter (half the instructions of
+        // the row-by-row loop, which was half of this kernel: profiles/r2_av_lines.txt)
+        const uint8_t *up = center + u, *dn = up;
+        int colsum = *up;                                  // v = 0: umax[0] = 15 covers every lane < 31
 #pragma unroll
-        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
-            if (au <= k_umax[v < 0 ? -v : v]) {
-                const int val = col[v * pitch];
-                colsum += val;
-                m01 += v * val;
+        for (int v = 1; v <= ORBX_HALF_PATCH; v++) {
+            up += pitch; dn -= pitch;
+            if (au <= k_umax[v]) {
+                const int a = *up, b = *dn;
+                colsum += a + b;
+                m01 += v * (a - b);
             }
         }
         m10 = u * colsum;
