@@ -194,10 +194,14 @@ static orbx_status build_geometry(const orbx_extractor *e, int w, int h, Geometr
             while (g.rxt.size() % 4) g.rxt.push_back(0);
             L.rx_off = (int)g.rxt.size();
             for (int px = 0; px < L.pitch; px++) {
-                int ix = px - ORBX_EDGE;
+                // the columns behind the padded image (up to the 16-byte pitch) are never looked at; they repeat the last real column, so
+                // that the group they share with real columns keeps its sources in one window (a zero entry sent every row's last
+                // group -- and with it the whole warp -- down the byte-by-byte path: 12 % of the kernel's instructions)
+                const int pc = px < L.w + 2 * ORBX_EDGE ? px : L.w + 2 * ORBX_EDGE - 1;
+                int ix = pc - ORBX_EDGE;
                 if (ix < 0) ix = -ix;
                 if (ix >= L.w) ix = 2 * L.w - 2 - ix;
-                g.rxt.push_back(px < L.w + 2 * ORBX_EDGE ? xe[ix] : 0u);
+                g.rxt.push_back(xe[ix]);
             }
             for (int px = 0; px < L.pitch; px += 4) {   // group flag: 4 columns whose sources lie in one 12-byte window
                 uint32_t *q = &g.rxt[L.rx_off + px];

@@ -80,10 +80,11 @@ __global__ void __launch_bounds__(1024) k_pyr_level0(const uint8_t *__restrict__
 
 // OpenCV's fixed-point bilinear for one pixel: t0 / t1 hold the two horizontal neighbours of the upper / lower source row
 // in their low 16 bits, coef = a0 | a1 << 16 (a0 + a1 = 2048).  The horizontal step a0*p[sx] + a1*p[sx+1] is one DP2A.
-__device__ __forceinline__ uint32_t resize_px(uint32_t coef, int b0, int b1, uint32_t t0, uint32_t t1) {
-    const int s0 = (int)__dp2a_lo(coef, t0, 0u);
-    const int s1 = (int)__dp2a_lo(coef, t1, 0u);
-    return (uint32_t)((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2);
+// b0s / b1s = the vertical coefficients shifted left by 16 (0 .. 2048 << 16), so that (b * (s >> 4)) >> 16 is one multiply-high
+__device__ __forceinline__ uint32_t resize_px(uint32_t coef, uint32_t b0s, uint32_t b1s, uint32_t t0, uint32_t t1) {
+    const uint32_t s0 = __dp2a_lo(coef, t0, 0u);
+    const uint32_t s1 = __dp2a_lo(coef, t1, 0u);
+    return (__umulhi(b0s, s0 >> 4) + __umulhi(b1s, s1 >> 4) + 2u) >> 2;
 }
 
 // level l >= 1 from the interior of level l-1.  One thread = 16 consecutive bytes of one padded output row (one 128-bit
@@ -98,7 +99,7 @@ __device__ __forceinline__ void pyr_resize_item(uint8_t *__restrict__ frame, con
     const uint8_t *sint = frame + S.off + (size_t)ORBX_EDGE * S.pitch + ORBX_EDGE;  // interior origin of the source
     const int2 yy = __ldg(ry + py);
     const int sy0 = yy.x & 0xffff, sy1 = yy.x >> 16;
-    const int b0 = (int)(short)(yy.y & 0xffff), b1 = yy.y >> 16;
+    const uint32_t b0 = (uint32_t)(yy.y & 0xffff) << 16, b1 = (uint32_t)(yy.y >> 16) << 16;       // 0 .. 2048, pre-shifted for resize_px
     const uint8_t *r0 = sint + (size_t)sy0 * S.pitch;
     const ptrdiff_t r10 = ((ptrdiff_t)sy1 - sy0) * S.pitch;      // lower source row relative to the upper one (multiple of 16)
     uint32_t out[4];
