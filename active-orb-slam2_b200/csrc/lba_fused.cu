@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lba_fused(LfParams P) {
     const int l0 = (int)((long long)D.n_pts * rank / C), l1 = (int)((long long)D.n_pts * (rank + 1) / C);
     int slot = 0;
     if (rank == 0) lba_solve_table<LF_THREADS>(hs, np);
+    cl.sync();                       // every CTA of the cluster is running before anybody stores into CTA 0's shared memory
 
     // residuals (+ optionally the quadratic form) of this CTA's landmarks; returns nothing, partial sums go to CTA 0
     auto linearize = [&](bool build) {

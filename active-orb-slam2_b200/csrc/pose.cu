@@ -554,6 +554,7 @@ k_pose_optimize3(const PoseProbDev *__restrict__ probs, const double *__restrict
         for (int j = tid; j < Q.n; j += P3_THREADS) { sInfo[j] = info[j]; sOut[j] = 0; sChi[j] = 0; }
     }
     __syncthreads();
+    po3_cluster_sync();              // every CTA of the cluster is running before anybody stores into a peer's shared memory
     const Po2Cam K = {P.fx, P.fy, P.cx, P.cy, P.bf};
     const double d_mono = (double)(float)sqrt(5.991), d_stereo = (double)(float)sqrt(7.815);   // const float deltaMono / deltaStereo
     double T[7], R[12], sums[PO_NACC];
