@@ -334,6 +334,10 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         (P->n_edges && (!P->e_kf || !P->e_pt || !P->e_obs || !P->e_inv_sigma2 || !P->e_stereo)))
         return ORBX_ERR_INVALID;
     const int E = P->n_edges, L = P->n_pts, K = P->n_kf;
+    static const bool ltrace = getenv("ORBX_LBA_TRACE") != nullptr;
+    const auto lt0 = std::chrono::steady_clock::now();
+    auto lsince = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - lt0).count(); };
+    double lt[6] = {0, 0, 0, 0, 0, 0};
     for (int e = 0; e < E; e++)
         if (P->e_kf[e] < 0 || P->e_kf[e] >= K || P->e_pt[e] < 0 || P->e_pt[e] >= L) {
             orbx_set_error("edge %d refers to vertex (%d, %d) outside the problem", e, P->e_kf[e], P->e_pt[e]);
@@ -347,6 +351,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
     h->perm.assign(E, 0);
     cur.assign(start.begin(), start.end() - 1);
     for (int e = 0; e < E; e++) h->perm[cur[P->e_pt[e]]++] = e;       // stable: caller's order inside a landmark
+    lt[0] = lsince();                                   // validation + sort by landmark
     kfidx.assign(K, -1);
     int np = 0;
     for (int k = 0; k < K; k++) kfidx[k] = P->kf_fixed[k] ? -1 : np++;
@@ -388,6 +393,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         for (int b = 0; b < nblk; b++) { n_pchunks += std::max(1, (bcount[b + 1] + LBA_CHUNK - 1) / LBA_CHUNK); bcount[b + 1] += bcount[b]; }
         npairs = (size_t)bcount[nblk];
     }
+    lt[1] = lsince();                                   // + pair enumeration and counts
     const size_t bytes = 8 * (size_t)(7 * K + 3 * L + 3 * E + E) + 4 * (size_t)(K + L + 1 + 2 * E) + E +
                          16 * ((size_t)E + npairs + n_kchunks + n_pchunks) + 4 * (size_t)(np + 1 + nblk + 1) + 16 * 20;
     orbx_status st = arena_reserve(h, bytes);
@@ -413,6 +419,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         obs[3 * s] = P->e_obs[3 * e]; obs[3 * s + 1] = P->e_obs[3 * e + 1]; obs[3 * s + 2] = P->e_obs[3 * e + 2];
         info[s] = (double)P->e_inv_sigma2[e];
     }
+    lt[2] = lsince();                                   // + arena, estimates, edge arrays
     D.n_kchunks = D.n_pchunks = 0;
     if (true) {
         int4 *kfe = arena_take(h, E > 0 ? E : 1, &d_4); D.kfe = d_4;
@@ -448,6 +455,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
         if ((st = lba_grow(&h->d_part, &h->cap_part, 42 * ((size_t)D.n_pchunks + 1)))) return st;
         D.hppart = h->d_hppart; D.part = h->d_part; D.dinv = h->d_dinv;
     }
+    lt[3] = lsince();                                   // + work lists
     if (h->arena_used > h->arena_cap) {
         orbx_set_error("internal: arena sized %zu, used %zu", h->arena_cap, h->arena_used);
         return ORBX_ERR_NOMEM;
@@ -464,6 +472,7 @@ static orbx_status lba_load(orbx_lba *h, const orbx_lba_problem *P, bool wide = 
     D.d_mono = (double)(float)sqrt(5.991); D.d_stereo = (double)(float)sqrt(7.815);
     h->stop = P->stop_flag;
     h->loaded = 1;
+    if (ltrace) fprintf(stderr, "lba_load: sort %.0f, pairs %.0f, edge arrays %.0f, lists %.0f, enqueue %.0f us (cumulative), %zu bytes\n", lt[0], lt[1], lt[2], lt[3], lsince(), h->arena_used);
     return ORBX_OK;
 }
 
