@@ -1033,9 +1033,9 @@ extern "C" orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const
     ORBX_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
     if (n_jobs == 0) return ORBX_OK;
-    // a thread-block cluster per job: as many CTAs as the SMs allow (1, 2 or 4) share the candidate lists of one frame
+    // a thread-block cluster per job: as many CTAs as the SMs allow (1, 2, 4 or 8) share the candidate lists of one frame
     int csize = 1;
-    while (csize < 4 && 2 * csize * n_jobs <= m->sm_count) csize *= 2;
+    while (csize < 8 && 2 * csize * n_jobs <= m->sm_count) csize *= 2;      // up to the portable cluster size: a single frame gets 8 CTAs
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_jobs * csize));
     cfg.blockDim = dim3(M_THREADS);
