@@ -598,8 +598,11 @@ static int g_grid_ctas = -1;      // CTAs of the cooperative kernel (one per SM)
 size_t orbx_lba_fused_smem(int np);
 bool orbx_lba_fused_fits(int n_kf, int np);
 
-orbx_status orbx_lba_grid_init() {
-    if (g_grid_ctas >= 0) return ORBX_OK;
+orbx_status orbx_lba_grid_init() {           // called for every handle: the shared-memory limit of a kernel is a per-device attribute
+    if (g_grid_ctas >= 0) {
+        if (g_grid_ctas > 0) ORBX_CUDA(ORBX_RAISE_SMEM(k_lba_grid));
+        return ORBX_OK;
+    }
     g_grid_ctas = 0;
     int dev = 0, coop = 0, sms = 0;
     ORBX_CUDA(cudaGetDevice(&dev));

@@ -455,7 +455,8 @@ bool orbx_lba_fused_fits(int n_kf, int np) { return n_kf <= LF_MAX_KF && np >= 1
 static int g_wide_ok = -1;     // can this device co-schedule a 16-CTA cluster of this kernel?
 
 orbx_status orbx_lba_fused_init() {
-    ORBX_CUDA(ORBX_RAISE_SMEM(k_lba_fused));
+    ORBX_CUDA(ORBX_RAISE_SMEM(k_lba_fused));       // per-device attributes: set for every handle's device
+    if (g_wide_ok > 0) cudaFuncSetAttribute(k_lba_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (g_wide_ok < 0) {
         g_wide_ok = 0;
         if (cudaFuncSetAttribute(k_lba_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {

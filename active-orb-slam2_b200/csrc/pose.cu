@@ -686,11 +686,15 @@ static cudaError_t po_launch(int n_frames, int n_max, cudaStream_t s, const Pose
         k_pose_optimize<<<n_frames, PO_THREADS, 0, s>>>(probs, Xw, obs, info, outlier, chi2, out, 10);
         return cudaGetLastError();
     }
-    static bool raised = false;
-    if (!raised) {
-        const cudaError_t e = ORBX_RAISE_SMEM(k_pose_optimize3);
+    {   // the shared-memory limit of a kernel is a per-device attribute
+        static bool raised[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        raised = true;
+        if (dev < 0 || dev >= 64 || !raised[dev]) {
+            if ((e = ORBX_RAISE_SMEM(k_pose_optimize3)) != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) raised[dev] = true;
+        }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_frames * C)); cfg.blockDim = dim3(P3_THREADS);
