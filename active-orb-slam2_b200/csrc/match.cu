@@ -1035,7 +1035,10 @@ extern "C" orbx_status orbx_match_projection_frame_device(orbx_matcher *m, const
     if (n_jobs == 0) return ORBX_OK;
     // a thread-block cluster per job: as many CTAs as the SMs allow (1, 2, 4 or 8) share the candidate lists of one frame
     int csize = 1;
-    while (csize < 8 && 2 * csize * n_jobs <= m->sm_count) csize *= 2;      // up to the portable cluster size: a single frame gets 8 CTAs
+    // (8 only for a handful of frames, where the kernel is a latency chain on otherwise idle SMs: with 16 frames per launch and other
+    //  sub-batches' kernels next to it, 8 CTAs per frame cost the pipelined step 6 %)
+    const int cmax = n_jobs <= 4 ? 8 : 4;
+    while (csize < cmax && 2 * csize * n_jobs <= m->sm_count) csize *= 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_jobs * csize));
     cfg.blockDim = dim3(M_THREADS);
