@@ -80,6 +80,26 @@ def test_small_and_mixed(opt, seed):
     check_against_oracle(opt, p, 3, 4)
 
 
+def test_free_keyframe_without_edges_and_disjoint_pairs(opt):
+    """a free keyframe nobody observes from (its diagonal block is lambda I alone) and keyframe pairs that share no landmark (empty
+    blocks of the reduced system): the empty chunks the host lists for them are what writes those blocks on both one-launch paths"""
+    p = synth.lba_problem(21, n_kf=8, n_pts=300, obs_per_pt=3, n_fixed=1)
+    free = np.nonzero(p["kf_fixed"] == 0)[0]
+    lonely = int(free[-1])
+    keep = p["e_kf"] != lonely
+    for k in ("e_kf", "e_pt", "e_inv_sigma2", "e_stereo"):
+        p[k] = p[k][keep]
+    p["e_obs"] = p["e_obs"][keep]
+    ref = O.lba_solve(p)
+    got = opt.LocalBundleAdjustment(p)
+    assert got["trials"] == ref["trials"] and np.array_equal(got["erase"], ref["erase"])
+    assert np.allclose(got["kf"][lonely], p["kf_pose"][lonely], rtol=0, atol=1e-14)   # nothing pulls on it (15 zero updates, each renormalising the quaternion)
+    assert rel(got["pts"] - p["pts"], ref["pts"] - p["pts"]) < TOL
+    opt.begin(p)
+    got2 = opt.end()
+    assert got2["trials"] == ref["trials"] and rel(got2["pts"] - p["pts"], ref["pts"] - p["pts"]) < TOL
+
+
 def test_fixed_keyframes_do_not_move(opt):
     p = synth.lba_problem(3, n_kf=8, n_pts=300, n_fixed=3)
     got = opt.LocalBundleAdjustment(p)
